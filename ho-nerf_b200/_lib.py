@@ -1,0 +1,90 @@
+"""ctypes binding of libhonerf_b200.so (the C ABI declared in include/honerf_b200.h).
+
+There is no fallback: if the shared library is missing this module raises at import, and every
+compute entry point needs a CUDA device.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhonerf_b200.so")
+
+HN_MAX_LAYERS = 12
+HN_SIMT_FP32, HN_TC_TF32, HN_TC_BF16X3, HN_TC_BF16 = 0, 1, 2, 3
+HN_WS_SDF_ONLY, HN_WS_FWD, HN_WS_BWD = 0, 1, 2
+
+
+class hn_mlp_t(Structure):
+    _fields_ = [("n_layers", c_int32),
+                ("in_dim", c_int32 * HN_MAX_LAYERS),
+                ("out_dim", c_int32 * HN_MAX_LAYERS),
+                ("ld", c_int32 * HN_MAX_LAYERS),
+                ("W", c_void_p * HN_MAX_LAYERS),
+                ("b", c_void_p * HN_MAX_LAYERS)]
+
+
+class hn_mlp_grad_t(Structure):
+    _fields_ = [("dW", c_void_p * HN_MAX_LAYERS),
+                ("db", c_void_p * HN_MAX_LAYERS)]
+
+
+if not os.path.isfile(LIB_PATH):
+    raise ImportError(
+        "honerf_b200: %s is missing. Build it with `python ho-nerf_b200/build.py` (nvcc, sm_100a); "
+        "there is no CPU or PyTorch fallback." % LIB_PATH)
+
+lib = ctypes.CDLL(LIB_PATH)
+
+P = c_void_p
+_mlp_p = POINTER(hn_mlp_t)
+_grad_p = POINTER(hn_mlp_grad_t)
+
+# name -> (restype, argtypes).  Mirrors include/honerf_b200.h one to one.
+PROTOTYPES = {
+    "hn_last_error": (ctypes.c_char_p, []),
+    "hn_version": (c_int, []),
+    "hn_launch_count": (c_int64, []),
+    "hn_wn_pack": (c_int, [P, P, c_int, c_int, c_int, c_float, P, P]),
+    "hn_wn_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
+    "hn_sdf_obj_stash_floats": (c_int64, [c_int64]),
+    "hn_sdf_obj_ws_floats": (c_int64, [c_int64, c_int]),
+    "hn_sdf_obj_sdf": (c_int, [_mlp_p, P, c_int64, c_float, P, P, c_int64, c_int, P]),
+    "hn_sdf_obj_fwd": (c_int, [_mlp_p, P, c_int64, c_float, P, P, c_int64, P, P, c_int64, P, c_int64,
+                               c_int, P]),
+    "hn_sdf_obj_bwd": (c_int, [_mlp_p, c_int64, c_float, P, P, P, c_int64, P, P, _grad_p, P, c_int64,
+                               c_int, P]),
+    "hn_color_obj_stash_floats": (c_int64, [c_int64]),
+    "hn_color_obj_ws_floats": (c_int64, [c_int64, c_int]),
+    "hn_color_obj_fwd": (c_int, [_mlp_p, P, P, P, c_int64, P, c_int64, P, P, c_int64, c_int, P]),
+    "hn_color_obj_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, P, P, c_int64, P, _grad_p, P, c_int64,
+                                 c_int, P]),
+    "hn_ray_points": (c_int, [P, P, P, c_int64, c_int, P, P]),
+    "hn_mid_points": (c_int, [P, P, P, c_int64, c_int, c_float, P, P, P]),
+    "hn_up_sample": (c_int, [P, P, P, c_int64, c_int, c_int, c_float, P, P]),
+    "hn_inverse_cdf": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P]),
+    "hn_merge_sorted": (c_int, [P, c_int, P, c_int, c_int64, P, P, P, P, c_int64, P, P]),
+    "hn_sort_rows": (c_int, [P, c_int64, c_int, P, P, P]),
+    "hn_neus_composite_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "hn_neus_composite_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P,
+                                      P, P, P]),
+}
+
+for _name, (_res, _args) in PROTOTYPES.items():
+    _fn = getattr(lib, _name)          # AttributeError here == the .so is stale: rebuild
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class HonerfError(RuntimeError):
+    pass
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib.hn_last_error()
+        raise HonerfError("%s failed (%d): %s" % (what, status, msg.decode() if msg else "?"))
+
+
+def launch_count():
+    return int(lib.hn_launch_count())

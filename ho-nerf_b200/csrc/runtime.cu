@@ -1,0 +1,138 @@
+// Library runtime: error text, launch counter, device info, weight-norm pack/backward, column sums.
+#include <atomic>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "fields_common.cuh"
+
+namespace hn {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int sm_count() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            cached = 148;
+    }
+    return cached;
+}
+
+// ---- weight norm ---------------------------------------------------------------------------
+// one warp per output row
+__global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, int out_dim,
+                               int in_dim, int ld, float post_scale, float* __restrict__ W) {
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= out_dim) return;
+    const float* vr = v + (int64_t)row * in_dim;
+    float ss = 0.0f;
+    for (int k = lane; k < in_dim; k += 32) ss = fmaf(vr[k], vr[k], ss);
+    ss = warp_sum(ss);
+    float sc = post_scale * (g[row] / sqrtf(ss));
+    float* wr = W + (int64_t)row * ld;
+    for (int k = lane; k < ld; k += 32) wr[k] = k < in_dim ? vr[k] * sc : 0.0f;
+}
+
+__global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                              const float* __restrict__ dW, int out_dim, int in_dim, int ld,
+                              float post_scale, float* __restrict__ dv, float* __restrict__ dg) {
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (row >= out_dim) return;
+    const float* vr = v + (int64_t)row * in_dim;
+    const float* dr = dW + (int64_t)row * ld;
+    float ss = 0.0f, dot = 0.0f;
+    for (int k = lane; k < in_dim; k += 32) {
+        ss = fmaf(vr[k], vr[k], ss);
+        dot = fmaf(dr[k], vr[k], dot);
+    }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot) * post_scale;
+    float nrm = sqrtf(ss);
+    float gn = g[row] / nrm;
+    if (lane == 0) dg[row] = dot / nrm;
+    float coef = dot / ss;
+    float* dvr = dv + (int64_t)row * in_dim;
+    for (int k = lane; k < in_dim; k += 32) dvr[k] = gn * (post_scale * dr[k] - coef * vr[k]);
+}
+
+// ---- column sums -----------------------------------------------------------------------------
+// block = 32 columns x 8 row lanes; grid.y splits the rows
+__global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int cols,
+                              float scale, int64_t rows_per_block, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    int rl = threadIdx.x >> 5;
+    int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    int64_t r1 = min(rows, r0 + rows_per_block);
+    float acc = 0.0f;
+    if (c < cols)
+        for (int64_t r = r0 + rl; r < r1; r += 8) acc += X[r * ldx + c];
+    red[rl][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rl == 0 && c < cols) {
+        float t = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+        atomicAdd(&out[c], t * scale);
+    }
+}
+
+int launch_colsum(const float* X, int64_t ldx, int64_t rows, int cols, float scale, float* out,
+                  cudaStream_t stream) {
+    if (rows <= 0 || cols <= 0) return HN_OK;
+    int64_t rpb = 1024;
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, rpb));
+    colsum_kernel<<<grid, 256, 0, stream>>>(X, ldx, rows, cols, scale, rpb, out);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" {
+
+const char* hn_last_error(void) { return g_err; }
+int hn_version(void) { return 100; }
+int64_t hn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld, float post_scale,
+               float* W, hn_stream_t stream) {
+    HN_REQUIRE(v && g && W && out_dim > 0 && in_dim > 0 && ld >= in_dim, "hn_wn_pack: bad arguments");
+    wn_pack_kernel<<<(unsigned)ceil_div((int64_t)out_dim * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        v, g, out_dim, in_dim, ld, post_scale, W);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hn_wn_bwd(const float* v, const float* g, const float* dW, int out_dim, int in_dim, int ld,
+              float post_scale, float* dv, float* dg, hn_stream_t stream) {
+    HN_REQUIRE(v && g && dW && dv && dg && out_dim > 0 && in_dim > 0 && ld >= in_dim, "hn_wn_bwd: bad arguments");
+    wn_bwd_kernel<<<(unsigned)ceil_div((int64_t)out_dim * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        v, g, dW, out_dim, in_dim, ld, post_scale, dv, dg);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+"""Torch-facing operators over the C ABI: tensor plumbing (allocation, streams, autograd glue) only.
+All arithmetic happens in libhonerf_b200.so; nothing here falls back to PyTorch math."""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import HN_SIMT_FP32, HN_WS_BWD, HN_WS_SDF_ONLY, check, hn_mlp_grad_t, hn_mlp_t, lib
+
+_PRECISIONS = {"simt_fp32": _lib.HN_SIMT_FP32, "tc_tf32": _lib.HN_TC_TF32,
+               "tc_bf16x3": _lib.HN_TC_BF16X3, "tc_bf16": _lib.HN_TC_BF16}
+_default_precision = HN_SIMT_FP32
+
+
+def set_default_precision(name):
+    """'simt_fp32' (verification path) | 'tc_tf32' | 'tc_bf16x3' | 'tc_bf16'."""
+    global _default_precision
+    _default_precision = _PRECISIONS[name]
+
+
+def default_precision():
+    return _default_precision
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise _lib.HonerfError("%s: honerf_b200 has no CPU path; tensor is on %s" % (what, t.device))
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _round4(x):
+    return (x + 3) // 4 * 4
+
+
+# ------------------------------------------------------------------------------------------------
+# packed (weight-normalised) MLP parameters
+# ------------------------------------------------------------------------------------------------
+class PackedMLP:
+    """Effective weights of a stack of weight-normalised Linears, packed once per parameter
+    version by hn_wn_pack (the reference recomputes g*v/||v|| inside every Linear call)."""
+
+    def __init__(self, layers, post_scales):
+        # layers: list of (weight_g [out,1], weight_v [out,in], bias [out]) parameters
+        self.layers = layers
+        self.post_scales = list(post_scales)
+        self.dims = [(v.shape[1], v.shape[0]) for (_, v, _) in layers]
+        self.lds = [_round4(i) for (i, _) in self.dims]
+        self.offsets = []
+        off = 0
+        for (i, o), ld in zip(self.dims, self.lds):
+            self.offsets.append(off)
+            off += o * ld
+        self.total = off
+        self.W = None
+        self.bias = None
+        self.struct = None
+        self._key = None
+
+    def _version_key(self):
+        return tuple((p.data_ptr(), p._version) for layer in self.layers for p in layer)
+
+    def get(self):
+        key = self._version_key()
+        if key == self._key:
+            return self
+        dev = self.layers[0][1].device
+        _require_cuda(self.layers[0][1], "PackedMLP")
+        if self.W is None or self.W.device != dev:
+            self.W = torch.empty(self.total, device=dev, dtype=torch.float32)
+        st = hn_mlp_t()
+        st.n_layers = len(self.layers)
+        keep = []
+        for l, (g, v, b) in enumerate(self.layers):
+            gd, vd, bd = _f32c(g.detach()), _f32c(v.detach()), _f32c(b.detach())
+            keep.append((gd, vd, bd))
+            i, o = self.dims[l]
+            Wl = self.W[self.offsets[l]: self.offsets[l] + o * self.lds[l]]
+            check(lib.hn_wn_pack(_ptr(vd), _ptr(gd), o, i, self.lds[l], self.post_scales[l], _ptr(Wl),
+                                 _stream(vd)), "hn_wn_pack")
+            st.in_dim[l], st.out_dim[l], st.ld[l] = i, o, self.lds[l]
+            st.W[l] = Wl.data_ptr()
+            st.b[l] = bd.data_ptr()
+        self._keep = keep
+        self.struct = st
+        self._key = key
+        return self
+
+    def new_grad(self):
+        """Zeroed packed gradient buffers + the struct pointing at them."""
+        dev = self.W.device
+        dW = torch.zeros(self.total, device=dev, dtype=torch.float32)
+        db = [torch.zeros(o, device=dev, dtype=torch.float32) for (_, o) in self.dims]
+        gs = hn_mlp_grad_t()
+        for l in range(len(self.layers)):
+            gs.dW[l] = dW[self.offsets[l]:].data_ptr()
+            gs.db[l] = db[l].data_ptr()
+        return dW, db, gs
+
+    def unpack_grads(self, dW, db):
+        """(dg, dv, db) per layer from packed dW via hn_wn_bwd.  Returns a flat list in the order
+        of ``flat_params``."""
+        out = []
+        for l, (gd, vd, bd) in enumerate(self._keep):
+            i, o = self.dims[l]
+            dv = torch.empty_like(vd)
+            dg = torch.empty(o, 1, device=vd.device, dtype=torch.float32)
+            dWl = dW[self.offsets[l]: self.offsets[l] + o * self.lds[l]]
+            check(lib.hn_wn_bwd(_ptr(vd), _ptr(gd), _ptr(dWl), o, i, self.lds[l], self.post_scales[l],
+                                _ptr(dv), _ptr(dg), _stream(vd)), "hn_wn_bwd")
+            out += [dg, dv, db[l]]
+        return out
+
+    def flat_params(self):
+        return [p for layer in self.layers for p in layer]
+
+
+# ------------------------------------------------------------------------------------------------
+# object SDF field
+# ------------------------------------------------------------------------------------------------
+def sdf_obj_sdf_only(packed, pts, inv_scale=1.0, precision=None):
+    """SDFNetwork_OBJ.sdf under no_grad (utils/fields.py:330-331): [N,3] -> [N,1]."""
+    pts = _f32c(pts.detach())
+    _require_cuda(pts, "sdf_obj_sdf_only")
+    pk = packed.get()
+    n = pts.shape[0]
+    sdf = torch.empty(n, 1, device=pts.device, dtype=torch.float32)
+    if n == 0:
+        return sdf
+    wsf = lib.hn_sdf_obj_ws_floats(n, HN_WS_SDF_ONLY)
+    ws = torch.empty(wsf, device=pts.device, dtype=torch.float32)
+    check(lib.hn_sdf_obj_sdf(ctypes.byref(pk.struct), _ptr(pts), n, inv_scale, _ptr(sdf), _ptr(ws), wsf,
+                             _default_precision if precision is None else precision, _stream(pts)),
+          "hn_sdf_obj_sdf")
+    return sdf
+
+
+class _SdfObjFn(torch.autograd.Function):
+    """(sdf, feature, normal) = f(pts, params) with a second-order-aware backward."""
+
+    @staticmethod
+    def forward(ctx, pts, packed, inv_scale, precision, *params):
+        pts_c = _f32c(pts.detach())
+        _require_cuda(pts_c, "sdf_obj")
+        pk = packed.get()
+        n = pts_c.shape[0]
+        dev = pts_c.device
+        sdf = torch.empty(n, 1, device=dev, dtype=torch.float32)
+        feat = torch.empty(n, 256, device=dev, dtype=torch.float32)
+        normal = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        stf = lib.hn_sdf_obj_stash_floats(n)
+        stash = torch.empty(max(stf, 4), device=dev, dtype=torch.float32)
+        if n > 0:
+            check(lib.hn_sdf_obj_fwd(ctypes.byref(pk.struct), _ptr(pts_c), n, inv_scale, _ptr(sdf), _ptr(feat),
+                                     256, _ptr(normal), _ptr(stash), stf, None, 0, precision, _stream(pts_c)),
+                  "hn_sdf_obj_fwd")
+        ctx.packed, ctx.stash, ctx.n = pk, stash, n
+        ctx.inv_scale, ctx.precision = inv_scale, precision
+        ctx.struct = pk.struct
+        ctx.pts_needs_grad = pts.requires_grad
+        ctx.params_need_grad = any(p.requires_grad for p in params)
+        return sdf, feat, normal
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_sdf, d_feat, d_normal):
+        n, pk = ctx.n, ctx.packed
+        if ctx.stash is None:
+            raise _lib.HonerfError("sdf_obj backward called twice (the stash is consumed)")
+        dev = ctx.stash.device
+        d_sdf = _f32c(d_sdf) if d_sdf is not None else None
+        d_feat = _f32c(d_feat) if d_feat is not None else None
+        d_normal = _f32c(d_normal) if d_normal is not None else torch.zeros(n, 3, device=dev)
+        d_pts = torch.empty(n, 3, device=dev, dtype=torch.float32) if ctx.pts_needs_grad else None
+        grads = [None] * (3 * len(pk.layers))
+        if n > 0:
+            gs = None
+            if ctx.params_need_grad:
+                dW, db, gs = pk.new_grad()
+            wsf = lib.hn_sdf_obj_ws_floats(n, HN_WS_BWD)
+            ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+            check(lib.hn_sdf_obj_bwd(ctypes.byref(ctx.struct), n, ctx.inv_scale, _ptr(ctx.stash), _ptr(d_sdf),
+                                     _ptr(d_feat), 256, _ptr(d_normal), _ptr(d_pts),
+                                     ctypes.byref(gs) if gs is not None else None, _ptr(ws), wsf,
+                                     ctx.precision, _stream(ctx.stash)), "hn_sdf_obj_bwd")
+            if gs is not None:
+                grads = pk.unpack_grads(dW, db)
+        elif d_pts is not None:
+            d_pts.zero_()
+        ctx.stash = None
+        return (d_pts, None, None, None) + tuple(grads)
+
+
+def sdf_obj(packed, pts, inv_scale=1.0, precision=None):
+    """Fused SDFNetwork_OBJ.forward + .gradient (utils/fields.py:316-347).
+    Returns sdf [N,1], feature [N,256], normal [N,3]; differentiable w.r.t. pts and parameters."""
+    precision = _default_precision if precision is None else precision
+    return _SdfObjFn.apply(pts, packed, float(inv_scale), precision, *packed.flat_params())
+
+
+# ------------------------------------------------------------------------------------------------
+# object colour field
+# ------------------------------------------------------------------------------------------------
+class _ColorObjFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pts, dirs, feat, normal, packed, precision, *params):
+        pts_c, dirs_c = _f32c(pts.detach()), _f32c(dirs.detach())
+        feat_c, nrm_c = _f32c(feat.detach()), _f32c(normal.detach())
+        _require_cuda(pts_c, "color_obj")
+        pk = packed.get()
+        n, dev = pts_c.shape[0], pts_c.device
+        rgb = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        stf = lib.hn_color_obj_stash_floats(n)
+        stash = torch.empty(max(stf, 4), device=dev, dtype=torch.float32)
+        if n > 0:
+            check(lib.hn_color_obj_fwd(ctypes.byref(pk.struct), _ptr(pts_c), _ptr(dirs_c), _ptr(feat_c),
+                                       feat_c.shape[1], _ptr(nrm_c), n, _ptr(rgb), _ptr(stash), stf, precision,
+                                       _stream(pts_c)), "hn_color_obj_fwd")
+        ctx.packed, ctx.stash, ctx.n, ctx.precision, ctx.struct = pk, stash, n, precision, pk.struct
+        ctx.rgb = rgb
+        ctx.need = (pts.requires_grad, dirs.requires_grad, feat.requires_grad, normal.requires_grad)
+        ctx.params_need_grad = any(p.requires_grad for p in params)
+        return rgb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_rgb):
+        if ctx.stash is None:
+            raise _lib.HonerfError("color_obj backward called twice (the stash is consumed)")
+        n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
+        d_rgb = _f32c(d_rgb)
+        d_pts = torch.empty(n, 3, device=dev) if ctx.need[0] else None
+        d_dirs = torch.empty(n, 3, device=dev) if ctx.need[1] else None
+        d_feat = torch.empty(n, 256, device=dev) if ctx.need[2] else None
+        d_nrm = torch.empty(n, 3, device=dev) if ctx.need[3] else None
+        grads = [None] * (3 * len(pk.layers))
+        if n > 0:
+            gs = None
+            if ctx.params_need_grad:
+                dW, db, gs = pk.new_grad()
+            wsf = lib.hn_color_obj_ws_floats(n, HN_WS_BWD)
+            ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+            check(lib.hn_color_obj_bwd(ctypes.byref(ctx.struct), n, _ptr(ctx.stash), _ptr(ctx.rgb), _ptr(d_rgb),
+                                       _ptr(d_pts), _ptr(d_dirs), _ptr(d_feat), 256, _ptr(d_nrm),
+                                       ctypes.byref(gs) if gs is not None else None, _ptr(ws), wsf,
+                                       ctx.precision, _stream(ctx.stash)), "hn_color_obj_bwd")
+            if gs is not None:
+                grads = pk.unpack_grads(dW, db)
+        ctx.stash = None
+        return (d_pts, d_dirs, d_feat, d_nrm, None, None) + tuple(grads)
+
+
+def color_obj(packed, pts, dirs, feat, normal, precision=None):
+    """RenderingNetwork_OBJ.forward (utils/fields.py:387-405): -> rgb [N,3]."""
+    precision = _default_precision if precision is None else precision
+    return _ColorObjFn.apply(pts, dirs, feat, normal, packed, precision, *packed.flat_params())
+
+
+# ------------------------------------------------------------------------------------------------
+# rays and hierarchical sampling (all under no_grad in the reference)
+# ------------------------------------------------------------------------------------------------
+def ray_points(rays_o, rays_d, z):
+    """[B,3],[B,3],[B,n] -> [B*n,3], bit-exact with rays_o[:,None]+rays_d[:,None]*z[...,None]."""
+    o, d, z = _f32c(rays_o.detach()), _f32c(rays_d.detach()), _f32c(z.detach())
+    _require_cuda(z, "ray_points")
+    B, n = z.shape
+    pts = torch.empty(B * n, 3, device=z.device, dtype=torch.float32)
+    check(lib.hn_ray_points(_ptr(o), _ptr(d), _ptr(z), B, n, _ptr(pts), _stream(z)), "hn_ray_points")
+    return pts
+
+
+_u_cache = {}
+
+
+def _u_samples(n, device):
+    key = (n, str(device))
+    if key not in _u_cache:
+        # generated by torch on the host so the values are the reference's (utils/renderer.py:19)
+        _u_cache[key] = torch.linspace(0.0 + 0.5 / n, 1.0 - 0.5 / n, steps=n).to(device)
+    return _u_cache[key]
+
+
+def up_sample(z_vals, sdf, n_importance, inv_s):
+    """NeuSRenderer.up_sample (utils/renderer.py:60-86): [B,m],[B,m] -> [B,n_importance]."""
+    z, s = _f32c(z_vals.detach()), _f32c(sdf.detach()).reshape(z_vals.shape)
+    _require_cuda(z, "up_sample")
+    B, m = z.shape
+    out = torch.empty(B, n_importance, device=z.device, dtype=torch.float32)
+    u = _u_samples(n_importance, z.device)
+    check(lib.hn_up_sample(_ptr(z), _ptr(s), _ptr(u), B, m, n_importance, float(inv_s), _ptr(out), _stream(z)),
+          "hn_up_sample")
+    return out
+
+
+def inverse_cdf(bins, cdf, n_samples, return_indices=False):
+    bins, cdf = _f32c(bins), _f32c(cdf)
+    _require_cuda(cdf, "inverse_cdf")
+    B, m = cdf.shape
+    out = torch.empty(B, n_samples, device=cdf.device, dtype=torch.float32)
+    below = above = None
+    if return_indices:
+        below = torch.empty(B, n_samples, device=cdf.device, dtype=torch.int64)
+        above = torch.empty_like(below)
+    u = _u_samples(n_samples, cdf.device)
+    check(lib.hn_inverse_cdf(_ptr(bins), _ptr(cdf), _ptr(u), B, m, n_samples, _ptr(out), _ptr(below), _ptr(above),
+                             _stream(cdf)), "hn_inverse_cdf")
+    return (out, below, above) if return_indices else out
+
+
+def merge_sorted(z_a, z_b, sdf_a=None, sdf_b=None, sdf_row_mod=0, return_index=False):
+    """cat_z_vals' sort + gather (utils/renderer.py:88-105) for two sorted rows."""
+    za, zb = _f32c(z_a.detach()), _f32c(z_b.detach())
+    _require_cuda(za, "merge_sorted")
+    B, m = za.shape
+    k = zb.shape[1]
+    zo = torch.empty(B, m + k, device=za.device, dtype=torch.float32)
+    idx = torch.empty(B, m + k, device=za.device, dtype=torch.int64) if return_index else None
+    so = sa = sb = None
+    if sdf_a is not None:
+        sa, sb = _f32c(sdf_a.detach()).reshape(B, m), _f32c(sdf_b.detach()).reshape(B, k)
+        so = torch.empty(B, m + k, device=za.device, dtype=torch.float32)
+    check(lib.hn_merge_sorted(_ptr(za), m, _ptr(zb), k, B, _ptr(zo), _ptr(idx), _ptr(sa), _ptr(sb),
+                              int(sdf_row_mod), _ptr(so), _stream(za)), "hn_merge_sorted")
+    return zo, so, idx
+
+
+def sort_rows(x, return_index=False):
+    x = _f32c(x.detach())
+    _require_cuda(x, "sort_rows")
+    B, n = x.shape
+    out = torch.empty_like(x)
+    idx = torch.empty(B, n, device=x.device, dtype=torch.int64) if return_index else None
+    check(lib.hn_sort_rows(_ptr(x), B, n, _ptr(out), _ptr(idx), _stream(x)), "hn_sort_rows")
+    return (out, idx) if return_index else out
+
+
+class _MidPointsFn(torch.autograd.Function):
+    """pts = o + d * (z + dists/2) (utils/renderer.py:119-124); z is a constant (no_grad)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, z, sample_dist):
+        o, d, zc = _f32c(rays_o.detach()), _f32c(rays_d.detach()), _f32c(z.detach())
+        _require_cuda(zc, "mid_points")
+        B, n = zc.shape
+        pts = torch.empty(B * n, 3, device=zc.device, dtype=torch.float32)
+        dists = torch.empty(B, n, device=zc.device, dtype=torch.float32)
+        check(lib.hn_mid_points(_ptr(o), _ptr(d), _ptr(zc), B, n, float(sample_dist), _ptr(pts), _ptr(dists),
+                                _stream(zc)), "hn_mid_points")
+        ctx.save_for_backward(zc, dists, d)
+        ctx.mark_non_differentiable(dists)
+        return pts, dists
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_pts, _):
+        zc, dists, d = ctx.saved_tensors
+        B, n = zc.shape
+        g = d_pts.reshape(B, n, 3)
+        mid = zc + dists * 0.5
+        return g.sum(1), (g * mid[..., None]).sum(1), None, None
+
+
+def mid_points(rays_o, rays_d, z, sample_dist):
+    return _MidPointsFn.apply(rays_o, rays_d, z, sample_dist)
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+class _CompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sdf, normal, rgb, dists, rays_d, variance, seed_with_c0):
+        sdf_c, nrm_c, rgb_c = _f32c(sdf.detach()), _f32c(normal.detach()), _f32c(rgb.detach())
+        dist_c, d_c, var_c = _f32c(dists.detach()), _f32c(rays_d.detach()), _f32c(variance.detach()).reshape(1)
+        _require_cuda(sdf_c, "neus_composite")
+        B, n = dist_c.shape
+        dev = sdf_c.device
+        weights = torch.empty(B, n, device=dev)
+        cdf = torch.empty(B, n, device=dev)
+        color = torch.empty(B, 3, device=dev)
+        wsum = torch.empty(B, 1, device=dev)
+        wmax = torch.empty(B, 1, device=dev)
+        eik = torch.empty(B, device=dev)
+        check(lib.hn_neus_composite_fwd(_ptr(sdf_c), _ptr(nrm_c), _ptr(rgb_c), _ptr(dist_c), _ptr(d_c), _ptr(var_c),
+                                        B, n, int(seed_with_c0), _ptr(weights), _ptr(cdf), None, _ptr(color),
+                                        _ptr(wsum), _ptr(wmax), _ptr(eik), _stream(sdf_c)), "hn_neus_composite_fwd")
+        ctx.save_for_backward(sdf_c, nrm_c, rgb_c, dist_c, d_c, var_c, weights)
+        ctx.seed = int(seed_with_c0)
+        ctx.need_d = rays_d.requires_grad
+        ctx.var_shape = variance.shape
+        ctx.rgb_shape = rgb.shape
+        ctx.mark_non_differentiable(cdf, wmax)
+        return color, weights, cdf, wsum, wmax, eik
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_color, d_weights, _d_cdf, d_wsum, _d_wmax, d_eik):
+        sdf_c, nrm_c, rgb_c, dist_c, d_c, var_c, weights = ctx.saved_tensors
+        B, n = dist_c.shape
+        dev = sdf_c.device
+        d_color = _f32c(d_color) if d_color is not None else torch.zeros(B, 3, device=dev)
+        d_weights = _f32c(d_weights) if d_weights is not None else None
+        d_wsum = _f32c(d_wsum) if d_wsum is not None else None
+        d_eik = _f32c(d_eik) if d_eik is not None else None
+        d_sdf = torch.empty(B * n, 1, device=dev)
+        d_nrm = torch.empty(B * n, 3, device=dev)
+        d_rgb = torch.empty(B * n, 3, device=dev)
+        d_rd = torch.empty(B, 3, device=dev) if ctx.need_d else None
+        d_var = torch.zeros(1, device=dev)
+        check(lib.hn_neus_composite_bwd(_ptr(sdf_c), _ptr(nrm_c), _ptr(rgb_c), _ptr(dist_c), _ptr(d_c), _ptr(var_c),
+                                        _ptr(weights), B, n, ctx.seed, _ptr(d_color), _ptr(d_wsum), _ptr(d_weights),
+                                        _ptr(d_eik), _ptr(d_sdf), _ptr(d_nrm), _ptr(d_rgb), _ptr(d_rd), _ptr(d_var),
+                                        _stream(sdf_c)), "hn_neus_composite_bwd")
+        return d_sdf, d_nrm, d_rgb.reshape(ctx.rgb_shape), None, d_rd, d_var.reshape(ctx.var_shape), None
+
+
+def neus_composite(sdf, normal, rgb, dists, rays_d, variance, seed_with_c0=True):
+    """alpha / transmittance / compositing of render_core (utils/renderer.py:144-169).
+    sdf [B*n,1], normal [B*n,3], rgb [B*n,3] or [B,n,3], dists [B,n], rays_d [B,3], variance scalar.
+    Returns color [B,3], weights [B,n], cdf [B,n], weight_sum [B,1], weight_max [B,1],
+    eik [B] (per-ray sums of (||n||-1)^2)."""
+    return _CompositeFn.apply(sdf, normal, rgb, dists, rays_d, variance, seed_with_c0)
+
+
+SQRT1_2 = 1.0 / math.sqrt(2.0)

@@ -1,0 +1,180 @@
+/* honerf_b200 -- C ABI of the B200-native NeuS volume-rendering hot path of HO-NeRF.
+ *
+ * The reference (iscas3dv/HO-NeRF) has no FFI layer: its hot path is plain PyTorch
+ * (utils/fields.py, utils/renderer.py, utils/renderer_batch.py).  This header is the boundary a
+ * maintainer would bind instead: every entry point names the reference code it replaces
+ * (file:line).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; all tensors are dense row-major
+ *     fp32 (indices int64), 16-byte aligned, leading dimensions multiples of 4 floats;
+ *   - functions never allocate, never synchronise and enqueue all work on `stream`
+ *     (a cudaStream_t); outputs, stashes and workspaces are caller-allocated -- the *_floats()
+ *     queries give their sizes;
+ *   - return value: HN_OK (0) or a negative hn_status; hn_last_error() gives the message of the
+ *     calling thread's last failure;
+ *   - there is NO CPU fallback: with no CUDA device every compute entry point fails.
+ */
+#ifndef HONERF_B200_H
+#define HONERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HN_API __attribute__((visibility("default")))
+
+typedef void* hn_stream_t; /* cudaStream_t */
+
+enum hn_status { HN_OK = 0, HN_ERR_ARG = -1, HN_ERR_CUDA = -2, HN_ERR_UNSUPPORTED = -3 };
+
+/* Arithmetic of the dense contractions.  HN_SIMT_FP32 is the verification path (fp32 FFMA);
+ * the HN_TC_* values run on tcgen05 tensor cores with fp32 accumulation in TMEM. */
+enum hn_precision { HN_SIMT_FP32 = 0, HN_TC_TF32 = 1, HN_TC_BF16X3 = 2, HN_TC_BF16 = 3 };
+
+HN_API const char* hn_last_error(void);
+HN_API int hn_version(void);
+/* Number of kernels this library has launched on behalf of the calling process (all streams). */
+HN_API int64_t hn_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight-normalised MLP parameters (nn.utils.weight_norm, dim=0:
+ * utils/fields.py:120-121, 216-217, 307-308, 382-383).
+ * ------------------------------------------------------------------------------------------- */
+#define HN_MAX_LAYERS 12
+
+typedef struct hn_mlp {
+    int32_t n_layers;
+    int32_t in_dim[HN_MAX_LAYERS];
+    int32_t out_dim[HN_MAX_LAYERS];
+    int32_t ld[HN_MAX_LAYERS];     /* leading dimension of W[l], >= round_up(in_dim, 4) */
+    const float* W[HN_MAX_LAYERS]; /* effective weights g*v/||v|| (times post_scale), [out, ld] */
+    const float* b[HN_MAX_LAYERS]; /* bias [out] */
+} hn_mlp_t;
+
+typedef struct hn_mlp_grad {
+    float* dW[HN_MAX_LAYERS]; /* same layout as W; ACCUMULATED into (caller zeroes) */
+    float* db[HN_MAX_LAYERS]; /* [out]; ACCUMULATED into */
+} hn_mlp_grad_t;
+
+/* W[o, :in] = post_scale * g[o] * v[o, :] / ||v[o, :]||, padding columns [in, ld) zeroed.
+ * Replaces the per-call `_weight_norm` recomputation of every Linear. */
+HN_API int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld,
+                      float post_scale, float* W, hn_stream_t stream);
+/* (dv, dg) from dW; dW is the gradient w.r.t. the PACKED weight (so it is
+ * multiplied by post_scale first).  dv [out,in] and dg [out] are overwritten. */
+HN_API int hn_wn_bwd(const float* v, const float* g, const float* dW, int out_dim, int in_dim,
+                     int ld, float post_scale, float* dv, float* dg, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Object SDF field: SDFNetwork_OBJ.forward / .sdf / .gradient (utils/fields.py:316-347) as ONE
+ * operator (value + feature + analytic normal) with a hand-written second-order backward.
+ * mlp: 9 layers 63->256->256->256->193->[cat 63]->256->256->256->256->257; W[4] must be packed
+ * with post_scale = 1/sqrt(2) (the skip concat's division is folded into it).
+ * ------------------------------------------------------------------------------------------- */
+enum hn_ws_kind { HN_WS_SDF_ONLY = 0, HN_WS_FWD = 1, HN_WS_BWD = 2 };
+HN_API int64_t hn_sdf_obj_stash_floats(int64_t n_pts);
+HN_API int64_t hn_sdf_obj_ws_floats(int64_t n_pts, int ws_kind);
+
+/* sdf[n] = SDFNetwork_OBJ.sdf(pts) (utils/fields.py:330-331); no stash, no normal. */
+HN_API int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n_pts, float inv_scale,
+                          float* sdf, float* ws, int64_t ws_floats, int precision,
+                          hn_stream_t stream);
+/* sdf [n], feat [n, ld_feat>=256], normal [n,3] = d sdf / d pts (replaces the second forward +
+ * autograd.grad(create_graph=True) of utils/fields.py:336-347).  `stash` keeps what the backward
+ * needs. */
+HN_API int hn_sdf_obj_fwd(const hn_mlp_t* mlp, const float* pts, int64_t n_pts, float inv_scale,
+                          float* sdf, float* feat, int64_t ld_feat, float* normal, float* stash,
+                          int64_t stash_floats, float* ws, int64_t ws_floats, int precision,
+                          hn_stream_t stream);
+/* Backward of hn_sdf_obj_fwd given cotangents of (sdf, feat, normal): accumulates dW/db, and
+ * writes d_pts [n,3] when non-NULL.  This contains the Hessian-vector products the reference
+ * obtains by differentiating through autograd.grad (SoftplusBackwardBackward).  The stash is
+ * consumed (overwritten). d_feat may be NULL (treated as zero). */
+HN_API int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n_pts, float inv_scale, float* stash,
+                          const float* d_sdf, const float* d_feat, int64_t ld_dfeat,
+                          const float* d_normal, float* d_pts, const hn_mlp_grad_t* grad,
+                          float* ws, int64_t ws_floats, int precision, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Object colour field: RenderingNetwork_OBJ.forward (utils/fields.py:387-405).
+ * mlp: 5 layers 373->256->256->256->256->3, ReLU, sigmoid.
+ * ------------------------------------------------------------------------------------------- */
+HN_API int64_t hn_color_obj_stash_floats(int64_t n_pts);
+HN_API int64_t hn_color_obj_ws_floats(int64_t n_pts, int ws_kind);
+HN_API int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs,
+                            const float* feat, int64_t ld_feat, const float* normal,
+                            int64_t n_pts, float* rgb, float* stash, int64_t stash_floats,
+                            int precision, hn_stream_t stream);
+/* d_pts, d_dirs, d_normal [n,3] and d_feat [n, ld_dfeat] are overwritten (any may be NULL);
+ * grad may be NULL (weights frozen: pose fitting, SURVEY D-11). */
+HN_API int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n_pts, float* stash, const float* rgb,
+                            const float* d_rgb, float* d_pts, float* d_dirs, float* d_feat,
+                            int64_t ld_dfeat, float* d_normal, const hn_mlp_grad_t* grad,
+                            float* ws, int64_t ws_floats, int precision, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ray helpers and hierarchical sampling (utils/renderer.py:10-37, 60-105, 119-127, 204-234).
+ * ------------------------------------------------------------------------------------------- */
+/* pts[b,i,:] = o[b,:] + d[b,:] * z[b,i]  with a separately rounded multiply and add, bit-exact
+ * with eager PyTorch (utils/renderer.py:91,216). */
+HN_API int hn_ray_points(const float* rays_o, const float* rays_d, const float* z, int64_t n_rays,
+                         int n, float* pts, hn_stream_t stream);
+/* dists / mid-point samples of render_core (utils/renderer.py:119-124):
+ * dists[b,i] = z[b,i+1]-z[b,i] (last = sample_dist), mid = z + dists*0.5, pts = o + d*mid. */
+HN_API int hn_mid_points(const float* rays_o, const float* rays_d, const float* z, int64_t n_rays,
+                         int n, float sample_dist, float* pts, float* dists, hn_stream_t stream);
+/* NeuSRenderer.up_sample (utils/renderer.py:60-86): one warp per ray; section weights, fp64
+ * running cdf (matching torch CPU cumsum/cumprod), inverse-CDF search. */
+HN_API int hn_up_sample(const float* z, const float* sdf, const float* u, int64_t n_rays, int m, int n_importance,
+                        float inv_s, float* new_z, hn_stream_t stream);
+/* The inverse-CDF step of sample_pdf (utils/renderer.py:18-35) given an explicit cdf [B,m]:
+ * u = linspace(.5/n, 1-.5/n, n) supplied by the caller (host-generated with torch to stay
+ * bit-identical); searchsorted(right=True); below/above (int64, may be NULL). */
+HN_API int hn_inverse_cdf(const float* bins, const float* cdf, const float* u, int64_t n_rays,
+                          int m, int n_samples, float* samples, int64_t* below, int64_t* above,
+                          hn_stream_t stream);
+/* cat_z_vals (utils/renderer.py:88-105): stable merge of two sorted rows z_a [B,m], z_b [B,k]
+ * -> z_out [B,m+k], index (position in cat[z_a,z_b]; int64, may be NULL); when sdf_a/sdf_b are
+ * given, sdf_out[b,i] = cat[sdf_a,sdf_b][src_row(b), index[b,i]] with src_row(b) = b, or
+ * b % sdf_row_mod when sdf_row_mod > 0 (the frame-0 gather quirk of
+ * utils/renderer_batch.py:108-111, SURVEY D-7). */
+HN_API int hn_merge_sorted(const float* z_a, int m, const float* z_b, int k, int64_t n_rays,
+                           float* z_out, int64_t* index, const float* sdf_a, const float* sdf_b,
+                           int64_t sdf_row_mod, float* sdf_out, hn_stream_t stream);
+/* Stable ascending sort of every row of x [B,n] (n <= 1024): the final torch.sort of
+ * NeuSRenderer_fitting.render (utils/renderer.py:498). index may be NULL. */
+HN_API int hn_sort_rows(const float* x, int64_t n_rays, int n, float* out, int64_t* index,
+                        hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * s-density alpha + transmittance + compositing (utils/renderer.py:144-169), one warp per ray.
+ * variance: device pointer to SingleVarianceNetwork.variance; inv_s = clip(exp(10 v), 1e-6, 1e6).
+ * seed_with_c0 != 0 reproduces render_core's cumprod seeded with c[:, :1] (SURVEY D-1).
+ * Outputs: weights [B,n], cdf c [B,n], alpha [B,n] (may be NULL), color [B,3], weight_sum [B],
+ * weight_max [B], eik [B] = per-ray sum of (||normal||-1)^2.
+ * ------------------------------------------------------------------------------------------- */
+HN_API int hn_neus_composite_fwd(const float* sdf, const float* normal, const float* rgb,
+                                 const float* dists, const float* rays_d, const float* variance,
+                                 int64_t n_rays, int n, int seed_with_c0, float* weights,
+                                 float* cdf, float* alpha, float* color, float* weight_sum,
+                                 float* weight_max, float* eik, hn_stream_t stream);
+/* Backward (SURVEY E-5).  Cotangents: d_color [B,3], d_weight_sum [B] (may be NULL),
+ * d_weights [B,n] (may be NULL), d_eik [B] (may be NULL).  Outputs (overwritten): d_sdf [B*n],
+ * d_normal [B*n,3], d_rgb [B*n,3], d_rays_d [B,3] (may be NULL); d_variance (1 float) is
+ * ACCUMULATED with atomics (caller zeroes). */
+HN_API int hn_neus_composite_bwd(const float* sdf, const float* normal, const float* rgb,
+                                 const float* dists, const float* rays_d, const float* variance,
+                                 const float* weights, int64_t n_rays, int n, int seed_with_c0,
+                                 const float* d_color, const float* d_weight_sum,
+                                 const float* d_weights, const float* d_eik, float* d_sdf,
+                                 float* d_normal, float* d_rgb, float* d_rays_d,
+                                 float* d_variance, hn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HONERF_B200_H */

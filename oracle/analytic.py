@@ -1,0 +1,187 @@
+"""CPU model of the *kernel algorithm*: SDF value + feature + analytic normal as ONE operator with a
+hand-derived second-order backward, written with explicit
+matrix products so that (a) the formulas the CUDA kernels implement are validated against autograd
+on CPU before any GPU time is spent, and (b) the effect of tensor-core operand rounding
+(TF32 / BF16 / split-BF16) can be emulated by swapping the ``mm`` callable.
+
+TEST INFRASTRUCTURE ONLY (same rules as oracle/honerf_oracle.py).  Restates utils/fields.py:316-347
+(object SDF forward + gradient) and the backward autograd derives for it.
+"""
+import math
+
+import torch
+
+SQRT1_2 = 1.0 / math.sqrt(2.0)
+
+
+def exact_mm(a, b):
+    return a @ b
+
+
+def round_tf32(x):
+    """round-to-nearest-even to 10 explicit mantissa bits (what cvt.rna.tf32.f32 produces)."""
+    i = x.contiguous().view(torch.int32)
+    r = ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF)
+    return r.view(torch.float32)
+
+
+def trunc_tf32(x):
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+def tf32_mm(a, b):
+    return round_tf32(a) @ round_tf32(b)
+
+
+def bf16_mm(a, b):
+    return a.bfloat16().float() @ b.bfloat16().float()
+
+
+def bf16x3_mm(a, b):
+    ah = a.bfloat16().float()
+    al = (a - ah).bfloat16().float()
+    bh = b.bfloat16().float()
+    bl = (b - bh).bfloat16().float()
+    return ah @ bh + (ah @ bl + al @ bh)
+
+
+def bf16x2_mm(a, b):
+    """activation split only (a_hi + a_lo) x b_hi"""
+    ah = a.bfloat16().float()
+    al = (a - ah).bfloat16().float()
+    bh = b.bfloat16().float()
+    return ah @ bh + al @ bh
+
+
+def enc_obj(x, L=10):
+    """[x, channel-major sin/cos] (utils/fields.py:13-20, 318-319) and the sin/cos themselves."""
+    freq = (2.0 ** torch.arange(L, dtype=torch.float32)).to(x.dtype)
+    spec = x[:, :, None] * freq                       # [N,3,L]
+    s, c = spec.sin(), spec.cos()
+    e = torch.cat([x, torch.stack([s, c], dim=2).reshape(x.shape[0], -1)], dim=1)
+    return e, s, c, freq
+
+
+def enc_jt(g, s, c, freq):
+    """J_e^T g : [N,3+6L] -> [N,3]."""
+    N, _, L = s.shape
+    ge = g[:, 3:].reshape(N, 3, 2, L)
+    return g[:, :3] + (freq * (c * ge[:, :, 0] - s * ge[:, :, 1])).sum(-1)
+
+
+def enc_j(t, s, c, freq):
+    """J_e t : [N,3] -> [N,3+6L]."""
+    N, _, L = s.shape
+    ds = freq * c * t[:, :, None]
+    dc = -freq * s * t[:, :, None]
+    return torch.cat([t, torch.stack([ds, dc], dim=2).reshape(N, -1)], dim=1)
+
+
+def enc_hess(g, t, s, c, freq):
+    """sum_k d2 e_k/dx2 * g_k * t  (diagonal per coordinate): [N,3]."""
+    N, _, L = s.shape
+    ge = g[:, 3:].reshape(N, 3, 2, L)
+    return t * (freq * freq * (-s * ge[:, :, 0] - c * ge[:, :, 1])).sum(-1)
+
+
+def effective_weights(p, n_lin=9):
+    Ws, bs = [], []
+    for l in range(n_lin):
+        v, g = p["lin%d.weight_v" % l], p["lin%d.weight_g" % l]
+        Ws.append(v * (g / v.norm(dim=1, keepdim=True)))
+        bs.append(p["lin%d.bias" % l])
+    return Ws, bs
+
+
+def sp_prime_from_h(h, beta=100.0):
+    """softplus'(z) = sigmoid(beta z) = 1 - exp(-beta h) with h = softplus(z)."""
+    return -torch.expm1(-beta * h)
+
+
+def sdf_obj_fwd(Ws, bs, x, scale=1.0, mm=exact_mm, skip=4, beta=100.0):
+    """Returns sdf [N,1], feat [N,256], normal [N,3] and the stash the backward needs."""
+    e, s, c, freq = enc_obj(x)
+    H, a_in = [], []
+    a = e
+    n_lin = len(Ws)
+    for l in range(n_lin):
+        if l == skip:
+            a = torch.cat([a, e], dim=1) * SQRT1_2
+        a_in.append(a)
+        z = mm(a, Ws[l].t()) + bs[l]
+        if l < n_lin - 1:
+            a = torch.nn.functional.softplus(z, beta=beta)
+            H.append(a)
+    sdf = z[:, :1] / scale
+    feat = z[:, 1:]
+    # normal sweep (reverse mode with the one-hot seed on the sdf column)
+    D = [None] * (n_lin - 1)
+    hb = (Ws[n_lin - 1][0] / scale)[None, :].expand(x.shape[0], -1)
+    eb_skip = None
+    for l in range(n_lin - 2, -1, -1):
+        D[l] = sp_prime_from_h(H[l], beta) * hb
+        ab = mm(D[l], Ws[l])
+        if l == skip:
+            n_h = Ws[l].shape[1] - e.shape[1]
+            eb_skip = ab[:, n_h:] * SQRT1_2
+            hb = ab[:, :n_h] * SQRT1_2
+        else:
+            hb = ab
+    eb = hb + eb_skip
+    normal = enc_jt(eb, s, c, freq)
+    stash = dict(e=e, s=s, c=c, freq=freq, H=H, D=D, a_in=a_in, eb=eb)
+    return sdf, feat, normal, stash
+
+
+def sdf_obj_bwd(Ws, bs, stash, d_sdf, d_feat, d_normal, scale=1.0, mm=exact_mm, skip=4,
+                beta=100.0, need_dx=True):
+    """Second-order backward: returns (d_x, dW list, db list)."""
+    e, s, c, freq, H, D, a_in = (stash[k] for k in ("e", "s", "c", "freq", "H", "D", "a_in"))
+    n_lin = len(Ws)
+    # tangent sweep along d_normal
+    ue = enc_j(d_normal, s, c, freq)
+    u = ue
+    au_in, X = [], []
+    for l in range(n_lin - 1):
+        if l == skip:
+            u = torch.cat([u, ue], dim=1) * SQRT1_2
+        au_in.append(u)
+        q = mm(u, Ws[l].t())
+        sp1 = sp_prime_from_h(H[l], beta)
+        u = sp1 * q
+        X.append(beta * (1.0 - sp1) * D[l] * q)       # s''(z) * hb * q with D = s' * hb
+    u_last = u                                        # tangent entering the output layer
+    # reverse sweep
+    dz = torch.cat([d_sdf / scale, d_feat], dim=1)
+    dW, db = [None] * n_lin, [None] * n_lin
+    de_skip = None
+    for l in range(n_lin - 1, -1, -1):
+        dW[l] = mm(dz.t(), a_in[l])
+        if l < n_lin - 1:
+            dW[l] = dW[l] + mm(D[l].t(), au_in[l])
+        else:
+            # the normal sweep is seeded with row 0 of the output layer: <dn, n> = W_out[0].u / scale
+            dW[l] = dW[l].clone()
+            dW[l][0] += u_last.sum(0) / scale
+        db[l] = dz.sum(0)
+        da = mm(dz, Ws[l])
+        if l == skip:
+            n_h = Ws[l].shape[1] - e.shape[1]
+            de_skip = da[:, n_h:] * SQRT1_2
+            da = da[:, :n_h] * SQRT1_2
+        if l > 0:
+            dz = sp_prime_from_h(H[l - 1], beta) * da + X[l - 1]
+    de = da + de_skip
+    d_x = None
+    if need_dx:
+        d_x = enc_jt(de, s, c, freq) + enc_hess(stash["eb"], d_normal, s, c, freq)
+    return d_x, dW, db
+
+
+def wn_backward(v, g, dW):
+    """(dg, dv) of W = g v / ||v||_row (SURVEY E-2)."""
+    n = v.norm(dim=1, keepdim=True)
+    dot = (dW * v).sum(1, keepdim=True)
+    dg = dot / n
+    dv = (g / n) * (dW - dot * v / (n * n))
+    return dg, dv

@@ -1,0 +1,220 @@
+"""GPU parity: hierarchical sampling (exact indices / positions), compositing, and the end-to-end
+object render + training-loss gradients, against the oracle and the reference's golden vectors."""
+import pytest
+import torch
+
+import cases
+import honerf_oracle as O
+import synth
+from golden_util import check_grads_against_golden, load_golden, max_abs, rel_err
+from gpu_util import DEV, obj_modules
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ray_points_bit_exact():
+    from honerf_b200 import ops
+    gen = torch.Generator().manual_seed(1)
+    o, d = torch.randn(333, 3, generator=gen), torch.randn(333, 3, generator=gen)
+    z = torch.rand(333, 77, generator=gen) * 2
+    ref = (o[:, None, :] + d[:, None, :] * z[..., :, None]).reshape(-1, 3)
+    got = ops.ray_points(o.to(DEV), d.to(DEV), z.to(DEV)).cpu()
+    assert torch.equal(got, ref)
+
+
+def test_mid_points_bit_exact():
+    from honerf_b200 import ops
+    gen = torch.Generator().manual_seed(2)
+    o, d = torch.randn(100, 3, generator=gen), torch.randn(100, 3, generator=gen)
+    z = torch.sort(torch.rand(100, 128, generator=gen) + 0.4, -1)[0]
+    dists, pts, _ = O.mid_points(o, d, z, 1.1 / 64)
+    gp, gd = ops.mid_points(o.to(DEV), d.to(DEV), z.to(DEV), 1.1 / 64)
+    assert torch.equal(gd.cpu(), dists) and torch.equal(gp.cpu(), pts)
+
+
+def test_inverse_cdf_exact_indices_and_positions():
+    """Given the oracle's cdf: searchsorted indices and sample positions are bit-exact."""
+    from honerf_b200 import ops
+    g = load_golden("sampling")
+    c = cases.sampling_case()
+    cdf = O.sample_pdf_cdf(c["pdf_w"])
+    s_ref, below_ref, above_ref = O.inverse_cdf(c["pdf_bins"], cdf, 16)
+    s, below, above = ops.inverse_cdf(c["pdf_bins"].to(DEV), cdf.to(DEV), 16, return_indices=True)
+    assert torch.equal(below.cpu(), below_ref) and torch.equal(above.cpu(), above_ref)
+    assert torch.equal(s.cpu(), s_ref)
+    assert torch.equal(s.cpu(), g["pdf_samples"])
+    # ties go right, and the edge cases of SURVEY appendix B
+    cdf = torch.tensor([[0.0, 0.25, 0.25, 0.5, 1.0]])
+    bins = torch.tensor([[0.0, 1.0, 2.0, 3.0, 4.0]])
+    s_ref, b_ref, a_ref = O.inverse_cdf(bins, cdf, 4)
+    s, b, a = ops.inverse_cdf(bins.to(DEV), cdf.to(DEV), 4, return_indices=True)
+    assert torch.equal(b.cpu(), b_ref) and torch.equal(a.cpu(), a_ref) and torch.equal(s.cpu(), s_ref)
+
+
+def test_up_sample_and_merge_chain_vs_golden():
+    """up_sample: importance samples within 2e-6 of the reference and >= 99% bit-identical (the
+    only inexact step is sigmoid/sum rounding); merge: exact."""
+    from honerf_b200 import ops
+    g = load_golden("sampling")
+    z, s = g["z0"].to(DEV), g["sdf0"].to(DEV)
+    exact = total = 0
+    for i in range(4):
+        new_z = ops.up_sample(z, s, 16, 64 * 2 ** i)
+        ref_new = g["new_z%d" % i]
+        assert max_abs(new_z, ref_new) < 2e-6, i
+        exact += int((new_z.cpu() == ref_new).sum())
+        total += ref_new.numel()
+        # continue the chain from the reference's samples so later steps see identical inputs
+        new_z = ref_new.to(DEV)
+        merged, _, idx = ops.merge_sorted(z, new_z, return_index=True)
+        ref_sorted, ref_idx = torch.sort(torch.cat([z.cpu(), ref_new], -1), -1, stable=True)
+        assert torch.equal(merged.cpu(), g["z%d" % (i + 1)])
+        assert torch.equal(idx.cpu(), ref_idx)
+        z = merged
+        if i < 3:
+            s = g["sdf%d" % (i + 1)].to(DEV)
+    assert exact / total > 0.99, exact / total
+
+
+def test_merge_gathers_sdf_and_row_mod_quirk():
+    from honerf_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    za = torch.sort(torch.rand(6, 64, generator=gen), -1)[0]
+    zb = torch.sort(torch.rand(6, 16, generator=gen), -1)[0]
+    sa, sb = torch.randn(6, 64, generator=gen), torch.randn(6, 16, generator=gen)
+    zr, idx = torch.sort(torch.cat([za, zb], -1), -1, stable=True)
+    cat = torch.cat([sa, sb], -1)
+    z, s, _ = ops.merge_sorted(za.to(DEV), zb.to(DEV), sa.to(DEV), sb.to(DEV))
+    assert torch.equal(z.cpu(), zr) and torch.equal(s.cpu(), torch.gather(cat, -1, idx))
+    # frame-0 gather quirk (utils/renderer_batch.py:108-111): rows b take sdf from row b % 3
+    z, s, _ = ops.merge_sorted(za.to(DEV), zb.to(DEV), sa.to(DEV), sb.to(DEV), sdf_row_mod=3)
+    src = torch.cat([cat[:3], cat[:3]], 0)
+    assert torch.equal(s.cpu(), torch.gather(src, -1, idx))
+
+
+def test_sort_rows():
+    from honerf_b200 import ops
+    gen = torch.Generator().manual_seed(4)
+    x = torch.rand(37, 192, generator=gen)
+    x[:, 5] = x[:, 100]        # ties
+    ref, ridx = torch.sort(x, -1, stable=True)
+    out, idx = ops.sort_rows(x.to(DEV), return_index=True)
+    assert torch.equal(out.cpu(), ref) and torch.equal(idx.cpu(), ridx)
+
+
+def _composite_inputs(B, n, seed):
+    gen = torch.Generator().manual_seed(seed)
+    z = torch.sort(0.4 + 1.1 * torch.rand(B, n, generator=gen), -1)[0]
+    dists = torch.cat([z[:, 1:] - z[:, :-1], torch.full((B, 1), 1.1 / 64)], -1)
+    sdf = (0.9 - z + 0.05 * torch.randn(B, n, generator=gen)).reshape(-1, 1) * 0.3
+    nrm = torch.randn(B * n, 3, generator=gen)
+    rgb = torch.rand(B * n, 3, generator=gen)
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=gen), dim=-1)
+    return sdf, nrm, rgb, dists, d
+
+
+def _oracle_composite(sdf, nrm, rgb, dists, d, var, seed_c0):
+    B, n = dists.shape
+    dirs = d[:, None, :].expand(B, n, 3).reshape(-1, 3)
+    alpha, c = O.neus_alpha(sdf, nrm, dirs, dists, O.inv_s_from_variance(var))
+    lead = c[:, :1] if seed_c0 else torch.ones_like(c[:, :1])
+    T = torch.cumprod(torch.cat([lead, 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    w = alpha * T
+    color = (rgb.reshape(B, n, 3) * w[:, :, None]).sum(1)
+    eik = ((torch.linalg.norm(nrm.reshape(B, n, 3), dim=-1) - 1.0) ** 2).sum(-1)
+    return color, w, c, w.sum(-1, keepdim=True), w.max(-1, keepdim=True)[0], eik
+
+
+@pytest.mark.parametrize("B,n,seed_c0", [(65, 128, True), (7, 192, False), (3, 33, True), (1, 1, True)])
+def test_composite_forward_backward_vs_oracle(B, n, seed_c0):
+    """forward <= 2e-6 abs; every input cotangent <= 1e-3 relative vs fp64 autograd."""
+    from honerf_b200 import ops
+    ins = _composite_inputs(B, n, 100 + n)
+    var = torch.tensor(0.3)
+    dd = [t.double().requires_grad_(True) for t in ins[:3]] + [ins[3].double(), ins[4].double().requires_grad_(True)]
+    vd = var.double().requires_grad_(True)
+    ref = _oracle_composite(dd[0], dd[1], dd[2], dd[3], dd[4], vd, seed_c0)
+    gen = torch.Generator().manual_seed(5)
+    gc, gw, gs, ge = (torch.randn(B, 3, generator=gen), torch.randn(B, n, generator=gen),
+                      torch.randn(B, 1, generator=gen), torch.randn(B, generator=gen))
+    L = (ref[0] * gc.double()).sum() + (ref[1] * gw.double()).sum() + (ref[3] * gs.double()).sum() + (ref[5] * ge.double()).sum()
+    rg = torch.autograd.grad(L, [dd[0], dd[1], dd[2], dd[4], vd])
+    gi = [t.to(DEV).requires_grad_(True) for t in ins[:3]] + [ins[3].to(DEV), ins[4].to(DEV).requires_grad_(True)]
+    vg = var.to(DEV).requires_grad_(True)
+    out = ops.neus_composite(gi[0], gi[1], gi[2], gi[3], gi[4], vg, seed_with_c0=seed_c0)
+    for a, b, nm in zip(out, ref, ("color", "weights", "cdf", "wsum", "wmax", "eik")):
+        tol = 2e-6 if nm != "eik" else 2e-4
+        assert max_abs(a, b) < tol, nm
+    Lg = (out[0] * gc.to(DEV)).sum() + (out[1] * gw.to(DEV)).sum() + (out[3] * gs.to(DEV)).sum() + (out[5] * ge.to(DEV)).sum()
+    Lg.backward()
+    for t, r, nm in zip([gi[0], gi[1], gi[2], gi[4], vg], rg, ("sdf", "normal", "rgb", "rays_d", "variance")):
+        assert rel_err(t.grad, r) < 1e-3, nm
+
+
+def _render_obj(R, requires_grad=True):
+    import honerf_b200 as H
+    import ref_conf
+    sdf, col, dev, sp, cp = obj_modules(requires_grad=requires_grad)
+    r = H.NeuSRenderer(sdf, dev, col, "obj", **ref_conf.RENDERER_CONF)
+    return r, sdf, col, dev
+
+
+class _fixed_rand:
+    def __init__(self, t_rand):
+        self.val = t_rand + 0.5
+
+    def __enter__(self):
+        self.orig = torch.rand
+        torch.rand = lambda *a, **k: self.val.clone().to(k.get("device", "cpu"))
+
+    def __exit__(self, *a):
+        torch.rand = self.orig
+
+
+def test_render_vs_golden_and_training_gradients():
+    """End to end (utils/renderer.py:190-258 + loss of exp_runner.py:206-227): colour / weight_sum
+    <= 1e-3 abs and every gradient <= 1e-2 relative vs the reference (north-star tolerances)."""
+    g = load_golden("obj_render")
+    c = cases.obj_render_case()
+    R = c["R"]
+    r, sdf, col, dev = _render_obj(R)
+    Ro = R["Ro"].to(DEV).requires_grad_(True)
+    To = R["To"].to(DEV).requires_grad_(True)
+    zb, zT = torch.zeros(21, 4, 4, device=DEV), torch.zeros(21, 3, device=DEV)
+    with _fixed_rand(R["t_rand"]):
+        out = r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), R["near"], R["far"], zb, zT, None, Ro, To, 0)
+    assert set(out) == {"color_fine", "s_val", "cdf_fine", "weight_sum", "weight_max", "gradient_error"}
+    for k in ("color_fine", "s_val", "cdf_fine", "weight_sum", "weight_max"):
+        assert max_abs(out[k], g[k]) < 1e-3, k
+    assert rel_err(out["gradient_error"], g["gradient_error"]) < 1e-3
+    loss = O.training_loss(out, c["true_rgb"].to(DEV), c["true_mask"].to(DEV))
+    assert rel_err(loss, g["loss"]) < 1e-3
+    loss.backward()
+    grads = {"sdf." + k: p.grad.cpu() for k, p in sdf.named_parameters() if p.grad is not None}
+    grads.update({"color." + k: p.grad.cpu() for k, p in col.named_parameters() if p.grad is not None})
+    grads.update({"variance": dev.variance.grad.cpu(), "Ro": Ro.grad.cpu(), "To": To.grad.cpu()})
+    check_grads_against_golden(g, grads, 1e-2)
+
+
+def test_render_same_z_as_oracle_then_tight():
+    """With perturb=0 the coarse z are identical; check the whole importance-sampling loop lands on
+    the oracle's z (>= 99.5% of samples bit-identical) and colour within 2e-4."""
+    import honerf_b200 as H
+    import ref_conf
+    R = synth.object_rays(48, seed=21)
+    sdf, col, dev, sp, cp = obj_modules(requires_grad=False)
+    r = H.NeuSRenderer(sdf, dev, col, "obj", **dict(ref_conf.RENDERER_CONF, perturb=0.0))
+    ref = O.render_obj(sp, cp, torch.tensor(0.3), R["rays_o"], R["rays_d"], 0.4, 1.5, R["Ro"], R["To"], None)
+    seen = {}
+    orig = r.render_core
+
+    def spy(rays_o, rays_d, bt, T, verts, z_vals, *a):
+        seen["z"] = z_vals
+        return orig(rays_o, rays_d, bt, T, verts, z_vals, *a)
+
+    r.render_core = spy
+    out = r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), 0.4, 1.5, None, None, None, R["Ro"].to(DEV),
+                   R["To"].to(DEV), 0)
+    same = (seen["z"].cpu() == ref["z_vals"]).float().mean().item()
+    assert same > 0.98, same
+    assert max_abs(out["color_fine"], ref["color_fine"]) < 1e-3
