@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the object-field NeuS training step (render fwd + second-order bwd,
+64 coarse + 64 importance samples) on N B200s, with roofline, CPU baseline and end-to-end numbers.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--rays R] [--precision simt_fp32|...]
+    python bench.py --impl reference ...      # the reference algorithm on the host cores (oracle port)
+
+One JSON line on stdout (rank 0).  A "step" = NeuSRenderer.render on one batch of synthetic rays +
+the training loss of exp_runner.py:206-227 (masked L1 + BCE + eikonal, no VGG) + backward +
+gradient all-reduce (N > 1) + Adam step.  Rays are sharded across ranks (weak scaling: --rays per
+GPU); the only collective is the flat MLP-gradient all-reduce.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+N_SAMPLES, N_IMPORTANCE = 64, 64
+# algorithmic FLOPs per ray of the train step: 112 F_o + 128 (6 F_o + 3 C_o)
+F_O, C_O = 1_049_088, 585_728
+FLOPS_PER_RAY_TRAIN = 112 * F_O + 128 * (6 * F_O + 3 * C_O)
+
+
+def training_loss(out, true_rgb, true_mask, igr_weight=1.0, mask_weight=1.0):
+    """exp_runner.py:206-227 without the VGG term (caller-side code of the reference)."""
+    mask_sum = true_mask.sum() + 1e-5
+    color_error = (out["color_fine"] - true_rgb) * true_mask
+    color_loss = F.l1_loss(color_error, torch.zeros_like(color_error), reduction="sum") / mask_sum
+    mask_loss = F.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), true_mask)
+    return color_loss + mask_loss * mask_weight + out["gradient_error"] * igr_weight
+
+
+def synthetic_batch(n_rays, seed):
+    import synth
+    R = synth.object_rays(n_rays, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    R["true_rgb"] = torch.rand(n_rays, 3, generator=g)
+    R["true_mask"] = (torch.rand(n_rays, 1, generator=g) > 0.5).float()
+    return R
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for nm, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port, torch CPU, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_train_step_fn(n_rays, seed=7):
+    import honerf_oracle as O
+    import synth
+    sp, cp = synth.obj_states()
+    sp = {k: v.clone().requires_grad_(k != "se3_refine") for k, v in sp.items()}
+    cp = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
+    var = torch.tensor(0.3, requires_grad=True)
+    B = synthetic_batch(n_rays, seed)
+    params = [v for k, v in sp.items() if k != "se3_refine"] + list(cp.values()) + [var]
+    opt = torch.optim.Adam(params, lr=1e-4)
+
+    def step():
+        out = O.render_obj(sp, cp, var, B["rays_o"], B["rays_d"], B["near"], B["far"], B["Ro"], B["To"],
+                           B["t_rand"])
+        loss = O.training_loss(out, B["true_rgb"], B["true_mask"])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return float(loss)
+    return step
+
+
+def time_cpu(n_rays, steps, warmup):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_train_step_fn(n_rays)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return n_rays / dt, dt, cores
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_rays = min(args.rays, 512)      # bounded sample: one 512-ray batch per step (~3 s on 8 cores)
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    rps, dt, cores = time_cpu(n_rays, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "rays/sec render fwd+bwd (64+64 samples), object-field train step",
+        "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "obj-field train step, %d rays x (64+64) samples, masked-L1+BCE+eikonal, Adam" % n_rays,
+                   "rays_per_step": n_rays},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "%d steps of one %d-ray batch (oracle/honerf_oracle.py, torch CPU)" % (steps, n_rays)},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def build_gpu_model(device, precision):
+    import honerf_b200 as H
+    import ref_conf
+    import synth
+    H.set_default_precision(precision)
+    sp, cp = synth.obj_states()
+    sdf = H.SDFNetwork_OBJ(H.Embedding(), 4, "real", **ref_conf.OBJ_SDF_CONF)
+    col = H.RenderingNetwork_OBJ(H.Embedding(), "real", **ref_conf.OBJ_COLOR_CONF)
+    var = H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT)
+    sdf.load_state_dict(sp); col.load_state_dict(cp)
+    for m in (sdf, col, var):
+        m.to(device)
+    r = H.NeuSRenderer(sdf, var, col, "obj", **ref_conf.RENDERER_CONF)
+    params = list(sdf.parameters()) + list(var.parameters()) + list(col.parameters())
+    opt = torch.optim.Adam(params, lr=1e-4)
+    return H, r, params, opt
+
+
+def run_gpu_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    H, renderer, params, opt = build_gpu_model(device, args.precision)
+    from honerf_b200 import dist as hdist
+    n_rays = args.rays
+    host = synthetic_batch(n_rays, seed=7 + rank)
+    pinned = {k: v.pin_memory() for k, v in host.items() if torch.is_tensor(v)}
+    dev_batch = {k: v.to(device) for k, v in pinned.items()}
+    Ro = dev_batch["Ro"].clone().requires_grad_(True)
+    To = dev_batch["To"].clone().requires_grad_(True)
+
+    def train_step(b):
+        out = renderer.render(b["rays_o"], b["rays_d"], host["near"], host["far"], None, None, None, Ro, To, 0)
+        loss = training_loss(out, b["true_rgb"], b["true_mask"])
+        opt.zero_grad(set_to_none=True)
+        Ro.grad = None; To.grad = None
+        loss.backward()
+        if world > 1:
+            hdist.allreduce_gradients(params, world)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- device-resident number -------------------------------------------------------------
+    for _ in range(args.warmup):
+        train_step(dev_batch)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = H.launch_count()
+    ms = timed(lambda: train_step(dev_batch), args.steps)
+    launches = H.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * n_rays / (ms_per_step * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step --------------------
+    loss_host = torch.empty((), pin_memory=True)
+    keys = ("rays_o", "rays_d", "t_rand", "true_rgb", "true_mask")
+    h2d = sum(pinned[k].numel() * 4 for k in keys)
+
+    def e2e_step():
+        b = {k: pinned[k].to(device, non_blocking=True) for k in keys}
+        loss = train_step(b)
+        loss_host.copy_(loss.detach(), non_blocking=False)
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps) / args.steps
+    e2e_value = world * n_rays / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel family (the MLP contractions), rank 0, separate pass ----
+    roof, comp = None, None
+    if rank == 0:
+        roof = mlp_roofline(H, lambda: train_step(dev_batch), n_rays)
+        comp = compositor_roofline(H, device)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rps, dt, cores = time_cpu(min(n_rays, 512), 3, 1)
+        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
+               "sample": "3 steps of one %d-ray batch (oracle/honerf_oracle.py, torch CPU)" % min(n_rays, 512)}
+    if rank == 0:
+        line = {
+            "metric": "rays/sec render fwd+bwd (64+64 samples), object-field train step",
+            "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"simt_fp32": "f32", "tc_tf32": "tf32", "tc_bf16x3": "bf16x3", "tc_bf16": "bf16"}[args.precision],
+            "data": "synthetic",
+            "config": {"workload": "obj-field train step (BASELINE configs[2]): %d rays/GPU x (64+64) samples, "
+                                   "masked-L1+BCE+eikonal loss, 2nd-order bwd, Adam" % n_rays,
+                       "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
+                       "l2": "per-step activation stash (~2 GB at 512 rays) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu,
+            "mlp_flops_per_ray": FLOPS_PER_RAY_TRAIN,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def mlp_roofline(H, step_fn, n_rays):
+    """Tensor roofline of the MLP contractions: algorithmic FLOPs (per ray
+    112 F_o + 128 (6 F_o + 3 C_o)) over the summed device time of the library's GEMM launches, taken
+    with CUDA events recorded on the launching stream inside the library (hn_timing_*)."""
+    from honerf_b200 import _lib
+    peaks, src = measured_peaks()
+    if not hasattr(_lib.lib, "hn_timing_enable"):
+        return None
+    _lib.lib.hn_timing_enable(1)
+    step_fn()
+    torch.cuda.synchronize()
+    _lib.lib.hn_timing_reset()
+    reps = 2
+    for _ in range(reps):
+        step_fn()
+    torch.cuda.synchronize()
+    import ctypes
+    ms, n = ctypes.c_double(0), ctypes.c_int64(0)
+    _lib.lib.hn_timing_collect(ctypes.byref(ms), ctypes.byref(n))
+    _lib.lib.hn_timing_enable(0)
+    if n.value == 0 or ms.value <= 0:
+        return None
+    flops = reps * n_rays * FLOPS_PER_RAY_TRAIN
+    achieved = flops / (ms.value * 1e-3) / 1e12
+    peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    return {"bound": "tensor", "kernel": "MLP contractions (all GEMM launches of one step)", "achieved": achieved,
+            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": src + ", sustained bf16",
+            "gemm_launches_per_step": n.value // reps, "gemm_ms_per_step": ms.value / reps,
+            "algorithmic_flops_per_step": flops // reps}
+
+
+def compositor_roofline(H, device, n_rays=1 << 18, n=128):
+    """HBM roofline of the compositor alone: 2^18 rays x 128 samples, fwd 40 B + bwd 64 B per sample."""
+    from honerf_b200 import ops
+    peaks, src = measured_peaks()
+    N = n_rays * n
+    g = torch.Generator(device=device).manual_seed(0)
+    sdf = (torch.rand(N, 1, device=device, generator=g) - 0.3).requires_grad_(True)
+    nrm = torch.randn(N, 3, device=device, generator=g).requires_grad_(True)
+    rgb = torch.rand(N, 3, device=device, generator=g).requires_grad_(True)
+    dists = torch.full((n_rays, n), 1.1 / 128, device=device)
+    d = F.normalize(torch.randn(n_rays, 3, device=device, generator=g), dim=-1)
+    var = torch.tensor(0.3, device=device, requires_grad=True)
+    res = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from honerf_b200._lib import lib, check
+    import ctypes
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    w = torch.empty(n_rays, n, device=device); c = torch.empty_like(w)
+    col = torch.empty(n_rays, 3, device=device); ws = torch.empty(n_rays, device=device)
+    wm = torch.empty_like(ws); ek = torch.empty_like(ws)
+    ds, dn, dr = torch.empty(N, device=device), torch.empty(N, 3, device=device), torch.empty(N, 3, device=device)
+    dv = torch.zeros(1, device=device)
+    gc = torch.randn(n_rays, 3, device=device)
+
+    def fwd():
+        check(lib.hn_neus_composite_fwd(P(sdf), P(nrm), P(rgb), P(dists), P(d), P(var), n_rays, n, 1, P(w), P(c), None,
+                                        P(col), P(ws), P(wm), P(ek), st), "fwd")
+
+    def bwd():
+        check(lib.hn_neus_composite_bwd(P(sdf), P(nrm), P(rgb), P(dists), P(d), P(var), P(w), n_rays, n, 1, P(gc), None,
+                                        None, None, P(ds), P(dn), P(dr), None, P(dv), st), "bwd")
+
+    for name, fn, bytes_per_sample in (("fwd", fwd, 40), ("bwd", bwd, 64)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        gbs = N * bytes_per_sample / (ms * 1e-3) / 1e9
+        res[name] = {"ms": ms, "achieved": gbs, "unit": "GB/s", "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"],
+                     "algorithmic_bytes": N * bytes_per_sample}
+    res["bound"] = "hbm"
+    res["workload"] = "%d rays x %d samples (3.4 GB fwd working set > L2)" % (n_rays, n)
+    res["peak_source"] = src
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--rays", type=int, default=512, help="rays per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="simt_fp32", choices=["simt_fp32", "tc_tf32", "tc_bf16x3", "tc_bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

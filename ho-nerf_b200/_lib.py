@@ -45,6 +45,9 @@ PROTOTYPES = {
     "hn_last_error": (ctypes.c_char_p, []),
     "hn_version": (c_int, []),
     "hn_launch_count": (c_int64, []),
+    "hn_timing_enable": (c_int, [c_int]),
+    "hn_timing_reset": (c_int, []),
+    "hn_timing_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "hn_wn_pack": (c_int, [P, P, c_int, c_int, c_int, c_float, P, P]),
     "hn_wn_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     "hn_sdf_obj_stash_floats": (c_int64, [c_int64]),

@@ -68,4 +68,13 @@ int sm_count();
 // bump the process-wide kernel-launch counter reported by hn_launch_count()
 void count_launch(int n = 1);
 
+// Opt-in device timing of the dense-contraction launches (hn_timing_* in the C ABI): when enabled,
+// a pair of CUDA events is recorded on the launching stream around every GEMM launch.
+struct TimingScope {
+    cudaStream_t stream;
+    int slot;
+    explicit TimingScope(cudaStream_t s);
+    ~TimingScope();
+};
+
 }  // namespace hn

@@ -292,7 +292,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream, int k_splits = 1) {
         a.k_chunk = chunk;
         grid.z = (unsigned)ceil_div(g.K, chunk);
     }
-    gemm_simt_kernel<A_KMAJ, B_KMAJ, EPI><<<grid, GTHREADS, 0, stream>>>(a);
+    {
+        TimingScope ts(stream);
+        gemm_simt_kernel<A_KMAJ, B_KMAJ, EPI><<<grid, GTHREADS, 0, stream>>>(a);
+    }
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -1,5 +1,7 @@
 // Library runtime: error text, launch counter, device info, weight-norm pack/backward, column sums.
 #include <atomic>
+#include <mutex>
+#include <vector>
 #include <stdarg.h>
 #include <string.h>
 
@@ -19,6 +21,29 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_timing_on{0};
+static std::mutex g_timing_mu;
+static std::vector<cudaEvent_t> g_ev_start, g_ev_stop;
+static size_t g_ev_used = 0;
+
+TimingScope::TimingScope(cudaStream_t s) : stream(s), slot(-1) {
+    if (!g_timing_on.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (g_ev_used == g_ev_start.size()) {
+        cudaEvent_t a, b;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        g_ev_start.push_back(a);
+        g_ev_stop.push_back(b);
+    }
+    slot = (int)g_ev_used++;
+    cudaEventRecord(g_ev_start[slot], stream);
+}
+TimingScope::~TimingScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    cudaEventRecord(g_ev_stop[slot], stream);
+}
 
 int sm_count() {
     static int cached = 0;
@@ -114,6 +139,26 @@ extern "C" {
 const char* hn_last_error(void) { return g_err; }
 int hn_version(void) { return 100; }
 int64_t hn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int hn_timing_enable(int on) { g_timing_on.store(on ? 1 : 0); return HN_OK; }
+int hn_timing_reset(void) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    g_ev_used = 0;
+    return HN_OK;
+}
+int hn_timing_collect(double* total_ms, int64_t* n_launches) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    double tot = 0.0;
+    for (size_t i = 0; i < g_ev_used; ++i) {
+        float ms = 0.0f;
+        HN_CHECK_CUDA(cudaEventSynchronize(g_ev_stop[i]));
+        HN_CHECK_CUDA(cudaEventElapsedTime(&ms, g_ev_start[i], g_ev_stop[i]));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (n_launches) *n_launches = (int64_t)g_ev_used;
+    return HN_OK;
+}
 
 int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld, float post_scale,
                float* W, hn_stream_t stream) {

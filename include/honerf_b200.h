@@ -40,6 +40,13 @@ HN_API int hn_version(void);
 /* Number of kernels this library has launched on behalf of the calling process (all streams). */
 HN_API int64_t hn_launch_count(void);
 
+/* Profiling aid for bench.py's roofline: when enabled, CUDA events are recorded on the launching
+ * stream around every dense-contraction (GEMM) launch; collect() synchronises them and returns the
+ * summed device time and the number of launches since the last reset. */
+HN_API int hn_timing_enable(int on);
+HN_API int hn_timing_reset(void);
+HN_API int hn_timing_collect(double* total_ms, int64_t* n_launches); /* HOST pointers */
+
 /* ---------------------------------------------------------------------------------------------
  * Weight-normalised MLP parameters (nn.utils.weight_norm, dim=0:
  * utils/fields.py:120-121, 216-217, 307-308, 382-383).

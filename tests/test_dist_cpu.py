@@ -1,0 +1,45 @@
+"""world_size-2 gloo test of the multi-GPU plumbing (ray sharding + flat gradient all-reduce)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from honerf_b200 import dist as hdist
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7)),
+              torch.nn.Parameter(torch.randn(2))]
+    # rank-dependent gradients on the first two, none on the third
+    params[0].grad = torch.full((5, 3), float(rank + 1))
+    params[1].grad = torch.arange(7.0) * (rank + 1)
+    n = hdist.allreduce_gradients(params, world)
+    lo, hi = hdist.shard_rays(11, rank, world)
+    out[rank] = (n, params[0].grad.clone(), params[1].grad.clone(), params[2].grad, (lo, hi))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        n, g0, g1, g2, shard = out[r]
+        assert n == 22
+        assert torch.allclose(g0, torch.full((5, 3), 1.5))
+        assert torch.allclose(g1, torch.arange(7.0) * 1.5)
+        assert g2 is None
+    assert out[0][4] == (0, 6) and out[1][4] == (6, 11)
