@@ -181,6 +181,14 @@ HN_API int hn_neus_composite_bwd(const float* sdf, const float* normal, const fl
                                  float* d_normal, float* d_rgb, float* d_rays_d,
                                  float* d_variance, hn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Diagnostics: C[M,N] (fp32) = A[M,K] * B[N,K]^T with fp16 (or bf16) operands on tcgen05 tensor cores
+ * (fp32 accumulation in TMEM).  Self-test of the descriptors / TMEM / mbarrier plumbing shared by the
+ * fused field kernels.  16 <= N <= 256, N % 16 == 0, K % 64 == 0.
+ * ------------------------------------------------------------------------------------------- */
+HN_API int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
+                           hn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
