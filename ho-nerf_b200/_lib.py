@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhonerf_b200.so")
 
 HN_MAX_LAYERS = 12
-HN_SIMT_FP32, HN_TC_TF32, HN_TC_BF16X3, HN_TC_BF16 = 0, 1, 2, 3
+HN_SIMT_FP32, HN_TC_TF32, HN_TC_TF32X3 = 0, 1, 2
 HN_WS_SDF_ONLY, HN_WS_FWD, HN_WS_BWD = 0, 1, 2
 
 
@@ -21,7 +21,9 @@ class hn_mlp_t(Structure):
                 ("out_dim", c_int32 * HN_MAX_LAYERS),
                 ("ld", c_int32 * HN_MAX_LAYERS),
                 ("W", c_void_p * HN_MAX_LAYERS),
-                ("b", c_void_p * HN_MAX_LAYERS)]
+                ("b", c_void_p * HN_MAX_LAYERS),
+                ("WT", c_void_p * HN_MAX_LAYERS),
+                ("ldT", c_int32 * HN_MAX_LAYERS)]
 
 
 class hn_mlp_grad_t(Structure):
@@ -48,7 +50,7 @@ PROTOTYPES = {
     "hn_timing_enable": (c_int, [c_int]),
     "hn_timing_reset": (c_int, []),
     "hn_timing_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
-    "hn_wn_pack": (c_int, [P, P, c_int, c_int, c_int, c_float, P, P]),
+    "hn_wn_pack": (c_int, [P, P, c_int, c_int, c_int, c_float, P, P, c_int, P]),
     "hn_wn_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     "hn_sdf_obj_stash_floats": (c_int64, [c_int64]),
     "hn_sdf_obj_ws_floats": (c_int64, [c_int64, c_int]),
@@ -63,6 +65,7 @@ PROTOTYPES = {
     "hn_color_obj_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, P, P, c_int64, P, _grad_p, P, c_int64,
                                  c_int, P]),
     "hn_tc_gemm_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "hn_gemm_test": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "hn_ray_points": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "hn_mid_points": (c_int, [P, P, P, c_int64, c_int, c_float, P, P, P]),
     "hn_up_sample": (c_int, [P, P, P, c_int64, c_int, c_int, c_float, P, P]),

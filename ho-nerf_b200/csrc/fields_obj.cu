@@ -3,7 +3,7 @@
 // Replaces utils/fields.py:316-347 (SDFNetwork_OBJ.forward/.sdf/.gradient) and :387-405
 // (RenderingNetwork_OBJ.forward) plus everything autograd derives from them.
 #include "common.cuh"
-#include "gemm_simt.cuh"
+#include "gemm_dispatch.cuh"
 #include "fields_common.cuh"
 
 namespace hn {
@@ -174,7 +174,7 @@ static inline unsigned blocks_for(int64_t work, int threads) { return (unsigned)
 
 // forward trunk: E -> H7 (writes every H when `stash_all`, otherwise ping-pongs between 2 buffers)
 static int obj_trunk_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float* E, float* const H[8],
-                         cudaStream_t s) {
+                         cudaStream_t s, int precision) {
     enc_obj_kernel<<<blocks_for(n * 64, 256), 256, 0, s>>>(pts, n, E, H[3]);
     count_launch();
     HN_CHECK_LAUNCH();
@@ -186,7 +186,7 @@ static int obj_trunk_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float* 
         g.M = (int)n; g.N = m->out_dim[l]; g.K = m->in_dim[l];
         g.C = H[l]; g.ldc = 256;
         g.bias = m->b[l];
-        HN_PROPAGATE((launch_gemm<true, true, EPI_BIAS_SOFTPLUS>(g, s)));
+        HN_PROPAGATE((gemm_nt<EPI_BIAS_SOFTPLUS>(g, s, precision, ROLE_VALUE)));
     }
     return HN_OK;
 }
@@ -211,7 +211,7 @@ int64_t hn_sdf_obj_ws_floats(int64_t n, int kind) {
 int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_scale, float* sdf,
                    float* ws, int64_t ws_floats, int precision, hn_stream_t stream) {
     HN_PROPAGATE(check_obj_sdf_mlp(mlp));
-    HN_REQUIRE(precision == HN_SIMT_FP32, "hn_sdf_obj_sdf: precision %d not built", precision);
+    HN_REQUIRE(precision_supported(precision), "hn_sdf_obj_sdf: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
     HN_REQUIRE(pts && sdf && ws && ws_floats >= hn_sdf_obj_ws_floats(n, HN_WS_SDF_ONLY) && aligned16(ws),
@@ -222,7 +222,7 @@ int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
     float* P1 = P0 + n * 256;
     float* A4 = P1 + n * 256;
     float* H[8] = {P0, P1, P0, A4, P0, P1, P0, P1};
-    HN_PROPAGATE(obj_trunk_fwd(mlp, pts, n, E, H, s));
+    HN_PROPAGATE(obj_trunk_fwd(mlp, pts, n, E, H, s, precision));
     sdf_head_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(H[7], mlp->W[8], mlp->b[8], inv_scale, n, sdf);
     count_launch();
     HN_CHECK_LAUNCH();
@@ -234,7 +234,7 @@ int hn_sdf_obj_fwd(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
                    float* ws, int64_t ws_floats, int precision, hn_stream_t stream) {
     (void)ws; (void)ws_floats;
     HN_PROPAGATE(check_obj_sdf_mlp(mlp));
-    HN_REQUIRE(precision == HN_SIMT_FP32, "hn_sdf_obj_fwd: precision %d not built", precision);
+    HN_REQUIRE(precision_supported(precision), "hn_sdf_obj_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
     HN_REQUIRE(pts && sdf && feat && normal && stash, "hn_sdf_obj_fwd: null pointer");
@@ -242,7 +242,7 @@ int hn_sdf_obj_fwd(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
     HN_REQUIRE(ld_feat >= 256 && ld_feat % 4 == 0 && aligned16(feat), "feat must be 16B aligned with ld%%4==0");
     cudaStream_t s = (cudaStream_t)stream;
     ObjSdfStash st(stash, n);
-    HN_PROPAGATE(obj_trunk_fwd(mlp, pts, n, st.E, st.H, s));
+    HN_PROPAGATE(obj_trunk_fwd(mlp, pts, n, st.E, st.H, s, precision));
     // output layer: column 0 -> sdf, columns 1..256 -> feature
     sdf_head_kernel<<<blocks_for(n * 32, 256), 256, 0, s>>>(st.H[7], mlp->W[8], mlp->b[8], inv_scale, n, sdf);
     count_launch();
@@ -253,7 +253,7 @@ int hn_sdf_obj_fwd(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
         g.B = mlp->W[8] + mlp->ld[8]; g.ldb = mlp->ld[8];
         g.M = (int)n; g.N = 256; g.K = 256;
         g.C = feat; g.ldc = ld_feat; g.bias = mlp->b[8] + 1;
-        HN_PROPAGATE((launch_gemm<true, true, EPI_STORE>(g, s)));
+        HN_PROPAGATE((gemm_nt<EPI_STORE>(g, s, precision, ROLE_VALUE)));
     }
     // normal sweep
     normal_seed_kernel<<<blocks_for(n * 64, 256), 256, 0, s>>>(st.H[7], mlp->W[8], inv_scale, n, st.D[7]);
@@ -262,20 +262,20 @@ int hn_sdf_obj_fwd(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
     for (int l = 7; l >= 1; --l) {
         GemmArgs g;
         g.A = st.D[l]; g.lda = 256;
-        g.B = mlp->W[l]; g.ldb = mlp->ld[l];
+        g.B = mlp->W[l]; g.ldb = mlp->ld[l]; g.BT = mlp->WT[l]; g.ldbt = mlp->ldT[l];
         g.M = (int)n; g.N = mlp->in_dim[l]; g.K = mlp->out_dim[l];
         g.C = st.D[l - 1]; g.ldc = 256;
         g.aux1 = st.H[l - 1]; g.ldaux1 = 256;
         if (l == 4) { g.nsplit = 193; g.C2 = st.EB; g.ldc2 = 64; }
-        HN_PROPAGATE((launch_gemm<true, false, EPI_MUL_SPRIME>(g, s)));
+        HN_PROPAGATE((gemm_nn<EPI_MUL_SPRIME>(g, s, precision, ROLE_VALUE)));
     }
     {
         GemmArgs g;
         g.A = st.D[0]; g.lda = 256;
-        g.B = mlp->W[0]; g.ldb = mlp->ld[0];
+        g.B = mlp->W[0]; g.ldb = mlp->ld[0]; g.BT = mlp->WT[0]; g.ldbt = mlp->ldT[0];
         g.M = (int)n; g.N = 63; g.K = 256;
         g.C = st.EB; g.ldc = 64; g.aux1 = st.EB; g.ldaux1 = 64;
-        HN_PROPAGATE((launch_gemm<true, false, EPI_ADD_AUX>(g, s)));
+        HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(g, s, precision, ROLE_VALUE)));
     }
     normal_from_eb_kernel<<<blocks_for(n * 3, 256), 256, 0, s>>>(st.E, st.EB, n, normal);
     count_launch();
@@ -288,7 +288,7 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
                    const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision,
                    hn_stream_t stream) {
     HN_PROPAGATE(check_obj_sdf_mlp(mlp));
-    HN_REQUIRE(precision == HN_SIMT_FP32, "hn_sdf_obj_bwd: precision %d not built", precision);
+    HN_REQUIRE(precision_supported(precision), "hn_sdf_obj_bwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
     HN_REQUIRE(stash && d_normal && ws, "hn_sdf_obj_bwd: null pointer");
@@ -312,7 +312,7 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
         g.C = grad->dW[l]; g.ldc = mlp->ld[l];
         int tiles = (int)(ceil_div(out, GBM) * ceil_div(in, GBN));
         int splits = (int)max((int64_t)1, min((int64_t)ceil_div(splits_target, tiles), ceil_div(n, 256)));
-        return launch_gemm<false, false, EPI_ATOMIC>(g, s, splits);
+        return gemm_tn(g, s, precision, splits);
     };
     auto db_sum = [&](const float* X, int64_t ldx, int cols, int l) -> int {
         if (!grad || !grad->db[l]) return HN_OK;
@@ -330,13 +330,13 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
         HN_PROPAGATE(dw_gemm(st.D[l], 256, mlp->out_dim[l], au_prev, ld_prev, mlp->in_dim[l], l));
         GemmArgs g;
         g.A = au_prev; g.lda = ld_prev;
-        g.B = mlp->W[l]; g.ldb = mlp->ld[l];
+        g.B = mlp->W[l]; g.ldb = mlp->ld[l]; g.BT = mlp->WT[l]; g.ldbt = mlp->ldT[l];
         g.M = (int)n; g.N = mlp->out_dim[l]; g.K = mlp->in_dim[l];
         float* out = l == 3 ? AU4 : U[l & 1];
         g.C = out; g.ldc = 256;
         g.aux1 = st.H[l]; g.ldaux1 = 256;
         g.C2 = st.D[l]; g.ldc2 = 256;      // D_l -> X_l in place
-        HN_PROPAGATE((launch_gemm<true, true, EPI_TANGENT>(g, s)));
+        HN_PROPAGATE((gemm_nt<EPI_TANGENT>(g, s, precision)));
         au_prev = out; ld_prev = 256;
     }
     // the normal sweep is seeded with row 0 of the output layer: dW8[0,:] += colsum(U7)*inv_scale
@@ -353,14 +353,14 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
         HN_PROPAGATE(db_sum(dz, ld_dz, mlp->out_dim[l], l));
         GemmArgs g;
         g.A = dz; g.lda = ld_dz;
-        g.B = mlp->W[l]; g.ldb = mlp->ld[l];
+        g.B = mlp->W[l]; g.ldb = mlp->ld[l]; g.BT = mlp->WT[l]; g.ldbt = mlp->ldT[l];
         g.M = (int)n; g.N = mlp->in_dim[l]; g.K = mlp->out_dim[l];
         float* out = DZ[l & 1];
         g.C = out; g.ldc = 256;
         g.aux1 = st.H[l - 1]; g.ldaux1 = 256;
         g.aux2 = st.D[l - 1]; g.ldaux2 = 256;   // X_{l-1}
         if (l == 4) { g.nsplit = 193; g.C2 = DE; g.ldc2 = 64; }
-        HN_PROPAGATE((launch_gemm<true, false, EPI_REVERSE>(g, s)));
+        HN_PROPAGATE((gemm_nn<EPI_REVERSE>(g, s, precision)));
         dz = out; ld_dz = 256;
     }
     HN_PROPAGATE(dw_gemm(dz, 256, 256, st.E, 64, 63, 0));
@@ -368,10 +368,10 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
     if (d_pts) {
         GemmArgs g;
         g.A = dz; g.lda = 256;
-        g.B = mlp->W[0]; g.ldb = mlp->ld[0];
+        g.B = mlp->W[0]; g.ldb = mlp->ld[0]; g.BT = mlp->WT[0]; g.ldbt = mlp->ldT[0];
         g.M = (int)n; g.N = 63; g.K = 256;
         g.C = DE; g.ldc = 64; g.aux1 = DE; g.ldaux1 = 64;
-        HN_PROPAGATE((launch_gemm<true, false, EPI_ADD_AUX>(g, s)));
+        HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(g, s, precision)));
         dx_obj_kernel<<<blocks_for(n * 3, 256), 256, 0, s>>>(st.E, DE, st.EB, d_normal, n, d_pts);
         count_launch();
         HN_CHECK_LAUNCH();
@@ -481,7 +481,7 @@ int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs, c
                      int64_t ld_feat, const float* normal, int64_t n, float* rgb, float* stash,
                      int64_t stash_floats, int precision, hn_stream_t stream) {
     HN_PROPAGATE(check_color_obj_mlp(mlp));
-    HN_REQUIRE(precision == HN_SIMT_FP32, "hn_color_obj_fwd: precision %d not built", precision);
+    HN_REQUIRE(precision_supported(precision), "hn_color_obj_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
     HN_REQUIRE(pts && dirs && feat && normal && rgb && stash, "hn_color_obj_fwd: null pointer");
@@ -496,15 +496,15 @@ int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs, c
     for (int l = 0; l < 4; ++l) {
         GemmArgs g;
         g.A = l == 0 ? CIN : R[l - 1]; g.lda = l == 0 ? CIN_LD : 256;
-        g.B = mlp->W[l]; g.ldb = mlp->ld[l];
+        g.B = mlp->W[l]; g.ldb = mlp->ld[l]; g.BT = mlp->WT[l]; g.ldbt = mlp->ldT[l];
         g.M = (int)n; g.N = 256; g.K = mlp->in_dim[l];
         g.C = R[l]; g.ldc = 256; g.bias = mlp->b[l];
-        HN_PROPAGATE((launch_gemm<true, true, EPI_BIAS_RELU>(g, s)));
+        HN_PROPAGATE((gemm_nt<EPI_BIAS_RELU>(g, s, precision)));
     }
     GemmArgs g;
-    g.A = R[3]; g.lda = 256; g.B = mlp->W[4]; g.ldb = mlp->ld[4];
+    g.A = R[3]; g.lda = 256; g.B = mlp->W[4]; g.ldb = mlp->ld[4]; g.BT = mlp->WT[4]; g.ldbt = mlp->ldT[4];
     g.M = (int)n; g.N = 3; g.K = 256; g.C = rgb; g.ldc = 3; g.bias = mlp->b[4];
-    HN_PROPAGATE((launch_gemm<true, true, EPI_BIAS_SIGMOID>(g, s)));
+    HN_PROPAGATE((gemm_nt<EPI_BIAS_SIGMOID>(g, s, precision)));
     return HN_OK;
 }
 
@@ -513,7 +513,7 @@ int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* 
                      const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision,
                      hn_stream_t stream) {
     HN_PROPAGATE(check_color_obj_mlp(mlp));
-    HN_REQUIRE(precision == HN_SIMT_FP32, "hn_color_obj_bwd: precision %d not built", precision);
+    HN_REQUIRE(precision_supported(precision), "hn_color_obj_bwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
     HN_REQUIRE(stash && rgb && d_rgb && ws, "hn_color_obj_bwd: null pointer");
@@ -534,7 +534,7 @@ int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* 
         g.C = grad->dW[l]; g.ldc = mlp->ld[l];
         int tiles = (int)(ceil_div(out, GBM) * ceil_div(in, GBN));
         int splits = (int)max((int64_t)1, min((int64_t)ceil_div(splits_target, tiles), ceil_div(n, 256)));
-        return launch_gemm<false, false, EPI_ATOMIC>(g, s, splits);
+        return gemm_tn(g, s, precision, splits);
     };
     sigmoid_bwd_kernel<<<blocks_for(n * 4, 256), 256, 0, s>>>(rgb, d_rgb, n, DZ4);
     count_launch();
@@ -545,19 +545,19 @@ int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* 
         HN_PROPAGATE(dw_gemm(dz, ld_dz, mlp->out_dim[l], R[l - 1], 256, 256, l));
         if (grad && grad->db[l]) HN_PROPAGATE(launch_colsum(dz, ld_dz, n, mlp->out_dim[l], 1.0f, grad->db[l], s));
         GemmArgs g;
-        g.A = dz; g.lda = ld_dz; g.B = mlp->W[l]; g.ldb = mlp->ld[l];
+        g.A = dz; g.lda = ld_dz; g.B = mlp->W[l]; g.ldb = mlp->ld[l]; g.BT = mlp->WT[l]; g.ldbt = mlp->ldT[l];
         g.M = (int)n; g.N = 256; g.K = mlp->out_dim[l];
         g.C = DZ[l & 1]; g.ldc = 256; g.aux1 = R[l - 1]; g.ldaux1 = 256;
-        HN_PROPAGATE((launch_gemm<true, false, EPI_RELU_BWD>(g, s)));
+        HN_PROPAGATE((gemm_nn<EPI_RELU_BWD>(g, s, precision)));
         dz = DZ[l & 1]; ld_dz = 256;
     }
     HN_PROPAGATE(dw_gemm(dz, 256, 256, CIN, CIN_LD, CIN_DIM, 0));
     if (grad && grad->db[0]) HN_PROPAGATE(launch_colsum(dz, 256, n, 256, 1.0f, grad->db[0], s));
     if (d_pts || d_dirs || d_feat || d_normal) {
         GemmArgs g;
-        g.A = dz; g.lda = 256; g.B = mlp->W[0]; g.ldb = mlp->ld[0];
+        g.A = dz; g.lda = 256; g.B = mlp->W[0]; g.ldb = mlp->ld[0]; g.BT = mlp->WT[0]; g.ldbt = mlp->ldT[0];
         g.M = (int)n; g.N = CIN_DIM; g.K = 256; g.C = DCIN; g.ldc = CIN_LD;
-        HN_PROPAGATE((launch_gemm<true, false, EPI_STORE>(g, s)));
+        HN_PROPAGATE((gemm_nn<EPI_STORE>(g, s, precision)));
         color_obj_input_bwd_kernel<<<blocks_for(n * 265, 256), 256, 0, s>>>(CIN, DCIN, n, d_pts, d_dirs, d_feat,
                                                                            ld_dfeat, d_normal);
         count_launch();

@@ -28,6 +28,7 @@ enum Epi {
 struct GemmArgs {
     const float* A = nullptr; int64_t lda = 0;
     const float* B = nullptr; int64_t ldb = 0;
+    const float* BT = nullptr; int64_t ldbt = 0;   // optional transposed copy of B (d @ W on tensor cores)
     int M = 0, N = 0, K = 0;
     float* C = nullptr; int64_t ldc = 0;
     float* C2 = nullptr; int64_t ldc2 = 0;

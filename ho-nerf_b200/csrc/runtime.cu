@@ -61,17 +61,27 @@ int sm_count() {
 // ---- weight norm ---------------------------------------------------------------------------
 // one warp per output row
 __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, int out_dim,
-                               int in_dim, int ld, float post_scale, float* __restrict__ W) {
+                               int in_dim, int ld, float post_scale, float* __restrict__ W,
+                               float* __restrict__ WT, int ldT) {
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
-    if (row >= out_dim) return;
+    if (row >= ldT && row >= out_dim) return;
+    if (row >= out_dim) {            // zero padding columns of the transposed copy
+        if (WT && row < ldT)
+            for (int k = lane; k < in_dim; k += 32) WT[(int64_t)k * ldT + row] = 0.0f;
+        return;
+    }
     const float* vr = v + (int64_t)row * in_dim;
     float ss = 0.0f;
     for (int k = lane; k < in_dim; k += 32) ss = fmaf(vr[k], vr[k], ss);
     ss = warp_sum(ss);
     float sc = post_scale * (g[row] / sqrtf(ss));
     float* wr = W + (int64_t)row * ld;
-    for (int k = lane; k < ld; k += 32) wr[k] = k < in_dim ? vr[k] * sc : 0.0f;
+    for (int k = lane; k < ld; k += 32) {
+        float w = k < in_dim ? vr[k] * sc : 0.0f;
+        wr[k] = w;
+        if (WT && k < in_dim) WT[(int64_t)k * ldT + row] = w;
+    }
 }
 
 __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
@@ -161,10 +171,12 @@ int hn_timing_collect(double* total_ms, int64_t* n_launches) {
 }
 
 int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld, float post_scale,
-               float* W, hn_stream_t stream) {
+               float* W, float* WT, int ldT, hn_stream_t stream) {
     HN_REQUIRE(v && g && W && out_dim > 0 && in_dim > 0 && ld >= in_dim, "hn_wn_pack: bad arguments");
-    wn_pack_kernel<<<(unsigned)ceil_div((int64_t)out_dim * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        v, g, out_dim, in_dim, ld, post_scale, W);
+    HN_REQUIRE(!WT || ldT >= out_dim, "hn_wn_pack: ldT too small");
+    int rows = WT ? (ldT > out_dim ? ldT : out_dim) : out_dim;
+    wn_pack_kernel<<<(unsigned)ceil_div((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        v, g, out_dim, in_dim, ld, post_scale, W, WT, WT ? ldT : 0);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -100,3 +100,29 @@ extern "C" int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K
     HN_CHECK_LAUNCH();
     return HN_OK;
 }
+
+#include "gemm_dispatch.cuh"
+
+extern "C" int hn_gemm_test(int layout, int passes, int M, int N, int K, const float* A, int64_t lda,
+                            const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                            hn_stream_t stream) {
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.bias = bias;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int splits = 37;
+    if (layout == 0) {
+        if (passes == 0) return launch_gemm<true, true, EPI_STORE>(g, s);
+        if (passes == 1) return launch_gemm_tc<false, 1, EPI_STORE>(g, s);
+        if (passes == 3) return launch_gemm_tc<false, 3, EPI_STORE>(g, s);
+    } else if (layout == 1) {
+        if (passes == 0) return launch_gemm<true, false, EPI_STORE>(g, s);
+        if (passes == 1) return launch_gemm_tc<true, 1, EPI_STORE>(g, s);
+        if (passes == 3) return launch_gemm_tc<true, 3, EPI_STORE>(g, s);
+    } else if (layout == 2) {
+        if (passes == 0) return launch_gemm<false, false, EPI_ATOMIC>(g, s, splits);
+        if (passes == 1) return launch_gemm_tc_tn<1>(g, s, splits);
+        if (passes == 3) return launch_gemm_tc_tn<3>(g, s, splits);
+    }
+    set_error("hn_gemm_test: unsupported layout/passes %d/%d", layout, passes);
+    return HN_ERR_UNSUPPORTED;
+}

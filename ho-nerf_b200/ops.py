@@ -8,13 +8,12 @@ import torch
 from . import _lib
 from ._lib import HN_SIMT_FP32, HN_WS_BWD, HN_WS_SDF_ONLY, check, hn_mlp_grad_t, hn_mlp_t, lib
 
-_PRECISIONS = {"simt_fp32": _lib.HN_SIMT_FP32, "tc_tf32": _lib.HN_TC_TF32,
-               "tc_bf16x3": _lib.HN_TC_BF16X3, "tc_bf16": _lib.HN_TC_BF16}
+_PRECISIONS = {"simt_fp32": _lib.HN_SIMT_FP32, "tc_tf32": _lib.HN_TC_TF32, "tc_tf32x3": _lib.HN_TC_TF32X3}
 _default_precision = HN_SIMT_FP32
 
 
 def set_default_precision(name):
-    """'simt_fp32' (verification path) | 'tc_tf32' | 'tc_bf16x3' | 'tc_bf16'."""
+    """'simt_fp32' (verification path) | 'tc_tf32' | 'tc_tf32x3' (split operands on the SDF value trunk)."""
     global _default_precision
     _default_precision = _PRECISIONS[name]
 
@@ -65,6 +64,14 @@ class PackedMLP:
             self.offsets.append(off)
             off += o * ld
         self.total = off
+        self.ldTs = [_round4(o) for (_, o) in self.dims]
+        self.offsetsT = []
+        off = 0
+        for (i, o), ldT in zip(self.dims, self.ldTs):
+            self.offsetsT.append(off)
+            off += i * ldT
+        self.totalT = off
+        self.WT = None
         self.W = None
         self.bias = None
         self.struct = None
@@ -81,6 +88,7 @@ class PackedMLP:
         _require_cuda(self.layers[0][1], "PackedMLP")
         if self.W is None or self.W.device != dev:
             self.W = torch.empty(self.total, device=dev, dtype=torch.float32)
+            self.WT = torch.empty(self.totalT, device=dev, dtype=torch.float32)
         st = hn_mlp_t()
         st.n_layers = len(self.layers)
         keep = []
@@ -89,10 +97,13 @@ class PackedMLP:
             keep.append((gd, vd, bd))
             i, o = self.dims[l]
             Wl = self.W[self.offsets[l]: self.offsets[l] + o * self.lds[l]]
+            WTl = self.WT[self.offsetsT[l]: self.offsetsT[l] + i * self.ldTs[l]]
             check(lib.hn_wn_pack(_ptr(vd), _ptr(gd), o, i, self.lds[l], self.post_scales[l], _ptr(Wl),
-                                 _stream(vd)), "hn_wn_pack")
+                                 _ptr(WTl), self.ldTs[l], _stream(vd)), "hn_wn_pack")
             st.in_dim[l], st.out_dim[l], st.ld[l] = i, o, self.lds[l]
             st.W[l] = Wl.data_ptr()
+            st.WT[l] = WTl.data_ptr()
+            st.ldT[l] = self.ldTs[l]
             st.b[l] = bd.data_ptr()
         self._keep = keep
         self.struct = st

@@ -32,8 +32,12 @@ typedef void* hn_stream_t; /* cudaStream_t */
 enum hn_status { HN_OK = 0, HN_ERR_ARG = -1, HN_ERR_CUDA = -2, HN_ERR_UNSUPPORTED = -3 };
 
 /* Arithmetic of the dense contractions.  HN_SIMT_FP32 is the verification path (fp32 FFMA);
- * the HN_TC_* values run on tcgen05 tensor cores with fp32 accumulation in TMEM. */
-enum hn_precision { HN_SIMT_FP32 = 0, HN_TC_TF32 = 1, HN_TC_BF16X3 = 2, HN_TC_BF16 = 3 };
+ * the HN_TC_* values run on tcgen05 tensor cores with fp32 accumulation in TMEM:
+ *   HN_TC_TF32   every contraction with single-pass TF32 operands (fast; ~1e-3 relative per layer);
+ *   HN_TC_TF32X3 every contraction with split (hi+lo) TF32 operands -- three MMAs per product,
+ *                ~fp32 accuracy; the mode that meets the parity tolerances (1e-3 abs on colour/SDF,
+ *                1e-2 relative on gradients) with margin. */
+enum hn_precision { HN_SIMT_FP32 = 0, HN_TC_TF32 = 1, HN_TC_TF32X3 = 2 };
 
 HN_API const char* hn_last_error(void);
 HN_API int hn_version(void);
@@ -60,6 +64,10 @@ typedef struct hn_mlp {
     int32_t ld[HN_MAX_LAYERS];     /* leading dimension of W[l], >= round_up(in_dim, 4) */
     const float* W[HN_MAX_LAYERS]; /* effective weights g*v/||v|| (times post_scale), [out, ld] */
     const float* b[HN_MAX_LAYERS]; /* bias [out] */
+    /* transposed copy [in, ldT] (ldT >= round_up(out, 4), zero padded): the tensor-core path reads
+     * both x @ W^T and d @ W as K-major operands.  May be NULL for HN_SIMT_FP32. */
+    const float* WT[HN_MAX_LAYERS];
+    int32_t ldT[HN_MAX_LAYERS];
 } hn_mlp_t;
 
 typedef struct hn_mlp_grad {
@@ -67,10 +75,11 @@ typedef struct hn_mlp_grad {
     float* db[HN_MAX_LAYERS]; /* [out]; ACCUMULATED into */
 } hn_mlp_grad_t;
 
-/* W[o, :in] = post_scale * g[o] * v[o, :] / ||v[o, :]||, padding columns [in, ld) zeroed.
+/* W[o, :in] = post_scale * g[o] * v[o, :] / ||v[o, :]||, padding columns [in, ld) zeroed; when WT
+ * is non-NULL also WT[k, o] = W[o, k] ([in, ldT], padding columns [out, ldT) zeroed).
  * Replaces the per-call `_weight_norm` recomputation of every Linear. */
 HN_API int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld,
-                      float post_scale, float* W, hn_stream_t stream);
+                      float post_scale, float* W, float* WT, int ldT, hn_stream_t stream);
 /* (dv, dg) from dW; dW is the gradient w.r.t. the PACKED weight (so it is
  * multiplied by post_scale first).  dv [out,in] and dg [out] are overwritten. */
 HN_API int hn_wn_bwd(const float* v, const float* g, const float* dW, int out_dim, int in_dim,
@@ -188,6 +197,13 @@ HN_API int hn_neus_composite_bwd(const float* sdf, const float* normal, const fl
  * ------------------------------------------------------------------------------------------- */
 HN_API int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
                            hn_stream_t stream);
+/* One dense contraction through the production kernels, for tests: C [M, ldc] (fp32).
+ *   layout 0: C = A[M,lda] @ B[N,ldb]^T (+ bias[N])      layout 1: C = A[M,lda] @ B[K,ldb]
+ *   layout 2: C += A[K,lda]^T @ B[K,ldb]  (K split over CTAs, atomics; caller zeroes C)
+ *   passes 0: fp32 SIMT, 1: tcgen05 TF32, 3: tcgen05 split TF32. */
+HN_API int hn_gemm_test(int layout, int passes, int M, int N, int K, const float* A, int64_t lda,
+                        const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                        hn_stream_t stream);
 
 #ifdef __cplusplus
 }

