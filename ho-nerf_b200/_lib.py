@@ -52,6 +52,20 @@ PROTOTYPES = {
     "hn_timing_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "hn_wn_pack": (c_int, [P, P, c_int, c_int, c_int, c_float, P, P, c_int, P]),
     "hn_wn_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
+    "hn_wn_pack_gap": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int, P]),
+    "hn_wn_bwd_gap": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, P]),
+    "hn_sdf_hand_stash_floats": (c_int64, [c_int64]),
+    "hn_sdf_hand_ws_floats": (c_int64, [c_int64, c_int]),
+    "hn_sdf_hand_sdf": (c_int, [_mlp_p, P, P, P, c_int64, c_int64, P, P, c_int64, c_int, P]),
+    "hn_sdf_hand_fwd": (c_int, [_mlp_p, P, P, P, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P, c_int64,
+                                c_int, P]),
+    "hn_sdf_hand_bwd": (c_int, [_mlp_p, P, P, P, c_int64, c_int64, P, P, P, c_int64, P, P, c_int64, P, P, P,
+                                _grad_p, P, c_int64, c_int, P]),
+    "hn_color_hand_stash_floats": (c_int64, [c_int64]),
+    "hn_color_hand_ws_floats": (c_int64, [c_int64, c_int]),
+    "hn_color_hand_fwd": (c_int, [_mlp_p, P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P]),
+    "hn_color_hand_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, c_int64, P, c_int64, P, _grad_p, P, c_int64,
+                                  c_int, P]),
     "hn_sdf_obj_stash_floats": (c_int64, [c_int64]),
     "hn_sdf_obj_ws_floats": (c_int64, [c_int64, c_int]),
     "hn_sdf_obj_sdf": (c_int, [_mlp_p, P, c_int64, c_float, P, P, c_int64, c_int, P]),

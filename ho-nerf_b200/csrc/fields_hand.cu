@@ -1,0 +1,661 @@
+// Hand SDF field (HALO pose-conditioned, utils/fields.py:56-177) as ONE operator: value + feature +
+// analytic normal, with the second-order backward to the weights, the points and the bone transforms;
+// and the hand colour field (utils/fields.py:179-240).  Same layer-by-layer structure as fields_obj.cu:
+// the 1386-wide HALO feature is produced once per point into the skip-input row [h3 (256) | feature
+// (1386) | pad 2] (ld 1644), which serves as the input of layer 0 and of the skip layer 4.
+#include "common.cuh"
+#include "fields_common.cuh"
+#include "gemm_dispatch.cuh"
+#include "halo.cuh"
+
+namespace hn {
+
+constexpr int HROW_LD = 1644;        // [h3 256 | feature 1386 | pad 2]
+constexpr int HFEAT_OFF = 256;
+constexpr int HFB_LD = 1388;         // feature cotangent rows
+constexpr int HALO_WARPS = 4;        // points per block (one warp per point)
+
+__device__ __forceinline__ void load_x(const float* pts, int64_t p, float x[3]) {
+    x[0] = pts[p * 3]; x[1] = pts[p * 3 + 1]; x[2] = pts[p * 3 + 2];
+}
+
+// feature rows: out[p, 0:1386] = F(x_p) (lanes 0..20 = joints), staged in smem, written coalesced
+__global__ void __launch_bounds__(HALO_WARPS * 32) halo_feature_kernel(
+    const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp, int64_t n,
+    int64_t ppf, float* __restrict__ out, int64_t ld) {
+    __shared__ float sm[HALO_WARPS][HALO_DIM + 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * HALO_WARPS + warp;
+    if (p >= n) return;
+    const int64_t f = p / ppf;
+    float x[3];
+    load_x(pts, p, x);
+    if (lane < HALO_J) {
+        HaloBase b = halo_base(bt_inv + (f * HALO_J + lane) * 16, Tp + (f * HALO_J + lane) * 3, x, lane);
+        halo_feature(b, &sm[warp][lane * HALO_F]);
+    }
+    __syncwarp();
+    float* o = out + p * ld;
+    for (int i = lane; i < HALO_DIM; i += 32) o[i] = sm[warp][i];
+    if (lane < 2) o[HALO_DIM + lane] = 0.0f;
+}
+
+// tangent rows: out[p, 0:1386] = F'(x_p) (R dn_p)
+__global__ void __launch_bounds__(HALO_WARPS * 32) halo_tangent_kernel(
+    const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp,
+    const float* __restrict__ dn, int64_t n, int64_t ppf, float* __restrict__ out, int64_t ld) {
+    __shared__ float sm[HALO_WARPS][HALO_DIM + 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * HALO_WARPS + warp;
+    if (p >= n) return;
+    const int64_t f = p / ppf;
+    float x[3], t[3];
+    load_x(pts, p, x);
+    load_x(dn, p, t);
+    if (lane < HALO_J) {
+        const float* M = bt_inv + (f * HALO_J + lane) * 16;
+        HaloBase b = halo_base(M, Tp + (f * HALO_J + lane) * 3, x, lane);
+        float w[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) w[a] = M[a * 4] * t[0] + M[a * 4 + 1] * t[1] + M[a * 4 + 2] * t[2];
+        halo_jvp(b, w, &sm[warp][lane * HALO_F]);
+    }
+    __syncwarp();
+    float* o = out + p * ld;
+    for (int i = lane; i < HALO_DIM; i += 32) o[i] = sm[warp][i];
+    if (lane < 2) o[HALO_DIM + lane] = 0.0f;
+}
+
+// normal[p] = sum_j R_j^T  dF_j/dq^T  FB[p, j]
+__global__ void __launch_bounds__(HALO_WARPS * 32) halo_normal_kernel(
+    const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp,
+    const float* __restrict__ FB, int64_t ld_fb, int64_t n, int64_t ppf, float* __restrict__ normal) {
+    __shared__ float sm[HALO_WARPS][HALO_DIM + 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * HALO_WARPS + warp;
+    if (p >= n) return;
+    const int64_t f = p / ppf;
+    for (int i = lane; i < HALO_DIM; i += 32) sm[warp][i] = FB[p * ld_fb + i];
+    __syncwarp();
+    float x[3], acc[3] = {0.f, 0.f, 0.f};
+    load_x(pts, p, x);
+    if (lane < HALO_J) {
+        const float* M = bt_inv + (f * HALO_J + lane) * 16;
+        HaloBase b = halo_base(M, Tp + (f * HALO_J + lane) * 3, x, lane);
+        float g[3], dummy[3], w[3] = {0.f, 0.f, 0.f};
+        halo_grad_hvp<false>(b, &sm[warp][lane * HALO_F], w, g, dummy);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) acc[a] = M[0 * 4 + a] * g[0] + M[1 * 4 + a] * g[1] + M[2 * 4 + a] * g[2];
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) acc[a] = warp_sum(acc[a]);
+    if (lane < 3) normal[p * 3 + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : acc[2]);
+}
+
+// Backward through the embedding.  DF = cotangent of the feature (first order), FB = feature cotangent
+// of the normal sweep, dn = cotangent of the normal (second order; may be NULL).
+//   dq_j = F'^T DF_j + H_j(FB_j) (R_j dn);   d_x = sum_j R_j^T dq_j
+//   dR_j += dq_j x^T + g_j(FB_j) dn^T ;  dt_j += dq_j ;  dT_j -= dq_j
+// d_bt [frames, 21, 16] (row-major 4x4, last row untouched) and d_T [frames, 21, 3] are ACCUMULATED.
+__global__ void __launch_bounds__(HALO_WARPS * 32) halo_bwd_kernel(
+    const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp,
+    const float* __restrict__ DF, int64_t ld_df, const float* __restrict__ FB, int64_t ld_fb,
+    const float* __restrict__ dn, int64_t n, int64_t ppf, float* __restrict__ d_pts, float* __restrict__ d_bt,
+    float* __restrict__ d_T) {
+    __shared__ float sdf_[HALO_WARPS][HALO_DIM + 2];
+    __shared__ float sfb_[HALO_WARPS][HALO_DIM + 2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * HALO_WARPS + warp;
+    if (p >= n) return;
+    const int64_t f = p / ppf;
+    for (int i = lane; i < HALO_DIM; i += 32) {
+        sdf_[warp][i] = DF ? DF[p * ld_df + i] : 0.0f;
+        sfb_[warp][i] = (dn && FB) ? FB[p * ld_fb + i] : 0.0f;
+    }
+    __syncwarp();
+    float x[3], t[3] = {0.f, 0.f, 0.f}, dx[3] = {0.f, 0.f, 0.f};
+    load_x(pts, p, x);
+    if (dn) load_x(dn, p, t);
+    if (lane < HALO_J) {
+        const float* M = bt_inv + (f * HALO_J + lane) * 16;
+        HaloBase b = halo_base(M, Tp + (f * HALO_J + lane) * 3, x, lane);
+        if (!b.dead) {
+            float gq[3], g2[3] = {0.f, 0.f, 0.f}, hv[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f}, dummy[3];
+            halo_grad_hvp<false>(b, &sdf_[warp][lane * HALO_F], w, gq, dummy);
+            if (dn) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) w[a] = M[a * 4] * t[0] + M[a * 4 + 1] * t[1] + M[a * 4 + 2] * t[2];
+                halo_grad_hvp<true>(b, &sfb_[warp][lane * HALO_F], w, g2, hv);
+            }
+            float dq[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dq[a] = gq[a] + hv[a];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dx[a] = M[0 * 4 + a] * dq[0] + M[1 * 4 + a] * dq[1] + M[2 * 4 + a] * dq[2];
+            if (d_bt) {
+                float* db = d_bt + (f * HALO_J + lane) * 16;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) atomicAdd(&db[a * 4 + c], dq[a] * x[c] + g2[a] * t[c]);
+                    atomicAdd(&db[a * 4 + 3], dq[a]);
+                }
+            }
+            if (d_T) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a) atomicAdd(&d_T[(f * HALO_J + lane) * 3 + a], -dq[a]);
+            }
+        }
+    }
+    if (d_pts) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) dx[a] = warp_sum(dx[a]);
+        if (lane < 3) d_pts[p * 3 + lane] = lane == 0 ? dx[0] : (lane == 1 ? dx[1] : dx[2]);
+    }
+}
+
+// D7[p, c] = s'(H7[p, c]) * w_out0[c]
+__global__ void hand_normal_seed_kernel(const float* __restrict__ H7, const float* __restrict__ w_out0, int64_t n,
+                                        float* __restrict__ D7) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 64) return;
+    int c = (int)(i & 63) * 4;
+    int64_t p = i >> 6;
+    float4 h = ld4(H7 + p * 256 + c);
+    float4 w = ld4(w_out0 + c);
+    st4(D7 + p * 256 + c, make_float4(sprime_from_h(h.x) * w.x, sprime_from_h(h.y) * w.y, sprime_from_h(h.z) * w.z,
+                                      sprime_from_h(h.w) * w.w));
+}
+__global__ void hand_sdf_head_kernel(const float* __restrict__ H7, const float* __restrict__ w_out0,
+                                     const float* __restrict__ b_out, int64_t n, float* __restrict__ sdf) {
+    int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (p >= n) return;
+    float acc = 0.0f;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        int c = (it * 32 + lane) * 4;
+        float4 h = ld4(H7 + p * 256 + c);
+        float4 w = ld4(w_out0 + c);
+        acc += h.x * w.x + h.y * w.y + h.z * w.z + h.w * w.w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sdf[p] = acc + b_out[0];
+}
+__global__ void hand_assemble_dz8_kernel(const float* __restrict__ d_sdf, const float* __restrict__ d_feat,
+                                         int64_t ld_dfeat, int64_t n, float* __restrict__ DZ8) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 260) return;
+    int64_t p = i / 260;
+    int j = (int)(i - p * 260);
+    float v = 0.0f;
+    if (j == 0) v = d_sdf ? d_sdf[p] : 0.0f;
+    else if (j < 257) v = d_feat ? d_feat[p * ld_dfeat + (j - 1)] : 0.0f;
+    DZ8[i] = v;
+}
+// dst[p, 0:cols] = src ? src[p, 0:cols] : 0   (row copies between different leading dimensions)
+__global__ void copy_rows_kernel(const float* __restrict__ src, int64_t ld_src, int64_t n, int cols,
+                                 float* __restrict__ dst, int64_t ld_dst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * cols) return;
+    int64_t p = i / cols;
+    int j = (int)(i - p * cols);
+    dst[p * ld_dst + j] = src ? src[p * ld_src + j] : 0.0f;
+}
+
+struct HandSdfStash {
+    float* HROW;   // [n,1644] = [h3 | feature | pad]
+    float* H[8];   // [n,256] (H[3] aliases HROW, ld 1644)
+    float* D[8];   // [n,256]
+    float* FB;     // [n,1388]
+    static constexpr int64_t kFloatsPerPoint = HROW_LD + 7 * 256 + 8 * 256 + HFB_LD;
+    HandSdfStash(float* base, int64_t n) {
+        float* p = base;
+        HROW = p; p += n * HROW_LD;
+        for (int l = 0; l < 8; ++l) {
+            if (l == 3) { H[l] = HROW; continue; }
+            H[l] = p; p += n * 256;
+        }
+        for (int l = 0; l < 8; ++l) { D[l] = p; p += n * 256; }
+        FB = p;
+    }
+    int64_t ldH(int l) const { return l == 3 ? HROW_LD : 256; }
+};
+
+static int check_hand_sdf_mlp(const hn_mlp_t* m) {
+    HN_REQUIRE(m && m->n_layers == 9, "hand SDF mlp must have 9 layers");
+    static const int in_d[9] = {1386, 256, 256, 256, 1642, 256, 256, 256, 256};
+    static const int out_d[9] = {256, 256, 256, 256, 256, 256, 256, 256, 257};
+    for (int l = 0; l < 9; ++l) {
+        HN_REQUIRE(m->in_dim[l] == in_d[l] && m->out_dim[l] == out_d[l], "hand SDF mlp layer %d is %dx%d, expected %dx%d",
+                   l, m->out_dim[l], m->in_dim[l], out_d[l], in_d[l]);
+        HN_REQUIRE(m->ld[l] >= round_up(in_d[l], 4) && m->ld[l] % 4 == 0, "bad ld for layer %d", l);
+        HN_REQUIRE(m->W[l] && m->b[l] && aligned16(m->W[l]), "layer %d: null or misaligned weights", l);
+    }
+    return HN_OK;
+}
+
+static inline unsigned nblocks(int64_t work, int threads) { return (unsigned)ceil_div(work, threads); }
+
+static void set_w(GemmArgs& g, const hn_mlp_t* m, int l, int col_off = 0) {
+    // weights of layer l, optionally starting at input column col_off (a multiple of 4)
+    g.B = m->W[l] + col_off; g.ldb = m->ld[l];
+    g.BT = m->WT[l] ? m->WT[l] + (int64_t)col_off * m->ldT[l] : nullptr; g.ldbt = m->ldT[l];
+}
+
+// forward trunk: HROW feature -> H7.  H[] / ldH describe where each layer's activation goes.
+static int hand_trunk_fwd(const hn_mlp_t* m, const float* pts, const float* bt_inv, const float* Tp, int64_t n,
+                          int64_t ppf, float* HROW, float* const H[8], cudaStream_t s, int precision) {
+    halo_feature_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, Tp, n, ppf, HROW + HFEAT_OFF,
+                                                                           HROW_LD);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    for (int l = 0; l < 8; ++l) {
+        GemmArgs g;
+        if (l == 0) { g.A = HROW + HFEAT_OFF; g.lda = HROW_LD; }
+        else if (l == 4) { g.A = HROW; g.lda = HROW_LD; }
+        else { g.A = H[l - 1]; g.lda = 256; }
+        set_w(g, m, l);
+        g.M = (int)n; g.N = 256; g.K = m->in_dim[l];
+        g.C = H[l]; g.ldc = (l == 3) ? HROW_LD : 256;
+        g.bias = m->b[l];
+        HN_PROPAGATE((gemm_nt<EPI_BIAS_SOFTPLUS>(g, s, precision, ROLE_VALUE)));
+    }
+    return HN_OK;
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" {
+
+int64_t hn_sdf_hand_stash_floats(int64_t n) { return n * HandSdfStash::kFloatsPerPoint; }
+
+int64_t hn_sdf_hand_ws_floats(int64_t n, int kind) {
+    switch (kind) {
+        case HN_WS_SDF_ONLY: return n * (HROW_LD + 2 * 256);
+        case HN_WS_FWD: return 4;
+        // AU4 [n,1644], U ping-pong 2x256, DZ8 260, DZ ping-pong 2x256, DF [n,1388]
+        case HN_WS_BWD: return n * (HROW_LD + 2 * 256 + 260 + 2 * 256 + HFB_LD);
+        default: return -1;
+    }
+}
+
+int hn_sdf_hand_sdf(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, const float* T_pose, int64_t n,
+                    int64_t pts_per_frame, float* sdf, float* ws, int64_t ws_floats, int precision,
+                    hn_stream_t stream) {
+    HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_sdf: precision %d not supported", precision);
+    HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
+    if (n == 0) return HN_OK;
+    HN_REQUIRE(pts && bt_inv && T_pose && sdf && ws && ws_floats >= hn_sdf_hand_ws_floats(n, HN_WS_SDF_ONLY) &&
+                   aligned16(ws), "hn_sdf_hand_sdf: null pointer or workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* HROW = ws;
+    float* P0 = HROW + n * HROW_LD;
+    float* P1 = P0 + n * 256;
+    float* H[8] = {P0, P1, P0, HROW, P0, P1, P0, P1};
+    HN_PROPAGATE(hand_trunk_fwd(mlp, pts, bt_inv, T_pose, n, pts_per_frame, HROW, H, s, precision));
+    hand_sdf_head_kernel<<<nblocks(n * 32, 256), 256, 0, s>>>(H[7], mlp->W[8], mlp->b[8], n, sdf);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, const float* T_pose, int64_t n,
+                    int64_t pts_per_frame, float* sdf, float* feat, int64_t ld_feat, float* normal,
+                    float* xyz_feature, int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
+                    hn_stream_t stream) {
+    HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_fwd: precision %d not supported", precision);
+    HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
+    if (n == 0) return HN_OK;
+    HN_REQUIRE(pts && bt_inv && T_pose && sdf && feat && normal && stash, "hn_sdf_hand_fwd: null pointer");
+    HN_REQUIRE(stash_floats >= hn_sdf_hand_stash_floats(n) && aligned16(stash), "stash too small or misaligned");
+    HN_REQUIRE(ld_feat >= 256 && ld_feat % 4 == 0 && aligned16(feat), "feat must be 16B aligned with ld%%4==0");
+    cudaStream_t s = (cudaStream_t)stream;
+    HandSdfStash st(stash, n);
+    HN_PROPAGATE(hand_trunk_fwd(mlp, pts, bt_inv, T_pose, n, pts_per_frame, st.HROW, st.H, s, precision));
+    hand_sdf_head_kernel<<<nblocks(n * 32, 256), 256, 0, s>>>(st.H[7], mlp->W[8], mlp->b[8], n, sdf);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    {
+        GemmArgs g;
+        g.A = st.H[7]; g.lda = 256;
+        g.B = mlp->W[8] + mlp->ld[8]; g.ldb = mlp->ld[8];
+        g.M = (int)n; g.N = 256; g.K = 256;
+        g.C = feat; g.ldc = ld_feat; g.bias = mlp->b[8] + 1;
+        HN_PROPAGATE((gemm_nt<EPI_STORE>(g, s, precision, ROLE_VALUE)));
+    }
+    if (xyz_feature) {
+        copy_rows_kernel<<<nblocks(n * HALO_DIM, 256), 256, 0, s>>>(st.HROW + HFEAT_OFF, HROW_LD, n, HALO_DIM, xyz_feature,
+                                                                    ld_xyz);
+        count_launch();
+        HN_CHECK_LAUNCH();
+    }
+    // normal sweep
+    hand_normal_seed_kernel<<<nblocks(n * 64, 256), 256, 0, s>>>(st.H[7], mlp->W[8], n, st.D[7]);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    for (int l = 7; l >= 1; --l) {
+        GemmArgs g;
+        g.A = st.D[l]; g.lda = 256;
+        set_w(g, mlp, l);
+        g.M = (int)n; g.N = 256; g.K = 256;
+        g.C = st.D[l - 1]; g.ldc = 256;
+        g.aux1 = st.H[l - 1]; g.ldaux1 = st.ldH(l - 1);
+        HN_PROPAGATE((gemm_nn<EPI_MUL_SPRIME>(g, s, precision, ROLE_VALUE)));
+        if (l == 4) {      // the feature part of the skip input: FB = D4 @ W4[:, 256:]
+            GemmArgs f;
+            f.A = st.D[4]; f.lda = 256;
+            set_w(f, mlp, 4, HFEAT_OFF);
+            f.M = (int)n; f.N = HALO_DIM; f.K = 256;
+            f.C = st.FB; f.ldc = HFB_LD;
+            HN_PROPAGATE((gemm_nn<EPI_STORE>(f, s, precision, ROLE_VALUE)));
+        }
+    }
+    {
+        GemmArgs g;
+        g.A = st.D[0]; g.lda = 256;
+        set_w(g, mlp, 0);
+        g.M = (int)n; g.N = HALO_DIM; g.K = 256;
+        g.C = st.FB; g.ldc = HFB_LD; g.aux1 = st.FB; g.ldaux1 = HFB_LD;
+        HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(g, s, precision, ROLE_VALUE)));
+    }
+    halo_normal_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, st.FB, HFB_LD, n,
+                                                                          pts_per_frame, normal);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, const float* T_pose, int64_t n,
+                    int64_t pts_per_frame, float* stash, const float* d_sdf, const float* d_feat, int64_t ld_dfeat,
+                    const float* d_normal, const float* d_xyz_feature, int64_t ld_dxyz, float* d_pts, float* d_bt_inv,
+                    float* d_T_pose, const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision,
+                    hn_stream_t stream) {
+    HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_bwd: precision %d not supported", precision);
+    HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
+    if (n == 0) return HN_OK;
+    HN_REQUIRE(pts && bt_inv && T_pose && stash && d_normal && ws, "hn_sdf_hand_bwd: null pointer");
+    HN_REQUIRE(ws_floats >= hn_sdf_hand_ws_floats(n, HN_WS_BWD) && aligned16(ws), "workspace too small or misaligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    HandSdfStash st(stash, n);
+    float* AU4 = ws;                                  // [n,1644] = [u3 | tangent feature | pad]
+    float* U[2] = {AU4 + n * HROW_LD, AU4 + n * HROW_LD + n * 256};
+    float* DZ8 = U[1] + n * 256;
+    float* DZ[2] = {DZ8 + n * 260, DZ8 + n * 260 + n * 256};
+    float* DF = DZ[1] + n * 256;                      // [n,1388]
+    const int splits_target = 2 * sm_count();
+    const bool need_input_grad = d_pts || d_bt_inv || d_T_pose;
+
+    auto dw_gemm = [&](const float* P, int64_t ldp, int out, const float* Q, int64_t ldq, int in, int l) -> int {
+        if (!grad || !grad->dW[l]) return HN_OK;
+        GemmArgs g;
+        g.A = P; g.lda = ldp; g.B = Q; g.ldb = ldq;
+        g.M = out; g.N = in; g.K = (int)n;
+        g.C = grad->dW[l]; g.ldc = mlp->ld[l];
+        int tiles = (int)(ceil_div(out, 128) * ceil_div(in, 256));
+        int splits = (int)max((int64_t)1, min((int64_t)ceil_div(splits_target, tiles), ceil_div(n, 256)));
+        return gemm_tn(g, s, precision, splits);
+    };
+    auto db_sum = [&](const float* X, int64_t ldx, int cols, int l) -> int {
+        if (!grad || !grad->db[l]) return HN_OK;
+        return launch_colsum(X, ldx, n, cols, 1.0f, grad->db[l], s);
+    };
+    auto in_ptr = [&](float* skiprow, float* const prev[8], int l, const float** A, int64_t* lda) {
+        if (l == 0) { *A = skiprow + HFEAT_OFF; *lda = HROW_LD; }
+        else if (l == 4) { *A = skiprow; *lda = HROW_LD; }
+        else { *A = prev[l - 1]; *lda = 256; }
+    };
+
+    // ---- tangent sweep ---------------------------------------------------------------------------
+    halo_tangent_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, d_normal, n,
+                                                                           pts_per_frame, AU4 + HFEAT_OFF, HROW_LD);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    float* Uout[8] = {U[0], U[1], U[0], AU4, U[0], U[1], U[0], U[1]};
+    for (int l = 0; l < 8; ++l) {
+        const float* A; int64_t lda;
+        in_ptr(AU4, Uout, l, &A, &lda);
+        HN_PROPAGATE(dw_gemm(st.D[l], 256, 256, A, lda, mlp->in_dim[l], l));
+        GemmArgs g;
+        g.A = A; g.lda = lda;
+        set_w(g, mlp, l);
+        g.M = (int)n; g.N = 256; g.K = mlp->in_dim[l];
+        g.C = Uout[l]; g.ldc = (l == 3) ? HROW_LD : 256;
+        g.aux1 = st.H[l]; g.ldaux1 = st.ldH(l);
+        g.C2 = st.D[l]; g.ldc2 = 256;
+        HN_PROPAGATE((gemm_nt<EPI_TANGENT>(g, s, precision)));
+    }
+    if (grad && grad->dW[8]) HN_PROPAGATE(launch_colsum(Uout[7], 256, n, 256, 1.0f, grad->dW[8], s));
+
+    // ---- reverse sweep ---------------------------------------------------------------------------
+    hand_assemble_dz8_kernel<<<nblocks(n * 260, 256), 256, 0, s>>>(d_sdf, d_feat, ld_dfeat, n, DZ8);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    // DF starts as the cotangent that reaches the feature from outside (the colour net)
+    if (need_input_grad) {
+        copy_rows_kernel<<<nblocks(n * HFB_LD, 256), 256, 0, s>>>(d_xyz_feature, ld_dxyz, n,
+                                                                  d_xyz_feature ? HALO_DIM : HFB_LD, DF, HFB_LD);
+        count_launch();
+        HN_CHECK_LAUNCH();
+    }
+    const float* dz = DZ8;
+    int64_t ld_dz = 260;
+    for (int l = 8; l >= 1; --l) {
+        const float* A; int64_t lda;
+        in_ptr(st.HROW, st.H, l, &A, &lda);
+        HN_PROPAGATE(dw_gemm(dz, ld_dz, mlp->out_dim[l], A, lda, mlp->in_dim[l], l));
+        HN_PROPAGATE(db_sum(dz, ld_dz, mlp->out_dim[l], l));
+        GemmArgs g;
+        g.A = dz; g.lda = ld_dz;
+        set_w(g, mlp, l);
+        g.M = (int)n; g.N = 256; g.K = mlp->out_dim[l];
+        float* out = DZ[l & 1];
+        g.C = out; g.ldc = 256;
+        g.aux1 = st.H[l - 1]; g.ldaux1 = st.ldH(l - 1);
+        g.aux2 = st.D[l - 1]; g.ldaux2 = 256;
+        HN_PROPAGATE((gemm_nn<EPI_REVERSE>(g, s, precision)));
+        if (l == 4 && need_input_grad) {      // skip part: DF += DZ4 @ W4[:, 256:]
+            GemmArgs f;
+            f.A = dz; f.lda = ld_dz;
+            set_w(f, mlp, 4, HFEAT_OFF);
+            f.M = (int)n; f.N = HALO_DIM; f.K = 256;
+            f.C = DF; f.ldc = HFB_LD; f.aux1 = DF; f.ldaux1 = HFB_LD;
+            HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(f, s, precision)));
+        }
+        dz = out; ld_dz = 256;
+    }
+    HN_PROPAGATE(dw_gemm(dz, 256, 256, st.HROW + HFEAT_OFF, HROW_LD, HALO_DIM, 0));
+    HN_PROPAGATE(db_sum(dz, 256, 256, 0));
+    if (need_input_grad) {
+        GemmArgs g;
+        g.A = dz; g.lda = 256;
+        set_w(g, mlp, 0);
+        g.M = (int)n; g.N = HALO_DIM; g.K = 256;
+        g.C = DF; g.ldc = HFB_LD; g.aux1 = DF; g.ldaux1 = HFB_LD;
+        HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(g, s, precision)));
+        halo_bwd_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, DF, HFB_LD, st.FB, HFB_LD,
+                                                                           d_normal, n, pts_per_frame, d_pts, d_bt_inv,
+                                                                           d_T_pose);
+        count_launch();
+        HN_CHECK_LAUNCH();
+    }
+    return HN_OK;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// Hand colour field: input [xyz_feature 1386 | pad 2 | feature 256 | enc4(normal) 27 | pad 1] = 1672;
+// the mlp's layer 0 must be packed with a 2-column gap after input column 1386 (in_dim 1671).
+// ==========================================================================================
+namespace hn {
+
+constexpr int HCIN_LD = 1672, HCIN_OFF_FEAT = 1388, HCIN_OFF_NRM = 1644, HCIN_DIM = 1671;
+
+__global__ void color_hand_input_kernel(const float* __restrict__ xyz, int64_t ld_xyz, const float* __restrict__ feat,
+                                        int64_t ld_feat, const float* __restrict__ normal, int64_t n,
+                                        float* __restrict__ CIN) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * HCIN_LD) return;
+    int64_t p = i / HCIN_LD;
+    int j = (int)(i - p * HCIN_LD);
+    float v = 0.0f;
+    if (j < HALO_DIM) v = xyz[p * ld_xyz + j];
+    else if (j >= HCIN_OFF_FEAT && j < HCIN_OFF_NRM) v = feat[p * ld_feat + (j - HCIN_OFF_FEAT)];
+    else if (j >= HCIN_OFF_NRM && j < HCIN_DIM) {
+        const float x[3] = {normal[p * 3], normal[p * 3 + 1], normal[p * 3 + 2]};
+        v = enc3_col(x, 4, j - HCIN_OFF_NRM);
+    }
+    CIN[i] = v;
+}
+
+__global__ void color_hand_input_bwd_kernel(const float* __restrict__ CIN, const float* __restrict__ DCIN, int64_t n,
+                                            float* __restrict__ d_xyz, int64_t ld_dxyz, float* __restrict__ d_feat,
+                                            int64_t ld_dfeat, float* __restrict__ d_normal) {
+    const int per = HALO_DIM + 256 + 3;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * per) return;
+    int64_t p = i / per;
+    int j = (int)(i - p * per);
+    const float* g = DCIN + p * HCIN_LD;
+    if (j < HALO_DIM) {
+        if (d_xyz) d_xyz[p * ld_dxyz + j] = g[j];
+    } else if (j < HALO_DIM + 256) {
+        if (d_feat) d_feat[p * ld_dfeat + (j - HALO_DIM)] = g[HCIN_OFF_FEAT + (j - HALO_DIM)];
+    } else if (d_normal) {
+        int c = j - HALO_DIM - 256;
+        d_normal[p * 3 + c] = enc3_jt_from_enc(CIN + p * HCIN_LD + HCIN_OFF_NRM, g + HCIN_OFF_NRM, 4, c);
+    }
+}
+
+__global__ void sigmoid_bwd4_kernel(const float* __restrict__ rgb, const float* __restrict__ d_rgb, int64_t n,
+                                    float* __restrict__ DZ) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * 4) return;
+    int64_t p = i >> 2;
+    int j = (int)(i & 3);
+    float v = 0.0f;
+    if (j < 3) {
+        float y = rgb[p * 3 + j];
+        v = d_rgb[p * 3 + j] * y * (1.0f - y);
+    }
+    DZ[i] = v;
+}
+
+static int check_color_hand_mlp(const hn_mlp_t* m) {
+    HN_REQUIRE(m && m->n_layers == 5, "hand colour mlp must have 5 layers");
+    static const int in_d[5] = {HCIN_DIM, 256, 256, 256, 256};
+    static const int out_d[5] = {256, 256, 256, 256, 3};
+    for (int l = 0; l < 5; ++l) {
+        HN_REQUIRE(m->in_dim[l] == in_d[l] && m->out_dim[l] == out_d[l],
+                   "hand colour mlp layer %d has wrong shape (layer 0 must be packed with the 2-column gap: in_dim 1671)", l);
+        HN_REQUIRE(m->ld[l] >= round_up(in_d[l], 4) && m->ld[l] % 4 == 0, "bad ld for layer %d", l);
+        HN_REQUIRE(m->W[l] && m->b[l] && aligned16(m->W[l]), "layer %d: null or misaligned weights", l);
+    }
+    return HN_OK;
+}
+
+}  // namespace hn
+
+extern "C" {
+
+int64_t hn_color_hand_stash_floats(int64_t n) { return n * (HCIN_LD + 4 * 256); }
+int64_t hn_color_hand_ws_floats(int64_t n, int kind) {
+    if (kind == HN_WS_BWD) return n * (2 * 256 + 4 + HCIN_LD);
+    return 4;
+}
+
+int hn_color_hand_fwd(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_xyz, const float* feat,
+                      int64_t ld_feat, const float* normal, int64_t n, float* rgb, float* stash,
+                      int64_t stash_floats, int precision, hn_stream_t stream) {
+    HN_PROPAGATE(check_color_hand_mlp(mlp));
+    HN_REQUIRE(precision_supported(precision), "hn_color_hand_fwd: precision %d not supported", precision);
+    HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
+    if (n == 0) return HN_OK;
+    HN_REQUIRE(xyz_feature && feat && normal && rgb && stash, "hn_color_hand_fwd: null pointer");
+    HN_REQUIRE(stash_floats >= hn_color_hand_stash_floats(n) && aligned16(stash), "stash too small or misaligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* CIN = stash;
+    float* R[4];
+    for (int l = 0; l < 4; ++l) R[l] = stash + n * HCIN_LD + (int64_t)l * n * 256;
+    color_hand_input_kernel<<<nblocks(n * HCIN_LD, 256), 256, 0, s>>>(xyz_feature, ld_xyz, feat, ld_feat, normal, n, CIN);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    for (int l = 0; l < 4; ++l) {
+        GemmArgs g;
+        g.A = l == 0 ? CIN : R[l - 1]; g.lda = l == 0 ? HCIN_LD : 256;
+        set_w(g, mlp, l);
+        g.M = (int)n; g.N = 256; g.K = mlp->in_dim[l];
+        g.C = R[l]; g.ldc = 256; g.bias = mlp->b[l];
+        HN_PROPAGATE((gemm_nt<EPI_BIAS_RELU>(g, s, precision)));
+    }
+    GemmArgs g;
+    g.A = R[3]; g.lda = 256; set_w(g, mlp, 4);
+    g.M = (int)n; g.N = 3; g.K = 256; g.C = rgb; g.ldc = 3; g.bias = mlp->b[4];
+    HN_PROPAGATE((gemm_nt<EPI_BIAS_SIGMOID>(g, s, precision)));
+    return HN_OK;
+}
+
+int hn_color_hand_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* rgb, const float* d_rgb,
+                      float* d_xyz_feature, int64_t ld_dxyz, float* d_feat, int64_t ld_dfeat, float* d_normal,
+                      const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision, hn_stream_t stream) {
+    HN_PROPAGATE(check_color_hand_mlp(mlp));
+    HN_REQUIRE(precision_supported(precision), "hn_color_hand_bwd: precision %d not supported", precision);
+    HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
+    if (n == 0) return HN_OK;
+    HN_REQUIRE(stash && rgb && d_rgb && ws, "hn_color_hand_bwd: null pointer");
+    HN_REQUIRE(ws_floats >= hn_color_hand_ws_floats(n, HN_WS_BWD) && aligned16(ws), "workspace too small or misaligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    float* CIN = stash;
+    float* R[4];
+    for (int l = 0; l < 4; ++l) R[l] = stash + n * HCIN_LD + (int64_t)l * n * 256;
+    float* DZ[2] = {ws, ws + n * 256};
+    float* DZ4 = ws + 2 * n * 256;
+    float* DCIN = DZ4 + n * 4;
+    const int splits_target = 2 * sm_count();
+    auto dw_gemm = [&](const float* P, int64_t ldp, int out, const float* Q, int64_t ldq, int in, int l) -> int {
+        if (!grad || !grad->dW[l]) return HN_OK;
+        GemmArgs g;
+        g.A = P; g.lda = ldp; g.B = Q; g.ldb = ldq;
+        g.M = out; g.N = in; g.K = (int)n;
+        g.C = grad->dW[l]; g.ldc = mlp->ld[l];
+        int tiles = (int)(ceil_div(out, 128) * ceil_div(in, 256));
+        int splits = (int)max((int64_t)1, min((int64_t)ceil_div(splits_target, tiles), ceil_div(n, 256)));
+        return gemm_tn(g, s, precision, splits);
+    };
+    sigmoid_bwd4_kernel<<<nblocks(n * 4, 256), 256, 0, s>>>(rgb, d_rgb, n, DZ4);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    const float* dz = DZ4;
+    int64_t ld_dz = 4;
+    for (int l = 4; l >= 1; --l) {
+        HN_PROPAGATE(dw_gemm(dz, ld_dz, mlp->out_dim[l], R[l - 1], 256, 256, l));
+        if (grad && grad->db[l]) HN_PROPAGATE(launch_colsum(dz, ld_dz, n, mlp->out_dim[l], 1.0f, grad->db[l], s));
+        GemmArgs g;
+        g.A = dz; g.lda = ld_dz; set_w(g, mlp, l);
+        g.M = (int)n; g.N = 256; g.K = mlp->out_dim[l];
+        g.C = DZ[l & 1]; g.ldc = 256; g.aux1 = R[l - 1]; g.ldaux1 = 256;
+        HN_PROPAGATE((gemm_nn<EPI_RELU_BWD>(g, s, precision)));
+        dz = DZ[l & 1]; ld_dz = 256;
+    }
+    HN_PROPAGATE(dw_gemm(dz, 256, 256, CIN, HCIN_LD, HCIN_DIM, 0));
+    if (grad && grad->db[0]) HN_PROPAGATE(launch_colsum(dz, 256, n, 256, 1.0f, grad->db[0], s));
+    if (d_xyz_feature || d_feat || d_normal) {
+        GemmArgs g;
+        g.A = dz; g.lda = 256; set_w(g, mlp, 0);
+        g.M = (int)n; g.N = HCIN_DIM; g.K = 256; g.C = DCIN; g.ldc = HCIN_LD;
+        HN_PROPAGATE((gemm_nn<EPI_STORE>(g, s, precision)));
+        color_hand_input_bwd_kernel<<<nblocks(n * (HALO_DIM + 256 + 3), 256), 256, 0, s>>>(CIN, DCIN, n, d_xyz_feature, ld_dxyz,
+                                                                                          d_feat, ld_dfeat, d_normal);
+        count_launch();
+        HN_CHECK_LAUNCH();
+    }
+    return HN_OK;
+}
+
+}  // extern "C"

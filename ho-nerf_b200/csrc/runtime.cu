@@ -60,15 +60,18 @@ int sm_count() {
 
 // ---- weight norm ---------------------------------------------------------------------------
 // one warp per output row
+// packed column of input column k when `gap` zero columns follow input column gap_at
+__device__ __forceinline__ int packed_col(int k, int gap_at, int gap) { return k < gap_at ? k : k + gap; }
+
 __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, int out_dim,
                                int in_dim, int ld, float post_scale, float* __restrict__ W,
-                               float* __restrict__ WT, int ldT) {
+                               float* __restrict__ WT, int ldT, int gap_at, int gap) {
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= ldT && row >= out_dim) return;
     if (row >= out_dim) {            // zero padding columns of the transposed copy
         if (WT && row < ldT)
-            for (int k = lane; k < in_dim; k += 32) WT[(int64_t)k * ldT + row] = 0.0f;
+            for (int k = lane; k < in_dim + gap; k += 32) WT[(int64_t)k * ldT + row] = 0.0f;
         return;
     }
     const float* vr = v + (int64_t)row * in_dim;
@@ -77,16 +80,19 @@ __global__ void wn_pack_kernel(const float* __restrict__ v, const float* __restr
     ss = warp_sum(ss);
     float sc = post_scale * (g[row] / sqrtf(ss));
     float* wr = W + (int64_t)row * ld;
-    for (int k = lane; k < ld; k += 32) {
-        float w = k < in_dim ? vr[k] * sc : 0.0f;
+    for (int k = lane; k < ld; k += 32) {         // k = packed column
+        int src = k < gap_at ? k : k - gap;
+        bool live = (k < gap_at || k >= gap_at + gap) && src < in_dim;
+        float w = live ? vr[src] * sc : 0.0f;
         wr[k] = w;
-        if (WT && k < in_dim) WT[(int64_t)k * ldT + row] = w;
+        if (WT && k < in_dim + gap) WT[(int64_t)k * ldT + row] = w;
     }
 }
 
 __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
                               const float* __restrict__ dW, int out_dim, int in_dim, int ld,
-                              float post_scale, float* __restrict__ dv, float* __restrict__ dg) {
+                              float post_scale, float* __restrict__ dv, float* __restrict__ dg,
+                              int gap_at, int gap) {
     int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= out_dim) return;
@@ -95,7 +101,7 @@ __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restri
     float ss = 0.0f, dot = 0.0f;
     for (int k = lane; k < in_dim; k += 32) {
         ss = fmaf(vr[k], vr[k], ss);
-        dot = fmaf(dr[k], vr[k], dot);
+        dot = fmaf(dr[packed_col(k, gap_at, gap)], vr[k], dot);
     }
     ss = warp_sum(ss);
     dot = warp_sum(dot) * post_scale;
@@ -104,7 +110,7 @@ __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restri
     if (lane == 0) dg[row] = dot / nrm;
     float coef = dot / ss;
     float* dvr = dv + (int64_t)row * in_dim;
-    for (int k = lane; k < in_dim; k += 32) dvr[k] = gn * (post_scale * dr[k] - coef * vr[k]);
+    for (int k = lane; k < in_dim; k += 32) dvr[k] = gn * (post_scale * dr[packed_col(k, gap_at, gap)] - coef * vr[k]);
 }
 
 // ---- column sums -----------------------------------------------------------------------------
@@ -172,11 +178,17 @@ int hn_timing_collect(double* total_ms, int64_t* n_launches) {
 
 int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld, float post_scale,
                float* W, float* WT, int ldT, hn_stream_t stream) {
-    HN_REQUIRE(v && g && W && out_dim > 0 && in_dim > 0 && ld >= in_dim, "hn_wn_pack: bad arguments");
+    return hn_wn_pack_gap(v, g, out_dim, in_dim, ld, post_scale, in_dim, 0, W, WT, ldT, stream);
+}
+
+int hn_wn_pack_gap(const float* v, const float* g, int out_dim, int in_dim, int ld, float post_scale,
+                   int gap_at, int gap, float* W, float* WT, int ldT, hn_stream_t stream) {
+    HN_REQUIRE(v && g && W && out_dim > 0 && in_dim > 0 && gap >= 0 && gap_at >= 0 && gap_at <= in_dim &&
+                   ld >= in_dim + gap, "hn_wn_pack: bad arguments");
     HN_REQUIRE(!WT || ldT >= out_dim, "hn_wn_pack: ldT too small");
     int rows = WT ? (ldT > out_dim ? ldT : out_dim) : out_dim;
     wn_pack_kernel<<<(unsigned)ceil_div((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        v, g, out_dim, in_dim, ld, post_scale, W, WT, WT ? ldT : 0);
+        v, g, out_dim, in_dim, ld, post_scale, W, WT, WT ? ldT : 0, gap_at, gap);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;
@@ -184,9 +196,15 @@ int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld, 
 
 int hn_wn_bwd(const float* v, const float* g, const float* dW, int out_dim, int in_dim, int ld,
               float post_scale, float* dv, float* dg, hn_stream_t stream) {
-    HN_REQUIRE(v && g && dW && dv && dg && out_dim > 0 && in_dim > 0 && ld >= in_dim, "hn_wn_bwd: bad arguments");
+    return hn_wn_bwd_gap(v, g, dW, out_dim, in_dim, ld, post_scale, in_dim, 0, dv, dg, stream);
+}
+
+int hn_wn_bwd_gap(const float* v, const float* g, const float* dW, int out_dim, int in_dim, int ld,
+                  float post_scale, int gap_at, int gap, float* dv, float* dg, hn_stream_t stream) {
+    HN_REQUIRE(v && g && dW && dv && dg && out_dim > 0 && in_dim > 0 && gap >= 0 && ld >= in_dim + gap,
+               "hn_wn_bwd: bad arguments");
     wn_bwd_kernel<<<(unsigned)ceil_div((int64_t)out_dim * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-        v, g, dW, out_dim, in_dim, ld, post_scale, dv, dg);
+        v, g, dW, out_dim, in_dim, ld, post_scale, dv, dg, gap_at, gap);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

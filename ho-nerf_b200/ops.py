@@ -52,11 +52,15 @@ class PackedMLP:
     """Effective weights of a stack of weight-normalised Linears, packed once per parameter
     version by hn_wn_pack (the reference recomputes g*v/||v|| inside every Linear call)."""
 
-    def __init__(self, layers, post_scales):
+    def __init__(self, layers, post_scales, gaps=None):
         # layers: list of (weight_g [out,1], weight_v [out,in], bias [out]) parameters
+        # gaps: per layer (gap_at, gap): `gap` zero columns inserted after input column gap_at of
+        #       the packed layout (hand colour net, see include/honerf_b200.h)
         self.layers = layers
         self.post_scales = list(post_scales)
-        self.dims = [(v.shape[1], v.shape[0]) for (_, v, _) in layers]
+        self.raw_in = [v.shape[1] for (_, v, _) in layers]
+        self.gaps = list(gaps) if gaps is not None else [(i, 0) for i in self.raw_in]
+        self.dims = [(v.shape[1] + gp[1], v.shape[0]) for (_, v, _), gp in zip(layers, self.gaps)]
         self.lds = [_round4(i) for (i, _) in self.dims]
         self.offsets = []
         off = 0
@@ -98,8 +102,9 @@ class PackedMLP:
             i, o = self.dims[l]
             Wl = self.W[self.offsets[l]: self.offsets[l] + o * self.lds[l]]
             WTl = self.WT[self.offsetsT[l]: self.offsetsT[l] + i * self.ldTs[l]]
-            check(lib.hn_wn_pack(_ptr(vd), _ptr(gd), o, i, self.lds[l], self.post_scales[l], _ptr(Wl),
-                                 _ptr(WTl), self.ldTs[l], _stream(vd)), "hn_wn_pack")
+            check(lib.hn_wn_pack_gap(_ptr(vd), _ptr(gd), o, self.raw_in[l], self.lds[l], self.post_scales[l],
+                                     self.gaps[l][0], self.gaps[l][1], _ptr(Wl), _ptr(WTl), self.ldTs[l],
+                                     _stream(vd)), "hn_wn_pack")
             st.in_dim[l], st.out_dim[l], st.ld[l] = i, o, self.lds[l]
             st.W[l] = Wl.data_ptr()
             st.WT[l] = WTl.data_ptr()
@@ -130,8 +135,9 @@ class PackedMLP:
             dv = torch.empty_like(vd)
             dg = torch.empty(o, 1, device=vd.device, dtype=torch.float32)
             dWl = dW[self.offsets[l]: self.offsets[l] + o * self.lds[l]]
-            check(lib.hn_wn_bwd(_ptr(vd), _ptr(gd), _ptr(dWl), o, i, self.lds[l], self.post_scales[l],
-                                _ptr(dv), _ptr(dg), _stream(vd)), "hn_wn_bwd")
+            check(lib.hn_wn_bwd_gap(_ptr(vd), _ptr(gd), _ptr(dWl), o, self.raw_in[l], self.lds[l],
+                                    self.post_scales[l], self.gaps[l][0], self.gaps[l][1], _ptr(dv), _ptr(dg),
+                                    _stream(vd)), "hn_wn_bwd")
             out += [dg, dv, db[l]]
         return out
 
@@ -278,6 +284,159 @@ def color_obj(packed, pts, dirs, feat, normal, precision=None):
     """RenderingNetwork_OBJ.forward (utils/fields.py:387-405): -> rgb [N,3]."""
     precision = _default_precision if precision is None else precision
     return _ColorObjFn.apply(pts, dirs, feat, normal, packed, precision, *packed.flat_params())
+
+
+# ------------------------------------------------------------------------------------------------
+# hand SDF / colour fields
+# ------------------------------------------------------------------------------------------------
+def _hand_pose_args(pts, bt_inv, T_pose_21):
+    """Flatten (possibly frame-batched) hand inputs: pts [N,3] | [F,P,3], bt_inv [21,4,4] | [F,21,4,4],
+    T_pose_21 [21,3] | [F,21,3]  ->  pts [n,3], bt [F,21,4,4], T [F,21,3], points per frame."""
+    if pts.dim() == 3:
+        ppf = pts.shape[1]
+        pts2 = pts.reshape(-1, 3)
+    else:
+        pts2, ppf = pts, max(int(pts.shape[0]), 1)
+    bt = bt_inv if bt_inv.dim() == 4 else bt_inv[None]
+    T = T_pose_21 if T_pose_21.dim() == 3 else T_pose_21[None]
+    if pts.dim() == 2 and bt.shape[0] != 1:
+        raise ValueError("un-batched points need a single [21,4,4] bone transform set")
+    return pts2, bt, T, ppf
+
+
+def sdf_hand_sdf_only(packed, pts, bt_inv, T_pose_21, precision=None):
+    """SDFNetwork.sdf under no_grad (utils/fields.py:158-160)."""
+    pts2, bt, T, ppf = _hand_pose_args(pts, bt_inv, T_pose_21)
+    pts2, bt, T = _f32c(pts2.detach()), _f32c(bt.detach()), _f32c(T.detach())
+    _require_cuda(pts2, "sdf_hand_sdf_only")
+    pk = packed.get()
+    n = pts2.shape[0]
+    sdf = torch.empty(n, 1, device=pts2.device, dtype=torch.float32)
+    if n == 0:
+        return sdf
+    wsf = lib.hn_sdf_hand_ws_floats(n, HN_WS_SDF_ONLY)
+    ws = torch.empty(wsf, device=pts2.device, dtype=torch.float32)
+    check(lib.hn_sdf_hand_sdf(ctypes.byref(pk.struct), _ptr(pts2), _ptr(bt), _ptr(T), n, ppf, _ptr(sdf), _ptr(ws), wsf,
+                              _default_precision if precision is None else precision, _stream(pts2)),
+          "hn_sdf_hand_sdf")
+    return sdf
+
+
+class _SdfHandFn(torch.autograd.Function):
+    """(sdf, feature, normal, xyz_feature) = f(pts, bt_inv, T_pose_21, params)."""
+
+    @staticmethod
+    def forward(ctx, pts, bt_inv, T_pose, ppf, packed, precision, *params):
+        pts_c, bt_c, T_c = _f32c(pts.detach()), _f32c(bt_inv.detach()), _f32c(T_pose.detach())
+        _require_cuda(pts_c, "sdf_hand")
+        pk = packed.get()
+        n, dev = pts_c.shape[0], pts_c.device
+        sdf = torch.empty(n, 1, device=dev)
+        feat = torch.empty(n, 256, device=dev)
+        normal = torch.empty(n, 3, device=dev)
+        xyz = torch.empty(n, 1386, device=dev)
+        stf = lib.hn_sdf_hand_stash_floats(n)
+        stash = torch.empty(max(stf, 4), device=dev, dtype=torch.float32)
+        if n > 0:
+            check(lib.hn_sdf_hand_fwd(ctypes.byref(pk.struct), _ptr(pts_c), _ptr(bt_c), _ptr(T_c), n, ppf, _ptr(sdf),
+                                      _ptr(feat), 256, _ptr(normal), _ptr(xyz), 1386, _ptr(stash), stf, precision,
+                                      _stream(pts_c)), "hn_sdf_hand_fwd")
+        ctx.packed, ctx.stash, ctx.n, ctx.ppf, ctx.precision, ctx.struct = pk, stash, n, ppf, precision, pk.struct
+        ctx.pts_c, ctx.bt_c, ctx.T_c = pts_c, bt_c, T_c
+        ctx.need = (pts.requires_grad, bt_inv.requires_grad, T_pose.requires_grad)
+        ctx.params_need_grad = any(p.requires_grad for p in params)
+        return sdf, feat, normal, xyz
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_sdf, d_feat, d_normal, d_xyz):
+        if ctx.stash is None:
+            raise _lib.HonerfError("sdf_hand backward called twice (the stash is consumed)")
+        n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
+        d_sdf = _f32c(d_sdf) if d_sdf is not None else None
+        d_feat = _f32c(d_feat) if d_feat is not None else None
+        d_xyz = _f32c(d_xyz) if d_xyz is not None else None
+        d_normal = _f32c(d_normal) if d_normal is not None else torch.zeros(n, 3, device=dev)
+        d_pts = torch.empty(n, 3, device=dev) if ctx.need[0] else None
+        d_bt = torch.zeros_like(ctx.bt_c) if ctx.need[1] else None
+        d_T = torch.zeros_like(ctx.T_c) if ctx.need[2] else None
+        grads = [None] * (3 * len(pk.layers))
+        if n > 0:
+            gs = None
+            if ctx.params_need_grad:
+                dW, db, gs = pk.new_grad()
+            wsf = lib.hn_sdf_hand_ws_floats(n, HN_WS_BWD)
+            ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+            check(lib.hn_sdf_hand_bwd(ctypes.byref(ctx.struct), _ptr(ctx.pts_c), _ptr(ctx.bt_c), _ptr(ctx.T_c), n, ctx.ppf,
+                                      _ptr(ctx.stash), _ptr(d_sdf), _ptr(d_feat), 256, _ptr(d_normal), _ptr(d_xyz), 1386,
+                                      _ptr(d_pts), _ptr(d_bt), _ptr(d_T), ctypes.byref(gs) if gs is not None else None,
+                                      _ptr(ws), wsf, ctx.precision, _stream(ctx.stash)), "hn_sdf_hand_bwd")
+            if gs is not None:
+                grads = pk.unpack_grads(dW, db)
+        elif d_pts is not None:
+            d_pts.zero_()
+        ctx.stash = None
+        return (d_pts, d_bt, d_T, None, None, None) + tuple(grads)
+
+
+def sdf_hand(packed, pts, bt_inv, T_pose_21, precision=None):
+    """Fused anerf_emb_point(_batch) + SDFNetwork.forward + .gradient (utils/fields.py:22-52, 132-177).
+    Returns sdf [N,1], feature [N,256], normal [N,3], xyz_feature [N,1386]."""
+    precision = _default_precision if precision is None else precision
+    pts2, bt, T, ppf = _hand_pose_args(pts, bt_inv, T_pose_21)
+    return _SdfHandFn.apply(pts2, bt, T, ppf, packed, precision, *packed.flat_params())
+
+
+class _ColorHandFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, feat, normal, packed, precision, *params):
+        xyz_c, feat_c, nrm_c = _f32c(xyz.detach()), _f32c(feat.detach()), _f32c(normal.detach())
+        _require_cuda(xyz_c, "color_hand")
+        pk = packed.get()
+        n, dev = xyz_c.shape[0], xyz_c.device
+        rgb = torch.empty(n, 3, device=dev)
+        stf = lib.hn_color_hand_stash_floats(n)
+        stash = torch.empty(max(stf, 4), device=dev, dtype=torch.float32)
+        if n > 0:
+            check(lib.hn_color_hand_fwd(ctypes.byref(pk.struct), _ptr(xyz_c), xyz_c.shape[1], _ptr(feat_c),
+                                        feat_c.shape[1], _ptr(nrm_c), n, _ptr(rgb), _ptr(stash), stf, precision,
+                                        _stream(xyz_c)), "hn_color_hand_fwd")
+        ctx.packed, ctx.stash, ctx.n, ctx.precision, ctx.struct, ctx.rgb = pk, stash, n, precision, pk.struct, rgb
+        ctx.need = (xyz.requires_grad, feat.requires_grad, normal.requires_grad)
+        ctx.params_need_grad = any(p.requires_grad for p in params)
+        return rgb
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_rgb):
+        if ctx.stash is None:
+            raise _lib.HonerfError("color_hand backward called twice (the stash is consumed)")
+        n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
+        d_rgb = _f32c(d_rgb)
+        d_xyz = torch.empty(n, 1386, device=dev) if ctx.need[0] else None
+        d_feat = torch.empty(n, 256, device=dev) if ctx.need[1] else None
+        d_nrm = torch.empty(n, 3, device=dev) if ctx.need[2] else None
+        grads = [None] * (3 * len(pk.layers))
+        if n > 0:
+            gs = None
+            if ctx.params_need_grad:
+                dW, db, gs = pk.new_grad()
+            wsf = lib.hn_color_hand_ws_floats(n, HN_WS_BWD)
+            ws = torch.empty(wsf, device=dev, dtype=torch.float32)
+            check(lib.hn_color_hand_bwd(ctypes.byref(ctx.struct), n, _ptr(ctx.stash), _ptr(ctx.rgb), _ptr(d_rgb),
+                                        _ptr(d_xyz), 1386, _ptr(d_feat), 256, _ptr(d_nrm),
+                                        ctypes.byref(gs) if gs is not None else None, _ptr(ws), wsf, ctx.precision,
+                                        _stream(ctx.stash)), "hn_color_hand_bwd")
+            if gs is not None:
+                grads = pk.unpack_grads(dW, db)
+        ctx.stash = None
+        return (d_xyz, d_feat, d_nrm, None, None) + tuple(grads)
+
+
+def color_hand(packed, xyz_feature, feat, normal, precision=None):
+    """RenderingNetwork.forward (utils/fields.py:222-240): -> rgb [N,3]."""
+    precision = _default_precision if precision is None else precision
+    return _ColorHandFn.apply(xyz_feature, feat, normal, packed, precision, *packed.flat_params())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -80,6 +80,15 @@ typedef struct hn_mlp_grad {
  * Replaces the per-call `_weight_norm` recomputation of every Linear. */
 HN_API int hn_wn_pack(const float* v, const float* g, int out_dim, int in_dim, int ld,
                       float post_scale, float* W, float* WT, int ldT, hn_stream_t stream);
+/* Same with `gap` zero columns inserted after input column `gap_at` of the packed layouts (packed
+ * in_dim = in_dim + gap; ld >= in_dim + gap).  Used by the hand colour net, whose input row is
+ * [xyz_feature 1386 | pad 2 | feature 256 | enc(normal) 27]. */
+HN_API int hn_wn_pack_gap(const float* v, const float* g, int out_dim, int in_dim, int ld,
+                          float post_scale, int gap_at, int gap, float* W, float* WT, int ldT,
+                          hn_stream_t stream);
+HN_API int hn_wn_bwd_gap(const float* v, const float* g, const float* dW, int out_dim, int in_dim,
+                         int ld, float post_scale, int gap_at, int gap, float* dv, float* dg,
+                         hn_stream_t stream);
 /* (dv, dg) from dW; dW is the gradient w.r.t. the PACKED weight (so it is
  * multiplied by post_scale first).  dv [out,in] and dg [out] are overwritten. */
 HN_API int hn_wn_bwd(const float* v, const float* g, const float* dW, int out_dim, int in_dim,
@@ -131,6 +140,48 @@ HN_API int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n_pts, float* stash, co
                             const float* d_rgb, float* d_pts, float* d_dirs, float* d_feat,
                             int64_t ld_dfeat, float* d_normal, const hn_mlp_grad_t* grad,
                             float* ws, int64_t ws_floats, int precision, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Hand SDF field (HALO pose-conditioned): anerf_emb_point(_batch) + SDFNetwork.forward/.sdf/.gradient
+ * (utils/fields.py:22-52, 132-177) as one operator, second-order backward included.
+ * pts [n,3] are grouped by frame: point p belongs to frame p / pts_per_frame; bt_inv
+ * [frames,21,4,4] (row-major), T_pose [frames,21,3].  mlp: 9 layers 1386->256 x3 ->256->[cat 1386]
+ * ->256 x4 ->257 (W[4] packed with post_scale 1/sqrt(2)); no division by `scale` (SURVEY A-9).
+ * Outputs: sdf [n], feat [n, ld_feat], normal [n,3], xyz_feature [n, ld_xyz >= 1386] (may be NULL).
+ * Backward: cotangents d_sdf, d_feat, d_normal, d_xyz_feature (any of d_sdf/d_feat/d_xyz may be
+ * NULL); writes d_pts [n,3] (may be NULL), ACCUMULATES d_bt_inv [frames,21,4,4] and d_T_pose
+ * [frames,21,3] (may be NULL; caller zeroes) and dW/db.
+ * ------------------------------------------------------------------------------------------- */
+HN_API int64_t hn_sdf_hand_stash_floats(int64_t n_pts);
+HN_API int64_t hn_sdf_hand_ws_floats(int64_t n_pts, int ws_kind);
+HN_API int hn_sdf_hand_sdf(const hn_mlp_t* mlp, const float* pts, const float* bt_inv,
+                           const float* T_pose, int64_t n_pts, int64_t pts_per_frame, float* sdf,
+                           float* ws, int64_t ws_floats, int precision, hn_stream_t stream);
+HN_API int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv,
+                           const float* T_pose, int64_t n_pts, int64_t pts_per_frame, float* sdf,
+                           float* feat, int64_t ld_feat, float* normal, float* xyz_feature,
+                           int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
+                           hn_stream_t stream);
+HN_API int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv,
+                           const float* T_pose, int64_t n_pts, int64_t pts_per_frame, float* stash,
+                           const float* d_sdf, const float* d_feat, int64_t ld_dfeat,
+                           const float* d_normal, const float* d_xyz_feature, int64_t ld_dxyz,
+                           float* d_pts, float* d_bt_inv, float* d_T_pose, const hn_mlp_grad_t* grad,
+                           float* ws, int64_t ws_floats, int precision, hn_stream_t stream);
+
+/* Hand colour field: RenderingNetwork.forward (utils/fields.py:222-240), input
+ * cat[xyz_feature (1386), feature (256), normal + enc4 (27)] = 1669 -> 256 x4 -> 3, sigmoid.
+ * mlp layer 0 must be packed with hn_wn_pack_gap(gap_at = 1386, gap = 2) (in_dim 1671). */
+HN_API int64_t hn_color_hand_stash_floats(int64_t n_pts);
+HN_API int64_t hn_color_hand_ws_floats(int64_t n_pts, int ws_kind);
+HN_API int hn_color_hand_fwd(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_xyz,
+                             const float* feat, int64_t ld_feat, const float* normal, int64_t n_pts,
+                             float* rgb, float* stash, int64_t stash_floats, int precision,
+                             hn_stream_t stream);
+HN_API int hn_color_hand_bwd(const hn_mlp_t* mlp, int64_t n_pts, float* stash, const float* rgb,
+                             const float* d_rgb, float* d_xyz_feature, int64_t ld_dxyz, float* d_feat,
+                             int64_t ld_dfeat, float* d_normal, const hn_mlp_grad_t* grad, float* ws,
+                             int64_t ws_floats, int precision, hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Ray helpers and hierarchical sampling (utils/renderer.py:10-37, 60-105, 119-127, 204-234).

@@ -185,3 +185,81 @@ def wn_backward(v, g, dW):
     dg = dot / n
     dv = (g / n) * (dW - dot * v / (n * n))
     return dg, dv
+
+
+# ------------------------------------------------------------------------------------------------
+# HALO per-bone feature (utils/fields.py:22-36, 142-148) and its derivatives, per (point, joint):
+#   q = R x + t - T,  v = |q|,  r = q / v,  h = 1 - sigmoid(200 (v - cutoff))
+#   F(q) = h * [v, sin(2^k v), cos(2^k v) (k<10), r (3), sin(2^k r_a), cos(2^k r_a) (k<7, a<3)]   (66)
+# For a cotangent c (66) define s(q) = <c, F(q)> = h(v) (A(v) + B(r)).  The CUDA kernels need
+#   grad   g  = d s / d q            (normal sweep, first-order backward)
+#   jvp    dF = F'(q) w              (tangent sweep)
+#   hvp    Hw = d/dq (g . w)         (second-order backward: d<dn, normal>/d(x, R, t, T))
+# ------------------------------------------------------------------------------------------------
+HALO_CUTOFF = (0.08, 0.03, 0.03, 0.02, 0.02, 0.03, 0.02, 0.02, 0.02, 0.03, 0.02, 0.02, 0.02, 0.03,
+               0.02, 0.02, 0.02, 0.03, 0.02, 0.02, 0.02)
+
+
+def _halo_parts(q, cutoff, Lv=10, Lr=7, tau=200.0):
+    """q [..,3], cutoff [..] -> dict of the shared scalars."""
+    v = q.norm(dim=-1)
+    r = q / v[..., None]
+    sg = torch.sigmoid(tau * (v - cutoff))
+    h = 1.0 - sg
+    h1 = -tau * sg * (1.0 - sg)
+    h2 = -tau * tau * sg * (1.0 - sg) * (1.0 - 2.0 * sg)
+    fv = (2.0 ** torch.arange(Lv, dtype=q.dtype))
+    fr = (2.0 ** torch.arange(Lr, dtype=q.dtype))
+    av = v[..., None] * fv                    # [.., Lv]
+    ar = r[..., None] * fr                    # [.., 3, Lr]
+    return dict(v=v, r=r, h=h, h1=h1, h2=h2, fv=fv, fr=fr, sv=av.sin(), cv=av.cos(), sr=ar.sin(), cr=ar.cos())
+
+
+def halo_feature_block(q, cutoff):
+    p = _halo_parts(q, cutoff)
+    phi = torch.cat([p["v"][..., None], p["sv"], p["cv"], p["r"],
+                     torch.cat([p["sr"], p["cr"]], dim=-1).flatten(-2)], dim=-1)   # [.., 66]
+    return phi * p["h"][..., None], p, phi
+
+
+def _split_c(c, Lv=10, Lr=7):
+    c0 = c[..., 0]
+    cs, cc = c[..., 1:1 + Lv], c[..., 1 + Lv:1 + 2 * Lv]
+    cr = c[..., 1 + 2 * Lv:4 + 2 * Lv]
+    ang = c[..., 4 + 2 * Lv:].reshape(*c.shape[:-1], 3, 2 * Lr)
+    return c0, cs, cc, cr, ang[..., :Lr], ang[..., Lr:]
+
+
+def halo_grad_hvp(q, cutoff, c, w=None):
+    """Returns g = d<c,F>/dq [..,3] and, when w is given, (jvp [..,66], hvp [..,3])."""
+    F, p, phi = halo_feature_block(q, cutoff)
+    c0, cs, cc, cr, cas, cac = _split_c(c)
+    v, r, h, h1, h2 = p["v"], p["r"], p["h"], p["h1"], p["h2"]
+    fv, fr = p["fv"], p["fr"]
+    A = c0 * v + (cs * p["sv"] + cc * p["cv"]).sum(-1)
+    A1 = c0 + (fv * (cs * p["cv"] - cc * p["sv"])).sum(-1)
+    A2 = (fv * fv * (-cs * p["sv"] - cc * p["cv"])).sum(-1)
+    B = (cr * r).sum(-1) + (cas * p["sr"] + cac * p["cr"]).sum((-1, -2))
+    b1 = cr + (fr * (cas * p["cr"] - cac * p["sr"])).sum(-1)            # [..,3]
+    b2 = (fr * fr * (-cas * p["sr"] - cac * p["cr"])).sum(-1)          # [..,3]
+    G = A + B
+    rb1 = (r * b1).sum(-1)
+    Pb1 = b1 - r * rb1[..., None]
+    g = (h1 * G + h * A1)[..., None] * r + (h / v)[..., None] * Pb1
+    if w is None:
+        return g
+    dv = (r * w).sum(-1)
+    dr = (w - r * dv[..., None]) / v[..., None]
+    # jvp of the 66 features
+    dphi = torch.cat([dv[..., None], fv * p["cv"] * dv[..., None], -fv * p["sv"] * dv[..., None], dr,
+                      torch.cat([fr * p["cr"] * dr[..., None], -fr * p["sr"] * dr[..., None]], dim=-1).flatten(-2)],
+                     dim=-1)
+    jvp = dphi * h[..., None] + phi * (h1 * dv)[..., None]
+    # hvp
+    dG = A1 * dv + (b1 * dr).sum(-1)
+    db1 = b2 * dr
+    dPb1 = -dr * rb1[..., None] - r * (dr * b1).sum(-1)[..., None] + (db1 - r * (r * db1).sum(-1)[..., None])
+    hvp = (h2 * dv * G + h1 * dG + h1 * dv * A1 + h * A2 * dv)[..., None] * r \
+        + (h1 * G + h * A1)[..., None] * dr \
+        + (h1 * dv / v)[..., None] * Pb1 + (h / v)[..., None] * dPb1 - (h * dv / (v * v))[..., None] * Pb1
+    return g, jvp, hvp

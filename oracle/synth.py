@@ -167,8 +167,8 @@ def hand_states(seed=20):
     free space and surface crossings near the bones."""
     sd = make_state(HAND_SDF_DIMS, seed, "sdf", n_se3=4, se3_width=36)
     g = torch.Generator().manual_seed(seed + 7)
-    sd["lin0.weight_v"] = sd["lin0.weight_v"] + 0.02 * torch.randn(256, 1386, generator=g)
-    sd["lin4.weight_v"][:, 256:] += 0.01 * torch.randn(256, 1386, generator=g)
+    sd["lin0.weight_v"] = sd["lin0.weight_v"] + 0.006 * torch.randn(256, 1386, generator=g)
+    sd["lin4.weight_v"][:, 256:] += 0.003 * torch.randn(256, 1386, generator=g)
     for l in (0, 4):
         sd["lin%d.weight_g" % l] = sd["lin%d.weight_v" % l].norm(dim=1, keepdim=True) * (
             0.9 + 0.2 * torch.rand(256, 1, generator=g))

@@ -49,3 +49,19 @@ def oracle_core_fp64(case, z_vals):
     tens = [v for k, v in spd.items() if k != "se3_refine"] + list(cpd.values()) + [var, Ro, To]
     grads = dict(zip(names, torch.autograd.grad(loss, tens)))
     return core, loss, grads, names
+
+
+def hand_modules(device=DEV, requires_grad=True, use_batch=False):
+    import honerf_b200 as H
+    sp, cp = synth.hand_states()
+    emb = H.Embedding()
+    sdf = H.SDFNetwork(emb, 4, "real", use_batch=use_batch, **ref_conf.HAND_SDF_CONF)
+    col = H.RenderingNetwork(emb, "real", **ref_conf.HAND_COLOR_CONF)
+    dev = H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT)
+    sdf.load_state_dict(sp)
+    col.load_state_dict(cp)
+    for m in (sdf, col, dev):
+        m.to(device)
+        for p in m.parameters():
+            p.requires_grad_(requires_grad)
+    return sdf, col, dev, sp, cp
