@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhonerf_b200.so")
 
 HN_MAX_LAYERS = 12
-HN_SIMT_FP32, HN_TC_TF32, HN_TC_TF32X3 = 0, 1, 2
+HN_SIMT_FP32, HN_TC_TF32, HN_TC_TF32X3, HN_TC_BF16X3 = 0, 1, 2, 3
 HN_WS_SDF_ONLY, HN_WS_FWD, HN_WS_BWD = 0, 1, 2
 
 
@@ -23,7 +23,9 @@ class hn_mlp_t(Structure):
                 ("W", c_void_p * HN_MAX_LAYERS),
                 ("b", c_void_p * HN_MAX_LAYERS),
                 ("WT", c_void_p * HN_MAX_LAYERS),
-                ("ldT", c_int32 * HN_MAX_LAYERS)]
+                ("ldT", c_int32 * HN_MAX_LAYERS),
+                ("chain", c_void_p),
+                ("chain_bytes", c_int64)]
 
 
 class hn_mlp_grad_t(Structure):
@@ -66,6 +68,9 @@ PROTOTYPES = {
     "hn_color_hand_fwd": (c_int, [_mlp_p, P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P]),
     "hn_color_hand_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, c_int64, P, c_int64, P, _grad_p, P, c_int64,
                                   c_int, P]),
+    "hn_chain_set_prof": (c_int, [P]),
+    "hn_sdf_obj_chain_bytes": (c_int64, []),
+    "hn_sdf_obj_chain_pack": (c_int, [_mlp_p, P, c_int64, P]),
     "hn_sdf_obj_stash_floats": (c_int64, [c_int64]),
     "hn_sdf_obj_ws_floats": (c_int64, [c_int64, c_int]),
     "hn_sdf_obj_sdf": (c_int, [_mlp_p, P, c_int64, c_float, P, P, c_int64, c_int, P]),
@@ -89,6 +94,10 @@ PROTOTYPES = {
     "hn_neus_composite_fwd": (c_int, [P, P, P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P, P]),
     "hn_neus_composite_bwd": (c_int, [P, P, P, P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P,
                                       P, P, P]),
+    "hn_neus_alpha_fwd": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P]),
+    "hn_neus_alpha_bwd": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P, P, P, P, P]),
+    "hn_fit_composite_fwd": (c_int, [P, P, P, P, c_int64, c_int, P, P, P, P]),
+    "hn_fit_composite_bwd": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P, P, P, P, P]),
 }
 
 for _name, (_res, _args) in PROTOTYPES.items():

@@ -1,0 +1,249 @@
+// Fused tile-chain MLP kernels on tcgen05 (HN_TC_BF16X3): shared machinery.
+//
+// One persistent CTA per SM walks over 128-point tiles.  A tile's activations never leave the SM
+// between layers: they live in shared memory as TWO bf16 matrices (hi + lo, hi = bf16(x),
+// lo = bf16(x - hi)) in the canonical K-major SWIZZLE_128B UMMA layout, and every layer is
+//     acc[128, N] (fp32, TMEM) = A_hi B_hi^T + A_lo B_hi^T + A_hi B_lo^T
+// i.e. three bf16 MMAs per product, which restores ~16 mantissa bits (oracle/analytic.py:
+// bf16x3 gives 8e-6 max-abs on the SDF and 5e-5 relative on weight gradients, against the
+// 1e-3 / 1e-2 north-star bounds; a single bf16 or tf32 pass does not).
+//
+// Weights are packed ONCE per parameter version (hn_*_chain_pack) as bf16 hi/lo tiles already in
+// the UMMA shared-memory layout, so a warp-specialised producer streams them L2 -> shared memory
+// with plain 1-D bulk copies (cp.async.bulk + mbarrier transaction counts), 32 KB per stage.
+//
+// Warp roles (320 threads):  warp 0 = weight producer, warp 1 = MMA issuer (one thread),
+// warps 2..9 = epilogue (TMEM -> registers -> activation math -> next layer's A operand in shared
+// memory, plus whatever the mode streams to / from HBM).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace hn {
+namespace chain {
+
+constexpr int TILE_M = 128;
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;
+constexpr int KB_BYTES = TILE_M * 128;            // one 64-column k-block of an A matrix: 16 KB
+constexpr int A_KBLOCKS = 4;                      // 256 activation columns
+constexpr int A_LO_OFF = A_KBLOCKS * KB_BYTES;    // 64 KB
+constexpr int RING_OFF = 2 * A_KBLOCKS * KB_BYTES;   // 128 KB
+constexpr int STAGE_BYTES = 256 * 128;            // 32 KB: [256 rows x 64 bf16]
+constexpr int STAGES = 3;
+constexpr int SMEM_BYTES = RING_OFF + STAGES * STAGE_BYTES + 1024;   // + alignment slack
+constexpr int TMEM_COLS = 256;
+constexpr int MAX_STEPS = 24;
+
+// One layer of a chain: acc[128, n_mma] = A[:, 64*a_kb0 : 64*(a_kb0+kblocks)] @ B^T.
+// B is stored at chain + b_off as kblocks x { hi tile [n_mma x 128 B], lo tile [n_mma x 128 B] }.
+struct Step {
+    uint32_t b_off;
+    uint16_t n_mma;
+    uint8_t kblocks;
+    uint8_t a_kb0;
+};
+struct Program {
+    int n_steps;
+    Step step[MAX_STEPS];
+};
+
+__host__ __device__ inline uint32_t b_operand_bytes(int n_mma, int kblocks) {
+    return (uint32_t)kblocks * 2u * (uint32_t)n_mma * 128u;
+}
+
+struct Barriers {
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t a_ready;     // epilogue -> MMA: the A operand of the next step is in shared memory
+    uint64_t acc_full;    // MMA -> epilogue: the accumulator of this step is complete
+    uint32_t tmem_base;
+};
+
+// ---- bf16 hi/lo split ------------------------------------------------------------------------
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    float2 hf = __bfloat1622float2(h);
+    __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
+// 8 consecutive columns [col, col+8) (col % 8 == 0) of row `row`
+__device__ __forceinline__ void a_store8(uint8_t* smem, int row, int col, const float* v) {
+    uint4 hi, lo;
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z);
+    split2(v[6], v[7], hi.w, lo.w);
+    uint32_t off = (uint32_t)(col >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)row, (uint32_t)((col & 63) >> 3));
+    *reinterpret_cast<uint4*>(smem + off) = hi;
+    *reinterpret_cast<uint4*>(smem + A_LO_OFF + off) = lo;
+}
+__device__ __forceinline__ void a_store1(uint8_t* smem, int row, int col, float v) {
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    uint32_t off = (uint32_t)(col >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)row, (uint32_t)((col & 63) >> 3)) +
+                   (uint32_t)(col & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(smem + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(smem + A_LO_OFF + off) = l;
+}
+// read back 8 consecutive columns as fp32 (hi + lo)
+__device__ __forceinline__ void a_load8(const uint8_t* smem, int row, int col, float* v) {
+    uint32_t off = (uint32_t)(col >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)row, (uint32_t)((col & 63) >> 3));
+    uint4 hi = *reinterpret_cast<const uint4*>(smem + off);
+    uint4 lo = *reinterpret_cast<const uint4*>(smem + A_LO_OFF + off);
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+        v[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+    }
+}
+
+// softplus(beta=100) with torch's threshold (identity for 100 z > 20; below it the log1p term is
+// < 2.1e-11, far under an ulp of z >= 0.2, so the two branches agree to fp32 rounding)
+__device__ __forceinline__ float softplus100_fast(float z) {
+    float t = z * 100.0f;
+    float e = __expf(-fabsf(t));
+    return fmaxf(z, 0.0f) + 0.01f * __logf(1.0f + e);
+}
+
+// ---- setup / teardown (all threads) -----------------------------------------------------------
+__device__ __forceinline__ uint8_t* chain_setup(uint8_t* smem_raw, Barriers* bar) {
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tc::tmem_alloc(&bar->tmem_base, TMEM_COLS);
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(&bar->full[s], 1);
+            tc::mbar_init(&bar->empty[s], 1);
+        }
+        tc::mbar_init(&bar->a_ready, EPI_THREADS);
+        tc::mbar_init(&bar->acc_full, 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    return smem;
+}
+__device__ __forceinline__ void chain_teardown(Barriers* bar) {
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(bar->tmem_base, TMEM_COLS);
+}
+
+// ---- warp 0: stream the packed weights of every step of every tile of this CTA -----------------
+__device__ __forceinline__ void producer_loop(const Program& prog, const uint8_t* __restrict__ chain_w,
+                                              uint8_t* smem, Barriers* bar, int n_my_tiles) {
+    if ((threadIdx.x & 31) != 0) return;
+    uint32_t stage = 0, phase = 0;
+    for (int t = 0; t < n_my_tiles; ++t) {
+        for (int s = 0; s < prog.n_steps; ++s) {
+            const Step st = prog.step[s];
+            const uint32_t bytes = (uint32_t)st.n_mma * 128u;
+            const uint8_t* src = chain_w + st.b_off;
+            for (int c = 0; c < 2 * st.kblocks; ++c) {
+                tc::mbar_wait(&bar->empty[stage], phase ^ 1u);
+                tc::mbar_arrive_expect_tx(&bar->full[stage], bytes);
+                tc::bulk_g2s(smem + RING_OFF + stage * STAGE_BYTES, src + (size_t)c * bytes, bytes, &bar->full[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    }
+}
+
+// ---- warp 1: issue the MMAs ----------------------------------------------------------------------
+// prof (may be NULL): per CTA {cycles waiting for the A operand, cycles waiting for weights, total cycles}
+__device__ __forceinline__ void mma_loop(const Program& prog, uint8_t* smem, Barriers* bar, int n_my_tiles,
+                                         long long* prof = nullptr) {
+    if ((threadIdx.x & 31) != 0) return;
+    long long t_a = 0, t_w = 0, t0 = clock64(), tt;
+    const uint32_t tmem = bar->tmem_base;
+    const uint32_t a_hi = tc::smem_u32(smem), a_lo = a_hi + A_LO_OFF, ring = a_hi + RING_OFF;
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    for (int t = 0; t < n_my_tiles; ++t) {
+        for (int s = 0; s < prog.n_steps; ++s) {
+            const Step st = prog.step[s];
+            const uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, st.n_mma);
+            tt = clock64();
+            tc::mbar_wait(&bar->a_ready, a_par);
+            t_a += clock64() - tt;
+            a_par ^= 1u;
+            tc::tc_fence_after_sync();
+            for (int kb = 0; kb < st.kblocks; ++kb) {
+                const uint64_t dAh = tc::make_smem_desc_sw128(a_hi + (uint32_t)(st.a_kb0 + kb) * KB_BYTES);
+                const uint64_t dAl = tc::make_smem_desc_sw128(a_lo + (uint32_t)(st.a_kb0 + kb) * KB_BYTES);
+                // stage "hi": A_lo B_hi^T + A_hi B_hi^T
+                tt = clock64();
+                tc::mbar_wait(&bar->full[stage], phase);
+                t_w += clock64() - tt;
+                tc::tc_fence_after_sync();
+                uint64_t dB = tc::make_smem_desc_sw128(ring + stage * STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tc::umma_f16(tmem, dAl + 2 * k, dB + 2 * k, idesc, (kb | k) != 0);
+                    tc::umma_f16(tmem, dAh + 2 * k, dB + 2 * k, idesc, 1);
+                }
+                tc::umma_commit(&bar->empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                // stage "lo": A_hi B_lo^T
+                tt = clock64();
+                tc::mbar_wait(&bar->full[stage], phase);
+                t_w += clock64() - tt;
+                tc::tc_fence_after_sync();
+                dB = tc::make_smem_desc_sw128(ring + stage * STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc::umma_f16(tmem, dAh + 2 * k, dB + 2 * k, idesc, 1);
+                tc::umma_commit(&bar->empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            tc::umma_commit(&bar->acc_full);
+        }
+    }
+    if (prof) {
+        prof[blockIdx.x * 4 + 0] = t_a;
+        prof[blockIdx.x * 4 + 1] = t_w;
+        prof[blockIdx.x * 4 + 2] = clock64() - t0;
+    }
+}
+
+// epilogue side of the handshake
+__device__ __forceinline__ void epi_publish_a(Barriers* bar) {
+    tc::tc_fence_before_sync();       // orders this thread's tcgen05.ld before the MMAs that overwrite the accumulator
+    tc::fence_proxy_async_smem();     // generic-proxy stores of the A operand -> visible to the MMA's async proxy
+    tc::mbar_arrive(&bar->a_ready);
+}
+__device__ __forceinline__ void epi_wait_acc(Barriers* bar, uint32_t& par) {
+    tc::mbar_wait(&bar->acc_full, par);
+    par ^= 1u;
+    tc::tc_fence_after_sync();
+}
+// rows 32*(warp%4) + lane (hardware: a warp reads the TMEM lane quarter warp_id % 4)
+// column group cg = 0..EPI_WARPS/4-1 of (256 / (EPI_WARPS/4)) columns
+constexpr int EPI_CGROUPS = EPI_WARPS / 4;
+constexpr int EPI_COLS = 256 / EPI_CGROUPS;
+__device__ __forceinline__ void epi_coords(int& row, int& cg) {
+    const int warp = threadIdx.x >> 5;
+    row = (warp & 3) * 32 + (threadIdx.x & 31);
+    cg = (warp - 2) >> 2;
+}
+__device__ __forceinline__ void acc_load32(uint32_t tmem_base, int row, int col0, float* v) {
+    tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(row & ~31) << 16) + (uint32_t)col0, v);
+    tc::tmem_ld_wait();
+}
+__device__ __forceinline__ void acc_load32_nowait(uint32_t tmem_base, int row, int col0, float* v) {
+    tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(row & ~31) << 16) + (uint32_t)col0, v);
+}
+
+// ---- packing ---------------------------------------------------------------------------------------
+// dst tile element (n, k) <- src[(row0 + n) * ld + col0 + k] for n < rows, k < cols, else 0;
+// layout: k-block kb at kb * 2 * n_pad * 128 B: hi tile then lo tile, each [n_pad x 128 B] SW128.
+int launch_pack_b(const float* src, int64_t ld, int row0, int col0, int rows, int cols, int n_pad, int kblocks,
+                  uint8_t* dst, cudaStream_t stream);
+
+}  // namespace chain
+}  // namespace hn

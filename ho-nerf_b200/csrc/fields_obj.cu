@@ -8,6 +8,10 @@
 
 namespace hn {
 
+namespace chain {   // chain_obj.cu
+int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s);
+}
+
 // ------------------------------------------------------------------------------------------
 // elementwise kernels of the object SDF net
 // ------------------------------------------------------------------------------------------
@@ -214,9 +218,13 @@ int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
     HN_REQUIRE(precision_supported(precision), "hn_sdf_obj_sdf: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (precision == HN_TC_BF16X3) {
+        HN_REQUIRE(pts && sdf, "hn_sdf_obj_sdf: null pointer");
+        return chain::launch_sdf_only(mlp, pts, n, inv_scale, sdf, s);
+    }
     HN_REQUIRE(pts && sdf && ws && ws_floats >= hn_sdf_obj_ws_floats(n, HN_WS_SDF_ONLY) && aligned16(ws),
                "hn_sdf_obj_sdf: workspace too small or misaligned");
-    cudaStream_t s = (cudaStream_t)stream;
     float* E = ws;
     float* P0 = E + n * 64;
     float* P1 = P0 + n * 256;

@@ -13,14 +13,16 @@ namespace hn {
 
 enum GemmRole { ROLE_VALUE = 0, ROLE_OTHER = 1 };
 
-inline bool precision_supported(int p) { return p == HN_SIMT_FP32 || p == HN_TC_TF32 || p == HN_TC_TF32X3; }
+inline bool precision_supported(int p) {
+    return p == HN_SIMT_FP32 || p == HN_TC_TF32 || p == HN_TC_TF32X3 || p == HN_TC_BF16X3;
+}
 
 // C = epi(A @ W^T)
 template <int EPI>
 int gemm_nt(const GemmArgs& g, cudaStream_t s, int precision, int role = ROLE_OTHER) {
     (void)role;
     if (precision == HN_SIMT_FP32) return launch_gemm<true, true, EPI>(g, s);
-    if (precision == HN_TC_TF32X3) return launch_gemm_tc<false, 3, EPI>(g, s);
+    if (precision == HN_TC_TF32X3 || precision == HN_TC_BF16X3) return launch_gemm_tc<false, 3, EPI>(g, s);
     return launch_gemm_tc<false, 1, EPI>(g, s);
 }
 // C = epi(A @ W)
@@ -32,16 +34,16 @@ int gemm_nn(const GemmArgs& g, cudaStream_t s, int precision, int role = ROLE_OT
         // a pre-transposed copy of the weights exists: run as x @ (W^T)^T, the cheap staging path
         GemmArgs t = g;
         t.B = g.BT; t.ldb = g.ldbt; t.BT = nullptr;
-        if (precision == HN_TC_TF32X3) return launch_gemm_tc<false, 3, EPI>(t, s);
+        if (precision == HN_TC_TF32X3 || precision == HN_TC_BF16X3) return launch_gemm_tc<false, 3, EPI>(t, s);
         return launch_gemm_tc<false, 1, EPI>(t, s);
     }
-    if (precision == HN_TC_TF32X3) return launch_gemm_tc<true, 3, EPI>(g, s);
+    if (precision == HN_TC_TF32X3 || precision == HN_TC_BF16X3) return launch_gemm_tc<true, 3, EPI>(g, s);
     return launch_gemm_tc<true, 1, EPI>(g, s);
 }
 // C += A^T @ B over points (weight gradients)
 inline int gemm_tn(const GemmArgs& g, cudaStream_t s, int precision, int splits) {
     if (precision == HN_SIMT_FP32) return launch_gemm<false, false, EPI_ATOMIC>(g, s, splits);
-    if (precision == HN_TC_TF32X3) return launch_gemm_tc_tn<3>(g, s, splits);
+    if (precision == HN_TC_TF32X3 || precision == HN_TC_BF16X3) return launch_gemm_tc_tn<3>(g, s, splits);
     return launch_gemm_tc_tn<1>(g, s, splits);
 }
 

@@ -162,6 +162,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): `bytes` % 16 == 0, both addresses 16 B aligned;
+// completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// named barrier among `nthreads` threads (id 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile(

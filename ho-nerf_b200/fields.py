@@ -224,7 +224,7 @@ class SDFNetwork_OBJ(nn.Module):
             layers = [(getattr(self, "lin%d" % l).weight_g, getattr(self, "lin%d" % l).weight_v,
                        getattr(self, "lin%d" % l).bias) for l in range(self.num_layers - 1)]
             scales = [ops.SQRT1_2 if l in self.skip_in else 1.0 for l in range(self.num_layers - 1)]
-            self._packed = ops.PackedMLP(layers, scales)
+            self._packed = ops.PackedMLP(layers, scales, chain_kind="sdf_obj")
         return self._packed
 
     def _apply(self, fn, *a, **k):      # .to()/.cuda()/.float() replace the parameter tensors

@@ -8,12 +8,14 @@ import torch
 from . import _lib
 from ._lib import HN_SIMT_FP32, HN_WS_BWD, HN_WS_SDF_ONLY, check, hn_mlp_grad_t, hn_mlp_t, lib
 
-_PRECISIONS = {"simt_fp32": _lib.HN_SIMT_FP32, "tc_tf32": _lib.HN_TC_TF32, "tc_tf32x3": _lib.HN_TC_TF32X3}
+_PRECISIONS = {"simt_fp32": _lib.HN_SIMT_FP32, "tc_tf32": _lib.HN_TC_TF32, "tc_tf32x3": _lib.HN_TC_TF32X3,
+               "tc_bf16x3": _lib.HN_TC_BF16X3}
 _default_precision = HN_SIMT_FP32
 
 
 def set_default_precision(name):
-    """'simt_fp32' (verification path) | 'tc_tf32' | 'tc_tf32x3' (split operands on the SDF value trunk)."""
+    """'simt_fp32' (verification path) | 'tc_tf32' | 'tc_tf32x3' (split TF32 operands, per-layer kernels) |
+    'tc_bf16x3' (fused tile-chain kernels, split bf16 operands)."""
     global _default_precision
     _default_precision = _PRECISIONS[name]
 
@@ -52,7 +54,7 @@ class PackedMLP:
     """Effective weights of a stack of weight-normalised Linears, packed once per parameter
     version by hn_wn_pack (the reference recomputes g*v/||v|| inside every Linear call)."""
 
-    def __init__(self, layers, post_scales, gaps=None):
+    def __init__(self, layers, post_scales, gaps=None, chain_kind=None):
         # layers: list of (weight_g [out,1], weight_v [out,in], bias [out]) parameters
         # gaps: per layer (gap_at, gap): `gap` zero columns inserted after input column gap_at of
         #       the packed layout (hand colour net, see include/honerf_b200.h)
@@ -78,6 +80,8 @@ class PackedMLP:
         self.WT = None
         self.W = None
         self.bias = None
+        self.chain_kind = chain_kind        # 'sdf_obj': also pack the HN_TC_BF16X3 chain operands
+        self.chain = None
         self.struct = None
         self._key = None
 
@@ -110,6 +114,14 @@ class PackedMLP:
             st.WT[l] = WTl.data_ptr()
             st.ldT[l] = self.ldTs[l]
             st.b[l] = bd.data_ptr()
+        if self.chain_kind == "sdf_obj":
+            nbytes = int(lib.hn_sdf_obj_chain_bytes())
+            if self.chain is None or self.chain.device != dev:
+                self.chain = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            check(lib.hn_sdf_obj_chain_pack(ctypes.byref(st), _ptr(self.chain), nbytes, _stream(self.W)),
+                  "hn_sdf_obj_chain_pack")
+            st.chain = self.chain.data_ptr()
+            st.chain_bytes = nbytes
         self._keep = keep
         self.struct = st
         self._key = key
@@ -603,6 +615,87 @@ def neus_composite(sdf, normal, rgb, dists, rays_d, variance, seed_with_c0=True)
     Returns color [B,3], weights [B,n], cdf [B,n], weight_sum [B,1], weight_max [B,1],
     eik [B] (per-ray sums of (||n||-1)^2)."""
     return _CompositeFn.apply(sdf, normal, rgb, dists, rays_d, variance, seed_with_c0)
+
+
+class _AlphaFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sdf, normal, dists, rays_d, variance):
+        sdf_c, nrm_c = _f32c(sdf.detach()), _f32c(normal.detach())
+        dist_c, d_c, var_c = _f32c(dists.detach()), _f32c(rays_d.detach()), _f32c(variance.detach()).reshape(1)
+        _require_cuda(sdf_c, "neus_alpha")
+        B, n = dist_c.shape
+        alpha = torch.empty(B, n, device=sdf_c.device)
+        eik = torch.empty(B, device=sdf_c.device)
+        check(lib.hn_neus_alpha_fwd(_ptr(sdf_c), _ptr(nrm_c), _ptr(dist_c), _ptr(d_c), _ptr(var_c), B, n, _ptr(alpha),
+                                    _ptr(eik), _stream(sdf_c)), "hn_neus_alpha_fwd")
+        ctx.save_for_backward(sdf_c, nrm_c, dist_c, d_c, var_c)
+        ctx.need_d = rays_d.requires_grad
+        ctx.shapes = (sdf.shape, normal.shape, rays_d.shape, variance.shape)
+        return alpha, eik
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_alpha, d_eik):
+        sdf_c, nrm_c, dist_c, d_c, var_c = ctx.saved_tensors
+        B, n = dist_c.shape
+        dev = sdf_c.device
+        d_alpha = _f32c(d_alpha) if d_alpha is not None else None
+        d_eik = _f32c(d_eik) if d_eik is not None else None
+        d_sdf = torch.empty(B * n, 1, device=dev)
+        d_nrm = torch.empty(B * n, 3, device=dev)
+        d_rd = torch.empty(B, 3, device=dev) if ctx.need_d else None
+        d_var = torch.zeros(1, device=dev)
+        check(lib.hn_neus_alpha_bwd(_ptr(sdf_c), _ptr(nrm_c), _ptr(dist_c), _ptr(d_c), _ptr(var_c), B, n, _ptr(d_alpha),
+                                    _ptr(d_eik), _ptr(d_sdf), _ptr(d_nrm), _ptr(d_rd), _ptr(d_var), _stream(sdf_c)),
+              "hn_neus_alpha_bwd")
+        s_sdf, s_nrm, s_rd, s_var = ctx.shapes
+        return (d_sdf.reshape(s_sdf), d_nrm.reshape(s_nrm), None, d_rd.reshape(s_rd) if d_rd is not None else None,
+                d_var.reshape(s_var))
+
+
+def neus_alpha(sdf, normal, dists, rays_d, variance):
+    """alpha of get_alpha_sample_color (utils/renderer.py:396-420): sdf [B*n,1], normal [B*n,3],
+    dists [B,n], rays_d [B,3] -> alpha [B,n], eik [B] (per-ray sums of (||n||-1)^2)."""
+    return _AlphaFn.apply(sdf, normal, dists, rays_d, variance)
+
+
+class _FitCompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha_h, rgb_h, alpha_o, rgb_o):
+        ah, ao = _f32c(alpha_h.detach()), _f32c(alpha_o.detach())
+        ch, co = _f32c(rgb_h.detach()), _f32c(rgb_o.detach())
+        _require_cuda(ah, "fit_composite")
+        B, n = ah.shape
+        dev = ah.device
+        trans = torch.empty(B, n, device=dev)
+        color = torch.empty(B, 3, device=dev)
+        wsum = torch.empty(B, 1, device=dev)
+        check(lib.hn_fit_composite_fwd(_ptr(ah), _ptr(ch), _ptr(ao), _ptr(co), B, n, _ptr(trans), _ptr(color),
+                                       _ptr(wsum), _stream(ah)), "hn_fit_composite_fwd")
+        ctx.save_for_backward(ah, ch, ao, co, trans)
+        ctx.rgb_shapes = (rgb_h.shape, rgb_o.shape)
+        return color, wsum
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, d_color, d_wsum):
+        ah, ch, ao, co, trans = ctx.saved_tensors
+        B, n = ah.shape
+        dev = ah.device
+        d_color = _f32c(d_color) if d_color is not None else None
+        d_wsum = _f32c(d_wsum) if d_wsum is not None else None
+        d_ah, d_ao = torch.empty(B, n, device=dev), torch.empty(B, n, device=dev)
+        d_ch, d_co = torch.empty(B * n, 3, device=dev), torch.empty(B * n, 3, device=dev)
+        check(lib.hn_fit_composite_bwd(_ptr(ah), _ptr(ch), _ptr(ao), _ptr(co), _ptr(trans), B, n, _ptr(d_color),
+                                       _ptr(d_wsum), _ptr(d_ah), _ptr(d_ch), _ptr(d_ao), _ptr(d_co), _stream(ah)),
+              "hn_fit_composite_bwd")
+        return d_ah, d_ch.reshape(ctx.rgb_shapes[0]), d_ao, d_co.reshape(ctx.rgb_shapes[1])
+
+
+def fit_composite(alpha_h, rgb_h, alpha_o, rgb_o):
+    """Joint two-field compositing (utils/renderer.py:512-524): alpha [B,n], rgb [B,n,3] (or [B*n,3])
+    -> color [B,3], weight_sum [B,1]."""
+    return _FitCompositeFn.apply(alpha_h, rgb_h, alpha_o, rgb_o)
 
 
 SQRT1_2 = 1.0 / math.sqrt(2.0)

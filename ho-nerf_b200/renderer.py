@@ -151,3 +151,191 @@ class NeuSRenderer:
         triangles = triangles[..., ::-1]
         vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
         return vertices, triangles
+
+
+class _FittingBase:
+    """Shared implementation of the two NeuSRenderer_fitting classes (utils/renderer.py:286-572,
+    utils/renderer_batch.py:41-371).  Rays carry a leading shape ``lead`` = (B,) or (F, P); the
+    kernels see the flattened [prod(lead), ...] buffers."""
+
+    def __init__(self, sdf_network_hand, deviation_network_hand, color_network_hand, sdf_network_obj,
+                 deviation_network_obj, color_network_obj, n_samples, n_importance, n_outside, up_sample_steps,
+                 perturb):
+        self.sdf_network_hand = sdf_network_hand
+        self.deviation_network_hand = deviation_network_hand
+        self.color_network_hand = color_network_hand
+        self.sdf_network_obj = sdf_network_obj
+        self.deviation_network_obj = deviation_network_obj
+        self.color_network_obj = color_network_obj
+        self.use_multiple_streams = True    # stored and never read, as in the reference (SURVEY D-5)
+        self.n_samples = n_samples
+        self.n_importance = n_importance
+        self.n_outside = n_outside
+        self.up_sample_steps = up_sample_steps
+        self.perturb = perturb
+
+    # -- helpers ---------------------------------------------------------------------------------
+    def _hand_pts(self, pts, lead):
+        """Hand SDF input: un-batched [N,3]; frame-batched [F, N/F, 3] (utils/renderer_batch.py:107,143)."""
+        return pts if len(lead) == 1 else pts.reshape(lead[0], -1, 3)
+
+    def _sdf_only(self, ctype, pts, lead, bt_inv, T_pose_21):
+        if ctype == 'obj':
+            return self.sdf_network_obj.sdf(pts)
+        return self.sdf_network_hand.sdf(self._hand_pts(pts, lead), bt_inv, T_pose_21)
+
+    # -- reference public methods ----------------------------------------------------------------
+    def up_sample(self, rays_o, rays_d, z_vals, sdf, n_importance, inv_s):
+        lead = z_vals.shape[:-1]
+        n = z_vals.shape[-1]
+        out = ops.up_sample(z_vals.reshape(-1, n), sdf.reshape(-1, n), n_importance, inv_s)
+        return out.reshape(*lead, n_importance)
+
+    def cat_z_vals(self, rays_o, rays_d, z_vals, new_z_vals, sdf, bt_inv, T_pose_21, ctype, last=False):
+        lead = z_vals.shape[:-1]
+        m, k = z_vals.shape[-1], new_z_vals.shape[-1]
+        za, zb = z_vals.reshape(-1, m), new_z_vals.reshape(-1, k)
+        if last:
+            z, _, _ = ops.merge_sorted(za, zb)
+            return z.reshape(*lead, m + k), sdf
+        with torch.no_grad():
+            pts = ops.ray_points(rays_o.reshape(-1, 3), rays_d.reshape(-1, 3), zb)
+            new_sdf = self._sdf_only(ctype, pts, lead, bt_inv, T_pose_21).reshape(-1, k)
+        # frame-batched quirk (SURVEY D-7): the re-ordered SDF rows all come from frame 0
+        row_mod = lead[1] if len(lead) == 2 else 0
+        z, s, _ = ops.merge_sorted(za, zb, sdf.reshape(-1, m), new_sdf, sdf_row_mod=row_mod)
+        return z.reshape(*lead, m + k), s.reshape(*lead, m + k)
+
+    def get_alpha_sample_color(self, rays_o, rays_d, bt_inv, T_pose_21, z_vals, sample_dist, ctype, get_SDF=False):
+        lead = z_vals.shape[:-1]
+        n = z_vals.shape[-1]
+        ro, rd = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+        pts, dists = ops.mid_points(ro, rd, z_vals.reshape(-1, n), sample_dist)
+        dirs = rd[:, None, :].expand(rd.shape[0], n, 3).reshape(-1, 3)
+        if ctype == 'obj':
+            sdf, feature_vector, gradients = self.sdf_network_obj.fused(pts)
+            sampled_color = self.color_network_obj(pts, dirs, feature_vector, gradients, 0)
+            variance = self.deviation_network_obj.variance
+        else:
+            sdf, feature_vector, gradients, xyz_feature = self.sdf_network_hand.fused(
+                self._hand_pts(pts, lead), bt_inv, T_pose_21)
+            sampled_color = self.color_network_hand(dirs, xyz_feature, feature_vector, None, gradients, 0)
+            variance = self.deviation_network_hand.variance
+        alpha, eik = ops.neus_alpha(sdf, gradients, dists, rd, variance)
+        gradient_error = eik.sum() / float(eik.shape[0] * n)
+        return (alpha.reshape(*lead, n), sampled_color.reshape(*lead, n, 3), sdf.reshape(-1, 1), gradient_error,
+                gradients.reshape(-1, 3))
+
+    def _render(self, rays_o, rays_d, near, far, bt_inv, T_pose_21, Ro, To):
+        lead = rays_o.shape[:-1]
+        device = rays_o.device
+        rays_o_hand, rays_d_hand = rays_o, rays_d
+        rays_o_obj, rays_d_obj = self.convert_obj_to_local(rays_o, rays_d, Ro, To)
+        sample_dist = (far - near) / self.n_samples
+        z_vals = _linspace_z(near, far, self.n_samples, device)
+        if self.perturb > 0:
+            t_rand = torch.rand([*lead, 1], device=device) - 0.5
+            z_vals = z_vals + t_rand * sample_dist
+        else:
+            z_vals = z_vals.expand(*lead, self.n_samples)
+        z_vals = z_vals.contiguous()
+        z_vals_hand = z_vals_obj = z_vals
+        if self.n_importance > 0:
+            with torch.no_grad():
+                flat = z_vals.reshape(-1, self.n_samples)
+                pts_hand = ops.ray_points(rays_o_hand.reshape(-1, 3), rays_d_hand.reshape(-1, 3), flat)
+                pts_obj = ops.ray_points(rays_o_obj.reshape(-1, 3), rays_d_obj.reshape(-1, 3), flat)
+                sdf_hand = self._sdf_only('hand', pts_hand, lead, bt_inv, T_pose_21).reshape(*lead, self.n_samples)
+                sdf_obj = self._sdf_only('obj', pts_obj, lead, bt_inv, T_pose_21).reshape(*lead, self.n_samples)
+                new_all = [z_vals]
+                for i in range(self.up_sample_steps):
+                    last = i + 1 == self.up_sample_steps
+                    k = self.n_importance // self.up_sample_steps
+                    new_hand = self.up_sample(rays_o_hand, rays_d_hand, z_vals_hand, sdf_hand, k, 64 * 2 ** i)
+                    z_vals_hand, sdf_hand = self.cat_z_vals(rays_o_hand, rays_d_hand, z_vals_hand, new_hand, sdf_hand,
+                                                            bt_inv, T_pose_21, 'hand', last=last)
+                    new_obj = self.up_sample(rays_o_obj, rays_d_obj, z_vals_obj, sdf_obj, k, 64 * 2 ** i)
+                    z_vals_obj, sdf_obj = self.cat_z_vals(rays_o_obj, rays_d_obj, z_vals_obj, new_obj, sdf_obj,
+                                                          bt_inv, T_pose_21, 'obj', last=last)
+                    new_all += [new_hand, new_obj]
+                z_vals = torch.cat(new_all, dim=-1)
+        n = z_vals.shape[-1]
+        z_vals = ops.sort_rows(z_vals.reshape(-1, n)).reshape(*lead, n)
+        self.last_z_vals = z_vals
+
+        alpha_hand, color_hand, sdf_hand, ge_hand, grad_hand = self.get_alpha_sample_color(
+            rays_o_hand, rays_d_hand, bt_inv, T_pose_21, z_vals, sample_dist, 'hand')
+        alpha_obj, color_obj, sdf_obj, ge_obj, grad_obj = self.get_alpha_sample_color(
+            rays_o_obj, rays_d_obj, bt_inv, T_pose_21, z_vals, sample_dist, 'obj')
+        color, weights_sum = ops.fit_composite(alpha_hand.reshape(-1, n), color_hand.reshape(-1, n, 3),
+                                               alpha_obj.reshape(-1, n), color_obj.reshape(-1, n, 3))
+        return {
+            'color_fine': color.reshape(*lead, 3),
+            'weight_sum': weights_sum.reshape(*lead, 1),
+            'sdf_hand': sdf_hand,
+            'sdf_obj': sdf_obj,
+            'gradient_error_hand': ge_hand,
+            'gradient_error_obj': ge_obj,
+            'gradient_hand': grad_hand,
+            'gradient_obj': grad_obj,
+        }
+
+    def _grid(self, bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type, chunk_points=1 << 20):
+        device = next(self.sdf_network_hand.parameters()).device
+        xs = torch.linspace(float(bound_min[0]), float(bound_max[0]), resolution).to(device)
+        ys = torch.linspace(float(bound_min[1]), float(bound_max[1]), resolution).to(device)
+        zs = torch.linspace(float(bound_min[2]), float(bound_max[2]), resolution).to(device)
+        u = torch.empty(resolution, resolution, resolution, device=device)
+        slab = max(1, chunk_points // (resolution * resolution))
+        with torch.no_grad():
+            for x0 in range(0, resolution, slab):
+                xx, yy, zz = torch.meshgrid(xs[x0:x0 + slab], ys, zs, indexing='ij')
+                pts = torch.stack([xx, yy, zz], dim=-1).reshape(-1, 3)
+                if get_type == 'hand':
+                    val = self.sdf_network_hand.sdf(self._grid_hand_pts(pts), bt_inv, T_pose_21)
+                else:
+                    val = self.sdf_network_obj.sdf(self._grid_obj_pts(pts, Ro, To))
+                u[x0:x0 + slab] = val.reshape(xx.shape)
+        return u
+
+    def sdf_grid(self, bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type):
+        """Device-resident ``u`` lattice of extract_geometry (no per-chunk host round trip)."""
+        return self._grid(bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type)
+
+    def extract_geometry(self, bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type, threshold=0.0):
+        u = self.sdf_grid(bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type).cpu().numpy()
+        import mcubes  # noqa: deferred, optional third-party dependency exactly as in the reference
+        vertices, triangles = mcubes.marching_cubes(u, threshold)
+        b_max_np = bound_max.detach().cpu().numpy()
+        b_min_np = bound_min.detach().cpu().numpy()
+        triangles = triangles[..., ::-1]
+        vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
+        return vertices, triangles
+
+
+class NeuSRenderer_fitting(_FittingBase):
+    """utils/renderer.py:286-572 (per-view hand + object renderer used by fitting_single.py / get_res.py)."""
+
+    def convert_obj_to_local(self, rays_o, rays_d, Ro, To):
+        """utils/renderer.py:424-432."""
+        rays_o = rays_o - To.unsqueeze(0)
+        rays_o = torch.matmul(Ro.unsqueeze(0), rays_o.unsqueeze(-1))[..., -1]
+        rays_d = torch.matmul(Ro.unsqueeze(0), rays_d.unsqueeze(-1))[..., -1]
+        return rays_o, rays_d
+
+    def render(self, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, Ro, To, get_SDF=False):
+        """utils/renderer.py:434-535."""
+        return self._render(rays_o, rays_d, near, far, bt_inv, T_pose_21, Ro, To)
+
+    def _grid_hand_pts(self, pts):
+        return pts
+
+    def _grid_obj_pts(self, pts, Ro, To):
+        obj_pts = pts - To.unsqueeze(0)
+        return torch.matmul(Ro.unsqueeze(0), obj_pts.unsqueeze(-1))[..., 0]
+
+    def get_inner_point_id(self, pts, bt_inv, T_pose_21):
+        """utils/renderer.py:566-572."""
+        with torch.no_grad():
+            val = self.sdf_network_hand.sdf(pts.reshape(-1, 3), bt_inv, T_pose_21).detach().cpu().numpy().reshape(-1)
+        return np.array(np.where(val <= 0))[0]

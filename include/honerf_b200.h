@@ -36,8 +36,13 @@ enum hn_status { HN_OK = 0, HN_ERR_ARG = -1, HN_ERR_CUDA = -2, HN_ERR_UNSUPPORTE
  *   HN_TC_TF32   every contraction with single-pass TF32 operands (fast; ~1e-3 relative per layer);
  *   HN_TC_TF32X3 every contraction with split (hi+lo) TF32 operands -- three MMAs per product,
  *                ~fp32 accuracy; the mode that meets the parity tolerances (1e-3 abs on colour/SDF,
- *                1e-2 relative on gradients) with margin. */
-enum hn_precision { HN_SIMT_FP32 = 0, HN_TC_TF32 = 1, HN_TC_TF32X3 = 2 };
+ *                1e-2 relative on gradients) with margin.
+ *   HN_TC_BF16X3 fused tile-chain kernels: a 128-point tile's activations stay in shared memory
+ *                between layers as split (hi+lo) bf16 operands, three bf16 MMAs per product, weights
+ *                streamed from the pre-packed chain buffer (hn_*_chain_pack).  ~16 mantissa bits:
+ *                8e-6 abs on the SDF, 5e-5 relative on weight gradients (oracle/analytic.py).
+ *                Entry points without a chain kernel run their HN_TC_TF32X3 path. */
+enum hn_precision { HN_SIMT_FP32 = 0, HN_TC_TF32 = 1, HN_TC_TF32X3 = 2, HN_TC_BF16X3 = 3 };
 
 HN_API const char* hn_last_error(void);
 HN_API int hn_version(void);
@@ -68,6 +73,9 @@ typedef struct hn_mlp {
      * both x @ W^T and d @ W as K-major operands.  May be NULL for HN_SIMT_FP32. */
     const float* WT[HN_MAX_LAYERS];
     int32_t ldT[HN_MAX_LAYERS];
+    /* HN_TC_BF16X3: bf16 hi/lo operands pre-swizzled for tcgen05 (hn_*_chain_pack); else NULL */
+    const void* chain;
+    int64_t chain_bytes;
 } hn_mlp_t;
 
 typedef struct hn_mlp_grad {
@@ -103,6 +111,17 @@ HN_API int hn_wn_bwd(const float* v, const float* g, const float* dW, int out_di
 enum hn_ws_kind { HN_WS_SDF_ONLY = 0, HN_WS_FWD = 1, HN_WS_BWD = 2 };
 HN_API int64_t hn_sdf_obj_stash_floats(int64_t n_pts);
 HN_API int64_t hn_sdf_obj_ws_floats(int64_t n_pts, int ws_kind);
+
+/* Pack the object SDF net's weights (W and WT of `mlp`, already weight-normalised by hn_wn_pack)
+ * into the HN_TC_BF16X3 chain buffer: bf16 hi/lo tiles in the tcgen05 shared-memory layout. */
+HN_API int64_t hn_sdf_obj_chain_bytes(void);
+HN_API int hn_sdf_obj_chain_pack(const hn_mlp_t* mlp, void* chain, int64_t chain_bytes,
+                                 hn_stream_t stream);
+
+/* Diagnostics: device buffer of int64 [n_ctas][4] that the chain kernels fill with cycle counters
+ * {MMA warp waiting for activations, waiting for weights, total, epilogue waiting for the
+ * accumulator}; NULL disables. */
+HN_API int hn_chain_set_prof(void* buf);
 
 /* sdf[n] = SDFNetwork_OBJ.sdf(pts) (utils/fields.py:330-331); no stash, no normal. */
 HN_API int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n_pts, float inv_scale,
@@ -240,6 +259,34 @@ HN_API int hn_neus_composite_bwd(const float* sdf, const float* normal, const fl
                                  const float* d_weights, const float* d_eik, float* d_sdf,
                                  float* d_normal, float* d_rgb, float* d_rays_d,
                                  float* d_variance, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Two-field (hand + object) fitting compositor, one warp per ray, n <= 256.
+ * hn_neus_alpha_*: NeuSRenderer_fitting.get_alpha_sample_color's alpha and eikonal sums
+ *   (utils/renderer.py:396-420; utils/renderer_batch.py:150-172): alpha [B,n], eik [B] = per-ray
+ *   sums of (||normal||-1)^2.  Backward overwrites d_sdf [B*n], d_normal [B*n,3], d_rays_d [B,3]
+ *   (may be NULL) and ACCUMULATES d_variance (1 float, caller zeroes); d_alpha / d_eik may be NULL.
+ * hn_fit_composite_*: T_i = prod_{j<i} (1-a_h+1e-7)(1-a_o+1e-7) with a leading ONE (SURVEY D-1),
+ *   color = sum a_h T rgb_h + sum a_o T rgb_o, weight_sum = sum a_h T + sum a_o T
+ *   (utils/renderer.py:512-524; utils/renderer_batch.py:258-270).  trans [B,n] is the stash the
+ *   backward reads.  d_color [B,3] / d_weight_sum [B] may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+HN_API int hn_neus_alpha_fwd(const float* sdf, const float* normal, const float* dists,
+                             const float* rays_d, const float* variance, int64_t n_rays, int n,
+                             float* alpha, float* eik, hn_stream_t stream);
+HN_API int hn_neus_alpha_bwd(const float* sdf, const float* normal, const float* dists,
+                             const float* rays_d, const float* variance, int64_t n_rays, int n,
+                             const float* d_alpha, const float* d_eik, float* d_sdf,
+                             float* d_normal, float* d_rays_d, float* d_variance,
+                             hn_stream_t stream);
+HN_API int hn_fit_composite_fwd(const float* alpha_h, const float* rgb_h, const float* alpha_o,
+                                const float* rgb_o, int64_t n_rays, int n, float* trans,
+                                float* color, float* weight_sum, hn_stream_t stream);
+HN_API int hn_fit_composite_bwd(const float* alpha_h, const float* rgb_h, const float* alpha_o,
+                                const float* rgb_o, const float* trans, int64_t n_rays, int n,
+                                const float* d_color, const float* d_weight_sum, float* d_alpha_h,
+                                float* d_rgb_h, float* d_alpha_o, float* d_rgb_o,
+                                hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Diagnostics: C[M,N] (fp32) = A[M,K] * B[N,K]^T with fp16 (or bf16) operands on tcgen05 tensor cores

@@ -1,0 +1,62 @@
+"""Micro-benchmark of the fused tile-chain kernels (run on a B200): device time per call with CUDA events."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+import honerf_b200 as H  # noqa: E402
+from gpu_util import obj_modules  # noqa: E402
+
+F_O = 1049088
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def main():
+    sdf, col, dev, _, _ = obj_modules(requires_grad=False)
+    for n in (65536, 1 << 20):
+        x = (0.45 * torch.randn(n, 3)).cuda()
+        for prec in ("tc_bf16x3", "tc_tf32x3", "simt_fp32"):
+            p = H.ops._PRECISIONS[prec]
+            ms = timeit(lambda: H.ops.sdf_obj_sdf_only(sdf.packed(), x, 1.0, precision=p))
+            print("sdf_only n=%d %-10s %.3f ms  %.1f algorithmic TFLOP/s" % (n, prec, ms, n * (F_O - 2 * 257 * 256 + 512) / ms / 1e9))
+
+
+def prof():
+    """cycle split of the chain kernel's MMA warp / epilogue (1M points)"""
+    import ctypes
+    sdf, col, dev, _, _ = obj_modules(requires_grad=False)
+    n = 1 << 20
+    x = (0.45 * torch.randn(n, 3)).cuda()
+    buf = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+    p = H.ops._PRECISIONS["tc_bf16x3"]
+    H.ops.sdf_obj_sdf_only(sdf.packed(), x, 1.0, precision=p)
+    H._lib.lib.hn_chain_set_prof(ctypes.c_void_p(buf.data_ptr()))
+    H.ops.sdf_obj_sdf_only(sdf.packed(), x, 1.0, precision=p)
+    torch.cuda.synchronize()
+    H._lib.lib.hn_chain_set_prof(None)
+    b = buf.reshape(148, 4).double().mean(0).tolist()
+    print("MMA warp: wait A %.0f  wait weights %.0f  total %.0f cycles;  epilogue waits for acc %.0f  (per CTA, 55 tiles x 8 layers)"
+          % tuple(b))
+    steps = (n / 128 / 148) * 8
+    print("per layer-tile: total %.0f  waitA %.0f  waitW %.0f  mma-issue+rest %.0f ; epi wait acc %.0f"
+          % (b[2] / steps, b[0] / steps, b[1] / steps, (b[2] - b[0] - b[1]) / steps, b[3] / steps))
+
+
+if __name__ == "__main__":
+    prof()
+    main()
