@@ -281,7 +281,8 @@ def run_gpu_arm(args):
             "metric": "rays/sec render fwd+bwd (64+64 samples), object-field train step",
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"simt_fp32": "f32", "tc_tf32": "tf32", "tc_tf32x3": "tf32 (3xTF32 split on the SDF value trunk)"}[args.precision],
+            "dtype": {"simt_fp32": "f32", "tc_tf32": "tf32", "tc_tf32x3": "tf32 (3xTF32 split operands)",
+                      "tc_bf16x3": "bf16 (split hi+lo operands, 3 MMAs per product, fp32 accumulate)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": "obj-field train step (BASELINE configs[2]): %d rays/GPU x (64+64) samples, "
                                    "masked-L1+BCE+eikonal loss, 2nd-order bwd, Adam" % n_rays,
@@ -389,7 +390,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays", type=int, default=512, help="rays per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="simt_fp32", choices=["simt_fp32", "tc_tf32", "tc_tf32x3"])
+    ap.add_argument("--precision", default="simt_fp32", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -63,6 +63,9 @@ struct Barriers {
     uint32_t tmem_base;
 };
 
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
 // ---- bf16 hi/lo split ------------------------------------------------------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);

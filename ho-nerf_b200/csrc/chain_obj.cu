@@ -83,11 +83,19 @@ static ObjLayout obj_layout() {
 // [x(3), sin/cos(2^k x_c)] of one point written as columns shift + j of the A operand; the column
 // groups of a row share the 30 (coordinate, frequency) pairs.  Column shift+63 (the K padding of the
 // first layer) is zeroed when shift == 0.
-__device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, const float x[3], int shift) {
+// `g` (may be NULL): fp32 copy for the stash, g[j] = e_j.
+__device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, const float x[3], int shift,
+                                               float* __restrict__ g = nullptr) {
     if (cg == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) a_store1(smem, row, shift + c, x[c]);
-        if (shift == 0) a_store1(smem, row, 63, 0.0f);
+        for (int c = 0; c < 3; ++c) {
+            a_store1(smem, row, shift + c, x[c]);
+            if (g) g[c] = x[c];
+        }
+        if (shift == 0) {
+            a_store1(smem, row, 63, 0.0f);
+            if (g) g[63] = 0.0f;
+        }
     }
     for (int idx = cg; idx < 30; idx += EPI_CGROUPS) {
         const int c = idx / 10, k = idx - c * 10;
@@ -95,6 +103,7 @@ __device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, c
         sincosf(x[c] * (float)(1 << k), &s, &co);
         a_store1(smem, row, shift + 3 + c * 20 + k, s);
         a_store1(smem, row, shift + 3 + c * 20 + 10 + k, co);
+        if (g) { g[3 + c * 20 + k] = s; g[3 + c * 20 + 10 + k] = co; }
     }
 }
 
@@ -196,6 +205,439 @@ sdf_only_kernel(const __grid_constant__ SdfOnlyParams p, const __grid_constant__
     chain_teardown(&bar);
 }
 
+// ------------------------------------------------------------------------------------------------
+// value + feature + analytic normal (SDFNetwork_OBJ.forward + .gradient, utils/fields.py:316-347) with
+// the stash of hn_sdf_obj_bwd: 17 chained layers per tile -- value trunk (8), feature head (1), normal
+// sweep (7 + the 64-wide encoding layer).
+// ------------------------------------------------------------------------------------------------
+struct FwdParams {
+    const float* pts;
+    int64_t n;
+    float inv_scale;
+    float* sdf;
+    float* feat;
+    int64_t ld_feat;
+    float* normal;
+    float* E;          // stash pieces, same layout as the per-layer path (fields_obj.cu: ObjSdfStash)
+    float* H[8];
+    float* D[8];
+    float* EB;
+    const uint8_t* chain;
+    const float* bias[9];
+    const float* w_out0;
+    int n_tiles;
+    long long* prof;
+};
+
+__device__ __forceinline__ float sprime_fast(float h) { return 1.0f - __expf(-100.0f * h); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Program prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Barriers bar;
+    uint8_t* smem = chain_setup(smem_raw, &bar);
+    const int warp = threadIdx.x >> 5;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        producer_loop(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        mma_loop(prog, smem, &bar, n_my_tiles, p.prof);
+    } else {
+        int row, cg;
+        epi_coords(row, cg);
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            float x[3] = {0.f, 0.f, 0.f};
+            if (live) { x[0] = p.pts[gp * 3]; x[1] = p.pts[gp * 3 + 1]; x[2] = p.pts[gp * 3 + 2]; }
+            write_encoding(smem, row, cg, x, 0, live ? p.E + gp * 64 : nullptr);
+            epi_publish_a(&bar);
+            // ---- value trunk ----------------------------------------------------------------------
+            float head = 0.0f;
+            for (int l = 0; l < 8; ++l) {
+                epi_wait_acc(&bar, acc_par);
+                const float* __restrict__ bias = p.bias[l];
+                float* __restrict__ hrow = p.H[l] + gp * 256;
+                const bool skip_tail = l == 3 && cg == EPI_CGROUPS - 1;      // columns >= 192: below
+                if (!skip_tail) {
+#pragma unroll
+                    for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                        const int col0 = cg * EPI_COLS + blk * 32;
+                        float v[32];
+                        acc_load32(tmem, row, col0, v);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                            v[j] = softplus100_fast(v[j] + b.x);
+                            v[j + 1] = softplus100_fast(v[j + 1] + b.y);
+                            v[j + 2] = softplus100_fast(v[j + 2] + b.z);
+                            v[j + 3] = softplus100_fast(v[j + 3] + b.w);
+                            if (live) st4(hrow + col0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                        if (l == 7) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
+                                head += v[j] * w.x + v[j + 1] * w.y + v[j + 2] * w.z + v[j + 3] * w.w;
+                            }
+                        }
+                    }
+                }
+                if (l == 3) {
+                    if (cg == EPI_CGROUPS - 1) {
+                        float v[32];
+                        acc_load32(tmem, row, 192, v);
+                        const float h = softplus100_fast(v[0] + __ldg(bias + 192));
+                        a_store1(smem, row, 192, h);
+                        if (live) hrow[192] = h;
+                    }
+                    write_encoding(smem, row, cg, x, 193, live ? hrow + 193 : nullptr);
+                }
+                epi_publish_a(&bar);
+            }
+            // sdf = (h7 . W_out[0] + b_out[0]) / scale; the 4 column groups meet through the (still unused) EB rows
+            if (live) p.EB[gp * 64 + cg] = head;
+            tc::named_bar_sync(1, EPI_THREADS);
+            if (cg == 0 && live) {
+                const float4 h4 = *reinterpret_cast<const float4*>(p.EB + gp * 64);
+                p.sdf[gp] = (h4.x + h4.y + h4.z + h4.w + __ldg(p.bias[8])) * p.inv_scale;
+            }
+            // ---- feature head; seed of the normal sweep D7 = s'(h7) * W_out[0] / scale ----------------
+            epi_wait_acc(&bar, acc_par);
+            {
+                const float* __restrict__ bias = p.bias[8] + 1;
+#pragma unroll
+                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                    const int col0 = cg * EPI_COLS + blk * 32;
+                    float v[32];
+                    acc_load32(tmem, row, col0, v);
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            st4(p.feat + gp * p.ld_feat + col0 + j,
+                                make_float4(v[j] + __ldg(bias + col0 + j), v[j + 1] + __ldg(bias + col0 + j + 1),
+                                            v[j + 2] + __ldg(bias + col0 + j + 2), v[j + 3] + __ldg(bias + col0 + j + 3)));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float h[8];
+                        a_load8(smem, row, col0 + j, h);
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
+                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j + 4));
+                        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) h[i] = sprime_fast(h[i]) * w[i] * p.inv_scale;
+                        a_store8(smem, row, col0 + j, h);
+                        if (live) {
+                            st4(p.D[7] + gp * 256 + col0 + j, make_float4(h[0], h[1], h[2], h[3]));
+                            st4(p.D[7] + gp * 256 + col0 + j + 4, make_float4(h[4], h[5], h[6], h[7]));
+                        }
+                    }
+                }
+            }
+            epi_publish_a(&bar);
+            // ---- normal sweep: D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1 ------------------------------
+            for (int l = 7; l >= 1; --l) {
+                epi_wait_acc(&bar, acc_par);
+                const float* __restrict__ hrow = p.H[l - 1] + gp * 256;
+                float* __restrict__ drow = p.D[l - 1] + gp * 256;
+#pragma unroll
+                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                    const int col0 = cg * EPI_COLS + blk * 32;
+                    float v[32];
+                    acc_load32(tmem, row, col0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) h = ld4(hrow + col0 + j);
+                        float d[4] = {v[j] * sprime_fast(h.x), v[j + 1] * sprime_fast(h.y), v[j + 2] * sprime_fast(h.z),
+                                      v[j + 3] * sprime_fast(h.w)};
+                        if (l == 4 && col0 + j + 3 > 192) {
+                            // columns 193..255 of the skip layer's input are the encoding: their cotangent goes to EB
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int col = col0 + j + i;
+                                if (col > 192) {
+                                    if (live) p.EB[gp * 64 + col - 193] = v[j + i];
+                                    d[i] = 0.0f;
+                                }
+                            }
+                        }
+                        v[j] = d[0]; v[j + 1] = d[1]; v[j + 2] = d[2]; v[j + 3] = d[3];
+                        if (live) st4(drow + col0 + j, make_float4(d[0], d[1], d[2], d[3]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                }
+                epi_publish_a(&bar);
+            }
+            // ---- encoding layer: eb = D_0 W_0 + (skip part); normal = J_e^T eb ----------------------------
+            epi_wait_acc(&bar, acc_par);
+            {
+                float v[16];
+                tc::tmem_ld_32x32b_x16(tmem + ((uint32_t)(row & ~31) << 16) + (uint32_t)(cg * 16), v);
+                tc::tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const int col = cg * 16 + j;
+                        float4 e = ld4(p.EB + gp * 64 + col);
+                        e.x += v[j]; e.y += v[j + 1]; e.z += v[j + 2];
+                        e.w = col + 3 == 63 ? 0.0f : e.w + v[j + 3];
+                        st4(p.EB + gp * 64 + col, e);
+                    }
+                }
+            }
+            tc::tc_fence_before_sync();
+            tc::named_bar_sync(1, EPI_THREADS);
+            if (cg < 3 && live) {
+                const float* __restrict__ e = p.E + gp * 64 + 3 + cg * 20;
+                const float* __restrict__ g = p.EB + gp * 64 + 3 + cg * 20;
+                float acc = p.EB[gp * 64 + cg];
+                float f = 1.0f;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    acc += f * (e[10 + k] * g[k] - e[k] * g[10 + k]);
+                    f *= 2.0f;
+                }
+                p.normal[gp * 3 + cg] = acc;
+            }
+        }
+    }
+    chain_teardown(&bar);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second-order backward of (sdf, feature, normal) (the Hessian-vector products the reference gets from
+// autograd.grad(create_graph=True), utils/fields.py:336-347): tangent sweep along d_normal (8 layers) then
+// reverse sweep (output layer + 7 hidden + the encoding layer), 17 chained layers per tile.  Produces
+// d_pts and, in the workspace, the operands of the weight-gradient contractions
+//   dW_l = DZ_l^T a_{l-1} + D_l^T u_{l-1}    (a = value activations H, u = tangent activations U).
+// ------------------------------------------------------------------------------------------------
+struct BwdParams {
+    int64_t n;
+    float inv_scale;
+    const float* E;       // stash of the forward
+    const float* H[8];
+    const float* D[8];
+    const float* EB;
+    const float* d_sdf;   // may be NULL
+    const float* d_feat;  // may be NULL
+    int64_t ld_dfeat;
+    const float* d_normal;
+    float* d_pts;         // may be NULL
+    float* UE;            // workspace
+    float* U[8];
+    float* X[8];
+    float* DZ[8];
+    float* DE;
+    const uint8_t* chain;
+    const float* w_out0;
+    int n_tiles;
+    long long* prof;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Program prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Barriers bar;
+    uint8_t* smem = chain_setup(smem_raw, &bar);
+    const int warp = threadIdx.x >> 5;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        producer_loop(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        mma_loop(prog, smem, &bar, n_my_tiles, p.prof);
+    } else {
+        int row, cg;
+        epi_coords(row, cg);
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            float dn[3] = {0.f, 0.f, 0.f};
+            if (live) { dn[0] = p.d_normal[gp * 3]; dn[1] = p.d_normal[gp * 3 + 1]; dn[2] = p.d_normal[gp * 3 + 2]; }
+            // ue = J_e(x) dn: tangent of the encoding, columns shift + j of the A operand (and of `g`)
+            auto write_ue = [&](int shift, float* __restrict__ g) {
+                const float* __restrict__ e = p.E + gp * 64;
+                if (cg == 0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        a_store1(smem, row, shift + c, dn[c]);
+                        if (live) g[c] = dn[c];
+                    }
+                    if (shift == 0) {
+                        a_store1(smem, row, 63, 0.0f);
+                        if (live) g[63] = 0.0f;
+                    }
+                }
+                for (int idx = cg; idx < 30; idx += EPI_CGROUPS) {
+                    const int c = idx / 10, k = idx - c * 10;
+                    const float f = (float)(1 << k);
+                    float sn = 0.f, cs = 0.f;
+                    if (live) { sn = e[3 + c * 20 + k]; cs = e[3 + c * 20 + 10 + k]; }
+                    const float us = f * cs * dn[c], uc = -f * sn * dn[c];
+                    a_store1(smem, row, shift + 3 + c * 20 + k, us);
+                    a_store1(smem, row, shift + 3 + c * 20 + 10 + k, uc);
+                    if (live) { g[3 + c * 20 + k] = us; g[3 + c * 20 + 10 + k] = uc; }
+                }
+            };
+            write_ue(0, p.UE + gp * 64);
+            epi_publish_a(&bar);
+            // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l -----------
+            for (int l = 0; l < 8; ++l) {
+                epi_wait_acc(&bar, acc_par);
+                const float* __restrict__ hrow = p.H[l] + gp * 256;
+                const float* __restrict__ drow = p.D[l] + gp * 256;
+                float* __restrict__ urow = p.U[l] + gp * 256;
+                float* __restrict__ xrow = p.X[l] + gp * 256;
+                const bool skip_tail = l == 3 && cg == EPI_CGROUPS - 1;
+                if (!skip_tail) {
+#pragma unroll
+                    for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                        const int col0 = cg * EPI_COLS + blk * 32;
+                        float v[32];
+                        acc_load32(tmem, row, col0, v);
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 h = make_float4(0.f, 0.f, 0.f, 0.f), d = h;
+                            if (live) { h = ld4(hrow + col0 + j); d = ld4(drow + col0 + j); }
+                            const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {d.x, d.y, d.z, d.w};
+                            float xx[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float q = v[j + i];
+                                const float em = __expf(-100.0f * hh[i]);       // 1 - s'
+                                v[j + i] = (1.0f - em) * q;
+                                xx[i] = 100.0f * em * dd[i] * q;
+                            }
+                            if (live) {
+                                st4(urow + col0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                                st4(xrow + col0 + j, make_float4(xx[0], xx[1], xx[2], xx[3]));
+                            }
+                        }
+                        if (l < 7) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                        }
+                    }
+                }
+                if (l == 3) {
+                    if (cg == EPI_CGROUPS - 1) {
+                        float v[32];
+                        acc_load32(tmem, row, 192, v);
+                        float u = 0.f, xv = 0.f;
+                        if (live) {
+                            const float em = __expf(-100.0f * hrow[192]);
+                            u = (1.0f - em) * v[0];
+                            xv = 100.0f * em * drow[192] * v[0];
+                            urow[192] = u;
+                            xrow[192] = xv;
+                        }
+                        a_store1(smem, row, 192, u);
+                    }
+                    write_ue(193, urow + 193);
+                }
+                if (l == 7) {
+                    // A operand of the output layer's reverse step: d_feat
+#pragma unroll
+                    for (int j = 0; j < EPI_COLS; j += 8) {
+                        const int col = cg * EPI_COLS + j;
+                        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (live && p.d_feat) {
+                            const float4 a = ld4(p.d_feat + gp * p.ld_dfeat + col), b = ld4(p.d_feat + gp * p.ld_dfeat + col + 4);
+                            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                        }
+                        a_store8(smem, row, col, f);
+                    }
+                }
+                epi_publish_a(&bar);
+            }
+            // ---- reverse sweep: dz_{l-1} = s'(h_{l-1}) (dz_l W_l) + X_{l-1}, l = 8..1 ------------------------
+            const float gs = (live && p.d_sdf) ? p.d_sdf[gp] * p.inv_scale : 0.0f;
+            for (int l = 8; l >= 1; --l) {
+                epi_wait_acc(&bar, acc_par);
+                const float* __restrict__ hrow = p.H[l - 1] + gp * 256;
+                const float* __restrict__ xrow = p.X[l - 1] + gp * 256;
+                float* __restrict__ zrow = p.DZ[l - 1] + gp * 256;
+#pragma unroll
+                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                    const int col0 = cg * EPI_COLS + blk * 32;
+                    float v[32];
+                    acc_load32(tmem, row, col0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f), xq = h;
+                        if (live) { h = ld4(hrow + col0 + j); xq = ld4(xrow + col0 + j); }
+                        float da[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
+                        if (l == 8) {
+                            const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
+                            da[0] += gs * w.x; da[1] += gs * w.y; da[2] += gs * w.z; da[3] += gs * w.w;
+                        }
+                        float dz[4] = {sprime_fast(h.x) * da[0] + xq.x, sprime_fast(h.y) * da[1] + xq.y,
+                                       sprime_fast(h.z) * da[2] + xq.z, sprime_fast(h.w) * da[3] + xq.w};
+                        if (l == 4 && col0 + j + 3 > 192) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int col = col0 + j + i;
+                                if (col > 192) {
+                                    if (live) p.DE[gp * 64 + col - 193] = da[i];
+                                    dz[i] = 0.0f;
+                                }
+                            }
+                        }
+                        v[j] = dz[0]; v[j + 1] = dz[1]; v[j + 2] = dz[2]; v[j + 3] = dz[3];
+                        if (live) st4(zrow + col0 + j, make_float4(dz[0], dz[1], dz[2], dz[3]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                }
+                epi_publish_a(&bar);
+            }
+            // ---- encoding layer: de = dz_0 W_0 + (skip part); d_x = J_e^T de + Hessian term ---------------------
+            epi_wait_acc(&bar, acc_par);
+            if (p.d_pts) {
+                float v[16];
+                tc::tmem_ld_32x32b_x16(tmem + ((uint32_t)(row & ~31) << 16) + (uint32_t)(cg * 16), v);
+                tc::tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const int col = cg * 16 + j;
+                        float4 e = ld4(p.DE + gp * 64 + col);
+                        e.x += v[j]; e.y += v[j + 1]; e.z += v[j + 2];
+                        e.w = col + 3 == 63 ? 0.0f : e.w + v[j + 3];
+                        st4(p.DE + gp * 64 + col, e);
+                    }
+                }
+                tc::tc_fence_before_sync();
+                tc::named_bar_sync(1, EPI_THREADS);
+                if (cg < 3 && live) {
+                    const float* __restrict__ e = p.E + gp * 64 + 3 + cg * 20;
+                    const float* __restrict__ g = p.DE + gp * 64 + 3 + cg * 20;
+                    const float* __restrict__ b = p.EB + gp * 64 + 3 + cg * 20;
+                    float acc = p.DE[gp * 64 + cg], hess = 0.0f, f = 1.0f;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+                        acc += f * (e[10 + k] * g[k] - e[k] * g[10 + k]);
+                        hess -= f * f * (e[k] * b[k] + e[10 + k] * b[10 + k]);
+                        f *= 2.0f;
+                    }
+                    p.d_pts[gp * 3 + cg] = acc + dn[cg] * hess;
+                }
+            }
+        }
+    }
+    chain_teardown(&bar);
+}
+
 static int check_chain_mlp(const hn_mlp_t* m) {
     HN_REQUIRE(m && m->n_layers == 9, "object SDF mlp must have 9 layers");
     HN_REQUIRE(m->chain && m->chain_bytes >= (int64_t)obj_layout().total && aligned16(m->chain),
@@ -232,6 +674,111 @@ int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sc
     {
         TimingScope ts(s);
         sdf_only_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p, prog);
+    }
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat,
+                   int64_t ld_feat, float* normal, float* stash, cudaStream_t s) {
+    HN_PROPAGATE(check_chain_mlp(m));
+    const ObjLayout L = obj_layout();
+    FwdParams p;
+    p.pts = pts; p.n = n; p.inv_scale = inv_scale; p.sdf = sdf; p.feat = feat; p.ld_feat = ld_feat; p.normal = normal;
+    p.E = stash;
+    for (int l = 0; l < 8; ++l) {
+        p.H[l] = stash + n * 64 + (int64_t)l * n * 256;
+        p.D[l] = stash + n * 64 + (int64_t)(8 + l) * n * 256;
+    }
+    p.EB = stash + n * 64 + 16 * n * 256;
+    p.chain = reinterpret_cast<const uint8_t*>(m->chain);
+    for (int l = 0; l < 9; ++l) p.bias[l] = m->b[l];
+    p.w_out0 = m->W[8];
+    p.n_tiles = (int)ceil_div(n, TILE_M);
+    p.prof = g_prof;
+    Program prog;
+    int k = 0;
+    for (int l = 0; l < 9; ++l, ++k) {           // value trunk + feature head: a @ W_l^T
+        prog.step[k].b_off = L.nt_off[l];
+        prog.step[k].n_mma = L.nt_n[l];
+        prog.step[k].kblocks = L.nt_kb[l];
+        prog.step[k].a_kb0 = 0;
+    }
+    for (int l = 7; l >= 0; --l, ++k) {          // normal sweep: d @ W_l
+        prog.step[k].b_off = L.nn_off[l];
+        prog.step[k].n_mma = L.nn_n[l];
+        prog.step[k].kblocks = L.nn_kb[l];
+        prog.step[k].a_kb0 = 0;
+    }
+    prog.n_steps = k;
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(sdf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = std::min(p.n_tiles, sm_count());
+    {
+        TimingScope ts(s);
+        sdf_fwd_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p, prog);
+    }
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+// floats per point of the backward workspace: UE | U[8] | X[8] | DZ8 (ld 260) | DZ[8] | DE
+int64_t bwd_ws_floats_per_point() { return 64 + 8 * 256 + 8 * 256 + 260 + 8 * 256 + 64; }
+
+int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
+                   const float* d_feat, int64_t ld_dfeat, const float* d_normal, float* d_pts, float* ws,
+                   cudaStream_t s) {
+    HN_PROPAGATE(check_chain_mlp(m));
+    const ObjLayout L = obj_layout();
+    BwdParams p;
+    p.n = n; p.inv_scale = inv_scale;
+    p.E = stash;
+    for (int l = 0; l < 8; ++l) {
+        p.H[l] = stash + n * 64 + (int64_t)l * n * 256;
+        p.D[l] = stash + n * 64 + (int64_t)(8 + l) * n * 256;
+    }
+    p.EB = stash + n * 64 + 16 * n * 256;
+    p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.d_normal = d_normal; p.d_pts = d_pts;
+    float* q = ws;
+    p.UE = q; q += n * 64;
+    for (int l = 0; l < 8; ++l) { p.U[l] = q; q += n * 256; }
+    for (int l = 0; l < 8; ++l) { p.X[l] = q; q += n * 256; }
+    q += n * 260;                                   // DZ8, assembled by the caller
+    for (int l = 0; l < 8; ++l) { p.DZ[l] = q; q += n * 256; }
+    p.DE = q;
+    p.chain = reinterpret_cast<const uint8_t*>(m->chain);
+    p.w_out0 = m->W[8];
+    p.n_tiles = (int)ceil_div(n, TILE_M);
+    p.prof = g_prof;
+    Program prog;
+    int k = 0;
+    for (int l = 0; l < 8; ++l, ++k) {           // tangent sweep: u @ W_l^T
+        prog.step[k].b_off = L.nt_off[l];
+        prog.step[k].n_mma = L.nt_n[l];
+        prog.step[k].kblocks = L.nt_kb[l];
+        prog.step[k].a_kb0 = 0;
+    }
+    for (int l = 8; l >= 0; --l, ++k) {          // reverse sweep: dz @ W_l
+        prog.step[k].b_off = L.nn_off[l];
+        prog.step[k].n_mma = L.nn_n[l];
+        prog.step[k].kblocks = L.nn_kb[l];
+        prog.step[k].a_kb0 = 0;
+    }
+    prog.n_steps = k;
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(sdf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = std::min(p.n_tiles, sm_count());
+    {
+        TimingScope ts(s);
+        sdf_bwd_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p, prog);
     }
     count_launch();
     HN_CHECK_LAUNCH();

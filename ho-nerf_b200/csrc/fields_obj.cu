@@ -2,6 +2,8 @@
 // field, HN_SIMT_FP32 path: layer-by-layer fp32 GEMMs with fused epilogues, activations in HBM.
 // Replaces utils/fields.py:316-347 (SDFNetwork_OBJ.forward/.sdf/.gradient) and :387-405
 // (RenderingNetwork_OBJ.forward) plus everything autograd derives from them.
+#include <algorithm>
+
 #include "common.cuh"
 #include "gemm_dispatch.cuh"
 #include "fields_common.cuh"
@@ -10,6 +12,12 @@ namespace hn {
 
 namespace chain {   // chain_obj.cu
 int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s);
+int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat,
+                   int64_t ld_feat, float* normal, float* stash, cudaStream_t s);
+int64_t bwd_ws_floats_per_point();
+int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
+                   const float* d_feat, int64_t ld_dfeat, const float* d_normal, float* d_pts, float* ws,
+                   cudaStream_t s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -207,7 +215,7 @@ int64_t hn_sdf_obj_ws_floats(int64_t n, int kind) {
     switch (kind) {
         case HN_WS_SDF_ONLY: return n * (64 + 3 * 256);       // E, two ping-pong H, A4
         case HN_WS_FWD: return 4;                              // nothing beyond the stash
-        case HN_WS_BWD: return n * (64 + 2 * 256 + 256 + 260 + 2 * 256 + 64);
+        case HN_WS_BWD: return n * std::max<int64_t>(64 + 2 * 256 + 256 + 260 + 2 * 256 + 64, chain::bwd_ws_floats_per_point());
         default: return -1;
     }
 }
@@ -249,6 +257,7 @@ int hn_sdf_obj_fwd(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
     HN_REQUIRE(stash_floats >= hn_sdf_obj_stash_floats(n) && aligned16(stash), "stash too small or misaligned");
     HN_REQUIRE(ld_feat >= 256 && ld_feat % 4 == 0 && aligned16(feat), "feat must be 16B aligned with ld%%4==0");
     cudaStream_t s = (cudaStream_t)stream;
+    if (precision == HN_TC_BF16X3) return chain::launch_sdf_fwd(mlp, pts, n, inv_scale, sdf, feat, ld_feat, normal, stash, s);
     ObjSdfStash st(stash, n);
     HN_PROPAGATE(obj_trunk_fwd(mlp, pts, n, st.E, st.H, s, precision));
     // output layer: column 0 -> sdf, columns 1..256 -> feature
@@ -304,6 +313,42 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
     HN_REQUIRE(!d_feat || (ld_dfeat >= 256), "bad ld_dfeat");
     cudaStream_t s = (cudaStream_t)stream;
     ObjSdfStash st(stash, n);
+    if (precision == HN_TC_BF16X3) {
+        // fused tangent + reverse sweeps, then the weight-gradient contractions over the operands they left in ws
+        HN_PROPAGATE(chain::launch_sdf_bwd(mlp, n, inv_scale, stash, d_sdf, d_feat, ld_dfeat, d_normal, d_pts, ws, s));
+        if (!grad) return HN_OK;
+        float* cUE = ws;
+        float* cU = cUE + n * 64;
+        float* cDZ8 = cU + 16 * n * 256;
+        float* cDZ = cDZ8 + n * 260;
+        const int splits_target = 2 * sm_count();
+        auto dw = [&](const float* P, int64_t ldp, int out, const float* Q, int64_t ldq, int in, int l) -> int {
+            if (!grad->dW[l]) return HN_OK;
+            GemmArgs g;
+            g.A = P; g.lda = ldp; g.B = Q; g.ldb = ldq;
+            g.M = out; g.N = in; g.K = (int)n;
+            g.C = grad->dW[l]; g.ldc = mlp->ld[l];
+            int tiles = (int)(ceil_div(out, GBM) * ceil_div(in, GBN));
+            int splits = (int)max((int64_t)1, min((int64_t)ceil_div(splits_target, tiles), ceil_div(n, 256)));
+            return gemm_tn(g, s, precision, splits);
+        };
+        for (int l = 0; l < 8; ++l) {
+            const float* au = l == 0 ? cUE : cU + (int64_t)(l - 1) * n * 256;     // u_{l-1} (U[3] holds [u3 | ue])
+            const float* a = l == 0 ? st.E : st.H[l - 1];
+            const int64_t lda = l == 0 ? 64 : 256;
+            const float* dz = cDZ + (int64_t)l * n * 256;
+            HN_PROPAGATE(dw(st.D[l], 256, mlp->out_dim[l], au, lda, mlp->in_dim[l], l));
+            HN_PROPAGATE(dw(dz, 256, mlp->out_dim[l], a, lda, mlp->in_dim[l], l));
+            if (grad->db[l]) HN_PROPAGATE(launch_colsum(dz, 256, n, mlp->out_dim[l], 1.0f, grad->db[l], s));
+        }
+        assemble_dz8_kernel<<<blocks_for(n * 260, 256), 256, 0, s>>>(d_sdf, d_feat, ld_dfeat, inv_scale, n, cDZ8);
+        count_launch();
+        HN_CHECK_LAUNCH();
+        HN_PROPAGATE(dw(cDZ8, 260, 257, st.H[7], 256, 256, 8));
+        if (grad->db[8]) HN_PROPAGATE(launch_colsum(cDZ8, 260, n, 257, 1.0f, grad->db[8], s));
+        if (grad->dW[8]) HN_PROPAGATE(launch_colsum(cU + (int64_t)7 * n * 256, 256, n, 256, inv_scale, grad->dW[8], s));
+        return HN_OK;
+    }
     float* UE = ws;
     float* U[2] = {UE + n * 64, UE + n * 64 + n * 256};
     float* AU4 = U[1] + n * 256;

@@ -57,6 +57,33 @@ def prof():
           % (b[2] / steps, b[0] / steps, b[1] / steps, (b[2] - b[0] - b[1]) / steps, b[3] / steps))
 
 
+def fwd_bench():
+    sdf, col, dev, _, _ = obj_modules(requires_grad=False)
+    n = 65536
+    x = (0.45 * torch.randn(n, 3)).cuda()
+    for prec in ("tc_bf16x3", "tc_tf32x3"):
+        p = H.ops._PRECISIONS[prec]
+        ms = timeit(lambda: H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p))
+        print("sdf fwd (value+feat+normal) n=%d %-10s %.3f ms  %.1f algorithmic TFLOP/s" % (n, prec, ms, n * 2 * F_O / ms / 1e9))
+
+
+def fwdbwd_bench():
+    sdf, col, dev, _, _ = obj_modules(requires_grad=True)
+    n = 65536
+    x = (0.45 * torch.randn(n, 3)).cuda().requires_grad_(True)
+    gs, gf, gn = torch.randn(n, 1).cuda(), torch.randn(n, 256).cuda(), torch.randn(n, 3).cuda()
+    for prec in ("tc_bf16x3", "tc_tf32x3"):
+        p = H.ops._PRECISIONS[prec]
+
+        def step():
+            s, f, nn = H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p)
+            torch.autograd.backward([s, f, nn], [gs, gf, gn])
+        ms = timeit(step, iters=5)
+        print("sdf fwd+bwd (2nd order, dW) n=%d %-10s %.3f ms  %.1f algorithmic TFLOP/s" % (n, prec, ms, n * 6 * F_O / ms / 1e9))
+
+
 if __name__ == "__main__":
     prof()
+    fwd_bench()
+    fwdbwd_bench()
     main()
