@@ -83,6 +83,7 @@ PROTOTYPES = {
     "hn_color_obj_fwd": (c_int, [_mlp_p, P, P, P, c_int64, P, c_int64, P, P, c_int64, c_int, P]),
     "hn_color_obj_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, P, P, c_int64, P, _grad_p, P, c_int64,
                                  c_int, P]),
+    "hn_dw_test": (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "hn_tc_gemm_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "hn_gemm_test": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "hn_ray_points": (c_int, [P, P, P, c_int64, c_int, P, P]),

@@ -1,0 +1,47 @@
+// Job descriptions of the weight-gradient kernel (chain_dw.cu).
+#pragma once
+#include <stdint.h>
+
+namespace hn {
+namespace chain {
+
+constexpr int DW_MAX_JOBS = 12;
+constexpr int DW_SPLITS = 16;
+
+// fp32 operand [points, cols]: tiled ([tile][col/4][128 rows][4], the chain stash layout) or row-major
+struct DwOperand {
+    const float* ptr;
+    int64_t ld;        // row-major leading dimension (ignored when tiled)
+    int cols;          // valid columns (the rest of the 256-wide tile is zero)
+    int tiled;
+};
+struct DwJob {
+    DwOperand P[2], Q[2];
+    int n_pairs;
+    int n_mma;         // UMMA N = round_up(Q cols, 16)
+    float* db;         // += column sums of P[0] (may be NULL)
+    float db_scale;
+};
+struct DwParams {
+    int64_t n;
+    int n_tiles;
+    int n_jobs;
+    DwJob job[DW_MAX_JOBS];
+    float* part;       // [n_jobs][DW_SPLITS][256][256]
+};
+
+// dW[(row0 + r) * ld + c] += sum_s part[job][s][r][c]   for r < rows, c < cols
+struct DwReduceJob {
+    float* dW;
+    int ld, row0, rows, cols;
+};
+struct DwReduceParams {
+    DwReduceJob job[DW_MAX_JOBS];
+    const float* part;
+};
+
+int64_t dw_part_floats(int n_jobs);
+int launch_dw(const DwParams& p, const DwReduceParams& r, cudaStream_t s);
+
+}  // namespace chain
+}  // namespace hn

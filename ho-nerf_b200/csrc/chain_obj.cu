@@ -7,6 +7,7 @@
 #include <algorithm>
 
 #include "chain_common.cuh"
+#include "chain_dw.cuh"
 #include "fields_common.cuh"
 
 namespace hn {
@@ -80,21 +81,31 @@ static ObjLayout obj_layout() {
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------------
+// The [points, 256] fp32 arrays the chain kernels exchange through HBM (H, D, U, X, DZ) are TILED:
+// [tile][column / 4][row in tile (128)][4 floats], so that the epilogue's access pattern (thread = row,
+// four consecutive columns per access) is one contiguous 512-byte segment per warp instruction, and the
+// weight-gradient kernel (lane = point) reads them coalesced as well.  n is padded to whole tiles.
+constexpr int64_t TILE_FLOATS = (int64_t)TILE_M * 256;
+__device__ __forceinline__ int toff(int row, int col) { return (col >> 2) * 512 + row * 4 + (col & 3); }
 // [x(3), sin/cos(2^k x_c)] of one point written as columns shift + j of the A operand; the column
 // groups of a row share the 30 (coordinate, frequency) pairs.  Column shift+63 (the K padding of the
 // first layer) is zeroed when shift == 0.
-// `g` (may be NULL): fp32 copy for the stash, g[j] = e_j.
+// `g` (may be NULL): fp32 copy for the stash: row-major row pointer (g[j] = e_j) when !g_tiled, else the
+// base of a tiled [128, 256] tile whose columns shift + j receive e_j.
 __device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, const float x[3], int shift,
-                                               float* __restrict__ g = nullptr) {
+                                               float* __restrict__ g = nullptr, bool g_tiled = false) {
+    auto gput = [&](int j, float v) {
+        if (g) g[g_tiled ? toff(row, shift + j) : j] = v;
+    };
     if (cg == 0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             a_store1(smem, row, shift + c, x[c]);
-            if (g) g[c] = x[c];
+            gput(c, x[c]);
         }
         if (shift == 0) {
             a_store1(smem, row, 63, 0.0f);
-            if (g) g[63] = 0.0f;
+            gput(63, 0.0f);
         }
     }
     for (int idx = cg; idx < 30; idx += EPI_CGROUPS) {
@@ -103,7 +114,8 @@ __device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, c
         sincosf(x[c] * (float)(1 << k), &s, &co);
         a_store1(smem, row, shift + 3 + c * 20 + k, s);
         a_store1(smem, row, shift + 3 + c * 20 + 10 + k, co);
-        if (g) { g[3 + c * 20 + k] = s; g[3 + c * 20 + 10 + k] = co; }
+        gput(3 + c * 20 + k, s);
+        gput(3 + c * 20 + 10 + k, co);
     }
 }
 
@@ -260,7 +272,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
             for (int l = 0; l < 8; ++l) {
                 epi_wait_acc(&bar, acc_par);
                 const float* __restrict__ bias = p.bias[l];
-                float* __restrict__ hrow = p.H[l] + gp * 256;
+                float* __restrict__ ht = p.H[l] + tile * TILE_FLOATS;       // tiled [128, 256]
                 const bool skip_tail = l == 3 && cg == EPI_CGROUPS - 1;      // columns >= 192: below
                 if (!skip_tail) {
 #pragma unroll
@@ -275,7 +287,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                             v[j + 1] = softplus100_fast(v[j + 1] + b.y);
                             v[j + 2] = softplus100_fast(v[j + 2] + b.z);
                             v[j + 3] = softplus100_fast(v[j + 3] + b.w);
-                            if (live) st4(hrow + col0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                            if (live) st4(ht + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                         }
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
@@ -294,9 +306,9 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                         acc_load32(tmem, row, 192, v);
                         const float h = softplus100_fast(v[0] + __ldg(bias + 192));
                         a_store1(smem, row, 192, h);
-                        if (live) hrow[192] = h;
+                        if (live) ht[toff(row, 192)] = h;
                     }
-                    write_encoding(smem, row, cg, x, 193, live ? hrow + 193 : nullptr);
+                    write_encoding(smem, row, cg, x, 193, live ? ht : nullptr, true);
                 }
                 epi_publish_a(&bar);
             }
@@ -334,8 +346,9 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                         for (int i = 0; i < 8; ++i) h[i] = sprime_fast(h[i]) * w[i] * p.inv_scale;
                         a_store8(smem, row, col0 + j, h);
                         if (live) {
-                            st4(p.D[7] + gp * 256 + col0 + j, make_float4(h[0], h[1], h[2], h[3]));
-                            st4(p.D[7] + gp * 256 + col0 + j + 4, make_float4(h[4], h[5], h[6], h[7]));
+                            float* __restrict__ dt = p.D[7] + tile * TILE_FLOATS;
+                            st4(dt + toff(row, col0 + j), make_float4(h[0], h[1], h[2], h[3]));
+                            st4(dt + toff(row, col0 + j + 4), make_float4(h[4], h[5], h[6], h[7]));
                         }
                     }
                 }
@@ -344,8 +357,8 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
             // ---- normal sweep: D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1 ------------------------------
             for (int l = 7; l >= 1; --l) {
                 epi_wait_acc(&bar, acc_par);
-                const float* __restrict__ hrow = p.H[l - 1] + gp * 256;
-                float* __restrict__ drow = p.D[l - 1] + gp * 256;
+                const float* __restrict__ ht = p.H[l - 1] + tile * TILE_FLOATS;
+                float* __restrict__ dt = p.D[l - 1] + tile * TILE_FLOATS;
 #pragma unroll
                 for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
                     const int col0 = cg * EPI_COLS + blk * 32;
@@ -354,7 +367,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live) h = ld4(hrow + col0 + j);
+                        if (live) h = ld4(ht + toff(row, col0 + j));
                         float d[4] = {v[j] * sprime_fast(h.x), v[j + 1] * sprime_fast(h.y), v[j + 2] * sprime_fast(h.z),
                                       v[j + 3] * sprime_fast(h.w)};
                         if (l == 4 && col0 + j + 3 > 192) {
@@ -369,7 +382,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                             }
                         }
                         v[j] = d[0]; v[j + 1] = d[1]; v[j + 2] = d[2]; v[j + 3] = d[3];
-                        if (live) st4(drow + col0 + j, make_float4(d[0], d[1], d[2], d[3]));
+                        if (live) st4(dt + toff(row, col0 + j), make_float4(d[0], d[1], d[2], d[3]));
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
@@ -465,13 +478,13 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
             float dn[3] = {0.f, 0.f, 0.f};
             if (live) { dn[0] = p.d_normal[gp * 3]; dn[1] = p.d_normal[gp * 3 + 1]; dn[2] = p.d_normal[gp * 3 + 2]; }
             // ue = J_e(x) dn: tangent of the encoding, columns shift + j of the A operand (and of `g`)
-            auto write_ue = [&](int shift, float* __restrict__ g) {
+            auto write_ue = [&](int shift, float* __restrict__ g, bool gt) {
                 const float* __restrict__ e = p.E + gp * 64;
                 if (cg == 0) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         a_store1(smem, row, shift + c, dn[c]);
-                        if (live) g[c] = dn[c];
+                        if (live) g[gt ? toff(row, shift + c) : c] = dn[c];
                     }
                     if (shift == 0) {
                         a_store1(smem, row, 63, 0.0f);
@@ -486,18 +499,21 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                     const float us = f * cs * dn[c], uc = -f * sn * dn[c];
                     a_store1(smem, row, shift + 3 + c * 20 + k, us);
                     a_store1(smem, row, shift + 3 + c * 20 + 10 + k, uc);
-                    if (live) { g[3 + c * 20 + k] = us; g[3 + c * 20 + 10 + k] = uc; }
+                    if (live) {
+                        g[gt ? toff(row, shift + 3 + c * 20 + k) : 3 + c * 20 + k] = us;
+                        g[gt ? toff(row, shift + 3 + c * 20 + 10 + k) : 3 + c * 20 + 10 + k] = uc;
+                    }
                 }
             };
-            write_ue(0, p.UE + gp * 64);
+            write_ue(0, p.UE + gp * 64, false);
             epi_publish_a(&bar);
             // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l -----------
             for (int l = 0; l < 8; ++l) {
                 epi_wait_acc(&bar, acc_par);
-                const float* __restrict__ hrow = p.H[l] + gp * 256;
-                const float* __restrict__ drow = p.D[l] + gp * 256;
-                float* __restrict__ urow = p.U[l] + gp * 256;
-                float* __restrict__ xrow = p.X[l] + gp * 256;
+                const float* __restrict__ ht = p.H[l] + tile * TILE_FLOATS;
+                const float* __restrict__ dt = p.D[l] + tile * TILE_FLOATS;
+                float* __restrict__ ut = p.U[l] + tile * TILE_FLOATS;
+                float* __restrict__ xt = p.X[l] + tile * TILE_FLOATS;
                 const bool skip_tail = l == 3 && cg == EPI_CGROUPS - 1;
                 if (!skip_tail) {
 #pragma unroll
@@ -508,7 +524,7 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             float4 h = make_float4(0.f, 0.f, 0.f, 0.f), d = h;
-                            if (live) { h = ld4(hrow + col0 + j); d = ld4(drow + col0 + j); }
+                            if (live) { h = ld4(ht + toff(row, col0 + j)); d = ld4(dt + toff(row, col0 + j)); }
                             const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {d.x, d.y, d.z, d.w};
                             float xx[4];
 #pragma unroll
@@ -519,8 +535,8 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                                 xx[i] = 100.0f * em * dd[i] * q;
                             }
                             if (live) {
-                                st4(urow + col0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                                st4(xrow + col0 + j, make_float4(xx[0], xx[1], xx[2], xx[3]));
+                                st4(ut + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                                st4(xt + toff(row, col0 + j), make_float4(xx[0], xx[1], xx[2], xx[3]));
                             }
                         }
                         if (l < 7) {
@@ -535,15 +551,15 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                         acc_load32(tmem, row, 192, v);
                         float u = 0.f, xv = 0.f;
                         if (live) {
-                            const float em = __expf(-100.0f * hrow[192]);
+                            const float em = __expf(-100.0f * ht[toff(row, 192)]);
                             u = (1.0f - em) * v[0];
-                            xv = 100.0f * em * drow[192] * v[0];
-                            urow[192] = u;
-                            xrow[192] = xv;
+                            xv = 100.0f * em * dt[toff(row, 192)] * v[0];
+                            ut[toff(row, 192)] = u;
+                            xt[toff(row, 192)] = xv;
                         }
                         a_store1(smem, row, 192, u);
                     }
-                    write_ue(193, urow + 193);
+                    write_ue(193, ut, true);
                 }
                 if (l == 7) {
                     // A operand of the output layer's reverse step: d_feat
@@ -564,9 +580,9 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
             const float gs = (live && p.d_sdf) ? p.d_sdf[gp] * p.inv_scale : 0.0f;
             for (int l = 8; l >= 1; --l) {
                 epi_wait_acc(&bar, acc_par);
-                const float* __restrict__ hrow = p.H[l - 1] + gp * 256;
-                const float* __restrict__ xrow = p.X[l - 1] + gp * 256;
-                float* __restrict__ zrow = p.DZ[l - 1] + gp * 256;
+                const float* __restrict__ ht = p.H[l - 1] + tile * TILE_FLOATS;
+                const float* __restrict__ xt = p.X[l - 1] + tile * TILE_FLOATS;
+                float* __restrict__ zt = p.DZ[l - 1] + tile * TILE_FLOATS;
 #pragma unroll
                 for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
                     const int col0 = cg * EPI_COLS + blk * 32;
@@ -575,7 +591,7 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         float4 h = make_float4(0.f, 0.f, 0.f, 0.f), xq = h;
-                        if (live) { h = ld4(hrow + col0 + j); xq = ld4(xrow + col0 + j); }
+                        if (live) { h = ld4(ht + toff(row, col0 + j)); xq = ld4(xt + toff(row, col0 + j)); }
                         float da[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
                         if (l == 8) {
                             const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
@@ -594,7 +610,7 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                             }
                         }
                         v[j] = dz[0]; v[j + 1] = dz[1]; v[j + 2] = dz[2]; v[j + 3] = dz[3];
-                        if (live) st4(zrow + col0 + j, make_float4(dz[0], dz[1], dz[2], dz[3]));
+                        if (live) st4(zt + toff(row, col0 + j), make_float4(dz[0], dz[1], dz[2], dz[3]));
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
@@ -686,12 +702,13 @@ int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
     const ObjLayout L = obj_layout();
     FwdParams p;
     p.pts = pts; p.n = n; p.inv_scale = inv_scale; p.sdf = sdf; p.feat = feat; p.ld_feat = ld_feat; p.normal = normal;
+    const int64_t np = round_up(n, TILE_M);      // the tiled arrays hold whole tiles
     p.E = stash;
     for (int l = 0; l < 8; ++l) {
-        p.H[l] = stash + n * 64 + (int64_t)l * n * 256;
-        p.D[l] = stash + n * 64 + (int64_t)(8 + l) * n * 256;
+        p.H[l] = stash + np * 64 + (int64_t)l * np * 256;
+        p.D[l] = stash + np * 64 + (int64_t)(8 + l) * np * 256;
     }
-    p.EB = stash + n * 64 + 16 * n * 256;
+    p.EB = stash + np * 64 + 16 * np * 256;
     p.chain = reinterpret_cast<const uint8_t*>(m->chain);
     for (int l = 0; l < 9; ++l) p.bias[l] = m->b[l];
     p.w_out0 = m->W[8];
@@ -727,8 +744,8 @@ int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
     return HN_OK;
 }
 
-// floats per point of the backward workspace: UE | U[8] | X[8] | DZ8 (ld 260) | DZ[8] | DE
-int64_t bwd_ws_floats_per_point() { return 64 + 8 * 256 + 8 * 256 + 260 + 8 * 256 + 64; }
+// backward workspace (n padded to whole tiles): UE | U[8] | X[8] | DZ[8] | DE | partial sums of the dW kernel
+int64_t bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (64 + 3 * 8 * 256 + 64) + dw_part_floats(9); }
 
 int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
                    const float* d_feat, int64_t ld_dfeat, const float* d_normal, float* d_pts, float* ws,
@@ -737,19 +754,19 @@ int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     const ObjLayout L = obj_layout();
     BwdParams p;
     p.n = n; p.inv_scale = inv_scale;
+    const int64_t np = round_up(n, TILE_M);
     p.E = stash;
     for (int l = 0; l < 8; ++l) {
-        p.H[l] = stash + n * 64 + (int64_t)l * n * 256;
-        p.D[l] = stash + n * 64 + (int64_t)(8 + l) * n * 256;
+        p.H[l] = stash + np * 64 + (int64_t)l * np * 256;
+        p.D[l] = stash + np * 64 + (int64_t)(8 + l) * np * 256;
     }
-    p.EB = stash + n * 64 + 16 * n * 256;
+    p.EB = stash + np * 64 + 16 * np * 256;
     p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.d_normal = d_normal; p.d_pts = d_pts;
     float* q = ws;
-    p.UE = q; q += n * 64;
-    for (int l = 0; l < 8; ++l) { p.U[l] = q; q += n * 256; }
-    for (int l = 0; l < 8; ++l) { p.X[l] = q; q += n * 256; }
-    q += n * 260;                                   // DZ8, assembled by the caller
-    for (int l = 0; l < 8; ++l) { p.DZ[l] = q; q += n * 256; }
+    p.UE = q; q += np * 64;
+    for (int l = 0; l < 8; ++l) { p.U[l] = q; q += np * 256; }
+    for (int l = 0; l < 8; ++l) { p.X[l] = q; q += np * 256; }
+    for (int l = 0; l < 8; ++l) { p.DZ[l] = q; q += np * 256; }
     p.DE = q;
     p.chain = reinterpret_cast<const uint8_t*>(m->chain);
     p.w_out0 = m->W[8];
@@ -784,6 +801,100 @@ int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     HN_CHECK_LAUNCH();
     return HN_OK;
 }
+
+// dW_out[0, :] += inv_scale * sum_p (d_sdf[p] * h7[p, :] + u7[p, :]);  db_out[0] += inv_scale * sum_p d_sdf[p]
+// (row 0 of the output layer: the sdf value uses it directly, the normal sweep is seeded with it).
+__global__ void __launch_bounds__(128) out_row0_grad_kernel(const float* __restrict__ H7, const float* __restrict__ U7,
+                                                            const float* __restrict__ d_sdf, int64_t n, int n_tiles,
+                                                            float inv_scale, float* __restrict__ dW_row0,
+                                                            float* __restrict__ db0) {
+    __shared__ float red[4][5];
+    const int c4 = blockIdx.x, row = threadIdx.x;
+    const int t0 = (int)((int64_t)n_tiles * blockIdx.y / gridDim.y), t1 = (int)((int64_t)n_tiles * (blockIdx.y + 1) / gridDim.y);
+    float a[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = t0; t < t1; ++t) {
+        const int64_t pnt = (int64_t)t * TILE_M + row;
+        if (pnt >= n) continue;
+        const float w = d_sdf ? d_sdf[pnt] : 0.0f;
+        const float4 h = ld4(H7 + t * TILE_FLOATS + c4 * 512 + row * 4);
+        const float4 u = ld4(U7 + t * TILE_FLOATS + c4 * 512 + row * 4);
+        a[0] += w * h.x + u.x; a[1] += w * h.y + u.y; a[2] += w * h.z + u.z; a[3] += w * h.w + u.w;
+        a[4] += w;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        a[i] = warp_sum(a[i]);
+        if ((row & 31) == 0) red[row >> 5][i] = a[i];
+    }
+    __syncthreads();
+    if (row < 5) {
+        const float v = (red[0][row] + red[1][row] + red[2][row] + red[3][row]) * inv_scale;
+        if (row < 4) {
+            if (dW_row0) atomicAdd(dW_row0 + c4 * 4 + row, v);
+        } else if (c4 == 0 && db0) {
+            atomicAdd(db0, v);
+        }
+    }
+}
+
+// all weight / bias gradients of the object SDF net from the operands the backward chain kernel left in HBM
+int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
+                           const float* d_feat, int64_t ld_dfeat, float* ws, const hn_mlp_grad_t* grad,
+                           cudaStream_t s) {
+    const int64_t np = round_up(n, TILE_M);
+    const float* E = stash;
+    const float* H = stash + np * 64;
+    const float* D = H + 8 * np * 256;
+    const float* UE = ws;
+    const float* U = UE + np * 64;
+    const float* DZ = U + 16 * np * 256;
+    float* part = ws + np * (64 + 3 * 8 * 256 + 64);
+    DwParams p;
+    DwReduceParams r;
+    p.n = n; p.n_tiles = (int)(np / TILE_M); p.part = part;
+    r.part = part;
+    int k = 0;
+    for (int l = 0; l < 8; ++l, ++k) {
+        DwJob& j = p.job[k];
+        const int out = m->out_dim[l], in = m->in_dim[l];
+        j.P[0] = {DZ + (int64_t)l * np * 256, 0, out, 1};
+        j.P[1] = {D + (int64_t)l * np * 256, 0, out, 1};
+        if (l == 0) {
+            j.Q[0] = {E, 64, in, 0};
+            j.Q[1] = {UE, 64, in, 0};
+        } else {
+            j.Q[0] = {H + (int64_t)(l - 1) * np * 256, 0, in, 1};       // H[3] holds the skip input [h3 | e]
+            j.Q[1] = {U + (int64_t)(l - 1) * np * 256, 0, in, 1};       // U[3] holds [u3 | ue]
+        }
+        j.n_pairs = 2;
+        j.n_mma = (int)round_up(in, 16);
+        j.db = grad->db[l]; j.db_scale = 1.0f;
+        r.job[k] = {grad->dW[l], m->ld[l], 0, out, in};
+    }
+    if (d_feat) {
+        DwJob& j = p.job[k];
+        j.P[0] = {d_feat, ld_dfeat, 256, 0};
+        j.Q[0] = {H + (int64_t)7 * np * 256, 0, 256, 1};
+        j.P[1] = j.P[0]; j.Q[1] = j.Q[0];
+        j.n_pairs = 1;
+        j.n_mma = 256;
+        j.db = grad->db[8] ? grad->db[8] + 1 : nullptr; j.db_scale = 1.0f;
+        r.job[k] = {grad->dW[8], m->ld[8], 1, 256, 256};
+        ++k;
+    }
+    p.n_jobs = k;
+    HN_PROPAGATE(launch_dw(p, r, s));
+    if (grad->dW[8] || grad->db[8]) {
+        const int splits = std::max(1, std::min(p.n_tiles, 16));
+        out_row0_grad_kernel<<<dim3(64, splits), 128, 0, s>>>(H + (int64_t)7 * np * 256, U + (int64_t)7 * np * 256, d_sdf, n,
+                                                            p.n_tiles, inv_scale, grad->dW[8], grad->db[8]);
+        count_launch();
+        HN_CHECK_LAUNCH();
+    }
+    return HN_OK;
+}
+
+int64_t stash_floats(int64_t n) { return round_up(n, TILE_M) * (64 + 16 * 256 + 64); }
 
 }  // namespace chain
 }  // namespace hn

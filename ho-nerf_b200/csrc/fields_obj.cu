@@ -14,7 +14,11 @@ namespace chain {   // chain_obj.cu
 int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s);
 int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat,
                    int64_t ld_feat, float* normal, float* stash, cudaStream_t s);
-int64_t bwd_ws_floats_per_point();
+int64_t bwd_ws_floats(int64_t n);
+int64_t stash_floats(int64_t n);
+int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
+                           const float* d_feat, int64_t ld_dfeat, float* ws, const hn_mlp_grad_t* grad,
+                           cudaStream_t s);
 int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
                    const float* d_feat, int64_t ld_dfeat, const float* d_normal, float* d_pts, float* ws,
                    cudaStream_t s);
@@ -209,13 +213,14 @@ using namespace hn;
 
 extern "C" {
 
-int64_t hn_sdf_obj_stash_floats(int64_t n) { return n * ObjSdfStash::kFloatsPerPoint; }
+// sized for the tiled layout of the HN_TC_BF16X3 path (n padded to whole 128-point tiles)
+int64_t hn_sdf_obj_stash_floats(int64_t n) { return std::max<int64_t>(n * ObjSdfStash::kFloatsPerPoint, chain::stash_floats(n)); }
 
 int64_t hn_sdf_obj_ws_floats(int64_t n, int kind) {
     switch (kind) {
         case HN_WS_SDF_ONLY: return n * (64 + 3 * 256);       // E, two ping-pong H, A4
         case HN_WS_FWD: return 4;                              // nothing beyond the stash
-        case HN_WS_BWD: return n * std::max<int64_t>(64 + 2 * 256 + 256 + 260 + 2 * 256 + 64, chain::bwd_ws_floats_per_point());
+        case HN_WS_BWD: return std::max<int64_t>(n * (64 + 2 * 256 + 256 + 260 + 2 * 256 + 64), chain::bwd_ws_floats(n));
         default: return -1;
     }
 }
@@ -314,40 +319,11 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
     cudaStream_t s = (cudaStream_t)stream;
     ObjSdfStash st(stash, n);
     if (precision == HN_TC_BF16X3) {
-        // fused tangent + reverse sweeps, then the weight-gradient contractions over the operands they left in ws
+        // fused tangent + reverse sweeps, then every weight-gradient contraction in one launch over the operands
+        // the sweeps left in ws
         HN_PROPAGATE(chain::launch_sdf_bwd(mlp, n, inv_scale, stash, d_sdf, d_feat, ld_dfeat, d_normal, d_pts, ws, s));
         if (!grad) return HN_OK;
-        float* cUE = ws;
-        float* cU = cUE + n * 64;
-        float* cDZ8 = cU + 16 * n * 256;
-        float* cDZ = cDZ8 + n * 260;
-        const int splits_target = 2 * sm_count();
-        auto dw = [&](const float* P, int64_t ldp, int out, const float* Q, int64_t ldq, int in, int l) -> int {
-            if (!grad->dW[l]) return HN_OK;
-            GemmArgs g;
-            g.A = P; g.lda = ldp; g.B = Q; g.ldb = ldq;
-            g.M = out; g.N = in; g.K = (int)n;
-            g.C = grad->dW[l]; g.ldc = mlp->ld[l];
-            int tiles = (int)(ceil_div(out, GBM) * ceil_div(in, GBN));
-            int splits = (int)max((int64_t)1, min((int64_t)ceil_div(splits_target, tiles), ceil_div(n, 256)));
-            return gemm_tn(g, s, precision, splits);
-        };
-        for (int l = 0; l < 8; ++l) {
-            const float* au = l == 0 ? cUE : cU + (int64_t)(l - 1) * n * 256;     // u_{l-1} (U[3] holds [u3 | ue])
-            const float* a = l == 0 ? st.E : st.H[l - 1];
-            const int64_t lda = l == 0 ? 64 : 256;
-            const float* dz = cDZ + (int64_t)l * n * 256;
-            HN_PROPAGATE(dw(st.D[l], 256, mlp->out_dim[l], au, lda, mlp->in_dim[l], l));
-            HN_PROPAGATE(dw(dz, 256, mlp->out_dim[l], a, lda, mlp->in_dim[l], l));
-            if (grad->db[l]) HN_PROPAGATE(launch_colsum(dz, 256, n, mlp->out_dim[l], 1.0f, grad->db[l], s));
-        }
-        assemble_dz8_kernel<<<blocks_for(n * 260, 256), 256, 0, s>>>(d_sdf, d_feat, ld_dfeat, inv_scale, n, cDZ8);
-        count_launch();
-        HN_CHECK_LAUNCH();
-        HN_PROPAGATE(dw(cDZ8, 260, 257, st.H[7], 256, 256, 8));
-        if (grad->db[8]) HN_PROPAGATE(launch_colsum(cDZ8, 260, n, 257, 1.0f, grad->db[8], s));
-        if (grad->dW[8]) HN_PROPAGATE(launch_colsum(cU + (int64_t)7 * n * 256, 256, n, 256, inv_scale, grad->dW[8], s));
-        return HN_OK;
+        return chain::launch_sdf_bwd_weights(mlp, n, inv_scale, stash, d_sdf, d_feat, ld_dfeat, ws, grad, s);
     }
     float* UE = ws;
     float* U[2] = {UE + n * 64, UE + n * 64 + n * 256};

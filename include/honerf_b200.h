@@ -295,6 +295,12 @@ HN_API int hn_fit_composite_bwd(const float* alpha_h, const float* rgb_h, const 
  * ------------------------------------------------------------------------------------------- */
 HN_API int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
                            hn_stream_t stream);
+/* The weight-gradient kernel of the HN_TC_BF16X3 path, for tests: C [out, ldc] += P^T Q (+ P2^T Q2) over n
+ * points, P [n, out] and Q [n, in] fp32, row-major (ld) or tiled ([tile][col/4][128][4], n padded to 128);
+ * db [out] += column sums of P (may be NULL); part: workspace of >= 16 * 65536 floats. */
+HN_API int hn_dw_test(const float* P, int64_t ldp, int p_tiled, int out, const float* Q, int64_t ldq,
+                      int q_tiled, int in, const float* P2, const float* Q2, int64_t n, float* C,
+                      int64_t ldc, float* db, float* part, int64_t part_floats, hn_stream_t stream);
 /* One dense contraction through the production kernels, for tests: C [M, ldc] (fp32).
  *   layout 0: C = A[M,lda] @ B[N,ldb]^T (+ bias[N])      layout 1: C = A[M,lda] @ B[K,ldb]
  *   layout 2: C += A[K,lda]^T @ B[K,ldb]  (K split over CTAs, atomics; caller zeroes C)
