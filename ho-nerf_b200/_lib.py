@@ -78,6 +78,8 @@ PROTOTYPES = {
                                c_int, P]),
     "hn_sdf_obj_bwd": (c_int, [_mlp_p, c_int64, c_float, P, P, P, c_int64, P, P, _grad_p, P, c_int64,
                                c_int, P]),
+    "hn_color_obj_chain_bytes": (c_int64, []),
+    "hn_color_obj_chain_pack": (c_int, [_mlp_p, P, c_int64, P]),
     "hn_color_obj_stash_floats": (c_int64, [c_int64]),
     "hn_color_obj_ws_floats": (c_int64, [c_int64, c_int]),
     "hn_color_obj_fwd": (c_int, [_mlp_p, P, P, P, c_int64, P, c_int64, P, P, c_int64, c_int, P]),

@@ -1,0 +1,446 @@
+// Object colour field (RenderingNetwork_OBJ.forward, utils/fields.py:387-405) as fused tile-chain kernels
+// on tcgen05 (HN_TC_BF16X3), forward and backward.  Input row of the first layer:
+//   [pts + enc10 (63) | dirs + enc4 (27) | feature (256) | normal + enc4 (27)] = 373
+// The 373-wide first layer is two chained steps on one accumulator: the 256 feature columns, then the 117
+// encoding columns (computed by the epilogue warps straight into the A operand).  ReLU between layers,
+// sigmoid on the 3 outputs (the last layer runs as an N = 16 MMA).
+#include <algorithm>
+
+#include "chain_common.cuh"
+#include "chain_dw.cuh"
+#include "fields_common.cuh"
+
+namespace hn {
+namespace chain {
+
+constexpr int ENC_LD = 128;      // [enc10(pts) 63 | enc4(dirs) 27 | enc4(normal) 27 | 0 x 11]
+constexpr int ENC_DIRS = 63, ENC_NRM = 90, ENC_DIM = 117;
+constexpr int CIN_FEAT0 = 90, CIN_NRM0 = 346;     // column offsets inside the reference's 373-wide input
+
+struct ColorLayout {
+    uint32_t nt0a, nt0b, nt[5], nn[5], nn0a, nn0b, total;   // nt[1..4], nn[1..4] used
+};
+static ColorLayout color_layout() {
+    ColorLayout L;
+    uint32_t off = 0;
+    L.nt0a = off; off += b_operand_bytes(256, 4);
+    L.nt0b = off; off += b_operand_bytes(256, 2);
+    for (int l = 1; l <= 3; ++l) { L.nt[l] = off; off += b_operand_bytes(256, 4); }
+    L.nt[4] = off; off += b_operand_bytes(16, 4);
+    L.nn[4] = off; off += b_operand_bytes(256, 1);
+    for (int l = 3; l >= 1; --l) { L.nn[l] = off; off += b_operand_bytes(256, 4); }
+    L.nn0a = off; off += b_operand_bytes(256, 4);
+    L.nn0b = off; off += b_operand_bytes(128, 4);
+    L.nt[0] = L.nn[0] = 0;
+    L.total = off;
+    return L;
+}
+
+// [x(3), sin/cos(2^k x_c), k < L] of a 3-vector -> columns col_base + j of the A operand and of the row-major
+// global row g (may be NULL); the (coordinate, frequency) pairs are shared by the 4 column groups of a row
+__device__ __forceinline__ void write_enc3(uint8_t* smem, int row, int cg, const float x[3], int L, int col_base,
+                                           float* __restrict__ g) {
+    if (cg == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a_store1(smem, row, col_base + c, x[c]);
+            if (g) g[col_base + c] = x[c];
+        }
+    }
+    for (int idx = cg; idx < 3 * L; idx += EPI_CGROUPS) {
+        const int c = idx / L, k = idx - c * L;
+        float s, co;
+        sincosf(x[c] * (float)(1 << k), &s, &co);
+        const int js = col_base + 3 + c * 2 * L + k, jc = js + L;
+        a_store1(smem, row, js, s);
+        a_store1(smem, row, jc, co);
+        if (g) { g[js] = s; g[jc] = co; }
+    }
+}
+
+struct ColorFwdParams {
+    const float* pts;
+    const float* dirs;
+    const float* feat;
+    int64_t ld_feat;
+    const float* normal;
+    int64_t n;
+    float* rgb;
+    float* ENC;       // stash: [np, 128] row-major
+    float* FEAT;      // stash: tiled copy of the feature input (operand of the first layer's weight gradient)
+    float* R[4];      // stash: tiled ReLU outputs
+    const uint8_t* chain;
+    const float* bias[5];
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant__ Program prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Barriers bar;
+    uint8_t* smem = chain_setup(smem_raw, &bar);
+    const int warp = threadIdx.x >> 5;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        producer_loop(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        mma_loop(prog, smem, &bar, n_my_tiles);
+    } else {
+        int row, cg;
+        epi_coords(row, cg);
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            // ---- A <- feature columns (and their tiled copy for the backward) ------------------------------
+            {
+                float* __restrict__ ft = p.FEAT + tile * TILE_FLOATS;
+#pragma unroll
+                for (int j = 0; j < EPI_COLS; j += 8) {
+                    const int col = cg * EPI_COLS + j;
+                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (live) {
+                        const float4 a = ld4(p.feat + gp * p.ld_feat + col), b = ld4(p.feat + gp * p.ld_feat + col + 4);
+                        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+                        st4(ft + toff(row, col), a);
+                        st4(ft + toff(row, col + 4), b);
+                    }
+                    a_store8(smem, row, col, f);
+                }
+            }
+            epi_publish_a(&bar);
+            // ---- A <- encodings of pts, dirs, normal (columns 0..127), accumulated onto the feature part ------
+            epi_wait_acc(&bar, acc_par);
+            {
+                float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, nr[3] = {0.f, 0.f, 0.f};
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { x[c] = p.pts[gp * 3 + c]; d[c] = p.dirs[gp * 3 + c]; nr[c] = p.normal[gp * 3 + c]; }
+                }
+                float* __restrict__ g = live ? p.ENC + gp * ENC_LD : nullptr;
+                write_enc3(smem, row, cg, x, 10, 0, g);
+                write_enc3(smem, row, cg, d, 4, ENC_DIRS, g);
+                write_enc3(smem, row, cg, nr, 4, ENC_NRM, g);
+                if (cg == 0) {
+                    for (int j = ENC_DIM; j < ENC_LD; ++j) {
+                        a_store1(smem, row, j, 0.0f);
+                        if (g) g[j] = 0.0f;
+                    }
+                }
+            }
+            epi_publish_a(&bar);
+            // ---- hidden layers: ReLU ----------------------------------------------------------------------------
+            for (int l = 0; l < 4; ++l) {
+                epi_wait_acc(&bar, acc_par);
+                const float* __restrict__ bias = p.bias[l];
+                float* __restrict__ rt = p.R[l] + tile * TILE_FLOATS;
+#pragma unroll
+                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                    const int col0 = cg * EPI_COLS + blk * 32;
+                    float v[32];
+                    acc_load32(tmem, row, col0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                        v[j] = fmaxf(v[j] + b.x, 0.0f);
+                        v[j + 1] = fmaxf(v[j + 1] + b.y, 0.0f);
+                        v[j + 2] = fmaxf(v[j + 2] + b.z, 0.0f);
+                        v[j + 3] = fmaxf(v[j + 3] + b.w, 0.0f);
+                        if (live) st4(rt + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                }
+                epi_publish_a(&bar);
+            }
+            // ---- output layer: sigmoid ---------------------------------------------------------------------------
+            epi_wait_acc(&bar, acc_par);
+            if (cg == 0) {
+                float v[16];
+                tc::tmem_ld_32x32b_x16(tmem + ((uint32_t)(row & ~31) << 16), v);
+                tc::tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) p.rgb[gp * 3 + c] = 1.0f / (1.0f + __expf(-(v[c] + __ldg(p.bias[4] + c))));
+                }
+            }
+        }
+    }
+    chain_teardown(&bar);
+}
+
+struct ColorBwdParams {
+    int64_t n;
+    const float* ENC;
+    const float* R[4];
+    const float* rgb;
+    const float* d_rgb;
+    float* d_pts;      // any of the four input cotangents may be NULL
+    float* d_dirs;
+    float* d_feat;
+    int64_t ld_dfeat;
+    float* d_normal;
+    float* DZ4;        // workspace: [np, 4] row-major
+    float* DZ[4];      // tiled
+    float* DENC;       // [np, 128] row-major
+    const uint8_t* chain;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+color_bwd_kernel(const __grid_constant__ ColorBwdParams p, const __grid_constant__ Program prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ Barriers bar;
+    uint8_t* smem = chain_setup(smem_raw, &bar);
+    const int warp = threadIdx.x >> 5;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        producer_loop(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        mma_loop(prog, smem, &bar, n_my_tiles);
+    } else {
+        int row, cg;
+        epi_coords(row, cg);
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            // ---- A <- dz_4 = d_rgb * rgb (1 - rgb), K padded to 64 ------------------------------------------
+            if (cg == 0) {
+                float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float y = p.rgb[gp * 3 + c];
+                        z[c] = p.d_rgb[gp * 3 + c] * y * (1.0f - y);
+                    }
+                    st4(p.DZ4 + gp * 4, make_float4(z[0], z[1], z[2], 0.0f));
+                }
+                a_store8(smem, row, 0, z);
+                const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int j = 8; j < 64; j += 8) a_store8(smem, row, j, zero);
+            }
+            epi_publish_a(&bar);
+            // ---- hidden layers: dz_{l-1} = [r_{l-1} > 0] (dz_l W_l), l = 4..1 ----------------------------------------
+            for (int l = 4; l >= 1; --l) {
+                epi_wait_acc(&bar, acc_par);
+                const float* __restrict__ rt = p.R[l - 1] + tile * TILE_FLOATS;
+                float* __restrict__ zt = p.DZ[l - 1] + tile * TILE_FLOATS;
+#pragma unroll
+                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                    const int col0 = cg * EPI_COLS + blk * 32;
+                    float v[32];
+                    acc_load32(tmem, row, col0, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (live) r = ld4(rt + toff(row, col0 + j));
+                        v[j] = r.x > 0.0f ? v[j] : 0.0f;
+                        v[j + 1] = r.y > 0.0f ? v[j + 1] : 0.0f;
+                        v[j + 2] = r.z > 0.0f ? v[j + 2] : 0.0f;
+                        v[j + 3] = r.w > 0.0f ? v[j + 3] : 0.0f;
+                        if (live) st4(zt + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                }
+                epi_publish_a(&bar);
+            }
+            // ---- input cotangent, feature columns: d_feat = dz_0 W_0[:, 90:346] ------------------------------------------
+            epi_wait_acc(&bar, acc_par);
+            if (p.d_feat) {
+#pragma unroll
+                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
+                    const int col0 = cg * EPI_COLS + blk * 32;
+                    float v[32];
+                    acc_load32(tmem, row, col0, v);
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            st4(p.d_feat + gp * p.ld_dfeat + col0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    }
+                }
+            }
+            epi_publish_a(&bar);      // A (dz_0) is unchanged; this only releases the accumulator
+            // ---- input cotangent, encoding columns -> d_pts, d_dirs, d_normal through J_enc^T ----------------------------
+            epi_wait_acc(&bar, acc_par);
+            if (p.d_pts || p.d_dirs || p.d_normal) {
+                float v[32];
+                acc_load32(tmem, row, cg * 32, v);
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) st4(p.DENC + gp * ENC_LD + cg * 32 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                }
+                tc::tc_fence_before_sync();
+                tc::named_bar_sync(1, EPI_THREADS);
+                if (live && cg < 3) {
+                    const float* __restrict__ e = p.ENC + gp * ENC_LD;
+                    const float* __restrict__ g = p.DENC + gp * ENC_LD;
+                    float* out = cg == 0 ? p.d_pts : cg == 1 ? p.d_dirs : p.d_normal;
+                    const int base = cg == 0 ? 0 : cg == 1 ? ENC_DIRS : ENC_NRM;
+                    const int L = cg == 0 ? 10 : 4;
+                    if (out) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) out[gp * 3 + c] = enc3_jt_from_enc(e + base, g + base, L, c);
+                    }
+                }
+            }
+        }
+    }
+    chain_teardown(&bar);
+}
+
+static int check_color_chain(const hn_mlp_t* m) {
+    HN_REQUIRE(m && m->n_layers == 5, "object colour mlp must have 5 layers");
+    HN_REQUIRE(m->chain && m->chain_bytes >= (int64_t)color_layout().total && aligned16(m->chain),
+               "HN_TC_BF16X3 needs the packed chain operands (hn_color_obj_chain_pack)");
+    return HN_OK;
+}
+static void set_step(Step& s, uint32_t off, int n_mma, int kb, int acc_in = 0) {
+    s.b_off = off; s.n_mma = (uint16_t)n_mma; s.kblocks = (uint8_t)kb; s.a_kb0 = 0; s.acc_in = (uint8_t)acc_in;
+}
+
+int64_t color_stash_floats(int64_t n) { return round_up(n, TILE_M) * (ENC_LD + 5 * 256); }
+int64_t color_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (4 + 4 * 256 + ENC_LD) + dw_part_floats(6); }
+
+int launch_color_fwd(const hn_mlp_t* m, const float* pts, const float* dirs, const float* feat, int64_t ld_feat,
+                     const float* normal, int64_t n, float* rgb, float* stash, cudaStream_t s) {
+    HN_PROPAGATE(check_color_chain(m));
+    HN_REQUIRE(ld_feat % 4 == 0 && aligned16(feat), "feature input must be 16-byte aligned with ld %% 4 == 0");
+    const ColorLayout L = color_layout();
+    const int64_t np = round_up(n, TILE_M);
+    ColorFwdParams p;
+    p.pts = pts; p.dirs = dirs; p.feat = feat; p.ld_feat = ld_feat; p.normal = normal; p.n = n; p.rgb = rgb;
+    p.ENC = stash;
+    p.FEAT = stash + np * ENC_LD;
+    for (int l = 0; l < 4; ++l) p.R[l] = stash + np * ENC_LD + (int64_t)(1 + l) * np * 256;
+    p.chain = reinterpret_cast<const uint8_t*>(m->chain);
+    for (int l = 0; l < 5; ++l) p.bias[l] = m->b[l];
+    p.n_tiles = (int)(np / TILE_M);
+    Program prog = {};
+    set_step(prog.step[0], L.nt0a, 256, 4);
+    set_step(prog.step[1], L.nt0b, 256, 2, 1);
+    for (int l = 1; l <= 3; ++l) set_step(prog.step[1 + l], L.nt[l], 256, 4);
+    set_step(prog.step[5], L.nt[4], 16, 4);
+    prog.n_steps = 6;
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(color_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    {
+        TimingScope ts(s);
+        color_fwd_kernel<<<std::min(p.n_tiles, sm_count()), THREADS, SMEM_BYTES, s>>>(p, prog);
+    }
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int launch_color_bwd(const hn_mlp_t* m, int64_t n, const float* stash, const float* rgb, const float* d_rgb, float* d_pts,
+                     float* d_dirs, float* d_feat, int64_t ld_dfeat, float* d_normal, const hn_mlp_grad_t* grad, float* ws,
+                     cudaStream_t s) {
+    HN_PROPAGATE(check_color_chain(m));
+    HN_REQUIRE(!d_feat || (ld_dfeat % 4 == 0 && aligned16(d_feat)), "d_feat must be 16-byte aligned with ld %% 4 == 0");
+    const ColorLayout L = color_layout();
+    const int64_t np = round_up(n, TILE_M);
+    ColorBwdParams p;
+    p.n = n;
+    p.ENC = stash;
+    const float* FEAT = stash + np * ENC_LD;
+    for (int l = 0; l < 4; ++l) p.R[l] = stash + np * ENC_LD + (int64_t)(1 + l) * np * 256;
+    p.rgb = rgb; p.d_rgb = d_rgb; p.d_pts = d_pts; p.d_dirs = d_dirs; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.d_normal = d_normal;
+    p.DZ4 = ws;
+    for (int l = 0; l < 4; ++l) p.DZ[l] = ws + np * 4 + (int64_t)l * np * 256;
+    p.DENC = ws + np * 4 + 4 * np * 256;
+    float* part = p.DENC + np * ENC_LD;
+    p.chain = reinterpret_cast<const uint8_t*>(m->chain);
+    p.n_tiles = (int)(np / TILE_M);
+    Program prog = {};
+    set_step(prog.step[0], L.nn[4], 256, 1);
+    for (int l = 3; l >= 1; --l) set_step(prog.step[4 - l], L.nn[l], 256, 4);
+    set_step(prog.step[4], L.nn0a, 256, 4);
+    set_step(prog.step[5], L.nn0b, 128, 4);
+    prog.n_steps = 6;
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(color_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    {
+        TimingScope ts(s);
+        color_bwd_kernel<<<std::min(p.n_tiles, sm_count()), THREADS, SMEM_BYTES, s>>>(p, prog);
+    }
+    count_launch();
+    HN_CHECK_LAUNCH();
+    if (!grad) return HN_OK;
+    // ---- weight gradients: dW_l = DZ_l^T a_{l-1} for all five layers in one launch -------------------------------
+    DwParams dp;
+    DwReduceParams rp;
+    dp.n = n; dp.n_tiles = p.n_tiles; dp.part = part; rp.part = part;
+    int k = 0;
+    auto job = [&](DwOperand P, DwOperand Q, float* db, DwReduceJob r) {
+        DwJob& j = dp.job[k];
+        j.P[0] = P; j.Q[0] = Q; j.P[1] = P; j.Q[1] = Q;
+        j.n_pairs = 1;
+        j.n_mma = (int)round_up(Q.cols, 16);
+        j.db = db; j.db_scale = 1.0f;
+        rp.job[k] = r;
+        ++k;
+    };
+    const int ld0 = m->ld[0];
+    job({p.DZ[0], 0, 256, 1}, {FEAT, 0, 256, 1}, grad->db[0], reduce_job(grad->dW[0], ld0, 0, 256, 256, CIN_FEAT0));
+    job({p.DZ[0], 0, 256, 1}, {p.ENC, ENC_LD, ENC_DIM, 0}, nullptr,
+        reduce_job(grad->dW[0], ld0, 0, 256, ENC_DIM, 0, CIN_FEAT0, CIN_NRM0));
+    for (int l = 1; l <= 3; ++l)
+        job({p.DZ[l], 0, 256, 1}, {p.R[l - 1], 0, 256, 1}, grad->db[l], reduce_job(grad->dW[l], m->ld[l], 0, 256, 256));
+    job({p.DZ4, 4, 3, 0}, {p.R[3], 0, 256, 1}, grad->db[4], reduce_job(grad->dW[4], m->ld[4], 0, 3, 256));
+    dp.n_jobs = k;
+    return launch_dw(dp, rp, s);
+}
+
+}  // namespace chain
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" {
+
+int64_t hn_color_obj_chain_bytes(void) { return (int64_t)chain::color_layout().total; }
+
+int hn_color_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_bytes, hn_stream_t stream) {
+    HN_REQUIRE(m && m->n_layers == 5, "hn_color_obj_chain_pack: object colour mlp must have 5 layers");
+    const chain::ColorLayout L = chain::color_layout();
+    HN_REQUIRE(chain_buf && chain_bytes >= (int64_t)L.total && aligned16(chain_buf),
+               "hn_color_obj_chain_pack: buffer too small or misaligned (need %u bytes)", L.total);
+    static const int in_d[5] = {373, 256, 256, 256, 256};
+    static const int out_d[5] = {256, 256, 256, 256, 3};
+    for (int l = 0; l < 5; ++l)
+        HN_REQUIRE(m->in_dim[l] == in_d[l] && m->out_dim[l] == out_d[l] && m->W[l] && m->WT[l],
+                   "hn_color_obj_chain_pack: layer %d has the wrong shape or no transposed copy", l);
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* dst = reinterpret_cast<uint8_t*>(chain_buf);
+    using chain::PackMap;
+    using chain::launch_pack_b;
+    const int big = 1 << 30;
+    // a @ W^T operands: B(n = out, k = in)
+    HN_PROPAGATE(launch_pack_b(m->W[0], m->ld[0], 0, chain::CIN_FEAT0, 256, 256, 256, 4, dst + L.nt0a, s));
+    HN_PROPAGATE(launch_pack_b(m->W[0], m->ld[0], PackMap{0, big, 0, 0, chain::CIN_FEAT0, chain::CIN_NRM0}, 256, chain::ENC_DIM, 256, 2,
+                               dst + L.nt0b, s));
+    for (int l = 1; l <= 3; ++l) HN_PROPAGATE(launch_pack_b(m->W[l], m->ld[l], 0, 0, 256, 256, 256, 4, dst + L.nt[l], s));
+    HN_PROPAGATE(launch_pack_b(m->W[4], m->ld[4], 0, 0, 3, 256, 16, 4, dst + L.nt[4], s));
+    // d @ W operands: B(n = in, k = out) from the transposed copies
+    HN_PROPAGATE(launch_pack_b(m->WT[4], m->ldT[4], 0, 0, 256, 3, 256, 1, dst + L.nn[4], s));
+    for (int l = 3; l >= 1; --l) HN_PROPAGATE(launch_pack_b(m->WT[l], m->ldT[l], 0, 0, 256, 256, 256, 4, dst + L.nn[l], s));
+    HN_PROPAGATE(launch_pack_b(m->WT[0], m->ldT[0], chain::CIN_FEAT0, 0, 256, 256, 256, 4, dst + L.nn0a, s));
+    HN_PROPAGATE(launch_pack_b(m->WT[0], m->ldT[0], PackMap{0, chain::CIN_FEAT0, chain::CIN_NRM0, 0, big, 0}, chain::ENC_DIM, 256, 128, 4,
+                               dst + L.nn0b, s));
+    return HN_OK;
+}
+
+}  // extern "C"

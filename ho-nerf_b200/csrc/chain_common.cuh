@@ -44,7 +44,8 @@ struct Step {
     uint32_t b_off;
     uint16_t n_mma;
     uint8_t kblocks;
-    uint8_t a_kb0;
+    uint8_t a_kb0 : 4;
+    uint8_t acc_in : 1;      // accumulate onto the previous step's result (a layer whose K is split in two steps)
 };
 struct Program {
     int n_steps;
@@ -65,6 +66,13 @@ struct Barriers {
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// The [points, 256] fp32 arrays the chain kernels exchange through HBM (H, D, U, X, DZ) are TILED:
+// [tile][column / 4][row in tile (128)][4 floats], so that the epilogue's access pattern (thread = row,
+// four consecutive columns per access) is one contiguous 512-byte segment per warp instruction, and the
+// weight-gradient kernel (lane = point) reads them coalesced as well.  n is padded to whole tiles.
+constexpr int64_t TILE_FLOATS = (int64_t)TILE_M * 256;
+__device__ __forceinline__ int toff(int row, int col) { return (col >> 2) * 512 + row * 4 + (col & 3); }
 
 // ---- bf16 hi/lo split ------------------------------------------------------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -188,7 +196,7 @@ __device__ __forceinline__ void mma_loop(const Program& prog, uint8_t* smem, Bar
                 uint64_t dB = tc::make_smem_desc_sw128(ring + stage * STAGE_BYTES);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    tc::umma_f16(tmem, dAl + 2 * k, dB + 2 * k, idesc, (kb | k) != 0);
+                    tc::umma_f16(tmem, dAl + 2 * k, dB + 2 * k, idesc, (kb | k | st.acc_in) != 0);
                     tc::umma_f16(tmem, dAh + 2 * k, dB + 2 * k, idesc, 1);
                 }
                 tc::umma_commit(&bar->empty[stage]);
@@ -245,8 +253,18 @@ __device__ __forceinline__ void acc_load32_nowait(uint32_t tmem_base, int row, i
 // ---- packing ---------------------------------------------------------------------------------------
 // dst tile element (n, k) <- src[(row0 + n) * ld + col0 + k] for n < rows, k < cols, else 0;
 // layout: k-block kb at kb * 2 * n_pad * 128 B: hi tile then lo tile, each [n_pad x 128 B] SW128.
-int launch_pack_b(const float* src, int64_t ld, int row0, int col0, int rows, int cols, int n_pad, int kblocks,
+// Row / column maps let an operand gather two ranges of the source: n < rsplit -> row0 + n, else
+// row1 + (n - rsplit); k < ksplit -> col0 + k, else col1 + (k - ksplit).
+struct PackMap {
+    int row0, rsplit, row1, col0, ksplit, col1;
+};
+inline PackMap pack_map(int row0, int col0) { return PackMap{row0, 1 << 30, 0, col0, 1 << 30, 0}; }
+int launch_pack_b(const float* src, int64_t ld, PackMap map, int rows, int cols, int n_pad, int kblocks,
                   uint8_t* dst, cudaStream_t stream);
+inline int launch_pack_b(const float* src, int64_t ld, int row0, int col0, int rows, int cols, int n_pad, int kblocks,
+                         uint8_t* dst, cudaStream_t stream) {
+    return launch_pack_b(src, ld, pack_map(row0, col0), rows, cols, n_pad, kblocks, dst, stream);
+}
 
 }  // namespace chain
 }  // namespace hn

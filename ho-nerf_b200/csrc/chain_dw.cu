@@ -219,11 +219,11 @@ __global__ void dw_reduce_kernel(const __grid_constant__ DwReduceParams p) {
         const float4 v = ld4(src + (size_t)s * 65536);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    float* dst = jb.dW + (size_t)(jb.row0 + r) * jb.ld + c;
+    float* dst = jb.dW + (size_t)(jb.row0 + r) * jb.ld;
     const float a[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i)
-        if (c + i < jb.cols) dst[i] += a[i];
+        if (c + i < jb.cols) dst[c + i < jb.csplit ? jb.col0 + c + i : jb.col1 + (c + i - jb.csplit)] += a[i];
 }
 
 int64_t dw_part_floats(int n_jobs) { return (int64_t)n_jobs * DW_SPLITS * 65536; }
@@ -267,6 +267,6 @@ extern "C" int hn_dw_test(const float* P, int64_t ldp, int p_tiled, int out, con
     j.db = db; j.db_scale = 1.0f;
     chain::DwReduceParams r;
     r.part = part;
-    r.job[0] = {C, (int)ldc, 0, out, in};
+    r.job[0] = chain::reduce_job(C, (int)ldc, 0, out, in);
     return chain::launch_dw(p, r, (cudaStream_t)stream);
 }

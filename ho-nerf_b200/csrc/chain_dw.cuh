@@ -30,11 +30,16 @@ struct DwParams {
     float* part;       // [n_jobs][DW_SPLITS][256][256]
 };
 
-// dW[(row0 + r) * ld + c] += sum_s part[job][s][r][c]   for r < rows, c < cols
+// dW[(row0 + r) * ld + col(c)] += sum_s part[job][s][r][c]   for r < rows, c < cols, where
+// col(c) = c < csplit ? col0 + c : col1 + (c - csplit)
 struct DwReduceJob {
     float* dW;
     int ld, row0, rows, cols;
+    int col0, csplit, col1;
 };
+inline DwReduceJob reduce_job(float* dW, int ld, int row0, int rows, int cols, int col0 = 0, int csplit = 1 << 30, int col1 = 0) {
+    return DwReduceJob{dW, ld, row0, rows, cols, col0, csplit, col1};
+}
 struct DwReduceParams {
     DwReduceJob job[DW_MAX_JOBS];
     const float* part;

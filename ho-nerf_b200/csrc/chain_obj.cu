@@ -13,42 +13,6 @@
 namespace hn {
 namespace chain {
 
-// ------------------------------------------------------------------------------------------------
-// packing
-// ------------------------------------------------------------------------------------------------
-__global__ void pack_b_kernel(const float* __restrict__ src, int64_t ld, int row0, int col0, int rows, int cols,
-                              int n_pad, int kblocks, uint8_t* __restrict__ dst) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;          // one 16-byte chunk (8 columns) of one row
-    int total = n_pad * kblocks * 8;
-    if (idx >= total) return;
-    int n = idx / (kblocks * 8);
-    int c = idx - n * (kblocks * 8);
-    int kb = c >> 3, c16 = c & 7;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        int k = kb * 64 + c16 * 8 + j;
-        v[j] = (n < rows && k < cols) ? src[(int64_t)(row0 + n) * ld + col0 + k] : 0.0f;
-    }
-    uint4 hi, lo;
-    split2(v[0], v[1], hi.x, lo.x);
-    split2(v[2], v[3], hi.y, lo.y);
-    split2(v[4], v[5], hi.z, lo.z);
-    split2(v[6], v[7], hi.w, lo.w);
-    size_t base = (size_t)kb * 2 * n_pad * 128 + tc::sw128_offset((uint32_t)n, (uint32_t)c16);
-    *reinterpret_cast<uint4*>(dst + base) = hi;
-    *reinterpret_cast<uint4*>(dst + base + (size_t)n_pad * 128) = lo;
-}
-
-int launch_pack_b(const float* src, int64_t ld, int row0, int col0, int rows, int cols, int n_pad, int kblocks,
-                  uint8_t* dst, cudaStream_t stream) {
-    int total = n_pad * kblocks * 8;
-    pack_b_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, ld, row0, col0, rows, cols, n_pad, kblocks, dst);
-    count_launch();
-    HN_CHECK_LAUNCH();
-    return HN_OK;
-}
-
 // Packed operands of the object SDF net.  NT[l]: B(n = output feature, k = input feature) for
 // a @ W_l^T (value trunk, tangent sweep); NN[l]: B(n = input feature, k = output feature) for
 // d @ W_l (normal sweep, reverse sweep).  The output layer is packed without its sdf row (row 0),
@@ -81,12 +45,7 @@ static ObjLayout obj_layout() {
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
 // ------------------------------------------------------------------------------------------------
-// The [points, 256] fp32 arrays the chain kernels exchange through HBM (H, D, U, X, DZ) are TILED:
-// [tile][column / 4][row in tile (128)][4 floats], so that the epilogue's access pattern (thread = row,
-// four consecutive columns per access) is one contiguous 512-byte segment per warp instruction, and the
-// weight-gradient kernel (lane = point) reads them coalesced as well.  n is padded to whole tiles.
-constexpr int64_t TILE_FLOATS = (int64_t)TILE_M * 256;
-__device__ __forceinline__ int toff(int row, int col) { return (col >> 2) * 512 + row * 4 + (col & 3); }
+
 // [x(3), sin/cos(2^k x_c)] of one point written as columns shift + j of the A operand; the column
 // groups of a row share the 30 (coordinate, frequency) pairs.  Column shift+63 (the K padding of the
 // first layer) is zeroed when shift == 0.
@@ -673,7 +632,7 @@ int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sc
     p.w_out0 = m->W[8];
     p.n_tiles = (int)ceil_div(n, TILE_M);
     p.prof = g_prof;
-    Program prog;
+    Program prog = {};
     prog.n_steps = 8;
     for (int l = 0; l < 8; ++l) {
         prog.step[l].b_off = L.nt_off[l];
@@ -714,7 +673,7 @@ int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
     p.w_out0 = m->W[8];
     p.n_tiles = (int)ceil_div(n, TILE_M);
     p.prof = g_prof;
-    Program prog;
+    Program prog = {};
     int k = 0;
     for (int l = 0; l < 9; ++l, ++k) {           // value trunk + feature head: a @ W_l^T
         prog.step[k].b_off = L.nt_off[l];
@@ -772,7 +731,7 @@ int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     p.w_out0 = m->W[8];
     p.n_tiles = (int)ceil_div(n, TILE_M);
     p.prof = g_prof;
-    Program prog;
+    Program prog = {};
     int k = 0;
     for (int l = 0; l < 8; ++l, ++k) {           // tangent sweep: u @ W_l^T
         prog.step[k].b_off = L.nt_off[l];
@@ -869,7 +828,7 @@ int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const 
         j.n_pairs = 2;
         j.n_mma = (int)round_up(in, 16);
         j.db = grad->db[l]; j.db_scale = 1.0f;
-        r.job[k] = {grad->dW[l], m->ld[l], 0, out, in};
+        r.job[k] = reduce_job(grad->dW[l], m->ld[l], 0, out, in);
     }
     if (d_feat) {
         DwJob& j = p.job[k];
@@ -879,7 +838,7 @@ int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const 
         j.n_pairs = 1;
         j.n_mma = 256;
         j.db = grad->db[8] ? grad->db[8] + 1 : nullptr; j.db_scale = 1.0f;
-        r.job[k] = {grad->dW[8], m->ld[8], 1, 256, 256};
+        r.job[k] = reduce_job(grad->dW[8], m->ld[8], 1, 256, 256);
         ++k;
     }
     p.n_jobs = k;

@@ -1,0 +1,45 @@
+// Weight packing for the fused chain kernels: fp32 effective weights -> bf16 hi/lo tiles already in the
+// tcgen05 shared-memory layout (K-major, SWIZZLE_128B), so the kernels' producer warp streams them with
+// plain bulk copies.  Runs once per parameter version.
+#include "chain_common.cuh"
+
+namespace hn {
+namespace chain {
+
+__global__ void pack_b_kernel(const float* __restrict__ src, int64_t ld, PackMap m, int rows, int cols, int n_pad,
+                              int kblocks, uint8_t* __restrict__ dst) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;          // one 16-byte chunk (8 columns) of one row
+    int total = n_pad * kblocks * 8;
+    if (idx >= total) return;
+    int n = idx / (kblocks * 8);
+    int c = idx - n * (kblocks * 8);
+    int kb = c >> 3, c16 = c & 7;
+    const int64_t srow = n < m.rsplit ? m.row0 + n : m.row1 + (n - m.rsplit);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        int k = kb * 64 + c16 * 8 + j;
+        const int scol = k < m.ksplit ? m.col0 + k : m.col1 + (k - m.ksplit);
+        v[j] = (n < rows && k < cols) ? src[srow * ld + scol] : 0.0f;
+    }
+    uint4 hi, lo;
+    split2(v[0], v[1], hi.x, lo.x);
+    split2(v[2], v[3], hi.y, lo.y);
+    split2(v[4], v[5], hi.z, lo.z);
+    split2(v[6], v[7], hi.w, lo.w);
+    size_t base = (size_t)kb * 2 * n_pad * 128 + tc::sw128_offset((uint32_t)n, (uint32_t)c16);
+    *reinterpret_cast<uint4*>(dst + base) = hi;
+    *reinterpret_cast<uint4*>(dst + base + (size_t)n_pad * 128) = lo;
+}
+
+int launch_pack_b(const float* src, int64_t ld, PackMap map, int rows, int cols, int n_pad, int kblocks, uint8_t* dst,
+                  cudaStream_t stream) {
+    int total = n_pad * kblocks * 8;
+    pack_b_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, ld, map, rows, cols, n_pad, kblocks, dst);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+}  // namespace chain
+}  // namespace hn

@@ -14,6 +14,13 @@ namespace chain {   // chain_obj.cu
 int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s);
 int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat,
                    int64_t ld_feat, float* normal, float* stash, cudaStream_t s);
+int64_t color_stash_floats(int64_t n);
+int64_t color_bwd_ws_floats(int64_t n);
+int launch_color_fwd(const hn_mlp_t* m, const float* pts, const float* dirs, const float* feat, int64_t ld_feat,
+                     const float* normal, int64_t n, float* rgb, float* stash, cudaStream_t s);
+int launch_color_bwd(const hn_mlp_t* m, int64_t n, const float* stash, const float* rgb, const float* d_rgb, float* d_pts,
+                     float* d_dirs, float* d_feat, int64_t ld_dfeat, float* d_normal, const hn_mlp_grad_t* grad, float* ws,
+                     cudaStream_t s);
 int64_t bwd_ws_floats(int64_t n);
 int64_t stash_floats(int64_t n);
 int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
@@ -499,10 +506,10 @@ static int check_color_obj_mlp(const hn_mlp_t* m) {
 
 extern "C" {
 
-int64_t hn_color_obj_stash_floats(int64_t n) { return n * (CIN_LD + 4 * 256); }
+int64_t hn_color_obj_stash_floats(int64_t n) { return std::max<int64_t>(n * (CIN_LD + 4 * 256), chain::color_stash_floats(n)); }
 
 int64_t hn_color_obj_ws_floats(int64_t n, int kind) {
-    if (kind == HN_WS_BWD) return n * (2 * 256 + 4 + CIN_LD);
+    if (kind == HN_WS_BWD) return std::max<int64_t>(n * (2 * 256 + 4 + CIN_LD), chain::color_bwd_ws_floats(n));
     return 4;
 }
 
@@ -516,6 +523,7 @@ int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs, c
     HN_REQUIRE(pts && dirs && feat && normal && rgb && stash, "hn_color_obj_fwd: null pointer");
     HN_REQUIRE(stash_floats >= hn_color_obj_stash_floats(n) && aligned16(stash), "stash too small or misaligned");
     cudaStream_t s = (cudaStream_t)stream;
+    if (precision == HN_TC_BF16X3) return chain::launch_color_fwd(mlp, pts, dirs, feat, ld_feat, normal, n, rgb, stash, s);
     float* CIN = stash;
     float* R[4];
     for (int l = 0; l < 4; ++l) R[l] = stash + n * CIN_LD + (int64_t)l * n * 256;
@@ -548,6 +556,8 @@ int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* 
     HN_REQUIRE(stash && rgb && d_rgb && ws, "hn_color_obj_bwd: null pointer");
     HN_REQUIRE(ws_floats >= hn_color_obj_ws_floats(n, HN_WS_BWD) && aligned16(ws), "workspace too small or misaligned");
     cudaStream_t s = (cudaStream_t)stream;
+    if (precision == HN_TC_BF16X3)
+        return chain::launch_color_bwd(mlp, n, stash, rgb, d_rgb, d_pts, d_dirs, d_feat, ld_dfeat, d_normal, grad, ws, s);
     float* CIN = stash;
     float* R[4];
     for (int l = 0; l < 4; ++l) R[l] = stash + n * CIN_LD + (int64_t)l * n * 256;

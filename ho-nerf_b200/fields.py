@@ -281,7 +281,7 @@ class RenderingNetwork_OBJ(nn.Module):
         if self._packed is None:
             layers = [(getattr(self, "lin%d" % l).weight_g, getattr(self, "lin%d" % l).weight_v,
                        getattr(self, "lin%d" % l).bias) for l in range(self.num_layers - 1)]
-            self._packed = ops.PackedMLP(layers, [1.0] * len(layers))
+            self._packed = ops.PackedMLP(layers, [1.0] * len(layers), chain_kind="color_obj")
         return self._packed
 
     def _apply(self, fn, *a, **k):

@@ -80,7 +80,7 @@ class PackedMLP:
         self.WT = None
         self.W = None
         self.bias = None
-        self.chain_kind = chain_kind        # 'sdf_obj': also pack the HN_TC_BF16X3 chain operands
+        self.chain_kind = chain_kind        # 'sdf_obj' | 'color_obj': also pack the HN_TC_BF16X3 chain operands
         self.chain = None
         self.struct = None
         self._key = None
@@ -114,12 +114,13 @@ class PackedMLP:
             st.WT[l] = WTl.data_ptr()
             st.ldT[l] = self.ldTs[l]
             st.b[l] = bd.data_ptr()
-        if self.chain_kind == "sdf_obj":
-            nbytes = int(lib.hn_sdf_obj_chain_bytes())
+        if self.chain_kind is not None:
+            size_fn, pack_fn = {"sdf_obj": (lib.hn_sdf_obj_chain_bytes, lib.hn_sdf_obj_chain_pack),
+                                "color_obj": (lib.hn_color_obj_chain_bytes, lib.hn_color_obj_chain_pack)}[self.chain_kind]
+            nbytes = int(size_fn())
             if self.chain is None or self.chain.device != dev:
                 self.chain = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-            check(lib.hn_sdf_obj_chain_pack(ctypes.byref(st), _ptr(self.chain), nbytes, _stream(self.W)),
-                  "hn_sdf_obj_chain_pack")
+            check(pack_fn(ctypes.byref(st), _ptr(self.chain), nbytes, _stream(self.W)), "hn_%s_chain_pack" % self.chain_kind)
             st.chain = self.chain.data_ptr()
             st.chain_bytes = nbytes
         self._keep = keep

@@ -149,6 +149,10 @@ HN_API int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n_pts, float inv_scale, f
  * ------------------------------------------------------------------------------------------- */
 HN_API int64_t hn_color_obj_stash_floats(int64_t n_pts);
 HN_API int64_t hn_color_obj_ws_floats(int64_t n_pts, int ws_kind);
+/* HN_TC_BF16X3 chain operands of the colour net (see hn_sdf_obj_chain_pack). */
+HN_API int64_t hn_color_obj_chain_bytes(void);
+HN_API int hn_color_obj_chain_pack(const hn_mlp_t* mlp, void* chain, int64_t chain_bytes,
+                                   hn_stream_t stream);
 HN_API int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs,
                             const float* feat, int64_t ld_feat, const float* normal,
                             int64_t n_pts, float* rgb, float* stash, int64_t stash_floats,
