@@ -69,6 +69,7 @@ PROTOTYPES = {
     "hn_color_hand_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, c_int64, P, c_int64, P, _grad_p, P, c_int64,
                                   c_int, P]),
     "hn_chain_set_prof": (c_int, [P]),
+    "hn_chain_set_stagger": (c_int, [c_int, c_int]),
     "hn_sdf_obj_chain_bytes": (c_int64, []),
     "hn_sdf_obj_chain_pack": (c_int, [_mlp_p, P, c_int64, P]),
     "hn_sdf_obj_stash_floats": (c_int64, [c_int64]),

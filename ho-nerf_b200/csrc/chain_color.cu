@@ -228,27 +228,21 @@ color_bwd_kernel(const __grid_constant__ ColorBwdParams p, const __grid_constant
             epi_publish_a(&bar);
             // ---- hidden layers: dz_{l-1} = [r_{l-1} > 0] (dz_l W_l), l = 4..1 ----------------------------------------
             for (int l = 4; l >= 1; --l) {
-                epi_wait_acc(&bar, acc_par);
                 const float* __restrict__ rt = p.R[l - 1] + tile * TILE_FLOATS;
                 float* __restrict__ zt = p.DZ[l - 1] + tile * TILE_FLOATS;
+                epi_stream<1, 8>(&bar, acc_par, tmem, row, cg, live, true, rt, rt, [&](int col0, float* v, float4 (*aux)[2]) {
 #pragma unroll
-                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
-                    const int col0 = cg * EPI_COLS + blk * 32;
-                    float v[32];
-                    acc_load32(tmem, row, col0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live) r = ld4(rt + toff(row, col0 + j));
+                    for (int q = 0; q < 2; ++q) {
+                        const int j = q * 4;
+                        const float4 r = aux[0][q];
                         v[j] = r.x > 0.0f ? v[j] : 0.0f;
                         v[j + 1] = r.y > 0.0f ? v[j + 1] : 0.0f;
                         v[j + 2] = r.z > 0.0f ? v[j + 2] : 0.0f;
                         v[j + 3] = r.w > 0.0f ? v[j + 3] : 0.0f;
                         if (live) st4(zt + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
-                }
+                    a_store8(smem, row, col0, v);
+                });
                 epi_publish_a(&bar);
             }
             // ---- input cotangent, feature columns: d_feat = dz_0 W_0[:, 90:346] ------------------------------------------

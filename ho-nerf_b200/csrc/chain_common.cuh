@@ -222,6 +222,25 @@ __device__ __forceinline__ void mma_loop(const Program& prog, uint8_t* smem, Bar
     }
 }
 
+// One epilogue thread asks L2 for a whole [128, 256] fp32 tile (128 KB contiguous in the tiled layout) that the
+// NEXT epilogue will read, so that the HBM traffic overlaps the MMAs instead of following them.
+__device__ __forceinline__ void prefetch_tile(const float* tile_base, bool enable = true) {
+    if (!enable) return;
+    // 128 KB = 1024 lines of 128 B; 512 epilogue threads take two lines each
+    const char* base = reinterpret_cast<const char*>(tile_base) + (size_t)(threadIdx.x - 64) * 128;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 65536));
+}
+
+// All CTAs run the same program, so without help their HBM-heavy epilogues and their MMA phases line up
+// across the chip (HBM saturated, then idle).  Shifting CTAs by a fraction of a layer period spreads the
+// memory phases over time.  Called once by the epilogue warps before the first tile.
+__device__ __forceinline__ void stagger_start(int cycles_per_slot, int slots) {
+    const long long until = clock64() + (long long)(blockIdx.x % slots) * cycles_per_slot;
+    while (clock64() < until) {
+    }
+}
+
 // epilogue side of the handshake
 __device__ __forceinline__ void epi_publish_a(Barriers* bar) {
     tc::tc_fence_before_sync();       // orders this thread's tcgen05.ld before the MMAs that overwrite the accumulator
@@ -248,6 +267,39 @@ __device__ __forceinline__ void acc_load32(uint32_t tmem_base, int row, int col0
 }
 __device__ __forceinline__ void acc_load32_nowait(uint32_t tmem_base, int row, int col0, float* v) {
     tc::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(row & ~31) << 16) + (uint32_t)col0, v);
+}
+
+// Streams this thread's EPI_COLS accumulator columns in sub-blocks of SUB (8 or 16) through
+// f(col0, v[SUB], aux), with up to two tiled fp32 input arrays (a0, a1: tile base pointers) software-pipelined
+// one sub-block ahead in registers.  The first loads are issued BEFORE the wait for the accumulator, so their
+// latency overlaps the MMAs.  SUB = 8 keeps two arrays within the 96-register budget of the 576-thread CTA.
+template <int NA, int SUB, class F>
+__device__ __forceinline__ void epi_stream(Barriers* bar, uint32_t& acc_par, uint32_t tmem, int row, int cg, bool live,
+                                           bool active, const float* __restrict__ a0, const float* __restrict__ a1,
+                                           F&& f) {
+    constexpr int NSB = EPI_COLS / SUB, NQ = SUB / 4;
+    float4 buf[2][NA][NQ];
+    auto issue = [&](int sb, int slot) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int off = toff(row, cg * EPI_COLS + sb * SUB + q * 4);
+            buf[slot][0][q] = live ? ld4(a0 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (NA > 1) buf[slot][NA - 1][q] = live ? ld4(a1 + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if (active) issue(0, 0);
+    epi_wait_acc(bar, acc_par);
+    if (!active) return;
+#pragma unroll
+    for (int sb = 0; sb < NSB; ++sb) {
+        if (sb + 1 < NSB) issue(sb + 1, (sb + 1) & 1);
+        const int col0 = cg * EPI_COLS + sb * SUB;
+        float v[SUB];
+        const uint32_t taddr = tmem + ((uint32_t)(row & ~31) << 16) + (uint32_t)col0;
+        if (SUB == 16) tc::tmem_ld_32x32b_x16(taddr, v); else tc::tmem_ld_32x32b_x8(taddr, v);
+        tc::tmem_ld_wait();
+        f(col0, v, buf[sb & 1]);
+    }
 }
 
 // ---- packing ---------------------------------------------------------------------------------------

@@ -15,7 +15,9 @@
 namespace hn {
 namespace chain {
 
-constexpr int DW_THREADS = 288;          // 8 staging / epilogue warps + 1 MMA warp
+constexpr int DW_SWARPS = 16;            // staging / epilogue warps
+constexpr int DW_THREADS = DW_SWARPS * 32 + 32;   // + 1 MMA warp
+constexpr int DW_CPW = 32 / DW_SWARPS;   // 8-feature chunks per warp and operand
 constexpr int DW_KP = 32;                // points per stage
 constexpr int DW_OPER_BYTES = 256 * DW_KP * 2;        // one bf16 matrix of a stage: 16 KB
 constexpr int DW_STAGE_BYTES = 4 * DW_OPER_BYTES;     // P_hi, P_lo, Q_hi, Q_lo
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 32) {
         for (int s = 0; s < DW_STAGES; ++s) {
-            tc::mbar_init(&full[s], 256);
+            tc::mbar_init(&full[s], DW_SWARPS * 32);
             tc::mbar_init(&empty[s], 1);
         }
         tc::mbar_init(&done, 1);
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
     tc::tc_fence_after_sync();
     const uint32_t tmem = tmem_base_s;
 
-    if (warp == 8) {
+    if (warp == DW_SWARPS) {
         // ---- MMA issuer ---------------------------------------------------------------------------
         if (lane == 0 && n_iters > 0) {
             const uint32_t idesc = make_idesc_mn(128, (uint32_t)job.n_mma);
@@ -134,9 +136,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
         }
     } else {
         // ---- staging: HBM fp32 -> bf16 hi/lo MN-major tiles; lane = point, warp w owns feature chunks w, w+8, ... --
-        float bsum[4][8];
+        float bsum[DW_CPW][8];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < DW_CPW; ++a)
 #pragma unroll
             for (int i = 0; i < 8; ++i) bsum[a][i] = 0.0f;
         uint32_t stage = 0, phase = 0;
@@ -145,18 +147,18 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
             for (int sub = 0; sub < TILE_M / DW_KP; ++sub) {
                 const int64_t pnt = (int64_t)tile * TILE_M + sub * DW_KP + lane;
                 for (int pair = 0; pair < job.n_pairs; ++pair, ++it) {
-                    float vp[4][8], vq[4][8];
+                    float vp[DW_CPW][8], vq[DW_CPW][8];
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        load8(job.P[pair], pnt, p.n, warp + 8 * a, vp[a]);
-                        load8(job.Q[pair], pnt, p.n, warp + 8 * a, vq[a]);
+                    for (int a = 0; a < DW_CPW; ++a) {
+                        load8(job.P[pair], pnt, p.n, warp + DW_SWARPS * a, vp[a]);
+                        load8(job.Q[pair], pnt, p.n, warp + DW_SWARPS * a, vq[a]);
                     }
                     tc::mbar_wait(&empty[stage], phase ^ 1u);
                     uint8_t* base = smem + stage * DW_STAGE_BYTES;
 #pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        store8_mn(base, base + DW_OPER_BYTES, lane, warp + 8 * a, vp[a]);
-                        store8_mn(base + 2 * DW_OPER_BYTES, base + 3 * DW_OPER_BYTES, lane, warp + 8 * a, vq[a]);
+                    for (int a = 0; a < DW_CPW; ++a) {
+                        store8_mn(base, base + DW_OPER_BYTES, lane, warp + DW_SWARPS * a, vp[a]);
+                        store8_mn(base + 2 * DW_OPER_BYTES, base + 3 * DW_OPER_BYTES, lane, warp + DW_SWARPS * a, vq[a]);
                         if (pair == 0) {
 #pragma unroll
                             for (int i = 0; i < 8; ++i) bsum[a][i] += vp[a][i];
@@ -170,25 +172,26 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
         }
         if (job.db) {
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < DW_CPW; ++a)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float s = warp_sum(bsum[a][i]);
-                    const int c = (warp + 8 * a) * 8 + i;
+                    const int c = (warp + DW_SWARPS * a) * 8 + i;
                     if (lane == 0 && c < job.P[0].cols && s != 0.0f) atomicAdd(job.db + c, s * job.db_scale);
                 }
         }
         // ---- epilogue: partial sums -> workspace ----------------------------------------------------------
         float* part = p.part + ((size_t)j * DW_SPLITS + split) * 65536;
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, cgrp = warp >> 2;
+        constexpr int CW = 256 / (DW_SWARPS / 4);       // accumulator columns per warp
         if (n_iters > 0) {
             tc::mbar_wait(&done, 0);
             tc::tc_fence_after_sync();
         }
         for (int mc = 0; mc < 2; ++mc) {
             const int row = mc * 128 + q * 32 + lane;
-            for (int blk = 0; blk < 4; ++blk) {
-                const int col0 = half * 128 + blk * 32;
+            for (int blk = 0; blk < CW / 32; ++blk) {
+                const int col0 = cgrp * CW + blk * 32;
                 float v[32];
                 if (n_iters > 0 && col0 < job.n_mma) {
                     acc_load32(tmem + (uint32_t)mc * 256, q * 32, col0, v);

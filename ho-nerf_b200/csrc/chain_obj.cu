@@ -197,6 +197,7 @@ struct FwdParams {
     const float* bias[9];
     const float* w_out0;
     int n_tiles;
+    int stagger;
     long long* prof;
 };
 
@@ -218,6 +219,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
         epi_coords(row, cg);
         const uint32_t tmem = bar.tmem_base;
         uint32_t acc_par = 0;
+        stagger_start(p.stagger, 4);
         for (int t = 0; t < n_my_tiles; ++t) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t gp = tile * TILE_M + row;
@@ -312,21 +314,18 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                     }
                 }
             }
+            prefetch_tile(p.H[6] + tile * TILE_FLOATS, tile * TILE_M < p.n);
             epi_publish_a(&bar);
             // ---- normal sweep: D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1 ------------------------------
             for (int l = 7; l >= 1; --l) {
-                epi_wait_acc(&bar, acc_par);
+                if (l >= 2) prefetch_tile(p.H[l - 2] + tile * TILE_FLOATS);      // for the next epilogue
                 const float* __restrict__ ht = p.H[l - 1] + tile * TILE_FLOATS;
                 float* __restrict__ dt = p.D[l - 1] + tile * TILE_FLOATS;
+                epi_stream<1, 8>(&bar, acc_par, tmem, row, cg, live, true, ht, ht, [&](int col0, float* v, float4 (*aux)[2]) {
 #pragma unroll
-                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
-                    const int col0 = cg * EPI_COLS + blk * 32;
-                    float v[32];
-                    acc_load32(tmem, row, col0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (live) h = ld4(ht + toff(row, col0 + j));
+                    for (int q = 0; q < 2; ++q) {
+                        const int j = q * 4;
+                        const float4 h = aux[0][q];
                         float d[4] = {v[j] * sprime_fast(h.x), v[j + 1] * sprime_fast(h.y), v[j + 2] * sprime_fast(h.z),
                                       v[j + 3] * sprime_fast(h.w)};
                         if (l == 4 && col0 + j + 3 > 192) {
@@ -343,9 +342,8 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                         v[j] = d[0]; v[j + 1] = d[1]; v[j + 2] = d[2]; v[j + 3] = d[3];
                         if (live) st4(dt + toff(row, col0 + j), make_float4(d[0], d[1], d[2], d[3]));
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
-                }
+                    a_store8(smem, row, col0, v);
+                });
                 epi_publish_a(&bar);
             }
             // ---- encoding layer: eb = D_0 W_0 + (skip part); normal = J_e^T eb ----------------------------
@@ -411,6 +409,7 @@ struct BwdParams {
     const uint8_t* chain;
     const float* w_out0;
     int n_tiles;
+    int stagger;
     long long* prof;
 };
 
@@ -430,6 +429,7 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
         epi_coords(row, cg);
         const uint32_t tmem = bar.tmem_base;
         uint32_t acc_par = 0;
+        stagger_start(p.stagger, 4);
         for (int t = 0; t < n_my_tiles; ++t) {
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t gp = tile * TILE_M + row;
@@ -465,45 +465,43 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                 }
             };
             write_ue(0, p.UE + gp * 64, false);
+            prefetch_tile(p.H[0] + tile * TILE_FLOATS);
+            prefetch_tile(p.D[0] + tile * TILE_FLOATS);
             epi_publish_a(&bar);
             // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l -----------
             for (int l = 0; l < 8; ++l) {
-                epi_wait_acc(&bar, acc_par);
+                if (l < 7) {
+                    prefetch_tile(p.H[l + 1] + tile * TILE_FLOATS);
+                    prefetch_tile(p.D[l + 1] + tile * TILE_FLOATS);
+                } else {
+                    prefetch_tile(p.X[7] + tile * TILE_FLOATS);      // H[7] was just read
+                }
                 const float* __restrict__ ht = p.H[l] + tile * TILE_FLOATS;
                 const float* __restrict__ dt = p.D[l] + tile * TILE_FLOATS;
                 float* __restrict__ ut = p.U[l] + tile * TILE_FLOATS;
                 float* __restrict__ xt = p.X[l] + tile * TILE_FLOATS;
                 const bool skip_tail = l == 3 && cg == EPI_CGROUPS - 1;
-                if (!skip_tail) {
+                epi_stream<2, 8>(&bar, acc_par, tmem, row, cg, live, !skip_tail, ht, dt, [&](int col0, float* v, float4 (*aux)[2]) {
 #pragma unroll
-                    for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
-                        const int col0 = cg * EPI_COLS + blk * 32;
-                        float v[32];
-                        acc_load32(tmem, row, col0, v);
+                    for (int q = 0; q < 2; ++q) {
+                        const int j = q * 4;
+                        const float4 h = aux[0][q], d = aux[1][q];
+                        const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {d.x, d.y, d.z, d.w};
+                        float xx[4];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            float4 h = make_float4(0.f, 0.f, 0.f, 0.f), d = h;
-                            if (live) { h = ld4(ht + toff(row, col0 + j)); d = ld4(dt + toff(row, col0 + j)); }
-                            const float hh[4] = {h.x, h.y, h.z, h.w}, dd[4] = {d.x, d.y, d.z, d.w};
-                            float xx[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float q = v[j + i];
-                                const float em = __expf(-100.0f * hh[i]);       // 1 - s'
-                                v[j + i] = (1.0f - em) * q;
-                                xx[i] = 100.0f * em * dd[i] * q;
-                            }
-                            if (live) {
-                                st4(ut + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-                                st4(xt + toff(row, col0 + j), make_float4(xx[0], xx[1], xx[2], xx[3]));
-                            }
+                        for (int i = 0; i < 4; ++i) {
+                            const float qv = v[j + i];
+                            const float em = __expf(-100.0f * hh[i]);       // 1 - s'
+                            v[j + i] = (1.0f - em) * qv;
+                            xx[i] = 100.0f * em * dd[i] * qv;
                         }
-                        if (l < 7) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                        if (live) {
+                            st4(ut + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                            st4(xt + toff(row, col0 + j), make_float4(xx[0], xx[1], xx[2], xx[3]));
                         }
                     }
-                }
+                    if (l < 7) a_store8(smem, row, col0, v);
+                });
                 if (l == 3) {
                     if (cg == EPI_CGROUPS - 1) {
                         float v[32];
@@ -538,19 +536,18 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
             // ---- reverse sweep: dz_{l-1} = s'(h_{l-1}) (dz_l W_l) + X_{l-1}, l = 8..1 ------------------------
             const float gs = (live && p.d_sdf) ? p.d_sdf[gp] * p.inv_scale : 0.0f;
             for (int l = 8; l >= 1; --l) {
-                epi_wait_acc(&bar, acc_par);
+                if (l >= 2) {
+                    prefetch_tile(p.H[l - 2] + tile * TILE_FLOATS);
+                    prefetch_tile(p.X[l - 2] + tile * TILE_FLOATS);
+                }
                 const float* __restrict__ ht = p.H[l - 1] + tile * TILE_FLOATS;
                 const float* __restrict__ xt = p.X[l - 1] + tile * TILE_FLOATS;
                 float* __restrict__ zt = p.DZ[l - 1] + tile * TILE_FLOATS;
+                epi_stream<2, 8>(&bar, acc_par, tmem, row, cg, live, true, ht, xt, [&](int col0, float* v, float4 (*aux)[2]) {
 #pragma unroll
-                for (int blk = 0; blk < EPI_COLS / 32; ++blk) {
-                    const int col0 = cg * EPI_COLS + blk * 32;
-                    float v[32];
-                    acc_load32(tmem, row, col0, v);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f), xq = h;
-                        if (live) { h = ld4(ht + toff(row, col0 + j)); xq = ld4(xt + toff(row, col0 + j)); }
+                    for (int q = 0; q < 2; ++q) {
+                        const int j = q * 4;
+                        const float4 h = aux[0][q], xq = aux[1][q];
                         float da[4] = {v[j], v[j + 1], v[j + 2], v[j + 3]};
                         if (l == 8) {
                             const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
@@ -571,9 +568,8 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                         v[j] = dz[0]; v[j + 1] = dz[1]; v[j + 2] = dz[2]; v[j + 3] = dz[3];
                         if (live) st4(zt + toff(row, col0 + j), make_float4(dz[0], dz[1], dz[2], dz[3]));
                     }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
-                }
+                    a_store8(smem, row, col0, v);
+                });
                 epi_publish_a(&bar);
             }
             // ---- encoding layer: de = dz_0 W_0 + (skip part); d_x = J_e^T de + Hessian term ---------------------
@@ -621,6 +617,7 @@ static int check_chain_mlp(const hn_mlp_t* m) {
 }
 
 static long long* g_prof = nullptr;   // set by hn_chain_set_prof (diagnostics)
+static int g_stagger_fwd = 5000, g_stagger_bwd = 8000;   // cycles per stagger slot (hn_chain_set_stagger)
 
 int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s) {
     HN_PROPAGATE(check_chain_mlp(m));
@@ -673,6 +670,7 @@ int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
     p.w_out0 = m->W[8];
     p.n_tiles = (int)ceil_div(n, TILE_M);
     p.prof = g_prof;
+    p.stagger = g_stagger_fwd;
     Program prog = {};
     int k = 0;
     for (int l = 0; l < 9; ++l, ++k) {           // value trunk + feature head: a @ W_l^T
@@ -731,6 +729,7 @@ int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     p.w_out0 = m->W[8];
     p.n_tiles = (int)ceil_div(n, TILE_M);
     p.prof = g_prof;
+    p.stagger = g_stagger_bwd;
     Program prog = {};
     int k = 0;
     for (int l = 0; l < 8; ++l, ++k) {           // tangent sweep: u @ W_l^T
@@ -861,6 +860,12 @@ int64_t stash_floats(int64_t n) { return round_up(n, TILE_M) * (64 + 16 * 256 + 
 using namespace hn;
 
 extern "C" {
+
+int hn_chain_set_stagger(int fwd_cycles, int bwd_cycles) {
+    chain::g_stagger_fwd = fwd_cycles;
+    chain::g_stagger_bwd = bwd_cycles;
+    return HN_OK;
+}
 
 int hn_chain_set_prof(void* buf) {
     chain::g_prof = reinterpret_cast<long long*>(buf);

@@ -122,6 +122,9 @@ HN_API int hn_sdf_obj_chain_pack(const hn_mlp_t* mlp, void* chain, int64_t chain
  * {MMA warp waiting for activations, waiting for weights, total, epilogue waiting for the
  * accumulator}; NULL disables. */
 HN_API int hn_chain_set_prof(void* buf);
+/* Tuning: CTA i of the forward / backward chain kernels starts (i % 4) * cycles late, which de-phases the
+ * HBM-heavy epilogues of different SMs (0 = all CTAs in lock step). */
+HN_API int hn_chain_set_stagger(int fwd_cycles, int bwd_cycles);
 
 /* sdf[n] = SDFNetwork_OBJ.sdf(pts) (utils/fields.py:330-331); no stash, no normal. */
 HN_API int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n_pts, float inv_scale,

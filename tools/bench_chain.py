@@ -82,8 +82,54 @@ def fwdbwd_bench():
         print("sdf fwd+bwd (2nd order, dW) n=%d %-10s %.3f ms  %.1f algorithmic TFLOP/s" % (n, prec, ms, n * 6 * F_O / ms / 1e9))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     prof()
     fwd_bench()
     fwdbwd_bench()
     main()
+
+
+def prof_fwd_bwd():
+    import ctypes
+    sdf, col, dev, _, _ = obj_modules(requires_grad=True)
+    n = 65536
+    x = (0.45 * torch.randn(n, 3)).cuda().requires_grad_(True)
+    gs, gf, gn = torch.randn(n, 1).cuda(), torch.randn(n, 256).cuda(), torch.randn(n, 3).cuda()
+    p = H.ops._PRECISIONS["tc_bf16x3"]
+    buf = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+    for which in ("fwd", "bwd"):
+        s, f, nn = H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p)
+        torch.autograd.backward([s, f, nn], [gs, gf, gn])
+        torch.cuda.synchronize()
+        buf.zero_()
+        if which == "fwd":
+            H._lib.lib.hn_chain_set_prof(ctypes.c_void_p(buf.data_ptr()))
+            s, f, nn = H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p)
+            torch.cuda.synchronize()
+            H._lib.lib.hn_chain_set_prof(None)
+            torch.autograd.backward([s, f, nn], [gs, gf, gn])
+        else:
+            s, f, nn = H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p)
+            torch.cuda.synchronize()
+            H._lib.lib.hn_chain_set_prof(ctypes.c_void_p(buf.data_ptr()))
+            torch.autograd.backward([s, f, nn], [gs, gf, gn])
+            torch.cuda.synchronize()
+            H._lib.lib.hn_chain_set_prof(None)
+        b = buf.reshape(148, 4).double().cpu()
+        tiles = torch.tensor([4.0 if i < 68 else 3.0 for i in range(148)], dtype=torch.float64)
+        steps = tiles * 17
+        print("%s chain kernel, per layer-tile cycles (mean over CTAs): total %.0f  MMA-warp waits for epilogue %.0f  for weights %.0f  issue+rest %.0f; max CTA total %.0f cycles"
+              % (which, (b[:, 2] / steps).mean(), (b[:, 0] / steps).mean(), (b[:, 1] / steps).mean(),
+                 ((b[:, 2] - b[:, 0] - b[:, 1]) / steps).mean(), b[:, 2].max()))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "prof2":
+    prof_fwd_bwd()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "stagger":
+    for fc, bc in ((0, 0), (5000, 8000), (3000, 5000), (8000, 12000), (12000, 18000)):
+        H._lib.lib.hn_chain_set_stagger(fc, bc)
+        print("stagger", fc, bc)
+        fwd_bench()
+        fwdbwd_bench()

@@ -1,0 +1,23 @@
+"""Short workload for `ncu --set full`: a few object-SDF forward + second-order backward calls (65 536 points)
+and colour forward/backward through the chain kernels."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+import honerf_b200 as H  # noqa: E402
+from gpu_util import obj_modules  # noqa: E402
+
+sdf, col, dev, _, _ = obj_modules(requires_grad=True)
+n = 65536
+x = (0.45 * torch.randn(n, 3)).cuda().requires_grad_(True)
+d = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1).cuda()
+p = H.ops._PRECISIONS["tc_bf16x3"]
+for _ in range(3):
+    s, f, nn = H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p)
+    rgb = H.ops.color_obj(col.packed(), x, d, f, nn, precision=p)
+    (rgb.sum() + s.sum() + (nn * nn).sum()).backward()
+torch.cuda.synchronize()
