@@ -181,7 +181,7 @@ def build_gpu_model(device, precision):
         m.to(device)
     r = H.NeuSRenderer(sdf, var, col, "obj", **ref_conf.RENDERER_CONF)
     params = list(sdf.parameters()) + list(var.parameters()) + list(col.parameters())
-    opt = torch.optim.Adam(params, lr=1e-4)
+    opt = torch.optim.Adam(params, lr=1e-4, capturable=True)      # capturable: the step can live in a CUDA graph
     return H, r, params, opt
 
 
@@ -239,14 +239,51 @@ def run_gpu_arm(args):
         return ms
 
     # ---- device-resident number -------------------------------------------------------------
-    for _ in range(args.warmup):
-        train_step(dev_batch)
+    # The whole step (render, loss, backward, gradient all-reduce, Adam) is a fixed launch sequence: capture it once
+    # in a CUDA graph and replay it, as a training loop would.  Everything before the capture runs on the capture's
+    # side stream (autograd's AccumulateGrad nodes remember the stream they were created on).
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    static = {k: v.clone() for k, v in dev_batch.items()}
+    with torch.cuda.stream(side):
+        for _ in range(args.warmup):
+            train_step(static)
+        torch.cuda.synchronize()
+        l0 = H.launch_count()
+        train_step(static)
+        launches_per_step = H.launch_count() - l0
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph, loss_static = None, None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss_static = train_step(static)
+            graph.replay()
+            torch.cuda.synchronize()
+            if not torch.isfinite(loss_static).all():
+                raise RuntimeError("non-finite loss from the captured step")
+        except Exception as e:      # noqa: BLE001
+            # a failed capture leaves the CUDA RNG registered to a dead graph: start over without graphs
+            sys.stderr.write("bench.py: CUDA graph capture failed (%s: %s); re-running with --no-graph\n"
+                             % (type(e).__name__, str(e)[:300]))
+            sys.stderr.flush()
+            os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+
+    def resident_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            train_step(dev_batch)
+
+    for _ in range(2):
+        resident_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = H.launch_count()
-    ms = timed(lambda: train_step(dev_batch), args.steps)
-    launches = H.launch_count() - l0
+    ms = timed(resident_step, args.steps)
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = world * n_rays / (ms_per_step * 1e-3)
@@ -257,9 +294,15 @@ def run_gpu_arm(args):
     h2d = sum(pinned[k].numel() * 4 for k in keys)
 
     def e2e_step():
-        b = {k: pinned[k].to(device, non_blocking=True) for k in keys}
-        loss = train_step(b)
-        loss_host.copy_(loss.detach(), non_blocking=False)
+        if graph is not None:
+            for k in keys:
+                static[k].copy_(pinned[k], non_blocking=True)
+            graph.replay()
+            loss_host.copy_(loss_static.detach(), non_blocking=False)
+        else:
+            b = {k: pinned[k].to(device, non_blocking=True) for k in keys}
+            loss = train_step(b)
+            loss_host.copy_(loss.detach(), non_blocking=False)
 
     for _ in range(2):
         e2e_step()
@@ -271,6 +314,21 @@ def run_gpu_arm(args):
     if rank == 0:
         roof = mlp_roofline(H, lambda: train_step(dev_batch), n_rays)
         comp = compositor_roofline(H, device)
+    large = None
+    if rank == 0 and world == 1 and args.large_rays > 0:
+        # informational: the same step on a batch that fills the 148 SMs for many waves (not the headline config)
+        try:
+            hb = synthetic_batch(args.large_rays, seed=99)
+            lb = {k: v.to(device) for k, v in hb.items() if torch.is_tensor(v)}
+            for _ in range(2):
+                train_step(lb)
+            ms_l = timed(lambda: train_step(lb), 3) / 3
+            large = {"rays_per_gpu": args.large_rays, "ms_per_step": ms_l, "value": args.large_rays / (ms_l * 1e-3),
+                     "unit": "rays/s", "note": "eager launches, device-resident inputs"}
+            del lb
+        except Exception as e:      # noqa: BLE001
+            large = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, dt, cores = time_cpu(min(n_rays, 512), 3, 1)
@@ -287,11 +345,12 @@ def run_gpu_arm(args):
             "config": {"workload": "obj-field train step (BASELINE configs[2]): %d rays/GPU x (64+64) samples, "
                                    "masked-L1+BCE+eikonal loss, 2nd-order bwd, Adam" % n_rays,
                        "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
+                       "cuda_graph": graph is not None,
                        "l2": "per-step activation stash (~2 GB at 512 rays) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu,
+            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large,
             "mlp_flops_per_ray": FLOPS_PER_RAY_TRAIN,
         }
         print(json.dumps(line), flush=True)
@@ -390,8 +449,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays", type=int, default=512, help="rays per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="simt_fp32", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
+    ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

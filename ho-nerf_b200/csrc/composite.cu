@@ -2,6 +2,8 @@
 // replaces utils/renderer.py:144-169 (render_core) and the autograd graph behind it.
 // One warp per ray; every per-sample buffer is read/written once, coalesced along the ray.
 // Algorithmic traffic per sample: fwd 40 B, fwd+bwd 104 B.
+#include <initializer_list>
+
 #include "common.cuh"
 
 namespace hn {
@@ -204,6 +206,193 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) neus_composite_bwd_kernel(
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Vectorised variants for n = 32 * S samples per ray (S = 4, 6, 8: the 128-sample render_core and the
+// 192-sample fitting renderers): a lane owns S CONSECUTIVE samples, so every per-sample buffer is moved with
+// 8/16-byte vector accesses (a warp instruction covers one contiguous segment of the ray), the transmittance
+// is a serial product inside the lane plus one warp scan of the lane totals, and nothing is re-read.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, float* out) {
+    if constexpr (K % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < K; i += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(p + i);
+            out[i] = v.x; out[i + 1] = v.y; out[i + 2] = v.z; out[i + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; i += 2) {
+            const float2 v = *reinterpret_cast<const float2*>(p + i);
+            out[i] = v.x; out[i + 1] = v.y;
+        }
+    }
+}
+template <int K>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, const float* in) {
+    if constexpr (K % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < K; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(in[i], in[i + 1], in[i + 2], in[i + 3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; i += 2) *reinterpret_cast<float2*>(p + i) = make_float2(in[i], in[i + 1]);
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(CMP_WARPS * 32) neus_composite_fwd_vec_kernel(
+    const float* __restrict__ sdf, const float* __restrict__ normal, const float* __restrict__ rgb,
+    const float* __restrict__ dists, const float* __restrict__ rays_d, const float* __restrict__ variance,
+    int64_t n_rays, int seed_c0, float* __restrict__ weights, float* __restrict__ cdf,
+    float* __restrict__ alpha_out, float* __restrict__ color, float* __restrict__ wsum_out,
+    float* __restrict__ wmax_out, float* __restrict__ eik_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * CMP_WARPS + (threadIdx.x >> 5);
+    if (ray >= n_rays) return;
+    const float inv_s = inv_s_of(variance);
+    const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    const int64_t s0 = ray * (32 * S) + lane * S;
+    float vs[S], vd[S], vn[3 * S], vc[3 * S];
+    load_vec<S>(sdf + s0, vs);
+    load_vec<S>(dists + s0, vd);
+    load_vec<3 * S>(normal + s0 * 3, vn);
+    load_vec<3 * S>(rgb + s0 * 3, vc);
+    float al[S], cc[S], tl[S];
+    float prod = 1.0f, ek = 0.0f;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const SampleEval e = eval_sample(vs[i], vn[3 * i], vn[3 * i + 1], vn[3 * i + 2], dx, dy, dz, vd[i], inv_s);
+        al[i] = e.alpha; cc[i] = e.c;
+        tl[i] = prod;                        // product over the lane's earlier samples
+        prod *= 1.0f - e.alpha + 1e-7f;
+        const float nn = sqrtf(vn[3 * i] * vn[3 * i] + vn[3 * i + 1] * vn[3 * i + 1] + vn[3 * i + 2] * vn[3 * i + 2]) - 1.0f;
+        ek += nn * nn;
+    }
+    float tot;
+    float T = warp_excl_prod(prod, lane, &tot);
+    if (seed_c0) T *= __shfl_sync(0xffffffffu, cc[0], 0);
+    float w[S], cr = 0.f, cg = 0.f, cb = 0.f, ws = 0.f, wm = 0.f;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        w[i] = al[i] * (T * tl[i]);
+        cr += w[i] * vc[3 * i]; cg += w[i] * vc[3 * i + 1]; cb += w[i] * vc[3 * i + 2];
+        ws += w[i];
+        wm = fmaxf(wm, w[i]);
+    }
+    store_vec<S>(weights + s0, w);
+    store_vec<S>(cdf + s0, cc);
+    if (alpha_out) store_vec<S>(alpha_out + s0, al);
+    cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb);
+    ws = warp_sum(ws); ek = warp_sum(ek); wm = warp_max(wm);
+    if (lane == 0) {
+        color[ray * 3] = cr; color[ray * 3 + 1] = cg; color[ray * 3 + 2] = cb;
+        wsum_out[ray] = ws;
+        wmax_out[ray] = wm;
+        eik_out[ray] = ek;
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(CMP_WARPS * 32) neus_composite_bwd_vec_kernel(
+    const float* __restrict__ sdf, const float* __restrict__ normal, const float* __restrict__ rgb,
+    const float* __restrict__ dists, const float* __restrict__ rays_d, const float* __restrict__ variance,
+    int64_t n_rays, int seed_c0, const float* __restrict__ d_color, const float* __restrict__ d_wsum,
+    const float* __restrict__ d_weights, const float* __restrict__ d_eik, float* __restrict__ d_sdf,
+    float* __restrict__ d_normal, float* __restrict__ d_rgb, float* __restrict__ d_rays_d,
+    float* __restrict__ d_variance) {
+    const int lane = threadIdx.x & 31;
+    const int64_t ray = (int64_t)blockIdx.x * CMP_WARPS + (threadIdx.x >> 5);
+    if (ray >= n_rays) return;
+    const float inv_s_raw = expf(variance[0] * 10.0f);
+    const float inv_s = fminf(fmaxf(inv_s_raw, 1e-6f), 1e6f);
+    const bool s_live = inv_s_raw >= 1e-6f && inv_s_raw <= 1e6f;
+    const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    const float gcr = d_color[ray * 3], gcg = d_color[ray * 3 + 1], gcb = d_color[ray * 3 + 2];
+    const float gws = d_wsum ? d_wsum[ray] : 0.0f;
+    const float gek = d_eik ? d_eik[ray] : 0.0f;
+    const int64_t s0 = ray * (32 * S) + lane * S;
+    float vs[S], vd[S], vn[3 * S], vc[3 * S], gwt[S];
+    load_vec<S>(sdf + s0, vs);
+    load_vec<S>(dists + s0, vd);
+    load_vec<3 * S>(normal + s0 * 3, vn);
+    load_vec<3 * S>(rgb + s0 * 3, vc);
+    if (d_weights) {
+        load_vec<S>(d_weights + s0, gwt);
+    } else {
+#pragma unroll
+        for (int i = 0; i < S; ++i) gwt[i] = 0.0f;
+    }
+    SampleEval ev[S];
+    float tl[S];
+    float prod = 1.0f;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        ev[i] = eval_sample(vs[i], vn[3 * i], vn[3 * i + 1], vn[3 * i + 2], dx, dy, dz, vd[i], inv_s);
+        tl[i] = prod;
+        prod *= 1.0f - ev[i].alpha + 1e-7f;
+    }
+    float tot;
+    float T = warp_excl_prod(prod, lane, &tot);
+    const float c0 = __shfl_sync(0xffffffffu, ev[0].c, 0);
+    if (seed_c0) T *= c0;
+    // g_i = dL/dw_i ; suffix sums of g_i w_i: inside the lane, then across lanes
+    float g[S], w[S], suf[S], run = 0.0f;
+#pragma unroll
+    for (int i = S - 1; i >= 0; --i) {
+        w[i] = ev[i].alpha * (T * tl[i]);
+        g[i] = gcr * vc[3 * i] + gcg * vc[3 * i + 1] + gcb * vc[3 * i + 2] + gws + gwt[i];
+        run += g[i] * w[i];
+        suf[i] = run;                        // sum over this lane's samples >= i
+    }
+    float total;
+    const float later = warp_suffix_sum(run, lane, &total) - run;     // lanes > this one
+    float o_sdf[S], o_nrm[3 * S], o_rgb[3 * S];
+    float drx = 0.f, dry = 0.f, drz = 0.f, dinv = 0.f;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        const SampleEval& e = ev[i];
+        const float Si = suf[i] + later;                 // sum over all samples k >= this one
+        const float f = 1.0f - e.alpha + 1e-7f;
+        const float dalpha = g[i] * (T * tl[i]) - (Si - g[i] * w[i]) / f;
+        const float dar = (e.alpha_raw >= 0.0f && e.alpha_raw <= 1.0f) ? dalpha : 0.0f;
+        const float den = e.c + 1e-5f;
+        const float num = e.c - e.nx + 1e-5f;
+        float dc = dar * (1.0f / den - num / (den * den));
+        const float dnx = -dar / den;
+        if (seed_c0 && lane == 0 && i == 0) dc += Si / c0;
+        const float dap = dc * e.c * (1.0f - e.c);
+        const float dan = dnx * e.nx * (1.0f - e.nx);
+        dinv += dap * e.est_prev + dan * e.est_next;
+        const float dprev = dap * inv_s, dnext = dan * inv_s;
+        o_sdf[i] = dprev + dnext;
+        const float dic = (dnext - dprev) * vd[i] * 0.5f;
+        const float dtc = e.true_cos < 0.0f ? dic : 0.0f;
+        const float nxv = vn[3 * i], nyv = vn[3 * i + 1], nzv = vn[3 * i + 2];
+        const float nrm = sqrtf(nxv * nxv + nyv * nyv + nzv * nzv);
+        const float ke = nrm > 0.0f ? gek * 2.0f * (nrm - 1.0f) / nrm : 0.0f;
+        o_nrm[3 * i] = dtc * dx + ke * nxv;
+        o_nrm[3 * i + 1] = dtc * dy + ke * nyv;
+        o_nrm[3 * i + 2] = dtc * dz + ke * nzv;
+        drx += dtc * nxv; dry += dtc * nyv; drz += dtc * nzv;
+        o_rgb[3 * i] = w[i] * gcr; o_rgb[3 * i + 1] = w[i] * gcg; o_rgb[3 * i + 2] = w[i] * gcb;
+    }
+    store_vec<S>(d_sdf + s0, o_sdf);
+    store_vec<3 * S>(d_normal + s0 * 3, o_nrm);
+    store_vec<3 * S>(d_rgb + s0 * 3, o_rgb);
+    drx = warp_sum(drx); dry = warp_sum(dry); drz = warp_sum(drz); dinv = warp_sum(dinv);
+    if (lane == 0) {
+        if (d_rays_d) { d_rays_d[ray * 3] = drx; d_rays_d[ray * 3 + 1] = dry; d_rays_d[ray * 3 + 2] = drz; }
+        if (d_variance && s_live) atomicAdd(d_variance, dinv * 10.0f * inv_s);
+    }
+}
+
+static inline bool vec_ok(int n, std::initializer_list<const void*> ptrs) {
+    if (n != 128 && n != 192 && n != 256) return false;
+    for (const void* p : ptrs)
+        if (p && (reinterpret_cast<uintptr_t>(p) & 15) != 0) return false;
+    return true;
+}
+
 }  // namespace hn
 
 using namespace hn;
@@ -218,9 +407,20 @@ int hn_neus_composite_fwd(const float* sdf, const float* normal, const float* rg
     if (n_rays == 0) return HN_OK;
     HN_REQUIRE(sdf && normal && rgb && dists && rays_d && variance && weights && cdf && color && weight_sum &&
                    weight_max && eik, "hn_neus_composite_fwd: null pointer");
-    neus_composite_fwd_kernel<<<(unsigned)ceil_div(n_rays, CMP_WARPS), CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        sdf, normal, rgb, dists, rays_d, variance, n_rays, n, seed_with_c0, weights, cdf, alpha, color,
-        weight_sum, weight_max, eik);
+    const unsigned grid = (unsigned)ceil_div(n_rays, CMP_WARPS);
+    cudaStream_t st = (cudaStream_t)stream;
+#define HN_FWD_VEC(S)                                                                                                  \
+    neus_composite_fwd_vec_kernel<S><<<grid, CMP_WARPS * 32, 0, st>>>(sdf, normal, rgb, dists, rays_d, variance, n_rays, \
+                                                                      seed_with_c0, weights, cdf, alpha, color,        \
+                                                                      weight_sum, weight_max, eik)
+    if (vec_ok(n, {sdf, normal, rgb, dists, weights, cdf, alpha})) {
+        if (n == 128) HN_FWD_VEC(4); else if (n == 192) HN_FWD_VEC(6); else HN_FWD_VEC(8);
+    } else {
+        neus_composite_fwd_kernel<<<grid, CMP_WARPS * 32, 0, st>>>(sdf, normal, rgb, dists, rays_d, variance, n_rays, n,
+                                                                   seed_with_c0, weights, cdf, alpha, color, weight_sum,
+                                                                   weight_max, eik);
+    }
+#undef HN_FWD_VEC
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;
@@ -239,9 +439,20 @@ int hn_neus_composite_bwd(const float* sdf, const float* normal, const float* rg
     if (n_rays == 0) return HN_OK;
     HN_REQUIRE(sdf && normal && rgb && dists && rays_d && variance && weights && d_color && d_sdf && d_normal &&
                    d_rgb, "hn_neus_composite_bwd: null pointer");
-    neus_composite_bwd_kernel<<<(unsigned)ceil_div(n_rays, CMP_WARPS), CMP_WARPS * 32, 0, (cudaStream_t)stream>>>(
-        sdf, normal, rgb, dists, rays_d, variance, weights, n_rays, n, seed_with_c0, d_color, d_weight_sum,
-        d_weights, d_eik, d_sdf, d_normal, d_rgb, d_rays_d, d_variance);
+    const unsigned grid = (unsigned)ceil_div(n_rays, CMP_WARPS);
+    cudaStream_t st = (cudaStream_t)stream;
+#define HN_BWD_VEC(S)                                                                                                  \
+    neus_composite_bwd_vec_kernel<S><<<grid, CMP_WARPS * 32, 0, st>>>(sdf, normal, rgb, dists, rays_d, variance, n_rays, \
+                                                                      seed_with_c0, d_color, d_weight_sum, d_weights,  \
+                                                                      d_eik, d_sdf, d_normal, d_rgb, d_rays_d, d_variance)
+    if (vec_ok(n, {sdf, normal, rgb, dists, d_weights, d_sdf, d_normal, d_rgb})) {
+        if (n == 128) HN_BWD_VEC(4); else if (n == 192) HN_BWD_VEC(6); else HN_BWD_VEC(8);
+    } else {
+        neus_composite_bwd_kernel<<<grid, CMP_WARPS * 32, 0, st>>>(sdf, normal, rgb, dists, rays_d, variance, weights, n_rays,
+                                                                   n, seed_with_c0, d_color, d_weight_sum, d_weights, d_eik,
+                                                                   d_sdf, d_normal, d_rgb, d_rays_d, d_variance);
+    }
+#undef HN_BWD_VEC
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -8,10 +8,17 @@ import torch
 from . import ops
 
 
+_z_cache = {}
+
+
 def _linspace_z(near, far, n_samples, device):
-    # host-side torch.linspace, as the reference (utils/renderer.py:204-205), then moved to the device
-    z = torch.linspace(0.0, 1.0, n_samples)
-    return (near + (far - near) * z[None, :]).to(device)
+    # host-side torch.linspace, as the reference (utils/renderer.py:204-205), then moved to the device; cached so
+    # that a steady-state render issues no host-to-device copy (and can be captured in a CUDA graph)
+    key = (float(near), float(far), int(n_samples), str(device))
+    if key not in _z_cache:
+        z = torch.linspace(0.0, 1.0, n_samples)
+        _z_cache[key] = (near + (far - near) * z[None, :]).to(device)
+    return _z_cache[key]
 
 
 class NeuSRenderer:

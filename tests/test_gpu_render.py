@@ -126,9 +126,10 @@ def _oracle_composite(sdf, nrm, rgb, dists, d, var, seed_c0):
     return color, w, c, w.sum(-1, keepdim=True), w.max(-1, keepdim=True)[0], eik
 
 
-@pytest.mark.parametrize("B,n,seed_c0", [(65, 128, True), (7, 192, False), (3, 33, True), (1, 1, True)])
+@pytest.mark.parametrize("B,n,seed_c0", [(65, 128, True), (7, 192, False), (3, 33, True), (1, 1, True), (5, 256, True),
+                                          (9, 192, True), (4, 128, False)])
 def test_composite_forward_backward_vs_oracle(B, n, seed_c0):
-    """forward <= 2e-6 abs; every input cotangent <= 1e-3 relative vs fp64 autograd."""
+    """forward <= 5e-6 abs (fp32 sums of up to 256 terms ~ 1); every input cotangent <= 1e-3 relative vs fp64 autograd."""
     from honerf_b200 import ops
     ins = _composite_inputs(B, n, 100 + n)
     var = torch.tensor(0.3)
@@ -144,7 +145,7 @@ def test_composite_forward_backward_vs_oracle(B, n, seed_c0):
     vg = var.to(DEV).requires_grad_(True)
     out = ops.neus_composite(gi[0], gi[1], gi[2], gi[3], gi[4], vg, seed_with_c0=seed_c0)
     for a, b, nm in zip(out, ref, ("color", "weights", "cdf", "wsum", "wmax", "eik")):
-        tol = 2e-6 if nm != "eik" else 2e-4
+        tol = 5e-6 if nm != "eik" else 2e-4
         assert max_abs(a, b) < tol, nm
     Lg = (out[0] * gc.to(DEV)).sum() + (out[1] * gw.to(DEV)).sum() + (out[3] * gs.to(DEV)).sum() + (out[5] * ge.to(DEV)).sum()
     Lg.backward()
