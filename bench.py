@@ -329,6 +329,26 @@ def run_gpu_arm(args):
         except Exception as e:      # noqa: BLE001
             large = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
+    grid = None
+    if rank == 0 and world == 1 and args.grid_res > 0:
+        # informational (BASELINE configs[1]): SDFNetwork_OBJ.sdf on the res^3 lattice of extract_geometry
+        try:
+            bmin, bmax = torch.full((3,), -0.2), torch.full((3,), 0.2)
+            renderer.sdf_grid(bmin, bmax, 64)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            u = renderer.sdf_grid(bmin, bmax, args.grid_res)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_g = e0.elapsed_time(e1)
+            npts = args.grid_res ** 3
+            grid = {"resolution": args.grid_res, "ms": ms_g, "points_per_s": npts / (ms_g * 1e-3),
+                    "algorithmic_tflops": npts * F_O / (ms_g * 1e-3) / 1e12, "finite": bool(torch.isfinite(u).all())}
+            del u
+        except Exception as e:      # noqa: BLE001
+            grid = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, dt, cores = time_cpu(min(n_rays, 512), 3, 1)
@@ -350,7 +370,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large,
+            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large, "sdf_grid": grid,
             "mlp_flops_per_ray": FLOPS_PER_RAY_TRAIN,
         }
         print(json.dumps(line), flush=True)
@@ -453,6 +473,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")
+    ap.add_argument("--grid-res", type=int, default=256, help="extra informational SDF-lattice measurement (0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

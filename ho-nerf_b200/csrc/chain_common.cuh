@@ -17,6 +17,7 @@
 // memory, plus whatever the mode streams to / from HBM).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -46,6 +47,9 @@ struct Step {
     uint8_t kblocks;
     uint8_t a_kb0 : 4;
     uint8_t acc_in : 1;      // accumulate onto the previous step's result (a layer whose K is split in two steps)
+    uint8_t f16 : 1;         // A and B are fp16 (hi + lo) pairs instead of bf16 pairs: ~2^-21 instead of ~2^-17
+                             // relative, but fp16 range -- only for the O(1) forward values (value trunk), never
+                             // for cotangents (kind::f16 cannot mix fp16 and bf16 operands in one MMA)
 };
 struct Program {
     int n_steps;
@@ -82,26 +86,49 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     hi = *reinterpret_cast<uint32_t*>(&h);
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
+// fp16 pair: hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split2_lo16(float a, float b, uint32_t& hi, uint32_t& lo) {
+    __half2 h = __floats2half2_rn(a, b);
+    float2 hf = __half22float2(h);
+    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<uint32_t*>(&h);
+    lo = *reinterpret_cast<uint32_t*>(&l);
+}
 // 8 consecutive columns [col, col+8) (col % 8 == 0) of row `row`
+template <bool LO16 = false>
 __device__ __forceinline__ void a_store8(uint8_t* smem, int row, int col, const float* v) {
     uint4 hi, lo;
-    split2(v[0], v[1], hi.x, lo.x);
-    split2(v[2], v[3], hi.y, lo.y);
-    split2(v[4], v[5], hi.z, lo.z);
-    split2(v[6], v[7], hi.w, lo.w);
+    if (LO16) {
+        split2_lo16(v[0], v[1], hi.x, lo.x);
+        split2_lo16(v[2], v[3], hi.y, lo.y);
+        split2_lo16(v[4], v[5], hi.z, lo.z);
+        split2_lo16(v[6], v[7], hi.w, lo.w);
+    } else {
+        split2(v[0], v[1], hi.x, lo.x);
+        split2(v[2], v[3], hi.y, lo.y);
+        split2(v[4], v[5], hi.z, lo.z);
+        split2(v[6], v[7], hi.w, lo.w);
+    }
     uint32_t off = (uint32_t)(col >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)row, (uint32_t)((col & 63) >> 3));
     *reinterpret_cast<uint4*>(smem + off) = hi;
     *reinterpret_cast<uint4*>(smem + A_LO_OFF + off) = lo;
 }
+template <bool LO16 = false>
 __device__ __forceinline__ void a_store1(uint8_t* smem, int row, int col, float v) {
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
-    __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
     uint32_t off = (uint32_t)(col >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)row, (uint32_t)((col & 63) >> 3)) +
                    (uint32_t)(col & 7) * 2u;
-    *reinterpret_cast<__nv_bfloat16*>(smem + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(smem + A_LO_OFF + off) = l;
+    if (LO16) {
+        const __half h = __float2half_rn(v);
+        *reinterpret_cast<__half*>(smem + off) = h;
+        *reinterpret_cast<__half*>(smem + A_LO_OFF + off) = __float2half_rn(v - __half2float(h));
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        *reinterpret_cast<__nv_bfloat16*>(smem + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(smem + A_LO_OFF + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
 }
 // read back 8 consecutive columns as fp32 (hi + lo)
+template <bool LO16 = false>
 __device__ __forceinline__ void a_load8(const uint8_t* smem, int row, int col, float* v) {
     uint32_t off = (uint32_t)(col >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)row, (uint32_t)((col & 63) >> 3));
     uint4 hi = *reinterpret_cast<const uint4*>(smem + off);
@@ -109,8 +136,15 @@ __device__ __forceinline__ void a_load8(const uint8_t* smem, int row, int col, f
     const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
-        v[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+        if (LO16) {
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&l[i]));
+            v[2 * i] = a.x + b.x;
+            v[2 * i + 1] = a.y + b.y;
+        } else {
+            v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+            v[2 * i + 1] = __uint_as_float(h[i] & 0xffff0000u) + __uint_as_float(l[i] & 0xffff0000u);
+        }
     }
 }
 
@@ -179,7 +213,7 @@ __device__ __forceinline__ void mma_loop(const Program& prog, uint8_t* smem, Bar
     for (int t = 0; t < n_my_tiles; ++t) {
         for (int s = 0; s < prog.n_steps; ++s) {
             const Step st = prog.step[s];
-            const uint32_t idesc = tc::make_idesc(tc::FMT_BF16, 128, st.n_mma);
+            const uint32_t idesc = tc::make_idesc(st.f16 ? tc::FMT_F16 : tc::FMT_BF16, 128, st.n_mma);
             tt = clock64();
             tc::mbar_wait(&bar->a_ready, a_par);
             t_a += clock64() - tt;
@@ -312,7 +346,7 @@ struct PackMap {
 };
 inline PackMap pack_map(int row0, int col0) { return PackMap{row0, 1 << 30, 0, col0, 1 << 30, 0}; }
 int launch_pack_b(const float* src, int64_t ld, PackMap map, int rows, int cols, int n_pad, int kblocks,
-                  uint8_t* dst, cudaStream_t stream);
+                  uint8_t* dst, cudaStream_t stream, bool lo16 = false);
 inline int launch_pack_b(const float* src, int64_t ld, int row0, int col0, int rows, int cols, int n_pad, int kblocks,
                          uint8_t* dst, cudaStream_t stream) {
     return launch_pack_b(src, ld, pack_map(row0, col0), rows, cols, n_pad, kblocks, dst, stream);

@@ -19,6 +19,7 @@ namespace chain {
 // which is applied as a rank-one term by the epilogues.
 struct ObjLayout {
     uint32_t nt_off[9], nn_off[9];
+    uint32_t nt16_off[9];         // a @ W_l^T operands again as fp16 (hi + lo) pairs: the forward value trunk
     uint16_t nt_n[9], nn_n[9];
     uint8_t nt_kb[9], nn_kb[9];
     uint32_t total;
@@ -38,6 +39,10 @@ static ObjLayout obj_layout() {
         L.nn_off[l] = off;
         off += b_operand_bytes(L.nn_n[l], L.nn_kb[l]);
     }
+    for (int l = 0; l < 9; ++l) {
+        L.nt16_off[l] = off;
+        off += b_operand_bytes(L.nt_n[l], L.nt_kb[l]);
+    }
     L.total = off;
     return L;
 }
@@ -51,6 +56,7 @@ static ObjLayout obj_layout() {
 // first layer) is zeroed when shift == 0.
 // `g` (may be NULL): fp32 copy for the stash: row-major row pointer (g[j] = e_j) when !g_tiled, else the
 // base of a tiled [128, 256] tile whose columns shift + j receive e_j.
+template <bool LO16 = false>
 __device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, const float x[3], int shift,
                                                float* __restrict__ g = nullptr, bool g_tiled = false) {
     auto gput = [&](int j, float v) {
@@ -59,11 +65,11 @@ __device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, c
     if (cg == 0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            a_store1(smem, row, shift + c, x[c]);
+            a_store1<LO16>(smem, row, shift + c, x[c]);
             gput(c, x[c]);
         }
         if (shift == 0) {
-            a_store1(smem, row, 63, 0.0f);
+            a_store1<LO16>(smem, row, 63, 0.0f);
             gput(63, 0.0f);
         }
     }
@@ -71,8 +77,8 @@ __device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, c
         const int c = idx / 10, k = idx - c * 10;
         float s, co;
         sincosf(x[c] * (float)(1 << k), &s, &co);
-        a_store1(smem, row, shift + 3 + c * 20 + k, s);
-        a_store1(smem, row, shift + 3 + c * 20 + 10 + k, co);
+        a_store1<LO16>(smem, row, shift + 3 + c * 20 + k, s);
+        a_store1<LO16>(smem, row, shift + 3 + c * 20 + 10 + k, co);
         gput(3 + c * 20 + k, s);
         gput(3 + c * 20 + 10 + k, co);
     }
@@ -115,7 +121,7 @@ sdf_only_kernel(const __grid_constant__ SdfOnlyParams p, const __grid_constant__
             const int64_t gp = tile * TILE_M + row;
             float x[3] = {0.f, 0.f, 0.f};
             if (gp < p.n) { x[0] = p.pts[gp * 3]; x[1] = p.pts[gp * 3 + 1]; x[2] = p.pts[gp * 3 + 2]; }
-            write_encoding(smem, row, cg, x, 0);
+            write_encoding<true>(smem, row, cg, x, 0);
             epi_publish_a(&bar);
             float head = 0.0f;
             for (int l = 0; l < 8; ++l) {
@@ -140,7 +146,7 @@ sdf_only_kernel(const __grid_constant__ SdfOnlyParams p, const __grid_constant__
                         }
                         if (l < 7) {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                            for (int j = 0; j < 32; j += 8) a_store8<true>(smem, row, col0 + j, v + j);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -155,9 +161,9 @@ sdf_only_kernel(const __grid_constant__ SdfOnlyParams p, const __grid_constant__
                     if (cg == EPI_CGROUPS - 1) {
                         float v[32];
                         acc_load32(tmem, row, 192, v);
-                        a_store1(smem, row, 192, softplus100_fast(v[0] + __ldg(bias + 192)));
+                        a_store1<true>(smem, row, 192, softplus100_fast(v[0] + __ldg(bias + 192)));
                     }
-                    write_encoding(smem, row, cg, x, 193);
+                    write_encoding<true>(smem, row, cg, x, 193);
                 }
                 if (l < 7) epi_publish_a(&bar);
             }
@@ -226,7 +232,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
             const bool live = gp < p.n;
             float x[3] = {0.f, 0.f, 0.f};
             if (live) { x[0] = p.pts[gp * 3]; x[1] = p.pts[gp * 3 + 1]; x[2] = p.pts[gp * 3 + 2]; }
-            write_encoding(smem, row, cg, x, 0, live ? p.E + gp * 64 : nullptr);
+            write_encoding<true>(smem, row, cg, x, 0, live ? p.E + gp * 64 : nullptr);
             epi_publish_a(&bar);
             // ---- value trunk ----------------------------------------------------------------------
             float head = 0.0f;
@@ -251,7 +257,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                             if (live) st4(ht + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) a_store8(smem, row, col0 + j, v + j);
+                        for (int j = 0; j < 32; j += 8) a_store8<true>(smem, row, col0 + j, v + j);
                         if (l == 7) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
@@ -266,10 +272,10 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                         float v[32];
                         acc_load32(tmem, row, 192, v);
                         const float h = softplus100_fast(v[0] + __ldg(bias + 192));
-                        a_store1(smem, row, 192, h);
+                        a_store1<true>(smem, row, 192, h);
                         if (live) ht[toff(row, 192)] = h;
                     }
-                    write_encoding(smem, row, cg, x, 193, live ? ht : nullptr, true);
+                    write_encoding<true>(smem, row, cg, x, 193, live ? ht : nullptr, true);
                 }
                 epi_publish_a(&bar);
             }
@@ -299,7 +305,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float h[8];
-                        a_load8(smem, row, col0 + j, h);
+                        a_load8<true>(smem, row, col0 + j, h);
                         const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
                         const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j + 4));
                         const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -632,10 +638,11 @@ int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sc
     Program prog = {};
     prog.n_steps = 8;
     for (int l = 0; l < 8; ++l) {
-        prog.step[l].b_off = L.nt_off[l];
+        prog.step[l].b_off = L.nt16_off[l];
         prog.step[l].n_mma = L.nt_n[l];
         prog.step[l].kblocks = L.nt_kb[l];
         prog.step[l].a_kb0 = 0;
+        prog.step[l].f16 = 1;
     }
     static bool configured = false;
     if (!configured) {
@@ -673,8 +680,9 @@ int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
     p.stagger = g_stagger_fwd;
     Program prog = {};
     int k = 0;
-    for (int l = 0; l < 9; ++l, ++k) {           // value trunk + feature head: a @ W_l^T
-        prog.step[k].b_off = L.nt_off[l];
+    for (int l = 0; l < 9; ++l, ++k) {           // value trunk + feature head: a @ W_l^T, fp16 pairs
+        prog.step[k].f16 = 1;
+        prog.step[k].b_off = L.nt16_off[l];
         prog.step[k].n_mma = L.nt_n[l];
         prog.step[k].kblocks = L.nt_kb[l];
         prog.step[k].a_kb0 = 0;
@@ -894,6 +902,8 @@ int hn_sdf_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_byte
         // NN: B(n = in, k = out) from WT [in, ldT]
         HN_PROPAGATE(chain::launch_pack_b(m->WT[l], m->ldT[l], 0, row0, in_d[l], rows, L.nn_n[l], L.nn_kb[l],
                                           dst + L.nn_off[l], s));
+        HN_PROPAGATE(chain::launch_pack_b(m->W[l], m->ld[l], chain::pack_map(row0, 0), rows, in_d[l], L.nt_n[l], L.nt_kb[l],
+                                          dst + L.nt16_off[l], s, true));
     }
     return HN_OK;
 }

@@ -7,7 +7,7 @@ namespace hn {
 namespace chain {
 
 __global__ void pack_b_kernel(const float* __restrict__ src, int64_t ld, PackMap m, int rows, int cols, int n_pad,
-                              int kblocks, uint8_t* __restrict__ dst) {
+                              int kblocks, uint8_t* __restrict__ dst, int lo16) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;          // one 16-byte chunk (8 columns) of one row
     int total = n_pad * kblocks * 8;
     if (idx >= total) return;
@@ -23,19 +23,27 @@ __global__ void pack_b_kernel(const float* __restrict__ src, int64_t ld, PackMap
         v[j] = (n < rows && k < cols) ? src[srow * ld + scol] : 0.0f;
     }
     uint4 hi, lo;
-    split2(v[0], v[1], hi.x, lo.x);
-    split2(v[2], v[3], hi.y, lo.y);
-    split2(v[4], v[5], hi.z, lo.z);
-    split2(v[6], v[7], hi.w, lo.w);
+    if (lo16) {
+        split2_lo16(v[0], v[1], hi.x, lo.x);
+        split2_lo16(v[2], v[3], hi.y, lo.y);
+        split2_lo16(v[4], v[5], hi.z, lo.z);
+        split2_lo16(v[6], v[7], hi.w, lo.w);
+    } else {
+        split2(v[0], v[1], hi.x, lo.x);
+        split2(v[2], v[3], hi.y, lo.y);
+        split2(v[4], v[5], hi.z, lo.z);
+        split2(v[6], v[7], hi.w, lo.w);
+    }
     size_t base = (size_t)kb * 2 * n_pad * 128 + tc::sw128_offset((uint32_t)n, (uint32_t)c16);
     *reinterpret_cast<uint4*>(dst + base) = hi;
     *reinterpret_cast<uint4*>(dst + base + (size_t)n_pad * 128) = lo;
 }
 
 int launch_pack_b(const float* src, int64_t ld, PackMap map, int rows, int cols, int n_pad, int kblocks, uint8_t* dst,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, bool lo16) {
     int total = n_pad * kblocks * 8;
-    pack_b_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, ld, map, rows, cols, n_pad, kblocks, dst);
+    pack_b_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, ld, map, rows, cols, n_pad, kblocks, dst,
+                                                                      lo16 ? 1 : 0);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -113,6 +113,11 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t M, uint
            | ((M >> 4) << 24);  // M / 16
 }
 
+// same with independent A / B element formats (kind::f16 lets one operand be fp16 and the other bf16)
+__host__ __device__ constexpr uint32_t make_idesc_ab(uint32_t afmt, uint32_t bfmt, uint32_t M, uint32_t N) {
+    return (1u << 4) | (afmt << 7) | (bfmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
 // K-major operand tile in the canonical SWIZZLE_128B layout: rows of 128 bytes, 8-row groups of
 // 1024 bytes stacked densely (SBO = 1024 B).  The tile base must be 1024-byte aligned; a K step
 // inside the 128-byte row is taken by advancing the start address (hardware swizzles on address

@@ -25,3 +25,23 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# Parity tests written against the fp32 SIMT verification path (tolerances ~1e-5) pin it explicitly; the tensor-core
+# default (tc_bf16x3) has its own tests (test_gpu_chain.py, test_gpu_product_default.py) with its own stated bounds.
+_SIMT_MODULES = ("test_gpu_obj_fields", "test_gpu_render", "test_gpu_hand", "test_gpu_fit")
+
+
+@pytest.fixture(autouse=True)
+def _precision_for_module(request):
+    mod = request.module.__name__.split(".")[-1]
+    try:
+        import honerf_b200 as H
+    except Exception:
+        yield
+        return
+    prev = H.ops.default_precision()
+    if mod in _SIMT_MODULES:
+        H.set_default_precision("simt_fp32")
+    yield
+    H.ops._default_precision = prev

@@ -27,9 +27,13 @@ def test_library_exports_every_header_symbol():
 
 def test_size_queries_run_without_a_gpu():
     from honerf_b200 import _lib
-    assert _lib.lib.hn_sdf_obj_stash_floats(1000) == 1000 * (64 + 16 * 256 + 64)
+    # stashes are sized for whole 128-point tiles (the tiled layout of the HN_TC_BF16X3 chain kernels)
+    assert _lib.lib.hn_sdf_obj_stash_floats(1000) == 1024 * (64 + 16 * 256 + 64)
+    assert _lib.lib.hn_sdf_obj_stash_floats(1024) == 1024 * (64 + 16 * 256 + 64)
     assert _lib.lib.hn_sdf_obj_ws_floats(10, _lib.HN_WS_SDF_ONLY) > 0
-    assert _lib.lib.hn_color_obj_stash_floats(10) == 10 * (384 + 1024)
+    assert _lib.lib.hn_sdf_obj_ws_floats(1000, _lib.HN_WS_BWD) >= 1024 * (64 + 24 * 256 + 64)
+    assert _lib.lib.hn_color_obj_stash_floats(10) == 128 * (128 + 5 * 256)
+    assert _lib.lib.hn_sdf_obj_chain_bytes() > 4 * 1024 * 1024 and _lib.lib.hn_color_obj_chain_bytes() > 2 * 1024 * 1024
 
 
 def test_no_cpu_fallback():
