@@ -185,12 +185,22 @@ def build_gpu_model(device, precision):
     return H, r, params, opt
 
 
+def _dbg(msg):
+    if os.environ.get("BENCH_DEBUG"):
+        sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter(), msg))
+        sys.stderr.flush()
+
+
 def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
@@ -205,15 +215,33 @@ def run_gpu_arm(args):
     Ro = dev_batch["Ro"].clone().requires_grad_(True)
     To = dev_batch["To"].clone().requires_grad_(True)
 
-    def train_step(b):
+    flat_holder = {}
+
+    def fwd_bwd(b):
+        """render + loss + backward; for N > 1 also packs every gradient into one flat buffer"""
         out = renderer.render(b["rays_o"], b["rays_d"], host["near"], host["far"], None, None, None, Ro, To, 0)
         loss = training_loss(out, b["true_rgb"], b["true_mask"])
         opt.zero_grad(set_to_none=True)
         Ro.grad = None; To.grad = None
         loss.backward()
         if world > 1:
-            hdist.allreduce_gradients(params, world)
+            flat_holder["flat"] = hdist.flatten_gradients(params)
+        return loss
+
+    def reduce_grads():
+        """the ONE collective of the step: all-reduce of the flat gradient buffer (NCCL over NVLink)"""
+        if world > 1:
+            hdist.allreduce_flat(flat_holder["flat"])
+
+    def apply_grads():
+        if world > 1:
+            hdist.unflatten_gradients(params, flat_holder["flat"], world)
         opt.step()
+
+    def train_step(b):
+        loss = fwd_bwd(b)
+        reduce_grads()
+        apply_grads()
         return loss
 
     def barrier():
@@ -254,13 +282,23 @@ def run_gpu_arm(args):
         launches_per_step = H.launch_count() - l0
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    graph, loss_static = None, None
+    _dbg("warm-up done, %d launches per step" % launches_per_step)
+    graph, graph_b, loss_static = None, None, None
     if not args.no_graph:
         try:
+            # N = 1: one graph for the whole step.  N > 1: graph A = render + loss + backward + gradient packing, then
+            # the NCCL all-reduce launched eagerly (never captured), then graph B = unpack + Adam.
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                loss_static = train_step(static)
+                loss_static = fwd_bwd(static) if world > 1 else train_step(static)
+            if world > 1:
+                graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_b, pool=graph.pool()):
+                    apply_grads()
             graph.replay()
+            if world > 1:
+                reduce_grads()
+                graph_b.replay()
             torch.cuda.synchronize()
             if not torch.isfinite(loss_static).all():
                 raise RuntimeError("non-finite loss from the captured step")
@@ -269,11 +307,17 @@ def run_gpu_arm(args):
             sys.stderr.write("bench.py: CUDA graph capture failed (%s: %s); re-running with --no-graph\n"
                              % (type(e).__name__, str(e)[:300]))
             sys.stderr.flush()
+            if world > 1:
+                raise           # under torchrun every rank must take the same path: fail loudly instead
             os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+    _dbg("graph capture done: %s" % (graph is not None))
 
     def resident_step():
         if graph is not None:
             graph.replay()
+            if graph_b is not None:
+                reduce_grads()
+                graph_b.replay()
         else:
             train_step(dev_batch)
 
@@ -297,7 +341,7 @@ def run_gpu_arm(args):
         if graph is not None:
             for k in keys:
                 static[k].copy_(pinned[k], non_blocking=True)
-            graph.replay()
+            resident_step()
             loss_host.copy_(loss_static.detach(), non_blocking=False)
         else:
             b = {k: pinned[k].to(device, non_blocking=True) for k in keys}
@@ -306,13 +350,16 @@ def run_gpu_arm(args):
 
     for _ in range(2):
         e2e_step()
+    _dbg("device-resident timing done")
     ms_e2e = timed(e2e_step, args.steps) / args.steps
+    _dbg("e2e timing done")
     e2e_value = world * n_rays / (ms_e2e * 1e-3)
 
     # ---- roofline of the dominant kernel family (the MLP contractions), rank 0, separate pass ----
     roof, comp = None, None
     if rank == 0:
-        roof = mlp_roofline(H, lambda: train_step(dev_batch), n_rays)
+        # rank 0 alone runs this pass: the step without its collective
+        roof = mlp_roofline(H, lambda: (fwd_bwd(dev_batch), apply_grads()), n_rays)
         comp = compositor_roofline(H, device)
     large = None
     if rank == 0 and world == 1 and args.large_rays > 0:
@@ -322,7 +369,7 @@ def run_gpu_arm(args):
             lb = {k: v.to(device) for k, v in hb.items() if torch.is_tensor(v)}
             for _ in range(2):
                 train_step(lb)
-            ms_l = timed(lambda: train_step(lb), 3) / 3
+            ms_l = timed(lambda: train_step(lb), 3) / 3      # world == 1 here: no collective inside
             large = {"rays_per_gpu": args.large_rays, "ms_per_step": ms_l, "value": args.large_rays / (ms_l * 1e-3),
                      "unit": "rays/s", "note": "eager launches, device-resident inputs"}
             del lb
@@ -373,7 +420,7 @@ def run_gpu_arm(args):
             "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large, "sdf_grid": grid,
             "mlp_flops_per_ray": FLOPS_PER_RAY_TRAIN,
         }
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -35,3 +35,28 @@ def allreduce_gradients(params, world_size=None, average=True):
         g.copy_(flat[off:off + n].view_as(g))
         off += n
     return flat.numel()
+
+
+def flatten_gradients(params):
+    """Every existing .grad packed into one contiguous buffer (the payload of the step's single collective)."""
+    grads = [p.grad for p in params if p.grad is not None]
+    return torch.cat([g.reshape(-1) for g in grads])
+
+
+def allreduce_flat(flat):
+    """The collective itself; kept separate so a caller can leave it outside a captured CUDA graph."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat
+
+
+def unflatten_gradients(params, flat, world_size, average=True):
+    off = 0
+    for p in params:
+        if p.grad is None:
+            continue
+        n = p.grad.numel()
+        src = flat[off:off + n].view_as(p.grad)
+        p.grad.copy_(src / world_size if average else src)
+        off += n
+    return off

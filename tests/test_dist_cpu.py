@@ -43,3 +43,30 @@ def test_flat_gradient_allreduce_gloo_world2():
         assert torch.allclose(g1, torch.arange(7.0) * 1.5)
         assert g2 is None
     assert out[0][4] == (0, 6) and out[1][4] == (6, 11)
+
+
+def _worker_split(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from honerf_b200 import dist as hdist
+    params = [torch.nn.Parameter(torch.zeros(4, 2)), torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(1))]
+    params[0].grad = torch.full((4, 2), float(rank + 1))
+    params[2].grad = torch.tensor([10.0 * (rank + 1)])
+    flat = hdist.flatten_gradients(params)          # what bench.py captures in graph A
+    hdist.allreduce_flat(flat)                      # the eager collective
+    n = hdist.unflatten_gradients(params, flat, world)      # graph B
+    out[rank] = (n, params[0].grad.clone(), params[1].grad, params[2].grad.clone())
+    dist.destroy_process_group()
+
+
+def test_split_flatten_allreduce_unflatten_gloo_world2():
+    """The three-phase form bench.py uses at N > 1 (pack in graph A, eager all-reduce, unpack + Adam in graph B)
+    gives the same averaged gradients as the one-call form."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_split, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        n, g0, g1, g2 = out[r]
+        assert n == 9 and g1 is None
+        assert torch.allclose(g0, torch.full((4, 2), 1.5)) and torch.allclose(g2, torch.tensor([15.0]))
