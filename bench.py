@@ -181,7 +181,7 @@ def build_gpu_model(device, precision):
         m.to(device)
     r = H.NeuSRenderer(sdf, var, col, "obj", **ref_conf.RENDERER_CONF)
     params = list(sdf.parameters()) + list(var.parameters()) + list(col.parameters())
-    opt = torch.optim.Adam(params, lr=1e-4, capturable=True)      # capturable: the step can live in a CUDA graph
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)   # one fused kernel; capturable in a CUDA graph
     return H, r, params, opt
 
 
@@ -426,35 +426,72 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+KERNEL_FAMILIES = ["per-layer contractions (gemm_* kernels)", "chain::sdf_only_kernel", "chain::sdf_fwd_kernel",
+                   "chain::sdf_bwd_kernel", "chain::dw_kernel", "chain::color_fwd_kernel", "chain::color_bwd_kernel"]
+
+
+def _family_flops_per_step(n_rays):
+    """ALGORITHMIC FLOPs per train step of each kernel family (sums to n_rays * FLOPS_PER_RAY_TRAIN)."""
+    n = n_rays * (N_SAMPLES + N_IMPORTANCE)
+    return [0, n_rays * 112 * F_O,       # sampler queries: 64 + 3 x 16 points per ray, F_o each
+            n * 2 * F_O,                 # value trunk + feature head, normal sweep
+            n * 2 * F_O,                 # tangent sweep, reverse sweep
+            n * (2 * F_O + C_O),         # weight gradients of both nets
+            n * C_O, n * C_O]
+
+
 def mlp_roofline(H, step_fn, n_rays):
-    """Tensor roofline of the MLP contractions: algorithmic FLOPs (per ray
-    112 F_o + 128 (6 F_o + 3 C_o)) over the summed device time of the library's GEMM launches, taken
-    with CUDA events recorded on the launching stream inside the library (hn_timing_*)."""
+    """Tensor roofline of the MLP kernels: algorithmic FLOPs (per ray 112 F_o + 128 (6 F_o + 3 C_o)) over
+    device time taken with CUDA events recorded on the launching stream inside the library around every such launch
+    (hn_timing_*), per kernel family.  `achieved`/`frac` at the top level are those of the DOMINANT kernel (largest
+    share of the step); `step` aggregates all families."""
+    import ctypes
     from honerf_b200 import _lib
     peaks, src = measured_peaks()
-    if not hasattr(_lib.lib, "hn_timing_enable"):
-        return None
     _lib.lib.hn_timing_enable(1)
     step_fn()
     torch.cuda.synchronize()
     _lib.lib.hn_timing_reset()
-    reps = 2
+    reps = 3
     for _ in range(reps):
         step_fn()
     torch.cuda.synchronize()
-    import ctypes
-    ms, n = ctypes.c_double(0), ctypes.c_int64(0)
-    _lib.lib.hn_timing_collect(ctypes.byref(ms), ctypes.byref(n))
+    nt = len(KERNEL_FAMILIES)
+    ms = (ctypes.c_double * nt)()
+    cnt = (ctypes.c_int64 * nt)()
+    _lib.lib.hn_timing_collect_tags(ms, cnt, nt)
     _lib.lib.hn_timing_enable(0)
-    if n.value == 0 or ms.value <= 0:
+    if sum(cnt) == 0:
         return None
-    flops = reps * n_rays * FLOPS_PER_RAY_TRAIN
-    achieved = flops / (ms.value * 1e-3) / 1e12
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-    return {"bound": "tensor", "kernel": "MLP contractions (all GEMM launches of one step)", "achieved": achieved,
-            "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": src + ", sustained bf16",
-            "gemm_launches_per_step": n.value // reps, "gemm_ms_per_step": ms.value / reps,
-            "algorithmic_flops_per_step": flops // reps}
+    flops = _family_flops_per_step(n_rays)
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_chain_ncu_metrics.json")
+    if os.path.isfile(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
+    fam = []
+    for t in range(nt):
+        if cnt[t] == 0:
+            continue
+        ms_step = ms[t] / reps
+        fam.append({"kernel": KERNEL_FAMILIES[t], "launches_per_step": cnt[t] // reps, "ms_per_step": ms_step,
+                    "ms_per_launch": ms[t] / cnt[t], "algorithmic_flops_per_step": flops[t],
+                    "achieved": flops[t] / (ms_step * 1e-3) / 1e12 if flops[t] else None,
+                    "frac": flops[t] / (ms_step * 1e-3) / 1e12 / peak if flops[t] else None,
+                    "traffic": traffic.get(KERNEL_FAMILIES[t])})
+    dom = max(fam, key=lambda f: f["ms_per_step"])
+    tot_ms = sum(f["ms_per_step"] for f in fam)
+    tot_fl = n_rays * FLOPS_PER_RAY_TRAIN
+    return {"bound": "tensor", "kernel": dom["kernel"],
+            "achieved": dom["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": dom["frac"], "traffic": dom["traffic"],
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_chain_ncu_metrics.json"
+                              if dom["traffic"] else None,
+            "algorithmic_flops_per_launch": dom["algorithmic_flops_per_step"] // max(dom["launches_per_step"], 1),
+            "ms_per_launch": dom["ms_per_launch"], "share_of_mlp_time": dom["ms_per_step"] / tot_ms,
+            "peak_source": src + ", sustained bf16 (dense, no split: the 3-MMA split caps algorithmic FLOPs at 1/3 of it)",
+            "step": {"achieved": tot_fl / (tot_ms * 1e-3) / 1e12, "frac": tot_fl / (tot_ms * 1e-3) / 1e12 / peak,
+                     "mlp_ms_per_step": tot_ms, "algorithmic_flops_per_step": tot_fl},
+            "families": fam}
 
 
 def compositor_roofline(H, device, n_rays=1 << 18, n=128):

@@ -52,6 +52,7 @@ PROTOTYPES = {
     "hn_timing_enable": (c_int, [c_int]),
     "hn_timing_reset": (c_int, []),
     "hn_timing_collect": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "hn_timing_collect_tags": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
     "hn_wn_pack": (c_int, [P, P, c_int, c_int, c_int, c_float, P, P, c_int, P]),
     "hn_wn_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
     "hn_wn_pack_gap": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int, P]),

@@ -328,7 +328,7 @@ int launch_color_fwd(const hn_mlp_t* m, const float* pts, const float* dirs, con
         configured = true;
     }
     {
-        TimingScope ts(s);
+        TimingScope ts(s, TT_COLOR_FWD);
         color_fwd_kernel<<<std::min(p.n_tiles, sm_count()), THREADS, SMEM_BYTES, s>>>(p, prog);
     }
     count_launch();
@@ -367,7 +367,7 @@ int launch_color_bwd(const hn_mlp_t* m, int64_t n, const float* stash, const flo
         configured = true;
     }
     {
-        TimingScope ts(s);
+        TimingScope ts(s, TT_COLOR_BWD);
         color_bwd_kernel<<<std::min(p.n_tiles, sm_count()), THREADS, SMEM_BYTES, s>>>(p, prog);
     }
     count_launch();

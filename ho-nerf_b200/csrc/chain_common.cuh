@@ -256,16 +256,6 @@ __device__ __forceinline__ void mma_loop(const Program& prog, uint8_t* smem, Bar
     }
 }
 
-// One epilogue thread asks L2 for a whole [128, 256] fp32 tile (128 KB contiguous in the tiled layout) that the
-// NEXT epilogue will read, so that the HBM traffic overlaps the MMAs instead of following them.
-__device__ __forceinline__ void prefetch_tile(const float* tile_base, bool enable = true) {
-    if (!enable) return;
-    // 128 KB = 1024 lines of 128 B; 512 epilogue threads take two lines each
-    const char* base = reinterpret_cast<const char*>(tile_base) + (size_t)(threadIdx.x - 64) * 128;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 65536));
-}
-
 // All CTAs run the same program, so without help their HBM-heavy epilogues and their MMA phases line up
 // across the chip (HBM saturated, then idle).  Shifting CTAs by a fraction of a layer period spreads the
 // memory phases over time.  Called once by the epilogue warps before the first tile.

@@ -238,7 +238,7 @@ int launch_dw(const DwParams& p, const DwReduceParams& r, cudaStream_t s) {
         configured = true;
     }
     {
-        TimingScope ts(s);
+        TimingScope ts(s, TT_DW);
         dw_kernel<<<p.n_jobs * DW_SPLITS, DW_THREADS, DW_SMEM_BYTES, s>>>(p);
     }
     count_launch();

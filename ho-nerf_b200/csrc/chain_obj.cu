@@ -320,11 +320,9 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                     }
                 }
             }
-            prefetch_tile(p.H[6] + tile * TILE_FLOATS, tile * TILE_M < p.n);
             epi_publish_a(&bar);
             // ---- normal sweep: D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1 ------------------------------
             for (int l = 7; l >= 1; --l) {
-                if (l >= 2) prefetch_tile(p.H[l - 2] + tile * TILE_FLOATS);      // for the next epilogue
                 const float* __restrict__ ht = p.H[l - 1] + tile * TILE_FLOATS;
                 float* __restrict__ dt = p.D[l - 1] + tile * TILE_FLOATS;
                 epi_stream<1, 8>(&bar, acc_par, tmem, row, cg, live, true, ht, ht, [&](int col0, float* v, float4 (*aux)[2]) {
@@ -471,17 +469,9 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                 }
             };
             write_ue(0, p.UE + gp * 64, false);
-            prefetch_tile(p.H[0] + tile * TILE_FLOATS);
-            prefetch_tile(p.D[0] + tile * TILE_FLOATS);
             epi_publish_a(&bar);
             // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l -----------
             for (int l = 0; l < 8; ++l) {
-                if (l < 7) {
-                    prefetch_tile(p.H[l + 1] + tile * TILE_FLOATS);
-                    prefetch_tile(p.D[l + 1] + tile * TILE_FLOATS);
-                } else {
-                    prefetch_tile(p.X[7] + tile * TILE_FLOATS);      // H[7] was just read
-                }
                 const float* __restrict__ ht = p.H[l] + tile * TILE_FLOATS;
                 const float* __restrict__ dt = p.D[l] + tile * TILE_FLOATS;
                 float* __restrict__ ut = p.U[l] + tile * TILE_FLOATS;
@@ -542,10 +532,6 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
             // ---- reverse sweep: dz_{l-1} = s'(h_{l-1}) (dz_l W_l) + X_{l-1}, l = 8..1 ------------------------
             const float gs = (live && p.d_sdf) ? p.d_sdf[gp] * p.inv_scale : 0.0f;
             for (int l = 8; l >= 1; --l) {
-                if (l >= 2) {
-                    prefetch_tile(p.H[l - 2] + tile * TILE_FLOATS);
-                    prefetch_tile(p.X[l - 2] + tile * TILE_FLOATS);
-                }
                 const float* __restrict__ ht = p.H[l - 1] + tile * TILE_FLOATS;
                 const float* __restrict__ xt = p.X[l - 1] + tile * TILE_FLOATS;
                 float* __restrict__ zt = p.DZ[l - 1] + tile * TILE_FLOATS;
@@ -651,7 +637,7 @@ int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sc
     }
     const int grid = std::min(p.n_tiles, sm_count());
     {
-        TimingScope ts(s);
+        TimingScope ts(s, TT_SDF_ONLY);
         sdf_only_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p, prog);
     }
     count_launch();
@@ -701,7 +687,7 @@ int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
     }
     const int grid = std::min(p.n_tiles, sm_count());
     {
-        TimingScope ts(s);
+        TimingScope ts(s, TT_SDF_FWD);
         sdf_fwd_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p, prog);
     }
     count_launch();
@@ -760,7 +746,7 @@ int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     }
     const int grid = std::min(p.n_tiles, sm_count());
     {
-        TimingScope ts(s);
+        TimingScope ts(s, TT_SDF_BWD);
         sdf_bwd_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(p, prog);
     }
     count_launch();

@@ -70,10 +70,20 @@ void count_launch(int n = 1);
 
 // Opt-in device timing of the dense-contraction launches (hn_timing_* in the C ABI): when enabled,
 // a pair of CUDA events is recorded on the launching stream around every GEMM launch.
+enum TimingTag {
+    TT_GEMM = 0,          // per-layer contractions (SIMT / TF32 paths, hand field)
+    TT_SDF_ONLY = 1,      // chain: sampler's SDF queries
+    TT_SDF_FWD = 2,       // chain: value + feature + normal sweep
+    TT_SDF_BWD = 3,       // chain: tangent + reverse sweeps
+    TT_DW = 4,            // chain: weight gradients
+    TT_COLOR_FWD = 5,
+    TT_COLOR_BWD = 6,
+    TT_COUNT = 7
+};
 struct TimingScope {
     cudaStream_t stream;
     int slot;
-    explicit TimingScope(cudaStream_t s);
+    explicit TimingScope(cudaStream_t s, int tag = TT_GEMM);
     ~TimingScope();
 };
 

@@ -25,9 +25,10 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 static std::atomic<int> g_timing_on{0};
 static std::mutex g_timing_mu;
 static std::vector<cudaEvent_t> g_ev_start, g_ev_stop;
+static std::vector<int> g_ev_tag;
 static size_t g_ev_used = 0;
 
-TimingScope::TimingScope(cudaStream_t s) : stream(s), slot(-1) {
+TimingScope::TimingScope(cudaStream_t s, int tag) : stream(s), slot(-1) {
     if (!g_timing_on.load(std::memory_order_relaxed)) return;
     std::lock_guard<std::mutex> lk(g_timing_mu);
     if (g_ev_used == g_ev_start.size()) {
@@ -35,8 +36,10 @@ TimingScope::TimingScope(cudaStream_t s) : stream(s), slot(-1) {
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
         g_ev_start.push_back(a);
         g_ev_stop.push_back(b);
+        g_ev_tag.push_back(0);
     }
     slot = (int)g_ev_used++;
+    g_ev_tag[slot] = tag;
     cudaEventRecord(g_ev_start[slot], stream);
 }
 TimingScope::~TimingScope() {
@@ -173,6 +176,25 @@ int hn_timing_collect(double* total_ms, int64_t* n_launches) {
     }
     if (total_ms) *total_ms = tot;
     if (n_launches) *n_launches = (int64_t)g_ev_used;
+    return HN_OK;
+}
+
+int hn_timing_collect_tags(double* ms_per_tag, int64_t* launches_per_tag, int n_tags) {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    for (int t = 0; t < n_tags; ++t) {
+        if (ms_per_tag) ms_per_tag[t] = 0.0;
+        if (launches_per_tag) launches_per_tag[t] = 0;
+    }
+    for (size_t i = 0; i < g_ev_used; ++i) {
+        float ms = 0.0f;
+        HN_CHECK_CUDA(cudaEventSynchronize(g_ev_stop[i]));
+        HN_CHECK_CUDA(cudaEventElapsedTime(&ms, g_ev_start[i], g_ev_stop[i]));
+        const int t = g_ev_tag[i];
+        if (t >= 0 && t < n_tags) {
+            if (ms_per_tag) ms_per_tag[t] += ms;
+            if (launches_per_tag) launches_per_tag[t] += 1;
+        }
+    }
     return HN_OK;
 }
 

@@ -55,6 +55,10 @@ HN_API int64_t hn_launch_count(void);
 HN_API int hn_timing_enable(int on);
 HN_API int hn_timing_reset(void);
 HN_API int hn_timing_collect(double* total_ms, int64_t* n_launches); /* HOST pointers */
+/* Same, split by kernel family: 0 per-layer contractions, 1 chain SDF-only, 2 chain SDF forward (value + feature +
+ * normal sweep), 3 chain SDF backward (tangent + reverse sweeps), 4 chain weight gradients, 5 chain colour forward,
+ * 6 chain colour backward.  HOST arrays of n_tags entries. */
+HN_API int hn_timing_collect_tags(double* ms_per_tag, int64_t* launches_per_tag, int n_tags);
 
 /* ---------------------------------------------------------------------------------------------
  * Weight-normalised MLP parameters (nn.utils.weight_norm, dim=0:
