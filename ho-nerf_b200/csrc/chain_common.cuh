@@ -148,12 +148,23 @@ __device__ __forceinline__ void a_load8(const uint8_t* smem, int row, int col, f
     }
 }
 
-// softplus(beta=100) with torch's threshold (identity for 100 z > 20; below it the log1p term is
-// < 2.1e-11, far under an ulp of z >= 0.2, so the two branches agree to fp32 rounding)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {     // x in [1, 2] here: no denormal handling needed
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// softplus(beta=100) = max(z, 0) + 0.01 log1p(exp(-|100 z|)).  torch's threshold branch (identity for 100 z > 20)
+// agrees with this to fp32 rounding: there the log1p term is < 2.1e-11, far under an ulp of z >= 0.2.  7 issue slots
+// (2 MUFU) per element: the raw ex2 / lg2 approximations skip the range fix-ups of __expf / __logf, which cannot
+// trigger here (the exponent is <= 0, the log argument lies in [1, 2]).
 __device__ __forceinline__ float softplus100_fast(float z) {
-    float t = z * 100.0f;
-    float e = __expf(-fabsf(t));
-    return fmaxf(z, 0.0f) + 0.01f * __logf(1.0f + e);
+    const float e = ex2_approx(-fabsf(z) * 144.26950408889634f);          // exp(-|100 z|)
+    return fmaf(lg2_approx(1.0f + e), 0.006931471805599453f, fmaxf(z, 0.0f));   // + 0.01 ln2 lg2(1 + e)
 }
 
 // ---- setup / teardown (all threads) -----------------------------------------------------------

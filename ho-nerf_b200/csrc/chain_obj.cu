@@ -207,7 +207,7 @@ struct FwdParams {
     long long* prof;
 };
 
-__device__ __forceinline__ float sprime_fast(float h) { return 1.0f - __expf(-100.0f * h); }
+__device__ __forceinline__ float sprime_fast(float h) { return 1.0f - ex2_approx(-144.26950408889634f * h); }
 
 __global__ void __launch_bounds__(THREADS, 1)
 sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Program prog) {
@@ -487,7 +487,7 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const float qv = v[j + i];
-                            const float em = __expf(-100.0f * hh[i]);       // 1 - s'
+                            const float em = ex2_approx(-144.26950408889634f * hh[i]);       // 1 - s'
                             v[j + i] = (1.0f - em) * qv;
                             xx[i] = 100.0f * em * dd[i] * qv;
                         }
@@ -504,7 +504,7 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                         acc_load32(tmem, row, 192, v);
                         float u = 0.f, xv = 0.f;
                         if (live) {
-                            const float em = __expf(-100.0f * ht[toff(row, 192)]);
+                            const float em = ex2_approx(-144.26950408889634f * ht[toff(row, 192)]);
                             u = (1.0f - em) * v[0];
                             xv = 100.0f * em * dt[toff(row, 192)] * v[0];
                             ut[toff(row, 192)] = u;
