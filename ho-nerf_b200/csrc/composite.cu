@@ -2,6 +2,7 @@
 // replaces utils/renderer.py:144-169 (render_core) and the autograd graph behind it.
 // One warp per ray; every per-sample buffer is read/written once, coalesced along the ray.
 // Algorithmic traffic per sample: fwd 40 B, fwd+bwd 104 B.
+#include <algorithm>
 #include <initializer_list>
 
 #include "common.cuh"
@@ -239,6 +240,23 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, const float* in
     }
 }
 
+// A lane's 3*S consecutive floats (normal / colour cotangents) are stored through a per-warp shared-memory transpose,
+// so that every warp store instruction writes one contiguous 512-byte segment (a direct store would put 16-byte
+// pieces at a 48-byte stride: half-filled sectors at L2).  K = 3*S floats per lane, K % 4 == 0.
+template <int K>
+__device__ __forceinline__ void store_vec_coalesced(float* __restrict__ warp_base, const float* in, float4* sbuf, int lane) {
+    constexpr int NV = K / 4;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) sbuf[j * 32 + lane] = make_float4(in[4 * j], in[4 * j + 1], in[4 * j + 2], in[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int g = k * 32 + lane;                  // float4 index inside the warp's contiguous block
+        reinterpret_cast<float4*>(warp_base)[g] = sbuf[(g % NV) * 32 + g / NV];
+    }
+    __syncwarp();
+}
+
 template <int S>
 __global__ void __launch_bounds__(CMP_WARPS * 32) neus_composite_fwd_vec_kernel(
     const float* __restrict__ sdf, const float* __restrict__ normal, const float* __restrict__ rgb,
@@ -300,12 +318,14 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) neus_composite_bwd_vec_kernel(
     const float* __restrict__ d_weights, const float* __restrict__ d_eik, float* __restrict__ d_sdf,
     float* __restrict__ d_normal, float* __restrict__ d_rgb, float* __restrict__ d_rays_d,
     float* __restrict__ d_variance) {
+    __shared__ float4 s_tr[(3 * S) % 4 == 0 ? CMP_WARPS * (3 * S / 4) * 32 : 1];
     const int lane = threadIdx.x & 31;
-    const int64_t ray = (int64_t)blockIdx.x * CMP_WARPS + (threadIdx.x >> 5);
-    if (ray >= n_rays) return;
     const float inv_s_raw = expf(variance[0] * 10.0f);
     const float inv_s = fminf(fmaxf(inv_s_raw, 1e-6f), 1e6f);
     const bool s_live = inv_s_raw >= 1e-6f && inv_s_raw <= 1e6f;
+    float dinv_acc = 0.0f;       // d/d inv_s summed over this warp's rays: ONE atomic per warp at the end
+    for (int64_t ray = (int64_t)blockIdx.x * CMP_WARPS + (threadIdx.x >> 5); ray < n_rays;
+         ray += (int64_t)gridDim.x * CMP_WARPS) {
     const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float gcr = d_color[ray * 3], gcg = d_color[ray * 3 + 1], gcb = d_color[ray * 3 + 2];
     const float gws = d_wsum ? d_wsum[ray] : 0.0f;
@@ -377,13 +397,20 @@ __global__ void __launch_bounds__(CMP_WARPS * 32) neus_composite_bwd_vec_kernel(
         o_rgb[3 * i] = w[i] * gcr; o_rgb[3 * i + 1] = w[i] * gcg; o_rgb[3 * i + 2] = w[i] * gcb;
     }
     store_vec<S>(d_sdf + s0, o_sdf);
-    store_vec<3 * S>(d_normal + s0 * 3, o_nrm);
-    store_vec<3 * S>(d_rgb + s0 * 3, o_rgb);
-    drx = warp_sum(drx); dry = warp_sum(dry); drz = warp_sum(drz); dinv = warp_sum(dinv);
-    if (lane == 0) {
-        if (d_rays_d) { d_rays_d[ray * 3] = drx; d_rays_d[ray * 3 + 1] = dry; d_rays_d[ray * 3 + 2] = drz; }
-        if (d_variance && s_live) atomicAdd(d_variance, dinv * 10.0f * inv_s);
+    if constexpr ((3 * S) % 4 == 0) {
+        float4* sbuf = s_tr + (threadIdx.x >> 5) * (3 * S / 4) * 32;
+        store_vec_coalesced<3 * S>(d_normal + ray * (32 * S) * 3, o_nrm, sbuf, lane);
+        store_vec_coalesced<3 * S>(d_rgb + ray * (32 * S) * 3, o_rgb, sbuf, lane);
+    } else {
+        store_vec<3 * S>(d_normal + s0 * 3, o_nrm);
+        store_vec<3 * S>(d_rgb + s0 * 3, o_rgb);
     }
+    drx = warp_sum(drx); dry = warp_sum(dry); drz = warp_sum(drz);
+    dinv_acc += dinv;
+    if (lane == 0 && d_rays_d) { d_rays_d[ray * 3] = drx; d_rays_d[ray * 3 + 1] = dry; d_rays_d[ray * 3 + 2] = drz; }
+    }
+    dinv_acc = warp_sum(dinv_acc);
+    if (lane == 0 && d_variance && s_live && dinv_acc != 0.0f) atomicAdd(d_variance, dinv_acc * 10.0f * inv_s);
 }
 
 static inline bool vec_ok(int n, std::initializer_list<const void*> ptrs) {
@@ -441,8 +468,9 @@ int hn_neus_composite_bwd(const float* sdf, const float* normal, const float* rg
                    d_rgb, "hn_neus_composite_bwd: null pointer");
     const unsigned grid = (unsigned)ceil_div(n_rays, CMP_WARPS);
     cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid_p = (unsigned)std::min<int64_t>(grid, (int64_t)sm_count() * 16);      // persistent warps
 #define HN_BWD_VEC(S)                                                                                                  \
-    neus_composite_bwd_vec_kernel<S><<<grid, CMP_WARPS * 32, 0, st>>>(sdf, normal, rgb, dists, rays_d, variance, n_rays, \
+    neus_composite_bwd_vec_kernel<S><<<grid_p, CMP_WARPS * 32, 0, st>>>(sdf, normal, rgb, dists, rays_d, variance, n_rays, \
                                                                       seed_with_c0, d_color, d_weight_sum, d_weights,  \
                                                                       d_eik, d_sdf, d_normal, d_rgb, d_rays_d, d_variance)
     if (vec_ok(n, {sdf, normal, rgb, dists, d_weights, d_sdf, d_normal, d_rgb})) {
