@@ -2,6 +2,8 @@
 // (NeuSRenderer_fitting.get_alpha_sample_color, utils/renderer.py:396-422; utils/renderer_batch.py:150-174)
 // and the joint transmittance / colour compositing of both fields (utils/renderer.py:512-524;
 // utils/renderer_batch.py:258-270), forward and backward.  One warp per ray, n <= 256 samples.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace hn {
@@ -56,11 +58,12 @@ __global__ void __launch_bounds__(FC_WARPS * 32) neus_alpha_bwd_kernel(
     const float* __restrict__ d_alpha, const float* __restrict__ d_eik, float* __restrict__ d_sdf,
     float* __restrict__ d_normal, float* __restrict__ d_rays_d, float* __restrict__ d_variance) {
     const int lane = threadIdx.x & 31;
-    int64_t ray = (int64_t)blockIdx.x * FC_WARPS + (threadIdx.x >> 5);
-    if (ray >= n_rays) return;
     const float inv_s_raw = expf(variance[0] * 10.0f);
     const float inv_s = fminf(fmaxf(inv_s_raw, 1e-6f), 1e6f);
     const bool s_live = inv_s_raw >= 1e-6f && inv_s_raw <= 1e6f;
+    float dinv_acc = 0.0f;       // ONE atomic on d_variance per warp (a per-ray atomic serialises at one L2 address)
+    for (int64_t ray = (int64_t)blockIdx.x * FC_WARPS + (threadIdx.x >> 5); ray < n_rays;
+         ray += (int64_t)gridDim.x * FC_WARPS) {
     const float dx = rays_d[ray * 3], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float gek = d_eik ? d_eik[ray] : 0.0f;
     float drx = 0.f, dry = 0.f, drz = 0.f, dinv = 0.f;
@@ -89,11 +92,12 @@ __global__ void __launch_bounds__(FC_WARPS * 32) neus_alpha_bwd_kernel(
         d_normal[s * 3 + 2] = dtc * dz + ke * nzv;
         drx += dtc * nxv; dry += dtc * nyv; drz += dtc * nzv;
     }
-    drx = warp_sum(drx); dry = warp_sum(dry); drz = warp_sum(drz); dinv = warp_sum(dinv);
-    if (lane == 0) {
-        if (d_rays_d) { d_rays_d[ray * 3] = drx; d_rays_d[ray * 3 + 1] = dry; d_rays_d[ray * 3 + 2] = drz; }
-        if (d_variance && s_live) atomicAdd(d_variance, dinv * 10.0f * inv_s);
+    drx = warp_sum(drx); dry = warp_sum(dry); drz = warp_sum(drz);
+    dinv_acc += dinv;
+    if (lane == 0 && d_rays_d) { d_rays_d[ray * 3] = drx; d_rays_d[ray * 3 + 1] = dry; d_rays_d[ray * 3 + 2] = drz; }
     }
+    dinv_acc = warp_sum(dinv_acc);
+    if (lane == 0 && d_variance && s_live && dinv_acc != 0.0f) atomicAdd(d_variance, dinv_acc * 10.0f * inv_s);
 }
 
 __device__ __forceinline__ float fc_excl_prod(float f, int lane, float* total) {
@@ -217,7 +221,8 @@ int hn_neus_alpha_bwd(const float* sdf, const float* normal, const float* dists,
     HN_REQUIRE(n_rays >= 0 && n > 0, "hn_neus_alpha_bwd: bad sizes");
     if (n_rays == 0) return HN_OK;
     HN_REQUIRE(sdf && normal && dists && rays_d && variance && d_sdf && d_normal, "hn_neus_alpha_bwd: null pointer");
-    neus_alpha_bwd_kernel<<<(unsigned)ceil_div(n_rays, FC_WARPS), FC_WARPS * 32, 0, (cudaStream_t)stream>>>(
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(n_rays, FC_WARPS), (int64_t)sm_count() * 16);
+    neus_alpha_bwd_kernel<<<grid, FC_WARPS * 32, 0, (cudaStream_t)stream>>>(
         sdf, normal, dists, rays_d, variance, n_rays, n, d_alpha, d_eik, d_sdf, d_normal, d_rays_d, d_variance);
     count_launch();
     HN_CHECK_LAUNCH();
