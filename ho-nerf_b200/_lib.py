@@ -89,6 +89,7 @@ PROTOTYPES = {
                                  c_int, P]),
     "hn_dw_test": (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "hn_tc_gemm_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "hn_tc_gemm_ts_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "hn_gemm_test": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "hn_ray_points": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "hn_mid_points": (c_int, [P, P, P, c_int64, c_int, c_float, P, P, P]),

@@ -306,6 +306,9 @@ HN_API int hn_fit_composite_bwd(const float* alpha_h, const float* rgb_h, const 
  * ------------------------------------------------------------------------------------------- */
 HN_API int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
                            hn_stream_t stream);
+/* Same product with the A operand staged in tensor memory (tcgen05.st + the `ts` MMA form); K <= 256. */
+HN_API int hn_tc_gemm_ts_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
+                              hn_stream_t stream);
 /* The weight-gradient kernel of the HN_TC_BF16X3 path, for tests: C [out, ldc] += P^T Q (+ P2^T Q2) over n
  * points, P [n, out] and Q [n, in] fp32, row-major (ld) or tiled ([tile][col/4][128][4], n padded to 128);
  * db [out] += column sums of P (may be NULL); part: workspace of >= 16 * 65536 floats. */
