@@ -50,6 +50,8 @@ struct Step {
     uint8_t f16 : 1;         // A and B are fp16 (hi + lo) pairs instead of bf16 pairs: ~2^-21 instead of ~2^-17
                              // relative, but fp16 range -- only for the O(1) forward values (value trunk), never
                              // for cotangents (kind::f16 cannot mix fp16 and bf16 operands in one MMA)
+    uint8_t no_wait : 1;     // chain_ts.cu: second column half of a layer, same A operand: do not wait for a_ready
+    uint16_t acc_col;        // chain_ts.cu: first TMEM column of this step's accumulator
 };
 struct Program {
     int n_steps;

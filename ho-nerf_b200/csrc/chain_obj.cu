@@ -5,47 +5,15 @@
 // first layer's A operand; the skip connection's [h3 | e] / sqrt2 (utils/fields.py:323-324) is formed in
 // place (1/sqrt2 is folded into W_4 at pack time, SURVEY A-8).
 #include <algorithm>
+#include <cstdlib>
 
 #include "chain_common.cuh"
 #include "chain_dw.cuh"
+#include "chain_obj_layout.cuh"
 #include "fields_common.cuh"
 
 namespace hn {
 namespace chain {
-
-// Packed operands of the object SDF net.  NT[l]: B(n = output feature, k = input feature) for
-// a @ W_l^T (value trunk, tangent sweep); NN[l]: B(n = input feature, k = output feature) for
-// d @ W_l (normal sweep, reverse sweep).  The output layer is packed without its sdf row (row 0),
-// which is applied as a rank-one term by the epilogues.
-struct ObjLayout {
-    uint32_t nt_off[9], nn_off[9];
-    uint32_t nt16_off[9];         // a @ W_l^T operands again as fp16 (hi + lo) pairs: the forward value trunk
-    uint16_t nt_n[9], nn_n[9];
-    uint8_t nt_kb[9], nn_kb[9];
-    uint32_t total;
-};
-static ObjLayout obj_layout() {
-    ObjLayout L;
-    uint32_t off = 0;
-    for (int l = 0; l < 9; ++l) {
-        L.nt_n[l] = l == 3 ? 208 : 256;
-        L.nt_kb[l] = l == 0 ? 1 : 4;
-        L.nt_off[l] = off;
-        off += b_operand_bytes(L.nt_n[l], L.nt_kb[l]);
-    }
-    for (int l = 0; l < 9; ++l) {
-        L.nn_n[l] = l == 0 ? 64 : 256;
-        L.nn_kb[l] = 4;
-        L.nn_off[l] = off;
-        off += b_operand_bytes(L.nn_n[l], L.nn_kb[l]);
-    }
-    for (int l = 0; l < 9; ++l) {
-        L.nt16_off[l] = off;
-        off += b_operand_bytes(L.nt_n[l], L.nt_kb[l]);
-    }
-    L.total = off;
-    return L;
-}
 
 // ------------------------------------------------------------------------------------------------
 // epilogue helpers
@@ -611,8 +579,13 @@ static int check_chain_mlp(const hn_mlp_t* m) {
 static long long* g_prof = nullptr;   // set by hn_chain_set_prof (diagnostics)
 static int g_stagger_fwd = 5000, g_stagger_bwd = 8000;   // cycles per stagger slot (hn_chain_set_stagger)
 
+int launch_sdf_only_ts(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s);   // chain_ts.cu
+void set_prof_ts(long long* p);
+
 int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s) {
     HN_PROPAGATE(check_chain_mlp(m));
+    static const bool use_ts = getenv("HONERF_SDF_TS") ? atoi(getenv("HONERF_SDF_TS")) != 0 : true;   // default: activations in TMEM
+    if (use_ts) return launch_sdf_only_ts(m, pts, n, inv_scale, sdf, s);
     const ObjLayout L = obj_layout();
     SdfOnlyParams p;
     p.pts = pts; p.n = n; p.inv_scale = inv_scale; p.sdf = sdf;
@@ -863,6 +836,7 @@ int hn_chain_set_stagger(int fwd_cycles, int bwd_cycles) {
 
 int hn_chain_set_prof(void* buf) {
     chain::g_prof = reinterpret_cast<long long*>(buf);
+    chain::set_prof_ts(chain::g_prof);
     return HN_OK;
 }
 
@@ -890,6 +864,11 @@ int hn_sdf_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_byte
                                           dst + L.nn_off[l], s));
         HN_PROPAGATE(chain::launch_pack_b(m->W[l], m->ld[l], chain::pack_map(row0, 0), rows, in_d[l], L.nt_n[l], L.nt_kb[l],
                                           dst + L.nt16_off[l], s, true));
+        if (l < 8)
+            for (int h = 0; h < 2; ++h)
+                HN_PROPAGATE(chain::launch_pack_b(m->W[l], m->ld[l], chain::pack_map(128 * h, 0),
+                                                  std::max(0, std::min(128, rows - 128 * h)), in_d[l], 128, L.nt_kb[l],
+                                                  dst + L.nth_off[l][h], s, true));
     }
     return HN_OK;
 }
