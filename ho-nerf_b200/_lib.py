@@ -28,6 +28,13 @@ class hn_mlp_t(Structure):
                 ("chain_bytes", c_int64)]
 
 
+class hn_wn_job_t(Structure):
+    _fields_ = [("v", c_void_p), ("g", c_void_p), ("dW", c_void_p), ("W", c_void_p), ("WT", c_void_p),
+                ("dv", c_void_p), ("dg", c_void_p),
+                ("out_dim", c_int32), ("in_dim", c_int32), ("ld", c_int32), ("ldT", c_int32),
+                ("gap_at", c_int32), ("gap", c_int32), ("post_scale", c_float), ("pad_", c_int32)]
+
+
 class hn_mlp_grad_t(Structure):
     _fields_ = [("dW", c_void_p * HN_MAX_LAYERS),
                 ("db", c_void_p * HN_MAX_LAYERS)]
@@ -55,6 +62,8 @@ PROTOTYPES = {
     "hn_timing_collect_tags": (c_int, [POINTER(ctypes.c_double), POINTER(c_int64), c_int]),
     "hn_wn_pack": (c_int, [P, P, c_int, c_int, c_int, c_float, P, P, c_int, P]),
     "hn_wn_bwd": (c_int, [P, P, P, c_int, c_int, c_int, c_float, P, P, P]),
+    "hn_wn_pack_batch": (c_int, [POINTER(hn_wn_job_t), c_int, P]),
+    "hn_wn_bwd_batch": (c_int, [POINTER(hn_wn_job_t), c_int, P]),
     "hn_wn_pack_gap": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int, P]),
     "hn_wn_bwd_gap": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, P]),
     "hn_sdf_hand_stash_floats": (c_int64, [c_int64]),

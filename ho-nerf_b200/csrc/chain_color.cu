@@ -422,6 +422,7 @@ int hn_color_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_by
     using chain::PackMap;
     using chain::launch_pack_b;
     const int big = 1 << 30;
+    chain::pack_batch_begin();
     // a @ W^T operands: B(n = out, k = in)
     HN_PROPAGATE(launch_pack_b(m->W[0], m->ld[0], 0, chain::CIN_FEAT0, 256, 256, 256, 4, dst + L.nt0a, s));
     HN_PROPAGATE(launch_pack_b(m->W[0], m->ld[0], PackMap{0, big, 0, 0, chain::CIN_FEAT0, chain::CIN_NRM0}, 256, chain::ENC_DIM, 256, 2,
@@ -434,7 +435,7 @@ int hn_color_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_by
     HN_PROPAGATE(launch_pack_b(m->WT[0], m->ldT[0], chain::CIN_FEAT0, 0, 256, 256, 256, 4, dst + L.nn0a, s));
     HN_PROPAGATE(launch_pack_b(m->WT[0], m->ldT[0], PackMap{0, chain::CIN_FEAT0, chain::CIN_NRM0, 0, big, 0}, chain::ENC_DIM, 256, 128, 4,
                                dst + L.nn0b, s));
-    return HN_OK;
+    return chain::pack_batch_flush(s);
 }
 
 }  // extern "C"

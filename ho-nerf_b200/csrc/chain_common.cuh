@@ -354,6 +354,11 @@ inline int launch_pack_b(const float* src, int64_t ld, int row0, int col0, int r
                          uint8_t* dst, cudaStream_t stream) {
     return launch_pack_b(src, ld, pack_map(row0, col0), rows, cols, n_pad, kblocks, dst, stream);
 }
+// All operands of a net in ONE launch: launch_pack_b calls made between pack_batch_begin() and pack_batch_flush()
+// are only recorded (up to PACK_MAX_JOBS) and run as one kernel (blockIdx.y = operand).
+constexpr int PACK_MAX_JOBS = 48;
+void pack_batch_begin();
+int pack_batch_flush(cudaStream_t stream);
 
 }  // namespace chain
 }  // namespace hn

@@ -851,6 +851,7 @@ int hn_sdf_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_byte
     static const int out_d[9] = {256, 256, 256, 193, 256, 256, 256, 256, 257};
     cudaStream_t s = (cudaStream_t)stream;
     uint8_t* dst = reinterpret_cast<uint8_t*>(chain_buf);
+    chain::pack_batch_begin();
     for (int l = 0; l < 9; ++l) {
         HN_REQUIRE(m->in_dim[l] == in_d[l] && m->out_dim[l] == out_d[l] && m->W[l] && m->WT[l],
                    "hn_sdf_obj_chain_pack: layer %d has the wrong shape or no transposed copy", l);
@@ -870,7 +871,7 @@ int hn_sdf_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_byte
                                                   std::max(0, std::min(128, rows - 128 * h)), in_d[l], 128, L.nt_kb[l],
                                                   dst + L.nth_off[l][h], s, true));
     }
-    return HN_OK;
+    return chain::pack_batch_flush(s);
 }
 
 }  // extern "C"

@@ -1,4 +1,5 @@
 // Library runtime: error text, launch counter, device info, weight-norm pack/backward, column sums.
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <vector>
@@ -116,6 +117,57 @@ __global__ void wn_bwd_kernel(const float* __restrict__ v, const float* __restri
     for (int k = lane; k < in_dim; k += 32) dvr[k] = gn * (post_scale * dr[packed_col(k, gap_at, gap)] - coef * vr[k]);
 }
 
+// ---- all layers of a net in one launch --------------------------------------------------------------------
+struct WnJobs {
+    int n;
+    hn_wn_job_t job[HN_MAX_LAYERS];
+};
+// one warp per output row; blockIdx.y = layer
+__global__ void wn_pack_batch_kernel(const __grid_constant__ WnJobs jobs) {
+    const hn_wn_job_t& j = jobs.job[blockIdx.y];
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= j.ldT && row >= j.out_dim) return;
+    if (row >= j.out_dim) {
+        if (j.WT && row < j.ldT)
+            for (int k = lane; k < j.in_dim + j.gap; k += 32) j.WT[(int64_t)k * j.ldT + row] = 0.0f;
+        return;
+    }
+    const float* vr = j.v + (int64_t)row * j.in_dim;
+    float ss = 0.0f;
+    for (int k = lane; k < j.in_dim; k += 32) ss = fmaf(vr[k], vr[k], ss);
+    ss = warp_sum(ss);
+    const float sc = j.post_scale * (j.g[row] / sqrtf(ss));
+    float* wr = j.W + (int64_t)row * j.ld;
+    for (int k = lane; k < j.ld; k += 32) {
+        const int src = k < j.gap_at ? k : k - j.gap;
+        const bool live = (k < j.gap_at || k >= j.gap_at + j.gap) && src < j.in_dim;
+        const float w = live ? vr[src] * sc : 0.0f;
+        wr[k] = w;
+        if (j.WT && k < j.in_dim + j.gap) j.WT[(int64_t)k * j.ldT + row] = w;
+    }
+}
+__global__ void wn_bwd_batch_kernel(const __grid_constant__ WnJobs jobs) {
+    const hn_wn_job_t& j = jobs.job[blockIdx.y];
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= j.out_dim) return;
+    const float* vr = j.v + (int64_t)row * j.in_dim;
+    const float* dr = j.dW + (int64_t)row * j.ld;
+    float ss = 0.0f, dot = 0.0f;
+    for (int k = lane; k < j.in_dim; k += 32) {
+        ss = fmaf(vr[k], vr[k], ss);
+        dot = fmaf(dr[packed_col(k, j.gap_at, j.gap)], vr[k], dot);
+    }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot) * j.post_scale;
+    const float nrm = sqrtf(ss);
+    const float gn = j.g[row] / nrm;
+    if (lane == 0) j.dg[row] = dot / nrm;
+    const float coef = dot / ss;
+    float* dvr = j.dv + (int64_t)row * j.in_dim;
+    for (int k = lane; k < j.in_dim; k += 32)
+        dvr[k] = gn * (j.post_scale * dr[packed_col(k, j.gap_at, j.gap)] - coef * vr[k]);
+}
+
 // ---- column sums -----------------------------------------------------------------------------
 // block = 32 columns x 8 row lanes; grid.y splits the rows
 __global__ void colsum_kernel(const float* __restrict__ X, int64_t ldx, int64_t rows, int cols,
@@ -195,6 +247,43 @@ int hn_timing_collect_tags(double* ms_per_tag, int64_t* launches_per_tag, int n_
             if (launches_per_tag) launches_per_tag[t] += 1;
         }
     }
+    return HN_OK;
+}
+
+int hn_wn_pack_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream) {
+    HN_REQUIRE(jobs && n >= 1 && n <= HN_MAX_LAYERS, "hn_wn_pack_batch: bad job list");
+    WnJobs w;
+    w.n = n;
+    int max_rows = 0;
+    for (int i = 0; i < n; ++i) {
+        const hn_wn_job_t& j = jobs[i];
+        HN_REQUIRE(j.v && j.g && j.W && j.out_dim > 0 && j.in_dim > 0 && j.gap >= 0 && j.gap_at >= 0 && j.gap_at <= j.in_dim &&
+                       j.ld >= j.in_dim + j.gap, "hn_wn_pack_batch: bad arguments for layer %d", i);
+        HN_REQUIRE(!j.WT || j.ldT >= j.out_dim, "hn_wn_pack_batch: ldT too small for layer %d", i);
+        w.job[i] = j;
+        max_rows = std::max(max_rows, std::max(j.out_dim, j.WT ? j.ldT : 0));
+    }
+    wn_pack_batch_kernel<<<dim3((unsigned)ceil_div((int64_t)max_rows * 32, 256), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(w);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hn_wn_bwd_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream) {
+    HN_REQUIRE(jobs && n >= 1 && n <= HN_MAX_LAYERS, "hn_wn_bwd_batch: bad job list");
+    WnJobs w;
+    w.n = n;
+    int max_rows = 0;
+    for (int i = 0; i < n; ++i) {
+        const hn_wn_job_t& j = jobs[i];
+        HN_REQUIRE(j.v && j.g && j.dW && j.dv && j.dg && j.out_dim > 0 && j.in_dim > 0 && j.ld >= j.in_dim + j.gap,
+                   "hn_wn_bwd_batch: bad arguments for layer %d", i);
+        w.job[i] = j;
+        max_rows = std::max(max_rows, j.out_dim);
+    }
+    wn_bwd_batch_kernel<<<dim3((unsigned)ceil_div((int64_t)max_rows * 32, 256), (unsigned)n), 256, 0, (cudaStream_t)stream>>>(w);
+    count_launch();
+    HN_CHECK_LAUNCH();
     return HN_OK;
 }
 

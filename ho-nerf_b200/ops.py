@@ -104,20 +104,24 @@ class PackedMLP:
         st = hn_mlp_t()
         st.n_layers = len(self.layers)
         keep = []
+        jobs = (_lib.hn_wn_job_t * len(self.layers))()
         for l, (g, v, b) in enumerate(self.layers):
             gd, vd, bd = _f32c(g.detach()), _f32c(v.detach()), _f32c(b.detach())
             keep.append((gd, vd, bd))
             i, o = self.dims[l]
             Wl = self.W[self.offsets[l]: self.offsets[l] + o * self.lds[l]]
             WTl = self.WT[self.offsetsT[l]: self.offsetsT[l] + i * self.ldTs[l]]
-            check(lib.hn_wn_pack_gap(_ptr(vd), _ptr(gd), o, self.raw_in[l], self.lds[l], self.post_scales[l],
-                                     self.gaps[l][0], self.gaps[l][1], _ptr(Wl), _ptr(WTl), self.ldTs[l],
-                                     _stream(vd)), "hn_wn_pack")
+            j = jobs[l]
+            j.v, j.g, j.W, j.WT = vd.data_ptr(), gd.data_ptr(), Wl.data_ptr(), WTl.data_ptr()
+            j.out_dim, j.in_dim, j.ld, j.ldT = o, self.raw_in[l], self.lds[l], self.ldTs[l]
+            j.gap_at, j.gap, j.post_scale = self.gaps[l][0], self.gaps[l][1], self.post_scales[l]
             st.in_dim[l], st.out_dim[l], st.ld[l] = i, o, self.lds[l]
             st.W[l] = Wl.data_ptr()
             st.WT[l] = WTl.data_ptr()
             st.ldT[l] = self.ldTs[l]
             st.b[l] = bd.data_ptr()
+        # every layer's g * v / ||v|| (and its transposed copy) in one launch
+        check(lib.hn_wn_pack_batch(jobs, len(self.layers), _stream(self.W)), "hn_wn_pack_batch")
         if self.chain_kind is not None:
             size_fn, pack_fn = {"sdf_obj": (lib.hn_sdf_obj_chain_bytes, lib.hn_sdf_obj_chain_pack),
                                 "color_obj": (lib.hn_color_obj_chain_bytes, lib.hn_color_obj_chain_pack)}[self.chain_kind]
@@ -135,8 +139,14 @@ class PackedMLP:
     def new_grad(self):
         """Zeroed packed gradient buffers + the struct pointing at them."""
         dev = self.W.device
-        dW = torch.zeros(self.total, device=dev, dtype=torch.float32)
-        db = [torch.zeros(o, device=dev, dtype=torch.float32) for (_, o) in self.dims]
+        # ONE zero-filled allocation (one fill kernel) carved into the packed dW and the per-layer db
+        n_b = sum(_round4(o) for (_, o) in self.dims)
+        flat = torch.zeros(self.total + n_b, device=dev, dtype=torch.float32)
+        dW = flat[:self.total]
+        db, off = [], self.total
+        for (_, o) in self.dims:
+            db.append(flat[off:off + o])
+            off += _round4(o)
         gs = hn_mlp_grad_t()
         for l in range(len(self.layers)):
             gs.dW[l] = dW[self.offsets[l]:].data_ptr()
@@ -147,15 +157,18 @@ class PackedMLP:
         """(dg, dv, db) per layer from packed dW via hn_wn_bwd.  Returns a flat list in the order
         of ``flat_params``."""
         out = []
+        jobs = (_lib.hn_wn_job_t * len(self._keep))()
         for l, (gd, vd, bd) in enumerate(self._keep):
             i, o = self.dims[l]
             dv = torch.empty_like(vd)
             dg = torch.empty(o, 1, device=vd.device, dtype=torch.float32)
             dWl = dW[self.offsets[l]: self.offsets[l] + o * self.lds[l]]
-            check(lib.hn_wn_bwd_gap(_ptr(vd), _ptr(gd), _ptr(dWl), o, self.raw_in[l], self.lds[l],
-                                    self.post_scales[l], self.gaps[l][0], self.gaps[l][1], _ptr(dv), _ptr(dg),
-                                    _stream(vd)), "hn_wn_bwd")
+            j = jobs[l]
+            j.v, j.g, j.dW, j.dv, j.dg = vd.data_ptr(), gd.data_ptr(), dWl.data_ptr(), dv.data_ptr(), dg.data_ptr()
+            j.out_dim, j.in_dim, j.ld = o, self.raw_in[l], self.lds[l]
+            j.gap_at, j.gap, j.post_scale = self.gaps[l][0], self.gaps[l][1], self.post_scales[l]
             out += [dg, dv, db[l]]
+        check(lib.hn_wn_bwd_batch(jobs, len(self._keep), _stream(dW)), "hn_wn_bwd_batch")
         return out
 
     def flat_params(self):

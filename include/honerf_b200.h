@@ -106,6 +106,24 @@ HN_API int hn_wn_bwd_gap(const float* v, const float* g, const float* dW, int ou
 HN_API int hn_wn_bwd(const float* v, const float* g, const float* dW, int out_dim, int in_dim,
                      int ld, float post_scale, float* dv, float* dg, hn_stream_t stream);
 
+/* All layers of a net in ONE launch each (the per-layer entry points above cost a launch per layer and step).
+ * jobs is a HOST array of n <= HN_MAX_LAYERS entries; pack uses {v, g, out_dim, in_dim, ld, post_scale, gap_at,
+ * gap, W, WT, ldT}, bwd uses {v, g, dW, out_dim, in_dim, ld, post_scale, gap_at, gap, dv, dg}. */
+typedef struct hn_wn_job {
+    const float* v;
+    const float* g;
+    const float* dW;
+    float* W;
+    float* WT;
+    float* dv;
+    float* dg;
+    int32_t out_dim, in_dim, ld, ldT, gap_at, gap;
+    float post_scale;
+    int32_t pad_;
+} hn_wn_job_t;
+HN_API int hn_wn_pack_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream);
+HN_API int hn_wn_bwd_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Object SDF field: SDFNetwork_OBJ.forward / .sdf / .gradient (utils/fields.py:316-347) as ONE
  * operator (value + feature + analytic normal) with a hand-written second-order backward.
