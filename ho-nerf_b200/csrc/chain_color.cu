@@ -94,20 +94,29 @@ color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t gp = tile * TILE_M + row;
             const bool live = gp < p.n;
-            // ---- A <- feature columns (and their tiled copy for the backward) ------------------------------
+            // ---- A <- feature columns (and their tiled copy for the backward).  A plain copy of row-major rows, so the
+            // threads are mapped for coalescing: consecutive threads take consecutive float4 of a row.
             {
                 float* __restrict__ ft = p.FEAT + tile * TILE_FLOATS;
-#pragma unroll
-                for (int j = 0; j < EPI_COLS; j += 8) {
-                    const int col = cg * EPI_COLS + j;
-                    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (live) {
-                        const float4 a = ld4(p.feat + gp * p.ld_feat + col), b = ld4(p.feat + gp * p.ld_feat + col + 4);
-                        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-                        st4(ft + toff(row, col), a);
-                        st4(ft + toff(row, col + 4), b);
+                // a warp takes 8 rows x 4 float4: the row-major loads are 64-byte segments, the tiled stores 128-byte ones
+                const int ew = (threadIdx.x - 64) >> 5, ln = threadIdx.x & 31;
+#pragma unroll 4
+                for (int it = 0; it < 16; ++it) {
+                    const int b = it * EPI_WARPS + ew;           // 256 blocks of 8 rows x 16 columns
+                    const int r = (b >> 4) * 8 + (ln & 7), c = ((b & 15) * 4 + (ln >> 3)) * 4;
+                    const int64_t g = tile * TILE_M + r;
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (g < p.n) {
+                        a = ld4(p.feat + g * p.ld_feat + c);
+                        st4(ft + toff(r, c), a);
                     }
-                    a_store8(smem, row, col, f);
+                    uint2 hi, lo;
+                    split2(a.x, a.y, hi.x, lo.x);
+                    split2(a.z, a.w, hi.y, lo.y);
+                    const uint32_t off = (uint32_t)(c >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)r, (uint32_t)((c & 63) >> 3)) +
+                                         (uint32_t)(c & 4) * 2u;
+                    *reinterpret_cast<uint2*>(smem + off) = hi;
+                    *reinterpret_cast<uint2*>(smem + A_LO_OFF + off) = lo;
                 }
             }
             epi_publish_a(&bar);

@@ -230,6 +230,7 @@ __device__ __forceinline__ void mma_loop(const Program& prog, uint8_t* smem, Bar
             tt = clock64();
             tc::mbar_wait(&bar->a_ready, a_par);
             t_a += clock64() - tt;
+            if (prof) prof[148 * 4 + blockIdx.x * 32 + s] += clock64() - tt;      // per-step epilogue wait
             a_par ^= 1u;
             tc::tc_fence_after_sync();
             for (int kb = 0; kb < st.kblocks; ++kb) {

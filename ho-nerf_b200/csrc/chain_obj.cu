@@ -236,14 +236,23 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                     }
                 }
                 if (l == 3) {
-                    if (cg == EPI_CGROUPS - 1) {
+                    // skip input, columns 192..255 = [h3[192], e_0 .. e_62]: 16 per column group, vector stores; e comes
+                    // back from the fp32 encoding stash written at the start of the tile (no second sincosf)
+                    const int c0 = 192 + cg * 16;
+                    float tl[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) tl[j] = (live && c0 + j >= 193) ? p.E[gp * 64 + c0 + j - 193] : 0.0f;
+                    if (cg == 0) {
                         float v[32];
                         acc_load32(tmem, row, 192, v);
-                        const float h = softplus100_fast(v[0] + __ldg(bias + 192));
-                        a_store1<true>(smem, row, 192, h);
-                        if (live) ht[toff(row, 192)] = h;
+                        tl[0] = softplus100_fast(v[0] + __ldg(bias + 192));
                     }
-                    write_encoding<true>(smem, row, cg, x, 193, live ? ht : nullptr, true);
+                    a_store8<true>(smem, row, c0, tl);
+                    a_store8<true>(smem, row, c0 + 8, tl + 8);
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) st4(ht + toff(row, c0 + j), make_float4(tl[j], tl[j + 1], tl[j + 2], tl[j + 3]));
+                    }
                 }
                 epi_publish_a(&bar);
             }
@@ -300,19 +309,20 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                         const float4 h = aux[0][q];
                         float d[4] = {v[j] * sprime_fast(h.x), v[j + 1] * sprime_fast(h.y), v[j + 2] * sprime_fast(h.z),
                                       v[j + 3] * sprime_fast(h.w)};
+                        float g4[4] = {d[0], d[1], d[2], d[3]};
                         if (l == 4 && col0 + j + 3 > 192) {
-                            // columns 193..255 of the skip layer's input are the encoding: their cotangent goes to EB
+                            // columns 193..255 of the skip layer's input are the encoding: their cotangent (the raw product)
+                            // rides in the otherwise unused columns 193..255 of the D_3 tile until the last step
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int col = col0 + j + i;
-                                if (col > 192) {
-                                    if (live) p.EB[gp * 64 + col - 193] = v[j + i];
+                                if (col0 + j + i > 192) {
+                                    g4[i] = v[j + i];
                                     d[i] = 0.0f;
                                 }
                             }
                         }
                         v[j] = d[0]; v[j + 1] = d[1]; v[j + 2] = d[2]; v[j + 3] = d[3];
-                        if (live) st4(dt + toff(row, col0 + j), make_float4(d[0], d[1], d[2], d[3]));
+                        if (live) st4(dt + toff(row, col0 + j), make_float4(g4[0], g4[1], g4[2], g4[3]));
                     }
                     a_store8(smem, row, col0, v);
                 });
@@ -325,12 +335,15 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                 tc::tmem_ld_32x32b_x16(tmem + ((uint32_t)(row & ~31) << 16) + (uint32_t)(cg * 16), v);
                 tc::tmem_ld_wait();
                 if (live) {
+                    const float* __restrict__ d3 = p.D[3] + tile * TILE_FLOATS;      // skip part: columns 193 + j
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const int col = cg * 16 + j;
-                        float4 e = ld4(p.EB + gp * 64 + col);
-                        e.x += v[j]; e.y += v[j + 1]; e.z += v[j + 2];
-                        e.w = col + 3 == 63 ? 0.0f : e.w + v[j + 3];
+                        float4 e;
+                        e.x = v[j] + d3[toff(row, 193 + col)];
+                        e.y = v[j + 1] + d3[toff(row, 194 + col)];
+                        e.z = v[j + 2] + d3[toff(row, 195 + col)];
+                        e.w = col + 3 == 63 ? 0.0f : v[j + 3] + d3[toff(row, 196 + col)];
                         st4(p.EB + gp * 64 + col, e);
                     }
                 }
@@ -467,32 +480,49 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                     if (l < 7) a_store8(smem, row, col0, v);
                 });
                 if (l == 3) {
-                    if (cg == EPI_CGROUPS - 1) {
+                    // tangent of the skip input, columns 192..255 = [u3[192], ue_0 .. ue_62]: 16 per column group; ue comes
+                    // back from the workspace written at the start of the tile
+                    const int c0 = 192 + cg * 16;
+                    float tl[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) tl[j] = (live && c0 + j >= 193) ? p.UE[gp * 64 + c0 + j - 193] : 0.0f;
+                    if (cg == 0) {
                         float v[32];
                         acc_load32(tmem, row, 192, v);
-                        float u = 0.f, xv = 0.f;
+                        float u = 0.f;
                         if (live) {
                             const float em = ex2_approx(-144.26950408889634f * ht[toff(row, 192)]);
                             u = (1.0f - em) * v[0];
-                            xv = 100.0f * em * dt[toff(row, 192)] * v[0];
-                            ut[toff(row, 192)] = u;
-                            xt[toff(row, 192)] = xv;
+                            xt[toff(row, 192)] = 100.0f * em * dt[toff(row, 192)] * v[0];
                         }
-                        a_store1(smem, row, 192, u);
+                        tl[0] = u;
                     }
-                    write_ue(193, ut, true);
+                    a_store8(smem, row, c0, tl);
+                    a_store8(smem, row, c0 + 8, tl + 8);
+                    if (live) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) st4(ut + toff(row, c0 + j), make_float4(tl[j], tl[j + 1], tl[j + 2], tl[j + 3]));
+                    }
                 }
                 if (l == 7) {
-                    // A operand of the output layer's reverse step: d_feat
-#pragma unroll
-                    for (int j = 0; j < EPI_COLS; j += 8) {
-                        const int col = cg * EPI_COLS + j;
-                        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        if (live && p.d_feat) {
-                            const float4 a = ld4(p.d_feat + gp * p.ld_dfeat + col), b = ld4(p.d_feat + gp * p.ld_dfeat + col + 4);
-                            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-                        }
-                        a_store8(smem, row, col, f);
+                    // A operand of the output layer's reverse step: the tile's rows of d_feat (row-major).  A plain copy, so
+                    // the threads are re-mapped for coalescing: consecutive threads take consecutive float4 of a row.
+                    tc::named_bar_sync(1, EPI_THREADS);        // every thread is done with its own A stores of this step
+                    const int et = threadIdx.x - 64;
+#pragma unroll 4
+                    for (int it = 0; it < TILE_M * 64 / EPI_THREADS; ++it) {
+                        const int idx = it * EPI_THREADS + et;
+                        const int r = idx >> 6, c = (idx & 63) * 4;
+                        const int64_t g = tile * TILE_M + r;
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (g < p.n && p.d_feat) a = ld4(p.d_feat + g * p.ld_dfeat + c);
+                        uint2 hi, lo;
+                        split2(a.x, a.y, hi.x, lo.x);
+                        split2(a.z, a.w, hi.y, lo.y);
+                        const uint32_t off = (uint32_t)(c >> 6) * KB_BYTES + tc::sw128_offset((uint32_t)r, (uint32_t)((c & 63) >> 3)) +
+                                             (uint32_t)(c & 4) * 2u;
+                        *reinterpret_cast<uint2*>(smem + off) = hi;
+                        *reinterpret_cast<uint2*>(smem + A_LO_OFF + off) = lo;
                     }
                 }
                 epi_publish_a(&bar);
@@ -515,18 +545,19 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                         }
                         float dz[4] = {sprime_fast(h.x) * da[0] + xq.x, sprime_fast(h.y) * da[1] + xq.y,
                                        sprime_fast(h.z) * da[2] + xq.z, sprime_fast(h.w) * da[3] + xq.w};
+                        float g4[4] = {dz[0], dz[1], dz[2], dz[3]};
                         if (l == 4 && col0 + j + 3 > 192) {
+                            // cotangent of the encoding part of the skip input: kept in the unused columns of the DZ_3 tile
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const int col = col0 + j + i;
-                                if (col > 192) {
-                                    if (live) p.DE[gp * 64 + col - 193] = da[i];
+                                if (col0 + j + i > 192) {
+                                    g4[i] = da[i];
                                     dz[i] = 0.0f;
                                 }
                             }
                         }
                         v[j] = dz[0]; v[j + 1] = dz[1]; v[j + 2] = dz[2]; v[j + 3] = dz[3];
-                        if (live) st4(zt + toff(row, col0 + j), make_float4(dz[0], dz[1], dz[2], dz[3]));
+                        if (live) st4(zt + toff(row, col0 + j), make_float4(g4[0], g4[1], g4[2], g4[3]));
                     }
                     a_store8(smem, row, col0, v);
                 });
@@ -539,12 +570,15 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                 tc::tmem_ld_32x32b_x16(tmem + ((uint32_t)(row & ~31) << 16) + (uint32_t)(cg * 16), v);
                 tc::tmem_ld_wait();
                 if (live) {
+                    const float* __restrict__ z3 = p.DZ[3] + tile * TILE_FLOATS;     // skip part: columns 193 + j
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const int col = cg * 16 + j;
-                        float4 e = ld4(p.DE + gp * 64 + col);
-                        e.x += v[j]; e.y += v[j + 1]; e.z += v[j + 2];
-                        e.w = col + 3 == 63 ? 0.0f : e.w + v[j + 3];
+                        float4 e;
+                        e.x = v[j] + z3[toff(row, 193 + col)];
+                        e.y = v[j + 1] + z3[toff(row, 194 + col)];
+                        e.z = v[j + 2] + z3[toff(row, 195 + col)];
+                        e.w = col + 3 == 63 ? 0.0f : v[j + 3] + z3[toff(row, 196 + col)];
                         st4(p.DE + gp * 64 + col, e);
                     }
                 }
@@ -577,7 +611,7 @@ static int check_chain_mlp(const hn_mlp_t* m) {
 }
 
 static long long* g_prof = nullptr;   // set by hn_chain_set_prof (diagnostics)
-static int g_stagger_fwd = 5000, g_stagger_bwd = 8000;   // cycles per stagger slot (hn_chain_set_stagger)
+static int g_stagger_fwd = 0, g_stagger_bwd = 0;   // cycles per stagger slot (hn_chain_set_stagger); measured: no effect
 
 int launch_sdf_only_ts(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s);   // chain_ts.cu
 void set_prof_ts(long long* p);

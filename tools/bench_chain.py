@@ -96,7 +96,7 @@ def prof_fwd_bwd():
     x = (0.45 * torch.randn(n, 3)).cuda().requires_grad_(True)
     gs, gf, gn = torch.randn(n, 1).cuda(), torch.randn(n, 256).cuda(), torch.randn(n, 3).cuda()
     p = H.ops._PRECISIONS["tc_bf16x3"]
-    buf = torch.zeros(148 * 4, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(148 * 4 + 148 * 32, dtype=torch.int64, device="cuda")
     for which in ("fwd", "bwd"):
         s, f, nn = H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p)
         torch.autograd.backward([s, f, nn], [gs, gf, gn])
@@ -115,7 +115,10 @@ def prof_fwd_bwd():
             torch.autograd.backward([s, f, nn], [gs, gf, gn])
             torch.cuda.synchronize()
             H._lib.lib.hn_chain_set_prof(None)
-        b = buf.reshape(148, 4).double().cpu()
+        b = buf[:148 * 4].reshape(148, 4).double().cpu()
+        per_step = buf[148 * 4:].reshape(148, 32).double().cpu()
+        tl = torch.tensor([4.0 if i < 68 else 3.0 for i in range(148)], dtype=torch.float64)
+        print(which, "wait for the epilogue BEFORE step s (cycles per tile):", [int(x) for x in (per_step / tl[:, None]).mean(0)[:18].tolist()])
         tiles = torch.tensor([4.0 if i < 68 else 3.0 for i in range(148)], dtype=torch.float64)
         steps = tiles * 17
         print("%s chain kernel, per layer-tile cycles (mean over CTAs): total %.0f  MMA-warp waits for epilogue %.0f  for weights %.0f  issue+rest %.0f; max CTA total %.0f cycles"
