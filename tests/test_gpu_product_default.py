@@ -61,3 +61,33 @@ def test_sdf_grid_vs_golden_with_default_precision():
 def test_smoke_entry_point():
     import __graft_entry__ as E
     E.smoke()
+
+
+def test_hand_field_and_fitting_renderer_with_default_precision():
+    """The hand nets have no chain kernels yet: under the default precision their contractions run on the per-layer
+    tcgen05 kernels with split TF32 operands (HN_TC_BF16X3 -> HN_TC_TF32X3 in gemm_dispatch.cuh).  Hand SDF / colour vs
+    the reference's golden vectors (relative bounds, see test_gpu_hand.py) and one two-field fitting render + backward."""
+    import honerf_b200 as H
+    import ref_conf
+    from golden_util import rel_l2
+    from gpu_util import hand_modules
+    g = load_golden("hand_fields")
+    c = cases.hand_fields_case()
+    hs, hc, hd, _, _ = hand_modules()
+    pts, bt, T = c["pts"].to(DEV), c["bt_inv"].to(DEV), c["T_pose_21"].to(DEV)
+    out, xyz, _, _ = hs(pts, bt, T)
+    n = hs.gradient(pts, bt, T).squeeze(1)
+    assert max_abs(xyz, g["xyz_feature"]) < 2e-4 and max_abs(out, g["sdf_out"]) < 1e-3
+    assert rel_l2(n, g["gradient"]) < 1e-2
+    assert max_abs(hc(None, xyz, out[:, 1:], None, n, 0), g["rgb"]) < 2e-3
+    # two-field renderer: hand (per-layer TF32x3) + object (chain kernels) in one render, gradients to the poses
+    os_, oc, od, _, _ = obj_modules()
+    r = H.renderer.NeuSRenderer_fitting(hs, hd, hc, os_, od, oc, **ref_conf.RENDERER_CONF)
+    fc = cases.fit_render_case()
+    R = fc["R"]
+    btg = fc["bt_inv"].to(DEV).requires_grad_(True)
+    Ro, To = fc["Ro"].to(DEV).requires_grad_(True), fc["To"].to(DEV).requires_grad_(True)
+    o = r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), R["near"], R["far"], btg, fc["T_pose_21"].to(DEV), None, Ro, To)
+    cases.fit_loss(o, fc["true_rgb"].to(DEV)).backward()
+    assert torch.isfinite(o["color_fine"]).all() and o["color_fine"].shape == (10, 3)
+    assert torch.isfinite(btg.grad).all() and torch.isfinite(Ro.grad).all() and float(btg.grad.abs().max()) > 0
