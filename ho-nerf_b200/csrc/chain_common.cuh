@@ -82,11 +82,12 @@ __device__ __forceinline__ int toff(int row, int col) { return (col >> 2) * 512 
 
 // ---- bf16 hi/lo split ------------------------------------------------------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    float2 hf = __bfloat1622float2(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+    // written out so that widening hi back to fp32 is one shift / one mask (the bf162 intrinsics cost two more per pair)
+    uint32_t h;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));      // low half = a, high half = b
+    const float ah = __uint_as_float(h << 16), bh = __uint_as_float(h & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+    hi = h;
 }
 // fp16 pair: hi = fp16(x), lo = fp16(x - hi)
 __device__ __forceinline__ void split2_lo16(float a, float b, uint32_t& hi, uint32_t& lo) {

@@ -2,8 +2,10 @@
 //     dW_l = sum over points of  P_a[p,:]^T Q_a[p,:]  (+ P_b[p,:]^T Q_b[p,:])
 // for ALL layers of a network in ONE launch.  The reduction dimension is the point index, so both
 // operands are consumed "MN-major" (feature index contiguous) exactly as the chain kernels leave them in
-// HBM: fp32 rows are split into bf16 hi + lo while being staged into shared memory (three MMAs per
-// product, fp32 accumulation in TMEM: 2 x [128 x 256] accumulators = all 512 TMEM columns).
+// HBM.  Every staging thread runs its own cp.async pipeline (fp32 pieces land in a private shared-memory
+// slot several stages ahead, so HBM latency is never exposed and no registers are held across it), then
+// splits its values into bf16 hi + lo in the UMMA operand tiles (three MMAs per product, fp32
+// accumulation in TMEM: 2 x [128 x 256] accumulators = all 512 TMEM columns).
 // A CTA owns one (layer, point-range) pair; partial sums go to a workspace and a second kernel adds them
 // into the packed gradient (no fp32 atomics on the 65 536-element tiles).  Bias gradients (column sums of
 // the first operand) are accumulated by the staging threads on the way.
@@ -17,14 +19,16 @@ namespace chain {
 
 constexpr int DW_SWARPS = 16;            // staging / epilogue warps
 constexpr int DW_THREADS = DW_SWARPS * 32 + 32;   // + 1 MMA warp
-constexpr int DW_CPW = 32 / DW_SWARPS;   // 8-feature chunks per warp and operand
-constexpr int DW_KP = 32;                // points per stage
-constexpr int DW_OPER_BYTES = 256 * DW_KP * 2;        // one bf16 matrix of a stage: 16 KB
+constexpr int DW_KP = 16;                // points per stage (one UMMA K step)
+constexpr int DW_OPER_BYTES = 256 * DW_KP * 2;        // one bf16 matrix of a stage: 8 KB
 constexpr int DW_STAGE_BYTES = 4 * DW_OPER_BYTES;     // P_hi, P_lo, Q_hi, Q_lo
 constexpr int DW_STAGES = 3;
-constexpr int DW_SMEM_BYTES = DW_STAGES * DW_STAGE_BYTES + 1024;
-constexpr int DW_SBO = 1024;             // next group of 8 points
-constexpr int DW_LBO = 4 * 1024;         // next block of 64 features
+constexpr int DW_RAW_SLOTS = 4;          // fp32 landing slots of the per-thread cp.async pipeline
+constexpr int DW_RAW_BYTES = 4 * DW_SWARPS * 32 * 16; // 4 x 16 bytes per staging thread: 32 KB
+constexpr int DW_SMEM_BYTES = DW_STAGES * DW_STAGE_BYTES + DW_RAW_SLOTS * DW_RAW_BYTES + 1024;
+constexpr int DW_SBO = 1024;                     // next group of 8 points
+constexpr int DW_LBO = (DW_KP / 8) * 1024;       // next block of 64 features
+static_assert(DW_KP * 32 == DW_SWARPS * 32, "one (point, 8-feature chunk) pair of each operand per staging thread");
 
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -40,45 +44,78 @@ __host__ __device__ constexpr uint32_t make_idesc_mn(uint32_t M, uint32_t N) {
            ((M >> 4) << 24);
 }
 
-// element address (floats) of (point p, column c) in the tiled stash layout
-__host__ __device__ __forceinline__ int64_t tiled_off(int64_t p, int c) {
-    return ((p >> 7) * 64 + (c >> 2)) * 512 + (p & 127) * 4 + (c & 3);
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ void load8(const DwOperand& op, int64_t p, int64_t n, int fc, float* v) {
+// Per-thread view of one operand: the thread owns columns [8 fc, 8 fc + 8) of point k of every 16-point group, read
+// as two 16-byte pieces.  The source pointer only ever advances by constant strides, so issuing a stage costs a
+// handful of instructions whatever the operand's layout.
+struct DwStream {
+    const float* ptr;      // piece 0 of the next group to fetch
+    int step;              // floats to the next 16-point group
+    uint32_t flags;        // bit 0 / 1: piece 0 / 1 holds operand columns; bit 2: tiled layout; bits 4..7: valid columns
+
+    __device__ __forceinline__ void init(const DwOperand& op, int tile0, int k, int fc) {
+        const int c = fc * 8;
+        const int n_valid = max(0, min(8, op.cols - c));
+        flags = (n_valid > 0 ? 1u : 0u) | (n_valid > 4 ? 2u : 0u) | ((uint32_t)n_valid << 4);
+        if (n_valid == 0) {                 // nothing to read: keep a valid address and never move
+            ptr = op.ptr; step = 0;
+        } else if (op.tiled) {
+            ptr = op.ptr + ((int64_t)tile0 * 64 + fc * 2) * 512 + k * 4;
+            step = DW_KP * 4;
+            flags |= 4u;
+        } else {
+            ptr = op.ptr + ((int64_t)tile0 * TILE_M + k) * op.ld + c;
+            step = DW_KP * (int)op.ld;
+        }
+    }
+    // start fetching the next group (`live`: the point exists; `last`: it is the last group of a 128-point tile)
+    __device__ __forceinline__ void fetch(bool live, bool last, uint32_t dst0, uint32_t dst1) {
+        const bool tiled = (flags & 4u) != 0u;
+        cp_async16(dst0, ptr, (live && (flags & 1u)) ? 16u : 0u);
+        cp_async16(dst1, ptr + ((flags & 2u) ? (tiled ? 512 : 4) : 0), (live && (flags & 2u)) ? 16u : 0u);
+        ptr += step + ((tiled && last) ? 64 * 512 - 512 : 0);
+    }
+    __device__ __forceinline__ void take(uint32_t src0, uint32_t src1, float* v) const {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(src0) : "memory");
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(src1) : "memory");
+        const int n_valid = (int)(flags >> 4);
+        if (n_valid < 8) {       // columns past the operand inside a fetched piece
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i >= n_valid) v[i] = 0.0f;
+        }
+    }
+};
+__device__ __forceinline__ bool dw_unaligned(const DwOperand& op) {
+    return !op.tiled && (((op.ld & 3) | (int)(reinterpret_cast<uintptr_t>(op.ptr) & 15)) != 0);
+}
+// synchronous scalar read of a chunk (operands that cannot be fetched in aligned 16-byte pieces)
+__device__ __forceinline__ void load8_scalar(const DwOperand& op, int64_t pnt, int64_t n, int fc, float* v) {
     const int c = fc * 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-    if (p >= n || c >= op.cols) return;
-    if (op.tiled) {
-        const float4 a = ld4(op.ptr + tiled_off(p, c));
-        const float4 b = ld4(op.ptr + tiled_off(p, c + 4));
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else if ((op.ld & 3) == 0 && c + 8 <= op.cols) {
-        const float4 a = ld4(op.ptr + p * op.ld + c);
-        const float4 b = ld4(op.ptr + p * op.ld + c + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (c + i < op.cols) v[i] = op.ptr[p * op.ld + c + i];
-    }
-    if (c + 8 > op.cols) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (c + i >= op.cols) v[i] = 0.0f;
+    for (int i = 0; i < 8; ++i) {
+        float x = 0.0f;
+        if (pnt < n && c + i < op.cols) x = op.tiled ? op.ptr[((pnt >> 7) * 64 + ((c + i) >> 2)) * 512 + (pnt & 127) * 4 + ((c + i) & 3)] : op.ptr[pnt * op.ld + c + i];
+        v[i] = x;
     }
 }
-// chunk of 8 features `fc` of point k (0..31) of a stage matrix
-__device__ __forceinline__ void store8_mn(uint8_t* hi_base, uint8_t* lo_base, int k, int fc, const float* v) {
+// split 8 values into bf16 hi + lo and store them at the thread's chunk of the hi / lo stage matrices
+__device__ __forceinline__ void store8_mn(uint32_t hi_addr, uint32_t lo_addr, const float* v) {
     uint4 hi, lo;
     split2(v[0], v[1], hi.x, lo.x);
     split2(v[2], v[3], hi.y, lo.y);
     split2(v[4], v[5], hi.z, lo.z);
     split2(v[6], v[7], hi.w, lo.w);
-    const uint32_t off = (uint32_t)(fc >> 3) * DW_LBO + (uint32_t)(k >> 3) * DW_SBO + tc::sw128_offset((uint32_t)(k & 7), (uint32_t)(fc & 7));
-    *reinterpret_cast<uint4*>(hi_base + off) = hi;
-    *reinterpret_cast<uint4*>(lo_base + off) = lo;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
 }
 
 __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant__ DwParams p) {
@@ -95,7 +132,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     if (tid == 32) {
         for (int s = 0; s < DW_STAGES; ++s) {
-            tc::mbar_init(&full[s], DW_SWARPS * 32);
+            tc::mbar_init(&full[s], DW_SWARPS);
             tc::mbar_init(&empty[s], 1);
         }
         tc::mbar_init(&done, 1);
@@ -135,50 +172,104 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
             tc::umma_commit(&done);
         }
     } else {
-        // ---- staging: HBM fp32 -> bf16 hi/lo MN-major tiles; lane = point, warp w owns feature chunks w, w+8, ... --
-        float bsum[DW_CPW][8];
+        // ---- staging: HBM fp32 -> (cp.async, DW_RAW_SLOTS deep, private to the thread) -> bf16 hi/lo MN-major tiles.
+        //      Thread = (point k of the 16-point group, 8-feature chunk fc) of both operands.  Stages run over
+        //      (group, operand pair); the fetch of the stage DW_RAW_SLOTS - 1 ahead is issued before each conversion.
+        const int k = tid & (DW_KP - 1), fc = tid >> 4;
+        const uint32_t smem0 = tc::smem_u32(smem);
+        const uint32_t raw0 = smem0 + DW_STAGES * DW_STAGE_BYTES + (uint32_t)tid * 16;
+        const uint32_t soff = (uint32_t)(fc >> 3) * DW_LBO + (uint32_t)(k >> 3) * DW_SBO + tc::sw128_offset((uint32_t)(k & 7), (uint32_t)(fc & 7));
+        const int n_groups = (t1 - t0) * (TILE_M / DW_KP);
+        const int64_t pnt0 = (int64_t)t0 * TILE_M + k;
+        float bsum[8];
 #pragma unroll
-        for (int a = 0; a < DW_CPW; ++a)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) bsum[a][i] = 0.0f;
+        for (int i = 0; i < 8; ++i) bsum[i] = 0.0f;
         uint32_t stage = 0, phase = 0;
-        int it = 0;
-        for (int tile = t0; tile < t1; ++tile) {
-            for (int sub = 0; sub < TILE_M / DW_KP; ++sub) {
-                const int64_t pnt = (int64_t)tile * TILE_M + sub * DW_KP + lane;
-                for (int pair = 0; pair < job.n_pairs; ++pair, ++it) {
-                    float vp[DW_CPW][8], vq[DW_CPW][8];
+        auto publish = [&](const float* vp, const float* vq) {      // convert + hand one stage to the MMA warp
+            tc::mbar_wait(&empty[stage], phase ^ 1u);
+            const uint32_t base = smem0 + stage * DW_STAGE_BYTES + soff;
+            store8_mn(base, base + DW_OPER_BYTES, vp);
+            store8_mn(base + 2 * DW_OPER_BYTES, base + 3 * DW_OPER_BYTES, vq);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&full[stage]);
+            if (++stage == DW_STAGES) { stage = 0; phase ^= 1u; }
+        };
+        bool unaligned = false;
+        for (int a = 0; a < job.n_pairs; ++a) unaligned = unaligned || dw_unaligned(job.P[a]) || dw_unaligned(job.Q[a]);
+        if (unaligned) {
+            // ---- rare: an operand with an odd leading dimension; plain loads, latency exposed --------------------
+            for (int g = 0; g < n_groups; ++g)
+                for (int pair = 0; pair < job.n_pairs; ++pair) {
+                    float vp[8], vq[8];
+                    load8_scalar(job.P[pair], pnt0 + (int64_t)g * DW_KP, p.n, fc, vp);
+                    load8_scalar(job.Q[pair], pnt0 + (int64_t)g * DW_KP, p.n, fc, vq);
+                    if (pair == 0) {
 #pragma unroll
-                    for (int a = 0; a < DW_CPW; ++a) {
-                        load8(job.P[pair], pnt, p.n, warp + DW_SWARPS * a, vp[a]);
-                        load8(job.Q[pair], pnt, p.n, warp + DW_SWARPS * a, vq[a]);
+                        for (int i = 0; i < 8; ++i) bsum[i] += vp[i];
                     }
-                    tc::mbar_wait(&empty[stage], phase ^ 1u);
-                    uint8_t* base = smem + stage * DW_STAGE_BYTES;
+                    publish(vp, vq);
+                }
+        } else {
+            DwStream sp[2], sq[2];
 #pragma unroll
-                    for (int a = 0; a < DW_CPW; ++a) {
-                        store8_mn(base, base + DW_OPER_BYTES, lane, warp + DW_SWARPS * a, vp[a]);
-                        store8_mn(base + 2 * DW_OPER_BYTES, base + 3 * DW_OPER_BYTES, lane, warp + DW_SWARPS * a, vq[a]);
-                        if (pair == 0) {
+            for (int a = 0; a < 2; ++a) {
+                sp[a].init(job.P[a < job.n_pairs ? a : 0], t0, k, fc);
+                sq[a].init(job.Q[a < job.n_pairs ? a : 0], t0, k, fc);
+            }
+            uint32_t slot_head = 0, slot_cur = 0;
+            auto issue = [&](int pair, int g) {          // `pair` is a compile-time constant at every call site
+                if (g < n_groups) {
+                    const uint32_t dst = raw0 + slot_head * DW_RAW_BYTES;
+                    const bool live = pnt0 + (int64_t)g * DW_KP < p.n;
+                    const bool last = (g & (TILE_M / DW_KP - 1)) == TILE_M / DW_KP - 1;
+                    sp[pair].fetch(live, last, dst, dst + 512 * 16);
+                    sq[pair].fetch(live, last, dst + 2 * 512 * 16, dst + 3 * 512 * 16);
+                }
+                cp_async_commit();
+                if (++slot_head == DW_RAW_SLOTS) slot_head = 0;
+            };
+            auto consume = [&](int pair) {
+                cp_async_wait<DW_RAW_SLOTS - 1>();
+                float vp[8], vq[8];
+                const uint32_t src = raw0 + slot_cur * DW_RAW_BYTES;
+                sp[pair].take(src, src + 512 * 16, vp);
+                sq[pair].take(src + 2 * 512 * 16, src + 3 * 512 * 16, vq);
+                if (pair == 0) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) bsum[a][i] += vp[a][i];
-                        }
-                    }
-                    tc::fence_proxy_async_smem();
-                    tc::mbar_arrive(&full[stage]);
-                    if (++stage == DW_STAGES) { stage = 0; phase ^= 1u; }
+                    for (int i = 0; i < 8; ++i) bsum[i] += vp[i];
+                }
+                publish(vp, vq);
+                if (++slot_cur == DW_RAW_SLOTS) slot_cur = 0;
+            };
+            static_assert(DW_RAW_SLOTS == 4, "the look-ahead pattern below is written for three stages in flight");
+            if (job.n_pairs == 2) {
+                // stage order (g,0) (g,1) (g+1,0) ...: three ahead of (g,0) is (g+1,1), three ahead of (g,1) is (g+2,0)
+                issue(0, 0); issue(1, 0); issue(0, 1);
+                for (int g = 0; g < n_groups; ++g) {
+                    issue(1, g + 1);
+                    consume(0);
+                    issue(0, g + 2);
+                    consume(1);
+                }
+            } else {
+                issue(0, 0); issue(0, 1); issue(0, 2);
+                for (int g = 0; g < n_groups; ++g) {
+                    issue(0, g + 3);
+                    consume(0);
                 }
             }
         }
+        cp_async_wait<0>();
         if (job.db) {
 #pragma unroll
-            for (int a = 0; a < DW_CPW; ++a)
+            for (int i = 0; i < 8; ++i) {
+                float s = bsum[i];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float s = warp_sum(bsum[a][i]);
-                    const int c = (warp + DW_SWARPS * a) * 8 + i;
-                    if (lane == 0 && c < job.P[0].cols && s != 0.0f) atomicAdd(job.db + c, s * job.db_scale);
-                }
+                for (int o = DW_KP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                const int c = fc * 8 + i;
+                if (k == 0 && c < job.P[0].cols && s != 0.0f) atomicAdd(job.db + c, s * job.db_scale);
+            }
         }
         // ---- epilogue: partial sums -> workspace ----------------------------------------------------------
         float* part = p.part + ((size_t)j * DW_SPLITS + split) * 65536;
