@@ -80,6 +80,13 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 constexpr int64_t TILE_FLOATS = (int64_t)TILE_M * 256;
 __device__ __forceinline__ int toff(int row, int col) { return (col >> 2) * 512 + row * 4 + (col & 3); }
 
+// The 64-wide per-point arrays (encoding E, its cotangents EB / DE, its tangent UE) are accessed one column at a time by
+// threads that each own a row, so their tiles are column-major: [tile][64 columns][128 rows] -- a warp's 32 rows of one
+// column are one 128-byte line.  eoff(point, 0) + 128 * col addresses column `col`.
+__host__ __device__ __forceinline__ int64_t eoff(int64_t point, int col = 0) {
+    return ((point >> 7) << 13) + (int64_t)col * TILE_M + (point & 127);
+}
+
 // ---- bf16 hi/lo split ------------------------------------------------------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
     // written out so that widening hi back to fp32 is one shift / one mask (the bf162 intrinsics cost two more per pair)
@@ -232,6 +239,7 @@ __device__ __forceinline__ void mma_loop(const Program& prog, uint8_t* smem, Bar
             tc::mbar_wait(&bar->a_ready, a_par);
             t_a += clock64() - tt;
             if (prof) prof[148 * 4 + blockIdx.x * 32 + s] += clock64() - tt;      // per-step epilogue wait
+            if (prof && t == 0 && s == 0) prof[148 * 4 + blockIdx.x * 32 + 31] += clock64() - tt;   // ... of the first tile
             a_par ^= 1u;
             tc::tc_fence_after_sync();
             for (int kb = 0; kb < st.kblocks; ++kb) {

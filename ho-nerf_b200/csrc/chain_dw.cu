@@ -56,18 +56,32 @@ __device__ __forceinline__ void cp_async_wait() {
 // Per-thread view of one operand: the thread owns columns [8 fc, 8 fc + 8) of point k of every 16-point group, read
 // as two 16-byte pieces.  The source pointer only ever advances by constant strides, so issuing a stage costs a
 // handful of instructions whatever the operand's layout.
+// Column-major tiles hold 4 consecutive POINTS of one column in 16 bytes, so there the warp shares its landing slots:
+// the warp's 32 rows x 16 columns are 64 pieces, lane L fetches pieces L and L + 32 (column 16 w + p / 4, points
+// 4 (p % 4) ..) into its own two slots and every lane then reads its 8 columns out of the warp's slots.
 struct DwStream {
     const float* ptr;      // piece 0 of the next group to fetch
     int step;              // floats to the next 16-point group
-    uint32_t flags;        // bit 0 / 1: piece 0 / 1 holds operand columns; bit 2: tiled layout; bits 4..7: valid columns
+    uint32_t flags;        // bit 0 / 1: piece 0 / 1 holds operand columns; bit 2: tiled layout; bit 3: column-major tiles
+                           // (bits 8..15: their column count); bits 4..7: valid columns of the chunk
+    int rem;               // column-major: points from the piece's first point (first group) to the end of the operand
 
-    __device__ __forceinline__ void init(const DwOperand& op, int tile0, int k, int fc) {
+    __device__ __forceinline__ void init(const DwOperand& op, int tile0, int64_t n, int tid) {
+        const int k = tid & (DW_KP - 1), fc = tid >> 4;
         const int c = fc * 8;
         const int n_valid = max(0, min(8, op.cols - c));
         flags = (n_valid > 0 ? 1u : 0u) | (n_valid > 4 ? 2u : 0u) | ((uint32_t)n_valid << 4);
-        if (n_valid == 0) {                 // nothing to read: keep a valid address and never move
+        rem = 0;
+        if (op.tiled == 2) {
+            const int lane = tid & 31, col = 16 * (tid >> 5) + (lane >> 2), q = lane & 3;
+            flags = (col < op.cols ? 1u : 0u) | (col + 8 < op.cols ? 2u : 0u) | (8u << 4) | 8u | ((uint32_t)op.ld << 8);
+            ptr = op.ptr + ((int64_t)tile0 * op.ld + col) * TILE_M + q * 4;
+            step = DW_KP;
+            rem = (int)max((int64_t)-4, min((int64_t)1 << 30, n - ((int64_t)tile0 * TILE_M + q * 4)));
+            if (!(flags & 1u)) { ptr = op.ptr; step = 0; flags = (flags & ~(255u << 8)) | (1u << 8); }      // never moves
+        } else if (n_valid == 0) {          // nothing to read: keep a valid address and never move
             ptr = op.ptr; step = 0;
-        } else if (op.tiled) {
+        } else if (op.tiled == 1) {
             ptr = op.ptr + ((int64_t)tile0 * 64 + fc * 2) * 512 + k * 4;
             step = DW_KP * 4;
             flags |= 4u;
@@ -76,17 +90,32 @@ struct DwStream {
             step = DW_KP * (int)op.ld;
         }
     }
-    // start fetching the next group (`live`: the point exists; `last`: it is the last group of a 128-point tile)
-    __device__ __forceinline__ void fetch(bool live, bool last, uint32_t dst0, uint32_t dst1) {
+    // start fetching group g (`live`: the thread's point exists; `last`: g is the last group of a 128-point tile)
+    template <bool CM>       // CM: the job has column-major operands (compiled out of the common loop)
+    __device__ __forceinline__ void fetch(int g, bool live, bool last, uint32_t dst0, uint32_t dst1) {
         const bool tiled = (flags & 4u) != 0u;
+        if (CM && (flags & 8u)) {
+            const uint32_t bytes = 4u * (uint32_t)max(0, min(4, rem - g * DW_KP));       // ragged last tile: zero-filled
+            cp_async16(dst0, ptr, (flags & 1u) ? bytes : 0u);
+            cp_async16(dst1, ptr + ((flags & 2u) ? 8 * TILE_M : 0), (flags & 2u) ? bytes : 0u);
+            ptr += step + (last ? (int)((flags >> 8) & 255u) * TILE_M - TILE_M : 0);
+            return;
+        }
         cp_async16(dst0, ptr, (live && (flags & 1u)) ? 16u : 0u);
         cp_async16(dst1, ptr + ((flags & 2u) ? (tiled ? 512 : 4) : 0), (live && (flags & 2u)) ? 16u : 0u);
         ptr += step + ((tiled && last) ? 64 * 512 - 512 : 0);
     }
-    __device__ __forceinline__ void take(uint32_t src0, uint32_t src1, float* v) const {
+    template <bool CM>
+    __device__ __forceinline__ void take(uint32_t src0, uint32_t src1, int tid, float* v) const {
+        if (CM && (flags & 8u)) {           // (after a warp sync) column 8 fc + i of point k: 64 i + 4 k into the warp's slots
+            const uint32_t base = (((tid >> 4) & 1) ? src1 : src0) - (uint32_t)(tid & 31) * 16u + (uint32_t)(tid & (DW_KP - 1)) * 4u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[i]) : "r"(base + 64u * i) : "memory");
+            return;
+        }
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(src0) : "memory");
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]) : "r"(src1) : "memory");
-        const int n_valid = (int)(flags >> 4);
+        const int n_valid = (int)((flags >> 4) & 15u);
         if (n_valid < 8) {       // columns past the operand inside a fetched piece
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -103,7 +132,10 @@ __device__ __forceinline__ void load8_scalar(const DwOperand& op, int64_t pnt, i
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         float x = 0.0f;
-        if (pnt < n && c + i < op.cols) x = op.tiled ? op.ptr[((pnt >> 7) * 64 + ((c + i) >> 2)) * 512 + (pnt & 127) * 4 + ((c + i) & 3)] : op.ptr[pnt * op.ld + c + i];
+        if (pnt < n && c + i < op.cols)
+            x = op.tiled == 1   ? op.ptr[((pnt >> 7) * 64 + ((c + i) >> 2)) * 512 + (pnt & 127) * 4 + ((c + i) & 3)]
+                : op.tiled == 2 ? op.ptr[((pnt >> 7) * op.ld + c + i) * TILE_M + (pnt & 127)]
+                                : op.ptr[pnt * op.ld + c + i];
         v[i] = x;
     }
 }
@@ -116,6 +148,85 @@ __device__ __forceinline__ void store8_mn(uint32_t hi_addr, uint32_t lo_addr, co
     split2(v[6], v[7], hi.w, lo.w);
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
+}
+
+// The common staging loop of a CTA (all operands readable in aligned pieces): see dw_kernel.
+template <bool CM>
+__device__ __forceinline__ void stage_streams(const DwJob& job, int64_t n, int t0, int n_groups, int tid, uint32_t smem0,
+                                              uint32_t raw0, uint32_t soff, uint64_t* full, uint64_t* empty, uint32_t& stage,
+                                              uint32_t& phase, float* bsum) {
+    const int k = tid & (DW_KP - 1), lane = tid & 31;
+    const bool q_used = (tid >> 4) * 8 < job.n_mma;      // the MMA reads n_mma features of Q: a narrow operand costs its warps only
+    const int64_t pnt0 = (int64_t)t0 * TILE_M + k;
+    DwStream sp[2], sq[2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        sp[a].init(job.P[a < job.n_pairs ? a : 0], t0, n, tid);
+        sq[a].init(job.Q[a < job.n_pairs ? a : 0], t0, n, tid);
+    }
+    // groups of this thread's point that exist (the last tile may be ragged)
+    const int g_live = (int)max((int64_t)0, min((int64_t)n_groups, (n - pnt0 + DW_KP - 1) / DW_KP));
+    uint32_t slot_head = 0, slot_cur = 0;
+    auto issue = [&](int pair, int g) {          // `pair` is a compile-time constant at every call site
+        if (g < n_groups) {
+            const uint32_t dst = raw0 + slot_head * DW_RAW_BYTES;
+            const bool live = g < g_live;
+            const bool last = (g & (TILE_M / DW_KP - 1)) == TILE_M / DW_KP - 1;
+            sp[pair].template fetch<CM>(g, live, last, dst, dst + 512 * 16);
+            if (q_used) sq[pair].template fetch<CM>(g, live, last, dst + 2 * 512 * 16, dst + 3 * 512 * 16);
+        }
+        cp_async_commit();
+        if (++slot_head == DW_RAW_SLOTS) slot_head = 0;
+    };
+    auto take = [&](int pair, float* vp, float* vq) {
+        const uint32_t src = raw0 + slot_cur * DW_RAW_BYTES;
+        sp[pair].template take<CM>(src, src + 512 * 16, tid, vp);
+        if (q_used) sq[pair].template take<CM>(src + 2 * 512 * 16, src + 3 * 512 * 16, tid, vq);
+        if (pair == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bsum[i] += vp[i];
+        }
+        if (++slot_cur == DW_RAW_SLOTS) slot_cur = 0;
+    };
+    // Two stages per trip (their count is even): one proxy fence and one warp sync for both, and the loads of
+    // one overlap the conversion of the other.  Stages s+3, s+4 are fetched into the slots stages s, s+1 vacate.
+    auto two_stages = [&](int pa, int pb, int pc, int gc, int pd, int gd) {
+        cp_async_wait<1>();
+        if (CM) __syncwarp();       // the warp's landing slots are shared: everybody's pieces have landed ...
+        float vp0[8], vq0[8], vp1[8], vq1[8];
+        take(pa, vp0, vq0);
+        take(pb, vp1, vq1);
+        if (CM) __syncwarp();       // ... and have been read before they are refilled
+        issue(pc, gc);
+        issue(pd, gd);
+        const uint32_t st0 = stage, ph0 = phase;
+        if (++stage == DW_STAGES) { stage = 0; phase ^= 1u; }
+        const uint32_t st1 = stage, ph1 = phase;
+        if (++stage == DW_STAGES) { stage = 0; phase ^= 1u; }
+        tc::mbar_wait(&empty[st0], ph0 ^ 1u);
+        const uint32_t b0 = smem0 + st0 * DW_STAGE_BYTES + soff;
+        store8_mn(b0, b0 + DW_OPER_BYTES, vp0);
+        if (q_used) store8_mn(b0 + 2 * DW_OPER_BYTES, b0 + 3 * DW_OPER_BYTES, vq0);
+        tc::mbar_wait(&empty[st1], ph1 ^ 1u);
+        const uint32_t b1 = smem0 + st1 * DW_STAGE_BYTES + soff;
+        store8_mn(b1, b1 + DW_OPER_BYTES, vp1);
+        if (q_used) store8_mn(b1 + 2 * DW_OPER_BYTES, b1 + 3 * DW_OPER_BYTES, vq1);
+        tc::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tc::mbar_arrive(&full[st0]);
+            tc::mbar_arrive(&full[st1]);
+        }
+    };
+    static_assert(DW_RAW_SLOTS == 4 && (TILE_M / DW_KP) % 2 == 0, "look-ahead pattern below: three stages in flight");
+    if (job.n_pairs == 2) {
+        // stage order (g,0) (g,1) (g+1,0) ...
+        issue(0, 0); issue(1, 0); issue(0, 1);
+        for (int g = 0; g < n_groups; ++g) two_stages(0, 1, 1, g + 1, 0, g + 2);
+    } else {
+        issue(0, 0); issue(0, 1); issue(0, 2);
+        for (int g = 0; g < n_groups; g += 2) two_stages(0, 0, 0, g + 3, 0, g + 4);
+    }
 }
 
 __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant__ DwParams p) {
@@ -195,8 +306,11 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
             if (lane == 0) tc::mbar_arrive(&full[stage]);
             if (++stage == DW_STAGES) { stage = 0; phase ^= 1u; }
         };
-        bool unaligned = false;
-        for (int a = 0; a < job.n_pairs; ++a) unaligned = unaligned || dw_unaligned(job.P[a]) || dw_unaligned(job.Q[a]);
+        bool unaligned = false, colmajor = false;
+        for (int a = 0; a < job.n_pairs; ++a) {
+            unaligned = unaligned || dw_unaligned(job.P[a]) || dw_unaligned(job.Q[a]);
+            colmajor = colmajor || job.P[a].tiled == 2 || job.Q[a].tiled == 2;
+        }
         if (unaligned) {
             // ---- rare: an operand with an odd leading dimension; plain loads, latency exposed --------------------
             for (int g = 0; g < n_groups; ++g)
@@ -211,54 +325,8 @@ __global__ void __launch_bounds__(DW_THREADS, 1) dw_kernel(const __grid_constant
                     publish(vp, vq);
                 }
         } else {
-            DwStream sp[2], sq[2];
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                sp[a].init(job.P[a < job.n_pairs ? a : 0], t0, k, fc);
-                sq[a].init(job.Q[a < job.n_pairs ? a : 0], t0, k, fc);
-            }
-            uint32_t slot_head = 0, slot_cur = 0;
-            auto issue = [&](int pair, int g) {          // `pair` is a compile-time constant at every call site
-                if (g < n_groups) {
-                    const uint32_t dst = raw0 + slot_head * DW_RAW_BYTES;
-                    const bool live = pnt0 + (int64_t)g * DW_KP < p.n;
-                    const bool last = (g & (TILE_M / DW_KP - 1)) == TILE_M / DW_KP - 1;
-                    sp[pair].fetch(live, last, dst, dst + 512 * 16);
-                    sq[pair].fetch(live, last, dst + 2 * 512 * 16, dst + 3 * 512 * 16);
-                }
-                cp_async_commit();
-                if (++slot_head == DW_RAW_SLOTS) slot_head = 0;
-            };
-            auto consume = [&](int pair) {
-                cp_async_wait<DW_RAW_SLOTS - 1>();
-                float vp[8], vq[8];
-                const uint32_t src = raw0 + slot_cur * DW_RAW_BYTES;
-                sp[pair].take(src, src + 512 * 16, vp);
-                sq[pair].take(src + 2 * 512 * 16, src + 3 * 512 * 16, vq);
-                if (pair == 0) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) bsum[i] += vp[i];
-                }
-                publish(vp, vq);
-                if (++slot_cur == DW_RAW_SLOTS) slot_cur = 0;
-            };
-            static_assert(DW_RAW_SLOTS == 4, "the look-ahead pattern below is written for three stages in flight");
-            if (job.n_pairs == 2) {
-                // stage order (g,0) (g,1) (g+1,0) ...: three ahead of (g,0) is (g+1,1), three ahead of (g,1) is (g+2,0)
-                issue(0, 0); issue(1, 0); issue(0, 1);
-                for (int g = 0; g < n_groups; ++g) {
-                    issue(1, g + 1);
-                    consume(0);
-                    issue(0, g + 2);
-                    consume(1);
-                }
-            } else {
-                issue(0, 0); issue(0, 1); issue(0, 2);
-                for (int g = 0; g < n_groups; ++g) {
-                    issue(0, g + 3);
-                    consume(0);
-                }
-            }
+            if (colmajor) stage_streams<true>(job, p.n, t0, n_groups, tid, smem0, raw0, soff, full, empty, stage, phase, bsum);
+            else stage_streams<false>(job, p.n, t0, n_groups, tid, smem0, raw0, soff, full, empty, stage, phase, bsum);
         }
         cp_async_wait<0>();
         if (job.db) {

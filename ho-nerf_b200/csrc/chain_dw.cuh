@@ -8,10 +8,11 @@ namespace chain {
 constexpr int DW_MAX_JOBS = 12;
 constexpr int DW_SPLITS = 16;
 
-// fp32 operand [points, cols]: tiled ([tile][col/4][128 rows][4], the chain stash layout) or row-major
+// fp32 operand [points, cols]: row-major (tiled = 0), the chain stash layout [tile][col/4][128 rows][4] (tiled = 1), or
+// column-major tiles [tile][ld columns][128 rows] (tiled = 2, the 64-wide encoding arrays)
 struct DwOperand {
     const float* ptr;
-    int64_t ld;        // row-major leading dimension (ignored when tiled)
+    int64_t ld;        // row-major leading dimension / columns per column-major tile (ignored when tiled = 1)
     int cols;          // valid columns (the rest of the 256-wide tile is zero)
     int tiled;
 };

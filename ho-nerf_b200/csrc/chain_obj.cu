@@ -22,13 +22,13 @@ namespace chain {
 // [x(3), sin/cos(2^k x_c)] of one point written as columns shift + j of the A operand; the column
 // groups of a row share the 30 (coordinate, frequency) pairs.  Column shift+63 (the K padding of the
 // first layer) is zeroed when shift == 0.
-// `g` (may be NULL): fp32 copy for the stash: row-major row pointer (g[j] = e_j) when !g_tiled, else the
-// base of a tiled [128, 256] tile whose columns shift + j receive e_j.
+// `g` (may be NULL): fp32 copy for the stash: the point's entry of a column-major [64][128] tile (g[128 j] = e_j,
+// see eoff) when !g_tiled, else the base of a tiled [128, 256] tile whose columns shift + j receive e_j.
 template <bool LO16 = false>
 __device__ __forceinline__ void write_encoding(uint8_t* smem, int row, int cg, const float x[3], int shift,
                                                float* __restrict__ g = nullptr, bool g_tiled = false) {
     auto gput = [&](int j, float v) {
-        if (g) g[g_tiled ? toff(row, shift + j) : j] = v;
+        if (g) g[g_tiled ? toff(row, shift + j) : j * TILE_M] = v;
     };
     if (cg == 0) {
 #pragma unroll
@@ -200,7 +200,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
             const bool live = gp < p.n;
             float x[3] = {0.f, 0.f, 0.f};
             if (live) { x[0] = p.pts[gp * 3]; x[1] = p.pts[gp * 3 + 1]; x[2] = p.pts[gp * 3 + 2]; }
-            write_encoding<true>(smem, row, cg, x, 0, live ? p.E + gp * 64 : nullptr);
+            write_encoding<true>(smem, row, cg, x, 0, live ? p.E + eoff(gp) : nullptr);
             epi_publish_a(&bar);
             // ---- value trunk ----------------------------------------------------------------------
             float head = 0.0f;
@@ -241,7 +241,7 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                     const int c0 = 192 + cg * 16;
                     float tl[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) tl[j] = (live && c0 + j >= 193) ? p.E[gp * 64 + c0 + j - 193] : 0.0f;
+                    for (int j = 0; j < 16; ++j) tl[j] = (live && c0 + j >= 193) ? p.E[eoff(gp, c0 + j - 193)] : 0.0f;
                     if (cg == 0) {
                         float v[32];
                         acc_load32(tmem, row, 192, v);
@@ -257,11 +257,11 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                 epi_publish_a(&bar);
             }
             // sdf = (h7 . W_out[0] + b_out[0]) / scale; the 4 column groups meet through the (still unused) EB rows
-            if (live) p.EB[gp * 64 + cg] = head;
+            if (live) p.EB[eoff(gp, cg)] = head;
             tc::named_bar_sync(1, EPI_THREADS);
             if (cg == 0 && live) {
-                const float4 h4 = *reinterpret_cast<const float4*>(p.EB + gp * 64);
-                p.sdf[gp] = (h4.x + h4.y + h4.z + h4.w + __ldg(p.bias[8])) * p.inv_scale;
+                const float* __restrict__ h4 = p.EB + eoff(gp);
+                p.sdf[gp] = (h4[0] + h4[TILE_M] + h4[2 * TILE_M] + h4[3 * TILE_M] + __ldg(p.bias[8])) * p.inv_scale;
             }
             // ---- feature head; seed of the normal sweep D7 = s'(h7) * W_out[0] / scale ----------------
             epi_wait_acc(&bar, acc_par);
@@ -344,20 +344,21 @@ sdf_fwd_kernel(const __grid_constant__ FwdParams p, const __grid_constant__ Prog
                         e.y = v[j + 1] + d3[toff(row, 194 + col)];
                         e.z = v[j + 2] + d3[toff(row, 195 + col)];
                         e.w = col + 3 == 63 ? 0.0f : v[j + 3] + d3[toff(row, 196 + col)];
-                        st4(p.EB + gp * 64 + col, e);
+                        float* __restrict__ eb = p.EB + eoff(gp, col);
+                        eb[0] = e.x; eb[TILE_M] = e.y; eb[2 * TILE_M] = e.z; eb[3 * TILE_M] = e.w;
                     }
                 }
             }
             tc::tc_fence_before_sync();
             tc::named_bar_sync(1, EPI_THREADS);
             if (cg < 3 && live) {
-                const float* __restrict__ e = p.E + gp * 64 + 3 + cg * 20;
-                const float* __restrict__ g = p.EB + gp * 64 + 3 + cg * 20;
-                float acc = p.EB[gp * 64 + cg];
+                const float* __restrict__ e = p.E + eoff(gp, 3 + cg * 20);
+                const float* __restrict__ g = p.EB + eoff(gp, 3 + cg * 20);
+                float acc = p.EB[eoff(gp, cg)];
                 float f = 1.0f;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
-                    acc += f * (e[10 + k] * g[k] - e[k] * g[10 + k]);
+                    acc += f * (e[(10 + k) * TILE_M] * g[k * TILE_M] - e[k * TILE_M] * g[(10 + k) * TILE_M]);
                     f *= 2.0f;
                 }
                 p.normal[gp * 3 + cg] = acc;
@@ -423,33 +424,33 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
             if (live) { dn[0] = p.d_normal[gp * 3]; dn[1] = p.d_normal[gp * 3 + 1]; dn[2] = p.d_normal[gp * 3 + 2]; }
             // ue = J_e(x) dn: tangent of the encoding, columns shift + j of the A operand (and of `g`)
             auto write_ue = [&](int shift, float* __restrict__ g, bool gt) {
-                const float* __restrict__ e = p.E + gp * 64;
+                const float* __restrict__ e = p.E + eoff(gp);
                 if (cg == 0) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         a_store1(smem, row, shift + c, dn[c]);
-                        if (live) g[gt ? toff(row, shift + c) : c] = dn[c];
+                        if (live) g[gt ? toff(row, shift + c) : c * TILE_M] = dn[c];
                     }
                     if (shift == 0) {
                         a_store1(smem, row, 63, 0.0f);
-                        if (live) g[63] = 0.0f;
+                        if (live) g[63 * TILE_M] = 0.0f;
                     }
                 }
                 for (int idx = cg; idx < 30; idx += EPI_CGROUPS) {
                     const int c = idx / 10, k = idx - c * 10;
                     const float f = (float)(1 << k);
                     float sn = 0.f, cs = 0.f;
-                    if (live) { sn = e[3 + c * 20 + k]; cs = e[3 + c * 20 + 10 + k]; }
+                    if (live) { sn = e[(3 + c * 20 + k) * TILE_M]; cs = e[(3 + c * 20 + 10 + k) * TILE_M]; }
                     const float us = f * cs * dn[c], uc = -f * sn * dn[c];
                     a_store1(smem, row, shift + 3 + c * 20 + k, us);
                     a_store1(smem, row, shift + 3 + c * 20 + 10 + k, uc);
                     if (live) {
-                        g[gt ? toff(row, shift + 3 + c * 20 + k) : 3 + c * 20 + k] = us;
-                        g[gt ? toff(row, shift + 3 + c * 20 + 10 + k) : 3 + c * 20 + 10 + k] = uc;
+                        g[gt ? toff(row, shift + 3 + c * 20 + k) : (3 + c * 20 + k) * TILE_M] = us;
+                        g[gt ? toff(row, shift + 3 + c * 20 + 10 + k) : (3 + c * 20 + 10 + k) * TILE_M] = uc;
                     }
                 }
             };
-            write_ue(0, p.UE + gp * 64, false);
+            write_ue(0, p.UE + eoff(gp), false);
             epi_publish_a(&bar);
             // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l -----------
             for (int l = 0; l < 8; ++l) {
@@ -485,7 +486,7 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                     const int c0 = 192 + cg * 16;
                     float tl[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) tl[j] = (live && c0 + j >= 193) ? p.UE[gp * 64 + c0 + j - 193] : 0.0f;
+                    for (int j = 0; j < 16; ++j) tl[j] = (live && c0 + j >= 193) ? p.UE[eoff(gp, c0 + j - 193)] : 0.0f;
                     if (cg == 0) {
                         float v[32];
                         acc_load32(tmem, row, 192, v);
@@ -579,20 +580,22 @@ sdf_bwd_kernel(const __grid_constant__ BwdParams p, const __grid_constant__ Prog
                         e.y = v[j + 1] + z3[toff(row, 194 + col)];
                         e.z = v[j + 2] + z3[toff(row, 195 + col)];
                         e.w = col + 3 == 63 ? 0.0f : v[j + 3] + z3[toff(row, 196 + col)];
-                        st4(p.DE + gp * 64 + col, e);
+                        float* __restrict__ de = p.DE + eoff(gp, col);
+                        de[0] = e.x; de[TILE_M] = e.y; de[2 * TILE_M] = e.z; de[3 * TILE_M] = e.w;
                     }
                 }
                 tc::tc_fence_before_sync();
                 tc::named_bar_sync(1, EPI_THREADS);
                 if (cg < 3 && live) {
-                    const float* __restrict__ e = p.E + gp * 64 + 3 + cg * 20;
-                    const float* __restrict__ g = p.DE + gp * 64 + 3 + cg * 20;
-                    const float* __restrict__ b = p.EB + gp * 64 + 3 + cg * 20;
-                    float acc = p.DE[gp * 64 + cg], hess = 0.0f, f = 1.0f;
+                    const float* __restrict__ e = p.E + eoff(gp, 3 + cg * 20);
+                    const float* __restrict__ g = p.DE + eoff(gp, 3 + cg * 20);
+                    const float* __restrict__ b = p.EB + eoff(gp, 3 + cg * 20);
+                    float acc = p.DE[eoff(gp, cg)], hess = 0.0f, f = 1.0f;
 #pragma unroll
                     for (int k = 0; k < 10; ++k) {
-                        acc += f * (e[10 + k] * g[k] - e[k] * g[10 + k]);
-                        hess -= f * f * (e[k] * b[k] + e[10 + k] * b[10 + k]);
+                        const float sn = e[k * TILE_M], cs = e[(10 + k) * TILE_M];
+                        acc += f * (cs * g[k * TILE_M] - sn * g[(10 + k) * TILE_M]);
+                        hess -= f * f * (sn * b[k * TILE_M] + cs * b[(10 + k) * TILE_M]);
                         f *= 2.0f;
                     }
                     p.d_pts[gp * 3 + cg] = acc + dn[cg] * hess;
@@ -819,8 +822,8 @@ int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const 
         j.P[0] = {DZ + (int64_t)l * np * 256, 0, out, 1};
         j.P[1] = {D + (int64_t)l * np * 256, 0, out, 1};
         if (l == 0) {
-            j.Q[0] = {E, 64, in, 0};
-            j.Q[1] = {UE, 64, in, 0};
+            j.Q[0] = {E, 64, in, 2};          // column-major [64][128] tiles
+            j.Q[1] = {UE, 64, in, 2};
         } else {
             j.Q[0] = {H + (int64_t)(l - 1) * np * 256, 0, in, 1};       // H[3] holds the skip input [h3 | e]
             j.Q[1] = {U + (int64_t)(l - 1) * np * 256, 0, in, 1};       // U[3] holds [u3 | ue]

@@ -328,7 +328,8 @@ HN_API int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K, in
 HN_API int hn_tc_gemm_ts_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
                               hn_stream_t stream);
 /* The weight-gradient kernel of the HN_TC_BF16X3 path, for tests: C [out, ldc] += P^T Q (+ P2^T Q2) over n
- * points, P [n, out] and Q [n, in] fp32, row-major (ld) or tiled ([tile][col/4][128][4], n padded to 128);
+ * points, P [n, out] and Q [n, in] fp32: row-major (x_tiled = 0, leading dimension ld), tiled (x_tiled = 1:
+ * [tile][col/4][128][4], n padded to 128) or column-major tiles (x_tiled = 2: [tile][ld columns][128 rows]);
  * db [out] += column sums of P (may be NULL); part: workspace of >= 16 * 65536 floats. */
 HN_API int hn_dw_test(const float* P, int64_t ldp, int p_tiled, int out, const float* Q, int64_t ldq,
                       int q_tiled, int in, const float* P2, const float* Q2, int64_t n, float* C,

@@ -115,6 +115,37 @@ def test_weight_gradient_kernel(n, out, nin, tiled, two):
         assert float(C[:, nin:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n", [77, 4096 + 130])
+def test_weight_gradient_kernel_column_major_operand(n):
+    """The first SDF layer's job: P in the tiled stash layout, Q (the 39-wide encoding) in column-major [64][128]
+    tiles; same bound as above."""
+    import ctypes
+    from honerf_b200 import _lib
+    g = torch.Generator().manual_seed(n)
+    mk = lambda c: torch.randn(n, c, generator=g).to(DEV)
+    P, Q, P2, Q2 = mk(256), mk(39), mk(256), mk(39)
+    ref = P.double().T @ Q.double() + P2.double().T @ Q2.double()
+
+    def colmajor(x):
+        npad = (n + 127) // 128 * 128
+        full = torch.zeros(npad, 64, device=DEV)
+        full[:n, :39] = x
+        return full.reshape(npad // 128, 128, 64).permute(0, 2, 1).contiguous()
+
+    C = torch.zeros(256, 40, device=DEV)
+    db = torch.zeros(256, device=DEV)
+    part = torch.empty(16 * 65536, device=DEV)
+    args = [_tile(P), colmajor(Q), _tile(P2), colmajor(Q2)]
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib.hn_dw_test(ptr(args[0]), 0, 1, 256, ptr(args[1]), 64, 2, 39, ptr(args[2]), ptr(args[3]), n, ptr(C), 40,
+                                   ptr(db), ptr(part), part.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "hn_dw_test")
+    err = max_abs(C[:, :39], ref) / float(ref.abs().max())
+    errb = max_abs(db, P.double().sum(0)) / float(P.double().sum(0).abs().max())
+    print("n=%d column-major Q: dW rel-to-max %.2e, db %.2e" % (n, err, errb))
+    assert err < 5e-5 and errb < 1e-5 and float(C[:, 39:].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("n", [1, 200, 5000])
 def test_color_chain_forward_backward(n):
     """RenderingNetwork_OBJ through the colour chain kernels (split 373-wide first layer, ReLU chain, N=16 output

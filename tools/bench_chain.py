@@ -119,6 +119,9 @@ def prof_fwd_bwd():
         per_step = buf[148 * 4:].reshape(148, 32).double().cpu()
         tl = torch.tensor([4.0 if i < 68 else 3.0 for i in range(148)], dtype=torch.float64)
         print(which, "wait for the epilogue BEFORE step s (cycles per tile):", [int(x) for x in (per_step / tl[:, None]).mean(0)[:18].tolist()])
+        first = per_step[:, 31]
+        later = (per_step[:, 0] - first) / (tl - 1)
+        print(which, "wait before step 0: first tile of a CTA %.0f (min %.0f max %.0f), later tiles %.0f cycles" % (first.mean(), first.min(), first.max(), later.mean()))
         tiles = torch.tensor([4.0 if i < 68 else 3.0 for i in range(148)], dtype=torch.float64)
         steps = tiles * 17
         print("%s chain kernel, per layer-tile cycles (mean over CTAs): total %.0f  MMA-warp waits for epilogue %.0f  for weights %.0f  issue+rest %.0f; max CTA total %.0f cycles"
