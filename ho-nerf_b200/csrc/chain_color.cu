@@ -13,6 +13,10 @@
 namespace hn {
 namespace chain {
 
+// entry of point `point`, column `col` in the column-major [tile][128 columns][128 rows] encoding stash
+__host__ __device__ __forceinline__ int64_t coff(int64_t point, int col = 0) {
+    return ((point >> 7) << 14) + (int64_t)col * TILE_M + (point & 127);
+}
 constexpr int ENC_LD = 128;      // [enc10(pts) 63 | enc4(dirs) 27 | enc4(normal) 27 | 0 x 11]
 constexpr int ENC_DIRS = 63, ENC_NRM = 90, ENC_DIM = 117;
 constexpr int CIN_FEAT0 = 90, CIN_NRM0 = 346;     // column offsets inside the reference's 373-wide input
@@ -36,15 +40,16 @@ static ColorLayout color_layout() {
     return L;
 }
 
-// [x(3), sin/cos(2^k x_c), k < L] of a 3-vector -> columns col_base + j of the A operand and of the row-major
-// global row g (may be NULL); the (coordinate, frequency) pairs are shared by the 4 column groups of a row
+// [x(3), sin/cos(2^k x_c), k < L] of a 3-vector -> columns col_base + j of the A operand and of the point's entry g
+// (may be NULL) of a column-major [128][128] stash tile (column j at g[128 j], see coff); the (coordinate, frequency)
+// pairs are shared by the 4 column groups of a row
 __device__ __forceinline__ void write_enc3(uint8_t* smem, int row, int cg, const float x[3], int L, int col_base,
                                            float* __restrict__ g) {
     if (cg == 0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             a_store1(smem, row, col_base + c, x[c]);
-            if (g) g[col_base + c] = x[c];
+            if (g) g[(col_base + c) * TILE_M] = x[c];
         }
     }
     for (int idx = cg; idx < 3 * L; idx += EPI_CGROUPS) {
@@ -54,7 +59,7 @@ __device__ __forceinline__ void write_enc3(uint8_t* smem, int row, int cg, const
         const int js = col_base + 3 + c * 2 * L + k, jc = js + L;
         a_store1(smem, row, js, s);
         a_store1(smem, row, jc, co);
-        if (g) { g[js] = s; g[jc] = co; }
+        if (g) { g[js * TILE_M] = s; g[jc * TILE_M] = co; }
     }
 }
 
@@ -66,7 +71,7 @@ struct ColorFwdParams {
     const float* normal;
     int64_t n;
     float* rgb;
-    float* ENC;       // stash: [np, 128] row-major
+    float* ENC;       // stash: column-major tiles [tile][128 columns][128 rows]
     float* FEAT;      // stash: tiled copy of the feature input (operand of the first layer's weight gradient)
     float* R[4];      // stash: tiled ReLU outputs
     const uint8_t* chain;
@@ -128,14 +133,14 @@ color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant
 #pragma unroll
                     for (int c = 0; c < 3; ++c) { x[c] = p.pts[gp * 3 + c]; d[c] = p.dirs[gp * 3 + c]; nr[c] = p.normal[gp * 3 + c]; }
                 }
-                float* __restrict__ g = live ? p.ENC + gp * ENC_LD : nullptr;
+                float* __restrict__ g = live ? p.ENC + coff(gp) : nullptr;
                 write_enc3(smem, row, cg, x, 10, 0, g);
                 write_enc3(smem, row, cg, d, 4, ENC_DIRS, g);
                 write_enc3(smem, row, cg, nr, 4, ENC_NRM, g);
                 if (cg == 0) {
                     for (int j = ENC_DIM; j < ENC_LD; ++j) {
                         a_store1(smem, row, j, 0.0f);
-                        if (g) g[j] = 0.0f;
+                        if (g) g[j * TILE_M] = 0.0f;
                     }
                 }
             }
@@ -193,7 +198,7 @@ struct ColorBwdParams {
     float* d_normal;
     float* DZ4;        // workspace: [np, 4] row-major
     float* DZ[4];      // tiled
-    float* DENC;       // [np, 128] row-major
+    float* DENC;       // column-major tiles like ENC
     const uint8_t* chain;
     int n_tiles;
 };
@@ -277,19 +282,19 @@ color_bwd_kernel(const __grid_constant__ ColorBwdParams p, const __grid_constant
                 acc_load32(tmem, row, cg * 32, v);
                 if (live) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) st4(p.DENC + gp * ENC_LD + cg * 32 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                    for (int j = 0; j < 32; ++j) p.DENC[coff(gp, cg * 32 + j)] = v[j];
                 }
                 tc::tc_fence_before_sync();
                 tc::named_bar_sync(1, EPI_THREADS);
                 if (live && cg < 3) {
-                    const float* __restrict__ e = p.ENC + gp * ENC_LD;
-                    const float* __restrict__ g = p.DENC + gp * ENC_LD;
+                    const float* __restrict__ e = p.ENC + coff(gp);
+                    const float* __restrict__ g = p.DENC + coff(gp);
                     float* out = cg == 0 ? p.d_pts : cg == 1 ? p.d_dirs : p.d_normal;
                     const int base = cg == 0 ? 0 : cg == 1 ? ENC_DIRS : ENC_NRM;
                     const int L = cg == 0 ? 10 : 4;
                     if (out) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) out[gp * 3 + c] = enc3_jt_from_enc(e + base, g + base, L, c);
+                        for (int c = 0; c < 3; ++c) out[gp * 3 + c] = enc3_jt_from_enc(e + base * TILE_M, g + base * TILE_M, L, c, TILE_M);
                     }
                 }
             }
@@ -398,7 +403,7 @@ int launch_color_bwd(const hn_mlp_t* m, int64_t n, const float* stash, const flo
     };
     const int ld0 = m->ld[0];
     job({p.DZ[0], 0, 256, 1}, {FEAT, 0, 256, 1}, grad->db[0], reduce_job(grad->dW[0], ld0, 0, 256, 256, CIN_FEAT0));
-    job({p.DZ[0], 0, 256, 1}, {p.ENC, ENC_LD, ENC_DIM, 0}, nullptr,
+    job({p.DZ[0], 0, 256, 1}, {p.ENC, ENC_LD, ENC_DIM, 2}, nullptr,
         reduce_job(grad->dW[0], ld0, 0, 256, ENC_DIM, 0, CIN_FEAT0, CIN_NRM0));
     for (int l = 1; l <= 3; ++l)
         job({p.DZ[l], 0, 256, 1}, {p.R[l - 1], 0, 256, 1}, grad->db[l], reduce_job(grad->dW[l], m->ld[l], 0, 256, 256));

@@ -17,13 +17,14 @@ __device__ __forceinline__ float enc3_col(const float x[3], int L, int j) {
 }
 
 // (J_enc^T g)_c with the sin/cos values read back from the encoded vector e
-__device__ __forceinline__ float enc3_jt_from_enc(const float* e, const float* g, int L, int c) {
-    float acc = g[c];
-    const float* es = e + 3 + c * 2 * L;
-    const float* gs = g + 3 + c * 2 * L;
+// `stride`: distance between consecutive encoding columns of the point in e and g (1 = row-major rows)
+__device__ __forceinline__ float enc3_jt_from_enc(const float* e, const float* g, int L, int c, int stride = 1) {
+    float acc = g[c * stride];
+    const float* es = e + (3 + c * 2 * L) * stride;
+    const float* gs = g + (3 + c * 2 * L) * stride;
     float f = 1.0f;
     for (int k = 0; k < L; ++k) {
-        acc += f * (es[L + k] * gs[k] - es[k] * gs[L + k]);
+        acc += f * (es[(L + k) * stride] * gs[k * stride] - es[k * stride] * gs[(L + k) * stride]);
         f *= 2.0f;
     }
     return acc;
