@@ -167,7 +167,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def build_gpu_model(device, precision):
+def build_gpu_model(device, precision, optimizer="flat"):
     import honerf_b200 as H
     import ref_conf
     import synth
@@ -181,7 +181,11 @@ def build_gpu_model(device, precision):
         m.to(device)
     r = H.NeuSRenderer(sdf, var, col, "obj", **ref_conf.RENDERER_CONF)
     params = list(sdf.parameters()) + list(var.parameters()) + list(col.parameters())
-    opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)   # one fused kernel; capturable in a CUDA graph
+    if optimizer == "flat":
+        from honerf_b200.optim import FlatAdam
+        opt = FlatAdam(params, lr=1e-4)         # every parameter in one buffer, one Adam launch per step
+    else:
+        opt = torch.optim.Adam(params, lr=1e-4, fused=True, capturable=True)   # capturable in a CUDA graph
     return H, r, params, opt
 
 
@@ -206,7 +210,8 @@ def run_gpu_arm(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
-    H, renderer, params, opt = build_gpu_model(device, args.precision)
+    H, renderer, params, opt = build_gpu_model(device, args.precision, args.optimizer)
+    flat_opt = args.optimizer == "flat"
     from honerf_b200 import dist as hdist
     n_rays = args.rays
     host = synthetic_batch(n_rays, seed=7 + rank)
@@ -224,16 +229,21 @@ def run_gpu_arm(args):
         opt.zero_grad(set_to_none=True)
         Ro.grad = None; To.grad = None
         loss.backward()
-        if world > 1:
+        if flat_opt:
+            flat_holder["runs"] = opt.gather_grads()        # gradients -> opt.flat_grad
+        elif world > 1:
             flat_holder["flat"] = hdist.flatten_gradients(params)
         return loss
 
     def reduce_grads():
         """the ONE collective of the step: all-reduce of the flat gradient buffer (NCCL over NVLink)"""
         if world > 1:
-            hdist.allreduce_flat(flat_holder["flat"])
+            hdist.allreduce_flat(opt.flat_grad if flat_opt else flat_holder["flat"])
 
     def apply_grads():
+        if flat_opt:
+            opt.step(flat_holder["runs"], grad_scale=1.0 / world)     # averaging folded into the Adam kernel
+            return
         if world > 1:
             hdist.unflatten_gradients(params, flat_holder["flat"], world)
         opt.step()
@@ -413,6 +423,7 @@ def run_gpu_arm(args):
                                    "masked-L1+BCE+eikonal loss, 2nd-order bwd, Adam" % n_rays,
                        "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
                        "cuda_graph": graph is not None,
+                       "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
                        "l2": "per-step activation stash (~2 GB at 512 rays) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
@@ -554,6 +565,8 @@ def main():
     ap.add_argument("--rays", type=int, default=512, help="rays per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
+    ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
+                    help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")

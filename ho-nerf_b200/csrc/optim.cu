@@ -1,0 +1,43 @@
+// Adam over one flat fp32 parameter buffer (torch.optim.Adam semantics, exp_runner.py:83 builds one Adam over every
+// network's parameters): one launch per step instead of a multi-tensor sweep over ~90 small tensors.
+// The step count lives in device memory so the launch is identical every step (CUDA-graph replay).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace hn {
+
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                        float* __restrict__ v, int64_t n, const float* __restrict__ step,
+                                                        float lr, float beta1, float beta2, float eps, float weight_decay,
+                                                        float grad_scale) {
+    const float t = *step;
+    const float bc1 = 1.0f - powf(beta1, t), bc2 = 1.0f - powf(beta2, t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float gi = g[i] * grad_scale;
+        const float pi = p[i];
+        if (weight_decay != 0.0f) gi += weight_decay * pi;
+        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
+        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+    }
+}
+
+}  // namespace hn
+
+using namespace hn;
+
+extern "C" int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* step, float lr,
+                            float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                            hn_stream_t stream) {
+    HN_REQUIRE(p && g && m && v && step && n >= 0, "hn_adam_flat: null argument");
+    if (n == 0) return HN_OK;
+    const int grid = (int)std::min<int64_t>(ceil_div(n, 256), 4 * 148);
+    adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step, lr, beta1, beta2, eps, weight_decay, grad_scale);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}

@@ -124,6 +124,14 @@ typedef struct hn_wn_job {
 HN_API int hn_wn_pack_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream);
 HN_API int hn_wn_bwd_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream);
 
+/* Adam over one flat fp32 parameter buffer (torch.optim.Adam semantics; the reference builds one Adam over all
+ * networks' parameters, exp_runner.py:83).  p, m, v [n] are updated in place from g [n] * grad_scale; `step` is a
+ * DEVICE float holding the 1-based step count (the caller increments it before the call), so the launch is the
+ * same every step and can be replayed from a CUDA graph. */
+HN_API int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* step, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                        hn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Object SDF field: SDFNetwork_OBJ.forward / .sdf / .gradient (utils/fields.py:316-347) as ONE
  * operator (value + feature + analytic normal) with a hand-written second-order backward.
