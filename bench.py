@@ -189,6 +189,59 @@ def build_gpu_model(device, precision, optimizer="flat"):
     return H, r, params, opt
 
 
+def fitting_extra(H, device, n_rays, precision):
+    """Informational: one pose-fitting iteration of fitting_single.py through NeuSRenderer_fitting (utils/renderer.py:
+    286-572): hand + object fields frozen, gradients to the hand pose (bt_inv) and the object pose (Ro, To) only."""
+    import ref_conf
+    import synth
+    hsp, hcp = synth.hand_states()
+    osp, ocp = synth.obj_states()
+    emb = H.Embedding()
+    hs = H.SDFNetwork(emb, 4, "real", use_batch=False, **ref_conf.HAND_SDF_CONF)
+    hc = H.RenderingNetwork(emb, "real", **ref_conf.HAND_COLOR_CONF)
+    os_ = H.SDFNetwork_OBJ(emb, 4, "real", **ref_conf.OBJ_SDF_CONF)
+    oc = H.RenderingNetwork_OBJ(emb, "real", **ref_conf.OBJ_COLOR_CONF)
+    hd, od = H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT), H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT)
+    hs.load_state_dict(hsp); hc.load_state_dict(hcp); os_.load_state_dict(osp); oc.load_state_dict(ocp)
+    for m in (hs, hc, hd, os_, oc, od):
+        m.to(device)
+        for q in m.parameters():
+            q.requires_grad_(False)
+    r = H.renderer.NeuSRenderer_fitting(hs, hd, hc, os_, od, oc, **ref_conf.RENDERER_CONF)
+    bt, T, J = synth.hand_pose()
+    HR = synth.hand_rays(n_rays, J, seed=7)
+    g = torch.Generator().manual_seed(106)
+    Ro = synth.random_rotation(g).to(device).requires_grad_(True)
+    To = (J.mean(0) + 0.02 * torch.randn(3, generator=g)).to(device).requires_grad_(True)
+    true_rgb = torch.rand(n_rays, 3, generator=g).to(device)
+    bt = bt.to(device).requires_grad_(True)
+    T = T.to(device)
+    ro, rd = HR["rays_o"].to(device), HR["rays_d"].to(device)
+
+    def step():
+        out = r.render(ro, rd, HR["near"], HR["far"], bt, T, None, Ro, To)
+        loss = (out["color_fine"] - true_rgb).abs().mean() + 0.5 * out["weight_sum"].mean() \
+            + out["sdf_hand"].clip(-1, 0).abs().mean() + out["sdf_obj"].clip(-1, 0).abs().mean()
+        bt.grad = None; Ro.grad = None; To.grad = None
+        loss.backward()
+        return out
+
+    for _ in range(2):
+        out = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return {"rays": n_rays, "samples_per_ray_and_field": int(out["sdf_hand"].shape[0] // n_rays), "ms_per_step": ms,
+            "value": n_rays / (ms * 1e-3), "unit": "rays/s", "precision": precision,
+            "finite_pose_grads": bool(torch.isfinite(bt.grad).all() and torch.isfinite(Ro.grad).all()),
+            "note": "eager launches; hand field on per-layer TF32x3 kernels, object field on the chain kernels"}
+
+
 def _dbg(msg):
     if os.environ.get("BENCH_DEBUG"):
         sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter(), msg))
@@ -406,6 +459,13 @@ def run_gpu_arm(args):
         except Exception as e:      # noqa: BLE001
             grid = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
+    fit = None
+    if rank == 0 and world == 1 and args.fit_rays > 0:
+        try:
+            fit = fitting_extra(H, device, args.fit_rays, args.precision)
+        except Exception as e:      # noqa: BLE001
+            fit = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, dt, cores = time_cpu(min(n_rays, 512), 3, 1)
@@ -428,7 +488,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large, "sdf_grid": grid,
+            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large, "sdf_grid": grid, "fitting_step": fit,
             "mlp_flops_per_ray": FLOPS_PER_RAY_TRAIN,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -570,6 +630,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")
+    ap.add_argument("--fit-rays", type=int, default=512, help="extra informational two-field fitting step (0 disables)")
     ap.add_argument("--grid-res", type=int, default=256, help="extra informational SDF-lattice measurement (0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
