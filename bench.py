@@ -242,6 +242,50 @@ def fitting_extra(H, device, n_rays, precision):
             "note": "eager launches; hand field on per-layer TF32x3 kernels, object field on the chain kernels"}
 
 
+def _time_calls(fn, warm=2, reps=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def forward_extras(H, device, renderer, batch, host, Ro, To, hand_rays_n):
+    """Informational forward-only renders (no autograd): BASELINE configs[0]'s shape on the GPU (object field, 512 rays)
+    and configs[3]'s hand field on a full-image chunk of rays."""
+    import ref_conf
+    import synth
+    res = {}
+    with torch.no_grad():
+        n = batch["rays_o"].shape[0]
+        ms = _time_calls(lambda: renderer.render(batch["rays_o"], batch["rays_d"], host["near"], host["far"], None, None,
+                                                 None, Ro, To, 0))
+        res["obj_render_fwd"] = {"rays": n, "ms": ms, "value": n / (ms * 1e-3), "unit": "rays/s",
+                                 "algorithmic_tflops": n * (112 * F_O + 128 * (2 * F_O + C_O)) / (ms * 1e-3) / 1e12}
+        hsp, hcp = synth.hand_states()
+        emb = H.Embedding()
+        hs = H.SDFNetwork(emb, 4, "real", use_batch=False, **ref_conf.HAND_SDF_CONF)
+        hc = H.RenderingNetwork(emb, "real", **ref_conf.HAND_COLOR_CONF)
+        hd = H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT)
+        hs.load_state_dict(hsp); hc.load_state_dict(hcp)
+        for m in (hs, hc, hd):
+            m.to(device)
+        rh = H.NeuSRenderer(hs, hd, hc, "hand", **ref_conf.RENDERER_CONF)
+        bt, T, J = synth.hand_pose()
+        HR = synth.hand_rays(hand_rays_n, J, seed=7)
+        bt, T = bt.to(device), T.to(device)
+        ro, rd = HR["rays_o"].to(device), HR["rays_d"].to(device)
+        ms = _time_calls(lambda: rh.render(ro, rd, HR["near"], HR["far"], bt, T, None, None, None, 0))
+        res["hand_render_fwd"] = {"rays": hand_rays_n, "ms": ms, "value": hand_rays_n / (ms * 1e-3), "unit": "rays/s",
+                                  "note": "hand field on the per-layer kernels (chain kernels: object field only)"}
+    return res
+
+
 def _dbg(msg):
     if os.environ.get("BENCH_DEBUG"):
         sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter(), msg))
@@ -466,6 +510,13 @@ def run_gpu_arm(args):
         except Exception as e:      # noqa: BLE001
             fit = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
+    fwd_extra = None
+    if rank == 0 and world == 1 and args.fit_rays > 0:
+        try:
+            fwd_extra = forward_extras(H, device, renderer, dev_batch, host, Ro, To, 4096)
+        except Exception as e:      # noqa: BLE001
+            fwd_extra = {"error": str(e)[:200]}
+        torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rps, dt, cores = time_cpu(min(n_rays, 512), 3, 1)
@@ -488,7 +539,7 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large, "sdf_grid": grid, "fitting_step": fit,
+            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large, "sdf_grid": grid, "fitting_step": fit, "forward_only": fwd_extra,
             "mlp_flops_per_ray": FLOPS_PER_RAY_TRAIN,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -630,8 +681,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")
-    ap.add_argument("--fit-rays", type=int, default=512, help="extra informational two-field fitting step (0 disables)")
-    ap.add_argument("--grid-res", type=int, default=256, help="extra informational SDF-lattice measurement (0 disables)")
+    ap.add_argument("--fit-rays", type=int, default=512, help="extra informational measurements: two-field fitting step, forward-only renders (0 disables)")
+    ap.add_argument("--grid-res", type=int, default=512, help="extra informational SDF-lattice measurement (0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
