@@ -241,6 +241,13 @@ static void set_w(GemmArgs& g, const hn_mlp_t* m, int l, int col_off = 0) {
     // weights of layer l, optionally starting at input column col_off (a multiple of 4)
     g.B = m->W[l] + col_off; g.ldb = m->ld[l];
     g.BT = m->WT[l] ? m->WT[l] + (int64_t)col_off * m->ldT[l] : nullptr; g.ldbt = m->ldT[l];
+    if (m->chain && col_off % 256 == 0) {      // pre-packed bf16 hi/lo operands (hn_mlp_bx3_pack), HN_TC_BF16X3 only
+        const Bx3Layout L = bx3_layout(m);
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(m->chain);
+        g.Bp = base + L.w[l]; g.bp_tile_bytes = bx3_tile_bytes(m->in_dim[l]); g.bp_kb0 = col_off / 64;
+        g.btp_tile_bytes = bx3_tile_bytes(m->out_dim[l]);
+        g.BTp = base + L.wt[l] + (col_off / 256) * g.btp_tile_bytes;
+    }
 }
 
 // forward trunk: HROW feature -> H7.  H[] / ldH describe where each layer's activation goes.

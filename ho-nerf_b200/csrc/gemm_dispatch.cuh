@@ -1,6 +1,8 @@
 // Precision-aware dispatch of the dense contractions:
 //   HN_SIMT_FP32  -> gemm_simt.cuh (fp32 FFMA, verification path)
 //   HN_TC_TF32    -> tcgen05, single-pass TF32 operands everywhere (fast, ~1e-3 relative per layer)
+//   HN_TC_BF16X3  -> the fused chain kernels where they exist (object nets); elsewhere gemm_bx3.cuh (pre-packed bf16
+//                    hi/lo weights, three bf16 MMAs per product) when the net carries packed operands, else TF32X3
 //   HN_TC_TF32X3  -> tcgen05, split (hi+lo) TF32 operands everywhere: three MMAs per product, ~fp32
 //                    accuracy; this is the mode that meets the north-star tolerances with margin
 //                    (weight-norm backward amplifies TF32-level errors of dW by ~10x, and the colour
@@ -8,6 +10,7 @@
 #pragma once
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_bx3.cuh"
 
 namespace hn {
 
@@ -22,6 +25,7 @@ template <int EPI>
 int gemm_nt(const GemmArgs& g, cudaStream_t s, int precision, int role = ROLE_OTHER) {
     (void)role;
     if (precision == HN_SIMT_FP32) return launch_gemm<true, true, EPI>(g, s);
+    if (precision == HN_TC_BF16X3 && g.Bp) return launch_gemm_bx3<EPI>(g, s);
     if (precision == HN_TC_TF32X3 || precision == HN_TC_BF16X3) return launch_gemm_tc<false, 3, EPI>(g, s);
     return launch_gemm_tc<false, 1, EPI>(g, s);
 }
@@ -30,6 +34,11 @@ template <int EPI>
 int gemm_nn(const GemmArgs& g, cudaStream_t s, int precision, int role = ROLE_OTHER) {
     (void)role;
     if (precision == HN_SIMT_FP32) return launch_gemm<true, false, EPI>(g, s);
+    if (precision == HN_TC_BF16X3 && g.BTp) {
+        GemmArgs t = g;
+        t.Bp = g.BTp; t.bp_tile_bytes = g.btp_tile_bytes; t.bp_kb0 = 0;
+        return launch_gemm_bx3<EPI>(t, s);
+    }
     if (g.BT) {
         // a pre-transposed copy of the weights exists: run as x @ (W^T)^T, the cheap staging path
         GemmArgs t = g;

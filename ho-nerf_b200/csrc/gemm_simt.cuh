@@ -29,6 +29,10 @@ struct GemmArgs {
     const float* A = nullptr; int64_t lda = 0;
     const float* B = nullptr; int64_t ldb = 0;
     const float* BT = nullptr; int64_t ldbt = 0;   // optional transposed copy of B (d @ W on tensor cores)
+    // HN_TC_BF16X3 without a chain kernel: B (resp. BT) pre-packed as bf16 hi/lo tcgen05 tiles (gemm_bx3.cuh), 256-row
+    // tiles `*_tile_bytes` apart, starting at k-block bp_kb0
+    const uint8_t* Bp = nullptr; int64_t bp_tile_bytes = 0; int bp_kb0 = 0;
+    const uint8_t* BTp = nullptr; int64_t btp_tile_bytes = 0;
     int M = 0, N = 0, K = 0;
     float* C = nullptr; int64_t ldc = 0;
     float* C2 = nullptr; int64_t ldc2 = 0;

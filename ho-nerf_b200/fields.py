@@ -96,7 +96,7 @@ class _PackedNet(nn.Module):
             layers = [(getattr(self, "lin%d" % l).weight_g, getattr(self, "lin%d" % l).weight_v,
                        getattr(self, "lin%d" % l).bias) for l in range(n)]
             scales = self._post_scales or [1.0] * n
-            self._packed = ops.PackedMLP(layers, scales, self._gaps)
+            self._packed = ops.PackedMLP(layers, scales, self._gaps, chain_kind="bx3")
         return self._packed
 
     def _apply(self, fn, *a, **k):      # .to()/.cuda()/.float() replace the parameter tensors

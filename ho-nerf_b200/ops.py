@@ -84,7 +84,7 @@ class PackedMLP:
         self.WT = None
         self.W = None
         self.bias = None
-        self.chain_kind = chain_kind        # 'sdf_obj' | 'color_obj': also pack the HN_TC_BF16X3 chain operands
+        self.chain_kind = chain_kind        # 'sdf_obj' | 'color_obj' | 'bx3': also pack the HN_TC_BF16X3 operands
         self.chain = None
         self.struct = None
         self._key = None
@@ -122,7 +122,16 @@ class PackedMLP:
             st.b[l] = bd.data_ptr()
         # every layer's g * v / ||v|| (and its transposed copy) in one launch
         check(lib.hn_wn_pack_batch(jobs, len(self.layers), _stream(self.W)), "hn_wn_pack_batch")
-        if self.chain_kind is not None:
+        if self.chain_kind == "bx3":
+            # no fused chain kernel for this net (hand field): pre-packed bf16 hi/lo operands of every layer for the
+            # per-layer HN_TC_BF16X3 contractions
+            nbytes = int(lib.hn_mlp_bx3_bytes(ctypes.byref(st)))
+            if self.chain is None or self.chain.device != dev or self.chain.numel() < nbytes:
+                self.chain = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            check(lib.hn_mlp_bx3_pack(ctypes.byref(st), _ptr(self.chain), nbytes, _stream(self.W)), "hn_mlp_bx3_pack")
+            st.chain = self.chain.data_ptr()
+            st.chain_bytes = nbytes
+        elif self.chain_kind is not None:
             size_fn, pack_fn = {"sdf_obj": (lib.hn_sdf_obj_chain_bytes, lib.hn_sdf_obj_chain_pack),
                                 "color_obj": (lib.hn_color_obj_chain_bytes, lib.hn_color_obj_chain_pack)}[self.chain_kind]
             nbytes = int(size_fn())

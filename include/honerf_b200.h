@@ -124,6 +124,13 @@ typedef struct hn_wn_job {
 HN_API int hn_wn_pack_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream);
 HN_API int hn_wn_bwd_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream);
 
+/* HN_TC_BF16X3 for nets without a fused chain kernel (the hand field, utils/fields.py:56-240): every layer's weights
+ * pre-packed as bf16 hi/lo tcgen05 tiles, both as the operand of x @ W^T and of d @ W (needs W and WT of every layer).
+ * Point hn_mlp_t::chain at the packed buffer; the per-layer contractions then run three bf16 MMAs per product instead
+ * of the split-TF32 kernel.  hn_mlp_bx3_bytes: size of that buffer. */
+HN_API int64_t hn_mlp_bx3_bytes(const hn_mlp_t* m);
+HN_API int hn_mlp_bx3_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_stream_t stream);
+
 /* Adam over one flat fp32 parameter buffer (torch.optim.Adam semantics; the reference builds one Adam over all
  * networks' parameters, exp_runner.py:83).  p, m, v [n] are updated in place from g [n] * grad_scale; `step` is a
  * DEVICE float holding the 1-based step count (the caller increments it before the call), so the launch is the
