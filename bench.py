@@ -322,7 +322,12 @@ def run_gpu_arm(args):
     def fwd_bwd(b):
         """render + loss + backward; for N > 1 also packs every gradient into one flat buffer"""
         out = renderer.render(b["rays_o"], b["rays_d"], host["near"], host["far"], None, None, None, Ro, To, 0)
-        loss = training_loss(out, b["true_rgb"], b["true_mask"])
+        if args.loss == "fused":
+            # csrc/loss.cu: one forward + one backward launch instead of ~30 torch launches (SURVEY 8f row 2)
+            loss = H.ops.render_loss(out["color_fine"], out["weight_sum"], b["true_rgb"], b["true_mask"],
+                                     out["gradient_error"], 0.0, 1.0, 1.0, 1.0)[0]
+        else:
+            loss = training_loss(out, b["true_rgb"], b["true_mask"])
         opt.zero_grad(set_to_none=True)
         Ro.grad = None; To.grad = None
         loss.backward()
@@ -535,6 +540,7 @@ def run_gpu_arm(args):
                        "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
                        "cuda_graph": graph is not None,
                        "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
+                       "loss": "hn_render_loss_fwd/_bwd (fused)" if args.loss == "fused" else "torch ops",
                        "l2": "per-step activation stash (~2 GB at 512 rays) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
@@ -678,6 +684,8 @@ def main():
     ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
+    ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
+                    help="fused: hn_render_loss_fwd/_bwd (default); torch: the reference's loss lines as torch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")

@@ -4,8 +4,8 @@ from ._lib import HonerfError, launch_count  # noqa: F401
 from .fields import (Embedding, RenderingNetwork, RenderingNetwork_OBJ, SDFNetwork,  # noqa: F401
                      SDFNetwork_OBJ, SingleVarianceNetwork)
 from .ops import set_default_precision  # noqa: F401
-from . import renderer, renderer_batch  # noqa: F401
+from . import losses, rays, renderer, renderer_batch  # noqa: F401
 from .renderer import NeuSRenderer, NeuSRenderer_fitting  # noqa: F401
 
 __all__ = ["Embedding", "SDFNetwork", "RenderingNetwork", "SDFNetwork_OBJ", "RenderingNetwork_OBJ", "SingleVarianceNetwork",
-           "NeuSRenderer", "NeuSRenderer_fitting", "renderer", "renderer_batch", "ops", "HonerfError", "launch_count", "set_default_precision"]
+           "NeuSRenderer", "NeuSRenderer_fitting", "renderer", "renderer_batch", "losses", "rays", "ops", "HonerfError", "launch_count", "set_default_precision"]

@@ -726,3 +726,163 @@ def fit_composite(alpha_h, rgb_h, alpha_o, rgb_o):
 
 
 SQRT1_2 = 1.0 / math.sqrt(2.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# ray generation
+# ------------------------------------------------------------------------------------------------
+def pack_cameras(R, T, focal_length, principal_point):
+    """pytorch3d PerspectiveCameras arguments ([n,3,3], [n,3], [n,2], [n,2]; a missing batch axis is added) ->
+    [n,16] device floats  R | T | fx fy | px py  (the camera record of include/honerf_b200.h)."""
+    R = R.reshape(-1, 3, 3)
+    n = R.shape[0]
+    parts = [_f32c(R).reshape(n, 9), _f32c(T).reshape(n, 3), _f32c(focal_length).reshape(-1, 2).expand(n, 2),
+             _f32c(principal_point).reshape(-1, 2).expand(n, 2)]
+    return torch.cat(parts, dim=1).contiguous()
+
+
+def rays_from_ndc(xy, cams):
+    """utils/utils.py:31-115 (_xy_to_ray_bundle, unit directions): xy [n_cams, ..., 2] NDC, cams [n_cams,16]
+    -> origins, directions [n_cams, ..., 3]."""
+    xy_c, cams_c = _f32c(xy.detach()), _f32c(cams.detach())
+    _require_cuda(xy_c, "rays_from_ndc")
+    _require_cuda(cams_c, "rays_from_ndc")
+    n_cams = cams_c.shape[0]
+    if xy_c.shape[0] != n_cams or xy_c.shape[-1] != 2 or cams_c.shape[-1] != 16:
+        raise _lib.HonerfError("rays_from_ndc: xy %s does not match cams %s" % (tuple(xy.shape), tuple(cams.shape)))
+    per = xy_c[0].numel() // 2 if n_cams else 0
+    o = torch.empty(*xy_c.shape[:-1], 3, device=xy_c.device)
+    d = torch.empty_like(o)
+    check(lib.hn_rays_from_ndc(_ptr(xy_c), _ptr(cams_c), n_cams, per, _ptr(o), _ptr(d), _stream(xy_c)),
+          "hn_rays_from_ndc")
+    return o, d
+
+
+def ndc_grid_axes(H, W, device):
+    """The reference's full-image NDC axes (exp_runner.py:338-348), made by torch so they are its values."""
+    if W >= H:
+        range_x, range_y = W / H, 1.0
+    else:
+        range_x, range_y = 1.0, H / W
+    return (torch.linspace(range_x, -range_x, W).to(device), torch.linspace(range_y, -range_y, H).to(device))
+
+
+def rays_ndc_grid(xs, ys, cam, first, count):
+    """Rays of pixels [first, first+count) of the H x W image whose NDC axes are xs [W], ys [H] (pixel = row*W + col):
+    the chunk rays_o.split(batch_size)[k] of exp_runner.py:349-355 without the full-image ray list."""
+    xs_c, ys_c, cam_c = _f32c(xs), _f32c(ys), _f32c(cam).reshape(-1)
+    _require_cuda(xs_c, "rays_ndc_grid")
+    if cam_c.numel() != 16:
+        raise _lib.HonerfError("rays_ndc_grid: one camera (16 floats) expected")
+    o = torch.empty(count, 3, device=xs_c.device)
+    d = torch.empty_like(o)
+    check(lib.hn_rays_ndc_grid(_ptr(xs_c), _ptr(ys_c), xs_c.numel(), ys_c.numel(), _ptr(cam_c), first, count, _ptr(o),
+                               _ptr(d), _stream(xs_c)), "hn_rays_ndc_grid")
+    return o, d
+
+
+# ------------------------------------------------------------------------------------------------
+# loss epilogues (SURVEY.md 8f row 2)
+# ------------------------------------------------------------------------------------------------
+_loss_ws = {}
+
+
+def _loss_workspace(device):
+    """Per device AND stream: the kernels leave the workspace clean, so it is zeroed once."""
+    key = (str(device), torch.cuda.current_stream(device).cuda_stream)
+    if key not in _loss_ws:
+        _loss_ws[key] = torch.zeros(int(lib.hn_loss_ws_floats()), device=device)
+    return _loss_ws[key]
+
+
+class _RenderLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, color, wsum, grad_err, true_rgb, true_mask, color_div, color_w, mask_w, igr_w):
+        c, w = _f32c(color.detach()).reshape(-1, 3), _f32c(wsum.detach()).reshape(-1)
+        t, m = _f32c(true_rgb.detach()).reshape(-1, 3), _f32c(true_mask.detach()).reshape(-1)
+        _require_cuda(c, "render_loss")
+        n = c.shape[0]
+        if w.numel() != n or t.shape[0] != n or m.numel() != n:
+            raise _lib.HonerfError("render_loss: color %s, weight_sum %s, true_rgb %s, true_mask %s disagree"
+                                   % (tuple(color.shape), tuple(wsum.shape), tuple(true_rgb.shape), tuple(true_mask.shape)))
+        ge = _f32c(grad_err.detach()).reshape(1) if grad_err is not None else None
+        out = torch.empty(8, device=c.device)
+        check(lib.hn_render_loss_fwd(_ptr(c), _ptr(w), _ptr(t), _ptr(m), _ptr(ge), n, float(color_div), float(color_w),
+                                     float(mask_w), float(igr_w), _ptr(_loss_workspace(c.device)), _ptr(out),
+                                     _stream(c)), "hn_render_loss_fwd")
+        ctx.save_for_backward(c, w, t, m, out)
+        ctx.coef = (float(color_w), float(mask_w), float(igr_w))
+        ctx.shapes = (color.shape, wsum.shape, grad_err.shape if grad_err is not None else None)
+        stats = out[1:4]
+        ctx.mark_non_differentiable(stats)
+        return out[0], stats
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g, _g_stats):
+        c, w, t, m, out = ctx.saved_tensors
+        n = c.shape[0]
+        g = _f32c(g).reshape(1)
+        d_c = torch.empty(n, 3, device=c.device)
+        d_w = torch.empty(n, device=c.device)
+        d_ge = torch.empty(1, device=c.device) if ctx.shapes[2] is not None else None
+        check(lib.hn_render_loss_bwd(_ptr(g), _ptr(c), _ptr(w), _ptr(t), _ptr(m), _ptr(out), n, ctx.coef[0], ctx.coef[1],
+                                     ctx.coef[2], _ptr(d_c), _ptr(d_w), _ptr(d_ge), _stream(c)), "hn_render_loss_bwd")
+        return (d_c.reshape(ctx.shapes[0]), d_w.reshape(ctx.shapes[1]),
+                d_ge.reshape(ctx.shapes[2]) if d_ge is not None else None, None, None, None, None, None, None)
+
+
+def render_loss(color, weight_sum, true_rgb, true_mask, gradient_error=None, color_div=0.0, color_weight=1.0,
+                mask_weight=1.0, igr_weight=1.0):
+    """Fused render loss: returns (total, stats) with stats = [color_loss, mask_loss, psnr] (not differentiable).
+    color_div <= 0: the training normaliser mask_sum + 1e-5 (exp_runner.py:207,221); > 0: an explicit divisor
+    (fitting_single.py:254: n rays; fitting_video.py:288: F * P).  true_mask must already be 0/1."""
+    return _RenderLossFn.apply(color, weight_sum, gradient_error, true_rgb, true_mask, color_div, color_weight,
+                               mask_weight, igr_weight)
+
+
+class _InteractionLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sdf_h, sdf_o, thr, w_c, w_p):
+        h, o = _f32c(sdf_h.detach()), _f32c(sdf_o.detach())
+        _require_cuda(h, "interaction_loss")
+        h2, o2 = h.reshape(h.shape[0], -1), o.reshape(o.shape[0], -1)
+        n = h2.shape[0]
+        if o2.shape[0] != n:
+            raise _lib.HonerfError("interaction_loss: %d hand samples vs %d object samples" % (n, o2.shape[0]))
+        out = torch.empty(8, device=h.device)
+        check(lib.hn_interaction_loss_fwd(_ptr(h2), h2.shape[1], _ptr(o2), o2.shape[1], n, float(thr), float(w_c),
+                                          float(w_p), _ptr(_loss_workspace(h.device)), _ptr(out), _stream(h)),
+              "hn_interaction_loss_fwd")
+        ctx.save_for_backward(h2, o2, out)
+        ctx.args = (float(thr), float(w_c), float(w_p))
+        ctx.shapes = (sdf_h.shape, sdf_o.shape)
+        stats = out[1:5]
+        ctx.mark_non_differentiable(stats)
+        return out[0], stats
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g, _g_stats):
+        h2, o2, out = ctx.saved_tensors
+        n = h2.shape[0]
+        g = _f32c(g).reshape(1)
+        d_h = torch.empty(n, device=h2.device)
+        d_o = torch.empty(n, device=h2.device)
+        check(lib.hn_interaction_loss_bwd(_ptr(g), _ptr(h2), h2.shape[1], _ptr(o2), o2.shape[1], _ptr(out), n,
+                                          ctx.args[0], ctx.args[1], ctx.args[2], _ptr(d_h), _ptr(d_o), _stream(h2)),
+              "hn_interaction_loss_bwd")
+
+        def widen(d, like):
+            if like.shape[1] == 1:
+                return d.reshape(-1, 1)
+            full = torch.zeros_like(like)
+            full[:, 0] = d
+            return full
+        return widen(d_h, h2).reshape(ctx.shapes[0]), widen(d_o, o2).reshape(ctx.shapes[1]), None, None, None
+
+
+def interaction_loss(sdf_hand, sdf_obj, contact_thr=1e-2, w_contact=30.0, w_penet=20.0):
+    """Contact + penetration terms of fitting_single.py:268-283 on column 0 of render_out['sdf_hand'] / ['sdf_obj']:
+    returns (w_contact * contact + w_penet * penet, stats = [contact, penet, contact_num, penet_num])."""
+    return _InteractionLossFn.apply(sdf_hand, sdf_obj, contact_thr, w_contact, w_penet)

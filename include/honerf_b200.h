@@ -333,6 +333,57 @@ HN_API int hn_fit_composite_bwd(const float* alpha_h, const float* rgb_h, const 
                                 hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Ray generation: utils/utils.py:31-115 (_xy_to_ray_bundle) on top of pytorch3d's
+ * PerspectiveCameras.unproject_points(from_ndc=True).  A camera is 16 device floats:
+ * R[9] (row-major, pytorch3d row-vector convention X_view = X_world R + T) | T[3] | fx fy | px py (NDC).
+ * origins = P(depth 1) - dir,  dir = normalize(P(depth 2) - P(depth 1)).
+ * ------------------------------------------------------------------------------------------- */
+/* xy [n_cams, n_per_cam, 2] NDC coordinates, cams [n_cams, 16] -> rays_o, rays_d [n_cams * n_per_cam, 3]. */
+HN_API int hn_rays_from_ndc(const float* xy, const float* cams, int64_t n_cams, int64_t n_per_cam,
+                            float* rays_o, float* rays_d, hn_stream_t stream);
+/* Full-image form (exp_runner.py:338-350): pixel p = row * W + col has NDC (xs[col], ys[row]); xs [W], ys [H] are
+ * the reference's linspace values (made by torch on the host so they are its values bit for bit).  Writes the
+ * `count` rays of pixels [first, first + count): a chunk of rays_o.split(batch_size) without the full-image list. */
+HN_API int hn_rays_ndc_grid(const float* xs, const float* ys, int W, int H, const float* cam, int64_t first,
+                            int64_t count, float* rays_o, float* rays_d, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss epilogues: one forward launch (deterministic two-level sums) + one elementwise
+ * backward launch writing the cotangents of the render outputs.  `ws`: hn_loss_ws_floats() floats, ZEROED once
+ * by the caller before its first use (the kernels leave it clean); `out`: 8 floats.
+ * ------------------------------------------------------------------------------------------- */
+HN_API int64_t hn_loss_ws_floats(void);
+/* Render loss of exp_runner.py:206-227 (training: color_div <= 0 -> divide by mask_sum + 1e-5),
+ * fitting_single.py:253-256 (color_div = n_rays) and fitting_video.py:287-291 (color_div = F * P):
+ *   color_loss = sum |(color - true_rgb) * mask| / div,  mask_loss = mean BCE(clip(weight_sum, 1e-3, 1 - 1e-3), mask),
+ *   total = color_weight * color_loss + mask_weight * mask_loss + igr_weight * (*gradient_error, may be NULL).
+ * color, true_rgb [n,3]; weight_sum, true_mask [n] (mask already thresholded to 0/1).
+ * out: [0] total, [1] color_loss, [2] mask_loss, [3] psnr (exp_runner.py:222), [4] divisor, [5] mask_sum + 1e-5,
+ * [6] eikonal term. */
+HN_API int hn_render_loss_fwd(const float* color, const float* weight_sum, const float* true_rgb,
+                              const float* true_mask, const float* gradient_error, int64_t n_rays,
+                              float color_div, float color_weight, float mask_weight, float igr_weight,
+                              float* ws, float* out, hn_stream_t stream);
+/* g_loss: device scalar (NULL = 1).  fwd_out: the forward's `out`.  d_gradient_error may be NULL. */
+HN_API int hn_render_loss_bwd(const float* g_loss, const float* color, const float* weight_sum,
+                              const float* true_rgb, const float* true_mask, const float* fwd_out,
+                              int64_t n_rays, float color_weight, float mask_weight, float igr_weight,
+                              float* d_color, float* d_weight_sum, float* d_gradient_error,
+                              hn_stream_t stream);
+/* Contact / penetration terms of fitting_single.py:268-283 and fitting_video.py:295-309 on column 0 of the
+ * per-sample SDFs (element i at sdf[i * ld]):
+ *   contact = mean over {|h| + |o| < contact_thr} of (|h| + |o|),  penet = mean over {h < 0, o < 0} of (|h| + |o|),
+ *   counts carry the reference's + 1e-9.  out: [0] w_contact * contact + w_penet * penet, [1] contact, [2] penet,
+ *   [3] contact count, [4] penetration count.  d_sdf_hand / d_sdf_obj: dense [n_pts]. */
+HN_API int hn_interaction_loss_fwd(const float* sdf_hand, int64_t ld_hand, const float* sdf_obj, int64_t ld_obj,
+                                   int64_t n_pts, float contact_thr, float w_contact, float w_penet, float* ws,
+                                   float* out, hn_stream_t stream);
+HN_API int hn_interaction_loss_bwd(const float* g_loss, const float* sdf_hand, int64_t ld_hand,
+                                   const float* sdf_obj, int64_t ld_obj, const float* fwd_out, int64_t n_pts,
+                                   float contact_thr, float w_contact, float w_penet, float* d_sdf_hand,
+                                   float* d_sdf_obj, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Diagnostics: C[M,N] (fp32) = A[M,K] * B[N,K]^T with fp16 (or bf16) operands on tcgen05 tensor cores
  * (fp32 accumulation in TMEM).  Self-test of the descriptors / TMEM / mbarrier plumbing shared by the
  * fused field kernels.  16 <= N <= 256, N % 16 == 0, K % 64 == 0.

@@ -263,3 +263,58 @@ def halo_grad_hvp(q, cutoff, c, w=None):
         + (h1 * G + h * A1)[..., None] * dr \
         + (h1 * dv / v)[..., None] * Pb1 + (h / v)[..., None] * dPb1 - (h * dv / (v * v))[..., None] * Pb1
     return g, jvp, hvp
+
+
+# --------------------------------------------------------------------------------------------
+# Closed forms used by csrc/loss.cu and csrc/rays.cu (no autograd), checked against the reference's golden vectors
+# on the CPU before the kernels are trusted on the GPU (tests/test_oracle_8f.py).
+# --------------------------------------------------------------------------------------------
+def render_loss_closed_form(color, wsum, true_rgb, mask, grad_err, color_div, color_w, mask_w, igr_w, g=1.0):
+    """Forward sums and the backward formulas of render_loss_fwd/bwd_kernel."""
+    n = color.shape[0]
+    m = mask.reshape(n, 1)
+    err = (color - true_rgb) * m
+    mask_sum = m.sum() + 1e-5
+    div = color_div if color_div > 0 else mask_sum
+    p = wsum.reshape(n, 1).clip(1e-3, 1.0 - 1e-3)
+    bce = (m - 1.0) * torch.log1p(-p).clamp_min(-100.0) - m * torch.log(p).clamp_min(-100.0)
+    color_loss = err.abs().sum() / div
+    mask_loss = bce.sum() / n
+    ge = grad_err if grad_err is not None else 0.0
+    total = color_w * color_loss + mask_w * mask_loss + igr_w * ge
+    d_color = g * color_w / div * torch.sign(err) * m
+    w = wsum.reshape(n, 1)
+    passes = ((w >= 1e-3) & (w <= 1.0 - 1e-3)).to(color.dtype)
+    d_wsum = passes * g * mask_w * (p - m) / ((1.0 - p) * p).clamp_min(1e-12) / n
+    return total, color_loss, mask_loss, d_color, d_wsum, g * igr_w
+
+
+def interaction_closed_form(sdf_h, sdf_o, thr, w_c, w_p, g=1.0):
+    h, o = sdf_h[:, 0], sdf_o[:, 0]
+    a = h.abs() + o.abs()
+    contact = a < thr
+    pen = (o < 0) & (h < 0)
+    cnum = contact.to(h.dtype).sum() + 1e-9
+    pnum = pen.to(h.dtype).sum() + 1e-9
+    c_loss, p_loss = (a * contact).sum() / cnum, (a * pen).sum() / pnum
+    k = g * (contact.to(h.dtype) * w_c / cnum + pen.to(h.dtype) * w_p / pnum)
+    return w_c * c_loss + w_p * p_loss, c_loss, p_loss, k * torch.sign(h), k * torch.sign(o)
+
+
+def rays_closed_form(R, T, focal, pp, xy):
+    """csrc/rays.cu: adjugate inverse of R, per-ray un-projection of the depth-1 / depth-2 points (single camera)."""
+    r = R.reshape(9)
+    c00, c01, c02 = r[4] * r[8] - r[5] * r[7], r[5] * r[6] - r[3] * r[8], r[3] * r[7] - r[4] * r[6]
+    det = r[0] * c00 + r[1] * c01 + r[2] * c02
+    inv = torch.stack([c00, r[2] * r[7] - r[1] * r[8], r[1] * r[5] - r[2] * r[4],
+                       c01, r[0] * r[8] - r[2] * r[6], r[2] * r[3] - r[0] * r[5],
+                       c02, r[1] * r[6] - r[0] * r[7], r[0] * r[4] - r[1] * r[3]]).reshape(3, 3) / det
+
+    def unproject(depth):
+        v = torch.stack([(xy[..., 0] - pp[0]) / focal[0] * depth - T[0], (xy[..., 1] - pp[1]) / focal[1] * depth - T[1],
+                         torch.full_like(xy[..., 0], depth) - T[2]], dim=-1)
+        return v @ inv
+    p1, p2 = unproject(1.0), unproject(2.0)
+    d = p2 - p1
+    d = d / d.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+    return p1 - d, d

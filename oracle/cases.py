@@ -89,3 +89,36 @@ def fit_loss(out, true_rgb):
 
 def sdf_grid_case():
     return dict(res=12, lo=-0.6, hi=0.6)
+
+
+def loss_case(n=200, seed=301):
+    """Render outputs as the loss epilogues see them: colours in (0,1), weight sums that hit both clip bounds,
+    SDF pairs with contact (|h|+|o| < 1e-2) and penetration (h<0, o<0) populations."""
+    g = torch.Generator().manual_seed(seed)
+    color = torch.rand(n, 3, generator=g)
+    wsum = (torch.rand(n, 1, generator=g) * 1.2 - 0.1).clip(0.0, 1.05)
+    wsum[:5] = torch.tensor([[0.0], [1e-3], [1.0 - 1e-3], [1.0], [0.5]])
+    true_rgb = torch.rand(n, 3, generator=g)
+    true_rgb[7] = color[7]                       # exact zero error: sign(0) = 0
+    true_mask = (torch.rand(n, 1, generator=g) > 0.4).float()
+    grad_err = torch.tensor(0.137)
+    m = 6 * n
+    sdf_h = 0.02 * torch.randn(m, 1, generator=g)
+    sdf_o = 0.02 * torch.randn(m, 1, generator=g)
+    sdf_h[:3] = torch.tensor([[0.0], [-0.001], [0.004]])
+    sdf_o[:3] = torch.tensor([[-0.002], [0.0], [0.0]])
+    return dict(color=color, wsum=wsum, true_rgb=true_rgb, true_mask=true_mask, grad_err=grad_err, sdf_h=sdf_h,
+                sdf_o=sdf_o)
+
+
+def rays_case(seed=302):
+    """Two cameras on a ring looking roughly at the origin (pytorch3d row-vector convention), NDC intrinsics like
+    the reference's labels (fx_ndc ~ 2-3, small principal-point offsets), random NDC points and a 7 x 5 image."""
+    import synth
+    g = torch.Generator().manual_seed(seed)
+    R = torch.stack([synth.random_rotation(g) for _ in range(2)])
+    T = torch.tensor([[0.02, -0.03, 0.95], [-0.05, 0.01, 1.10]]) + 0.01 * torch.randn(2, 3, generator=g)
+    focal = torch.tensor([[2.3, 2.4], [2.9, 2.8]])
+    pp = torch.tensor([[0.03, -0.02], [-0.04, 0.05]])
+    xy = torch.rand(2, 33, 2, generator=g) * 2.4 - 1.2
+    return dict(R=R, T=T, focal=focal, pp=pp, xy=xy, H=5, W=7)

@@ -545,3 +545,72 @@ def sdf_grid(sdf_fn, bound_min: Tensor, bound_max: Tensor, resolution: int, chun
             pts = torch.stack([xx, yy, zz], dim=-1).reshape(-1, 3)
             u[xi:xi + chunk] = sdf_fn(pts).reshape(xx.shape)
     return u
+
+
+# --------------------------------------------------------------------------------------------
+# caller-side losses and ray generation
+# --------------------------------------------------------------------------------------------
+def training_loss_terms(out, true_rgb, true_mask):
+    """exp_runner.py:205-224: (color_fine_loss, mask_loss, psnr)."""
+    mask = (true_mask > 0.5).to(out["color_fine"].dtype)
+    mask_sum = mask.sum() + 1e-5
+    color_error = (out["color_fine"] - true_rgb) * mask
+    color_loss = F.l1_loss(color_error, torch.zeros_like(color_error), reduction="sum") / mask_sum
+    psnr = 20.0 * torch.log10(1.0 / (((out["color_fine"] - true_rgb) ** 2 * mask).sum() / (mask_sum * 3.0)).sqrt())
+    mask_loss = F.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), mask)
+    return color_loss, mask_loss, psnr
+
+
+def fitting_render_loss(out, true_rgb, true_mask, scale=1.0):
+    """fitting_single.py:253-256 (scale=1); fitting_video.py:287-291 is the same on [F*P] flattened rays with
+    scale=0.5 (its divisor true_mask.shape[0] * true_mask.shape[1] is the ray count)."""
+    color_error = (out["color_fine"] - true_rgb) * true_mask
+    n = out["weight_sum"].numel()
+    color_loss = F.l1_loss(color_error, torch.zeros_like(color_error), reduction="sum") / n
+    mask_loss = F.binary_cross_entropy(out["weight_sum"].clip(1e-3, 1.0 - 1e-3), true_mask)
+    return scale * (color_loss + 0.5 * mask_loss)
+
+
+def interaction_loss(sdf_hand, sdf_obj, w_contact=30.0, w_penet=20.0):
+    """fitting_single.py:268-283 / fitting_video.py:295-309: returns (total, contact_loss, penet_loss)."""
+    sdf_hand, sdf_obj = sdf_hand[:, 0], sdf_obj[:, 0]
+    sdf_abs_sum = torch.abs(sdf_hand) + torch.abs(sdf_obj)
+    contact_id = sdf_abs_sum < 1e-2
+    contact_num = contact_id.to(sdf_hand.dtype).sum() + 1e-9
+    contact_loss = torch.sum(sdf_abs_sum[contact_id]) / contact_num
+    inner = sdf_obj < 0
+    hs, os_ = sdf_hand[inner], sdf_obj[inner]
+    pen = hs < 0
+    penet_num = pen.to(sdf_hand.dtype).sum() + 1e-9
+    penet_loss = torch.sum(torch.abs(hs[pen]) + torch.abs(os_[pen])) / penet_num
+    return w_contact * contact_loss + w_penet * penet_loss, contact_loss, penet_loss
+
+
+def unproject_ndc(R, T, focal, pp, xy_depth):
+    """pytorch3d (un-vendored dependency of the reference; version not pinned upstream) PerspectiveCameras
+    .unproject_points(xy_depth, from_ndc=True, world_coordinates=True), restated from its published camera model
+    (row vectors): X_view = X_world R + T; x_ndc = fx X/Z + px, y_ndc = fy Y/Z + py.  PARITY UNPINNED for this function
+    (pytorch3d is not importable here); the bundle construction around it IS pinned (tests/golden/rays.npz)."""
+    x, y, depth = xy_depth[..., 0], xy_depth[..., 1], xy_depth[..., 2]
+    view = torch.stack([(x - pp[0]) * depth / focal[0], (y - pp[1]) * depth / focal[1], depth], dim=-1)
+    return (view - T) @ torch.linalg.inv(R)
+
+
+def rays_from_ndc(R, T, focal, pp, xy):
+    """utils/utils.py:78-107: depth-1 and depth-2 planes -> unit directions and origins one unit behind plane 1."""
+    ones = torch.ones_like(xy[..., :1])
+    p1 = unproject_ndc(R, T, focal, pp, torch.cat([xy, ones], dim=-1))
+    p2 = unproject_ndc(R, T, focal, pp, torch.cat([xy, 2.0 * ones], dim=-1))
+    d = F.normalize(p2 - p1, dim=-1)
+    return p1 - d, d
+
+
+def ndc_grid_xy(H, W):
+    """exp_runner.py:338-350: [H*W, 2] NDC coordinates of the full image (pixel = row * W + col)."""
+    if W >= H:
+        range_x, range_y = W / H, 1.0
+    else:
+        range_x, range_y = 1.0, H / W
+    img_x = torch.linspace(range_x, -range_x, W).unsqueeze(0).repeat(H, 1).reshape(-1, 1)
+    img_y = torch.linspace(range_y, -range_y, H).unsqueeze(1).repeat(1, W).reshape(-1, 1)
+    return torch.cat((img_x, img_y), -1)

@@ -1,0 +1,222 @@
+"""GPU parity for SURVEY.md 8f rows 1-2 (csrc/rays.cu, csrc/loss.cu), through the C ABI: golden vectors produced by
+the reference's own source lines (oracle/make_golden_8f.py), the CPU oracle on seeded inputs, and size-independent
+properties at full sizes (a 512 x 512 image of rays; 2^20 rays / 2^22 samples of loss)."""
+import pytest
+import torch
+
+import cases
+import honerf_oracle as O
+from golden_util import load_golden, max_abs, rel_err
+from gpu_util import DEV
+
+pytestmark = pytest.mark.gpu
+
+
+def _grads(loss, tensors):
+    return torch.autograd.grad(loss, tensors)
+
+
+# ------------------------------------------------------------------------------------------------
+# loss epilogues
+# ------------------------------------------------------------------------------------------------
+def test_training_loss_vs_reference_lines():
+    """Values 1e-6 relative, gradients 1e-6 of the largest entry AND the reference's exact zero pattern (rays outside
+    the mask, weight sums outside the BCE clip, sign(0) = 0)."""
+    import honerf_b200 as H
+    g, c = load_golden("losses"), cases.loss_case()
+    color, wsum = c["color"].to(DEV).requires_grad_(True), c["wsum"].to(DEV).requires_grad_(True)
+    ge = c["grad_err"].to(DEV).requires_grad_(True)
+    out = {"color_fine": color, "weight_sum": wsum, "gradient_error": ge}
+    loss, stats = H.losses.training_loss(out, c["true_rgb"].to(DEV), c["true_mask"].to(DEV), igr_weight=0.3,
+                                         mask_weight=0.7, return_stats=True)
+    assert rel_err(loss, g["train:loss"]) < 1e-6
+    assert rel_err(stats[0], g["train:color_loss"]) < 1e-6 and rel_err(stats[1], g["train:mask_loss"]) < 1e-6
+    assert rel_err(stats[2], g["train:psnr"]) < 1e-5
+    assert not stats.requires_grad
+    d = _grads(loss * 2.0, [color, wsum, ge])                  # upstream gradient 2: read from the device scalar
+    assert d[0].shape == color.shape and d[1].shape == wsum.shape and d[2].shape == ge.shape
+    assert rel_err(d[0], 2 * g["train:d_color"]) < 1e-6 and rel_err(d[1], 2 * g["train:d_wsum"]) < 1e-6
+    assert rel_err(d[2], 2 * g["train:d_grad_err"]) < 1e-6
+    assert torch.equal(d[0].cpu() == 0, g["train:d_color"] == 0)
+    assert torch.equal(d[1].cpu() == 0, g["train:d_wsum"] == 0)
+
+
+def test_fitting_losses_vs_reference_lines():
+    import honerf_b200 as H
+    g, c = load_golden("losses"), cases.loss_case()
+    color, wsum = c["color"].to(DEV).requires_grad_(True), c["wsum"].to(DEV).requires_grad_(True)
+    out = {"color_fine": color, "weight_sum": wsum}
+    loss, stats = H.losses.fitting_render_loss(out, c["true_rgb"].to(DEV), c["true_mask"].to(DEV), return_stats=True)
+    assert rel_err(loss, g["fit:loss"]) < 1e-6 and rel_err(stats[0], g["fit:color_loss"]) < 1e-6
+    d = _grads(loss, [color, wsum])
+    assert rel_err(d[0], g["fit:d_color"]) < 1e-6 and rel_err(d[1], g["fit:d_wsum"]) < 1e-6
+    # fitting_video.py:287-291 = half of it
+    half = H.losses.fitting_render_loss(out, c["true_rgb"].to(DEV), c["true_mask"].to(DEV), scale=0.5)
+    assert rel_err(half, 0.5 * g["fit:loss"]) < 1e-6
+
+    sh, so = c["sdf_h"].to(DEV).requires_grad_(True), c["sdf_o"].to(DEV).requires_grad_(True)
+    tot, st = H.losses.interaction_loss({"sdf_hand": sh, "sdf_obj": so}, return_stats=True)
+    assert rel_err(tot, g["int:loss"]) < 1e-6 and rel_err(st[0], g["int:contact"]) < 1e-6
+    assert rel_err(st[1], g["int:penet"]) < 1e-6
+    assert float(st[2]) == float(g["int:contact_num"]) and float(st[3]) == float(g["int:penet_num"])   # exact counts
+    d = _grads(tot, [sh, so])
+    assert d[0].shape == sh.shape
+    assert rel_err(d[0], g["int:d_h"]) < 1e-6 and rel_err(d[1], g["int:d_o"]) < 1e-6
+    assert torch.equal(d[0].cpu() == 0, g["int:d_h"] == 0) and torch.equal(d[1].cpu() == 0, g["int:d_o"] == 0)
+    # SDF outputs wider than one column: only column 0 is read and only column 0 gets a gradient
+    wide_h = torch.cat([c["sdf_h"], torch.ones(c["sdf_h"].shape[0], 2)], 1).to(DEV).requires_grad_(True)
+    tot2 = H.ops.interaction_loss(wide_h, so)[0]
+    dw = _grads(tot2, [wide_h])[0]
+    assert rel_err(tot2, g["int:loss"]) < 1e-6 and rel_err(dw[:, :1], g["int:d_h"]) < 1e-6
+    assert float(dw[:, 1:].abs().max()) == 0.0
+
+
+def test_loss_properties_at_full_size():
+    """2^20 rays (a 1024^2 image) and 2^22 SDF samples: deterministic bits run to run (fixed-order two-level sums),
+    linear in the loss weights, agreement with the fp64 oracle to 2e-6 relative (fp32 per-thread partial sums over
+    ~14 elements each, fp64 across CTAs), empty populations give exactly 0 (the reference's +1e-9 guards)."""
+    import honerf_b200 as H
+    gen = torch.Generator().manual_seed(5)
+    n = 1 << 20
+    color, true_rgb = torch.rand(n, 3, generator=gen), torch.rand(n, 3, generator=gen)
+    wsum = torch.rand(n, 1, generator=gen) * 1.1 - 0.05
+    mask = (torch.rand(n, 1, generator=gen) > 0.5).float()
+    ge = torch.tensor(0.25)
+    dv = [t.to(DEV) for t in (color, wsum, true_rgb, mask, ge)]
+    full = H.ops.render_loss(dv[0], dv[1], dv[2], dv[3], dv[4], 0.0, 1.0, 0.7, 0.3)[0]
+    again = H.ops.render_loss(dv[0], dv[1], dv[2], dv[3], dv[4], 0.0, 1.0, 0.7, 0.3)[0]
+    assert torch.equal(full, again)
+    parts = [H.ops.render_loss(dv[0], dv[1], dv[2], dv[3], dv[4], 0.0, a, b, c)[0]
+             for a, b, c in ((1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0))]
+    assert abs(float(full) - float(parts[0] + 0.7 * parts[1] + 0.3 * parts[2])) < 1e-6 * abs(float(full))
+    ref = O.training_loss({"color_fine": color.double(), "weight_sum": wsum.double(), "gradient_error": ge.double()},
+                          true_rgb.double(), mask.double(), igr_weight=0.3, mask_weight=0.7)
+    assert abs(float(full) - float(ref)) < 2e-6 * abs(float(ref))
+    m = 1 << 22
+    sh, so = 0.02 * torch.randn(m, 1, generator=gen), 0.02 * torch.randn(m, 1, generator=gen)
+    tot, st = H.ops.interaction_loss(sh.to(DEV), so.to(DEV))
+    rt, rc, rp = O.interaction_loss(sh.double(), so.double())
+    assert abs(float(tot) - float(rt)) < 2e-6 * abs(float(rt))
+    a = sh.abs() + so.abs()
+    assert float(st[2]) == float((a < 1e-2).sum()) and float(st[3]) == float(((sh < 0) & (so < 0)).sum())
+    far = torch.full((1000, 1), 0.5, device=DEV)
+    tot0, st0 = H.ops.interaction_loss(far, far)
+    assert float(tot0) == 0.0 and float(st0[2]) == pytest.approx(1e-9) and float(st0[3]) == pytest.approx(1e-9)
+
+
+def test_fused_training_loss_drives_the_renderer_like_the_torch_lines():
+    """End to end: the fused loss on a real render gives the same network gradients as the reference's torch lines
+    applied to the same render (1e-5 relative: only summation order differs)."""
+    import honerf_b200 as H
+    import ref_conf
+    import synth
+    from gpu_util import obj_modules
+    sdf, col, var, _, _ = obj_modules()
+    r = H.NeuSRenderer(sdf, var, col, "obj", **dict(ref_conf.RENDERER_CONF, perturb=0.0))
+    R = synth.object_rays(48, seed=41)
+    gen = torch.Generator().manual_seed(9)
+    true_rgb, true_mask = torch.rand(48, 3, generator=gen).to(DEV), (torch.rand(48, 1, generator=gen) > 0.5).float().to(DEV)
+    params = [p for m in (sdf, col, var) for n, p in m.named_parameters() if n != "se3_refine"]
+
+    def run(loss_fn):
+        out = r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), 0.4, 1.5, None, None, None, R["Ro"].to(DEV),
+                       R["To"].to(DEV), 0)
+        loss = loss_fn(out)
+        return loss.detach(), torch.autograd.grad(loss, params, allow_unused=True)
+    l_f, g_f = run(lambda out: H.losses.training_loss(out, true_rgb, true_mask))
+    l_t, g_t = run(lambda out: O.training_loss(out, true_rgb, true_mask))
+    assert rel_err(l_f, l_t) < 1e-6
+    for a, b in zip(g_f, g_t):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert rel_err(a, b) < 1e-5
+
+
+def test_loss_errors_are_loud():
+    import honerf_b200 as H
+    c = cases.loss_case(n=8)
+    with pytest.raises(H.HonerfError):                         # CPU tensors: no fallback
+        H.ops.render_loss(c["color"], c["wsum"], c["true_rgb"], c["true_mask"])
+    with pytest.raises(H.HonerfError):                         # ragged inputs
+        H.ops.render_loss(c["color"].to(DEV), c["wsum"][:5].to(DEV), c["true_rgb"].to(DEV), c["true_mask"].to(DEV))
+    with pytest.raises(H.HonerfError):                         # empty batch: the reference's mean over 0 rays is NaN
+        e = torch.zeros(0, 3, device=DEV)
+        H.ops.render_loss(e, torch.zeros(0, 1, device=DEV), e, torch.zeros(0, 1, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------
+# ray generation
+# ------------------------------------------------------------------------------------------------
+def _cams(c, sel=slice(None)):
+    from honerf_b200 import rays
+    return rays.PerspectiveCameras(c["R"][sel], c["T"][sel], c["focal"][sel], c["pp"][sel]).to(DEV)
+
+
+def test_rays_vs_reference_bundle():
+    """Reference `_xy_to_ray_bundle` on the restated pytorch3d camera (make_golden_8f.py): 2e-6 absolute on origins
+    and directions (scene scale ~1; the golden path inverts a 4x4 in fp32, the kernel a 3x3), the depth table exact."""
+    from honerf_b200 import rays
+    g, c = load_golden("rays"), cases.rays_case()
+    b = rays._xy_to_ray_bundle(_cams(c), c["xy"].to(DEV), 0.4, 1.5, 64)
+    assert b.origins.shape == (2, 33, 3) and b.lengths.shape == (2, 33, 64)
+    assert max_abs(b.origins, g["o"]) < 2e-6 and max_abs(b.directions, g["d"]) < 2e-6
+    assert torch.equal(b.lengths[1, 7].cpu(), g["lengths0"])
+    for k in range(2):                                         # and the CPU oracle's direct formula
+        o, d = O.rays_from_ndc(c["R"][k], c["T"][k], c["focal"][k], c["pp"][k], c["xy"][k])
+        assert max_abs(b.origins[k], o) < 2e-6 and max_abs(b.directions[k], d) < 2e-6
+
+
+def test_image_grid_rays_vs_reference_lines_and_chunking():
+    """exp_runner.py:338-353 run verbatim (golden) vs the grid kernel; chunks of any size concatenate to the same bits
+    as one launch, and equal the list form fed the same NDC coordinates bit for bit."""
+    from honerf_b200 import ops, rays
+    g, c = load_golden("rays"), cases.rays_case()
+    cam = _cams(c, slice(0, 1))
+    H_, W_ = c["H"], c["W"]
+    chunks = list(rays.image_ray_chunks(cam, H_, W_, 8))
+    assert [o.shape[0] for o, _ in chunks] == [8, 8, 8, 8, 3]
+    o = torch.cat([x for x, _ in chunks])
+    d = torch.cat([x for _, x in chunks])
+    assert max_abs(o, g["grid_o"]) < 2e-6 and max_abs(d, g["grid_d"]) < 2e-6
+    whole = list(rays.image_ray_chunks(cam, H_, W_, H_ * W_))[0]
+    assert torch.equal(whole[0], o) and torch.equal(whole[1], d)
+    lo, ld = ops.rays_from_ndc(g["grid_xy"].to(DEV)[None], cam.record)
+    assert torch.equal(lo[0], o) and torch.equal(ld[0], d)
+
+
+def test_rays_full_image_round_trip():
+    """512 x 512 image (BASELINE configs[3] view size): unit directions, and projecting the depth-1 point o + d back
+    through the camera model returns the pixel's NDC coordinates (round trip, 2e-5: fp32 through two 3x3 products)."""
+    from honerf_b200 import ops, rays
+    c = cases.rays_case()
+    cam = _cams(c, slice(1, 2))
+    xs, ys = ops.ndc_grid_axes(512, 512, DEV)
+    o, d = ops.rays_ndc_grid(xs, ys, cam.record[0], 0, 512 * 512)
+    assert float((d.norm(dim=-1) - 1).abs().max()) < 1e-6
+    p1 = (o + d).double().cpu()
+    view = p1 @ c["R"][1].double() + c["T"][1].double()
+    assert float((view[:, 2] - 1.0).abs().max()) < 2e-5       # plane 1 is the depth-1 plane
+    x = c["focal"][1, 0].double() * view[:, 0] / view[:, 2] + c["pp"][1, 0].double()
+    y = c["focal"][1, 1].double() * view[:, 1] / view[:, 2] + c["pp"][1, 1].double()
+    xy = O.ndc_grid_xy(512, 512).double()
+    assert float((x - xy[:, 0]).abs().max()) < 2e-5 and float((y - xy[:, 1]).abs().max()) < 2e-5
+    # every ray of one camera passes through the camera centre  C = -T R^-1
+    centre = -(c["T"][1].double() @ torch.linalg.inv(c["R"][1].double()))
+    t = ((centre - o.double().cpu()) * d.double().cpu()).sum(-1, keepdim=True)
+    assert float((o.double().cpu() + t * d.double().cpu() - centre).abs().max()) < 2e-5
+
+
+def test_rays_edge_cases():
+    import honerf_b200 as H
+    from honerf_b200 import ops
+    c = cases.rays_case()
+    cam = _cams(c)
+    o, d = ops.rays_from_ndc(torch.zeros(2, 0, 2, device=DEV), cam.record)      # empty
+    assert o.shape == (2, 0, 3)
+    with pytest.raises(H.HonerfError):                                          # camera count mismatch
+        ops.rays_from_ndc(torch.zeros(3, 4, 2, device=DEV), cam.record)
+    with pytest.raises(H.HonerfError):                                          # CPU tensors: no fallback
+        ops.rays_from_ndc(torch.zeros(2, 4, 2), cam.record.cpu())
+    xs, ys = ops.ndc_grid_axes(5, 7, DEV)
+    with pytest.raises(H.HonerfError):                                          # pixel range outside the image
+        ops.rays_ndc_grid(xs, ys, cam.record[0], 30, 10)

@@ -1,0 +1,82 @@
+"""SURVEY.md 8f rows 1-2 on the CPU: the oracle restatements (oracle/honerf_oracle.py) and the closed forms the
+kernels implement (oracle/analytic.py) against golden vectors produced by the reference's own source lines
+(oracle/make_golden_8f.py)."""
+import torch
+
+import analytic as A
+import cases
+import honerf_oracle as O
+from golden_util import load_golden, max_abs, rel_err
+
+
+def test_training_loss_oracle_matches_reference_lines():
+    g, c = load_golden("losses"), cases.loss_case()
+    color, wsum = c["color"].clone().requires_grad_(True), c["wsum"].clone().requires_grad_(True)
+    ge = c["grad_err"].clone().requires_grad_(True)
+    out = {"color_fine": color, "weight_sum": wsum, "gradient_error": ge}
+    loss = O.training_loss(out, c["true_rgb"], c["true_mask"], igr_weight=0.3, mask_weight=0.7)
+    assert torch.equal(loss.detach(), g["train:loss"])
+    cl, ml, psnr = O.training_loss_terms(out, c["true_rgb"], c["true_mask"])
+    assert torch.equal(cl.detach(), g["train:color_loss"]) and torch.equal(ml.detach(), g["train:mask_loss"])
+    assert torch.equal(psnr.detach(), g["train:psnr"])
+    d = torch.autograd.grad(loss, [color, wsum, ge])
+    assert torch.equal(d[0], g["train:d_color"]) and torch.equal(d[1], g["train:d_wsum"])
+    assert torch.equal(d[2], g["train:d_grad_err"])
+
+
+def test_fitting_losses_oracle_matches_reference_lines():
+    g, c = load_golden("losses"), cases.loss_case()
+    color, wsum = c["color"].clone().requires_grad_(True), c["wsum"].clone().requires_grad_(True)
+    loss = O.fitting_render_loss({"color_fine": color, "weight_sum": wsum}, c["true_rgb"], c["true_mask"])
+    assert torch.equal(loss.detach(), g["fit:loss"])
+    d = torch.autograd.grad(loss, [color, wsum])
+    assert torch.equal(d[0], g["fit:d_color"]) and torch.equal(d[1], g["fit:d_wsum"])
+    sh, so = c["sdf_h"].clone().requires_grad_(True), c["sdf_o"].clone().requires_grad_(True)
+    tot, contact, penet = O.interaction_loss(sh, so)
+    assert torch.equal(tot.detach(), g["int:loss"]) and torch.equal(contact.detach(), g["int:contact"])
+    assert torch.equal(penet.detach(), g["int:penet"])
+    d = torch.autograd.grad(tot, [sh, so])
+    assert torch.equal(d[0], g["int:d_h"]) and torch.equal(d[1], g["int:d_o"])
+    # the case exercises both populations and the sign(0) = 0 corner
+    assert g["int:contact_num"] > 50 and g["int:penet_num"] > 50 and (g["int:d_h"] == 0).any()
+
+
+def test_kernel_closed_forms_match_reference_lines():
+    """The formulas csrc/loss.cu implements (no autograd): 1e-6 relative on values, 1e-6 of the largest entry on
+    gradients, and exactly the reference's zero pattern (clip bounds, masked rays, sign(0))."""
+    g, c = load_golden("losses"), cases.loss_case()
+    mask = (c["true_mask"] > 0.5).float()
+    tot, cl, ml, d_c, d_w, d_ge = A.render_loss_closed_form(c["color"], c["wsum"], c["true_rgb"], mask, c["grad_err"],
+                                                            0.0, 1.0, 0.7, 0.3)
+    assert rel_err(tot, g["train:loss"]) < 1e-6 and rel_err(cl, g["train:color_loss"]) < 1e-6
+    assert rel_err(ml, g["train:mask_loss"]) < 1e-6
+    assert rel_err(d_c, g["train:d_color"]) < 1e-6 and rel_err(d_w, g["train:d_wsum"]) < 1e-6
+    assert torch.equal(d_c == 0, g["train:d_color"] == 0) and torch.equal(d_w == 0, g["train:d_wsum"] == 0)
+    assert abs(d_ge - float(g["train:d_grad_err"])) < 1e-7
+    n = c["color"].shape[0]
+    tot, cl, ml, d_c, d_w, _ = A.render_loss_closed_form(c["color"], c["wsum"], c["true_rgb"], c["true_mask"], None,
+                                                         float(n), 1.0, 0.5, 0.0)
+    assert rel_err(tot, g["fit:loss"]) < 1e-6
+    assert rel_err(d_c, g["fit:d_color"]) < 1e-6 and rel_err(d_w, g["fit:d_wsum"]) < 1e-6
+    tot, contact, penet, d_h, d_o = A.interaction_closed_form(c["sdf_h"], c["sdf_o"], 1e-2, 30.0, 20.0)
+    assert rel_err(tot, g["int:loss"]) < 1e-6 and rel_err(contact, g["int:contact"]) < 1e-6
+    assert rel_err(penet, g["int:penet"]) < 1e-6
+    assert rel_err(d_h, g["int:d_h"][:, 0]) < 1e-6 and rel_err(d_o, g["int:d_o"][:, 0]) < 1e-6
+
+
+def test_ray_generation_oracle_and_closed_form():
+    """Reference `_xy_to_ray_bundle` (run on a restated pytorch3d camera, see make_golden_8f.py) vs the oracle's direct
+    pinhole formula and vs the kernel's adjugate form: 2e-6 absolute (scene scale ~1; the golden path inverts a 4x4 in
+    fp32, the restatements a 3x3)."""
+    g, c = load_golden("rays"), cases.rays_case()
+    for k in range(2):
+        o, d = O.rays_from_ndc(c["R"][k], c["T"][k], c["focal"][k], c["pp"][k], c["xy"][k])
+        assert max_abs(o, g["o"][k]) < 2e-6 and max_abs(d, g["d"][k]) < 2e-6
+        o2, d2 = A.rays_closed_form(c["R"][k], c["T"][k], c["focal"][k], c["pp"][k], c["xy"][k])
+        assert max_abs(o2, g["o"][k]) < 2e-6 and max_abs(d2, g["d"][k]) < 2e-6
+        assert max_abs(d.norm(dim=-1), torch.ones(d.shape[0])) < 1e-6
+    xy = O.ndc_grid_xy(c["H"], c["W"])
+    assert torch.equal(xy, g["grid_xy"])
+    o, d = O.rays_from_ndc(c["R"][0], c["T"][0], c["focal"][0], c["pp"][0], xy)
+    assert max_abs(o, g["grid_o"]) < 2e-6 and max_abs(d, g["grid_d"]) < 2e-6
+    assert torch.equal(g["lengths0"], torch.linspace(0.4, 1.5, 64))
