@@ -118,6 +118,7 @@ PROTOTYPES = {
     "hn_fit_composite_bwd": (c_int, [P, P, P, P, P, c_int64, c_int, P, P, P, P, P, P, P]),
     "hn_rays_from_ndc": (c_int, [P, P, c_int64, c_int64, P, P, P]),
     "hn_rays_ndc_grid": (c_int, [P, P, c_int, c_int, P, c_int64, c_int64, P, P, P]),
+    "hn_nn_select": (c_int, [P, P, P, c_int, c_int, P, P, P]),
     "hn_loss_ws_floats": (c_int64, []),
     "hn_render_loss_fwd": (c_int, [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P, P]),
     "hn_render_loss_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_float, c_float, c_float, P, P, P, P]),

@@ -886,3 +886,54 @@ def interaction_loss(sdf_hand, sdf_obj, contact_thr=1e-2, w_contact=30.0, w_pene
     """Contact + penetration terms of fitting_single.py:268-283 on column 0 of render_out['sdf_hand'] / ['sdf_obj']:
     returns (w_contact * contact + w_penet * penet, stats = [contact, penet, contact_num, penet_num])."""
     return _InteractionLossFn.apply(sdf_hand, sdf_obj, contact_thr, w_contact, w_penet)
+
+
+# ------------------------------------------------------------------------------------------------
+# temporal contact-stability loss (SURVEY.md 8f row 3)
+# ------------------------------------------------------------------------------------------------
+def nn_select(pts, in_mask, out_mask, return_nearest=False):
+    """pts [P,3]; in_mask, out_mask [T,P] bool -> flag [T,P] bool: flag[t,q] = q is the nearest out-candidate of some
+    in-point of frame t (np.unique of cKDTree.query(k=1) as a flag array, utils/renderer_batch.py:354-357)."""
+    p = _f32c(pts.detach())
+    _require_cuda(p, "nn_select")
+    im, om = in_mask.to(torch.uint8).contiguous(), out_mask.to(torch.uint8).contiguous()
+    T, P = im.shape
+    if p.shape != (P, 3) or om.shape != (T, P):
+        raise _lib.HonerfError("nn_select: pts %s, in_mask %s, out_mask %s disagree"
+                               % (tuple(pts.shape), tuple(in_mask.shape), tuple(out_mask.shape)))
+    flag = torch.zeros(T, P, dtype=torch.uint8, device=p.device)
+    nearest = torch.empty(T, P, dtype=torch.int64, device=p.device) if return_nearest else None
+    check(lib.hn_nn_select(_ptr(p), _ptr(im), _ptr(om), T, P, _ptr(flag), _ptr(nearest), _stream(p)), "hn_nn_select")
+    return (flag.bool(), nearest) if return_nearest else flag.bool()
+
+
+def stable_loss_from_sdf(hand_sdf, pts0, fixed=False):
+    """utils/renderer_batch.py:328-369 given the hand SDF of every frame at the (strided) object vertices:
+    hand_sdf [F,P] (differentiable), pts0 [P,3] = frame 0's vertices in the object frame.  Device-resident: the frame
+    filter, the in/out sets, the nearest-neighbour selection (hn_nn_select) and the sums never visit the host.
+
+    fixed=False reproduces upstream bit of behaviour: `np.setdiff1d(vert_id_all, cur_in_id)` receives the BOOLEAN
+    mask, so the "out" set is every vertex except the ids {0, 1} that occur as mask VALUES (0 if some vertex is
+    outside, 1 if some is inside); fixed=True uses the complement of the in-set, which is what the code reads like."""
+    F_, P = hand_sdf.shape
+    neg = hand_sdf.detach() < 0                                  # [F,P] in-sets
+    valid = neg.any(dim=1)                                       # frames that penetrate at all
+    in_time = valid.sum()
+    if fixed:
+        out_mask = ~neg
+    else:
+        out_mask = torch.ones_like(neg)
+        if P > 0:
+            out_mask[:, 0] = ~(~neg).any(dim=1)                  # id 0 leaves the set when a False is present
+        if P > 1:
+            out_mask[:, 1] = ~neg.any(dim=1)                     # id 1 leaves the set when a True is present
+    flag = nn_select(pts0, neg & valid[:, None], out_mask)
+    vf = valid.to(hand_sdf.dtype)
+    s_pos = (hand_sdf.clip(0, 1e7) * vf[:, None]).sum(0)         # [P] sums over the penetrating frames
+    s_neg = (hand_sdf.clip(-1e7, 0).abs() * vf[:, None]).sum(0)
+    n_in = neg.sum(dim=1).to(hand_sdf.dtype)                     # [F]
+    denom = ((in_time - 1).to(hand_sdf.dtype) * n_in).clamp_min(1.0)
+    in_err = (neg.to(hand_sdf.dtype) @ s_pos) / denom
+    out_err = (flag.to(hand_sdf.dtype) @ s_neg) / denom
+    total = ((in_err + 0.05 * out_err) * vf).sum() / in_time.clamp_min(1).to(hand_sdf.dtype)
+    return torch.where(in_time > 1, total, torch.zeros_like(total))

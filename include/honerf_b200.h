@@ -384,6 +384,17 @@ HN_API int hn_interaction_loss_bwd(const float* g_loss, const float* sdf_hand, i
                                    float* d_sdf_obj, hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Nearest-neighbour selection of get_stable_loss_cross (utils/renderer_batch.py:346-357, where
+ * the reference builds a scipy cKDTree per frame on the host).  pts [n_pts,3] (shared by all frames); in_mask,
+ * out_mask, flag: [n_frames, n_pts] bytes.  For each frame t and each p with in_mask[t,p]: q* = argmin over
+ * {q : out_mask[t,q]} of |pts[q] - pts[p]|^2 (fp64 distances like cKDTree, exact ties -> lowest q); sets
+ * flag[t,q*] = 1 (flag must be zeroed by the caller; = np.unique(near_out_id) as a flag array) and, if `nearest` is
+ * not NULL, nearest[t,p] = q* (-1 for points outside in_mask or when the frame has no candidate).
+ * ------------------------------------------------------------------------------------------- */
+HN_API int hn_nn_select(const float* pts, const uint8_t* in_mask, const uint8_t* out_mask, int n_frames,
+                        int n_pts, uint8_t* flag, int64_t* nearest, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Diagnostics: C[M,N] (fp32) = A[M,K] * B[N,K]^T with fp16 (or bf16) operands on tcgen05 tensor cores
  * (fp32 accumulation in TMEM).  Self-test of the descriptors / TMEM / mbarrier plumbing shared by the
  * fused field kernels.  16 <= N <= 256, N % 16 == 0, K % 64 == 0.

@@ -318,3 +318,46 @@ def rays_closed_form(R, T, focal, pp, xy):
     d = p2 - p1
     d = d / d.norm(dim=-1, keepdim=True).clamp_min(1e-12)
     return p1 - d, d
+
+
+def nn_select_bruteforce(pts, in_mask, out_mask):
+    """CPU model of csrc/neighbors.cu: fp64 distances, lowest index on exact ties."""
+    T, P = in_mask.shape
+    d2 = ((pts.double()[:, None, :] - pts.double()[None, :, :]) ** 2).sum(-1)          # [P(p), P(q)]
+    flag = torch.zeros(T, P, dtype=torch.bool)
+    nearest = torch.full((T, P), -1, dtype=torch.int64)
+    for t in range(T):
+        if not out_mask[t].any():
+            continue
+        dd = d2.clone()
+        dd[:, ~out_mask[t]] = float("inf")
+        q = dd.argmin(dim=1)                       # torch argmin returns the first minimum
+        nearest[t, in_mask[t]] = q[in_mask[t]]
+        flag[t, q[in_mask[t]]] = True
+    return flag, nearest
+
+
+def stable_loss_closed_form(hand_sdf, pts0, fixed=False, nn=None):
+    """The device formulation of honerf_b200.ops.stable_loss_from_sdf (masks + two matrix-vector products), with the
+    nearest-neighbour flags from `nn` (default: the brute-force model above)."""
+    nn = nn or (lambda p, i, o: nn_select_bruteforce(p, i, o)[0])
+    F_, P = hand_sdf.shape
+    neg = hand_sdf.detach() < 0
+    valid = neg.any(dim=1)
+    in_time = valid.sum()
+    if fixed:
+        out_mask = ~neg
+    else:
+        out_mask = torch.ones_like(neg)
+        out_mask[:, 0] = ~(~neg).any(dim=1)
+        out_mask[:, 1] = ~neg.any(dim=1)
+    flag = nn(pts0, neg & valid[:, None], out_mask)
+    vf = valid.to(hand_sdf.dtype)
+    s_pos = (hand_sdf.clip(0, 1e7) * vf[:, None]).sum(0)
+    s_neg = (hand_sdf.clip(-1e7, 0).abs() * vf[:, None]).sum(0)
+    n_in = neg.sum(dim=1).to(hand_sdf.dtype)
+    denom = ((in_time - 1).to(hand_sdf.dtype) * n_in).clamp_min(1.0)
+    in_err = (neg.to(hand_sdf.dtype) @ s_pos) / denom
+    out_err = (flag.to(hand_sdf.dtype) @ s_neg) / denom
+    total = ((in_err + 0.05 * out_err) * vf).sum() / in_time.clamp_min(1).to(hand_sdf.dtype)
+    return torch.where(in_time > 1, total, torch.zeros_like(total))

@@ -122,3 +122,19 @@ def rays_case(seed=302):
     pp = torch.tensor([[0.03, -0.02], [-0.04, 0.05]])
     xy = torch.rand(2, 33, 2, generator=g) * 2.4 - 1.2
     return dict(R=R, T=T, focal=focal, pp=pp, xy=xy, H=5, W=7)
+
+
+def stable_case(n_frames=4, n_pts=160, seed=303):
+    """get_stable_loss_cross inputs: object vertices (object frame) scattered around the hand joints, per-frame hand
+    poses and object poses.  `pts` is [F, 10 * n_pts, 3] so that the reference's `[:, ::10]` stride picks `sel`."""
+    import synth
+    g = torch.Generator().manual_seed(seed)
+    bt, T, J = synth.hand_pose(seed=5, n_frames=n_frames)
+    sel = J[0][torch.randint(0, 21, (n_pts,), generator=g)] + 0.012 * torch.randn(n_pts, 3, generator=g)
+    Ro = torch.stack([torch.eye(3) + 0.01 * torch.randn(3, 3, generator=g) for _ in range(n_frames)])
+    To = 0.004 * torch.randn(n_frames, 3, generator=g)
+    return dict(bt_inv=bt, T_pose_21=T, sel=sel, Ro=Ro, To=To)
+
+
+def stable_pts(sel, n_frames):
+    return sel.repeat_interleave(10, dim=0)[None].repeat(n_frames, 1, 1).contiguous()

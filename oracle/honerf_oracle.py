@@ -614,3 +614,38 @@ def ndc_grid_xy(H, W):
     img_x = torch.linspace(range_x, -range_x, W).unsqueeze(0).repeat(H, 1).reshape(-1, 1)
     img_y = torch.linspace(range_y, -range_y, H).unsqueeze(1).repeat(1, W).reshape(-1, 1)
     return torch.cat((img_x, img_y), -1)
+
+
+def stable_loss_from_sdf(hand_sdf, pts0):
+    """utils/renderer_batch.py:328-369 given hand_sdf [F,P] (the hand SDF of every frame at the strided object
+    vertices) and pts0 [P,3] = pts[0]: the reference's host logic line by line, scipy cKDTree included -- and
+    including its quirk that np.setdiff1d receives the BOOLEAN in-mask."""
+    import numpy as np
+    from scipy import spatial
+    p_num = pts0.shape[0]
+    vert_id_all = range(p_num)
+    hand_sdf_list, in_id_list = [], []
+    for f in range(hand_sdf.shape[0]):
+        cur = hand_sdf[f].reshape(-1)
+        penet_id = cur < 0
+        if penet_id.float().sum() > 0:
+            in_id_list.append(penet_id)
+            hand_sdf_list.append(cur)
+    stable_loss = 0
+    if len(in_id_list) > 1:
+        hand_sdf_list = torch.stack(hand_sdf_list, 0)
+        in_time = hand_sdf_list.shape[0]
+        for cid in range(in_time):
+            cur_in_id = in_id_list[cid].clone().cpu()
+            cur_out_id = np.setdiff1d(vert_id_all, cur_in_id)
+            in_points = pts0[cur_in_id].detach().cpu()
+            out_points = pts0[cur_out_id].detach().cpu()
+            n_in = in_points.shape[0]
+            _, near = spatial.cKDTree(out_points.numpy()).query(in_points.numpy(), k=1)
+            near = np.unique(near.reshape(-1))
+            in_err = hand_sdf_list[:, cur_in_id].clip(0, 1e7).sum() / ((in_time - 1) * n_in)
+            sel = hand_sdf_list[:, cur_out_id]
+            out_err = torch.abs(sel[:, near].clip(-1e7, 0)).sum() / ((in_time - 1) * n_in)
+            stable_loss = stable_loss + in_err + 0.05 * out_err
+        stable_loss /= in_time
+    return stable_loss

@@ -1,7 +1,7 @@
 """Golden vectors for the SURVEY.md 8f rows (loss epilogues, ray generation), produced by running the reference's
 OWN source lines (build container only; /root/reference does not travel).
 
-    python oracle/make_golden_8f.py        # writes tests/golden/losses.npz, tests/golden/rays.npz
+    python oracle/make_golden_8f.py        # writes tests/golden/losses.npz, rays.npz, stable.npz
 
 TEST INFRASTRUCTURE ONLY.
 * Losses: the reference's loss code is inline in its drivers (exp_runner.py, fitting_single.py), not a function, so
@@ -145,6 +145,51 @@ def rays():
     print("rays.npz:", {k: v.shape for k, v in out.items()})
 
 
+def stable():
+    """get_stable_loss_cross (utils/renderer_batch.py:318-371) of the UNMODIFIED reference class, called on a stub
+    `self` that carries the reference's own hand SDF network (CPU, use_batch=True) with the seeded synthetic weights.
+    lin8.bias[0] is shifted by the median SDF so the zero level set passes through the vertex cloud (stored as `shift`);
+    vertices closer than 3e-4 to the surface in any frame are dropped (stored as `keep`) so a 1e-5 SDF difference on
+    the GPU cannot move a vertex between the in and out sets."""
+    import ref_loader
+    import synth
+    ref = ref_loader.load_reference()
+    c = cases.stable_case()
+    sp, _ = synth.hand_states()
+    net = ref.fields.SDFNetwork(ref.fields.Embedding(), 4, "real", use_batch=True, **ref_loader.HAND_SDF_CONF)
+    net.load_state_dict(sp)
+    Fn = c["Ro"].shape[0]
+
+    def sdf_at(sel):
+        pw = (c["Ro"].unsqueeze(1) @ sel[None].repeat(Fn, 1, 1).unsqueeze(-1))[..., 0] + c["To"].unsqueeze(1)
+        with torch.no_grad():
+            return net.sdf(pw, c["bt_inv"], c["T_pose_21"]).reshape(Fn, -1)
+    shift = sdf_at(c["sel"]).median()
+    with torch.no_grad():
+        net.lin8.bias[0] -= shift
+    s = sdf_at(c["sel"])
+    keep = (s.abs() > 3e-4).all(dim=0)
+    sel = c["sel"][keep]
+    pts = cases.stable_pts(sel, Fn)
+    stub = types.SimpleNamespace(sdf_network_hand=net)
+    cls = ref.renderer_batch.NeuSRenderer_fitting
+    bt = c["bt_inv"].clone().requires_grad_(True)
+    loss = cls.get_stable_loss_cross(stub, pts, bt, c["T_pose_21"], c["Ro"], c["To"])
+    d_bt, = torch.autograd.grad(loss, [bt])
+    hand_sdf = sdf_at(sel)
+    out = {"shift": np_(shift), "keep": np_(keep), "hand_sdf": np_(hand_sdf), "loss": np_(loss), "d_bt_inv": np_(d_bt),
+           "n_in": np_((hand_sdf < 0).sum(1))}
+    # second fixture: only one frame penetrates -> the reference returns the int 0
+    one = hand_sdf.clone()
+    one[1:] = one[1:].abs() + 1e-3
+    out["loss_one_frame"] = np.float32(cls.get_stable_loss_cross(
+        types.SimpleNamespace(sdf_network_hand=types.SimpleNamespace(sdf=lambda p, b, t: one.reshape(-1, 1))),
+        pts, bt, c["T_pose_21"], c["Ro"], c["To"]))
+    np.savez_compressed(os.path.join(OUT, "stable.npz"), **out)
+    print("stable.npz:", {k: v.shape for k, v in out.items()}, "loss", float(loss), "n_in", out["n_in"], "kept", int(keep.sum()))
+
+
 if __name__ == "__main__":
-    losses()
-    rays()
+    which = sys.argv[1:] or ["losses", "rays", "stable"]
+    for w in which:
+        {"losses": losses, "rays": rays, "stable": stable}[w]()

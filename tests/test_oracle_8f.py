@@ -80,3 +80,44 @@ def test_ray_generation_oracle_and_closed_form():
     o, d = O.rays_from_ndc(c["R"][0], c["T"][0], c["focal"][0], c["pp"][0], xy)
     assert max_abs(o, g["grid_o"]) < 2e-6 and max_abs(d, g["grid_d"]) < 2e-6
     assert torch.equal(g["lengths0"], torch.linspace(0.4, 1.5, 64))
+
+
+def test_stable_loss_oracle_and_device_formulation():
+    """the reference's own get_stable_loss_cross (golden) vs (i) the oracle's line-by-line host logic
+    fed the golden hand SDFs (bit-exact), (ii) the mask / matrix-vector formulation the product runs on the device with
+    a brute-force nearest-neighbour model (1e-6 relative: summation order), incl. its gradient w.r.t. the SDFs."""
+    g, c = load_golden("stable"), cases.stable_case()
+    sel = c["sel"][g["keep"]]
+    hs = g["hand_sdf"].clone().requires_grad_(True)
+    ref = O.stable_loss_from_sdf(hs, sel)
+    assert torch.equal(ref.detach(), g["loss"])
+    d_ref, = torch.autograd.grad(ref, [hs])
+    hs2 = g["hand_sdf"].clone().requires_grad_(True)
+    got = A.stable_loss_closed_form(hs2, sel)
+    assert rel_err(got, g["loss"]) < 1e-6
+    d_got, = torch.autograd.grad(got, [hs2])
+    assert rel_err(d_got, d_ref) < 1e-6
+    # fewer than two penetrating frames: upstream returns the int 0
+    one = g["hand_sdf"].clone()
+    one[1:] = one[1:].abs() + 1e-3
+    assert float(g["loss_one_frame"]) == 0.0 and O.stable_loss_from_sdf(one, sel) == 0
+    assert float(A.stable_loss_closed_form(one, sel)) == 0.0
+    assert float(A.stable_loss_closed_form(one.abs() + 1e-3, sel)) == 0.0       # no frame penetrates at all
+
+
+def test_nn_bruteforce_model_equals_ckdtree():
+    """The kernel's selection rule (fp64 distances, first minimum) returns scipy cKDTree's neighbour on random clouds;
+    used with fixed=True semantics (out = complement of in)."""
+    import numpy as np
+    from scipy import spatial
+    gen = torch.Generator().manual_seed(11)
+    pts = torch.randn(700, 3, generator=gen)
+    in_mask = torch.rand(3, 700, generator=gen) < 0.3
+    flag, nearest = A.nn_select_bruteforce(pts, in_mask, ~in_mask)
+    for t in range(3):
+        out_ids = np.nonzero((~in_mask[t]).numpy())[0]
+        _, near = spatial.cKDTree(pts[~in_mask[t]].numpy()).query(pts[in_mask[t]].numpy(), k=1)
+        assert np.array_equal(out_ids[near], nearest[t, in_mask[t]].numpy())
+        want = torch.zeros(700, dtype=torch.bool)
+        want[torch.from_numpy(np.unique(out_ids[near]))] = True
+        assert torch.equal(flag[t], want)
