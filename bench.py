@@ -51,15 +51,53 @@ def synthetic_batch(n_rays, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).  The timed
+    region of the default run lasts tens of milliseconds, shorter than one `nvidia-smi` query, so the samples are taken
+    through NVML (pynvml: the same counters nvidia-smi reads) from a thread polling every ~2 ms; `nvidia-smi -lms` is
+    the fallback when pynvml is missing.  CUDA_VISIBLE_DEVICES is honoured when mapping the torch index to NVML's."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip() != ""]
+        try:
+            self.index = int(ids[index]) if ids else index
+        except Exception:
+            self.index = index
+        self.rows, self.proc, self.nvml, self.stop_flag, self.t = [], None, None, False, None
+        self.sm, self.mx, self.reasons = [], None, set()
+
+    def _poll(self):
+        n = self.nvml
+        names = {n.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 n.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 n.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 n.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -74,6 +112,12 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,7 +137,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peaks():
@@ -239,7 +283,7 @@ def fitting_extra(H, device, n_rays, precision):
     return {"rays": n_rays, "samples_per_ray_and_field": int(out["sdf_hand"].shape[0] // n_rays), "ms_per_step": ms,
             "value": n_rays / (ms * 1e-3), "unit": "rays/s", "precision": precision,
             "finite_pose_grads": bool(torch.isfinite(bt.grad).all() and torch.isfinite(Ro.grad).all()),
-            "note": "eager launches; hand field on per-layer TF32x3 kernels, object field on the chain kernels"}
+            "note": "eager launches; hand field on the per-layer pre-packed bf16x3 contractions (gemm_bx3), object field on the chain kernels"}
 
 
 def _time_calls(fn, warm=2, reps=3):
@@ -308,6 +352,7 @@ def run_gpu_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=device)
     H, renderer, params, opt = build_gpu_model(device, args.precision, args.optimizer)
+    renderer.ray_streams = args.ray_streams
     flat_opt = args.optimizer == "flat"
     from honerf_b200 import dist as hdist
     n_rays = args.rays
@@ -471,7 +516,13 @@ def run_gpu_arm(args):
     roof, comp = None, None
     if rank == 0:
         # rank 0 alone runs this pass: the step without its collective
+        # per-kernel durations are taken with the shards serialised (one stream): events around a launch that shares
+        # the SMs with the other shard's kernels would time the sharing, not the kernel
+        renderer.ray_streams = 1
         roof = mlp_roofline(H, lambda: (fwd_bwd(dev_batch), apply_grads()), n_rays)
+        renderer.ray_streams = args.ray_streams
+        if roof is not None:
+            roof["measured_with"] = "ray_streams=1 (kernels serialised, one launch per family and step)"
         comp = compositor_roofline(H, device)
     large = None
     if rank == 0 and world == 1 and args.large_rays > 0:
@@ -541,6 +592,7 @@ def run_gpu_arm(args):
                        "cuda_graph": graph is not None,
                        "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
                        "loss": "hn_render_loss_fwd/_bwd (fused)" if args.loss == "fused" else "torch ops",
+                       "ray_streams": args.ray_streams,
                        "l2": "per-step activation stash (~2 GB at 512 rays) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
@@ -684,6 +736,8 @@ def main():
     ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
+    ap.add_argument("--ray-streams", type=int, default=1,
+                    help="render each GPU's rays as this many shards on concurrent CUDA streams (NeuSRenderer.ray_streams)")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="fused: hn_render_loss_fwd/_bwd (default); torch: the reference's loss lines as torch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -88,6 +88,7 @@ class PackedMLP:
         self.chain = None
         self.struct = None
         self._key = None
+        self.shared_token = None            # see shared_param_tokens()
 
     def _version_key(self):
         return tuple((p.data_ptr(), p._version) for layer in self.layers for p in layer)
@@ -147,6 +148,10 @@ class PackedMLP:
 
     def new_grad(self):
         """Zeroed packed gradient buffers + the struct pointing at them."""
+        return self.new_grad_flat()[1:]
+
+    def new_grad_flat(self):
+        """(flat, dW, db, struct): `flat` is the ONE allocation dW and the per-layer db are carved from."""
         dev = self.W.device
         # ONE zero-filled allocation (one fill kernel) carved into the packed dW and the per-layer db
         n_b = sum(_round4(o) for (_, o) in self.dims)
@@ -160,7 +165,19 @@ class PackedMLP:
         for l in range(len(self.layers)):
             gs.dW[l] = dW[self.offsets[l]:].data_ptr()
             gs.db[l] = db[l].data_ptr()
-        return dW, db, gs
+        return flat, dW, db, gs
+
+    def flat_grad_floats(self):
+        return self.total + sum(_round4(o) for (_, o) in self.dims)
+
+    def split_flat_grad(self, flat):
+        """(dW, [db per layer]) views of a flat packed gradient laid out like new_grad()'s allocation."""
+        dW = flat[:self.total]
+        db, off = [], self.total
+        for (_, o) in self.dims:
+            db.append(flat[off:off + o])
+            off += _round4(o)
+        return dW, db
 
     def unpack_grads(self, dW, db):
         """(dg, dv, db) per layer from packed dW via hn_wn_bwd.  Returns a flat list in the order
@@ -182,6 +199,49 @@ class PackedMLP:
 
     def flat_params(self):
         return [p for layer in self.layers for p in layer]
+
+
+class _ParamTokenFn(torch.autograd.Function):
+    """One autograd edge for ALL parameters of a net: forward packs the weights (once per parameter version) and
+    returns a token shaped like the flat packed gradient; every field call made with that token returns its flat
+    packed gradient for it, autograd adds the flats of all consumers (one add per extra consumer instead of one per
+    parameter), and this backward unpacks the sum to (dg, dv, db) per layer once (hn_wn_bwd_batch, one launch)."""
+
+    @staticmethod
+    def forward(ctx, packed, *params):
+        pk = packed.get()
+        ctx.packed = pk
+        return torch.empty(pk.flat_grad_floats(), device=pk.W.device, dtype=torch.float32)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, flat):
+        pk = ctx.packed
+        dW, db = pk.split_flat_grad(_f32c(flat))
+        return (None,) + tuple(pk.unpack_grads(dW, db))
+
+
+class shared_param_tokens:
+    """with shared_param_tokens(packed_a, packed_b): every sdf_obj / color_obj call inside shares ONE parameter edge
+    per net.  Used when a batch is rendered as several ray shards on concurrent streams: the weights are packed once
+    on the current stream BEFORE the shards fork, and the parameter gradients are unpacked once after they join."""
+
+    def __init__(self, *packed):
+        self.packed = packed
+
+    def __enter__(self):
+        for pk in self.packed:
+            params = pk.flat_params()
+            if torch.is_grad_enabled() and any(q.requires_grad for q in params):
+                pk.shared_token = _ParamTokenFn.apply(pk, *params)
+            else:
+                pk.get()
+        return self
+
+    def __exit__(self, *exc):
+        for pk in self.packed:
+            pk.shared_token = None
+        return False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -228,6 +288,7 @@ class _SdfObjFn(torch.autograd.Function):
         ctx.struct = pk.struct
         ctx.pts_needs_grad = pts.requires_grad
         ctx.params_need_grad = any(p.requires_grad for p in params)
+        ctx.token_mode = len(params) == 1 and len(pk.layers) * 3 != 1
         return sdf, feat, normal
 
     @staticmethod
@@ -241,11 +302,11 @@ class _SdfObjFn(torch.autograd.Function):
         d_feat = _f32c(d_feat) if d_feat is not None else None
         d_normal = _f32c(d_normal) if d_normal is not None else torch.zeros(n, 3, device=dev)
         d_pts = torch.empty(n, 3, device=dev, dtype=torch.float32) if ctx.pts_needs_grad else None
-        grads = [None] * (3 * len(pk.layers))
+        grads = [None] * (1 if ctx.token_mode else 3 * len(pk.layers))
         if n > 0:
             gs = None
             if ctx.params_need_grad:
-                dW, db, gs = pk.new_grad()
+                flat, dW, db, gs = pk.new_grad_flat()
             wsf = lib.hn_sdf_obj_ws_floats(n, HN_WS_BWD)
             ws = torch.empty(wsf, device=dev, dtype=torch.float32)
             check(lib.hn_sdf_obj_bwd(ctypes.byref(ctx.struct), n, ctx.inv_scale, _ptr(ctx.stash), _ptr(d_sdf),
@@ -253,7 +314,7 @@ class _SdfObjFn(torch.autograd.Function):
                                      ctypes.byref(gs) if gs is not None else None, _ptr(ws), wsf,
                                      ctx.precision, _stream(ctx.stash)), "hn_sdf_obj_bwd")
             if gs is not None:
-                grads = pk.unpack_grads(dW, db)
+                grads = [flat] if ctx.token_mode else pk.unpack_grads(dW, db)
         elif d_pts is not None:
             d_pts.zero_()
         ctx.stash = None
@@ -264,6 +325,8 @@ def sdf_obj(packed, pts, inv_scale=1.0, precision=None):
     """Fused SDFNetwork_OBJ.forward + .gradient (utils/fields.py:316-347).
     Returns sdf [N,1], feature [N,256], normal [N,3]; differentiable w.r.t. pts and parameters."""
     precision = _default_precision if precision is None else precision
+    if packed.shared_token is not None:
+        return _SdfObjFn.apply(pts, packed, float(inv_scale), precision, packed.shared_token)
     return _SdfObjFn.apply(pts, packed, float(inv_scale), precision, *packed.flat_params())
 
 
@@ -289,6 +352,7 @@ class _ColorObjFn(torch.autograd.Function):
         ctx.rgb = rgb
         ctx.need = (pts.requires_grad, dirs.requires_grad, feat.requires_grad, normal.requires_grad)
         ctx.params_need_grad = any(p.requires_grad for p in params)
+        ctx.token_mode = len(params) == 1 and len(pk.layers) * 3 != 1
         return rgb
 
     @staticmethod
@@ -302,11 +366,11 @@ class _ColorObjFn(torch.autograd.Function):
         d_dirs = torch.empty(n, 3, device=dev) if ctx.need[1] else None
         d_feat = torch.empty(n, 256, device=dev) if ctx.need[2] else None
         d_nrm = torch.empty(n, 3, device=dev) if ctx.need[3] else None
-        grads = [None] * (3 * len(pk.layers))
+        grads = [None] * (1 if ctx.token_mode else 3 * len(pk.layers))
         if n > 0:
             gs = None
             if ctx.params_need_grad:
-                dW, db, gs = pk.new_grad()
+                flat, dW, db, gs = pk.new_grad_flat()
             wsf = lib.hn_color_obj_ws_floats(n, HN_WS_BWD)
             ws = torch.empty(wsf, device=dev, dtype=torch.float32)
             check(lib.hn_color_obj_bwd(ctypes.byref(ctx.struct), n, _ptr(ctx.stash), _ptr(ctx.rgb), _ptr(d_rgb),
@@ -314,7 +378,7 @@ class _ColorObjFn(torch.autograd.Function):
                                        ctypes.byref(gs) if gs is not None else None, _ptr(ws), wsf,
                                        ctx.precision, _stream(ctx.stash)), "hn_color_obj_bwd")
             if gs is not None:
-                grads = pk.unpack_grads(dW, db)
+                grads = [flat] if ctx.token_mode else pk.unpack_grads(dW, db)
         ctx.stash = None
         return (d_pts, d_dirs, d_feat, d_nrm, None, None) + tuple(grads)
 
@@ -322,6 +386,8 @@ class _ColorObjFn(torch.autograd.Function):
 def color_obj(packed, pts, dirs, feat, normal, precision=None):
     """RenderingNetwork_OBJ.forward (utils/fields.py:387-405): -> rgb [N,3]."""
     precision = _default_precision if precision is None else precision
+    if packed.shared_token is not None:
+        return _ColorObjFn.apply(pts, dirs, feat, normal, packed, precision, packed.shared_token)
     return _ColorObjFn.apply(pts, dirs, feat, normal, packed, precision, *packed.flat_params())
 
 

@@ -36,6 +36,12 @@ class NeuSRenderer:
         self.up_sample_steps = up_sample_steps
         self.perturb = perturb
         self.index = None
+        # B200 extension (not in the reference): render a batch as `ray_streams` contiguous ray shards on concurrent
+        # CUDA streams.  Rays are independent, every field kernel is a persistent one-CTA-per-SM kernel whose tile
+        # count rarely divides 148, and the sampler's small SDF queries fill under half of the SMs: with two shards
+        # in flight the idle SMs of one shard's last wave run the other shard's kernels.  Object field only.
+        self.ray_streams = 1
+        self._stream_pool = {}
 
     # -- field access ----------------------------------------------------------------------------
     def _sdf_only(self, pts, bt_inv, T_pose_21):
@@ -96,6 +102,48 @@ class NeuSRenderer:
         if self.model_type == 'obj':
             rays_o, rays_d = self.convert_obj_to_local(rays_o, rays_d, Ro, To)
         self.index = index
+        k = int(self.ray_streams)
+        if k > 1 and self.model_type == 'obj' and rays_o.is_cuda and len(rays_o) >= 2 * k:
+            return self._render_on_streams(k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts)
+        return self._render_local(rays_o, rays_d, near, far, bt_inv, T_pose_21, verts)
+
+    def _render_on_streams(self, k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts):
+        """`k` contiguous ray shards, each through _render_local on its own stream.  Fork/join on the caller's stream
+        (CUDA-graph capturable); the weights are packed and their ONE autograd edge per net is created before the fork
+        (ops.shared_param_tokens), so parameter gradients are unpacked once after the shards' backward passes join --
+        autograd runs every backward node on its forward's stream, so the backward overlaps the same way."""
+        dev = rays_o.device
+        cur = torch.cuda.current_stream(dev)
+        pool = self._stream_pool.setdefault(str(dev), [])
+        while len(pool) < k:
+            pool.append(torch.cuda.Stream(device=dev))
+        # host-made constants are cached per device: create them before the fork, not concurrently on two streams
+        _linspace_z(near, far, self.n_samples, dev)
+        if self.n_importance > 0:
+            ops._u_samples(self.n_importance // self.up_sample_steps, dev)
+        outs = []
+        with ops.shared_param_tokens(self.sdf_network.packed(), self.color_network.packed()):
+            shards = list(zip(torch.chunk(rays_o, k), torch.chunk(rays_d, k)))
+            for s, (o, d) in zip(pool, shards):
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    outs.append(self._render_local(o, d, near, far, bt_inv, T_pose_21, verts))
+        for s in pool[:len(shards)]:
+            cur.wait_stream(s)
+        total = float(len(rays_o))
+        merged = {}
+        for key in outs[0]:
+            parts = [o[key] for o in outs]
+            for t in parts:
+                t.record_stream(cur)                 # allocated on a shard stream, consumed on the caller's
+            if key == 'gradient_error':              # mean over all samples = shard means weighted by shard size
+                merged[key] = sum(t * (len(sh[0]) / total) for t, sh in zip(parts, shards))
+            else:
+                merged[key] = torch.cat(parts, dim=0)
+        return merged
+
+    def _render_local(self, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts):
+        """utils/renderer.py:199-258 on rays already in the field's frame."""
         batch_size = len(rays_o)
         device = rays_o.device
         sample_dist = (far - near) / self.n_samples

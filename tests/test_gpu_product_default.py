@@ -91,3 +91,51 @@ def test_hand_field_and_fitting_renderer_with_default_precision():
     cases.fit_loss(o, fc["true_rgb"].to(DEV)).backward()
     assert torch.isfinite(o["color_fine"]).all() and o["color_fine"].shape == (10, 3)
     assert torch.isfinite(btg.grad).all() and torch.isfinite(Ro.grad).all() and float(btg.grad.abs().max()) > 0
+
+
+def test_ray_streams_render_equals_single_stream():
+    """NeuSRenderer.ray_streams = 2 (two ray shards on concurrent streams, one shared parameter edge per net) against
+    the single-stream render of the same rays: rendered outputs identical to 1e-6 (per-ray arithmetic does not depend on
+    the batch a ray is in), loss equal to 1e-6 relative, every gradient to 1e-4 relative (summation order of the weight
+    gradients differs); also under torch.no_grad, with an odd shard split, and repeated (stash reuse across streams)."""
+    import honerf_b200 as H
+    import ref_conf
+    import synth
+    from golden_util import max_abs, rel_err
+    from gpu_util import DEV, obj_modules
+    sdf, col, var, _, _ = obj_modules()
+    r = H.NeuSRenderer(sdf, var, col, "obj", **dict(ref_conf.RENDERER_CONF, perturb=0.0))
+    R = synth.object_rays(301, seed=77)
+    gen = torch.Generator().manual_seed(3)
+    true_rgb = torch.rand(301, 3, generator=gen).to(DEV)
+    true_mask = (torch.rand(301, 1, generator=gen) > 0.5).float().to(DEV)
+    Ro, To = R["Ro"].to(DEV).requires_grad_(True), R["To"].to(DEV).requires_grad_(True)
+    params = [p for m in (sdf, col, var) for n, p in m.named_parameters() if n != "se3_refine"] + [Ro, To]
+
+    def run(k):
+        r.ray_streams = k
+        out = r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), 0.4, 1.5, None, None, None, Ro, To, 0)
+        loss = H.losses.training_loss(out, true_rgb, true_mask)
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        torch.cuda.synchronize()
+        return out, loss.detach(), grads
+    out1, l1, g1 = run(1)
+    for _ in range(2):
+        out2, l2, g2 = run(2)
+        assert set(out1) == set(out2)
+        for k in out1:
+            assert out1[k].shape == out2[k].shape, k
+            assert max_abs(out1[k], out2[k]) < 1e-6, k
+        assert rel_err(l2, l1) < 1e-6
+        for a, b in zip(g2, g1):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert rel_err(a, b) < 1e-4
+    out3, l3, g3 = run(3)
+    assert max_abs(out3["color_fine"], out1["color_fine"]) < 1e-6 and rel_err(g3[0], g1[0]) < 1e-4
+    with torch.no_grad():
+        r.ray_streams = 2
+        o = r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), 0.4, 1.5, None, None, None, Ro, To, 0)
+        torch.cuda.synchronize()
+    assert max_abs(o["color_fine"], out1["color_fine"]) < 1e-6 and not o["color_fine"].requires_grad
+    assert sdf.packed().shared_token is None
