@@ -32,6 +32,10 @@ F_O, C_O = 1_049_088, 585_728
 FLOPS_PER_RAY_TRAIN = 112 * F_O + 128 * (6 * F_O + 3 * C_O)
 
 
+WORKLOAD = ("obj-field train step (BASELINE configs[2]): %d rays/GPU x (64+64) samples, masked-L1+BCE+eikonal loss, "
+            "2nd-order bwd, Adam")
+
+
 def training_loss(out, true_rgb, true_mask, igr_weight=1.0, mask_weight=1.0):
     """exp_runner.py:206-227 without the VGG term (caller-side code of the reference)."""
     mask_sum = true_mask.sum() + 1e-5
@@ -191,15 +195,16 @@ def run_reference_arm(args):
     if rank != 0:
         return
     n_rays = min(args.rays, 512)      # bounded sample: one 512-ray batch per step (~3 s on 8 cores)
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    # exactly K steps / W warm-ups as asked, bounded so the arm stays within a few minutes (~1-4 s per step on the host)
+    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
     rps, dt, cores = time_cpu(n_rays, steps, warmup)
     line = {
         "impl": "reference", "metric": "rays/sec render fwd+bwd (64+64 samples), object-field train step",
         "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "obj-field train step, %d rays x (64+64) samples, masked-L1+BCE+eikonal, Adam" % n_rays,
-                   "rays_per_step": n_rays},
+        "config": {"workload": WORKLOAD % n_rays, "rays_per_gpu": n_rays, "precision": "f32 (torch CPU)",
+                   "parallelism": "CPU threads x%d" % cores},
         "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
                          "sample": "%d steps of one %d-ray batch (oracle/honerf_oracle.py, torch CPU)" % (steps, n_rays)},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -258,30 +263,37 @@ def fitting_extra(H, device, n_rays, precision):
     Ro = synth.random_rotation(g).to(device).requires_grad_(True)
     To = (J.mean(0) + 0.02 * torch.randn(3, generator=g)).to(device).requires_grad_(True)
     true_rgb = torch.rand(n_rays, 3, generator=g).to(device)
+    true_mask = (torch.rand(n_rays, 1, generator=g) > 0.3).float().to(device)
     bt = bt.to(device).requires_grad_(True)
     T = T.to(device)
     ro, rd = HR["rays_o"].to(device), HR["rays_d"].to(device)
 
     def step():
         out = r.render(ro, rd, HR["near"], HR["far"], bt, T, None, Ro, To)
-        loss = (out["color_fine"] - true_rgb).abs().mean() + 0.5 * out["weight_sum"].mean() \
-            + out["sdf_hand"].clip(-1, 0).abs().mean() + out["sdf_obj"].clip(-1, 0).abs().mean()
+        # fit_type '12' of fitting_single.py:253-283 (render loss + 30 contact + 20 penetration), fused loss kernels
+        loss = H.losses.fitting_render_loss(out, true_rgb, true_mask) + H.losses.interaction_loss(out)
         bt.grad = None; Ro.grad = None; To.grad = None
         loss.backward()
         return out
 
-    for _ in range(2):
-        out = step()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(3):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 3
+    def timed_steps():
+        for _ in range(2):
+            o = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 3, o
+    ms, out = timed_steps()
+    r.field_streams = True              # the two fields on two CUDA streams (NeuSRenderer_fitting.field_streams)
+    ms_fs, _ = timed_steps()
     return {"rays": n_rays, "samples_per_ray_and_field": int(out["sdf_hand"].shape[0] // n_rays), "ms_per_step": ms,
             "value": n_rays / (ms * 1e-3), "unit": "rays/s", "precision": precision,
+            "field_streams": {"ms_per_step": ms_fs, "value": n_rays / (ms_fs * 1e-3)},
+            "loss": "fitting_single.py:253-283 (render + 30 contact + 20 penetration), fused loss kernels",
             "finite_pose_grads": bool(torch.isfinite(bt.grad).all() and torch.isfinite(Ro.grad).all()),
             "note": "eager launches; hand field on the per-layer pre-packed bf16x3 contractions (gemm_bx3), object field on the chain kernels"}
 
@@ -586,8 +598,7 @@ def run_gpu_arm(args):
             "dtype": {"simt_fp32": "f32", "tc_tf32": "tf32", "tc_tf32x3": "tf32 (3xTF32 split operands)",
                       "tc_bf16x3": "bf16 (split hi+lo operands, 3 MMAs per product, fp32 accumulate)"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "obj-field train step (BASELINE configs[2]): %d rays/GPU x (64+64) samples, "
-                                   "masked-L1+BCE+eikonal loss, 2nd-order bwd, Adam" % n_rays,
+            "config": {"workload": WORKLOAD % n_rays,
                        "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
                        "cuda_graph": graph is not None,
                        "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
@@ -736,7 +747,7 @@ def main():
     ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
-    ap.add_argument("--ray-streams", type=int, default=1,
+    ap.add_argument("--ray-streams", type=int, default=3,
                     help="render each GPU's rays as this many shards on concurrent CUDA streams (NeuSRenderer.ray_streams)")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="fused: hn_render_loss_fwd/_bwd (default); torch: the reference's loss lines as torch ops")

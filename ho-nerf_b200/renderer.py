@@ -223,6 +223,11 @@ class _FittingBase:
         self.deviation_network_obj = deviation_network_obj
         self.color_network_obj = color_network_obj
         self.use_multiple_streams = True    # stored and never read, as in the reference (SURVEY D-5)
+        # B200 extension: evaluate the two fields (independent until the joint compositor) on two CUDA streams, so
+        # the object field's persistent chain kernels run in the tails and launch gaps of the hand field's ~100
+        # per-layer launches (and vice versa).  Off by default.
+        self.field_streams = False
+        self._side_streams = {}
         self.n_samples = n_samples
         self.n_importance = n_importance
         self.n_outside = n_outside
@@ -230,6 +235,25 @@ class _FittingBase:
         self.perturb = perturb
 
     # -- helpers ---------------------------------------------------------------------------------
+    def _two_fields(self, hand_fn, obj_fn, device):
+        """(hand_fn(), obj_fn()), the object field on a side stream when field_streams is set (fork / join on the
+        caller's stream: CUDA-graph capturable; autograd runs each field's backward on its forward's stream)."""
+        if not (self.field_streams and device.type == 'cuda'):
+            return hand_fn(), obj_fn()
+        cur = torch.cuda.current_stream(device)
+        side = self._side_streams.get(str(device))
+        if side is None:
+            side = self._side_streams[str(device)] = torch.cuda.Stream(device=device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            res_obj = obj_fn()
+        res_hand = hand_fn()
+        cur.wait_stream(side)
+        for t in (res_obj if isinstance(res_obj, (tuple, list)) else (res_obj,)):
+            if torch.is_tensor(t):
+                t.record_stream(cur)
+        return res_hand, res_obj
+
     def _hand_pts(self, pts, lead):
         """Hand SDF input: un-batched [N,3]; frame-batched [F, N/F, 3] (utils/renderer_batch.py:107,143)."""
         return pts if len(lead) == 1 else pts.reshape(lead[0], -1, 3)
@@ -298,30 +322,37 @@ class _FittingBase:
         if self.n_importance > 0:
             with torch.no_grad():
                 flat = z_vals.reshape(-1, self.n_samples)
-                pts_hand = ops.ray_points(rays_o_hand.reshape(-1, 3), rays_d_hand.reshape(-1, 3), flat)
-                pts_obj = ops.ray_points(rays_o_obj.reshape(-1, 3), rays_d_obj.reshape(-1, 3), flat)
-                sdf_hand = self._sdf_only('hand', pts_hand, lead, bt_inv, T_pose_21).reshape(*lead, self.n_samples)
-                sdf_obj = self._sdf_only('obj', pts_obj, lead, bt_inv, T_pose_21).reshape(*lead, self.n_samples)
+                k = self.n_importance // self.up_sample_steps
+                if rays_o.is_cuda:
+                    ops._u_samples(k, device)           # cached host-made constant: create it before any fork
+
+                def chain(ctype, ro, rd):
+                    """one field's hierarchical sampling (utils/renderer.py:433-470); returns its new samples"""
+                    pts = ops.ray_points(ro.reshape(-1, 3), rd.reshape(-1, 3), flat)
+                    sdf = self._sdf_only(ctype, pts, lead, bt_inv, T_pose_21).reshape(*lead, self.n_samples)
+                    z, news = z_vals, []
+                    for i in range(self.up_sample_steps):
+                        new = self.up_sample(ro, rd, z, sdf, k, 64 * 2 ** i)
+                        z, sdf = self.cat_z_vals(ro, rd, z, new, sdf, bt_inv, T_pose_21, ctype,
+                                                 last=(i + 1 == self.up_sample_steps))
+                        news.append(new)
+                    return news
+                news_hand, news_obj = self._two_fields(lambda: chain('hand', rays_o_hand, rays_d_hand),
+                                                       lambda: chain('obj', rays_o_obj, rays_d_obj), device)
                 new_all = [z_vals]
-                for i in range(self.up_sample_steps):
-                    last = i + 1 == self.up_sample_steps
-                    k = self.n_importance // self.up_sample_steps
-                    new_hand = self.up_sample(rays_o_hand, rays_d_hand, z_vals_hand, sdf_hand, k, 64 * 2 ** i)
-                    z_vals_hand, sdf_hand = self.cat_z_vals(rays_o_hand, rays_d_hand, z_vals_hand, new_hand, sdf_hand,
-                                                            bt_inv, T_pose_21, 'hand', last=last)
-                    new_obj = self.up_sample(rays_o_obj, rays_d_obj, z_vals_obj, sdf_obj, k, 64 * 2 ** i)
-                    z_vals_obj, sdf_obj = self.cat_z_vals(rays_o_obj, rays_d_obj, z_vals_obj, new_obj, sdf_obj,
-                                                          bt_inv, T_pose_21, 'obj', last=last)
-                    new_all += [new_hand, new_obj]
+                for nh, no in zip(news_hand, news_obj):
+                    new_all += [nh, no]
                 z_vals = torch.cat(new_all, dim=-1)
         n = z_vals.shape[-1]
         z_vals = ops.sort_rows(z_vals.reshape(-1, n)).reshape(*lead, n)
         self.last_z_vals = z_vals
 
-        alpha_hand, color_hand, sdf_hand, ge_hand, grad_hand = self.get_alpha_sample_color(
-            rays_o_hand, rays_d_hand, bt_inv, T_pose_21, z_vals, sample_dist, 'hand')
-        alpha_obj, color_obj, sdf_obj, ge_obj, grad_obj = self.get_alpha_sample_color(
-            rays_o_obj, rays_d_obj, bt_inv, T_pose_21, z_vals, sample_dist, 'obj')
+        (alpha_hand, color_hand, sdf_hand, ge_hand, grad_hand), (alpha_obj, color_obj, sdf_obj, ge_obj, grad_obj) = \
+            self._two_fields(
+                lambda: self.get_alpha_sample_color(rays_o_hand, rays_d_hand, bt_inv, T_pose_21, z_vals, sample_dist,
+                                                    'hand'),
+                lambda: self.get_alpha_sample_color(rays_o_obj, rays_d_obj, bt_inv, T_pose_21, z_vals, sample_dist,
+                                                    'obj'), device)
         color, weights_sum = ops.fit_composite(alpha_hand.reshape(-1, n), color_hand.reshape(-1, n, 3),
                                                alpha_obj.reshape(-1, n), color_obj.reshape(-1, n, 3))
         return {

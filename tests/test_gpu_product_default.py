@@ -96,7 +96,7 @@ def test_hand_field_and_fitting_renderer_with_default_precision():
 def test_ray_streams_render_equals_single_stream():
     """NeuSRenderer.ray_streams = 2 (two ray shards on concurrent streams, one shared parameter edge per net) against
     the single-stream render of the same rays: rendered outputs identical to 1e-6 (per-ray arithmetic does not depend on
-    the batch a ray is in), loss equal to 1e-6 relative, every gradient to 1e-4 relative (summation order of the weight
+    the batch a ray is in; the eikonal mean is recombined from shard means: 1e-6 relative), loss equal to 1e-6 relative, every gradient to 1e-4 relative (summation order of the weight
     gradients differs); also under torch.no_grad, with an odd shard split, and repeated (stash reuse across streams)."""
     import honerf_b200 as H
     import ref_conf
@@ -125,7 +125,10 @@ def test_ray_streams_render_equals_single_stream():
         assert set(out1) == set(out2)
         for k in out1:
             assert out1[k].shape == out2[k].shape, k
-            assert max_abs(out1[k], out2[k]) < 1e-6, k
+            if k == "gradient_error":       # a mean over all samples: shard means recombined, 1e-6 relative
+                assert rel_err(out2[k], out1[k]) < 1e-6
+            else:
+                assert max_abs(out1[k], out2[k]) < 1e-6, k
         assert rel_err(l2, l1) < 1e-6
         for a, b in zip(g2, g1):
             assert (a is None) == (b is None)
