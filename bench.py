@@ -526,7 +526,7 @@ def run_gpu_arm(args):
 
     # ---- roofline of the dominant kernel family (the MLP contractions), rank 0, separate pass ----
     roof, comp = None, None
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         # rank 0 alone runs this pass: the step without its collective
         # per-kernel durations are taken with the shards serialised (one stream): events around a launch that shares
         # the SMs with the other shard's kernels would time the sharing, not the kernel
@@ -581,7 +581,9 @@ def run_gpu_arm(args):
     fwd_extra = None
     if rank == 0 and world == 1 and args.fit_rays > 0:
         try:
+            renderer.ray_streams = 1          # eager launches: extra streams only add CPU launch work here
             fwd_extra = forward_extras(H, device, renderer, dev_batch, host, Ro, To, 4096)
+            renderer.ray_streams = args.ray_streams
         except Exception as e:      # noqa: BLE001
             fwd_extra = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
@@ -752,6 +754,8 @@ def main():
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="fused: hn_render_loss_fwd/_bwd (default); torch: the reference's loss lines as torch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true",
+                    help="skip the per-kernel event-timing passes (for an ncu launch list of the train step alone)")
     ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")
     ap.add_argument("--fit-rays", type=int, default=512, help="extra informational measurements: two-field fitting step, forward-only renders (0 disables)")
