@@ -365,6 +365,8 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=device)
     H, renderer, params, opt = build_gpu_model(device, args.precision, args.optimizer)
     renderer.ray_streams = args.ray_streams
+    if args.ray_shards:
+        renderer.ray_shard_sizes = [int(v) for v in args.ray_shards.split(",")]
     flat_opt = args.optimizer == "flat"
     from honerf_b200 import dist as hdist
     n_rays = args.rays
@@ -605,7 +607,7 @@ def run_gpu_arm(args):
                        "cuda_graph": graph is not None,
                        "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
                        "loss": "hn_render_loss_fwd/_bwd (fused)" if args.loss == "fused" else "torch ops",
-                       "ray_streams": args.ray_streams,
+                       "ray_streams": args.ray_streams, "ray_shards": args.ray_shards or "equal",
                        "l2": "per-step activation stash (~2 GB at 512 rays) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
@@ -751,6 +753,7 @@ def main():
                     help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
     ap.add_argument("--ray-streams", type=int, default=3,
                     help="render each GPU's rays as this many shards on concurrent CUDA streams (NeuSRenderer.ray_streams)")
+    ap.add_argument("--ray-shards", default="", help="explicit shard sizes, e.g. 148,148,216 (overrides --ray-streams)")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="fused: hn_render_loss_fwd/_bwd (default); torch: the reference's loss lines as torch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -41,6 +41,7 @@ class NeuSRenderer:
         # count rarely divides 148, and the sampler's small SDF queries fill under half of the SMs: with two shards
         # in flight the idle SMs of one shard's last wave run the other shard's kernels.  Object field only.
         self.ray_streams = 1
+        self.ray_shard_sizes = None         # optional explicit shard sizes (sum = batch); default: equal shards
         self._stream_pool = {}
 
     # -- field access ----------------------------------------------------------------------------
@@ -102,12 +103,15 @@ class NeuSRenderer:
         if self.model_type == 'obj':
             rays_o, rays_d = self.convert_obj_to_local(rays_o, rays_d, Ro, To)
         self.index = index
-        k = int(self.ray_streams)
+        sizes = self.ray_shard_sizes
+        if sizes is not None and sum(sizes) != len(rays_o):
+            sizes = None
+        k = len(sizes) if sizes is not None else int(self.ray_streams)
         if k > 1 and self.model_type == 'obj' and rays_o.is_cuda and len(rays_o) >= 2 * k:
-            return self._render_on_streams(k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts)
+            return self._render_on_streams(k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, sizes)
         return self._render_local(rays_o, rays_d, near, far, bt_inv, T_pose_21, verts)
 
-    def _render_on_streams(self, k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts):
+    def _render_on_streams(self, k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, sizes=None):
         """`k` contiguous ray shards, each through _render_local on its own stream.  Fork/join on the caller's stream
         (CUDA-graph capturable); the weights are packed and their ONE autograd edge per net is created before the fork
         (ops.shared_param_tokens), so parameter gradients are unpacked once after the shards' backward passes join --
@@ -123,7 +127,10 @@ class NeuSRenderer:
             ops._u_samples(self.n_importance // self.up_sample_steps, dev)
         outs = []
         with ops.shared_param_tokens(self.sdf_network.packed(), self.color_network.packed()):
-            shards = list(zip(torch.chunk(rays_o, k), torch.chunk(rays_d, k)))
+            if sizes is not None:
+                shards = list(zip(torch.split(rays_o, list(sizes)), torch.split(rays_d, list(sizes))))
+            else:
+                shards = list(zip(torch.chunk(rays_o, k), torch.chunk(rays_d, k)))
             for s, (o, d) in zip(pool, shards):
                 s.wait_stream(cur)
                 with torch.cuda.stream(s):
