@@ -380,13 +380,27 @@ def run_gpu_arm(args):
 
     def fwd_bwd(b):
         """render + loss + backward; for N > 1 also packs every gradient into one flat buffer"""
-        out = renderer.render(b["rays_o"], b["rays_d"], host["near"], host["far"], None, None, None, Ro, To, 0)
-        if args.loss == "fused":
-            # csrc/loss.cu: one forward + one backward launch instead of ~30 torch launches (SURVEY 8f row 2)
-            loss = H.ops.render_loss(out["color_fine"], out["weight_sum"], b["true_rgb"], b["true_mask"],
-                                     out["gradient_error"], 0.0, 1.0, 1.0, 1.0)[0]
+        if args.loss == "fused" and args.shard_loss:
+            # per-shard loss on the shard's own stream (no join between forward and backward): the shards' totals add
+            # up to the batch loss -- batch-wide mask_sum + 1e-5 as a device scalar, BCE / eikonal means weighted by
+            # the shard's share of the rays
+            div = b["true_mask"].sum() + 1e-5
+
+            def shard_loss(out, lo, hi):
+                w = (hi - lo) / float(n_rays)
+                return H.ops.render_loss(out["color_fine"], out["weight_sum"], b["true_rgb"][lo:hi], b["true_mask"][lo:hi],
+                                         out["gradient_error"], div, 1.0, w, w)[0]
+            parts = renderer.render_sharded(b["rays_o"], b["rays_d"], host["near"], host["far"], None, None, None, Ro, To,
+                                            0, shard_loss)
+            loss = parts[0] if len(parts) == 1 else torch.stack(parts).sum()
         else:
-            loss = training_loss(out, b["true_rgb"], b["true_mask"])
+            out = renderer.render(b["rays_o"], b["rays_d"], host["near"], host["far"], None, None, None, Ro, To, 0)
+            if args.loss == "fused":
+                # csrc/loss.cu: one forward + one backward launch instead of ~30 torch launches (SURVEY 8f row 2)
+                loss = H.ops.render_loss(out["color_fine"], out["weight_sum"], b["true_rgb"], b["true_mask"],
+                                         out["gradient_error"], 0.0, 1.0, 1.0, 1.0)[0]
+            else:
+                loss = training_loss(out, b["true_rgb"], b["true_mask"])
         opt.zero_grad(set_to_none=True)
         Ro.grad = None; To.grad = None
         loss.backward()
@@ -608,6 +622,7 @@ def run_gpu_arm(args):
                        "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
                        "loss": "hn_render_loss_fwd/_bwd (fused)" if args.loss == "fused" else "torch ops",
                        "ray_streams": args.ray_streams, "ray_shards": args.ray_shards or "equal",
+                       "shard_loss": bool(args.shard_loss) and args.loss == "fused",
                        "l2": "per-step activation stash (~2 GB at 512 rays) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
@@ -754,6 +769,9 @@ def main():
     ap.add_argument("--ray-streams", type=int, default=3,
                     help="render each GPU's rays as this many shards on concurrent CUDA streams (NeuSRenderer.ray_streams)")
     ap.add_argument("--ray-shards", default="", help="explicit shard sizes, e.g. 148,148,216 (overrides --ray-streams)")
+    ap.add_argument("--shard-loss", type=int, default=1,
+                    help="1: the fused loss is evaluated per ray shard on the shard's stream (render_sharded); 0: one "
+                         "loss launch on the merged outputs")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="fused: hn_render_loss_fwd/_bwd (default); torch: the reference's loss lines as torch ops")
     ap.add_argument("--no-cpu-baseline", action="store_true")

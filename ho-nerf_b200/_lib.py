@@ -120,7 +120,7 @@ PROTOTYPES = {
     "hn_rays_ndc_grid": (c_int, [P, P, c_int, c_int, P, c_int64, c_int64, P, P, P]),
     "hn_nn_select": (c_int, [P, P, P, c_int, c_int, P, P, P]),
     "hn_loss_ws_floats": (c_int64, []),
-    "hn_render_loss_fwd": (c_int, [P, P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, P, P]),
+    "hn_render_loss_fwd": (c_int, [P, P, P, P, P, c_int64, c_float, P, c_float, c_float, c_float, P, P, P]),
     "hn_render_loss_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_float, c_float, c_float, P, P, P, P]),
     "hn_interaction_loss_fwd": (c_int, [P, c_int64, P, c_int64, c_int64, c_float, c_float, c_float, P, P, P]),
     "hn_interaction_loss_bwd": (c_int, [P, P, c_int64, P, c_int64, P, c_int64, c_float, c_float, c_float, P, P, P]),

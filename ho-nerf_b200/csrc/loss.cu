@@ -65,8 +65,9 @@ __device__ __forceinline__ float clip_p(float w) { return fminf(fmaxf(w, 1e-3f),
 __global__ void __launch_bounds__(LOSS_THREADS)
 render_loss_fwd_kernel(const float* __restrict__ color, const float* __restrict__ wsum,
                        const float* __restrict__ true_rgb, const float* __restrict__ true_mask,
-                       const float* __restrict__ grad_err, int64_t n, float color_div, float color_weight,
-                       float mask_weight, float igr_weight, float* __restrict__ ws, float* __restrict__ out) {
+                       const float* __restrict__ grad_err, int64_t n, float color_div,
+                       const float* __restrict__ color_div_dev, float color_weight, float mask_weight,
+                       float igr_weight, float* __restrict__ ws, float* __restrict__ out) {
     __shared__ float red[LOSS_SUMS * 8];
     float v[LOSS_SUMS] = {0.f, 0.f, 0.f, 0.f};   // sum |err|, sum mask, sum BCE, sum err^2
     for (int64_t i = (int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LOSS_THREADS) {
@@ -89,7 +90,7 @@ render_loss_fwd_kernel(const float* __restrict__ color, const float* __restrict_
         double tot[LOSS_SUMS];
         final_sums(ws, tot);
         float mask_sum = (float)tot[1] + 1e-5f;
-        float div = color_div > 0.f ? color_div : mask_sum;
+        float div = color_div_dev ? *color_div_dev : (color_div > 0.f ? color_div : mask_sum);
         float color_loss = (float)tot[0] / div;
         float mask_loss = (float)(tot[2] / (double)n);
         float eik = grad_err ? *grad_err : 0.f;
@@ -198,13 +199,14 @@ extern "C" {
 int64_t hn_loss_ws_floats(void) { return LOSS_MAX_BLOCKS * LOSS_SUMS + 4; }
 
 int hn_render_loss_fwd(const float* color, const float* weight_sum, const float* true_rgb, const float* true_mask,
-                       const float* gradient_error, int64_t n_rays, float color_div, float color_weight,
-                       float mask_weight, float igr_weight, float* ws, float* out, hn_stream_t stream) {
+                       const float* gradient_error, int64_t n_rays, float color_div, const float* color_div_dev,
+                       float color_weight, float mask_weight, float igr_weight, float* ws, float* out,
+                       hn_stream_t stream) {
     HN_REQUIRE(n_rays > 0, "hn_render_loss_fwd: n_rays must be positive (the reference's mean over 0 rays is NaN)");
     HN_REQUIRE(color && weight_sum && true_rgb && true_mask && ws && out, "hn_render_loss_fwd: null pointer");
     render_loss_fwd_kernel<<<loss_grid(n_rays), LOSS_THREADS, 0, (cudaStream_t)stream>>>(
-        color, weight_sum, true_rgb, true_mask, gradient_error, n_rays, color_div, color_weight, mask_weight,
-        igr_weight, ws, out);
+        color, weight_sum, true_rgb, true_mask, gradient_error, n_rays, color_div, color_div_dev, color_weight,
+        mask_weight, igr_weight, ws, out);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -872,10 +872,15 @@ class _RenderLossFn(torch.autograd.Function):
             raise _lib.HonerfError("render_loss: color %s, weight_sum %s, true_rgb %s, true_mask %s disagree"
                                    % (tuple(color.shape), tuple(wsum.shape), tuple(true_rgb.shape), tuple(true_mask.shape)))
         ge = _f32c(grad_err.detach()).reshape(1) if grad_err is not None else None
+        div_dev = None
+        if torch.is_tensor(color_div):          # device scalar: the divisor of the whole batch this shard belongs to
+            div_dev = _f32c(color_div.detach()).reshape(1)
+            _require_cuda(div_dev, "render_loss")
+            color_div = 0.0
         out = torch.empty(8, device=c.device)
-        check(lib.hn_render_loss_fwd(_ptr(c), _ptr(w), _ptr(t), _ptr(m), _ptr(ge), n, float(color_div), float(color_w),
-                                     float(mask_w), float(igr_w), _ptr(_loss_workspace(c.device)), _ptr(out),
-                                     _stream(c)), "hn_render_loss_fwd")
+        check(lib.hn_render_loss_fwd(_ptr(c), _ptr(w), _ptr(t), _ptr(m), _ptr(ge), n, float(color_div), _ptr(div_dev),
+                                     float(color_w), float(mask_w), float(igr_w), _ptr(_loss_workspace(c.device)),
+                                     _ptr(out), _stream(c)), "hn_render_loss_fwd")
         ctx.save_for_backward(c, w, t, m, out)
         ctx.coef = (float(color_w), float(mask_w), float(igr_w))
         ctx.shapes = (color.shape, wsum.shape, grad_err.shape if grad_err is not None else None)
@@ -902,7 +907,8 @@ def render_loss(color, weight_sum, true_rgb, true_mask, gradient_error=None, col
                 mask_weight=1.0, igr_weight=1.0):
     """Fused render loss: returns (total, stats) with stats = [color_loss, mask_loss, psnr] (not differentiable).
     color_div <= 0: the training normaliser mask_sum + 1e-5 (exp_runner.py:207,221); > 0: an explicit divisor
-    (fitting_single.py:254: n rays; fitting_video.py:288: F * P).  true_mask must already be 0/1."""
+    (fitting_single.py:254: n rays; fitting_video.py:288: F * P); a device scalar tensor: that value (a ray shard
+    passes its batch's mask_sum + 1e-5).  true_mask must already be 0/1."""
     return _RenderLossFn.apply(color, weight_sum, gradient_error, true_rgb, true_mask, color_div, color_weight,
                                mask_weight, igr_weight)
 

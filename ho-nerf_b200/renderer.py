@@ -98,7 +98,14 @@ class NeuSRenderer:
         rays_d = torch.matmul(Ro.unsqueeze(0), rays_d.unsqueeze(-1))[..., -1]
         return rays_o, rays_d
 
-    def render(self, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, Ro, To, index):
+    def render_sharded(self, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, Ro, To, index, per_shard):
+        """B200 extension: like render() with ray_streams > 1, but instead of merging the shards' outputs calls
+        per_shard(out, start, stop) on each shard's stream (out = that shard's render dict, rays [start, stop)) and
+        returns the list of its results.  A per-shard loss keeps every shard's forward AND backward on its own stream
+        with no join in the middle of the step (ops.render_loss takes the batch-wide divisor as a device scalar)."""
+        return self.render(rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, Ro, To, index, _per_shard=per_shard)
+
+    def render(self, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, Ro, To, index, _per_shard=None):
         """utils/renderer.py:190-258."""
         if self.model_type == 'obj':
             rays_o, rays_d = self.convert_obj_to_local(rays_o, rays_d, Ro, To)
@@ -108,10 +115,11 @@ class NeuSRenderer:
             sizes = None
         k = len(sizes) if sizes is not None else int(self.ray_streams)
         if k > 1 and self.model_type == 'obj' and rays_o.is_cuda and len(rays_o) >= 2 * k:
-            return self._render_on_streams(k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, sizes)
-        return self._render_local(rays_o, rays_d, near, far, bt_inv, T_pose_21, verts)
+            return self._render_on_streams(k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, sizes, _per_shard)
+        out = self._render_local(rays_o, rays_d, near, far, bt_inv, T_pose_21, verts)
+        return out if _per_shard is None else [_per_shard(out, 0, len(rays_o))]
 
-    def _render_on_streams(self, k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, sizes=None):
+    def _render_on_streams(self, k, rays_o, rays_d, near, far, bt_inv, T_pose_21, verts, sizes=None, per_shard=None):
         """`k` contiguous ray shards, each through _render_local on its own stream.  Fork/join on the caller's stream
         (CUDA-graph capturable); the weights are packed and their ONE autograd edge per net is created before the fork
         (ops.shared_param_tokens), so parameter gradients are unpacked once after the shards' backward passes join --
@@ -131,12 +139,21 @@ class NeuSRenderer:
                 shards = list(zip(torch.split(rays_o, list(sizes)), torch.split(rays_d, list(sizes))))
             else:
                 shards = list(zip(torch.chunk(rays_o, k), torch.chunk(rays_d, k)))
+            start = 0
             for s, (o, d) in zip(pool, shards):
                 s.wait_stream(cur)
                 with torch.cuda.stream(s):
-                    outs.append(self._render_local(o, d, near, far, bt_inv, T_pose_21, verts))
+                    out = self._render_local(o, d, near, far, bt_inv, T_pose_21, verts)
+                    outs.append(out if per_shard is None else per_shard(out, start, start + len(o)))
+                start += len(o)
         for s in pool[:len(shards)]:
             cur.wait_stream(s)
+        if per_shard is not None:
+            for res in outs:
+                for t in (res.values() if isinstance(res, dict) else res if isinstance(res, (tuple, list)) else (res,)):
+                    if torch.is_tensor(t):
+                        t.record_stream(cur)
+            return outs
         total = float(len(rays_o))
         merged = {}
         for key in outs[0]:

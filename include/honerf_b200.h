@@ -358,12 +358,15 @@ HN_API int64_t hn_loss_ws_floats(void);
  *   color_loss = sum |(color - true_rgb) * mask| / div,  mask_loss = mean BCE(clip(weight_sum, 1e-3, 1 - 1e-3), mask),
  *   total = color_weight * color_loss + mask_weight * mask_loss + igr_weight * (*gradient_error, may be NULL).
  * color, true_rgb [n,3]; weight_sum, true_mask [n] (mask already thresholded to 0/1).
+ * color_div_dev (may be NULL): a DEVICE scalar that overrides color_div -- a ray shard of a larger batch passes the
+ * whole batch's mask_sum + 1e-5 (and color/mask/igr weights scaled by its share of the rays), so that the shards'
+ * totals add up to the batch loss without a host round trip.
  * out: [0] total, [1] color_loss, [2] mask_loss, [3] psnr (exp_runner.py:222), [4] divisor, [5] mask_sum + 1e-5,
  * [6] eikonal term. */
 HN_API int hn_render_loss_fwd(const float* color, const float* weight_sum, const float* true_rgb,
                               const float* true_mask, const float* gradient_error, int64_t n_rays,
-                              float color_div, float color_weight, float mask_weight, float igr_weight,
-                              float* ws, float* out, hn_stream_t stream);
+                              float color_div, const float* color_div_dev, float color_weight,
+                              float mask_weight, float igr_weight, float* ws, float* out, hn_stream_t stream);
 /* g_loss: device scalar (NULL = 1).  fwd_out: the forward's `out`.  d_gradient_error may be NULL. */
 HN_API int hn_render_loss_bwd(const float* g_loss, const float* color, const float* weight_sum,
                               const float* true_rgb, const float* true_mask, const float* fwd_out,

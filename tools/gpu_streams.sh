@@ -1,8 +1,9 @@
 #!/bin/bash
-# A/B of the ray-shard layout of NeuSRenderer.ray_streams on the GPU box (main bench measurement only).
+# A/B of the per-shard loss (no join between forward and backward) on the GPU box + its parity test.
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
-for cfg in "--ray-streams 3" "--ray-shards 148,148,216" "--ray-shards 216,148,148" "--ray-shards 296,216" "--ray-shards 148,148,148,68" "--ray-shards 148,216,148" "--ray-shards 222,290" "--ray-streams 3 --rays 444" "--ray-streams 3 --rays 592"; do
+timeout 300 python -m pytest tests/test_gpu_product_default.py tests/test_gpu_8f.py -q -x 2>&1 | tail -15 | tee gpurun_out/tests_streams.log
+for cfg in "--shard-loss 0" "--shard-loss 1" "--shard-loss 1 --ray-streams 2" "--shard-loss 1 --ray-streams 4" "--shard-loss 1 --ray-streams 5" "--shard-loss 1 --ray-streams 6"; do
   timeout 200 python bench.py $cfg --no-cpu-baseline --no-roofline --large-rays 0 --fit-rays 0 --grid-res 0 > gpurun_out/bench_ab.json 2> gpurun_out/bench_ab.err
   python - "$cfg" <<'PY'
 import json, sys
@@ -10,6 +11,6 @@ try:
     d = json.load(open("gpurun_out/bench_ab.json"))
     print("%-34s %8.0f rays/s %.4f ms; e2e %8.0f" % (sys.argv[1], d["value"], d["ms_per_step"], d["e2e"]["value"]))
 except Exception as e:
-    print(sys.argv[1], "no json:", e)
+    print(sys.argv[1], "no json:", e); print(open("gpurun_out/bench_ab.err").read()[-1500:])
 PY
-done 2>&1 | tee gpurun_out/streams_ab.log
+done 2>&1 | tee gpurun_out/shard_loss_ab.log
