@@ -20,7 +20,7 @@ __global__ void ray_points_kernel(const float* __restrict__ o, const float* __re
 
 __global__ void mid_points_kernel(const float* __restrict__ o, const float* __restrict__ d,
                                   const float* __restrict__ z, int64_t total, int n, float sample_dist,
-                                  float* __restrict__ pts, float* __restrict__ dists) {
+                                  float* __restrict__ pts, float* __restrict__ dists, float* __restrict__ dirs) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     int64_t b = i / n;
@@ -30,7 +30,43 @@ __global__ void mid_points_kernel(const float* __restrict__ o, const float* __re
     float mid = __fadd_rn(zi, __fmul_rn(dist, 0.5f));
     dists[i] = dist;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) pts[i * 3 + c] = __fadd_rn(o[b * 3 + c], __fmul_rn(d[b * 3 + c], mid));
+    for (int c = 0; c < 3; ++c) {
+        float dc = d[b * 3 + c];
+        pts[i * 3 + c] = __fadd_rn(o[b * 3 + c], __fmul_rn(dc, mid));
+        if (dirs) dirs[i * 3 + c] = dc;          // rays_d[:, None, :].expand(B, n, 3) (utils/renderer.py:127)
+    }
+}
+
+// Backward of pts = o + d * mid and dirs = expand(d): one warp per ray walks the ray's contiguous [n, 3] cotangent rows
+// (coalesced), d_o = sum_i g_i, d_d = sum_i (g_i * mid_i + gdirs_i).  Replaces two slow strided torch reductions, a
+// multiply and the expand's reduction per render.
+__global__ void __launch_bounds__(256)
+mid_points_bwd_kernel(const float* __restrict__ d_pts, const float* __restrict__ d_dirs, const float* __restrict__ z,
+                      const float* __restrict__ dists, int64_t n_rays, int n, float* __restrict__ d_o,
+                      float* __restrict__ d_d) {
+    int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (b >= n_rays) return;
+    const float* g = d_pts + b * n * 3;
+    const float* gd = d_dirs ? d_dirs + b * n * 3 : nullptr;
+    float ao[3] = {0.f, 0.f, 0.f}, ad[3] = {0.f, 0.f, 0.f};
+    for (int e = lane; e < n * 3; e += 32) {
+        int i = e / 3, c = e - i * 3;
+        float gv = g[e];
+        float mid = z[b * n + i] + dists[b * n + i] * 0.5f;
+        float dv = gv * mid + (gd ? gd[e] : 0.f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            ao[k] += (c == k) ? gv : 0.f;
+            ad[k] += (c == k) ? dv : 0.f;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { ao[k] = warp_sum(ao[k]); ad[k] = warp_sum(ad[k]); }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { d_o[b * 3 + k] = ao[k]; d_d[b * 3 + k] = ad[k]; }
+    }
 }
 
 // searchsorted(cdf, u, right=True): first index with cdf[idx] > u  (in [0, m])
@@ -208,13 +244,25 @@ int hn_ray_points(const float* rays_o, const float* rays_d, const float* z, int6
 }
 
 int hn_mid_points(const float* rays_o, const float* rays_d, const float* z, int64_t n_rays, int n,
-                  float sample_dist, float* pts, float* dists, hn_stream_t stream) {
+                  float sample_dist, float* pts, float* dists, float* dirs, hn_stream_t stream) {
     HN_REQUIRE(n_rays >= 0 && n > 0, "hn_mid_points: bad sizes");
     if (n_rays == 0) return HN_OK;
     HN_REQUIRE(rays_o && rays_d && z && pts && dists, "hn_mid_points: null pointer");
     int64_t total = n_rays * n;
     mid_points_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z, total, n,
-                                                                                       sample_dist, pts, dists);
+                                                                                       sample_dist, pts, dists, dirs);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hn_mid_points_bwd(const float* d_pts, const float* d_dirs, const float* z, const float* dists, int64_t n_rays,
+                      int n, float* d_rays_o, float* d_rays_d, hn_stream_t stream) {
+    HN_REQUIRE(n_rays >= 0 && n > 0, "hn_mid_points_bwd: bad sizes");
+    if (n_rays == 0) return HN_OK;
+    HN_REQUIRE(d_pts && z && dists && d_rays_o && d_rays_d, "hn_mid_points_bwd: null pointer");
+    mid_points_bwd_kernel<<<(unsigned)ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_pts, d_dirs, z, dists, n_rays, n, d_rays_o, d_rays_d);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -623,33 +623,44 @@ def sort_rows(x, return_index=False):
 
 
 class _MidPointsFn(torch.autograd.Function):
-    """pts = o + d * (z + dists/2) (utils/renderer.py:119-124); z is a constant (no_grad)."""
+    """pts = o + d * (z + dists/2) and dirs = expand(d) (utils/renderer.py:119-127); z is a constant (no_grad)."""
 
     @staticmethod
-    def forward(ctx, rays_o, rays_d, z, sample_dist):
+    def forward(ctx, rays_o, rays_d, z, sample_dist, with_dirs):
         o, d, zc = _f32c(rays_o.detach()), _f32c(rays_d.detach()), _f32c(z.detach())
         _require_cuda(zc, "mid_points")
         B, n = zc.shape
         pts = torch.empty(B * n, 3, device=zc.device, dtype=torch.float32)
         dists = torch.empty(B, n, device=zc.device, dtype=torch.float32)
+        dirs = torch.empty(B * n, 3, device=zc.device, dtype=torch.float32) if with_dirs else None
         check(lib.hn_mid_points(_ptr(o), _ptr(d), _ptr(zc), B, n, float(sample_dist), _ptr(pts), _ptr(dists),
-                                _stream(zc)), "hn_mid_points")
-        ctx.save_for_backward(zc, dists, d)
+                                _ptr(dirs), _stream(zc)), "hn_mid_points")
+        ctx.save_for_backward(zc, dists)
         ctx.mark_non_differentiable(dists)
+        if with_dirs:
+            return pts, dists, dirs
         return pts, dists
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, d_pts, _):
-        zc, dists, d = ctx.saved_tensors
+    def backward(ctx, d_pts, _d_dists, d_dirs=None):
+        zc, dists = ctx.saved_tensors
         B, n = zc.shape
-        g = d_pts.reshape(B, n, 3)
-        mid = zc + dists * 0.5
-        return g.sum(1), (g * mid[..., None]).sum(1), None, None
+        if d_pts is None and d_dirs is None:
+            return None, None, None, None, None
+        g = _f32c(d_pts) if d_pts is not None else torch.zeros(B * n, 3, device=zc.device)
+        gd = _f32c(d_dirs) if d_dirs is not None else None
+        d_o = torch.empty(B, 3, device=zc.device, dtype=torch.float32)
+        d_d = torch.empty(B, 3, device=zc.device, dtype=torch.float32)
+        check(lib.hn_mid_points_bwd(_ptr(g), _ptr(gd), _ptr(zc), _ptr(dists), B, n, _ptr(d_o), _ptr(d_d), _stream(zc)),
+              "hn_mid_points_bwd")
+        return d_o, d_d, None, None, None
 
 
-def mid_points(rays_o, rays_d, z, sample_dist):
-    return _MidPointsFn.apply(rays_o, rays_d, z, sample_dist)
+def mid_points(rays_o, rays_d, z, sample_dist, with_dirs=False):
+    """-> pts [B*n,3], dists [B,n] (and, with_dirs, the expanded view directions dirs [B*n,3], whose cotangent is
+    folded into d_rays_d by the same backward kernel)."""
+    return _MidPointsFn.apply(rays_o, rays_d, z, sample_dist, bool(with_dirs))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -70,8 +70,7 @@ class NeuSRenderer:
                     deviation_network, color_network):
         """utils/renderer.py:107-177."""
         batch_size, n_samples = z_vals.shape
-        pts, dists = ops.mid_points(rays_o, rays_d, z_vals, sample_dist)
-        dirs = rays_d[:, None, :].expand(batch_size, n_samples, 3).reshape(-1, 3)
+        pts, dists, dirs = ops.mid_points(rays_o, rays_d, z_vals, sample_dist, with_dirs=True)
         self.N = pts.shape[0]
         if self.model_type == 'obj':
             sdf, feature_vector, gradients = sdf_network.fused(pts)
@@ -313,8 +312,7 @@ class _FittingBase:
         lead = z_vals.shape[:-1]
         n = z_vals.shape[-1]
         ro, rd = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
-        pts, dists = ops.mid_points(ro, rd, z_vals.reshape(-1, n), sample_dist)
-        dirs = rd[:, None, :].expand(rd.shape[0], n, 3).reshape(-1, 3)
+        pts, dists, dirs = ops.mid_points(ro, rd, z_vals.reshape(-1, n), sample_dist, with_dirs=True)
         if ctype == 'obj':
             sdf, feature_vector, gradients = self.sdf_network_obj.fused(pts)
             sampled_color = self.color_network_obj(pts, dirs, feature_vector, gradients, 0)

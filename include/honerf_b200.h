@@ -253,10 +253,15 @@ HN_API int hn_color_hand_bwd(const hn_mlp_t* mlp, int64_t n_pts, float* stash, c
  * with eager PyTorch (utils/renderer.py:91,216). */
 HN_API int hn_ray_points(const float* rays_o, const float* rays_d, const float* z, int64_t n_rays,
                          int n, float* pts, hn_stream_t stream);
-/* dists / mid-point samples of render_core (utils/renderer.py:119-124):
- * dists[b,i] = z[b,i+1]-z[b,i] (last = sample_dist), mid = z + dists*0.5, pts = o + d*mid. */
-HN_API int hn_mid_points(const float* rays_o, const float* rays_d, const float* z, int64_t n_rays,
-                         int n, float sample_dist, float* pts, float* dists, hn_stream_t stream);
+/* dists / mid-point samples of render_core (utils/renderer.py:119-127):
+ * dists[b,i] = z[b,i+1]-z[b,i] (last = sample_dist), mid = z + dists*0.5, pts = o + d*mid; when `dirs` is not NULL
+ * also dirs[b,i,:] = d[b,:] (the expanded view directions the colour field reads). */
+HN_API int hn_mid_points(const float* rays_o, const float* rays_d, const float* z, int64_t n_rays, int n,
+                         float sample_dist, float* pts, float* dists, float* dirs, hn_stream_t stream);
+/* Its backward: d_rays_o[b] = sum_i d_pts[b,i], d_rays_d[b] = sum_i (d_pts[b,i] * mid[b,i] + d_dirs[b,i])
+ * (d_dirs may be NULL); one warp per ray. */
+HN_API int hn_mid_points_bwd(const float* d_pts, const float* d_dirs, const float* z, const float* dists,
+                             int64_t n_rays, int n, float* d_rays_o, float* d_rays_d, hn_stream_t stream);
 /* NeuSRenderer.up_sample (utils/renderer.py:60-86): one warp per ray; section weights, fp64
  * running cdf (matching torch CPU cumsum/cumprod), inverse-CDF search. */
 HN_API int hn_up_sample(const float* z, const float* sdf, const float* u, int64_t n_rays, int m, int n_importance,

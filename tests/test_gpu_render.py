@@ -32,6 +32,31 @@ def test_mid_points_bit_exact():
     assert torch.equal(gd.cpu(), dists) and torch.equal(gp.cpu(), pts)
 
 
+def test_mid_points_dirs_and_backward():
+    """with_dirs: dirs == rays_d[:, None, :].expand(...) bit for bit; hn_mid_points_bwd vs fp64 autograd of
+    pts = o + d * mid, dirs = expand(d): 1e-6 relative (one warp per ray, fp32 sums over 3 n values)."""
+    from honerf_b200 import ops
+    gen = torch.Generator().manual_seed(12)
+    for B, n in ((37, 128), (5, 192), (3, 1)):
+        o, d = torch.randn(B, 3, generator=gen), torch.randn(B, 3, generator=gen)
+        z = torch.sort(torch.rand(B, n, generator=gen) + 0.4, -1)[0]
+        w_p, w_d = torch.randn(B * n, 3, generator=gen), torch.randn(B * n, 3, generator=gen)
+        og, dg = o.to(DEV).requires_grad_(True), d.to(DEV).requires_grad_(True)
+        pts, dists, dirs = ops.mid_points(og, dg, z.to(DEV), 1.1 / 64, with_dirs=True)
+        assert torch.equal(dirs.cpu(), d[:, None, :].expand(B, n, 3).reshape(-1, 3))
+        g_o, g_d = torch.autograd.grad((pts * w_p.to(DEV)).sum() + (dirs * w_d.to(DEV)).sum(), [og, dg])
+        o64, d64 = o.double().requires_grad_(True), d.double().requires_grad_(True)
+        dist64, pts64, _ = O.mid_points(o64, d64, z.double(), 1.1 / 64)
+        dirs64 = d64[:, None, :].expand(B, n, 3).reshape(-1, 3)
+        r_o, r_d = torch.autograd.grad((pts64 * w_p.double()).sum() + (dirs64 * w_d.double()).sum(), [o64, d64])
+        assert rel_err(g_o, r_o) < 1e-6 and rel_err(g_d, r_d) < 1e-6
+        # without the dirs cotangent (pts only)
+        pts2, _ = ops.mid_points(og, dg, z.to(DEV), 1.1 / 64)
+        g_o2, g_d2 = torch.autograd.grad((pts2 * w_p.to(DEV)).sum(), [og, dg])
+        r_o2, r_d2 = torch.autograd.grad((O.mid_points(o64, d64, z.double(), 1.1 / 64)[1] * w_p.double()).sum(), [o64, d64])
+        assert rel_err(g_o2, r_o2) < 1e-6 and rel_err(g_d2, r_d2) < 1e-6
+
+
 def test_inverse_cdf_exact_indices_and_positions():
     """Given the oracle's cdf: searchsorted indices and sample positions are bit-exact."""
     from honerf_b200 import ops
