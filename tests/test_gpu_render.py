@@ -37,7 +37,7 @@ def test_mid_points_dirs_and_backward():
     pts = o + d * mid, dirs = expand(d): 1e-6 relative (one warp per ray, fp32 sums over 3 n values)."""
     from honerf_b200 import ops
     gen = torch.Generator().manual_seed(12)
-    for B, n in ((37, 128), (5, 192), (3, 1)):
+    for B, n in ((37, 128), (5, 192), (3, 2)):
         o, d = torch.randn(B, 3, generator=gen), torch.randn(B, 3, generator=gen)
         z = torch.sort(torch.rand(B, n, generator=gen) + 0.4, -1)[0]
         w_p, w_d = torch.randn(B * n, 3, generator=gen), torch.randn(B * n, 3, generator=gen)
