@@ -78,7 +78,7 @@ class NeuSRenderer:
         else:
             sdf, feature_vector, gradients, xyz_feature = sdf_network.fused(pts, bt_inv, T_pose_21)
             sampled_color = color_network(dirs, xyz_feature, feature_vector, None, gradients, self.index)
-        color, weights, cdf, _, _, eik = ops.neus_composite(
+        color, weights, cdf, wsum, wmax, eik = ops.neus_composite(
             sdf, gradients, sampled_color, dists, rays_d, deviation_network.variance, seed_with_c0=True)
         inv_s = torch.exp(deviation_network.variance * 10.0).clip(1e-6, 1e6)
         return {
@@ -87,6 +87,10 @@ class NeuSRenderer:
             'weights': weights,
             'cdf': cdf,
             'gradient_error': eik.sum() / float(batch_size * n_samples),
+            # per-ray sum / max of the weights, accumulated by the compositor kernel while it holds them (render()
+            # returns these instead of launching two more reductions over `weights`)
+            'weight_sum': wsum,
+            'weight_max': wmax,
         }
 
     def convert_obj_to_local(self, rays_o, rays_d, Ro, To):
@@ -192,14 +196,15 @@ class NeuSRenderer:
 
         ret_fine = self.render_core(rays_o, rays_d, bt_inv, T_pose_21, verts, z_vals, sample_dist,
                                     self.sdf_network, self.deviation_network, self.color_network)
-        weights = ret_fine['weights']
-        s_val = ret_fine['s_val'].reshape(batch_size, n_samples).mean(dim=-1, keepdim=True)
+        # mean over a ray's samples of the per-sample 1/inv_s, which is one scalar broadcast to every sample
+        # (utils/renderer.py:173,247): the first column IS that mean, no reduction needed
+        s_val = ret_fine['s_val'].reshape(batch_size, n_samples)[:, :1]
         return {
             'color_fine': ret_fine['color'],
             's_val': s_val,
             'cdf_fine': ret_fine['cdf'],
-            'weight_sum': weights.sum(dim=-1, keepdim=True),
-            'weight_max': torch.max(weights, dim=-1, keepdim=True)[0],
+            'weight_sum': ret_fine['weight_sum'],
+            'weight_max': ret_fine['weight_max'],
             'gradient_error': ret_fine['gradient_error'],
         }
 
