@@ -60,3 +60,11 @@ def unflatten_gradients(params, flat, world_size, average=True):
         p.grad.copy_(src / world_size if average else src)
         off += n
     return off
+
+
+def shard_views(n_views, rank, world):
+    """Fitting (fitting_single.py:200-291 loops over the views of a frame): contiguous view shards per rank.  The
+    reference steps its optimiser once per view; with views sharded the ranks render their views, SUM the pose-parameter
+    gradients (allreduce_gradients(pose_params, average=False): 45 F + 9 floats) and take one identical step --
+    parity is per render call, not per optimisation trajectory."""
+    return shard_rays(n_views, rank, world)

@@ -70,3 +70,33 @@ def test_split_flatten_allreduce_unflatten_gloo_world2():
         n, g0, g1, g2 = out[r]
         assert n == 9 and g1 is None
         assert torch.allclose(g0, torch.full((4, 2), 1.5)) and torch.allclose(g2, torch.tensor([15.0]))
+
+
+def _fit_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from honerf_b200 import dist as hdist
+    n_views = 8
+    lo, hi = hdist.shard_views(n_views, rank, world)
+    # pose parameters of fitting: 45 hand-pose values per frame + object rotation / translation; every view adds a
+    # known gradient, so the SUM over ranks must equal the sum over all views whatever the sharding
+    pose = torch.nn.Parameter(torch.zeros(45))
+    obj = torch.nn.Parameter(torch.zeros(9))
+    pose.grad = sum(torch.full((45,), float(v + 1)) for v in range(lo, hi))
+    obj.grad = sum(torch.arange(9.0) * (v + 1) for v in range(lo, hi))
+    n = hdist.allreduce_gradients([pose, obj], world, average=False)
+    out[rank] = (n, (lo, hi), pose.grad.clone(), obj.grad.clone())
+    dist.destroy_process_group()
+
+
+def test_view_sharded_pose_gradient_sum_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fit_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    total = sum(range(1, 9))
+    assert [out[r][1] for r in range(world)] == [(0, 4), (4, 8)]
+    for r in range(world):
+        n, _, gp, go = out[r]
+        assert n == 54
+        assert torch.equal(gp, torch.full((45,), float(total))) and torch.equal(go, torch.arange(9.0) * total)
