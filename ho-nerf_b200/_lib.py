@@ -106,6 +106,8 @@ PROTOTYPES = {
     "hn_ray_points": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "hn_mid_points": (c_int, [P, P, P, c_int64, c_int, c_float, P, P, P, P]),
     "hn_mid_points_bwd": (c_int, [P, P, P, P, c_int64, c_int, P, P, P]),
+    "hn_rays_to_local": (c_int, [P, P, P, P, c_int64, P, P, P]),
+    "hn_rays_to_local_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, P, P, P, P]),
     "hn_up_sample": (c_int, [P, P, P, c_int64, c_int, c_int, c_float, P, P]),
     "hn_inverse_cdf": (c_int, [P, P, P, c_int64, c_int, c_int, P, P, P, P]),
     "hn_merge_sorted": (c_int, [P, c_int, P, c_int, c_int64, P, P, P, P, c_int64, P, P]),

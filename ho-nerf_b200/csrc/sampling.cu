@@ -69,6 +69,77 @@ mid_points_bwd_kernel(const float* __restrict__ d_pts, const float* __restrict__
     }
 }
 
+// Rays into the object frame (utils/renderer.py:180-188): o' = Ro (o - To), d' = Ro d.  Ro [3,3] row-major, To [3]:
+// device memory (they are trained: se3_refine / the fitting pose), so nothing is read on the host.
+__global__ void rays_to_local_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                     const float* __restrict__ Ro, const float* __restrict__ To, int64_t n_rays,
+                                     float* __restrict__ lo, float* __restrict__ ld) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_rays) return;
+    float R[9], T[3], ov[3], dv[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = Ro[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { T[k] = To[k]; ov[k] = __fsub_rn(o[b * 3 + k], T[k]); dv[k] = d[b * 3 + k]; }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        lo[b * 3 + i] = R[i * 3] * ov[0] + R[i * 3 + 1] * ov[1] + R[i * 3 + 2] * ov[2];
+        ld[b * 3 + i] = R[i * 3] * dv[0] + R[i * 3 + 1] * dv[1] + R[i * 3 + 2] * dv[2];
+    }
+}
+
+// Its backward in ONE launch (one CTA, fixed summation order -> deterministic):
+//   d_Ro[i,j] = sum_b g_lo[b,i] (o[b,j] - To[j]) + g_ld[b,i] d[b,j],   d_To[j] = - sum_b sum_i Ro[i,j] g_lo[b,i],
+//   d_o[b] = Ro^T g_lo[b],  d_d[b] = Ro^T g_ld[b]  (optional).
+__global__ void __launch_bounds__(256)
+rays_to_local_bwd_kernel(const float* __restrict__ g_lo, const float* __restrict__ g_ld, const float* __restrict__ o,
+                         const float* __restrict__ d, const float* __restrict__ Ro, const float* __restrict__ To,
+                         int64_t n_rays, float* __restrict__ d_Ro, float* __restrict__ d_To, float* __restrict__ d_o,
+                         float* __restrict__ d_d) {
+    __shared__ float red[12][8];
+    float R[9], T[3];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = Ro[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) T[k] = To[k];
+    float acc[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc[k] = 0.f;
+    for (int64_t b = threadIdx.x; b < n_rays; b += blockDim.x) {
+        float go[3] = {0.f, 0.f, 0.f}, gd[3] = {0.f, 0.f, 0.f}, ov[3], dv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (g_lo) go[k] = g_lo[b * 3 + k];
+            if (g_ld) gd[k] = g_ld[b * 3 + k];
+            ov[k] = __fsub_rn(o[b * 3 + k], T[k]);
+            dv[k] = d[b * 3 + k];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[i * 3 + j] += go[i] * ov[j] + gd[i] * dv[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            float to = R[j] * go[0] + R[3 + j] * go[1] + R[6 + j] * go[2];        // (Ro^T g_lo)[j]
+            acc[9 + j] -= to;
+            if (d_o) d_o[b * 3 + j] = to;
+            if (d_d) d_d[b * 3 + j] = R[j] * gd[0] + R[3 + j] * gd[1] + R[6 + j] * gd[2];
+        }
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+        float v = warp_sum(acc[k]);
+        if (lane == 0) red[k][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[threadIdx.x][w];
+        if (threadIdx.x < 9) d_Ro[threadIdx.x] = v; else d_To[threadIdx.x - 9] = v;
+    }
+}
+
 // searchsorted(cdf, u, right=True): first index with cdf[idx] > u  (in [0, m])
 __device__ __forceinline__ int upper_bound(const float* cdf, int m, float u) {
     int lo = 0, hi = m;
@@ -263,6 +334,30 @@ int hn_mid_points_bwd(const float* d_pts, const float* d_dirs, const float* z, c
     HN_REQUIRE(d_pts && z && dists && d_rays_o && d_rays_d, "hn_mid_points_bwd: null pointer");
     mid_points_bwd_kernel<<<(unsigned)ceil_div(n_rays * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         d_pts, d_dirs, z, dists, n_rays, n, d_rays_o, d_rays_d);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hn_rays_to_local(const float* rays_o, const float* rays_d, const float* Ro, const float* To, int64_t n_rays,
+                     float* local_o, float* local_d, hn_stream_t stream) {
+    HN_REQUIRE(n_rays >= 0, "hn_rays_to_local: bad sizes");
+    if (n_rays == 0) return HN_OK;
+    HN_REQUIRE(rays_o && rays_d && Ro && To && local_o && local_d, "hn_rays_to_local: null pointer");
+    rays_to_local_kernel<<<(unsigned)ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, Ro, To, n_rays,
+                                                                                             local_o, local_d);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hn_rays_to_local_bwd(const float* d_local_o, const float* d_local_d, const float* rays_o, const float* rays_d,
+                         const float* Ro, const float* To, int64_t n_rays, float* d_Ro, float* d_To, float* d_rays_o,
+                         float* d_rays_d, hn_stream_t stream) {
+    HN_REQUIRE(n_rays >= 0, "hn_rays_to_local_bwd: bad sizes");
+    HN_REQUIRE(rays_o && rays_d && Ro && To && d_Ro && d_To, "hn_rays_to_local_bwd: null pointer");
+    rays_to_local_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_local_o, d_local_d, rays_o, rays_d, Ro, To, n_rays,
+                                                                  d_Ro, d_To, d_rays_o, d_rays_d);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -557,6 +557,44 @@ def ray_points(rays_o, rays_d, z):
     return pts
 
 
+class _RaysToLocalFn(torch.autograd.Function):
+    """o' = Ro (o - To), d' = Ro d (utils/renderer.py:180-188) with gradients to Ro, To (and the rays if needed)."""
+
+    @staticmethod
+    def forward(ctx, rays_o, rays_d, Ro, To):
+        o, d = _f32c(rays_o.detach()), _f32c(rays_d.detach())
+        R, T = _f32c(Ro.detach()), _f32c(To.detach())
+        _require_cuda(o, "rays_to_local")
+        _require_cuda(R, "rays_to_local")
+        B = o.shape[0]
+        lo, ld = torch.empty(B, 3, device=o.device), torch.empty(B, 3, device=o.device)
+        check(lib.hn_rays_to_local(_ptr(o), _ptr(d), _ptr(R), _ptr(T), B, _ptr(lo), _ptr(ld), _stream(o)),
+              "hn_rays_to_local")
+        ctx.save_for_backward(o, d, R, T)
+        ctx.need_rays = (rays_o.requires_grad, rays_d.requires_grad)
+        ctx.shapes = (Ro.shape, To.shape)
+        return lo, ld
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_lo, g_ld):
+        o, d, R, T = ctx.saved_tensors
+        B = o.shape[0]
+        g_lo = _f32c(g_lo) if g_lo is not None else None
+        g_ld = _f32c(g_ld) if g_ld is not None else None
+        d_R, d_T = torch.empty(9, device=o.device), torch.empty(3, device=o.device)
+        d_o = torch.empty(B, 3, device=o.device) if ctx.need_rays[0] else None
+        d_d = torch.empty(B, 3, device=o.device) if ctx.need_rays[1] else None
+        check(lib.hn_rays_to_local_bwd(_ptr(g_lo), _ptr(g_ld), _ptr(o), _ptr(d), _ptr(R), _ptr(T), B, _ptr(d_R), _ptr(d_T),
+                                       _ptr(d_o), _ptr(d_d), _stream(o)), "hn_rays_to_local_bwd")
+        return d_o, d_d, d_R.reshape(ctx.shapes[0]), d_T.reshape(ctx.shapes[1])
+
+
+def rays_to_local(rays_o, rays_d, Ro, To):
+    """[B,3], [B,3], Ro [3,3], To [3] -> rays in the object frame; one launch forward, one backward."""
+    return _RaysToLocalFn.apply(rays_o, rays_d, Ro, To)
+
+
 _u_cache = {}
 
 

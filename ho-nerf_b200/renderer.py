@@ -94,8 +94,10 @@ class NeuSRenderer:
         }
 
     def convert_obj_to_local(self, rays_o, rays_d, Ro, To):
-        """utils/renderer.py:180-188: o' = Ro (o - To), d' = Ro d (tiny; stays in torch so that
-        autograd carries gradients to the caller's pose parameters)."""
+        """utils/renderer.py:180-188: o' = Ro (o - To), d' = Ro d; gradients reach the caller's pose parameters
+        (hn_rays_to_local + its one-launch backward; plain torch for any other shapes)."""
+        if rays_o.is_cuda and rays_o.dim() == 2 and tuple(Ro.shape) == (3, 3) and To.numel() == 3:
+            return ops.rays_to_local(rays_o, rays_d, Ro, To)
         rays_o = rays_o - To.unsqueeze(0)
         rays_o = torch.matmul(Ro.unsqueeze(0), rays_o.unsqueeze(-1))[..., -1]
         rays_d = torch.matmul(Ro.unsqueeze(0), rays_d.unsqueeze(-1))[..., -1]
@@ -431,6 +433,8 @@ class NeuSRenderer_fitting(_FittingBase):
 
     def convert_obj_to_local(self, rays_o, rays_d, Ro, To):
         """utils/renderer.py:424-432."""
+        if rays_o.is_cuda and rays_o.dim() == 2 and tuple(Ro.shape) == (3, 3) and To.numel() == 3:
+            return ops.rays_to_local(rays_o, rays_d, Ro, To)
         rays_o = rays_o - To.unsqueeze(0)
         rays_o = torch.matmul(Ro.unsqueeze(0), rays_o.unsqueeze(-1))[..., -1]
         rays_d = torch.matmul(Ro.unsqueeze(0), rays_d.unsqueeze(-1))[..., -1]

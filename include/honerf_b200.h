@@ -262,6 +262,15 @@ HN_API int hn_mid_points(const float* rays_o, const float* rays_d, const float* 
  * (d_dirs may be NULL); one warp per ray. */
 HN_API int hn_mid_points_bwd(const float* d_pts, const float* d_dirs, const float* z, const float* dists,
                              int64_t n_rays, int n, float* d_rays_o, float* d_rays_d, hn_stream_t stream);
+/* Rays into the object frame (convert_obj_to_local, utils/renderer.py:180-188): o' = Ro (o - To), d' = Ro d with
+ * Ro [3,3] row-major and To [3] in DEVICE memory (trained pose parameters). */
+HN_API int hn_rays_to_local(const float* rays_o, const float* rays_d, const float* Ro, const float* To,
+                            int64_t n_rays, float* local_o, float* local_d, hn_stream_t stream);
+/* Backward in one launch (one CTA, deterministic): d_Ro [9], d_To [3] overwritten; d_local_o / d_local_d may be NULL
+ * (= zero); d_rays_o / d_rays_d [n_rays,3] optional (NULL when the rays are inputs). */
+HN_API int hn_rays_to_local_bwd(const float* d_local_o, const float* d_local_d, const float* rays_o,
+                                const float* rays_d, const float* Ro, const float* To, int64_t n_rays,
+                                float* d_Ro, float* d_To, float* d_rays_o, float* d_rays_d, hn_stream_t stream);
 /* NeuSRenderer.up_sample (utils/renderer.py:60-86): one warp per ray; section weights, fp64
  * running cdf (matching torch CPU cumsum/cumprod), inverse-CDF search. */
 HN_API int hn_up_sample(const float* z, const float* sdf, const float* u, int64_t n_rays, int m, int n_importance,

@@ -57,6 +57,33 @@ def test_mid_points_dirs_and_backward():
         assert rel_err(g_o2, r_o2) < 1e-6 and rel_err(g_d2, r_d2) < 1e-6
 
 
+def test_rays_to_local_and_backward():
+    """hn_rays_to_local vs the reference's torch lines (utils/renderer.py:180-188) in fp32: 1e-6 absolute; its
+    one-launch backward (d_Ro, d_To, and the rays' own cotangents) vs fp64 autograd of the oracle: 1e-5 relative
+    (fp32 sums over the rays); n = 1 and a non-multiple of the block size included."""
+    from honerf_b200 import ops
+    gen = torch.Generator().manual_seed(21)
+    for B in (1, 333, 2048):
+        o, d = torch.randn(B, 3, generator=gen), torch.randn(B, 3, generator=gen)
+        Ro = synth.random_rotation(gen) + 0.01 * torch.randn(3, 3, generator=gen)
+        To = 0.1 * torch.randn(3, generator=gen)
+        w_o, w_d = torch.randn(B, 3, generator=gen), torch.randn(B, 3, generator=gen)
+        ref_o, ref_d = O.rays_to_local(o, d, Ro, To)
+        leaves = [t.to(DEV).requires_grad_(True) for t in (o, d, Ro, To)]
+        lo, ld = ops.rays_to_local(*leaves)
+        assert max_abs(lo, ref_o) < 1e-6 and max_abs(ld, ref_d) < 1e-6
+        g = torch.autograd.grad((lo * w_o.to(DEV)).sum() + (ld * w_d.to(DEV)).sum(), leaves)
+        l64 = [t.double().requires_grad_(True) for t in (o, d, Ro, To)]
+        r_o, r_d = O.rays_to_local(*l64)
+        r = torch.autograd.grad((r_o * w_o.double()).sum() + (r_d * w_d.double()).sum(), l64)
+        for a, b in zip(g, r):
+            assert a.shape == b.shape and rel_err(a, b) < 1e-5
+        # rays as plain inputs (training): only the pose gets gradients
+        lo2, ld2 = ops.rays_to_local(o.to(DEV), d.to(DEV), leaves[2], leaves[3])
+        g2 = torch.autograd.grad((lo2 * w_o.to(DEV)).sum() + (ld2 * w_d.to(DEV)).sum(), leaves[2:])
+        assert rel_err(g2[0], r[2]) < 1e-5 and rel_err(g2[1], r[3]) < 1e-5
+
+
 def test_inverse_cdf_exact_indices_and_positions():
     """Given the oracle's cdf: searchsorted indices and sample positions are bit-exact."""
     from honerf_b200 import ops
