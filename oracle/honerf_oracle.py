@@ -13,7 +13,11 @@ committed under ``tests/golden/``; and, when the reference tree is present, the 
 live against the reference modules.
 
 Parity status: PINNED (golden vectors generated from the reference's own code; the reference ships
-no tests or fixtures of its own -- SURVEY.md section 4).
+no tests or fixtures of its own -- SURVEY.md section 4).  The SURVEY 8f rows (losses, contact stability, ray
+bundles) are pinned the same way by ``oracle/make_golden_8f.py`` / ``tests/test_oracle_8f.py``, with ONE exception that
+is PARITY UNPINNED: ``unproject_ndc`` restates the NDC camera model of pytorch3d, an un-vendored and un-pinned
+dependency of the reference that is not importable here (the ray-bundle construction around it is the reference's own
+function and is pinned).
 """
 from __future__ import annotations
 
