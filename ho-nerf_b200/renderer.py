@@ -43,6 +43,9 @@ class NeuSRenderer:
         self.ray_streams = 1
         self.ray_shard_sizes = None         # optional explicit shard sizes (sum = batch); default: equal shards
         self._stream_pool = {}
+        # test hook: when a list, every _render_local call appends the z_vals it rendered with (shard order), so a
+        # parity test can evaluate the oracle on exactly the product's samples ("when the same z_vals are fed")
+        self.keep_z_vals = None
 
     # -- field access ----------------------------------------------------------------------------
     def _sdf_only(self, pts, bt_inv, T_pose_21):
@@ -196,6 +199,8 @@ class NeuSRenderer:
                                                   last=(i + 1 == self.up_sample_steps))
             n_samples = self.n_samples + self.n_importance
 
+        if self.keep_z_vals is not None:
+            self.keep_z_vals.append(z_vals)
         ret_fine = self.render_core(rays_o, rays_d, bt_inv, T_pose_21, verts, z_vals, sample_dist,
                                     self.sdf_network, self.deviation_network, self.color_network)
         # mean over a ray's samples of the per-sample 1/inv_s, which is one scalar broadcast to every sample

@@ -1,0 +1,181 @@
+"""Parity AT THE BENCHMARKED SHAPE and under the product's default precision: what bench.py times is compared with the
+oracle, not only 24-ray goldens.
+
+* 512 rays x (64+64) samples = 65 536 points = 512 tiles = 3.46 waves of the persistent chain kernels, rendered as
+  3 ray shards on concurrent streams with the fused per-shard loss, captured in a CUDA graph and REPLAYED -- exactly
+  bench.py's step -- against oracle_core_fp64 evaluated on the z_vals the product sampled ("when the same z_vals are
+  fed", utils/renderer.py:107-177): colour / weight sums 1e-3 abs, loss 1e-3 relative, every gradient 1e-2 (rel. L2).
+* the fused SDF operator alone at n = 65 536 and n = 148 * 128 + 1 (every persistent CTA walks over several tiles, ragged
+  last tile) against fp64 autograd.
+* end to end (the product samples, the oracle samples: utils/renderer.py:190-258) on rays whose importance samples did
+  not cross a cdf knot; the filtered fraction is printed and bounded.
+"""
+import pytest
+import torch
+
+import analytic as A
+import honerf_oracle as O
+import synth
+from golden_util import max_abs, rel_err, rel_l2
+from gpu_util import DEV, obj_modules, oracle_core_fp64
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(n_rays, seed):
+    R = synth.object_rays(n_rays, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1000)
+    return dict(R=R, true_rgb=torch.rand(n_rays, 3, generator=g), true_mask=(torch.rand(n_rays, 1, generator=g) > 0.5).float())
+
+
+def _named_grads(sdf, col, var, Ro, To):
+    got = {"sdf." + k: p.grad for k, p in sdf.named_parameters() if p.grad is not None}
+    got.update({"color." + k: p.grad for k, p in col.named_parameters() if p.grad is not None})
+    got.update({"variance": var.variance.grad, "Ro": Ro.grad, "To": To.grad})
+    return got
+
+
+@pytest.mark.parametrize("n_rays,streams,use_graph", [(512, 3, True), (512, 1, False), (444, 3, True)])
+def test_bench_step_vs_fp64_oracle_on_the_products_z_vals(n_rays, streams, use_graph):
+    import honerf_b200 as H
+    import ref_conf
+    assert H.ops.default_precision() == H.ops._PRECISIONS["tc_bf16x3"]
+    c = _batch(n_rays, 7)
+    R = c["R"]
+    sdf, col, var, _, _ = obj_modules()
+    r = H.NeuSRenderer(sdf, var, col, "obj", **ref_conf.RENDERER_CONF)       # perturb = 1.0 like the bench
+    r.ray_streams = streams
+    Ro, To = R["Ro"].to(DEV).requires_grad_(True), R["To"].to(DEV).requires_grad_(True)
+    b = {k: v.to(DEV) for k, v in (("rays_o", R["rays_o"]), ("rays_d", R["rays_d"]), ("true_rgb", c["true_rgb"]),
+                                   ("true_mask", c["true_mask"]))}
+    params = [p for m in (sdf, col, var) for p in m.parameters()] + [Ro, To]
+    kept = {}
+
+    def fwd_bwd():
+        # bench.py: fwd_bwd() with --loss fused --shard-loss 1
+        div = b["true_mask"].sum() + 1e-5
+        outs = []
+
+        def shard_loss(out, lo, hi):
+            w = (hi - lo) / float(n_rays)
+            outs.append((lo, hi, out))
+            return H.ops.render_loss(out["color_fine"], out["weight_sum"], b["true_rgb"][lo:hi], b["true_mask"][lo:hi],
+                                     out["gradient_error"], div, 1.0, w, w)[0]
+        r.keep_z_vals = []
+        parts = r.render_sharded(b["rays_o"], b["rays_d"], R["near"], R["far"], None, None, None, Ro, To, 0, shard_loss)
+        loss = parts[0] if len(parts) == 1 else torch.stack(parts).sum()
+        for p in params:
+            p.grad = None
+        loss.backward()
+        kept["z"], kept["outs"], kept["loss"] = r.keep_z_vals, outs, loss
+        r.keep_z_vals = None
+
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fwd_bwd()
+        for _ in range(3):            # the tensors below are the graph's static outputs: they hold the LAST replay
+            graph.replay()
+    else:
+        fwd_bwd()
+    torch.cuda.synchronize()
+    z = torch.cat([t.cpu() for t in kept["z"]], 0)
+    assert z.shape == (n_rays, 128) and bool((z[:, 1:] >= z[:, :-1]).all())
+    color = torch.cat([o["color_fine"].cpu() for _, _, o in kept["outs"]], 0)
+    wsum = torch.cat([o["weight_sum"].cpu() for _, _, o in kept["outs"]], 0)
+    rcore, ref_loss, ref_g, names = oracle_core_fp64(c, z)
+    e_c, e_w = max_abs(color, rcore["color"]), max_abs(wsum, rcore["weights"].sum(-1, keepdim=True))
+    print("n_rays=%d streams=%d graph=%s: colour %.2e weight_sum %.2e loss rel %.2e" % (
+        n_rays, streams, use_graph, e_c, e_w, rel_err(kept["loss"], ref_loss)))
+    assert e_c < 1e-3 and e_w < 1e-3
+    assert rel_err(kept["loss"], ref_loss) < 1e-3
+    got = _named_grads(sdf, col, var, Ro, To)
+    worst = {k: rel_l2(got[k], ref_g[k]) for k in names}
+    print("worst gradient rel-L2:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    bad = {k: v for k, v in worst.items() if not v < 1e-2}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("n", [148 * 128 + 1, 65536])
+def test_sdf_operator_multi_tile_per_cta_vs_fp64(n):
+    """hn_sdf_obj_fwd / _bwd (utils/fields.py:316-347 + its double backward) where every persistent CTA processes 2-4
+    tiles: sdf / feature 1e-4 abs, normal 1e-2 relative, d_pts and every weight gradient 1e-2 relative (L2) vs fp64."""
+    import honerf_b200 as H
+    sdf, _, _, sp, _ = obj_modules()
+    g = torch.Generator().manual_seed(n)
+    x = 0.45 * torch.randn(n, 3, generator=g)
+    d_sdf, d_feat, d_n = torch.randn(n, 1, generator=g), 0.1 * torch.randn(n, 256, generator=g), torch.randn(n, 3, generator=g)
+    spd = {k: v.double().requires_grad_(True) for k, v in sp.items() if k != "se3_refine"}
+    Ws, bs = A.effective_weights(spd)
+    xd = x.double().requires_grad_(True)
+    rs, rf, rn, _ = A.sdf_obj_fwd(Ws, bs, xd)
+    L = (rs * d_sdf.double()).sum() + (rf * d_feat.double()).sum() + (rn * d_n.double()).sum()
+    names = list(spd)
+    ref_g = dict(zip(["pts"] + names, torch.autograd.grad(L, [xd] + [spd[k] for k in names])))
+    xg = x.to(DEV).requires_grad_(True)
+    s, f, nn = H.ops.sdf_obj(sdf.packed(), xg, 1.0)
+    print("n=%d sdf %.2e feat %.2e normal rel %.2e" % (n, max_abs(s, rs), max_abs(f, rf), rel_l2(nn, rn)))
+    assert max_abs(s, rs) < 1e-4 and max_abs(f, rf) < 1e-4 and rel_l2(nn, rn) < 1e-2
+    # per-point check: a stale tile would corrupt whole 128-point blocks while leaving the L2 norm almost intact
+    per_pt = (nn.detach().cpu().double() - rn.detach()).norm(dim=1) / rn.detach().norm(dim=1).clamp_min(1e-3)
+    assert float(per_pt.max()) < 5e-2, float(per_pt.max())
+    ((s * d_sdf.to(DEV)).sum() + (f * d_feat.to(DEV)).sum() + (nn * d_n.to(DEV)).sum()).backward()
+    got = {"pts": xg.grad}
+    got.update({k: p.grad for k, p in sdf.named_parameters() if p.grad is not None})
+    per_pt = (xg.grad.cpu().double() - ref_g["pts"]).norm(dim=1) / ref_g["pts"].norm(dim=1).clamp_min(1e-2 * float(ref_g["pts"].norm(dim=1).median()))
+    print("d_pts per-point worst %.2e" % float(per_pt.max()))
+    assert float(per_pt.max()) < 0.1
+    worst = {k: rel_l2(got[k], ref_g[k]) for k in ref_g}
+    print("worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:4])
+    assert all(v < 1e-2 for v in worst.values()), worst
+
+
+def test_end_to_end_on_knot_margin_filtered_rays():
+    """render() end to end (the product samples AND renders) against the oracle sampling in fp32 like the reference and
+    rendering in fp64, on the rays whose 64 importance samples landed where the oracle's did (no cdf-knot crossing,
+    SURVEY appendix B: a 1e-6 difference of a coarse SDF moves a sample across a knot on a few per cent of the rays).
+    Colour 1e-3, gradients 1e-2; prints the filtered fraction (must stay under 25 %)."""
+    import honerf_b200 as H
+    import ref_conf
+    n_rays = 256
+    c = _batch(n_rays, 11)
+    R = c["R"]
+    sdf, col, var, sp, cp = obj_modules()
+    r = H.NeuSRenderer(sdf, var, col, "obj", **dict(ref_conf.RENDERER_CONF, perturb=0.0))
+    zref = O.render_obj(sp, cp, torch.tensor(0.3), R["rays_o"], R["rays_d"], R["near"], R["far"], R["Ro"], R["To"], None)["z_vals"]
+    r.keep_z_vals = []
+    with torch.no_grad():
+        r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), R["near"], R["far"], None, None, None, R["Ro"].to(DEV), R["To"].to(DEV), 0)
+    zg = r.keep_z_vals[0].cpu()
+    r.keep_z_vals = None
+    # A ray is kept when none of its 64 importance samples moved by more than 1e-3 (1/17 of a coarse section): smaller
+    # moves are samples sliding inside a flat stretch of the cdf (free space, ~zero weight: t = (u - cdf[b]) / denom is
+    # ill-conditioned there and harmless); larger ones are samples that crossed a knot into another section.
+    dz = (zg - zref).abs().amax(dim=1)
+    for thr in (1e-5, 1e-4, 1e-3, 1e-2):
+        print("rays with a sample moved by more than %.0e: %.1f %%" % (thr, 100 * float((dz > thr).float().mean())))
+    keep = dz < 1e-3
+    frac = 1.0 - float(keep.float().mean())
+    print("rays filtered out (an importance sample crossed a cdf knot): %.1f %%" % (100 * frac))
+    assert frac < 0.25
+    idx = keep.nonzero()[:, 0]
+    sub = dict(R=dict(R, rays_o=R["rays_o"][idx], rays_d=R["rays_d"][idx]), true_rgb=c["true_rgb"][idx], true_mask=c["true_mask"][idx])
+    rcore, ref_loss, ref_g, names = oracle_core_fp64(sub, zref[idx])
+    Ro, To = R["Ro"].to(DEV).requires_grad_(True), R["To"].to(DEV).requires_grad_(True)
+    out = r.render(sub["R"]["rays_o"].to(DEV), sub["R"]["rays_d"].to(DEV), R["near"], R["far"], None, None, None, Ro, To, 0)
+    assert max_abs(out["color_fine"], rcore["color"]) < 1e-3
+    loss = O.training_loss(out, sub["true_rgb"].to(DEV), sub["true_mask"].to(DEV))
+    assert rel_err(loss, ref_loss) < 1e-3
+    loss.backward()
+    got = _named_grads(sdf, col, var, Ro, To)
+    worst = {k: rel_l2(got[k], ref_g[k]) for k in names}
+    print("worst gradient rel-L2:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    bad = {k: v for k, v in worst.items() if not v < 1e-2}
+    assert not bad, bad

@@ -135,6 +135,13 @@ def test_hand_render_vs_golden():
 def test_hand_render_core_given_same_z():
     """render_core (hand branch) on the oracle's z_vals: colour / weights <= 1e-3 abs, gradients to bone
     transforms, T-pose joints, variance and all weights <= 1e-2 relative (L2) vs the fp64 oracle."""
+    _hand_same_z(None)
+
+
+def _hand_same_z(own_factor):
+    """own_factor: None -> every gradient within 1e-2; a number -> within max(1e-2, own_factor x the error of the
+    reference's OWN fp32 arithmetic against fp64 on this case) -- the synthetic hand weights make normals of magnitude
+    up to ~70 whose sin/cos(8 n) encodings amplify any rounding of n (the reference in fp32 is itself 0.7-1.4e-2 off)."""
     import honerf_b200 as H
     import ref_conf
     c = cases.hand_render_case()
@@ -176,5 +183,19 @@ def test_hand_render_core_given_same_z():
     got.update({"variance": dev.variance.grad, "bt_inv": bt.grad, "T": T.grad})
     worst = {k: rel_l2(got[k], ref_g[k]) for k in names}
     print("worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
-    bad = {k: v for k, v in worst.items() if not v < 1e-2}
+    bound = {k: 1e-2 for k in names}
+    if own_factor is not None:
+        sp32 = {k: v.clone().requires_grad_(k != "se3_refine") for k, v in sp.items()}
+        cp32 = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
+        v32 = torch.tensor(0.3, requires_grad=True)
+        bt32, T32 = c["bt_inv"].clone().requires_grad_(True), c["T_pose_21"].clone().requires_grad_(True)
+        core32 = O.render_core_hand(sp32, cp32, v32, R["rays_o"], R["rays_d"], zref, 1.1 / 64, bt32, T32)
+        out32 = {"color_fine": core32["color"], "weight_sum": core32["weights"].sum(-1, keepdim=True),
+                 "gradient_error": core32["gradient_error"]}
+        t32 = [v for k, v in sp32.items() if k != "se3_refine"] + list(cp32.values()) + [v32, bt32, T32]
+        own = dict(zip(names, torch.autograd.grad(cases.hand_render_loss(out32, c["true_rgb"]), t32)))
+        own = {k: rel_l2(own[k], ref_g[k]) for k in names}
+        print("reference fp32 vs fp64:", sorted(own.items(), key=lambda kv: -kv[1])[:5])
+        bound = {k: max(1e-2, own_factor * own[k]) for k in names}
+    bad = {k: (v, bound[k]) for k, v in worst.items() if not v < bound[k]}
     assert not bad, bad
