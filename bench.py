@@ -629,7 +629,9 @@ def run_gpu_arm(args):
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"simt_fp32": "f32", "tc_tf32": "tf32", "tc_tf32x3": "tf32 (3xTF32 split operands)",
-                      "tc_bf16x3": "bf16 (split hi+lo operands, 3 MMAs per product, fp32 accumulate)"}[args.precision],
+                      "tc_bf16x3": "bf16 (split hi+lo operands, 3 MMAs per product, fp32 accumulate)",
+                      "tc_mixed16": "fp16/bf16 (value trunk: fp16 hi+lo, 3 MMAs; gradient sweeps: one 16-bit operand x hi+lo "
+                                    "weights, 2 MMAs; weight gradients: bf16, 1 MMA; fp32 accumulate)"}[args.precision],
             "data": "synthetic",
             "config": {"workload": WORKLOAD % n_rays,
                        "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
@@ -778,7 +780,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays", type=int, default=512, help="rays per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3"])
+    ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3", "tc_mixed16"])
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
     ap.add_argument("--ray-streams", type=int, default=3,

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhonerf_b200.so")
 
 HN_MAX_LAYERS = 12
-HN_SIMT_FP32, HN_TC_TF32, HN_TC_TF32X3, HN_TC_BF16X3 = 0, 1, 2, 3
+HN_SIMT_FP32, HN_TC_TF32, HN_TC_TF32X3, HN_TC_BF16X3, HN_TC_MIXED16 = 0, 1, 2, 3, 4
 HN_WS_SDF_ONLY, HN_WS_FWD, HN_WS_BWD = 0, 1, 2
 
 
@@ -100,6 +100,8 @@ PROTOTYPES = {
     "hn_color_obj_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, P, P, c_int64, P, _grad_p, P, c_int64,
                                  c_int, P]),
     "hn_dw_test": (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P]),
+    "hn_dw16_test": (c_int, [P, c_int, P, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P, c_int64, P]),
+    "hn_dw16_set_debug": (c_int, [c_int]),
     "hn_tc_gemm_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "hn_tc_gemm_ts_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "hn_gemm_test": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),

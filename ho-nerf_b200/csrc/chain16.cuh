@@ -1,0 +1,221 @@
+// HN_TC_MIXED16: the object SDF field with a 16-bit activation stash and TMEM-resident operands.
+//
+// What changes against the HN_TC_BF16X3 chain kernels (chain_obj.cu), and why (profiles/r02_precision_table.md):
+//  * the value trunk keeps three fp16 MMAs per product (sdf / feature error ~2e-6; anything less misses the 1e-3
+//    colour / SDF bound by less than 2x), but every sweep whose output is a gradient -- normal sweep, tangent sweep,
+//    reverse sweep -- rounds its A operand to ONE 16-bit value and keeps the weights as hi + lo pairs (two MMAs per
+//    product), and the weight gradients take their operands as stored (one MMA per product): normals 4e-4, weight
+//    gradients <= 6e-3 relative against the 1e-2 bound;
+//  * a single 16-bit A operand is 128 TMEM columns, so the sweeps keep it in tensor memory DOUBLE-BUFFERED
+//    (accumulator 256 + A0 128 + A1 128 = 512 columns): a layer is issued as two 128-column halves, the epilogue of
+//    the first half runs under the MMAs of the second and writes the next layer's operand straight into the other
+//    buffer (tcgen05.st), and shared memory holds nothing but the weight ring and two fp32 scratch tiles;
+//  * everything the sweeps exchange through HBM is 16-bit and "dW-ready": [128 points x 256 features] tiles in the
+//    un-swizzled MN-major core-matrix order the weight-gradient MMAs consume (8 points x 8 features = 128 contiguous
+//    bytes), grouped so that a warp's access (32 consecutive points, one 8-feature chunk) is one 512-byte segment and a
+//    64-point operand stage of the weight-gradient kernel is ONE 32 KB bulk copy with no conversion.
+//    Stored: EM = exp(-100 h) = 1 - softplus'(z) as fp16 (the sweeps need no transcendental), A16 = h as bf16 (weight-
+//    gradient operand), D16 / U16 / X16 / DZ16 as bf16: 28 bytes per element and layer through HBM instead of 56.
+#pragma once
+#include "chain_common.cuh"
+
+namespace hn {
+namespace chain {
+
+// ---- 16-bit stash tiles ---------------------------------------------------------------------------------------------
+// tile = [half (64 points)][chunk f8 (8 features, NCH per point)][64 points][16 bytes]
+constexpr int T16_TILE_BYTES = TILE_M * 256 * 2;         // 64 KB  (NCH = 32)
+constexpr int T16N_TILE_BYTES = TILE_M * 64 * 2;         // 16 KB  (NCH = 8: the 64-wide encoding arrays)
+template <int NCH = 32>
+__host__ __device__ __forceinline__ uint32_t t16_off(int p, int f8) {
+    return (uint32_t)(p >> 6) * (uint32_t)(NCH * 1024) + (uint32_t)f8 * 1024u + (uint32_t)(p & 63) * 16u;
+}
+__device__ __forceinline__ uint4 ldg16(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void stg16(uint8_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ float2 f16x2_unpack(uint32_t w) { return __half22float2(*reinterpret_cast<const __half2*>(&w)); }
+
+// softplus(beta = 100) and em = exp(-100 h) = 1 - sigmoid(100 z) from ONE exponential:
+//   e = exp(-|100 z|);  h = max(z, 0) + 0.01 log(1 + e);  em = (z >= 0 ? e : 1) / (1 + e)
+__device__ __forceinline__ float softplus100_em(float z, float& em) {
+    const float e = ex2_approx(-fabsf(z) * 144.26950408889634f);
+    const float t = 1.0f + e;
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    em = (z >= 0.0f ? e : 1.0f) * r;
+    return fmaf(lg2_approx(t), 0.006931471805599453f, fmaxf(z, 0.0f));
+}
+
+// ---- sweep kernels: A operand in tensor memory, double-buffered -------------------------------------------------------
+constexpr int SW_STAGE_BYTES = 128 * 128;        // one weight stage: [128 rows x 64 k] 16-bit
+constexpr int SW_STAGES = 9;
+constexpr int SW_SCR_LD = 65;                    // fp32 scratch tiles [128][65] (padded: conflict-free columns)
+constexpr int SW_SCR_BYTES = TILE_M * SW_SCR_LD * 4;
+constexpr int SW_SCR0_OFF = SW_STAGES * SW_STAGE_BYTES;
+constexpr int SW_SCR1_OFF = SW_SCR0_OFF + SW_SCR_BYTES;
+constexpr int SW_SMEM_BYTES = SW_SCR1_OFF + SW_SCR_BYTES + 1024;
+constexpr uint32_t SW_A0 = 256, SW_A1 = 384;     // TMEM columns of the two A buffers (accumulator: [0, 256))
+constexpr int SW_MAX_STEPS = 36;
+
+// one N-half of a layer: acc[128, n_mma] (TMEM columns acc_col ..) = A[a_buf][:, 0 : 64 kblocks] @ B^T
+struct SwStep {
+    uint32_t b_off;          // operand at chain + b_off: kblocks x { hi tile [n_mma x 128 B], lo tile [n_mma x 128 B] }
+    uint16_t n_mma;
+    uint8_t kblocks;
+    uint8_t a_buf : 1;
+    uint8_t wait_a : 1;      // first half of a layer: wait until the epilogue has published the A operand
+    uint8_t f16 : 1;         // fp16 operands (normal sweep) instead of bf16
+    uint8_t passes : 2;      // 2: A (B_hi + B_lo);  1: A B_hi
+    uint16_t acc_col;
+};
+struct SwProgram {
+    int n_steps;
+    SwStep step[SW_MAX_STEPS];
+};
+struct SwBarriers {
+    uint64_t full[SW_STAGES];
+    uint64_t empty[SW_STAGES];
+    uint64_t a_ready;
+    uint64_t acc_full;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint8_t* sw_setup(uint8_t* smem_raw, SwBarriers* bar) {
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) tc::tmem_alloc(&bar->tmem_base, 512);
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < SW_STAGES; ++s) {
+            tc::mbar_init(&bar->full[s], 1);
+            tc::mbar_init(&bar->empty[s], 1);
+        }
+        tc::mbar_init(&bar->a_ready, EPI_THREADS);
+        tc::mbar_init(&bar->acc_full, 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    return smem;
+}
+__device__ __forceinline__ void sw_teardown(SwBarriers* bar) {
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(bar->tmem_base, 512);
+}
+
+// warp 0, lane 0
+__device__ __forceinline__ void sw_producer(const SwProgram& prog, const uint8_t* __restrict__ chain_w, uint8_t* smem,
+                                            SwBarriers* bar, int n_my_tiles) {
+    uint32_t stage = 0, phase = 0;
+    for (int t = 0; t < n_my_tiles; ++t)
+        for (int s = 0; s < prog.n_steps; ++s) {
+            const SwStep st = prog.step[s];
+            const uint32_t bytes = (uint32_t)st.n_mma * 128u;
+            const uint8_t* src = chain_w + st.b_off;
+            for (int kb = 0; kb < st.kblocks; ++kb)
+                for (int ps = 0; ps < st.passes; ++ps) {
+                    tc::mbar_wait(&bar->empty[stage], phase ^ 1u);
+                    tc::mbar_arrive_expect_tx(&bar->full[stage], bytes);
+                    tc::bulk_g2s(smem + stage * SW_STAGE_BYTES, src + (size_t)(2 * kb + ps) * bytes, bytes, &bar->full[stage]);
+                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+                }
+        }
+}
+
+// warp 1, lane 0
+__device__ __forceinline__ void sw_mma(const SwProgram& prog, uint8_t* smem, SwBarriers* bar, int n_my_tiles) {
+    const uint32_t tmem = bar->tmem_base;
+    const uint32_t ring = tc::smem_u32(smem);
+    uint32_t stage = 0, phase = 0, a_par = 0;
+    for (int t = 0; t < n_my_tiles; ++t)
+        for (int s = 0; s < prog.n_steps; ++s) {
+            const SwStep st = prog.step[s];
+            const uint32_t idesc = tc::make_idesc(st.f16 ? tc::FMT_F16 : tc::FMT_BF16, 128, st.n_mma);
+            const uint32_t d = tmem + st.acc_col;
+            const uint32_t a = tmem + (st.a_buf ? SW_A1 : SW_A0);
+            if (st.wait_a) {
+                tc::mbar_wait(&bar->a_ready, a_par);
+                a_par ^= 1u;
+                tc::tc_fence_after_sync();
+            }
+            for (int kb = 0; kb < st.kblocks; ++kb)
+                for (int ps = 0; ps < st.passes; ++ps) {
+                    tc::mbar_wait(&bar->full[stage], phase);
+                    tc::tc_fence_after_sync();
+                    const uint64_t dB = tc::make_smem_desc_sw128(ring + stage * SW_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc::umma_f16_ts(d, a + (uint32_t)kb * 32u + 8u * k, dB + 2 * k, idesc, (kb | k | ps) != 0);
+                    tc::umma_commit(&bar->empty[stage]);
+                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            tc::umma_commit(&bar->acc_full);
+        }
+}
+
+// epilogue-side handshake
+__device__ __forceinline__ void sw_wait_acc(SwBarriers* bar, uint32_t& par) {
+    tc::mbar_wait(&bar->acc_full, par);
+    par ^= 1u;
+    tc::tc_fence_after_sync();
+}
+__device__ __forceinline__ void sw_publish(SwBarriers* bar) {
+    tc::tmem_st_wait();
+    tc::tc_fence_before_sync();
+    tc::mbar_arrive(&bar->a_ready);
+}
+// 16 accumulator columns [col0, col0 + 16) of this thread's lane
+__device__ __forceinline__ void sw_ld16(uint32_t tmem, uint32_t lane_base, int col0, float* v) {
+    tc::tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)col0, v);
+    tc::tmem_ld_wait();
+}
+// 16 operand columns [col0, col0 + 16) (8 packed words) into A buffer `abuf` (SW_A0 / SW_A1)
+__device__ __forceinline__ void sw_st16(uint32_t tmem, uint32_t lane_base, uint32_t abuf, int col0, const uint32_t* w) {
+    tc::tmem_st_32x32b_x8(tmem + lane_base + abuf + (uint32_t)(col0 >> 1), w);
+}
+
+// ---- launchers (chain16_obj.cu / chain16_dw.cu) -------------------------------------------------------------------------
+int64_t m16_stash_floats(int64_t n);
+int64_t m16_bwd_ws_floats(int64_t n);
+int launch_m16_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat, int64_t ld_feat,
+                   float* normal, float* stash, cudaStream_t s);
+int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf, const float* d_feat,
+                   int64_t ld_dfeat, const float* d_normal, float* d_pts, const hn_mlp_grad_t* grad, float* ws, cudaStream_t s);
+
+// weight-gradient kernel over 16-bit dW-ready tiles
+struct Dw16Job {
+    const uint8_t* P[2];     // [tiles] T16 tiles (256 features): M operand (output features)
+    const uint8_t* Q[2];     // [tiles] T16 tiles of q_chunks * 8 features: N operand (input features)
+    int n_pairs;
+    int q_chunks;            // 32 (T16) or 8 (T16N)
+    int n_mma;               // UMMA N: multiple of 16, <= 8 * q_chunks
+    float* db;               // += column sums of P[0] (may be NULL)
+    int p_cols;              // valid columns of P (length of db)
+};
+struct Dw16Params {
+    int n_tiles;
+    int n_jobs;
+    Dw16Job job[12];
+    float* part;             // [n_jobs][DW_SPLITS][256][256]
+};
+
+struct DwReduceParams;
+int launch_dw16(const Dw16Params& p, const DwReduceParams& r, cudaStream_t s);
+int launch_out_row0_grad16(const uint8_t* H7, const uint8_t* U7, const float* d_sdf, int64_t n, int n_tiles, float inv_scale,
+                           float* dW_row0, float* db0, cudaStream_t s);
+
+}  // namespace chain
+}  // namespace hn

@@ -1,0 +1,841 @@
+// Object SDF field, HN_TC_MIXED16 (see chain16.cuh):
+//   trunk16_kernel   SDFNetwork_OBJ.forward (utils/fields.py:316-331): value trunk + feature head, three fp16 MMAs per
+//                    product, activations in tensor memory (the design of chain_ts.cu); leaves EM = exp(-100 h) (fp16),
+//                    A16 = h (bf16), the encoding E (fp32) / E16 (bf16) in HBM
+//   nsweep16_kernel  SDFNetwork_OBJ.gradient (utils/fields.py:336-347) as the analytic normal sweep
+//                    D_{l-1} = s'(h_{l-1}) * (D_l W_l), normal = J_e^T (D_0 W_0 + skip part): fp16 A operand in tensor
+//                    memory (double-buffered), two MMAs per product; leaves D16 (bf16) and EB (fp32)
+//   bwd16_kernel     the second-order backward of (sdf, feature, normal): tangent sweep + reverse sweep, bf16 A operand
+//                    in tensor memory, two MMAs per product; leaves U16 / X16 / DZ16 / DF16 / UE16 (bf16) and d_pts
+//   + chain16_dw.cu  all weight / bias gradients from those tiles in one launch
+#include <algorithm>
+
+#include "chain16.cuh"
+#include "chain_dw.cuh"
+#include "chain_obj_layout.cuh"
+
+namespace hn {
+namespace chain {
+
+// ------------------------------------------------------------------------------------------------------------------
+// trunk: activations (fp16 hi + lo) in tensor memory, TMEM columns [0,256) accumulator, [256,384) A_hi, [384,512) A_lo
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int TR_STAGE_BYTES = 128 * 128;
+constexpr int TR_STAGES = 10;
+constexpr int TR_ENC_LD = 65;
+constexpr int TR_ENC_OFF = TR_STAGES * TR_STAGE_BYTES;
+constexpr int TR_HEAD_OFF = TR_ENC_OFF + TILE_M * TR_ENC_LD * 4;
+constexpr int TR_SMEM_BYTES = TR_HEAD_OFF + EPI_CGROUPS * TILE_M * 4 + 1024;
+constexpr uint32_t TR_A_HI = 256, TR_A_LO = 384;
+
+struct TrBarriers {
+    uint64_t full[TR_STAGES];
+    uint64_t empty[TR_STAGES];
+    uint64_t a_ready;
+    uint64_t acc_full;
+    uint32_t tmem_base;
+};
+
+struct Trunk16Params {
+    const float* pts;
+    int64_t n;
+    float inv_scale;
+    float* sdf;
+    float* feat;
+    int64_t ld_feat;
+    float* E;            // fp32 column-major [64][128] tiles (eoff)
+    uint8_t* E16;        // bf16 T16N tiles
+    uint8_t* EM[8];      // fp16 T16 tiles
+    uint8_t* A16[8];     // bf16 T16 tiles
+    const uint8_t* chain;
+    const float* bias[9];
+    const float* w_out0;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ Program prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ TrBarriers bar;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_enc = reinterpret_cast<float*>(smem + TR_ENC_OFF);
+    float* s_head = reinterpret_cast<float*>(smem + TR_HEAD_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tc::tmem_alloc(&bar.tmem_base, 512);
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < TR_STAGES; ++s) {
+            tc::mbar_init(&bar.full[s], 1);
+            tc::mbar_init(&bar.empty[s], 1);
+        }
+        tc::mbar_init(&bar.a_ready, EPI_THREADS);
+        tc::mbar_init(&bar.acc_full, 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = bar.tmem_base;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = 0; t < n_my_tiles; ++t)
+                for (int s = 0; s < prog.n_steps; ++s) {
+                    const Step st = prog.step[s];
+                    const uint8_t* src = p.chain + st.b_off;
+                    for (int c = 0; c < 2 * st.kblocks; ++c) {
+                        tc::mbar_wait(&bar.empty[stage], phase ^ 1u);
+                        tc::mbar_arrive_expect_tx(&bar.full[stage], TR_STAGE_BYTES);
+                        tc::bulk_g2s(smem + stage * TR_STAGE_BYTES, src + (size_t)c * TR_STAGE_BYTES, TR_STAGE_BYTES, &bar.full[stage]);
+                        if (++stage == TR_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t ring = tc::smem_u32(smem);
+            const uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, 128);
+            uint32_t stage = 0, phase = 0, a_par = 0;
+            for (int t = 0; t < n_my_tiles; ++t)
+                for (int s = 0; s < prog.n_steps; ++s) {
+                    const Step st = prog.step[s];
+                    const uint32_t d = tmem + st.acc_col;
+                    if (!st.no_wait) {
+                        tc::mbar_wait(&bar.a_ready, a_par);
+                        a_par ^= 1u;
+                        tc::tc_fence_after_sync();
+                    }
+                    for (int kb = 0; kb < st.kblocks; ++kb) {
+                        const uint32_t ah = tmem + TR_A_HI + (uint32_t)kb * 32, al = tmem + TR_A_LO + (uint32_t)kb * 32;
+                        tc::mbar_wait(&bar.full[stage], phase);
+                        tc::tc_fence_after_sync();
+                        uint64_t dB = tc::make_smem_desc_sw128(ring + stage * TR_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            tc::umma_f16_ts(d, al + 8 * k, dB + 2 * k, idesc, (kb | k) != 0);
+                            tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc, 1);
+                        }
+                        tc::umma_commit(&bar.empty[stage]);
+                        if (++stage == TR_STAGES) { stage = 0; phase ^= 1u; }
+                        tc::mbar_wait(&bar.full[stage], phase);
+                        tc::tc_fence_after_sync();
+                        dB = tc::make_smem_desc_sw128(ring + stage * TR_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc, 1);
+                        tc::umma_commit(&bar.empty[stage]);
+                        if (++stage == TR_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc::umma_commit(&bar.acc_full);
+                }
+        }
+    } else {
+        const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
+        uint32_t acc_par = 0;
+        auto publish = [&]() {
+            tc::tmem_st_wait();
+            tc::tc_fence_before_sync();
+            tc::mbar_arrive(&bar.a_ready);
+        };
+        auto wait_acc = [&]() {
+            tc::mbar_wait(&bar.acc_full, acc_par);
+            acc_par ^= 1u;
+            tc::tc_fence_after_sync();
+        };
+        auto store_a = [&](int col0, const uint32_t* hi, const uint32_t* lo) {
+            const uint32_t c = (uint32_t)(col0 >> 1);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + TR_A_HI + c, hi);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + TR_A_HI + c + 8, hi + 8);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + TR_A_LO + c, lo);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + TR_A_LO + c + 8, lo + 8);
+        };
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            // 8 columns [c, c + 8) of layer l: stash chunks (EM fp16, A16 bf16) + fp16 hi / lo words of the next A operand
+            auto emit8 = [&](int l, int c, const float* h, const float* em, uint32_t* hi4, uint32_t* lo4) {
+                const uint32_t off = t16_off(row, c >> 3);
+                uint4 q;
+                q.x = pack_f16x2(em[0], em[1]); q.y = pack_f16x2(em[2], em[3]); q.z = pack_f16x2(em[4], em[5]); q.w = pack_f16x2(em[6], em[7]);
+                stg16(p.EM[l] + (size_t)tile * T16_TILE_BYTES + off, q);
+                q.x = pack_bf16x2(h[0], h[1]); q.y = pack_bf16x2(h[2], h[3]); q.z = pack_bf16x2(h[4], h[5]); q.w = pack_bf16x2(h[6], h[7]);
+                stg16(p.A16[l] + (size_t)tile * T16_TILE_BYTES + off, q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2_lo16(h[2 * i], h[2 * i + 1], hi4[i], lo4[i]);
+            };
+            // softplus of accumulator columns [acc_col0, +32) = layer columns [col0, +32)
+            auto act_half = [&](int l, int col0, uint32_t* hh, uint32_t* hl, float& head) {
+                const float* __restrict__ bias = p.bias[l];
+                float v[32];
+                acc_load32(tmem, row, col0, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j + 4));
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float h[8], em[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) h[i] = softplus100_em(v[j + i] + bb[i], em[i]);
+                    emit8(l, col0 + j, h, em, hh + (j >> 1), hl + (j >> 1));
+                    if (l == 7) {
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
+                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j + 4));
+                        head += h[0] * w0.x + h[1] * w0.y + h[2] * w0.z + h[3] * w0.w + h[4] * w1.x + h[5] * w1.y + h[6] * w1.z + h[7] * w1.w;
+                    }
+                }
+            };
+            // ---- encoding -> shared scratch (fp32, kept for the skip connection), E / E16 stash, first-layer operand ------
+            {
+                float x[3] = {0.f, 0.f, 0.f};
+                if (gp < p.n) { x[0] = p.pts[gp * 3]; x[1] = p.pts[gp * 3 + 1]; x[2] = p.pts[gp * 3 + 2]; }
+                float* e = s_enc + row * TR_ENC_LD;
+                float* __restrict__ ge = p.E + eoff(gp);
+                if (cg == 0) {
+                    e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; e[63] = 0.0f;
+                    ge[0] = x[0]; ge[TILE_M] = x[1]; ge[2 * TILE_M] = x[2]; ge[63 * TILE_M] = 0.0f;
+                }
+                for (int idx = cg; idx < 30; idx += EPI_CGROUPS) {
+                    const int c = idx / 10, k = idx - c * 10;
+                    float s, co;
+                    sincosf(x[c] * (float)(1 << k), &s, &co);
+                    e[3 + c * 20 + k] = s;
+                    e[3 + c * 20 + 10 + k] = co;
+                    ge[(3 + c * 20 + k) * TILE_M] = s;
+                    ge[(3 + c * 20 + 10 + k) * TILE_M] = co;
+                }
+                tc::named_bar_sync(1, EPI_THREADS);
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2_lo16(e[cg * 16 + 2 * i], e[cg * 16 + 2 * i + 1], hi[i], lo[i]);
+                tc::tmem_st_32x32b_x8(tmem + lane_base + TR_A_HI + (uint32_t)(cg * 8), hi);
+                tc::tmem_st_32x32b_x8(tmem + lane_base + TR_A_LO + (uint32_t)(cg * 8), lo);
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const float* s = e + cg * 16 + c2 * 8;
+                    uint4 q;
+                    q.x = pack_bf16x2(s[0], s[1]); q.y = pack_bf16x2(s[2], s[3]); q.z = pack_bf16x2(s[4], s[5]); q.w = pack_bf16x2(s[6], s[7]);
+                    stg16(p.E16 + (size_t)tile * T16N_TILE_BYTES + t16_off<8>(row, cg * 2 + c2), q);
+                }
+            }
+            publish();
+            float head = 0.0f;
+            for (int l = 0; l < 8; ++l) {
+                uint32_t hh[16], hl[16];
+                // ---- first half (columns cg*32 ..), under the second half's MMAs ----------------------------------------
+                wait_acc();
+                act_half(l, cg * 32, hh, hl, head);
+                // ---- second half: every MMA of the layer has read A, it may be overwritten ---------------------------------
+                wait_acc();
+                store_a(cg * 32, hh, hl);
+                const int col0 = 128 + cg * 32;
+                if (l == 3 && col0 >= 192) {
+                    // skip input, columns 192..255 = [h3[192], e_0 .. e_62]
+                    const float* e = s_enc + row * TR_ENC_LD;
+                    float v[32], em0 = 0.0f;
+                    if (col0 == 192) {
+                        float a[32];
+                        acc_load32(tmem, row, 192, a);
+                        v[0] = softplus100_em(a[0] + __ldg(p.bias[3] + 192), em0);
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) v[j] = e[j - 1];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = e[31 + j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float em[8] = {j == 0 ? em0 : 0.0f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        emit8(l, col0 + j, v + j, em, hh + (j >> 1), hl + (j >> 1));
+                    }
+                } else {
+                    act_half(l, col0, hh, hl, head);
+                }
+                store_a(col0, hh, hl);
+                publish();
+            }
+            // sdf = (h7 . W_out[0] + b_out[0]) / scale
+            s_head[cg * TILE_M + row] = head;
+            tc::named_bar_sync(1, EPI_THREADS);
+            if (cg == 0 && gp < p.n) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int g = 0; g < EPI_CGROUPS; ++g) acc += s_head[g * TILE_M + row];
+                p.sdf[gp] = (acc + __ldg(p.bias[8])) * p.inv_scale;
+            }
+            // ---- feature head: rows 1..256 of the output layer, no activation ----------------------------------------------
+            for (int hf = 0; hf < 2; ++hf) {
+                wait_acc();
+                const int col0 = 128 * hf + cg * 32;
+                float v[32];
+                acc_load32(tmem, row, col0, v);
+                if (gp < p.n) {
+                    const float* __restrict__ bias = p.bias[8] + 1;
+                    float* __restrict__ fr = p.feat + gp * p.ld_feat + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        st4(fr + j, make_float4(v[j] + __ldg(bias + col0 + j), v[j + 1] + __ldg(bias + col0 + j + 1),
+                                                v[j + 2] + __ldg(bias + col0 + j + 2), v[j + 3] + __ldg(bias + col0 + j + 3)));
+                }
+            }
+            tc::tc_fence_before_sync();       // the accumulator reads above precede the next tile's MMAs (ordered by its a_ready)
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// normal sweep
+// ------------------------------------------------------------------------------------------------------------------
+struct Nsweep16Params {
+    int64_t n;
+    float inv_scale;
+    const float* E;
+    const uint8_t* EM[8];
+    uint8_t* D16[8];
+    float* EB;
+    float* normal;
+    const uint8_t* chain;
+    const float* w_out0;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant__ SwProgram prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ SwBarriers bar;
+    uint8_t* smem = sw_setup(smem_raw, &bar);
+    float* s_skip = reinterpret_cast<float*>(smem + SW_SCR1_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+    } else {
+        const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            const size_t tb = (size_t)tile * T16_TILE_BYTES;
+            // 16 columns [c, c + 16): d = s'(h) * g -> fp16 words of the next A operand, bf16 chunks of the D16 stash
+            auto emit16 = [&](int lyr, int c, const float* d, uint32_t abuf) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = pack_f16x2(d[2 * i], d[2 * i + 1]);
+                sw_st16(tmem, lane_base, abuf, c, w);
+                uint4 q0, q1;
+                q0.x = pack_bf16x2(d[0], d[1]); q0.y = pack_bf16x2(d[2], d[3]); q0.z = pack_bf16x2(d[4], d[5]); q0.w = pack_bf16x2(d[6], d[7]);
+                q1.x = pack_bf16x2(d[8], d[9]); q1.y = pack_bf16x2(d[10], d[11]); q1.z = pack_bf16x2(d[12], d[13]); q1.w = pack_bf16x2(d[14], d[15]);
+                stg16(p.D16[lyr] + tb + t16_off(row, c >> 3), q0);
+                stg16(p.D16[lyr] + tb + t16_off(row, (c >> 3) + 1), q1);
+            };
+            auto load_em16 = [&](int lyr, int c, float* sp) {       // s' = 1 - em of 16 columns
+                const uint4 a = ldg16(p.EM[lyr] + tb + t16_off(row, c >> 3));
+                const uint4 b = ldg16(p.EM[lyr] + tb + t16_off(row, (c >> 3) + 1));
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 f = f16x2_unpack(w[i]);
+                    sp[2 * i] = 1.0f - f.x;
+                    sp[2 * i + 1] = 1.0f - f.y;
+                }
+            };
+            // ---- seed: D_7 = s'(h_7) * W_out[0] / scale ---------------------------------------------------------------------
+#pragma unroll 1
+            for (int sb = 0; sb < 4; ++sb) {
+                const int c = 128 * (sb >> 1) + cg * 32 + 16 * (sb & 1);
+                float sp[16], d[16];
+                load_em16(7, c, sp);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + c + j));
+                    d[j] = sp[j] * w.x * p.inv_scale; d[j + 1] = sp[j + 1] * w.y * p.inv_scale;
+                    d[j + 2] = sp[j + 2] * w.z * p.inv_scale; d[j + 3] = sp[j + 3] * w.w * p.inv_scale;
+                }
+                if (!live) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+                }
+                emit16(7, c, d, SW_A0);
+            }
+            sw_publish(&bar);
+            // ---- D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1 ------------------------------------------------------------------
+            for (int l = 7; l >= 1; --l) {
+                const uint32_t abuf = ((7 - l) & 1) ? SW_A0 : SW_A1;       // the buffer this layer WRITES
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    sw_wait_acc(&bar, acc_par);
+#pragma unroll 1
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int c = 128 * hf + cg * 32 + 16 * sub;
+                        float g[16], sp[16];
+                        load_em16(l - 1, c, sp);
+                        sw_ld16(tmem, lane_base, c, g);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float d = sp[j] * g[j];
+                            if (l == 4 && c + j > 192) {
+                                // columns 193..255 of the skip layer's input are the encoding: their cotangent is the raw product
+                                s_skip[row * SW_SCR_LD + (c + j - 193)] = g[j];
+                                d = 0.0f;
+                            }
+                            g[j] = live ? d : 0.0f;
+                        }
+                        emit16(l - 1, c, g, abuf);
+                    }
+                }
+                sw_publish(&bar);
+            }
+            // ---- encoding layer: eb = D_0 W_0 + (skip part); normal = J_e^T eb ---------------------------------------------------
+            sw_wait_acc(&bar, acc_par);
+            {
+                float g[16];
+                sw_ld16(tmem, lane_base, cg * 16, g);
+                float* __restrict__ sk = s_skip + row * SW_SCR_LD + cg * 16;
+                float* __restrict__ eb = p.EB + eoff(gp, cg * 16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v = (cg * 16 + j == 63) ? 0.0f : g[j] + sk[j];
+                    sk[j] = v;
+                    eb[j * TILE_M] = v;
+                }
+            }
+            tc::tc_fence_before_sync();
+            tc::named_bar_sync(1, EPI_THREADS);
+            if (cg < 3 && live) {
+                const float* __restrict__ e = p.E + eoff(gp, 3 + cg * 20);
+                const float* __restrict__ g = s_skip + row * SW_SCR_LD + 3 + cg * 20;
+                float acc = s_skip[row * SW_SCR_LD + cg];
+                float f = 1.0f;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    acc += f * (e[(10 + k) * TILE_M] * g[k] - e[k * TILE_M] * g[10 + k]);
+                    f *= 2.0f;
+                }
+                p.normal[gp * 3 + cg] = acc;
+            }
+        }
+    }
+    sw_teardown(&bar);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// second-order backward: tangent sweep + reverse sweep
+// ------------------------------------------------------------------------------------------------------------------
+struct Bwd16Params {
+    int64_t n;
+    float inv_scale;
+    const float* E;
+    const float* EB;
+    const uint8_t* EM[8];
+    const uint8_t* D16[8];
+    const float* d_sdf;      // may be NULL
+    const float* d_feat;     // may be NULL
+    int64_t ld_dfeat;
+    const float* d_normal;
+    float* d_pts;            // may be NULL
+    uint8_t* U16[8];
+    uint8_t* X16[8];
+    uint8_t* DZ16[8];
+    uint8_t* UE16;
+    uint8_t* DF16;
+    int store_dw;            // 0: nobody needs weight gradients (pose fitting): skip the U16 / DZ16 / UE16 / DF16 stores
+    const uint8_t* chain;
+    const float* w_out0;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwProgram prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ SwBarriers bar;
+    uint8_t* smem = sw_setup(smem_raw, &bar);
+    float* s_ue = reinterpret_cast<float*>(smem + SW_SCR0_OFF);
+    float* s_skip = reinterpret_cast<float*>(smem + SW_SCR1_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+    } else {
+        const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0;
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            const size_t tb = (size_t)tile * T16_TILE_BYTES;
+            float dn[3] = {0.f, 0.f, 0.f};
+            if (live) { dn[0] = p.d_normal[gp * 3]; dn[1] = p.d_normal[gp * 3 + 1]; dn[2] = p.d_normal[gp * 3 + 2]; }
+            const float gs = (live && p.d_sdf) ? p.d_sdf[gp] * p.inv_scale : 0.0f;
+            auto pack16 = [&](const float* v, uint32_t* w) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            };
+            auto store16 = [&](uint8_t* arr, int c, const uint32_t* w) {
+                stg16(arr + tb + t16_off(row, c >> 3), make_uint4(w[0], w[1], w[2], w[3]));
+                stg16(arr + tb + t16_off(row, (c >> 3) + 1), make_uint4(w[4], w[5], w[6], w[7]));
+            };
+            auto load_bf16 = [&](const uint8_t* arr, int c, float* v) {
+                const uint4 a = ldg16(arr + tb + t16_off(row, c >> 3));
+                const uint4 b = ldg16(arr + tb + t16_off(row, (c >> 3) + 1));
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[2 * i] = bf16_lo(w[i]); v[2 * i + 1] = bf16_hi(w[i]); }
+            };
+            auto load_em = [&](const uint8_t* arr, int c, float* v) {
+                const uint4 a = ldg16(arr + tb + t16_off(row, c >> 3));
+                const uint4 b = ldg16(arr + tb + t16_off(row, (c >> 3) + 1));
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 f = f16x2_unpack(w[i]);
+                    v[2 * i] = f.x;
+                    v[2 * i + 1] = f.y;
+                }
+            };
+            // ---- ue = J_e(x) dn: tangent of the encoding, 16 columns per thread ---------------------------------------------
+            {
+                const float* __restrict__ e = p.E + eoff(gp);
+                float ue[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = cg * 16 + j;
+                    float v;
+                    if (col < 3) {
+                        v = dn[col];
+                    } else if (col == 63) {
+                        v = 0.0f;
+                    } else {
+                        const int jj = col - 3, c = jj / 20, r = jj - c * 20, k = r >= 10 ? r - 10 : r;
+                        const float f = (float)(1 << k);
+                        // column 3 + 20 c + k = sin(2^k x_c) -> f cos dn_c;  column 3 + 20 c + 10 + k = cos -> -f sin dn_c
+                        const float other = e[(r >= 10 ? col - 10 : col + 10) * TILE_M];
+                        v = (r >= 10 ? -f : f) * other * dn[c];
+                    }
+                    ue[j] = v;
+                    s_ue[row * SW_SCR_LD + col] = v;
+                }
+                uint32_t w[8];
+                pack16(ue, w);
+                sw_st16(tmem, lane_base, SW_A0, cg * 16, w);
+                if (p.store_dw) {
+                    stg16(p.UE16 + (size_t)tile * T16N_TILE_BYTES + t16_off<8>(row, cg * 2), make_uint4(w[0], w[1], w[2], w[3]));
+                    stg16(p.UE16 + (size_t)tile * T16N_TILE_BYTES + t16_off<8>(row, cg * 2 + 1), make_uint4(w[4], w[5], w[6], w[7]));
+                }
+            }
+            sw_publish(&bar);
+            int step = 0;
+            // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l ---------------------------------
+            for (int l = 0; l < 8; ++l, ++step) {
+                const uint32_t abuf = (step & 1) ? SW_A0 : SW_A1;      // the buffer this layer WRITES
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    sw_wait_acc(&bar, acc_par);
+#pragma unroll 1
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int c = 128 * hf + cg * 32 + 16 * sub;
+                        float q[16], em[16], d[16];
+                        load_em(p.EM[l], c, em);
+                        load_bf16(p.D16[l], c, d);
+                        sw_ld16(tmem, lane_base, c, q);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float u = (1.0f - em[j]) * q[j];
+                            float x = 100.0f * em[j] * d[j] * q[j];
+                            if (l == 3 && c + j > 192) {       // tangent of the skip input's encoding part
+                                u = s_ue[row * SW_SCR_LD + (c + j - 193)];
+                                x = 0.0f;
+                            }
+                            q[j] = u;
+                            d[j] = x;
+                        }
+                        uint32_t w[8];
+                        pack16(q, w);
+                        if (l < 7) sw_st16(tmem, lane_base, abuf, c, w);
+                        if (p.store_dw) store16(p.U16[l], c, w);
+                        pack16(d, w);
+                        store16(p.X16[l], c, w);
+                    }
+                }
+                if (l == 7) {
+                    // A operand of the output layer's reverse step: the point's row of d_feat
+#pragma unroll 1
+                    for (int sb = 0; sb < 4; ++sb) {
+                        const int c = 128 * (sb >> 1) + cg * 32 + 16 * (sb & 1);
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live && p.d_feat) a = ld4(p.d_feat + gp * p.ld_dfeat + c + j);
+                            v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
+                        }
+                        uint32_t w[8];
+                        pack16(v, w);
+                        sw_st16(tmem, lane_base, abuf, c, w);
+                        if (p.store_dw) store16(p.DF16, c, w);
+                    }
+                }
+                sw_publish(&bar);
+            }
+            // ---- reverse sweep: dz_{l-1} = s'(h_{l-1}) (dz_l W_l) + X_{l-1}, l = 8..1 -------------------------------------------
+            for (int l = 8; l >= 1; --l, ++step) {
+                const uint32_t abuf = (step & 1) ? SW_A0 : SW_A1;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    sw_wait_acc(&bar, acc_par);
+#pragma unroll 1
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int c = 128 * hf + cg * 32 + 16 * sub;
+                        float da[16], em[16], x[16];
+                        load_em(p.EM[l - 1], c, em);
+                        load_bf16(p.X16[l - 1], c, x);
+                        sw_ld16(tmem, lane_base, c, da);
+                        if (l == 8) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + c + j));
+                                da[j] += gs * w.x; da[j + 1] += gs * w.y; da[j + 2] += gs * w.z; da[j + 3] += gs * w.w;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float dz = fmaf(1.0f - em[j], da[j], x[j]);
+                            if (l == 4 && c + j > 192) {       // cotangent of the encoding part of the skip input
+                                s_skip[row * SW_SCR_LD + (c + j - 193)] = da[j];
+                                dz = 0.0f;
+                            }
+                            da[j] = dz;
+                        }
+                        uint32_t w[8];
+                        pack16(da, w);
+                        sw_st16(tmem, lane_base, abuf, c, w);
+                        if (p.store_dw) store16(p.DZ16[l - 1], c, w);
+                    }
+                }
+                sw_publish(&bar);
+            }
+            // ---- encoding layer: de = dz_0 W_0 + (skip part); d_x = J_e^T de + Hessian term -----------------------------------------
+            sw_wait_acc(&bar, acc_par);
+            {
+                float g[16];
+                sw_ld16(tmem, lane_base, cg * 16, g);
+                float* __restrict__ sk = s_skip + row * SW_SCR_LD + cg * 16;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sk[j] = (cg * 16 + j == 63) ? 0.0f : g[j] + sk[j];
+            }
+            tc::tc_fence_before_sync();
+            tc::named_bar_sync(1, EPI_THREADS);
+            if (p.d_pts && cg < 3 && live) {
+                const float* __restrict__ e = p.E + eoff(gp, 3 + cg * 20);
+                const float* __restrict__ b = p.EB + eoff(gp, 3 + cg * 20);
+                const float* __restrict__ g = s_skip + row * SW_SCR_LD + 3 + cg * 20;
+                float acc = s_skip[row * SW_SCR_LD + cg], hess = 0.0f, f = 1.0f;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    const float sn = e[k * TILE_M], cs = e[(10 + k) * TILE_M];
+                    acc += f * (cs * g[k] - sn * g[10 + k]);
+                    hess -= f * f * (sn * b[k * TILE_M] + cs * b[(10 + k) * TILE_M]);
+                    f *= 2.0f;
+                }
+                p.d_pts[gp * 3 + cg] = acc + dn[cg] * hess;
+            }
+        }
+    }
+    sw_teardown(&bar);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+struct M16Stash {
+    float* E;
+    float* EB;
+    uint8_t* E16;
+    uint8_t* EM[8];
+    uint8_t* A16[8];
+    uint8_t* D16[8];
+};
+static M16Stash m16_stash(float* stash, int64_t np) {
+    M16Stash s;
+    s.E = stash;
+    s.EB = stash + np * 64;
+    uint8_t* b = reinterpret_cast<uint8_t*>(stash + np * 128);
+    s.E16 = b; b += np * 128;
+    for (int l = 0; l < 8; ++l) { s.EM[l] = b; b += np * 512; }
+    for (int l = 0; l < 8; ++l) { s.A16[l] = b; b += np * 512; }
+    for (int l = 0; l < 8; ++l) { s.D16[l] = b; b += np * 512; }
+    return s;
+}
+int64_t m16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (128 + 32 + 24 * 128); }
+// backward workspace: U16[8] | X16[8] | DZ16[8] | DF16 | UE16 | partial sums of the dW kernel
+int64_t m16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (25 * 128 + 32) + dw_part_floats(9); }
+
+static int check_m16(const hn_mlp_t* m) {
+    HN_REQUIRE(m && m->n_layers == 9, "object SDF mlp must have 9 layers");
+    HN_REQUIRE(m->chain && m->chain_bytes >= (int64_t)obj_layout().total && aligned16(m->chain),
+               "HN_TC_MIXED16 needs the packed chain operands (hn_sdf_obj_chain_pack)");
+    return HN_OK;
+}
+
+static void sw_layer(SwProgram& prog, int& k, const uint32_t off[2], int n_halves, int n_mma, int kblocks, int layer_idx, int f16) {
+    for (int h = 0; h < n_halves; ++h) {
+        SwStep& st = prog.step[k++];
+        st.b_off = off[h];
+        st.n_mma = (uint16_t)n_mma;
+        st.kblocks = (uint8_t)kblocks;
+        st.a_buf = (uint8_t)(layer_idx & 1);
+        st.wait_a = (uint8_t)(h == 0);
+        st.f16 = (uint8_t)f16;
+        st.passes = 2;
+        st.acc_col = (uint16_t)(128 * h);
+    }
+}
+
+int launch_m16_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat, int64_t ld_feat,
+                   float* normal, float* stash, cudaStream_t s) {
+    HN_PROPAGATE(check_m16(m));
+    const ObjLayout L = obj_layout();
+    const int64_t np = round_up(n, TILE_M);
+    const M16Stash S = m16_stash(stash, np);
+    const int n_tiles = (int)(np / TILE_M);
+    const int grid = std::min(n_tiles, sm_count());
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(trunk16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM_BYTES));
+        HN_CHECK_CUDA(cudaFuncSetAttribute(nsweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+        configured = true;
+    }
+    {
+        Trunk16Params p;
+        p.pts = pts; p.n = n; p.inv_scale = inv_scale; p.sdf = sdf; p.feat = feat; p.ld_feat = ld_feat;
+        p.E = S.E; p.E16 = S.E16;
+        for (int l = 0; l < 8; ++l) { p.EM[l] = S.EM[l]; p.A16[l] = S.A16[l]; }
+        p.chain = reinterpret_cast<const uint8_t*>(m->chain);
+        for (int l = 0; l < 9; ++l) p.bias[l] = m->b[l];
+        p.w_out0 = m->W[8];
+        p.n_tiles = n_tiles;
+        Program prog = {};
+        prog.n_steps = 18;
+        for (int l = 0; l < 9; ++l)
+            for (int h = 0; h < 2; ++h) {
+                Step& st = prog.step[2 * l + h];
+                st.b_off = l < 8 ? L.nth_off[l][h] : L.nth8_off[h];
+                st.n_mma = 128;
+                st.kblocks = L.nt_kb[l];
+                st.f16 = 1;
+                st.no_wait = (uint8_t)h;
+                st.acc_col = (uint16_t)(128 * h);
+            }
+        TimingScope ts(s, TT_SDF_FWD);
+        trunk16_kernel<<<grid, THREADS, TR_SMEM_BYTES, s>>>(p, prog);
+    }
+    count_launch();
+    HN_CHECK_LAUNCH();
+    {
+        Nsweep16Params p;
+        p.n = n; p.inv_scale = inv_scale; p.E = S.E; p.EB = S.EB; p.normal = normal;
+        for (int l = 0; l < 8; ++l) { p.EM[l] = S.EM[l]; p.D16[l] = S.D16[l]; }
+        p.chain = reinterpret_cast<const uint8_t*>(m->chain);
+        p.w_out0 = m->W[8];
+        p.n_tiles = n_tiles;
+        SwProgram prog = {};
+        int k = 0;
+        for (int l = 7; l >= 1; --l) sw_layer(prog, k, L.nnh_off[l], 2, 128, 4, 7 - l, 1);
+        sw_layer(prog, k, L.nnh_off[0], 1, 64, 4, 7, 1);
+        prog.n_steps = k;
+        TimingScope ts(s, TT_SDF_FWD);
+        nsweep16_kernel<<<grid, THREADS, SW_SMEM_BYTES, s>>>(p, prog);
+    }
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf, const float* d_feat,
+                   int64_t ld_dfeat, const float* d_normal, float* d_pts, const hn_mlp_grad_t* grad, float* ws, cudaStream_t s) {
+    HN_PROPAGATE(check_m16(m));
+    HN_REQUIRE(!d_feat || (ld_dfeat % 4 == 0 && aligned16(d_feat)), "d_feat must be 16-byte aligned with ld %% 4 == 0");
+    const ObjLayout L = obj_layout();
+    const int64_t np = round_up(n, TILE_M);
+    const M16Stash S = m16_stash(const_cast<float*>(stash), np);
+    const int n_tiles = (int)(np / TILE_M);
+    uint8_t* b = reinterpret_cast<uint8_t*>(ws);
+    uint8_t *U16[8], *X16[8], *DZ16[8];
+    for (int l = 0; l < 8; ++l) { U16[l] = b; b += np * 512; }
+    for (int l = 0; l < 8; ++l) { X16[l] = b; b += np * 512; }
+    for (int l = 0; l < 8; ++l) { DZ16[l] = b; b += np * 512; }
+    uint8_t* DF16 = b; b += np * 512;
+    uint8_t* UE16 = b; b += np * 128;
+    float* part = reinterpret_cast<float*>(b);
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+        configured = true;
+    }
+    {
+        Bwd16Params p;
+        p.n = n; p.inv_scale = inv_scale; p.E = S.E; p.EB = S.EB;
+        for (int l = 0; l < 8; ++l) { p.EM[l] = S.EM[l]; p.D16[l] = S.D16[l]; p.U16[l] = U16[l]; p.X16[l] = X16[l]; p.DZ16[l] = DZ16[l]; }
+        p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.d_normal = d_normal; p.d_pts = d_pts;
+        p.UE16 = UE16; p.DF16 = DF16;
+        p.store_dw = grad ? 1 : 0;
+        p.chain = reinterpret_cast<const uint8_t*>(m->chain);
+        p.w_out0 = m->W[8];
+        p.n_tiles = n_tiles;
+        SwProgram prog = {};
+        int k = 0, idx = 0;
+        for (int l = 0; l < 8; ++l, ++idx) sw_layer(prog, k, L.ntb_off[l], 2, 128, L.nt_kb[l], idx, 0);      // tangent: u @ W_l^T
+        for (int l = 8; l >= 1; --l, ++idx) sw_layer(prog, k, L.nnb_off[l], 2, 128, 4, idx, 0);               // reverse: dz @ W_l
+        sw_layer(prog, k, L.nnb_off[0], 1, 64, 4, idx, 0);
+        prog.n_steps = k;
+        TimingScope ts(s, TT_SDF_BWD);
+        bwd16_kernel<<<std::min(n_tiles, sm_count()), THREADS, SW_SMEM_BYTES, s>>>(p, prog);
+    }
+    count_launch();
+    HN_CHECK_LAUNCH();
+    if (!grad) return HN_OK;
+    // ---- all weight / bias gradients from the tiles the two sweep kernels left in HBM ------------------------------------
+    Dw16Params dp;
+    DwReduceParams rp;
+    dp.n_tiles = n_tiles; dp.part = part; rp.part = part;
+    int k = 0;
+    for (int l = 0; l < 8; ++l, ++k) {
+        Dw16Job& j = dp.job[k];
+        const int out = m->out_dim[l], in = m->in_dim[l];
+        j.P[0] = DZ16[l]; j.P[1] = S.D16[l];
+        j.Q[0] = l == 0 ? S.E16 : S.A16[l - 1];          // A16[3] holds the skip input [h3 | e]
+        j.Q[1] = l == 0 ? UE16 : U16[l - 1];             // U16[3] holds [u3 | ue]
+        j.n_pairs = 2;
+        j.q_chunks = l == 0 ? 8 : 32;
+        j.n_mma = l == 0 ? 64 : 256;
+        j.db = grad->db[l]; j.p_cols = out;
+        rp.job[k] = reduce_job(grad->dW[l], m->ld[l], 0, out, in);
+    }
+    if (d_feat) {
+        Dw16Job& j = dp.job[k];
+        j.P[0] = DF16; j.Q[0] = S.A16[7]; j.P[1] = DF16; j.Q[1] = S.A16[7];
+        j.n_pairs = 1; j.q_chunks = 32; j.n_mma = 256;
+        j.db = grad->db[8] ? grad->db[8] + 1 : nullptr; j.p_cols = 256;
+        rp.job[k] = reduce_job(grad->dW[8], m->ld[8], 1, 256, 256);
+        ++k;
+    }
+    dp.n_jobs = k;
+    HN_PROPAGATE(launch_dw16(dp, rp, s));
+    if (grad->dW[8] || grad->db[8])
+        HN_PROPAGATE(launch_out_row0_grad16(S.A16[7], U16[7], d_sdf, n, n_tiles, inv_scale, grad->dW[8], grad->db[8], s));
+    return HN_OK;
+}
+
+}  // namespace chain
+}  // namespace hn

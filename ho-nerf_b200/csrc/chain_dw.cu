@@ -388,6 +388,13 @@ __global__ void dw_reduce_kernel(const __grid_constant__ DwReduceParams p) {
         if (c + i < jb.cols) dst[c + i < jb.csplit ? jb.col0 + c + i : jb.col1 + (c + i - jb.csplit)] += a[i];
 }
 
+int launch_dw_reduce(const DwReduceParams& r, int n_jobs, cudaStream_t s) {
+    dw_reduce_kernel<<<dim3(65536 / 4 / 256, n_jobs), 256, 0, s>>>(r);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
 int64_t dw_part_floats(int n_jobs) { return (int64_t)n_jobs * DW_SPLITS * 65536; }
 
 int launch_dw(const DwParams& p, const DwReduceParams& r, cudaStream_t s) {
@@ -402,10 +409,7 @@ int launch_dw(const DwParams& p, const DwReduceParams& r, cudaStream_t s) {
     }
     count_launch();
     HN_CHECK_LAUNCH();
-    dw_reduce_kernel<<<dim3(65536 / 4 / 256, p.n_jobs), 256, 0, s>>>(r);
-    count_launch();
-    HN_CHECK_LAUNCH();
-    return HN_OK;
+    return launch_dw_reduce(r, p.n_jobs, s);
 }
 
 }  // namespace chain

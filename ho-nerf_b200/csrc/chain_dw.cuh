@@ -48,6 +48,7 @@ struct DwReduceParams {
 
 int64_t dw_part_floats(int n_jobs);
 int launch_dw(const DwParams& p, const DwReduceParams& r, cudaStream_t s);
+int launch_dw_reduce(const DwReduceParams& r, int n_jobs, cudaStream_t s);
 
 }  // namespace chain
 }  // namespace hn

@@ -110,7 +110,10 @@ int pack_batch_flush(cudaStream_t stream) {
 int launch_pack_b(const float* src, int64_t ld, PackMap map, int rows, int cols, int n_pad, int kblocks, uint8_t* dst,
                   cudaStream_t stream, bool lo16) {
     if (g_batching) {
-        HN_REQUIRE(g_jobs.n < PACK_MAX_JOBS, "pack batch overflow");
+        if (g_jobs.n == PACK_MAX_JOBS) {            // a full batch: launch it and keep recording
+            HN_PROPAGATE(pack_batch_flush(stream));
+            g_batching = true;
+        }
         g_jobs.job[g_jobs.n++] = PackJob{src, ld, map, rows, cols, n_pad, kblocks, dst, lo16 ? 1 : 0};
         return HN_OK;
     }

@@ -293,6 +293,7 @@ int hn_sdf_hand_sdf(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
                     int64_t pts_per_frame, float* sdf, float* ws, int64_t ws_floats, int precision,
                     hn_stream_t stream) {
     HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_sdf: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
     if (n == 0) return HN_OK;
@@ -315,6 +316,7 @@ int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
                     float* xyz_feature, int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
                     hn_stream_t stream) {
     HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
     if (n == 0) return HN_OK;
@@ -383,6 +385,7 @@ int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
                     float* d_T_pose, const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision,
                     hn_stream_t stream) {
     HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_bwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
     if (n == 0) return HN_OK;
@@ -581,6 +584,7 @@ int hn_color_hand_fwd(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_
                       int64_t ld_feat, const float* normal, int64_t n, float* rgb, float* stash,
                       int64_t stash_floats, int precision, hn_stream_t stream) {
     HN_PROPAGATE(check_color_hand_mlp(mlp));
+    precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_color_hand_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
@@ -612,6 +616,7 @@ int hn_color_hand_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float*
                       float* d_xyz_feature, int64_t ld_dxyz, float* d_feat, int64_t ld_dfeat, float* d_normal,
                       const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision, hn_stream_t stream) {
     HN_PROPAGATE(check_color_hand_mlp(mlp));
+    precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_color_hand_bwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;

@@ -29,6 +29,13 @@ int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const 
 int launch_sdf_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
                    const float* d_feat, int64_t ld_dfeat, const float* d_normal, float* d_pts, float* ws,
                    cudaStream_t s);
+// chain16_obj.cu (HN_TC_MIXED16)
+int64_t m16_stash_floats(int64_t n);
+int64_t m16_bwd_ws_floats(int64_t n);
+int launch_m16_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat, int64_t ld_feat,
+                   float* normal, float* stash, cudaStream_t s);
+int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf, const float* d_feat,
+                   int64_t ld_dfeat, const float* d_normal, float* d_pts, const hn_mlp_grad_t* grad, float* ws, cudaStream_t s);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -221,13 +228,13 @@ using namespace hn;
 extern "C" {
 
 // sized for the tiled layout of the HN_TC_BF16X3 path (n padded to whole 128-point tiles)
-int64_t hn_sdf_obj_stash_floats(int64_t n) { return std::max<int64_t>(n * ObjSdfStash::kFloatsPerPoint, chain::stash_floats(n)); }
+int64_t hn_sdf_obj_stash_floats(int64_t n) { return std::max<int64_t>(std::max<int64_t>(n * ObjSdfStash::kFloatsPerPoint, chain::stash_floats(n)), chain::m16_stash_floats(n)); }
 
 int64_t hn_sdf_obj_ws_floats(int64_t n, int kind) {
     switch (kind) {
         case HN_WS_SDF_ONLY: return n * (64 + 3 * 256);       // E, two ping-pong H, A4
         case HN_WS_FWD: return 4;                              // nothing beyond the stash
-        case HN_WS_BWD: return std::max<int64_t>(n * (64 + 2 * 256 + 256 + 260 + 2 * 256 + 64), chain::bwd_ws_floats(n));
+        case HN_WS_BWD: return std::max<int64_t>(std::max<int64_t>(n * (64 + 2 * 256 + 256 + 260 + 2 * 256 + 64), chain::bwd_ws_floats(n)), chain::m16_bwd_ws_floats(n));
         default: return -1;
     }
 }
@@ -239,7 +246,7 @@ int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    if (precision == HN_TC_BF16X3) {
+    if (precision == HN_TC_BF16X3 || precision == HN_TC_MIXED16) {
         HN_REQUIRE(pts && sdf, "hn_sdf_obj_sdf: null pointer");
         return chain::launch_sdf_only(mlp, pts, n, inv_scale, sdf, s);
     }
@@ -270,6 +277,7 @@ int hn_sdf_obj_fwd(const hn_mlp_t* mlp, const float* pts, int64_t n, float inv_s
     HN_REQUIRE(ld_feat >= 256 && ld_feat % 4 == 0 && aligned16(feat), "feat must be 16B aligned with ld%%4==0");
     cudaStream_t s = (cudaStream_t)stream;
     if (precision == HN_TC_BF16X3) return chain::launch_sdf_fwd(mlp, pts, n, inv_scale, sdf, feat, ld_feat, normal, stash, s);
+    if (precision == HN_TC_MIXED16) return chain::launch_m16_fwd(mlp, pts, n, inv_scale, sdf, feat, ld_feat, normal, stash, s);
     ObjSdfStash st(stash, n);
     HN_PROPAGATE(obj_trunk_fwd(mlp, pts, n, st.E, st.H, s, precision));
     // output layer: column 0 -> sdf, columns 1..256 -> feature
@@ -325,6 +333,8 @@ int hn_sdf_obj_bwd(const hn_mlp_t* mlp, int64_t n, float inv_scale, float* stash
     HN_REQUIRE(!d_feat || (ld_dfeat >= 256), "bad ld_dfeat");
     cudaStream_t s = (cudaStream_t)stream;
     ObjSdfStash st(stash, n);
+    if (precision == HN_TC_MIXED16)
+        return chain::launch_m16_bwd(mlp, n, inv_scale, stash, d_sdf, d_feat, ld_dfeat, d_normal, d_pts, grad, ws, s);
     if (precision == HN_TC_BF16X3) {
         // fused tangent + reverse sweeps, then every weight-gradient contraction in one launch over the operands
         // the sweeps left in ws
@@ -517,6 +527,7 @@ int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs, c
                      int64_t ld_feat, const float* normal, int64_t n, float* rgb, float* stash,
                      int64_t stash_floats, int precision, hn_stream_t stream) {
     HN_PROPAGATE(check_color_obj_mlp(mlp));
+    precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_color_obj_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;
@@ -550,6 +561,7 @@ int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* 
                      const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision,
                      hn_stream_t stream) {
     HN_PROPAGATE(check_color_obj_mlp(mlp));
+    precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_color_obj_bwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
     if (n == 0) return HN_OK;

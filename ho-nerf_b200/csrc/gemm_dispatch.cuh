@@ -17,8 +17,10 @@ namespace hn {
 enum GemmRole { ROLE_VALUE = 0, ROLE_OTHER = 1 };
 
 inline bool precision_supported(int p) {
-    return p == HN_SIMT_FP32 || p == HN_TC_TF32 || p == HN_TC_TF32X3 || p == HN_TC_BF16X3;
+    return p == HN_SIMT_FP32 || p == HN_TC_TF32 || p == HN_TC_TF32X3 || p == HN_TC_BF16X3 || p == HN_TC_MIXED16;
 }
+// HN_TC_MIXED16 only exists for the object SDF field (chain16_obj.cu); every other entry point runs HN_TC_BF16X3
+inline int base_precision(int p) { return p == HN_TC_MIXED16 ? HN_TC_BF16X3 : p; }
 
 // C = epi(A @ W^T)
 template <int EPI>

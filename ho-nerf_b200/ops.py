@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import HN_SIMT_FP32, HN_WS_BWD, HN_WS_SDF_ONLY, check, hn_mlp_grad_t, hn_mlp_t, lib
 
 _PRECISIONS = {"simt_fp32": _lib.HN_SIMT_FP32, "tc_tf32": _lib.HN_TC_TF32, "tc_tf32x3": _lib.HN_TC_TF32X3,
-               "tc_bf16x3": _lib.HN_TC_BF16X3}
+               "tc_bf16x3": _lib.HN_TC_BF16X3, "tc_mixed16": _lib.HN_TC_MIXED16}
 # Product default: the fused tcgen05 chain kernels.  'simt_fp32' is the verification path (the north star's
 # "fp32 SIMT path kept for verification"); HONERF_PRECISION overrides the default at import.
 import os as _os
@@ -19,7 +19,8 @@ _default_precision = _PRECISIONS[_os.environ.get("HONERF_PRECISION", "tc_bf16x3"
 
 def set_default_precision(name):
     """'simt_fp32' (verification path) | 'tc_tf32' | 'tc_tf32x3' (split TF32 operands, per-layer kernels) |
-    'tc_bf16x3' (fused tile-chain kernels, split bf16 operands)."""
+    'tc_bf16x3' (fused tile-chain kernels, split bf16 operands) | 'tc_mixed16' (object SDF field: fp16x3 value trunk,
+    single-16-bit-operand sweeps in tensor memory, 16-bit activation stash; everything else as 'tc_bf16x3')."""
     global _default_precision
     _default_precision = _PRECISIONS[name]
 

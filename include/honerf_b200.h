@@ -41,8 +41,14 @@ enum hn_status { HN_OK = 0, HN_ERR_ARG = -1, HN_ERR_CUDA = -2, HN_ERR_UNSUPPORTE
  *                between layers as split (hi+lo) bf16 operands, three bf16 MMAs per product, weights
  *                streamed from the pre-packed chain buffer (hn_*_chain_pack).  ~16 mantissa bits:
  *                8e-6 abs on the SDF, 5e-5 relative on weight gradients (oracle/analytic.py).
- *                Entry points without a chain kernel run their HN_TC_TF32X3 path. */
-enum hn_precision { HN_SIMT_FP32 = 0, HN_TC_TF32 = 1, HN_TC_TF32X3 = 2, HN_TC_BF16X3 = 3 };
+ *                Entry points without a chain kernel run their HN_TC_TF32X3 path.
+ *   HN_TC_MIXED16 the object SDF field (utils/fields.py:316-347 and its double backward) with a 16-bit activation
+ *                stash and tensor-memory-resident operands (csrc/chain16*.cu): the value trunk keeps three fp16 MMAs
+ *                per product (sdf / feature ~2e-6), the normal / tangent / reverse sweeps round their A operand to one
+ *                16-bit value (two MMAs per product), the weight gradients use the stored bf16 operands (one MMA):
+ *                normals ~4e-4, weight gradients <= 6e-3 relative (north star: 1e-2).  Every other entry point runs
+ *                its HN_TC_BF16X3 path. */
+enum hn_precision { HN_SIMT_FP32 = 0, HN_TC_TF32 = 1, HN_TC_TF32X3 = 2, HN_TC_BF16X3 = 3, HN_TC_MIXED16 = 4 };
 
 HN_API const char* hn_last_error(void);
 HN_API int hn_version(void);
@@ -425,6 +431,12 @@ HN_API int hn_tc_gemm_ts_test(const void* A, const void* B, int M, int N, int K,
  * points, P [n, out] and Q [n, in] fp32: row-major (x_tiled = 0, leading dimension ld), tiled (x_tiled = 1:
  * [tile][col/4][128][4], n padded to 128) or column-major tiles (x_tiled = 2: [tile][ld columns][128 rows]);
  * db [out] += column sums of P (may be NULL); part: workspace of >= 16 * 65536 floats. */
+/* HN_TC_MIXED16 weight-gradient kernel on fp32 operands rounded to bf16 dW-ready tiles (diagnostics / tests):
+ * C[out, in] = P^T Q (+ P2^T Q2), db = column sums of P.  `tiles`: 4 * round_up(n,128) * 512 bytes of workspace. */
+HN_API int hn_dw16_test(const float* P, int out, const float* Q, int in, const float* P2, const float* Q2, int64_t n,
+                        float* C, int64_t ldc, float* db, void* tiles, int64_t tiles_bytes, float* part,
+                        int64_t part_floats, hn_stream_t stream);
+HN_API int hn_dw16_set_debug(int swap_lbo_sbo);
 HN_API int hn_dw_test(const float* P, int64_t ldp, int p_tiled, int out, const float* Q, int64_t ldq,
                       int q_tiled, int in, const float* P2, const float* Q2, int64_t n, float* C,
                       int64_t ldc, float* db, float* part, int64_t part_floats, hn_stream_t stream);
