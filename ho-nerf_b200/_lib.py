@@ -102,6 +102,7 @@ PROTOTYPES = {
     "hn_dw_test": (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "hn_dw16_test": (c_int, [P, c_int, P, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P, c_int64, P]),
     "hn_dw16_set_debug": (c_int, [c_int]),
+    "hn_chain16_set_debug": (c_int, [P]),
     "hn_tc_gemm_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "hn_tc_gemm_ts_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
     "hn_gemm_test": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),

@@ -59,13 +59,20 @@ __device__ __forceinline__ float softplus100_em(float z, float& em) {
 }
 
 // ---- sweep kernels: A operand in tensor memory, double-buffered -------------------------------------------------------
+// Shared memory: weight ring | two input slots | one fp32 scratch tile.  The 16-bit stash tiles an epilogue needs (EM,
+// D16) are pulled in by a dedicated producer warp with bulk copies, one N-half (128 columns x 128 points x up to two
+// arrays = 64 KB) ahead of the epilogue that reads them, so the epilogue warps never wait on a global load.
+constexpr int SW_THREADS = 64 + EPI_THREADS + 32;   // weight producer, MMA issuer, 16 epilogue warps, input producer
 constexpr int SW_STAGE_BYTES = 128 * 128;        // one weight stage: [128 rows x 64 k] 16-bit
-constexpr int SW_STAGES = 9;
-constexpr int SW_SCR_LD = 65;                    // fp32 scratch tiles [128][65] (padded: conflict-free columns)
+constexpr int SW_STAGES = 4;
+constexpr int SW_IN_OFF = SW_STAGES * SW_STAGE_BYTES;
+constexpr int SW_IN_ARRAY_BYTES = 128 * 128 * 2; // one array's N-half: [2 point halves][16 chunks][64 points][16 B]
+constexpr int SW_IN_SLOT_BYTES = 2 * SW_IN_ARRAY_BYTES;
+constexpr int SW_SCR_LD = 65;                    // fp32 scratch tile [128][65] (padded: conflict-free columns)
 constexpr int SW_SCR_BYTES = TILE_M * SW_SCR_LD * 4;
-constexpr int SW_SCR0_OFF = SW_STAGES * SW_STAGE_BYTES;
-constexpr int SW_SCR1_OFF = SW_SCR0_OFF + SW_SCR_BYTES;
-constexpr int SW_SMEM_BYTES = SW_SCR1_OFF + SW_SCR_BYTES + 1024;
+constexpr int SW_SKIP_OFF = SW_IN_OFF + 2 * SW_IN_SLOT_BYTES;
+constexpr int SW_SMEM_BYTES = SW_SKIP_OFF + SW_SCR_BYTES + 1024;
+static_assert(SW_SMEM_BYTES <= 232448, "sweep kernels: shared memory budget");
 constexpr uint32_t SW_A0 = 256, SW_A1 = 384;     // TMEM columns of the two A buffers (accumulator: [0, 256))
 constexpr int SW_MAX_STEPS = 36;
 
@@ -77,18 +84,33 @@ struct SwStep {
     uint8_t a_buf : 1;
     uint8_t wait_a : 1;      // first half of a layer: wait until the epilogue has published the A operand
     uint8_t f16 : 1;         // fp16 operands (normal sweep) instead of bf16
-    uint8_t passes : 2;      // 2: A (B_hi + B_lo);  1: A B_hi
+    uint8_t passes : 2;      // weight stages per k-block: 2 = B_hi, B_lo;  1 = B_hi only
+    uint8_t a_pair : 1;      // the A operand is a hi (SW_A0) + lo (SW_A1) pair: A_lo B_hi + A_hi B_hi + A_hi B_lo (three MMAs per
+                             // product, no double buffering); else ONE 16-bit operand in buffer a_buf
     uint16_t acc_col;
 };
 struct SwProgram {
     int n_steps;
     SwStep step[SW_MAX_STEPS];
 };
+// inputs of one epilogue half-step: N-half `hf` of up to two T16 arrays (pointers to tile 0; b may be NULL)
+struct SwInEvent {
+    const uint8_t* a;
+    const uint8_t* b;
+};
+struct SwInputs {
+    int n_events;            // per tile; event e uses slot e & 1 and N-half e & 1
+    SwInEvent ev[SW_MAX_STEPS];
+};
 struct SwBarriers {
     uint64_t full[SW_STAGES];
     uint64_t empty[SW_STAGES];
+    uint64_t in_full[2];
+    uint64_t in_empty[2];
     uint64_t a_ready;
-    uint64_t acc_full;
+    // one barrier per N-half: both halves of a layer can complete before a slow epilogue thread has looked at the first
+    // one, and a single barrier flipping twice would alias its parity (the thread would wait forever)
+    uint64_t acc_full[2];
     uint32_t tmem_base;
 };
 
@@ -101,8 +123,13 @@ __device__ __forceinline__ uint8_t* sw_setup(uint8_t* smem_raw, SwBarriers* bar)
             tc::mbar_init(&bar->full[s], 1);
             tc::mbar_init(&bar->empty[s], 1);
         }
+        for (int s = 0; s < 2; ++s) {
+            tc::mbar_init(&bar->in_full[s], 1);
+            tc::mbar_init(&bar->in_empty[s], EPI_THREADS);
+        }
         tc::mbar_init(&bar->a_ready, EPI_THREADS);
-        tc::mbar_init(&bar->acc_full, 1);
+        tc::mbar_init(&bar->acc_full[0], 1);
+        tc::mbar_init(&bar->acc_full[1], 1);
         tc::mbar_fence_init();
     }
     tc::tc_fence_before_sync();
@@ -116,12 +143,23 @@ __device__ __forceinline__ void sw_teardown(SwBarriers* bar) {
     if ((threadIdx.x >> 5) == 0) tc::tmem_dealloc(bar->tmem_base, 512);
 }
 
+// Diagnostics (hn_chain16_set_debug): a host-mapped buffer of [4 kernels][4 instances][148 CTAs][8] words; every role
+// of every CTA records (tile << 8 | step) as it goes, 0xffffffff when done -- readable from the host while a kernel hangs.
+extern uint32_t* g_m16_dbg;
+__device__ __forceinline__ void dbg_mark(uint32_t* dbg, int role, uint32_t v) {
+    if (dbg) {
+        *reinterpret_cast<volatile uint32_t*>(dbg + blockIdx.x * 8 + role) = v;
+    }
+}
+uint32_t* dbg_slot(int kernel_id);
+
 // warp 0, lane 0
 __device__ __forceinline__ void sw_producer(const SwProgram& prog, const uint8_t* __restrict__ chain_w, uint8_t* smem,
-                                            SwBarriers* bar, int n_my_tiles) {
+                                            SwBarriers* bar, int n_my_tiles, uint32_t* dbg = nullptr) {
     uint32_t stage = 0, phase = 0;
     for (int t = 0; t < n_my_tiles; ++t)
         for (int s = 0; s < prog.n_steps; ++s) {
+            dbg_mark(dbg, 0, (uint32_t)(t << 8 | s));
             const SwStep st = prog.step[s];
             const uint32_t bytes = (uint32_t)st.n_mma * 128u;
             const uint8_t* src = chain_w + st.b_off;
@@ -133,43 +171,114 @@ __device__ __forceinline__ void sw_producer(const SwProgram& prog, const uint8_t
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
                 }
         }
+    dbg_mark(dbg, 0, 0xffffffffu);
+}
+
+// warp 18, lane 0: the stash tiles of every epilogue half-step, one half-step ahead
+__device__ __forceinline__ void sw_in_producer(const SwInputs& in, uint8_t* smem, SwBarriers* bar, int n_my_tiles,
+                                               uint32_t* dbg = nullptr) {
+    uint32_t par[2] = {0u, 0u};
+    for (int t = 0; t < n_my_tiles; ++t) {
+        const size_t tb = ((size_t)blockIdx.x + (size_t)t * gridDim.x) * T16_TILE_BYTES;
+        for (int e = 0; e < in.n_events; ++e) {
+            dbg_mark(dbg, 3, (uint32_t)(t << 8 | e));
+            const int slot = e & 1;
+            const SwInEvent ev = in.ev[e];
+            tc::mbar_wait(&bar->in_empty[slot], par[slot] ^ 1u);
+            par[slot] ^= 1u;
+            tc::mbar_arrive_expect_tx(&bar->in_full[slot], ev.b ? 2u * SW_IN_ARRAY_BYTES : (uint32_t)SW_IN_ARRAY_BYTES);
+            uint8_t* dst = smem + SW_IN_OFF + slot * SW_IN_SLOT_BYTES;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {       // point halves: 16 chunks x 1 KB each, contiguous in the tile
+                tc::bulk_g2s(dst + ph * 16384, ev.a + tb + (size_t)ph * 32768 + (size_t)slot * 16384, 16384, &bar->in_full[slot]);
+                if (ev.b)
+                    tc::bulk_g2s(dst + SW_IN_ARRAY_BYTES + ph * 16384, ev.b + tb + (size_t)ph * 32768 + (size_t)slot * 16384, 16384,
+                                 &bar->in_full[slot]);
+            }
+        }
+    }
+    dbg_mark(dbg, 3, 0xffffffffu);
+}
+// epilogue side: wait for / release the input slot of N-half hf
+__device__ __forceinline__ void sw_in_wait(SwBarriers* bar, int hf, uint32_t* par) {
+    tc::mbar_wait(&bar->in_full[hf], par[hf]);
+    par[hf] ^= 1u;
+}
+__device__ __forceinline__ void sw_in_release(SwBarriers* bar, int hf) { tc::mbar_arrive(&bar->in_empty[hf]); }
+// the 16-byte chunk of (row, column c) of array `arr` in input slot hf (c inside N-half hf)
+__device__ __forceinline__ uint4 sw_in_ld(const uint8_t* smem, int hf, int arr, int row, int c) {
+    return *reinterpret_cast<const uint4*>(smem + SW_IN_OFF + hf * SW_IN_SLOT_BYTES + arr * SW_IN_ARRAY_BYTES + (row >> 6) * 16384 +
+                                           ((c >> 3) & 15) * 1024 + (row & 63) * 16);
+}
+
+// [x, sin / cos(2^k x_c)] encoding (utils/fields.py:13-20): column `col` of its tangent J_e(x) dn, from the stored encoding
+// e (column-major tile entry of the point: e[128 j] = e_j)
+__device__ __forceinline__ float enc_tangent_col(const float* __restrict__ e, float dn0, float dn1, float dn2, int col) {
+    if (col < 3) return col == 0 ? dn0 : (col == 1 ? dn1 : dn2);
+    if (col >= 63) return 0.0f;
+    const int jj = col - 3, c = jj / 20, r = jj - c * 20, k = r >= 10 ? r - 10 : r;
+    const float f = (float)(1 << k);
+    // column 3 + 20 c + k = sin(2^k x_c) -> f cos dn_c;  column 3 + 20 c + 10 + k = cos -> -f sin dn_c
+    const float other = e[(r >= 10 ? col - 10 : col + 10) * TILE_M];
+    return (r >= 10 ? -f : f) * other * (c == 0 ? dn0 : (c == 1 ? dn1 : dn2));
 }
 
 // warp 1, lane 0
-__device__ __forceinline__ void sw_mma(const SwProgram& prog, uint8_t* smem, SwBarriers* bar, int n_my_tiles) {
+__device__ __forceinline__ void sw_mma(const SwProgram& prog, uint8_t* smem, SwBarriers* bar, int n_my_tiles,
+                                       uint32_t* dbg = nullptr) {
     const uint32_t tmem = bar->tmem_base;
     const uint32_t ring = tc::smem_u32(smem);
     uint32_t stage = 0, phase = 0, a_par = 0;
+    long long t_a = 0, t_w = 0, tt;
+    const long long t0 = clock64();
     for (int t = 0; t < n_my_tiles; ++t)
         for (int s = 0; s < prog.n_steps; ++s) {
+            dbg_mark(dbg, 1, (uint32_t)(t << 8 | s));
             const SwStep st = prog.step[s];
             const uint32_t idesc = tc::make_idesc(st.f16 ? tc::FMT_F16 : tc::FMT_BF16, 128, st.n_mma);
             const uint32_t d = tmem + st.acc_col;
             const uint32_t a = tmem + (st.a_buf ? SW_A1 : SW_A0);
             if (st.wait_a) {
+                tt = clock64();
                 tc::mbar_wait(&bar->a_ready, a_par);
+                t_a += clock64() - tt;
                 a_par ^= 1u;
                 tc::tc_fence_after_sync();
             }
             for (int kb = 0; kb < st.kblocks; ++kb)
                 for (int ps = 0; ps < st.passes; ++ps) {
+                    tt = clock64();
                     tc::mbar_wait(&bar->full[stage], phase);
+                    t_w += clock64() - tt;
                     tc::tc_fence_after_sync();
                     const uint64_t dB = tc::make_smem_desc_sw128(ring + stage * SW_STAGE_BYTES);
+                    if (st.a_pair) {
+                        const uint32_t ah = tmem + SW_A0 + (uint32_t)kb * 32u, al = tmem + SW_A1 + (uint32_t)kb * 32u;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc::umma_f16_ts(d, a + (uint32_t)kb * 32u + 8u * k, dB + 2 * k, idesc, (kb | k | ps) != 0);
+                        for (int k = 0; k < 4; ++k) {
+                            if (ps == 0) tc::umma_f16_ts(d, al + 8u * k, dB + 2 * k, idesc, (kb | k) != 0);
+                            tc::umma_f16_ts(d, ah + 8u * k, dB + 2 * k, idesc, 1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc::umma_f16_ts(d, a + (uint32_t)kb * 32u + 8u * k, dB + 2 * k, idesc, (kb | k | ps) != 0);
+                    }
                     tc::umma_commit(&bar->empty[stage]);
                     if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
                 }
-            tc::umma_commit(&bar->acc_full);
+            tc::umma_commit(&bar->acc_full[st.acc_col ? 1 : 0]);
         }
+    dbg_mark(dbg, 1, 0xffffffffu);
+    dbg_mark(dbg, 4, (uint32_t)(t_a >> 4));                  // cycles / 16: MMA issuer waiting for the A operand
+    dbg_mark(dbg, 5, (uint32_t)(t_w >> 4));                  // ... for weight stages
+    dbg_mark(dbg, 6, (uint32_t)((clock64() - t0) >> 4));     // ... total
 }
 
 // epilogue-side handshake
-__device__ __forceinline__ void sw_wait_acc(SwBarriers* bar, uint32_t& par) {
-    tc::mbar_wait(&bar->acc_full, par);
-    par ^= 1u;
+__device__ __forceinline__ void sw_wait_acc(SwBarriers* bar, int hf, uint32_t* par) {
+    tc::mbar_wait(&bar->acc_full[hf], par[hf]);
+    par[hf] ^= 1u;
     tc::tc_fence_after_sync();
 }
 __device__ __forceinline__ void sw_publish(SwBarriers* bar) {

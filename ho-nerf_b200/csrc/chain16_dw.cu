@@ -44,6 +44,7 @@ __host__ __device__ constexpr uint32_t make_idesc_mn16(uint32_t M, uint32_t N) {
 struct Dw16Args {
     Dw16Params p;
     int swap;
+    uint32_t* dbg;
 };
 
 __global__ void __launch_bounds__(D16_THREADS, 1) dw16_kernel(const __grid_constant__ Dw16Args a) {
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(D16_THREADS, 1) dw16_kernel(const __grid_const
             for (int t = t0; t < t1; ++t)
                 for (int h = 0; h < 2; ++h)
                     for (int pr = 0; pr < job.n_pairs; ++pr) {
+                        dbg_mark(a.dbg, 0, (uint32_t)(t << 8 | h << 1 | pr));
                         tc::mbar_wait(&empty[stage], phase ^ 1u);
                         tc::mbar_arrive_expect_tx(&full[stage], (uint32_t)D16_P_BYTES + q_bytes);
                         uint8_t* dst = smem + stage * D16_STAGE_BYTES;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(D16_THREADS, 1) dw16_kernel(const __grid_const
             const uint32_t lbo = a.swap ? D16_SBO : D16_LBO, sbo = a.swap ? D16_LBO : D16_SBO;
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < n_iters; ++it) {
+                dbg_mark(a.dbg, 1, (uint32_t)it);
                 tc::mbar_wait(&full[stage], phase);
                 tc::tc_fence_after_sync();
                 const uint32_t P = tc::smem_u32(smem) + stage * D16_STAGE_BYTES, Q = P + D16_P_BYTES;
@@ -176,6 +179,7 @@ __global__ void __launch_bounds__(D16_THREADS, 1) dw16_kernel(const __grid_const
             }
         }
     }
+    if (lane == 0 && warp < 3) dbg_mark(a.dbg, warp, 0xffffffffu);
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
@@ -194,6 +198,7 @@ int launch_dw16(const Dw16Params& p, const DwReduceParams& r, cudaStream_t s) {
     Dw16Args a;
     a.p = p;
     a.swap = g_dw16_swap;
+    a.dbg = dbg_slot(3);
     {
         TimingScope ts(s, TT_DW);
         dw16_kernel<<<p.n_jobs * DW_SPLITS, D16_THREADS, D16_SMEM_BYTES, s>>>(a);

@@ -32,11 +32,12 @@ struct TrBarriers {
     uint64_t full[TR_STAGES];
     uint64_t empty[TR_STAGES];
     uint64_t a_ready;
-    uint64_t acc_full;
+    uint64_t acc_full[2];    // one per N-half (see SwBarriers)
     uint32_t tmem_base;
 };
 
 struct Trunk16Params {
+    uint32_t* dbg;
     const float* pts;
     int64_t n;
     float inv_scale;
@@ -45,7 +46,8 @@ struct Trunk16Params {
     int64_t ld_feat;
     float* E;            // fp32 column-major [64][128] tiles (eoff)
     uint8_t* E16;        // bf16 T16N tiles
-    uint8_t* EM[8];      // fp16 T16 tiles
+    uint8_t* EM[8];      // fp16 T16 tiles: em = exp(-100 h) rounded to fp16
+    uint8_t* EML[8];     // fp16 T16 tiles: fp16(em - fp16(em)), read by the normal sweep only
     uint8_t* A16[8];     // bf16 T16 tiles
     const uint8_t* chain;
     const float* bias[9];
@@ -68,7 +70,8 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
             tc::mbar_init(&bar.empty[s], 1);
         }
         tc::mbar_init(&bar.a_ready, EPI_THREADS);
-        tc::mbar_init(&bar.acc_full, 1);
+        tc::mbar_init(&bar.acc_full[0], 1);
+        tc::mbar_init(&bar.acc_full[1], 1);
         tc::mbar_fence_init();
     }
     tc::tc_fence_before_sync();
@@ -99,6 +102,7 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
             uint32_t stage = 0, phase = 0, a_par = 0;
             for (int t = 0; t < n_my_tiles; ++t)
                 for (int s = 0; s < prog.n_steps; ++s) {
+                    dbg_mark(p.dbg, 1, (uint32_t)(t << 8 | s));
                     const Step st = prog.step[s];
                     const uint32_t d = tmem + st.acc_col;
                     if (!st.no_wait) {
@@ -126,21 +130,22 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
                         tc::umma_commit(&bar.empty[stage]);
                         if (++stage == TR_STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    tc::umma_commit(&bar.acc_full);
+                    tc::umma_commit(&bar.acc_full[st.acc_col ? 1 : 0]);
                 }
+            dbg_mark(p.dbg, 1, 0xffffffffu);
         }
     } else {
         const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
-        uint32_t acc_par = 0;
+        uint32_t acc_par[2] = {0u, 0u};
         auto publish = [&]() {
             tc::tmem_st_wait();
             tc::tc_fence_before_sync();
             tc::mbar_arrive(&bar.a_ready);
         };
-        auto wait_acc = [&]() {
-            tc::mbar_wait(&bar.acc_full, acc_par);
-            acc_par ^= 1u;
+        auto wait_acc = [&](int hf) {
+            tc::mbar_wait(&bar.acc_full[hf], acc_par[hf]);
+            acc_par[hf] ^= 1u;
             tc::tc_fence_after_sync();
         };
         auto store_a = [&](int col0, const uint32_t* hi, const uint32_t* lo) {
@@ -156,9 +161,11 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
             // 8 columns [c, c + 8) of layer l: stash chunks (EM fp16, A16 bf16) + fp16 hi / lo words of the next A operand
             auto emit8 = [&](int l, int c, const float* h, const float* em, uint32_t* hi4, uint32_t* lo4) {
                 const uint32_t off = t16_off(row, c >> 3);
-                uint4 q;
-                q.x = pack_f16x2(em[0], em[1]); q.y = pack_f16x2(em[2], em[3]); q.z = pack_f16x2(em[4], em[5]); q.w = pack_f16x2(em[6], em[7]);
+                uint4 q, ql;
+                split2_lo16(em[0], em[1], q.x, ql.x); split2_lo16(em[2], em[3], q.y, ql.y);
+                split2_lo16(em[4], em[5], q.z, ql.z); split2_lo16(em[6], em[7], q.w, ql.w);
                 stg16(p.EM[l] + (size_t)tile * T16_TILE_BYTES + off, q);
+                stg16(p.EML[l] + (size_t)tile * T16_TILE_BYTES + off, ql);
                 q.x = pack_bf16x2(h[0], h[1]); q.y = pack_bf16x2(h[2], h[3]); q.z = pack_bf16x2(h[4], h[5]); q.w = pack_bf16x2(h[6], h[7]);
                 stg16(p.A16[l] + (size_t)tile * T16_TILE_BYTES + off, q);
 #pragma unroll
@@ -222,11 +229,12 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
             float head = 0.0f;
             for (int l = 0; l < 8; ++l) {
                 uint32_t hh[16], hl[16];
+                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | l));
                 // ---- first half (columns cg*32 ..), under the second half's MMAs ----------------------------------------
-                wait_acc();
+                wait_acc(0);
                 act_half(l, cg * 32, hh, hl, head);
                 // ---- second half: every MMA of the layer has read A, it may be overwritten ---------------------------------
-                wait_acc();
+                wait_acc(1);
                 store_a(cg * 32, hh, hl);
                 const int col0 = 128 + cg * 32;
                 if (l == 3 && col0 >= 192) {
@@ -265,7 +273,7 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
             }
             // ---- feature head: rows 1..256 of the output layer, no activation ----------------------------------------------
             for (int hf = 0; hf < 2; ++hf) {
-                wait_acc();
+                wait_acc(hf);
                 const int col0 = 128 * hf + cg * 32;
                 float v[32];
                 acc_load32(tmem, row, col0, v);
@@ -280,6 +288,7 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
             }
             tc::tc_fence_before_sync();       // the accumulator reads above precede the next tile's MMAs (ordered by its a_ready)
         }
+        if (threadIdx.x == 64) dbg_mark(p.dbg, 2, 0xffffffffu);
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -290,10 +299,10 @@ trunk16_kernel(const __grid_constant__ Trunk16Params p, const __grid_constant__ 
 // normal sweep
 // ------------------------------------------------------------------------------------------------------------------
 struct Nsweep16Params {
+    uint32_t* dbg;
     int64_t n;
     float inv_scale;
     const float* E;
-    const uint8_t* EM[8];
     uint8_t* D16[8];
     float* EB;
     float* normal;
@@ -302,99 +311,125 @@ struct Nsweep16Params {
     int n_tiles;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
-nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant__ SwProgram prog) {
+__global__ void __launch_bounds__(SW_THREADS, 1)
+nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant__ SwProgram prog,
+                const __grid_constant__ SwInputs inputs) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ SwBarriers bar;
     uint8_t* smem = sw_setup(smem_raw, &bar);
-    float* s_skip = reinterpret_cast<float*>(smem + SW_SCR1_OFF);
+    float* s_skip = reinterpret_cast<float*>(smem + SW_SKIP_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp == 0) {
-        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
+        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles, p.dbg);
     } else if (warp == 1) {
-        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles, p.dbg);
+    } else if (warp == 2 + EPI_WARPS) {
+        if (lane == 0) sw_in_producer(inputs, smem, &bar, n_my_tiles, p.dbg);
     } else {
         const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
         const uint32_t tmem = bar.tmem_base;
-        uint32_t acc_par = 0;
+        uint32_t acc_par[2] = {0u, 0u}, in_par[2] = {0u, 0u};
+        int dbg_step = 0;
         for (int t = 0; t < n_my_tiles; ++t) {
+            dbg_step = 0;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t gp = tile * TILE_M + row;
             const bool live = gp < p.n;
             const size_t tb = (size_t)tile * T16_TILE_BYTES;
-            // 16 columns [c, c + 16): d = s'(h) * g -> fp16 words of the next A operand, bf16 chunks of the D16 stash
-            auto emit16 = [&](int lyr, int c, const float* d, uint32_t abuf) {
-                uint32_t w[8];
+            // 16 columns [c, c + 16) of D_lyr: fp16 hi / lo words of the next A operand (returned), bf16 chunks of the D16 stash
+            auto emit16 = [&](int lyr, int c, const float* d, uint32_t* hi8, uint32_t* lo8) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = pack_f16x2(d[2 * i], d[2 * i + 1]);
-                sw_st16(tmem, lane_base, abuf, c, w);
+                for (int i = 0; i < 8; ++i) split2_lo16(d[2 * i], d[2 * i + 1], hi8[i], lo8[i]);
                 uint4 q0, q1;
                 q0.x = pack_bf16x2(d[0], d[1]); q0.y = pack_bf16x2(d[2], d[3]); q0.z = pack_bf16x2(d[4], d[5]); q0.w = pack_bf16x2(d[6], d[7]);
                 q1.x = pack_bf16x2(d[8], d[9]); q1.y = pack_bf16x2(d[10], d[11]); q1.z = pack_bf16x2(d[12], d[13]); q1.w = pack_bf16x2(d[14], d[15]);
                 stg16(p.D16[lyr] + tb + t16_off(row, c >> 3), q0);
                 stg16(p.D16[lyr] + tb + t16_off(row, (c >> 3) + 1), q1);
             };
-            auto load_em16 = [&](int lyr, int c, float* sp) {       // s' = 1 - em of 16 columns
-                const uint4 a = ldg16(p.EM[lyr] + tb + t16_off(row, c >> 3));
-                const uint4 b = ldg16(p.EM[lyr] + tb + t16_off(row, (c >> 3) + 1));
+            auto store_a16 = [&](int c, const uint32_t* hi8, const uint32_t* lo8) {
+                sw_st16(tmem, lane_base, SW_A0, c, hi8);
+                sw_st16(tmem, lane_base, SW_A1, c, lo8);
+            };
+            auto load_sp16 = [&](int hf, int c, float* sp) {       // s' = 1 - (em_hi + em_lo) of 16 columns, from the input slot
+                const uint4 a = sw_in_ld(smem, hf, 0, row, c), b = sw_in_ld(smem, hf, 0, row, c + 8);
+                const uint4 al = sw_in_ld(smem, hf, 1, row, c), bl = sw_in_ld(smem, hf, 1, row, c + 8);
                 const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                const uint32_t wl[8] = {al.x, al.y, al.z, al.w, bl.x, bl.y, bl.z, bl.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const float2 f = f16x2_unpack(w[i]);
-                    sp[2 * i] = 1.0f - f.x;
-                    sp[2 * i + 1] = 1.0f - f.y;
+                    const float2 f = f16x2_unpack(w[i]), fl = f16x2_unpack(wl[i]);
+                    sp[2 * i] = 1.0f - (f.x + fl.x);
+                    sp[2 * i + 1] = 1.0f - (f.y + fl.y);
                 }
             };
-            // ---- seed: D_7 = s'(h_7) * W_out[0] / scale ---------------------------------------------------------------------
+            // ---- seed: D_7 = s'(h_7) * W_out[0] / scale (the previous tile's MMAs are complete: A may be written) -------------
 #pragma unroll 1
-            for (int sb = 0; sb < 4; ++sb) {
-                const int c = 128 * (sb >> 1) + cg * 32 + 16 * (sb & 1);
-                float sp[16], d[16];
-                load_em16(7, c, sp);
+            for (int hf = 0; hf < 2; ++hf) {
+                sw_in_wait(&bar, hf, in_par);
+#pragma unroll 1
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int c = 128 * hf + cg * 32 + 16 * sub;
+                    float sp[16], d[16];
+                    load_sp16(hf, c, sp);
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                    const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + c + j));
-                    d[j] = sp[j] * w.x * p.inv_scale; d[j + 1] = sp[j + 1] * w.y * p.inv_scale;
-                    d[j + 2] = sp[j + 2] * w.z * p.inv_scale; d[j + 3] = sp[j + 3] * w.w * p.inv_scale;
-                }
-                if (!live) {
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + c + j));
+                        d[j] = sp[j] * w.x * p.inv_scale; d[j + 1] = sp[j + 1] * w.y * p.inv_scale;
+                        d[j + 2] = sp[j + 2] * w.z * p.inv_scale; d[j + 3] = sp[j + 3] * w.w * p.inv_scale;
+                    }
+                    if (!live) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+                        for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+                    }
+                    uint32_t hi8[8], lo8[8];
+                    emit16(7, c, d, hi8, lo8);
+                    store_a16(c, hi8, lo8);
                 }
-                emit16(7, c, d, SW_A0);
+                sw_in_release(&bar, hf);
             }
             sw_publish(&bar);
             // ---- D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1 ------------------------------------------------------------------
             for (int l = 7; l >= 1; --l) {
-                const uint32_t abuf = ((7 - l) & 1) ? SW_A0 : SW_A1;       // the buffer this layer WRITES
-#pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    sw_wait_acc(&bar, acc_par);
-#pragma unroll 1
+                uint32_t hh[16], hl[16];           // first half's operand words, held until every MMA of the layer has read A
+                auto half = [&](int hf, uint32_t* hi16, uint32_t* lo16) {
+#pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
                         const int c = 128 * hf + cg * 32 + 16 * sub;
                         float g[16], sp[16];
-                        load_em16(l - 1, c, sp);
+                        load_sp16(hf, c, sp);
                         sw_ld16(tmem, lane_base, c, g);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float d = sp[j] * g[j];
-                            if (l == 4 && c + j > 192) {
+                            if (l == 4 && hf == 1 && c + j > 192) {
                                 // columns 193..255 of the skip layer's input are the encoding: their cotangent is the raw product
                                 s_skip[row * SW_SCR_LD + (c + j - 193)] = g[j];
                                 d = 0.0f;
                             }
                             g[j] = live ? d : 0.0f;
                         }
-                        emit16(l - 1, c, g, abuf);
+                        emit16(l - 1, c, g, hi16 + 8 * sub, lo16 + 8 * sub);
                     }
-                }
+                };
+                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | (dbg_step++ & 255)));
+                sw_in_wait(&bar, 0, in_par);
+                sw_wait_acc(&bar, 0, acc_par);
+                half(0, hh, hl);
+                sw_in_release(&bar, 0);
+                sw_in_wait(&bar, 1, in_par);
+                sw_wait_acc(&bar, 1, acc_par);
+                store_a16(cg * 32, hh, hl);
+                store_a16(cg * 32 + 16, hh + 8, hl + 8);
+                half(1, hh, hl);
+                store_a16(128 + cg * 32, hh, hl);
+                store_a16(128 + cg * 32 + 16, hh + 8, hl + 8);
+                sw_in_release(&bar, 1);
                 sw_publish(&bar);
             }
             // ---- encoding layer: eb = D_0 W_0 + (skip part); normal = J_e^T eb ---------------------------------------------------
-            sw_wait_acc(&bar, acc_par);
+            sw_wait_acc(&bar, 0, acc_par);
             {
                 float g[16];
                 sw_ld16(tmem, lane_base, cg * 16, g);
@@ -422,6 +457,7 @@ nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant_
                 p.normal[gp * 3 + cg] = acc;
             }
         }
+        if (threadIdx.x == 64) dbg_mark(p.dbg, 2, 0xffffffffu);
     }
     sw_teardown(&bar);
 }
@@ -430,12 +466,11 @@ nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant_
 // second-order backward: tangent sweep + reverse sweep
 // ------------------------------------------------------------------------------------------------------------------
 struct Bwd16Params {
+    uint32_t* dbg;
     int64_t n;
     float inv_scale;
     const float* E;
     const float* EB;
-    const uint8_t* EM[8];
-    const uint8_t* D16[8];
     const float* d_sdf;      // may be NULL
     const float* d_feat;     // may be NULL
     int64_t ld_dfeat;
@@ -452,25 +487,29 @@ struct Bwd16Params {
     int n_tiles;
 };
 
-__global__ void __launch_bounds__(THREADS, 1)
-bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwProgram prog) {
+__global__ void __launch_bounds__(SW_THREADS, 1)
+bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwProgram prog,
+             const __grid_constant__ SwInputs inputs) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ SwBarriers bar;
     uint8_t* smem = sw_setup(smem_raw, &bar);
-    float* s_ue = reinterpret_cast<float*>(smem + SW_SCR0_OFF);
-    float* s_skip = reinterpret_cast<float*>(smem + SW_SCR1_OFF);
+    float* s_skip = reinterpret_cast<float*>(smem + SW_SKIP_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp == 0) {
-        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
+        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles, p.dbg);
     } else if (warp == 1) {
-        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles, p.dbg);
+    } else if (warp == 2 + EPI_WARPS) {
+        if (lane == 0) sw_in_producer(inputs, smem, &bar, n_my_tiles, p.dbg);
     } else {
         const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
         const uint32_t tmem = bar.tmem_base;
-        uint32_t acc_par = 0;
+        uint32_t acc_par[2] = {0u, 0u}, in_par[2] = {0u, 0u};
+        int dbg_step = 0;
         for (int t = 0; t < n_my_tiles; ++t) {
+            dbg_step = 0;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t gp = tile * TILE_M + row;
             const bool live = gp < p.n;
@@ -478,6 +517,12 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
             float dn[3] = {0.f, 0.f, 0.f};
             if (live) { dn[0] = p.d_normal[gp * 3]; dn[1] = p.d_normal[gp * 3 + 1]; dn[2] = p.d_normal[gp * 3 + 2]; }
             const float gs = (live && p.d_sdf) ? p.d_sdf[gp] * p.inv_scale : 0.0f;
+            const float* __restrict__ e_pt = p.E + eoff(gp);
+            // bf16 hi / lo words of 16 values: hi is also what the 16-bit stash holds
+            auto split16 = [&](const float* v, uint32_t* hi8, uint32_t* lo8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi8[i], lo8[i]);
+            };
             auto pack16 = [&](const float* v, uint32_t* w) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -486,16 +531,16 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                 stg16(arr + tb + t16_off(row, c >> 3), make_uint4(w[0], w[1], w[2], w[3]));
                 stg16(arr + tb + t16_off(row, (c >> 3) + 1), make_uint4(w[4], w[5], w[6], w[7]));
             };
-            auto load_bf16 = [&](const uint8_t* arr, int c, float* v) {
-                const uint4 a = ldg16(arr + tb + t16_off(row, c >> 3));
-                const uint4 b = ldg16(arr + tb + t16_off(row, (c >> 3) + 1));
+            auto store_a16 = [&](int c, const uint32_t* hi8, const uint32_t* lo8) {
+                sw_st16(tmem, lane_base, SW_A0, c, hi8);
+                sw_st16(tmem, lane_base, SW_A1, c, lo8);
+            };
+            auto unpack_bf16 = [&](const uint4& a, const uint4& b, float* v) {
                 const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { v[2 * i] = bf16_lo(w[i]); v[2 * i + 1] = bf16_hi(w[i]); }
             };
-            auto load_em = [&](const uint8_t* arr, int c, float* v) {
-                const uint4 a = ldg16(arr + tb + t16_off(row, c >> 3));
-                const uint4 b = ldg16(arr + tb + t16_off(row, (c >> 3) + 1));
+            auto unpack_f16 = [&](const uint4& a, const uint4& b, float* v) {
                 const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -506,68 +551,67 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
             };
             // ---- ue = J_e(x) dn: tangent of the encoding, 16 columns per thread ---------------------------------------------
             {
-                const float* __restrict__ e = p.E + eoff(gp);
                 float ue[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = cg * 16 + j;
-                    float v;
-                    if (col < 3) {
-                        v = dn[col];
-                    } else if (col == 63) {
-                        v = 0.0f;
-                    } else {
-                        const int jj = col - 3, c = jj / 20, r = jj - c * 20, k = r >= 10 ? r - 10 : r;
-                        const float f = (float)(1 << k);
-                        // column 3 + 20 c + k = sin(2^k x_c) -> f cos dn_c;  column 3 + 20 c + 10 + k = cos -> -f sin dn_c
-                        const float other = e[(r >= 10 ? col - 10 : col + 10) * TILE_M];
-                        v = (r >= 10 ? -f : f) * other * dn[c];
-                    }
-                    ue[j] = v;
-                    s_ue[row * SW_SCR_LD + col] = v;
-                }
-                uint32_t w[8];
-                pack16(ue, w);
-                sw_st16(tmem, lane_base, SW_A0, cg * 16, w);
+                for (int j = 0; j < 16; ++j) ue[j] = enc_tangent_col(e_pt, dn[0], dn[1], dn[2], cg * 16 + j);
+                uint32_t w[8], wl[8];
+                split16(ue, w, wl);
+                store_a16(cg * 16, w, wl);
                 if (p.store_dw) {
                     stg16(p.UE16 + (size_t)tile * T16N_TILE_BYTES + t16_off<8>(row, cg * 2), make_uint4(w[0], w[1], w[2], w[3]));
                     stg16(p.UE16 + (size_t)tile * T16N_TILE_BYTES + t16_off<8>(row, cg * 2 + 1), make_uint4(w[4], w[5], w[6], w[7]));
                 }
             }
             sw_publish(&bar);
-            int step = 0;
             // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l ---------------------------------
-            for (int l = 0; l < 8; ++l, ++step) {
-                const uint32_t abuf = (step & 1) ? SW_A0 : SW_A1;      // the buffer this layer WRITES
-#pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    sw_wait_acc(&bar, acc_par);
-#pragma unroll 1
+            for (int l = 0; l < 8; ++l) {
+                uint32_t hh[16], hl[16];
+                auto half = [&](int hf, uint32_t* hi16, uint32_t* lo16) {
+#pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
                         const int c = 128 * hf + cg * 32 + 16 * sub;
                         float q[16], em[16], d[16];
-                        load_em(p.EM[l], c, em);
-                        load_bf16(p.D16[l], c, d);
+                        unpack_f16(sw_in_ld(smem, hf, 0, row, c), sw_in_ld(smem, hf, 0, row, c + 8), em);
+                        unpack_bf16(sw_in_ld(smem, hf, 1, row, c), sw_in_ld(smem, hf, 1, row, c + 8), d);
                         sw_ld16(tmem, lane_base, c, q);
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float u = (1.0f - em[j]) * q[j];
-                            float x = 100.0f * em[j] * d[j] * q[j];
-                            if (l == 3 && c + j > 192) {       // tangent of the skip input's encoding part
-                                u = s_ue[row * SW_SCR_LD + (c + j - 193)];
-                                x = 0.0f;
-                            }
+                            const float u = (1.0f - em[j]) * q[j];
+                            d[j] = 100.0f * em[j] * d[j] * q[j];
                             q[j] = u;
-                            d[j] = x;
                         }
+                        if (l == 3 && hf == 1 && c + 15 > 192) {           // tangent of the skip input's encoding part (columns 193..255)
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c + j > 192) {
+                                    q[j] = enc_tangent_col(e_pt, dn[0], dn[1], dn[2], c + j - 193);
+                                    d[j] = 0.0f;
+                                }
+                        }
+                        split16(q, hi16 + 8 * sub, lo16 + 8 * sub);
+                        if (p.store_dw) store16(p.U16[l], c, hi16 + 8 * sub);
                         uint32_t w[8];
-                        pack16(q, w);
-                        if (l < 7) sw_st16(tmem, lane_base, abuf, c, w);
-                        if (p.store_dw) store16(p.U16[l], c, w);
                         pack16(d, w);
                         store16(p.X16[l], c, w);
                     }
+                };
+                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | (dbg_step++ & 255)));
+                sw_in_wait(&bar, 0, in_par);
+                sw_wait_acc(&bar, 0, acc_par);
+                half(0, hh, hl);
+                sw_in_release(&bar, 0);
+                sw_in_wait(&bar, 1, in_par);
+                sw_wait_acc(&bar, 1, acc_par);
+                if (l < 7) {
+                    store_a16(cg * 32, hh, hl);
+                    store_a16(cg * 32 + 16, hh + 8, hl + 8);
                 }
+                half(1, hh, hl);
+                if (l < 7) {
+                    store_a16(128 + cg * 32, hh, hl);
+                    store_a16(128 + cg * 32 + 16, hh + 8, hl + 8);
+                }
+                sw_in_release(&bar, 1);
                 if (l == 7) {
                     // A operand of the output layer's reverse step: the point's row of d_feat
 #pragma unroll 1
@@ -580,26 +624,25 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                             if (live && p.d_feat) a = ld4(p.d_feat + gp * p.ld_dfeat + c + j);
                             v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
                         }
-                        uint32_t w[8];
-                        pack16(v, w);
-                        sw_st16(tmem, lane_base, abuf, c, w);
+                        uint32_t w[8], wl[8];
+                        split16(v, w, wl);
+                        store_a16(c, w, wl);
                         if (p.store_dw) store16(p.DF16, c, w);
                     }
                 }
                 sw_publish(&bar);
             }
             // ---- reverse sweep: dz_{l-1} = s'(h_{l-1}) (dz_l W_l) + X_{l-1}, l = 8..1 -------------------------------------------
-            for (int l = 8; l >= 1; --l, ++step) {
-                const uint32_t abuf = (step & 1) ? SW_A0 : SW_A1;
-#pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
-                    sw_wait_acc(&bar, acc_par);
-#pragma unroll 1
+            for (int l = 8; l >= 1; --l) {
+                uint32_t hh[16], hl[16];
+                const uint8_t* xp = p.X16[l - 1] + tb;
+                auto half = [&](int hf, uint32_t* hi16, uint32_t* lo16, const uint4& x0, const uint4& x1, const uint4& x2, const uint4& x3) {
+#pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
                         const int c = 128 * hf + cg * 32 + 16 * sub;
                         float da[16], em[16], x[16];
-                        load_em(p.EM[l - 1], c, em);
-                        load_bf16(p.X16[l - 1], c, x);
+                        unpack_f16(sw_in_ld(smem, hf, 0, row, c), sw_in_ld(smem, hf, 0, row, c + 8), em);
+                        unpack_bf16(sub ? x2 : x0, sub ? x3 : x1, x);
                         sw_ld16(tmem, lane_base, c, da);
                         if (l == 8) {
 #pragma unroll
@@ -611,22 +654,39 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             float dz = fmaf(1.0f - em[j], da[j], x[j]);
-                            if (l == 4 && c + j > 192) {       // cotangent of the encoding part of the skip input
+                            if (l == 4 && hf == 1 && c + j > 192) {       // cotangent of the encoding part of the skip input
                                 s_skip[row * SW_SCR_LD + (c + j - 193)] = da[j];
                                 dz = 0.0f;
                             }
                             da[j] = dz;
                         }
-                        uint32_t w[8];
-                        pack16(da, w);
-                        sw_st16(tmem, lane_base, abuf, c, w);
-                        if (p.store_dw) store16(p.DZ16[l - 1], c, w);
+                        split16(da, hi16 + 8 * sub, lo16 + 8 * sub);
+                        if (p.store_dw) store16(p.DZ16[l - 1], c, hi16 + 8 * sub);
                     }
-                }
+                };
+                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | (dbg_step++ & 255)));
+                // X_{l-1} was written by THIS thread during the tangent sweep: plain loads, issued before the waits
+                const int ch0 = (cg * 32) >> 3, ch1 = (128 + cg * 32) >> 3;
+                uint4 x0 = ldg16(xp + t16_off(row, ch0)), x1 = ldg16(xp + t16_off(row, ch0 + 1));
+                uint4 x2 = ldg16(xp + t16_off(row, ch0 + 2)), x3 = ldg16(xp + t16_off(row, ch0 + 3));
+                sw_in_wait(&bar, 0, in_par);
+                sw_wait_acc(&bar, 0, acc_par);
+                half(0, hh, hl, x0, x1, x2, x3);
+                sw_in_release(&bar, 0);
+                x0 = ldg16(xp + t16_off(row, ch1)); x1 = ldg16(xp + t16_off(row, ch1 + 1));
+                x2 = ldg16(xp + t16_off(row, ch1 + 2)); x3 = ldg16(xp + t16_off(row, ch1 + 3));
+                sw_in_wait(&bar, 1, in_par);
+                sw_wait_acc(&bar, 1, acc_par);
+                store_a16(cg * 32, hh, hl);
+                store_a16(cg * 32 + 16, hh + 8, hl + 8);
+                half(1, hh, hl, x0, x1, x2, x3);
+                store_a16(128 + cg * 32, hh, hl);
+                store_a16(128 + cg * 32 + 16, hh + 8, hl + 8);
+                sw_in_release(&bar, 1);
                 sw_publish(&bar);
             }
             // ---- encoding layer: de = dz_0 W_0 + (skip part); d_x = J_e^T de + Hessian term -----------------------------------------
-            sw_wait_acc(&bar, acc_par);
+            sw_wait_acc(&bar, 0, acc_par);
             {
                 float g[16];
                 sw_ld16(tmem, lane_base, cg * 16, g);
@@ -651,6 +711,7 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                 p.d_pts[gp * 3 + cg] = acc + dn[cg] * hess;
             }
         }
+        if (threadIdx.x == 64) dbg_mark(p.dbg, 2, 0xffffffffu);
     }
     sw_teardown(&bar);
 }
@@ -658,11 +719,20 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
+uint32_t* g_m16_dbg = nullptr;
+static int g_dbg_count[4] = {0, 0, 0, 0};
+uint32_t* dbg_slot(int kernel_id) {
+    if (!g_m16_dbg) return nullptr;
+    const int inst = g_dbg_count[kernel_id]++ & 3;
+    return g_m16_dbg + ((size_t)kernel_id * 4 + inst) * 148 * 8;
+}
+
 struct M16Stash {
     float* E;
     float* EB;
     uint8_t* E16;
     uint8_t* EM[8];
+    uint8_t* EML[8];
     uint8_t* A16[8];
     uint8_t* D16[8];
 };
@@ -673,11 +743,12 @@ static M16Stash m16_stash(float* stash, int64_t np) {
     uint8_t* b = reinterpret_cast<uint8_t*>(stash + np * 128);
     s.E16 = b; b += np * 128;
     for (int l = 0; l < 8; ++l) { s.EM[l] = b; b += np * 512; }
+    for (int l = 0; l < 8; ++l) { s.EML[l] = b; b += np * 512; }
     for (int l = 0; l < 8; ++l) { s.A16[l] = b; b += np * 512; }
     for (int l = 0; l < 8; ++l) { s.D16[l] = b; b += np * 512; }
     return s;
 }
-int64_t m16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (128 + 32 + 24 * 128); }
+int64_t m16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (128 + 32 + 32 * 128); }
 // backward workspace: U16[8] | X16[8] | DZ16[8] | DF16 | UE16 | partial sums of the dW kernel
 int64_t m16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (25 * 128 + 32) + dw_part_floats(9); }
 
@@ -694,7 +765,9 @@ static void sw_layer(SwProgram& prog, int& k, const uint32_t off[2], int n_halve
         st.b_off = off[h];
         st.n_mma = (uint16_t)n_mma;
         st.kblocks = (uint8_t)kblocks;
-        st.a_buf = (uint8_t)(layer_idx & 1);
+        (void)layer_idx;
+        st.a_buf = 0;
+        st.a_pair = 1;
         st.wait_a = (uint8_t)(h == 0);
         st.f16 = (uint8_t)f16;
         st.passes = 2;
@@ -720,11 +793,12 @@ int launch_m16_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
         Trunk16Params p;
         p.pts = pts; p.n = n; p.inv_scale = inv_scale; p.sdf = sdf; p.feat = feat; p.ld_feat = ld_feat;
         p.E = S.E; p.E16 = S.E16;
-        for (int l = 0; l < 8; ++l) { p.EM[l] = S.EM[l]; p.A16[l] = S.A16[l]; }
+        for (int l = 0; l < 8; ++l) { p.EM[l] = S.EM[l]; p.EML[l] = S.EML[l]; p.A16[l] = S.A16[l]; }
         p.chain = reinterpret_cast<const uint8_t*>(m->chain);
         for (int l = 0; l < 9; ++l) p.bias[l] = m->b[l];
         p.w_out0 = m->W[8];
         p.n_tiles = n_tiles;
+        p.dbg = dbg_slot(0);
         Program prog = {};
         prog.n_steps = 18;
         for (int l = 0; l < 9; ++l)
@@ -745,17 +819,24 @@ int launch_m16_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
     {
         Nsweep16Params p;
         p.n = n; p.inv_scale = inv_scale; p.E = S.E; p.EB = S.EB; p.normal = normal;
-        for (int l = 0; l < 8; ++l) { p.EM[l] = S.EM[l]; p.D16[l] = S.D16[l]; }
+        for (int l = 0; l < 8; ++l) p.D16[l] = S.D16[l];
+        SwInputs in = {};
+        int ne = 0;
+        for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{S.EM[7], S.EML[7]};                  // seed
+        for (int l = 7; l >= 1; --l)
+            for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{S.EM[l - 1], S.EML[l - 1]};
+        in.n_events = ne;
         p.chain = reinterpret_cast<const uint8_t*>(m->chain);
         p.w_out0 = m->W[8];
         p.n_tiles = n_tiles;
+        p.dbg = dbg_slot(1);
         SwProgram prog = {};
         int k = 0;
         for (int l = 7; l >= 1; --l) sw_layer(prog, k, L.nnh_off[l], 2, 128, 4, 7 - l, 1);
         sw_layer(prog, k, L.nnh_off[0], 1, 64, 4, 7, 1);
         prog.n_steps = k;
         TimingScope ts(s, TT_SDF_FWD);
-        nsweep16_kernel<<<grid, THREADS, SW_SMEM_BYTES, s>>>(p, prog);
+        nsweep16_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);
     }
     count_launch();
     HN_CHECK_LAUNCH();
@@ -786,13 +867,21 @@ int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     {
         Bwd16Params p;
         p.n = n; p.inv_scale = inv_scale; p.E = S.E; p.EB = S.EB;
-        for (int l = 0; l < 8; ++l) { p.EM[l] = S.EM[l]; p.D16[l] = S.D16[l]; p.U16[l] = U16[l]; p.X16[l] = X16[l]; p.DZ16[l] = DZ16[l]; }
+        for (int l = 0; l < 8; ++l) { p.U16[l] = U16[l]; p.X16[l] = X16[l]; p.DZ16[l] = DZ16[l]; }
+        SwInputs in = {};
+        int ne = 0;
+        for (int l = 0; l < 8; ++l)
+            for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{S.EM[l], S.D16[l]};              // tangent sweep
+        for (int l = 8; l >= 1; --l)
+            for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{S.EM[l - 1], nullptr};           // reverse sweep
+        in.n_events = ne;
         p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.d_normal = d_normal; p.d_pts = d_pts;
         p.UE16 = UE16; p.DF16 = DF16;
         p.store_dw = grad ? 1 : 0;
         p.chain = reinterpret_cast<const uint8_t*>(m->chain);
         p.w_out0 = m->W[8];
         p.n_tiles = n_tiles;
+        p.dbg = dbg_slot(2);
         SwProgram prog = {};
         int k = 0, idx = 0;
         for (int l = 0; l < 8; ++l, ++idx) sw_layer(prog, k, L.ntb_off[l], 2, 128, L.nt_kb[l], idx, 0);      // tangent: u @ W_l^T
@@ -800,7 +889,7 @@ int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
         sw_layer(prog, k, L.nnb_off[0], 1, 64, 4, idx, 0);
         prog.n_steps = k;
         TimingScope ts(s, TT_SDF_BWD);
-        bwd16_kernel<<<std::min(n_tiles, sm_count()), THREADS, SW_SMEM_BYTES, s>>>(p, prog);
+        bwd16_kernel<<<std::min(n_tiles, sm_count()), SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);
     }
     count_launch();
     HN_CHECK_LAUNCH();
@@ -839,3 +928,8 @@ int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
 
 }  // namespace chain
 }  // namespace hn
+
+extern "C" int hn_chain16_set_debug(void* host_mapped_words) {
+    hn::chain::g_m16_dbg = reinterpret_cast<uint32_t*>(host_mapped_words);
+    return HN_OK;
+}

@@ -27,7 +27,7 @@ struct BarriersTs {
     uint64_t full[TS_STAGES];
     uint64_t empty[TS_STAGES];
     uint64_t a_ready;
-    uint64_t acc_full;
+    uint64_t acc_full[2];    // one per N-half: a single barrier completing twice before a slow thread looks would alias its parity
     uint32_t tmem_base;
 };
 
@@ -61,7 +61,8 @@ sdf_only_ts_kernel(const __grid_constant__ SdfTsParams p, const __grid_constant_
             tc::mbar_init(&bar.empty[s], 1);
         }
         tc::mbar_init(&bar.a_ready, EPI_THREADS);
-        tc::mbar_init(&bar.acc_full, 1);
+        tc::mbar_init(&bar.acc_full[0], 1);
+        tc::mbar_init(&bar.acc_full[1], 1);
         tc::mbar_fence_init();
     }
     tc::tc_fence_before_sync();
@@ -128,7 +129,7 @@ sdf_only_ts_kernel(const __grid_constant__ SdfTsParams p, const __grid_constant_
                         tc::umma_commit(&bar.empty[stage]);
                         if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    tc::umma_commit(&bar.acc_full);
+                    tc::umma_commit(&bar.acc_full[st.acc_col ? 1 : 0]);
                 }
             if (p.prof) {
                 p.prof[blockIdx.x * 4 + 0] = t_a;
@@ -140,15 +141,15 @@ sdf_only_ts_kernel(const __grid_constant__ SdfTsParams p, const __grid_constant_
         // ---- epilogue warps: thread = (row, 32-column group of each half) ---------------------------------------------
         const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
-        uint32_t acc_par = 0;
+        uint32_t acc_par[2] = {0u, 0u};
         auto publish = [&]() {
             tc::tmem_st_wait();
             tc::tc_fence_before_sync();
             tc::mbar_arrive(&bar.a_ready);
         };
-        auto wait_acc = [&]() {
-            tc::mbar_wait(&bar.acc_full, acc_par);
-            acc_par ^= 1u;
+        auto wait_acc = [&](int hf) {
+            tc::mbar_wait(&bar.acc_full[hf], acc_par[hf]);
+            acc_par[hf] ^= 1u;
             tc::tc_fence_after_sync();
         };
         // 32 activation values of columns [col0, col0+32) -> 16 (hi, lo) words
@@ -206,7 +207,7 @@ sdf_only_ts_kernel(const __grid_constant__ SdfTsParams p, const __grid_constant_
                 float v[32];
                 uint32_t hh[16], hl[16];
                 // ---- first half (columns cg*32 ..), under the second half's MMAs ----------------------------------------
-                wait_acc();
+                wait_acc(0);
                 activate32(cg * 32, cg * 32, bias, v);
                 if (l < 7) {
                     pack32(v, hh, hl);
@@ -218,7 +219,7 @@ sdf_only_ts_kernel(const __grid_constant__ SdfTsParams p, const __grid_constant_
                     }
                 }
                 // ---- second half: every MMA of the layer has read A, it may be overwritten ---------------------------------
-                wait_acc();
+                wait_acc(1);
                 if (l < 7) store_a(cg * 32, hh, hl);
                 const int col0 = 128 + cg * 32;
                 if (l == 3 && col0 >= 192) {

@@ -437,6 +437,8 @@ HN_API int hn_dw16_test(const float* P, int out, const float* Q, int in, const f
                         float* C, int64_t ldc, float* db, void* tiles, int64_t tiles_bytes, float* part,
                         int64_t part_floats, hn_stream_t stream);
 HN_API int hn_dw16_set_debug(int swap_lbo_sbo);
+/* diagnostics: progress words of the HN_TC_MIXED16 kernels in a host-mapped buffer of 4*4*148*8 uint32 (NULL: off) */
+HN_API int hn_chain16_set_debug(void* host_mapped_words);
 HN_API int hn_dw_test(const float* P, int64_t ldp, int p_tiled, int out, const float* Q, int64_t ldq,
                       int q_tiled, int in, const float* P2, const float* Q2, int64_t n, float* C,
                       int64_t ldc, float* db, float* part, int64_t part_floats, hn_stream_t stream);

@@ -39,7 +39,7 @@ def _named_grads(sdf, col, var, Ro, To):
 def test_bench_step_vs_fp64_oracle_on_the_products_z_vals(n_rays, streams, use_graph):
     import honerf_b200 as H
     import ref_conf
-    assert H.ops.default_precision() == H.ops._PRECISIONS["tc_bf16x3"]
+    assert H.ops.default_precision() in (H.ops._PRECISIONS["tc_bf16x3"], H.ops._PRECISIONS["tc_mixed16"])
     c = _batch(n_rays, 7)
     R = c["R"]
     sdf, col, var, _, _ = obj_modules()

@@ -62,10 +62,11 @@ def run(Ws, bs, x, cot, cfg):
             H.append(a)
     sdf, feat = z[:, :1], z[:, 1:]
     Hs = [sh(h) for h in H]                     # what the stash holds (the next layer's operand stays on chip, unrounded)
+    Hn = H if cfg.get("h_pair_for_normal") else Hs   # the normal sweep may read a hi + lo pair of the same quantity
     D = [None] * 8
     hb = Ws[8][0][None, :].expand(x.shape[0], -1)
     for l in range(7, -1, -1):
-        D[l] = A.sp_prime_from_h(Hs[l]) * hb
+        D[l] = A.sp_prime_from_h(Hn[l]) * hb
         ab = mm_n(D[l], Ws[l])
         if l == 4:
             eb_skip, hb = ab[:, 193:] * A.SQRT1_2, ab[:, :193] * A.SQRT1_2
@@ -148,6 +149,7 @@ def main():
         ("ALL b-split, 16-bit stash, dw x1", dict(trunk=F2b, normal=B2b, tangent=B2b, reverse=B2b, dw=B1, store_h="f16", store_c="bf16")),
         ("trunk x3; sweeps b-split, 16-bit stash, dw x1", dict(trunk=F3, normal=B2b, tangent=B2b, reverse=B2b, dw=B1, store_h="f16", store_c="bf16")),
         ("trunk b-split; sweeps x1, 16-bit stash, dw x1", dict(trunk=F2b, normal=B1, tangent=B1, reverse=B1, dw=B1, store_h="f16", store_c="bf16")),
+        ("r02 default: x3 everywhere, 16-bit stash (normal sweep reads s' as a hi+lo pair), dw on stored bf16", dict(trunk=F3, normal=F3, tangent=B3, reverse=B3, dw=B1, store_h="f16", store_c="bf16", h_pair_for_normal=True)),
         ("ALL x1, 16-bit stash", dict(trunk=F1, normal=B1, tangent=B1, reverse=B1, dw=B1, store_h="f16", store_c="bf16")),
     ]
     print("| variant | sdf max-abs | feat max-abs | normal rel-L2 | d_pts rel-L2 | worst dW rel-L2 | worst db rel-L2 |")

@@ -15,7 +15,7 @@ sdf, col, dev, _, _ = obj_modules(requires_grad=True)
 n = 65536
 x = (0.45 * torch.randn(n, 3)).cuda().requires_grad_(True)
 d = torch.nn.functional.normalize(torch.randn(n, 3), dim=-1).cuda()
-p = H.ops._PRECISIONS["tc_bf16x3"]
+p = H.ops._PRECISIONS[os.environ.get("PROF_PRECISION", "tc_bf16x3")]
 for _ in range(3):
     s, f, nn = H.ops.sdf_obj(sdf.packed(), x, 1.0, precision=p)
     rgb = H.ops.color_obj(col.packed(), x, d, f, nn, precision=p)
