@@ -780,7 +780,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rays", type=int, default=512, help="rays per GPU per step")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tc_bf16x3", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3", "tc_mixed16"])
+    ap.add_argument("--precision", default="tc_mixed16", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3", "tc_mixed16"])
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
     ap.add_argument("--ray-streams", type=int, default=3,

@@ -1,15 +1,14 @@
 // HN_TC_MIXED16: the object SDF field with a 16-bit activation stash and TMEM-resident operands.
 //
 // What changes against the HN_TC_BF16X3 chain kernels (chain_obj.cu), and why (profiles/r02_precision_table.md):
-//  * the value trunk keeps three fp16 MMAs per product (sdf / feature error ~2e-6; anything less misses the 1e-3
-//    colour / SDF bound by less than 2x), but every sweep whose output is a gradient -- normal sweep, tangent sweep,
-//    reverse sweep -- rounds its A operand to ONE 16-bit value and keeps the weights as hi + lo pairs (two MMAs per
-//    product), and the weight gradients take their operands as stored (one MMA per product): normals 4e-4, weight
-//    gradients <= 6e-3 relative against the 1e-2 bound;
-//  * a single 16-bit A operand is 128 TMEM columns, so the sweeps keep it in tensor memory DOUBLE-BUFFERED
-//    (accumulator 256 + A0 128 + A1 128 = 512 columns): a layer is issued as two 128-column halves, the epilogue of
-//    the first half runs under the MMAs of the second and writes the next layer's operand straight into the other
-//    buffer (tcgen05.st), and shared memory holds nothing but the weight ring and two fp32 scratch tiles;
+//  * every contraction of the forward and of the sweeps keeps three 16-bit MMAs per product (hi + lo operand pairs:
+//    measured on the B200, two MMAs per product in the normal sweep move normals by 3e-4, which flips enough ReLUs of
+//    the colour net to move ITS weight gradients by 3-4 %); what changes is the STASH: 16-bit, so the weight gradients
+//    take their operands as stored (one bf16 MMA per product): normals 2e-5, weight gradients <= 4e-3 relative against
+//    the 1e-2 bound;
+//  * the A operand of every sweep layer lives in tensor memory (accumulator 256 + A_hi 128 + A_lo 128 = 512 columns,
+//    written by the epilogue with tcgen05.st, consumed by the `ts` form of tcgen05.mma): shared memory holds nothing
+//    but the weight ring and the input slots the stash tiles are bulk-copied into one half layer ahead of their use;
 //  * everything the sweeps exchange through HBM is 16-bit and "dW-ready": [128 points x 256 features] tiles in the
 //    un-swizzled MN-major core-matrix order the weight-gradient MMAs consume (8 points x 8 features = 128 contiguous
 //    bytes), grouped so that a warp's access (32 consecutive points, one 8-feature chunk) is one 512-byte segment and a
@@ -63,31 +62,25 @@ __device__ __forceinline__ float softplus100_em(float z, float& em) {
 // D16) are pulled in by a dedicated producer warp with bulk copies, one N-half (128 columns x 128 points x up to two
 // arrays = 64 KB) ahead of the epilogue that reads them, so the epilogue warps never wait on a global load.
 constexpr int SW_THREADS = 64 + EPI_THREADS + 32;   // weight producer, MMA issuer, 16 epilogue warps, input producer
-constexpr int SW_STAGE_BYTES = 128 * 128;        // one weight stage: [128 rows x 64 k] 16-bit
-constexpr int SW_STAGES = 4;
+constexpr int SW_STAGE_BYTES = 256 * 128;        // one weight stage: [256 rows x 64 k] 16-bit (hi and lo stages alternate)
+constexpr int SW_STAGES = 3;
 constexpr int SW_IN_OFF = SW_STAGES * SW_STAGE_BYTES;
 constexpr int SW_IN_ARRAY_BYTES = 128 * 128 * 2; // one array's N-half: [2 point halves][16 chunks][64 points][16 B]
 constexpr int SW_IN_SLOT_BYTES = 2 * SW_IN_ARRAY_BYTES;
-constexpr int SW_SCR_LD = 65;                    // fp32 scratch tile [128][65] (padded: conflict-free columns)
-constexpr int SW_SCR_BYTES = TILE_M * SW_SCR_LD * 4;
-constexpr int SW_SKIP_OFF = SW_IN_OFF + 2 * SW_IN_SLOT_BYTES;
-constexpr int SW_SMEM_BYTES = SW_SKIP_OFF + SW_SCR_BYTES + 1024;
+constexpr int SW_SMEM_BYTES = SW_IN_OFF + 2 * SW_IN_SLOT_BYTES + 1024;
 static_assert(SW_SMEM_BYTES <= 232448, "sweep kernels: shared memory budget");
-constexpr uint32_t SW_A0 = 256, SW_A1 = 384;     // TMEM columns of the two A buffers (accumulator: [0, 256))
+constexpr uint32_t SW_A0 = 256, SW_A1 = 384;     // TMEM columns of A_hi / A_lo (accumulator: [0, 256))
 constexpr int SW_MAX_STEPS = 36;
 
-// one N-half of a layer: acc[128, n_mma] (TMEM columns acc_col ..) = A[a_buf][:, 0 : 64 kblocks] @ B^T
+// one layer: acc[128, n_mma] (TMEM columns 0 ..) = A[:, 0 : 64 kblocks] @ B^T with A = A_hi + A_lo in tensor memory:
+//   A_lo B_hi + A_hi B_hi + A_hi B_lo  (three MMAs of N = n_mma per 16-wide k step: 128 cycles each at N = 256, long enough
+//   to hide the ~90 cycles one elected thread needs to issue the next one -- 128-column half layers were issue-bound)
 struct SwStep {
     uint32_t b_off;          // operand at chain + b_off: kblocks x { hi tile [n_mma x 128 B], lo tile [n_mma x 128 B] }
     uint16_t n_mma;
     uint8_t kblocks;
-    uint8_t a_buf : 1;
-    uint8_t wait_a : 1;      // first half of a layer: wait until the epilogue has published the A operand
     uint8_t f16 : 1;         // fp16 operands (normal sweep) instead of bf16
-    uint8_t passes : 2;      // weight stages per k-block: 2 = B_hi, B_lo;  1 = B_hi only
-    uint8_t a_pair : 1;      // the A operand is a hi (SW_A0) + lo (SW_A1) pair: A_lo B_hi + A_hi B_hi + A_hi B_lo (three MMAs per
-                             // product, no double buffering); else ONE 16-bit operand in buffer a_buf
-    uint16_t acc_col;
+    uint8_t acc_in : 1;      // accumulate onto what the epilogue pre-seeded in the accumulator (tangent sweep, skip layer input)
 };
 struct SwProgram {
     int n_steps;
@@ -108,9 +101,8 @@ struct SwBarriers {
     uint64_t in_full[2];
     uint64_t in_empty[2];
     uint64_t a_ready;
-    // one barrier per N-half: both halves of a layer can complete before a slow epilogue thread has looked at the first
-    // one, and a single barrier flipping twice would alias its parity (the thread would wait forever)
-    uint64_t acc_full[2];
+    uint64_t acc_full;       // completes once per layer, and a_ready (every epilogue thread) separates two completions: a slow
+                             // thread can never see it two phases ahead (a barrier that flips twice aliases its parity)
     uint32_t tmem_base;
 };
 
@@ -128,8 +120,7 @@ __device__ __forceinline__ uint8_t* sw_setup(uint8_t* smem_raw, SwBarriers* bar)
             tc::mbar_init(&bar->in_empty[s], EPI_THREADS);
         }
         tc::mbar_init(&bar->a_ready, EPI_THREADS);
-        tc::mbar_init(&bar->acc_full[0], 1);
-        tc::mbar_init(&bar->acc_full[1], 1);
+        tc::mbar_init(&bar->acc_full, 1);
         tc::mbar_fence_init();
     }
     tc::tc_fence_before_sync();
@@ -164,7 +155,7 @@ __device__ __forceinline__ void sw_producer(const SwProgram& prog, const uint8_t
             const uint32_t bytes = (uint32_t)st.n_mma * 128u;
             const uint8_t* src = chain_w + st.b_off;
             for (int kb = 0; kb < st.kblocks; ++kb)
-                for (int ps = 0; ps < st.passes; ++ps) {
+                for (int ps = 0; ps < 2; ++ps) {
                     tc::mbar_wait(&bar->empty[stage], phase ^ 1u);
                     tc::mbar_arrive_expect_tx(&bar->full[stage], bytes);
                     tc::bulk_g2s(smem + stage * SW_STAGE_BYTES, src + (size_t)(2 * kb + ps) * bytes, bytes, &bar->full[stage]);
@@ -236,38 +227,38 @@ __device__ __forceinline__ void sw_mma(const SwProgram& prog, uint8_t* smem, SwB
             dbg_mark(dbg, 1, (uint32_t)(t << 8 | s));
             const SwStep st = prog.step[s];
             const uint32_t idesc = tc::make_idesc(st.f16 ? tc::FMT_F16 : tc::FMT_BF16, 128, st.n_mma);
-            const uint32_t d = tmem + st.acc_col;
-            const uint32_t a = tmem + (st.a_buf ? SW_A1 : SW_A0);
-            if (st.wait_a) {
+            tt = clock64();
+            tc::mbar_wait(&bar->a_ready, a_par);
+            t_a += clock64() - tt;
+            a_par ^= 1u;
+            tc::tc_fence_after_sync();
+            for (int kb = 0; kb < st.kblocks; ++kb) {
+                const uint32_t ah = tmem + SW_A0 + (uint32_t)kb * 32u, al = tmem + SW_A1 + (uint32_t)kb * 32u;
+                // stage "hi": A_lo B_hi + A_hi B_hi
                 tt = clock64();
-                tc::mbar_wait(&bar->a_ready, a_par);
-                t_a += clock64() - tt;
-                a_par ^= 1u;
+                tc::mbar_wait(&bar->full[stage], phase);
+                t_w += clock64() - tt;
                 tc::tc_fence_after_sync();
-            }
-            for (int kb = 0; kb < st.kblocks; ++kb)
-                for (int ps = 0; ps < st.passes; ++ps) {
-                    tt = clock64();
-                    tc::mbar_wait(&bar->full[stage], phase);
-                    t_w += clock64() - tt;
-                    tc::tc_fence_after_sync();
-                    const uint64_t dB = tc::make_smem_desc_sw128(ring + stage * SW_STAGE_BYTES);
-                    if (st.a_pair) {
-                        const uint32_t ah = tmem + SW_A0 + (uint32_t)kb * 32u, al = tmem + SW_A1 + (uint32_t)kb * 32u;
+                uint64_t dB = tc::make_smem_desc_sw128(ring + stage * SW_STAGE_BYTES);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            if (ps == 0) tc::umma_f16_ts(d, al + 8u * k, dB + 2 * k, idesc, (kb | k) != 0);
-                            tc::umma_f16_ts(d, ah + 8u * k, dB + 2 * k, idesc, 1);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc::umma_f16_ts(d, a + (uint32_t)kb * 32u + 8u * k, dB + 2 * k, idesc, (kb | k | ps) != 0);
-                    }
-                    tc::umma_commit(&bar->empty[stage]);
-                    if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+                for (int k = 0; k < 4; ++k) {
+                    tc::umma_f16_ts(tmem, al + 8u * k, dB + 2 * k, idesc, (kb | k | st.acc_in) != 0);
+                    tc::umma_f16_ts(tmem, ah + 8u * k, dB + 2 * k, idesc, 1);
                 }
-            tc::umma_commit(&bar->acc_full[st.acc_col ? 1 : 0]);
+                tc::umma_commit(&bar->empty[stage]);
+                if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+                // stage "lo": A_hi B_lo
+                tt = clock64();
+                tc::mbar_wait(&bar->full[stage], phase);
+                t_w += clock64() - tt;
+                tc::tc_fence_after_sync();
+                dB = tc::make_smem_desc_sw128(ring + stage * SW_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tc::umma_f16_ts(tmem, ah + 8u * k, dB + 2 * k, idesc, 1);
+                tc::umma_commit(&bar->empty[stage]);
+                if (++stage == SW_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            tc::umma_commit(&bar->acc_full);
         }
     dbg_mark(dbg, 1, 0xffffffffu);
     dbg_mark(dbg, 4, (uint32_t)(t_a >> 4));                  // cycles / 16: MMA issuer waiting for the A operand
@@ -276,9 +267,9 @@ __device__ __forceinline__ void sw_mma(const SwProgram& prog, uint8_t* smem, SwB
 }
 
 // epilogue-side handshake
-__device__ __forceinline__ void sw_wait_acc(SwBarriers* bar, int hf, uint32_t* par) {
-    tc::mbar_wait(&bar->acc_full[hf], par[hf]);
-    par[hf] ^= 1u;
+__device__ __forceinline__ void sw_wait_acc(SwBarriers* bar, uint32_t& par) {
+    tc::mbar_wait(&bar->acc_full, par);
+    par ^= 1u;
     tc::tc_fence_after_sync();
 }
 __device__ __forceinline__ void sw_publish(SwBarriers* bar) {
@@ -291,7 +282,10 @@ __device__ __forceinline__ void sw_ld16(uint32_t tmem, uint32_t lane_base, int c
     tc::tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)col0, v);
     tc::tmem_ld_wait();
 }
-// 16 operand columns [col0, col0 + 16) (8 packed words) into A buffer `abuf` (SW_A0 / SW_A1)
+__device__ __forceinline__ void sw_ld16_nowait(uint32_t tmem, uint32_t lane_base, int col0, float* v) {
+    tc::tmem_ld_32x32b_x16(tmem + lane_base + (uint32_t)col0, v);
+}
+// 16 operand columns [col0, col0 + 16) (8 packed words) into `abuf` (SW_A0: hi halves, SW_A1: lo halves)
 __device__ __forceinline__ void sw_st16(uint32_t tmem, uint32_t lane_base, uint32_t abuf, int col0, const uint32_t* w) {
     tc::tmem_st_32x32b_x8(tmem + lane_base + abuf + (uint32_t)(col0 >> 1), w);
 }

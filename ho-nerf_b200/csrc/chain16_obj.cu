@@ -317,7 +317,6 @@ nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ SwBarriers bar;
     uint8_t* smem = sw_setup(smem_raw, &bar);
-    float* s_skip = reinterpret_cast<float*>(smem + SW_SKIP_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp == 0) {
@@ -330,27 +329,24 @@ nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant_
         const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
         const uint32_t tmem = bar.tmem_base;
-        uint32_t acc_par[2] = {0u, 0u}, in_par[2] = {0u, 0u};
-        int dbg_step = 0;
+        uint32_t acc_par = 0, in_par[2] = {0u, 0u};
         for (int t = 0; t < n_my_tiles; ++t) {
-            dbg_step = 0;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t gp = tile * TILE_M + row;
             const bool live = gp < p.n;
             const size_t tb = (size_t)tile * T16_TILE_BYTES;
-            // 16 columns [c, c + 16) of D_lyr: fp16 hi / lo words of the next A operand (returned), bf16 chunks of the D16 stash
-            auto emit16 = [&](int lyr, int c, const float* d, uint32_t* hi8, uint32_t* lo8) {
+            // 16 columns [c, c + 16) of D_lyr -> fp16 hi / lo halves of the next A operand (tensor memory), bf16 chunks of D16
+            auto emit16 = [&](int lyr, int c, const float* d) {
+                uint32_t hi8[8], lo8[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) split2_lo16(d[2 * i], d[2 * i + 1], hi8[i], lo8[i]);
+                sw_st16(tmem, lane_base, SW_A0, c, hi8);
+                sw_st16(tmem, lane_base, SW_A1, c, lo8);
                 uint4 q0, q1;
                 q0.x = pack_bf16x2(d[0], d[1]); q0.y = pack_bf16x2(d[2], d[3]); q0.z = pack_bf16x2(d[4], d[5]); q0.w = pack_bf16x2(d[6], d[7]);
                 q1.x = pack_bf16x2(d[8], d[9]); q1.y = pack_bf16x2(d[10], d[11]); q1.z = pack_bf16x2(d[12], d[13]); q1.w = pack_bf16x2(d[14], d[15]);
                 stg16(p.D16[lyr] + tb + t16_off(row, c >> 3), q0);
                 stg16(p.D16[lyr] + tb + t16_off(row, (c >> 3) + 1), q1);
-            };
-            auto store_a16 = [&](int c, const uint32_t* hi8, const uint32_t* lo8) {
-                sw_st16(tmem, lane_base, SW_A0, c, hi8);
-                sw_st16(tmem, lane_base, SW_A1, c, lo8);
             };
             auto load_sp16 = [&](int hf, int c, float* sp) {       // s' = 1 - (em_hi + em_lo) of 16 columns, from the input slot
                 const uint4 a = sw_in_ld(smem, hf, 0, row, c), b = sw_in_ld(smem, hf, 0, row, c + 8);
@@ -368,7 +364,7 @@ nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant_
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
                 sw_in_wait(&bar, hf, in_par);
-#pragma unroll 1
+#pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     const int c = 128 * hf + cg * 32 + 16 * sub;
                     float sp[16], d[16];
@@ -383,75 +379,65 @@ nsweep16_kernel(const __grid_constant__ Nsweep16Params p, const __grid_constant_
 #pragma unroll
                         for (int j = 0; j < 16; ++j) d[j] = 0.0f;
                     }
-                    uint32_t hi8[8], lo8[8];
-                    emit16(7, c, d, hi8, lo8);
-                    store_a16(c, hi8, lo8);
+                    emit16(7, c, d);
                 }
                 sw_in_release(&bar, hf);
             }
             sw_publish(&bar);
             // ---- D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1 ------------------------------------------------------------------
             for (int l = 7; l >= 1; --l) {
-                uint32_t hh[16], hl[16];           // first half's operand words, held until every MMA of the layer has read A
-                auto half = [&](int hf, uint32_t* hi16, uint32_t* lo16) {
+                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | l));
+                sw_wait_acc(&bar, acc_par);
+                // four 16-column sub-blocks; the accumulator load of the next one is in flight while this one is processed
+                float accv[2][16];
+                sw_ld16_nowait(tmem, lane_base, cg * 32, accv[0]);
 #pragma unroll
-                    for (int sub = 0; sub < 2; ++sub) {
-                        const int c = 128 * hf + cg * 32 + 16 * sub;
-                        float g[16], sp[16];
-                        load_sp16(hf, c, sp);
-                        sw_ld16(tmem, lane_base, c, g);
+                for (int sb = 0; sb < 4; ++sb) {
+                    const int hf = sb >> 1;
+                    const int c = 128 * hf + cg * 32 + 16 * (sb & 1);
+                    if ((sb & 1) == 0) sw_in_wait(&bar, hf, in_par);
+                    float sp[16];
+                    load_sp16(hf, c, sp);
+                    tc::tmem_ld_wait();
+                    if (sb < 3) sw_ld16_nowait(tmem, lane_base, 128 * ((sb + 1) >> 1) + cg * 32 + 16 * ((sb + 1) & 1), accv[(sb + 1) & 1]);
+                    float* g = accv[sb & 1];
+                    if (l == 4 && c + 15 > 192) {
+                        // columns 193..255 of the skip layer's input are the encoding: their cotangent is the raw product,
+                        // parked in EB until the encoding layer adds its own part
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float d = sp[j] * g[j];
-                            if (l == 4 && hf == 1 && c + j > 192) {
-                                // columns 193..255 of the skip layer's input are the encoding: their cotangent is the raw product
-                                s_skip[row * SW_SCR_LD + (c + j - 193)] = g[j];
-                                d = 0.0f;
+                        for (int j = 0; j < 16; ++j)
+                            if (c + j > 192) {
+                                p.EB[eoff(gp, c + j - 193)] = g[j];
+                                g[j] = 0.0f;
                             }
-                            g[j] = live ? d : 0.0f;
-                        }
-                        emit16(l - 1, c, g, hi16 + 8 * sub, lo16 + 8 * sub);
                     }
-                };
-                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | (dbg_step++ & 255)));
-                sw_in_wait(&bar, 0, in_par);
-                sw_wait_acc(&bar, 0, acc_par);
-                half(0, hh, hl);
-                sw_in_release(&bar, 0);
-                sw_in_wait(&bar, 1, in_par);
-                sw_wait_acc(&bar, 1, acc_par);
-                store_a16(cg * 32, hh, hl);
-                store_a16(cg * 32 + 16, hh + 8, hl + 8);
-                half(1, hh, hl);
-                store_a16(128 + cg * 32, hh, hl);
-                store_a16(128 + cg * 32 + 16, hh + 8, hl + 8);
-                sw_in_release(&bar, 1);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) g[j] = live ? sp[j] * g[j] : 0.0f;
+                    emit16(l - 1, c, g);
+                    if (sb & 1) sw_in_release(&bar, hf);
+                }
                 sw_publish(&bar);
             }
             // ---- encoding layer: eb = D_0 W_0 + (skip part); normal = J_e^T eb ---------------------------------------------------
-            sw_wait_acc(&bar, 0, acc_par);
+            sw_wait_acc(&bar, acc_par);
+            tc::named_bar_sync(1, EPI_THREADS);          // the skip part was written by other threads of this CTA
             {
                 float g[16];
                 sw_ld16(tmem, lane_base, cg * 16, g);
-                float* __restrict__ sk = s_skip + row * SW_SCR_LD + cg * 16;
                 float* __restrict__ eb = p.EB + eoff(gp, cg * 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float v = (cg * 16 + j == 63) ? 0.0f : g[j] + sk[j];
-                    sk[j] = v;
-                    eb[j * TILE_M] = v;
-                }
+                for (int j = 0; j < 16; ++j) eb[j * TILE_M] = (cg * 16 + j == 63) ? 0.0f : g[j] + eb[j * TILE_M];
             }
             tc::tc_fence_before_sync();
             tc::named_bar_sync(1, EPI_THREADS);
             if (cg < 3 && live) {
                 const float* __restrict__ e = p.E + eoff(gp, 3 + cg * 20);
-                const float* __restrict__ g = s_skip + row * SW_SCR_LD + 3 + cg * 20;
-                float acc = s_skip[row * SW_SCR_LD + cg];
+                const float* __restrict__ g = p.EB + eoff(gp, 3 + cg * 20);
+                float acc = p.EB[eoff(gp, cg)];
                 float f = 1.0f;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
-                    acc += f * (e[(10 + k) * TILE_M] * g[k] - e[k * TILE_M] * g[10 + k]);
+                    acc += f * (e[(10 + k) * TILE_M] * g[k * TILE_M] - e[k * TILE_M] * g[(10 + k) * TILE_M]);
                     f *= 2.0f;
                 }
                 p.normal[gp * 3 + cg] = acc;
@@ -476,6 +462,7 @@ struct Bwd16Params {
     int64_t ld_dfeat;
     const float* d_normal;
     float* d_pts;            // may be NULL
+    float* DE;               // fp32 column-major [64][128] tiles: cotangent of the encoding
     uint8_t* U16[8];
     uint8_t* X16[8];
     uint8_t* DZ16[8];
@@ -493,7 +480,6 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ SwBarriers bar;
     uint8_t* smem = sw_setup(smem_raw, &bar);
-    float* s_skip = reinterpret_cast<float*>(smem + SW_SKIP_OFF);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     if (warp == 0) {
@@ -506,10 +492,8 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
         const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
         const uint32_t tmem = bar.tmem_base;
-        uint32_t acc_par[2] = {0u, 0u}, in_par[2] = {0u, 0u};
-        int dbg_step = 0;
+        uint32_t acc_par = 0, in_par[2] = {0u, 0u};
         for (int t = 0; t < n_my_tiles; ++t) {
-            dbg_step = 0;
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
             const int64_t gp = tile * TILE_M + row;
             const bool live = gp < p.n;
@@ -518,11 +502,6 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
             if (live) { dn[0] = p.d_normal[gp * 3]; dn[1] = p.d_normal[gp * 3 + 1]; dn[2] = p.d_normal[gp * 3 + 2]; }
             const float gs = (live && p.d_sdf) ? p.d_sdf[gp] * p.inv_scale : 0.0f;
             const float* __restrict__ e_pt = p.E + eoff(gp);
-            // bf16 hi / lo words of 16 values: hi is also what the 16-bit stash holds
-            auto split16 = [&](const float* v, uint32_t* hi8, uint32_t* lo8) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi8[i], lo8[i]);
-            };
             auto pack16 = [&](const float* v, uint32_t* w) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -531,7 +510,11 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                 stg16(arr + tb + t16_off(row, c >> 3), make_uint4(w[0], w[1], w[2], w[3]));
                 stg16(arr + tb + t16_off(row, (c >> 3) + 1), make_uint4(w[4], w[5], w[6], w[7]));
             };
-            auto store_a16 = [&](int c, const uint32_t* hi8, const uint32_t* lo8) {
+            // 16 values -> bf16 hi / lo halves of the next A operand (tensor memory); hi8 is also what the 16-bit stash holds
+            auto emit_a16 = [&](int c, const float* v, uint32_t* hi8) {
+                uint32_t lo8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi8[i], lo8[i]);
                 sw_st16(tmem, lane_base, SW_A0, c, hi8);
                 sw_st16(tmem, lane_base, SW_A1, c, lo8);
             };
@@ -554,9 +537,8 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                 float ue[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) ue[j] = enc_tangent_col(e_pt, dn[0], dn[1], dn[2], cg * 16 + j);
-                uint32_t w[8], wl[8];
-                split16(ue, w, wl);
-                store_a16(cg * 16, w, wl);
+                uint32_t w[8];
+                emit_a16(cg * 16, ue, w);
                 if (p.store_dw) {
                     stg16(p.UE16 + (size_t)tile * T16N_TILE_BYTES + t16_off<8>(row, cg * 2), make_uint4(w[0], w[1], w[2], w[3]));
                     stg16(p.UE16 + (size_t)tile * T16N_TILE_BYTES + t16_off<8>(row, cg * 2 + 1), make_uint4(w[4], w[5], w[6], w[7]));
@@ -565,8 +547,11 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
             sw_publish(&bar);
             // ---- tangent sweep: q_l = W_l u_{l-1}; u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l ---------------------------------
             for (int l = 0; l < 8; ++l) {
-                uint32_t hh[16], hl[16];
-                auto half = [&](int hf, uint32_t* hi16, uint32_t* lo16) {
+                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | l));
+                sw_wait_acc(&bar, acc_par);
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    sw_in_wait(&bar, hf, in_par);
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
                         const int c = 128 * hf + cg * 32 + 16 * sub;
@@ -580,38 +565,28 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                             d[j] = 100.0f * em[j] * d[j] * q[j];
                             q[j] = u;
                         }
-                        if (l == 3 && hf == 1 && c + 15 > 192) {           // tangent of the skip input's encoding part (columns 193..255)
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c + j > 192) {
-                                    q[j] = enc_tangent_col(e_pt, dn[0], dn[1], dn[2], c + j - 193);
-                                    d[j] = 0.0f;
-                                }
-                        }
-                        split16(q, hi16 + 8 * sub, lo16 + 8 * sub);
-                        if (p.store_dw) store16(p.U16[l], c, hi16 + 8 * sub);
                         uint32_t w[8];
+                        if (l < 7) emit_a16(c, q, w); else pack16(q, w);
+                        if (p.store_dw) store16(p.U16[l], c, w);
                         pack16(d, w);
                         store16(p.X16[l], c, w);
                     }
-                };
-                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | (dbg_step++ & 255)));
-                sw_in_wait(&bar, 0, in_par);
-                sw_wait_acc(&bar, 0, acc_par);
-                half(0, hh, hl);
-                sw_in_release(&bar, 0);
-                sw_in_wait(&bar, 1, in_par);
-                sw_wait_acc(&bar, 1, acc_par);
-                if (l < 7) {
-                    store_a16(cg * 32, hh, hl);
-                    store_a16(cg * 32 + 16, hh + 8, hl + 8);
+                    sw_in_release(&bar, hf);
                 }
-                half(1, hh, hl);
-                if (l < 7) {
-                    store_a16(128 + cg * 32, hh, hl);
-                    store_a16(128 + cg * 32 + 16, hh + 8, hl + 8);
+                if (l == 2) {
+                    // The skip layer's input is [u_3 (193) | ue (63)]: pre-seed the accumulator of layer 3 with [0 | ue] (this
+                    // thread's own columns, all read above) and let its MMAs accumulate: the weight rows 193..255 are zero
+                    // padding and EM_3 is 0 there (s' = 1, X = 0), so the ordinary epilogue passes ue through untouched.
+#pragma unroll 1
+                    for (int sb = 0; sb < 4; ++sb) {
+                        const int c = 128 * (sb >> 1) + cg * 32 + 16 * (sb & 1);
+                        uint32_t v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = __float_as_uint(c + j > 192 ? enc_tangent_col(e_pt, dn[0], dn[1], dn[2], c + j - 193) : 0.0f);
+                        tc::tmem_st_32x32b_x16(tmem + lane_base + (uint32_t)c, v);
+                    }
                 }
-                sw_in_release(&bar, 1);
                 if (l == 7) {
                     // A operand of the output layer's reverse step: the point's row of d_feat
 #pragma unroll 1
@@ -624,9 +599,8 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                             if (live && p.d_feat) a = ld4(p.d_feat + gp * p.ld_dfeat + c + j);
                             v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
                         }
-                        uint32_t w[8], wl[8];
-                        split16(v, w, wl);
-                        store_a16(c, w, wl);
+                        uint32_t w[8];
+                        emit_a16(c, v, w);
                         if (p.store_dw) store16(p.DF16, c, w);
                     }
                 }
@@ -634,15 +608,22 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
             }
             // ---- reverse sweep: dz_{l-1} = s'(h_{l-1}) (dz_l W_l) + X_{l-1}, l = 8..1 -------------------------------------------
             for (int l = 8; l >= 1; --l) {
-                uint32_t hh[16], hl[16];
+                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | (8 + (8 - l))));
+                // X_{l-1} was written by THIS thread during the tangent sweep: plain loads, issued before the wait for the MMAs
                 const uint8_t* xp = p.X16[l - 1] + tb;
-                auto half = [&](int hf, uint32_t* hi16, uint32_t* lo16, const uint4& x0, const uint4& x1, const uint4& x2, const uint4& x3) {
+                uint4 xq[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xq[i] = ldg16(xp + t16_off(row, ((128 * (i >> 2) + cg * 32) >> 3) + (i & 3)));
+                sw_wait_acc(&bar, acc_par);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    sw_in_wait(&bar, hf, in_par);
 #pragma unroll
                     for (int sub = 0; sub < 2; ++sub) {
                         const int c = 128 * hf + cg * 32 + 16 * sub;
                         float da[16], em[16], x[16];
                         unpack_f16(sw_in_ld(smem, hf, 0, row, c), sw_in_ld(smem, hf, 0, row, c + 8), em);
-                        unpack_bf16(sub ? x2 : x0, sub ? x3 : x1, x);
+                        unpack_bf16(xq[4 * hf + 2 * sub], xq[4 * hf + 2 * sub + 1], x);
                         sw_ld16(tmem, lane_base, c, da);
                         if (l == 8) {
 #pragma unroll
@@ -651,60 +632,46 @@ bwd16_kernel(const __grid_constant__ Bwd16Params p, const __grid_constant__ SwPr
                                 da[j] += gs * w.x; da[j + 1] += gs * w.y; da[j + 2] += gs * w.z; da[j + 3] += gs * w.w;
                             }
                         }
+                        if (l == 4 && hf == 1 && c + 15 > 192) {       // cotangent of the encoding part of the skip input
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float dz = fmaf(1.0f - em[j], da[j], x[j]);
-                            if (l == 4 && hf == 1 && c + j > 192) {       // cotangent of the encoding part of the skip input
-                                s_skip[row * SW_SCR_LD + (c + j - 193)] = da[j];
-                                dz = 0.0f;
-                            }
-                            da[j] = dz;
+                            for (int j = 0; j < 16; ++j)
+                                if (c + j > 192) {
+                                    p.DE[eoff(gp, c + j - 193)] = da[j];
+                                    da[j] = 0.0f;
+                                    x[j] = 0.0f;
+                                }
                         }
-                        split16(da, hi16 + 8 * sub, lo16 + 8 * sub);
-                        if (p.store_dw) store16(p.DZ16[l - 1], c, hi16 + 8 * sub);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) da[j] = fmaf(1.0f - em[j], da[j], x[j]);
+                        uint32_t w[8];
+                        emit_a16(c, da, w);
+                        if (p.store_dw) store16(p.DZ16[l - 1], c, w);
                     }
-                };
-                if (threadIdx.x == 64) dbg_mark(p.dbg, 2, (uint32_t)(t << 8 | (dbg_step++ & 255)));
-                // X_{l-1} was written by THIS thread during the tangent sweep: plain loads, issued before the waits
-                const int ch0 = (cg * 32) >> 3, ch1 = (128 + cg * 32) >> 3;
-                uint4 x0 = ldg16(xp + t16_off(row, ch0)), x1 = ldg16(xp + t16_off(row, ch0 + 1));
-                uint4 x2 = ldg16(xp + t16_off(row, ch0 + 2)), x3 = ldg16(xp + t16_off(row, ch0 + 3));
-                sw_in_wait(&bar, 0, in_par);
-                sw_wait_acc(&bar, 0, acc_par);
-                half(0, hh, hl, x0, x1, x2, x3);
-                sw_in_release(&bar, 0);
-                x0 = ldg16(xp + t16_off(row, ch1)); x1 = ldg16(xp + t16_off(row, ch1 + 1));
-                x2 = ldg16(xp + t16_off(row, ch1 + 2)); x3 = ldg16(xp + t16_off(row, ch1 + 3));
-                sw_in_wait(&bar, 1, in_par);
-                sw_wait_acc(&bar, 1, acc_par);
-                store_a16(cg * 32, hh, hl);
-                store_a16(cg * 32 + 16, hh + 8, hl + 8);
-                half(1, hh, hl, x0, x1, x2, x3);
-                store_a16(128 + cg * 32, hh, hl);
-                store_a16(128 + cg * 32 + 16, hh + 8, hl + 8);
-                sw_in_release(&bar, 1);
+                    sw_in_release(&bar, hf);
+                }
                 sw_publish(&bar);
             }
             // ---- encoding layer: de = dz_0 W_0 + (skip part); d_x = J_e^T de + Hessian term -----------------------------------------
-            sw_wait_acc(&bar, 0, acc_par);
-            {
+            sw_wait_acc(&bar, acc_par);
+            tc::named_bar_sync(1, EPI_THREADS);          // the skip part was written by other threads of this CTA
+            if (p.d_pts) {
                 float g[16];
                 sw_ld16(tmem, lane_base, cg * 16, g);
-                float* __restrict__ sk = s_skip + row * SW_SCR_LD + cg * 16;
+                float* __restrict__ de = p.DE + eoff(gp, cg * 16);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) sk[j] = (cg * 16 + j == 63) ? 0.0f : g[j] + sk[j];
+                for (int j = 0; j < 16; ++j) de[j * TILE_M] = (cg * 16 + j == 63) ? 0.0f : g[j] + de[j * TILE_M];
             }
             tc::tc_fence_before_sync();
             tc::named_bar_sync(1, EPI_THREADS);
             if (p.d_pts && cg < 3 && live) {
                 const float* __restrict__ e = p.E + eoff(gp, 3 + cg * 20);
                 const float* __restrict__ b = p.EB + eoff(gp, 3 + cg * 20);
-                const float* __restrict__ g = s_skip + row * SW_SCR_LD + 3 + cg * 20;
-                float acc = s_skip[row * SW_SCR_LD + cg], hess = 0.0f, f = 1.0f;
+                const float* __restrict__ g = p.DE + eoff(gp, 3 + cg * 20);
+                float acc = p.DE[eoff(gp, cg)], hess = 0.0f, f = 1.0f;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
                     const float sn = e[k * TILE_M], cs = e[(10 + k) * TILE_M];
-                    acc += f * (cs * g[k] - sn * g[10 + k]);
+                    acc += f * (cs * g[k * TILE_M] - sn * g[(10 + k) * TILE_M]);
                     hess -= f * f * (sn * b[k * TILE_M] + cs * b[(10 + k) * TILE_M]);
                     f *= 2.0f;
                 }
@@ -749,8 +716,8 @@ static M16Stash m16_stash(float* stash, int64_t np) {
     return s;
 }
 int64_t m16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (128 + 32 + 32 * 128); }
-// backward workspace: U16[8] | X16[8] | DZ16[8] | DF16 | UE16 | partial sums of the dW kernel
-int64_t m16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (25 * 128 + 32) + dw_part_floats(9); }
+// backward workspace: U16[8] | X16[8] | DZ16[8] | DF16 | UE16 | DE (fp32) | partial sums of the dW kernel
+int64_t m16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (25 * 128 + 32 + 64) + dw_part_floats(9); }
 
 static int check_m16(const hn_mlp_t* m) {
     HN_REQUIRE(m && m->n_layers == 9, "object SDF mlp must have 9 layers");
@@ -759,20 +726,13 @@ static int check_m16(const hn_mlp_t* m) {
     return HN_OK;
 }
 
-static void sw_layer(SwProgram& prog, int& k, const uint32_t off[2], int n_halves, int n_mma, int kblocks, int layer_idx, int f16) {
-    for (int h = 0; h < n_halves; ++h) {
-        SwStep& st = prog.step[k++];
-        st.b_off = off[h];
-        st.n_mma = (uint16_t)n_mma;
-        st.kblocks = (uint8_t)kblocks;
-        (void)layer_idx;
-        st.a_buf = 0;
-        st.a_pair = 1;
-        st.wait_a = (uint8_t)(h == 0);
-        st.f16 = (uint8_t)f16;
-        st.passes = 2;
-        st.acc_col = (uint16_t)(128 * h);
-    }
+static void sw_layer(SwProgram& prog, int& k, uint32_t off, int n_mma, int kblocks, int f16, bool acc_in = false) {
+    SwStep& st = prog.step[k++];
+    st.b_off = off;
+    st.n_mma = (uint16_t)n_mma;
+    st.kblocks = (uint8_t)kblocks;
+    st.f16 = (uint8_t)f16;
+    st.acc_in = acc_in ? 1 : 0;
 }
 
 int launch_m16_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, float* feat, int64_t ld_feat,
@@ -832,8 +792,7 @@ int launch_m16_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
         p.dbg = dbg_slot(1);
         SwProgram prog = {};
         int k = 0;
-        for (int l = 7; l >= 1; --l) sw_layer(prog, k, L.nnh_off[l], 2, 128, 4, 7 - l, 1);
-        sw_layer(prog, k, L.nnh_off[0], 1, 64, 4, 7, 1);
+        for (int l = 7; l >= 0; --l) sw_layer(prog, k, L.nn16_off[l], L.nn_n[l], L.nn_kb[l], 1);         // d @ W_l
         prog.n_steps = k;
         TimingScope ts(s, TT_SDF_FWD);
         nsweep16_kernel<<<grid, SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);
@@ -858,6 +817,7 @@ int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     for (int l = 0; l < 8; ++l) { DZ16[l] = b; b += np * 512; }
     uint8_t* DF16 = b; b += np * 512;
     uint8_t* UE16 = b; b += np * 128;
+    float* DE = reinterpret_cast<float*>(b); b += np * 256;
     float* part = reinterpret_cast<float*>(b);
     static bool configured = false;
     if (!configured) {
@@ -876,17 +836,16 @@ int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
             for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{S.EM[l - 1], nullptr};           // reverse sweep
         in.n_events = ne;
         p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.d_normal = d_normal; p.d_pts = d_pts;
-        p.UE16 = UE16; p.DF16 = DF16;
+        p.UE16 = UE16; p.DF16 = DF16; p.DE = DE;
         p.store_dw = grad ? 1 : 0;
         p.chain = reinterpret_cast<const uint8_t*>(m->chain);
         p.w_out0 = m->W[8];
         p.n_tiles = n_tiles;
         p.dbg = dbg_slot(2);
         SwProgram prog = {};
-        int k = 0, idx = 0;
-        for (int l = 0; l < 8; ++l, ++idx) sw_layer(prog, k, L.ntb_off[l], 2, 128, L.nt_kb[l], idx, 0);      // tangent: u @ W_l^T
-        for (int l = 8; l >= 1; --l, ++idx) sw_layer(prog, k, L.nnb_off[l], 2, 128, 4, idx, 0);               // reverse: dz @ W_l
-        sw_layer(prog, k, L.nnb_off[0], 1, 64, 4, idx, 0);
+        int k = 0;
+        for (int l = 0; l < 8; ++l) sw_layer(prog, k, L.nt_off[l], L.nt_n[l], L.nt_kb[l], 0, l == 3);     // tangent: u @ W_l^T
+        for (int l = 8; l >= 0; --l) sw_layer(prog, k, L.nn_off[l], L.nn_n[l], L.nn_kb[l], 0);            // reverse: dz @ W_l
         prog.n_steps = k;
         TimingScope ts(s, TT_SDF_BWD);
         bwd16_kernel<<<std::min(n_tiles, sm_count()), SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);

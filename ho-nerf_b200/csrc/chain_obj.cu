@@ -908,28 +908,13 @@ int hn_sdf_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_byte
                                                   std::max(0, std::min(128, rows - 128 * h)), in_d[l], 128, L.nt_kb[l],
                                                   dst + L.nth_off[l][h], s, true));
     }
-    // HN_TC_MIXED16 operands (chain16_obj.cu): 128-row halves of every sweep
+    // HN_TC_MIXED16 operands (chain16_obj.cu): the feature head as 128-row halves, the normal sweep's weights as fp16 pairs
     for (int h = 0; h < 2; ++h)
         HN_PROPAGATE(chain::launch_pack_b(m->W[8], m->ld[8], chain::pack_map(1 + 128 * h, 0), 128, 256, 128, 4,
                                           dst + L.nth8_off[h], s, true));
     for (int l = 0; l < 8; ++l)
-        for (int h = 0; h < 2; ++h)
-            HN_PROPAGATE(chain::launch_pack_b(m->W[l], m->ld[l], chain::pack_map(128 * h, 0),
-                                              std::max(0, std::min(128, out_d[l] - 128 * h)), in_d[l], 128, L.nt_kb[l],
-                                              dst + L.ntb_off[l][h], s, false));
-    for (int l = 0; l < 9; ++l) {
-        const int row0 = l == 8 ? 1 : 0;
-        const int k_out = l == 8 ? 256 : out_d[l];
-        for (int h = 0; h < (l == 0 ? 1 : 2); ++h) {
-            const int n_pad = l == 0 ? 64 : 128;
-            const int n_rows = std::max(0, std::min(n_pad, in_d[l] - 128 * h));
-            HN_PROPAGATE(chain::launch_pack_b(m->WT[l], m->ldT[l], chain::pack_map(128 * h, row0), n_rows, k_out, n_pad, 4,
-                                              dst + L.nnb_off[l][h], s, false));
-            if (l < 8)
-                HN_PROPAGATE(chain::launch_pack_b(m->WT[l], m->ldT[l], chain::pack_map(128 * h, row0), n_rows, k_out, n_pad, 4,
-                                                  dst + L.nnh_off[l][h], s, true));
-        }
-    }
+        HN_PROPAGATE(chain::launch_pack_b(m->WT[l], m->ldT[l], chain::pack_map(0, 0), in_d[l], out_d[l], L.nn_n[l], L.nn_kb[l],
+                                          dst + L.nn16_off[l], s, true));
     return chain::pack_batch_flush(s);
 }
 

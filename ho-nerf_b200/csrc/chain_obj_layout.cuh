@@ -13,11 +13,9 @@ struct ObjLayout {
     uint32_t nt_off[9], nn_off[9];
     uint32_t nt16_off[9];         // a @ W_l^T operands again as fp16 (hi + lo) pairs: the forward value trunk
     uint32_t nth_off[8][2];       // layers 0..7 once more as two 128-row halves (fp16 pairs): chain_ts.cu
-    // HN_TC_MIXED16 (chain16_obj.cu): every operand as 128-row halves
-    uint32_t nth8_off[2];         // feature head (rows 1..256 of the output layer), fp16 pairs: a @ W_8^T
-    uint32_t ntb_off[8][2];       // tangent sweep u @ W_l^T, bf16 pairs
-    uint32_t nnb_off[9][2];       // reverse sweep dz @ W_l, bf16 pairs ([0][0]: the 64-row encoding layer)
-    uint32_t nnh_off[8][2];       // normal sweep d @ W_l, fp16 pairs ([0][0]: the 64-row encoding layer)
+    // HN_TC_MIXED16 (chain16_obj.cu)
+    uint32_t nth8_off[2];         // feature head (rows 1..256 of the output layer) as two 128-row halves, fp16 pairs: a @ W_8^T
+    uint32_t nn16_off[8];         // normal sweep d @ W_l as fp16 pairs (same shapes as nn_off)
     uint16_t nt_n[9], nn_n[9];
     uint8_t nt_kb[9], nn_kb[9];
     uint32_t total;
@@ -47,14 +45,7 @@ inline ObjLayout obj_layout() {
             off += b_operand_bytes(128, L.nt_kb[l]);
         }
     for (int h = 0; h < 2; ++h) { L.nth8_off[h] = off; off += b_operand_bytes(128, 4); }
-    for (int l = 0; l < 8; ++l)
-        for (int h = 0; h < 2; ++h) { L.ntb_off[l][h] = off; off += b_operand_bytes(128, L.nt_kb[l]); }
-    for (int l = 0; l < 9; ++l)
-        for (int h = 0; h < (l == 0 ? 1 : 2); ++h) { L.nnb_off[l][h] = off; off += b_operand_bytes(l == 0 ? 64 : 128, 4); }
-    L.nnb_off[0][1] = 0;
-    for (int l = 0; l < 8; ++l)
-        for (int h = 0; h < (l == 0 ? 1 : 2); ++h) { L.nnh_off[l][h] = off; off += b_operand_bytes(l == 0 ? 64 : 128, 4); }
-    L.nnh_off[0][1] = 0;
+    for (int l = 0; l < 8; ++l) { L.nn16_off[l] = off; off += b_operand_bytes(L.nn_n[l], L.nn_kb[l]); }
     L.total = off;
     return L;
 }

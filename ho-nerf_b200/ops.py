@@ -10,11 +10,12 @@ from ._lib import HN_SIMT_FP32, HN_WS_BWD, HN_WS_SDF_ONLY, check, hn_mlp_grad_t,
 
 _PRECISIONS = {"simt_fp32": _lib.HN_SIMT_FP32, "tc_tf32": _lib.HN_TC_TF32, "tc_tf32x3": _lib.HN_TC_TF32X3,
                "tc_bf16x3": _lib.HN_TC_BF16X3, "tc_mixed16": _lib.HN_TC_MIXED16}
-# Product default: the fused tcgen05 chain kernels.  'simt_fp32' is the verification path (the north star's
+# Product default: 'tc_mixed16' = the fused tcgen05 chain kernels with the 16-bit activation stash for the object SDF field
+# (csrc/chain16*.cu), 'tc_bf16x3' arithmetic everywhere else.  'simt_fp32' is the verification path (the north star's
 # "fp32 SIMT path kept for verification"); HONERF_PRECISION overrides the default at import.
 import os as _os
 
-_default_precision = _PRECISIONS[_os.environ.get("HONERF_PRECISION", "tc_bf16x3")]
+_default_precision = _PRECISIONS[_os.environ.get("HONERF_PRECISION", "tc_mixed16")]
 
 
 def set_default_precision(name):

@@ -28,7 +28,8 @@ def pytest_collection_modifyitems(config, items):
 
 
 # Parity tests written against the fp32 SIMT verification path (tolerances ~1e-5) pin it explicitly; the tensor-core
-# default (tc_bf16x3) has its own tests (test_gpu_chain.py, test_gpu_product_default.py) with its own stated bounds.
+# default (tc_mixed16) has its own tests (test_gpu_mixed16.py, test_gpu_bench_shape.py, test_gpu_product_default.py,
+# test_gpu_obj_tc.py) with its own stated bounds; test_gpu_chain.py pins tc_bf16x3 explicitly.
 _SIMT_MODULES = ("test_gpu_obj_fields", "test_gpu_render", "test_gpu_hand", "test_gpu_fit")
 
 

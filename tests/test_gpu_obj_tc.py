@@ -1,7 +1,7 @@
 """GPU parity of the tensor-core paths at the north-star tolerances (max-abs <= 1e-3 on colour / SDF, <= 1e-2
-relative on normals and gradients): 'tc_bf16x3' (the product default: fused tile-chain kernels, split bf16
-operands) and 'tc_tf32x3' (per-layer tcgen05 GEMMs, split TF32 operands); 'tc_tf32' (single pass) is the
-reduced-accuracy mode and is only held to 1e-2."""
+relative on normals and gradients): 'tc_mixed16' (the product default: fused tile-chain kernels with the 16-bit
+activation stash), 'tc_bf16x3' (fused tile-chain kernels, fp32 stash) and 'tc_tf32x3' (per-layer tcgen05 GEMMs, split
+TF32 operands); 'tc_tf32' (single pass) is the reduced-accuracy mode and is only held to 1e-2."""
 import pytest
 import torch
 
@@ -14,7 +14,7 @@ from gpu_util import DEV, obj_modules
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tc_bf16x3", "tc_tf32x3", "tc_tf32"])
+@pytest.fixture(params=["tc_mixed16", "tc_bf16x3", "tc_tf32x3", "tc_tf32"])
 def tc_precision(request):
     import honerf_b200 as H
     H.set_default_precision(request.param)

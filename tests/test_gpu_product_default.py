@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 def test_default_precision_is_the_tensor_core_chain_path():
     import honerf_b200 as H
-    assert H.ops.default_precision() == H.ops._PRECISIONS["tc_bf16x3"]
+    assert H.ops.default_precision() == H.ops._PRECISIONS["tc_mixed16"]
 
 
 def test_render_vs_golden_with_default_precision():
@@ -38,7 +38,7 @@ def test_render_vs_golden_with_default_precision():
     loss.backward()
     # end to end the importance samples themselves move when a coarse SDF value differs by 1e-5 (the sampler's
     # sigmoid has inv_s up to 512), which shifts some gradients by ~1 %: same 5e-2 bound as the SIMT end-to-end test;
-    # the strict 1e-2 check on identical z_vals is test_gpu_obj_tc.py::test_render_core_given_same_z_tc[tc_bf16x3]
+    # the strict 1e-2 check on identical z_vals is test_gpu_obj_tc.py::test_render_core_given_same_z_tc[tc_mixed16] and tests/test_gpu_bench_shape.py
     grads = {"sdf." + k: p.grad.cpu() for k, p in sdf.named_parameters() if p.grad is not None}
     grads.update({"color." + k: p.grad.cpu() for k, p in col.named_parameters() if p.grad is not None})
     grads.update({"variance": dev.variance.grad.cpu(), "Ro": Ro.grad.cpu(), "To": To.grad.cpu()})
