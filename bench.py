@@ -155,49 +155,111 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference algorithm (oracle port, torch CPU, all host threads)
 # ------------------------------------------------------------------------------------------------
-def cpu_train_step_fn(n_rays, seed=7):
+def _reference_modules():
+    """The UNMODIFIED reference's hot-path modules (oracle/ref_loader.py) when its tree is reachable: HONERF_REFERENCE_ROOT,
+    baseline/_ref or /root/reference (the build container).  None on the GPU box, where only the oracle port travels."""
+    for root in (os.environ.get("HONERF_REFERENCE_ROOT"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if root and os.path.isfile(os.path.join(root, "utils", "renderer.py")):
+            os.environ["HONERF_REFERENCE_ROOT"] = root
+            try:
+                import importlib
+                import ref_loader
+                importlib.reload(ref_loader)
+                return ref_loader, ref_loader.load_reference()
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write("bench.py: reference tree at %s could not be imported (%s); using the oracle port\n" % (root, e))
+    return None, None
+
+
+def cpu_step_fns(n_rays, seed=7):
+    """(train_step, forward_only, kind): the reference algorithm on the host.  kind = "reference" when the reference's own
+    NeuSRenderer / networks run (utils/renderer.py, utils/fields.py through oracle/ref_loader.py), else "port"
+    (oracle/honerf_oracle.py).  Same synthetic batch, weights and loss either way."""
     import honerf_oracle as O
     import synth
+    B = synthetic_batch(n_rays, seed)
+    rl, ref = _reference_modules()
+    if ref is not None:
+        sp, cp = synth.obj_states()
+        emb = ref.fields.Embedding()
+        sdf = ref.fields.SDFNetwork_OBJ(emb, 4, "real", **rl.OBJ_SDF_CONF)
+        col = ref.fields.RenderingNetwork_OBJ(emb, "real", **rl.OBJ_COLOR_CONF)
+        dev = ref.fields.SingleVarianceNetwork(rl.VARIANCE_INIT)
+        sdf.load_state_dict(sp); col.load_state_dict(cp)
+        r = ref.renderer.NeuSRenderer(sdf, dev, col, "obj", **rl.RENDERER_CONF)
+        params = list(sdf.parameters()) + list(dev.parameters()) + list(col.parameters())
+        opt = torch.optim.Adam(params, lr=1e-4)
+        zb, zT = torch.zeros(21, 4, 4), torch.zeros(21, 3)
+
+        def render():
+            return r.render(B["rays_o"], B["rays_d"], B["near"], B["far"], zb, zT, None, B["Ro"], B["To"], 0)
+
+        def step():
+            out = render()
+            loss = training_loss(out, B["true_rgb"], B["true_mask"])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return float(loss)
+
+        def fwd():
+            with torch.no_grad():
+                # the reference's gradient() needs autograd even for a forward render (utils/fields.py:336-347)
+                with torch.enable_grad():
+                    return float(render()["color_fine"].sum())
+        return step, fwd, "reference"
     sp, cp = synth.obj_states()
     sp = {k: v.clone().requires_grad_(k != "se3_refine") for k, v in sp.items()}
     cp = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
     var = torch.tensor(0.3, requires_grad=True)
-    B = synthetic_batch(n_rays, seed)
     params = [v for k, v in sp.items() if k != "se3_refine"] + list(cp.values()) + [var]
     opt = torch.optim.Adam(params, lr=1e-4)
 
+    def render():
+        return O.render_obj(sp, cp, var, B["rays_o"], B["rays_d"], B["near"], B["far"], B["Ro"], B["To"], B["t_rand"])
+
     def step():
-        out = O.render_obj(sp, cp, var, B["rays_o"], B["rays_d"], B["near"], B["far"], B["Ro"], B["To"],
-                           B["t_rand"])
-        loss = O.training_loss(out, B["true_rgb"], B["true_mask"])
+        loss = O.training_loss(render(), B["true_rgb"], B["true_mask"])
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
         return float(loss)
-    return step
+
+    def fwd():
+        return float(render()["color_fine"].sum())
+    return step, fwd, "port"
 
 
-def time_cpu(n_rays, steps, warmup):
+def time_cpu(n_rays, steps, warmup, forward_steps=0):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = cpu_train_step_fn(n_rays)
+    step, fwd, kind = cpu_step_fns(n_rays)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return n_rays / dt, dt, cores
+    fwd_rps = None
+    if forward_steps > 0:
+        fwd()
+        t0 = time.perf_counter()
+        for _ in range(forward_steps):
+            fwd()
+        fwd_rps = n_rays / ((time.perf_counter() - t0) / forward_steps)
+    return n_rays / dt, dt, cores, kind, fwd_rps
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_rays = min(args.rays, 512)      # bounded sample: one 512-ray batch per step (~3 s on 8 cores)
-    # exactly K steps / W warm-ups as asked, bounded so the arm stays within a few minutes (~1-4 s per step on the host)
-    steps, warmup = max(1, min(args.steps, 20)), max(1, min(args.warmup, 3))
-    rps, dt, cores = time_cpu(n_rays, steps, warmup)
+    n_rays = min(args.rays, 512)      # bounded sample: one 512-ray batch per step (~1.5-4 s on the host)
+    # exactly the K steps / W warm-ups asked for, bounded so that the arm stays within a few minutes
+    steps, warmup = max(1, min(args.steps, 40)), max(0, min(args.warmup, 10))
+    rps, dt, cores, kind, fwd_rps = time_cpu(n_rays, steps, warmup, forward_steps=2)
+    what = ("the reference's own NeuSRenderer / SDFNetwork_OBJ / RenderingNetwork_OBJ (oracle/ref_loader.py)" if kind == "reference"
+            else "oracle/honerf_oracle.py (functional port, pinned to the reference by tests/golden)")
     line = {
         "impl": "reference", "metric": "rays/sec render fwd+bwd (64+64 samples), object-field train step",
         "value": rps, "unit": "rays/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -205,8 +267,10 @@ def run_reference_arm(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD % n_rays, "rays_per_gpu": n_rays, "precision": "f32 (torch CPU)",
                    "parallelism": "CPU threads x%d" % cores},
-        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": "%d steps of one %d-ray batch (oracle/honerf_oracle.py, torch CPU)" % (steps, n_rays)},
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": "%d steps of one %d-ray batch: %s, torch CPU" % (steps, n_rays, what)},
+        "forward_only": {"value": fwd_rps, "unit": "rays/s", "workload": "BASELINE configs[0]: render_core forward, %d rays x (64+64) "
+                         "samples, on CPU" % n_rays},
         "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -340,6 +404,170 @@ def forward_extras(H, device, renderer, batch, host, Ro, To, hand_rays_n):
         res["hand_render_fwd"] = {"rays": hand_rays_n, "ms": ms, "value": hand_rays_n / (ms * 1e-3), "unit": "rays/s",
                                   "note": "hand field on the per-layer kernels (chain kernels: object field only)"}
     return res
+
+
+def _dist_max_ms(ms, device, world):
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+    return ms
+
+
+def _timed_region(fn, device, world):
+    """fn() between barrier + synchronize on both sides, CUDA events, max over ranks; returns (ms, fn's result)."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    return _dist_max_ms(e0.elapsed_time(e1), device, world), out
+
+
+def lattice_extra(H, renderer, device, res, rank, world):
+    """BASELINE configs[1]: SDFNetwork_OBJ.sdf on the res^3 lattice of extract_geometry (utils/renderer.py:260-284,
+    bbox [-0.2, 0.2]^3 of exp_runner.py:511-517), sharded over the ranks in x slabs (honerf_b200.dist.shard_rays on the x
+    axis) with a final all-gather of u; the lattice points are generated inside the kernel (hn_sdf_obj_grid)."""
+    from honerf_b200 import dist as hdist
+    bmin, bmax = torch.full((3,), -0.2), torch.full((3,), 0.2)
+    sizes = [hdist.shard_rays(res, r, world) for r in range(world)]
+    lo, hi = sizes[rank]
+    renderer.sdf_grid(bmin, bmax, 64)
+
+    def run():
+        u = renderer.sdf_grid(bmin, bmax, res, x_range=(lo, hi))
+        return hdist.gather_slabs(u, [b - a for a, b in sizes], dim=0) if world > 1 else u
+    ms, u = _timed_region(run, device, world)
+    npts = res ** 3
+    out = {"resolution": res, "ms": ms, "points_per_s": npts / (ms * 1e-3), "algorithmic_tflops": npts * F_O / (ms * 1e-3) / 1e12,
+           "finite": bool(torch.isfinite(u).all()), "shape": list(u.shape), "sharding": "x slabs x%d + all-gather of u" % world,
+           "n_gpus": world}
+    del u
+    return out
+
+
+def hand_views_extra(H, device, rank, world, image=512, chunk=4096):
+    """BASELINE configs[3]: full-image render of synthetic image x image views of the hand field (HALO pose-conditioned,
+    wmask_realhand_hand1.conf), ONE VIEW PER GPU (weak scaling: N GPUs render N views), rays generated on the device
+    from the NDC grid in chunks (exp_runner.py:338-369)."""
+    import math
+    import ref_conf
+    import synth
+    from honerf_b200 import rays as hrays
+    hsp, hcp = synth.hand_states()
+    emb = H.Embedding()
+    hs = H.SDFNetwork(emb, 4, "real", use_batch=False, **ref_conf.HAND_SDF_CONF)
+    hc = H.RenderingNetwork(emb, "real", **ref_conf.HAND_COLOR_CONF)
+    hd = H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT)
+    hs.load_state_dict(hsp); hc.load_state_dict(hcp)
+    for m in (hs, hc, hd):
+        m.to(device)
+    rh = H.NeuSRenderer(hs, hd, hc, "hand", **dict(ref_conf.RENDERER_CONF, perturb=0.0))
+    bt, T, J = synth.hand_pose()
+    bt, T = bt.to(device), T.to(device)
+    # camera `rank` of 8 on a ring around the hand, looking at its centroid (pytorch3d row-vector convention)
+    a = 2.0 * math.pi * rank / 8.0
+    c = J.mean(0)
+    eye = c + 0.9 * torch.tensor([math.sin(a), 0.0, -math.cos(a)])
+    zax = torch.nn.functional.normalize(c - eye, dim=0)
+    xax = torch.nn.functional.normalize(torch.linalg.cross(torch.tensor([0.0, 1.0, 0.0]), zax), dim=0)
+    yax = torch.linalg.cross(zax, xax)
+    R = torch.stack([xax, yax, zax], dim=1)[None]
+    Tc = (-(eye @ R[0]))[None]
+    cam = hrays.PerspectiveCameras(R, Tc, torch.tensor([[6.0, 6.0]]), torch.zeros(1, 2)).to(device)
+
+    def run():
+        img = torch.empty(image * image, 3, device=device)
+        with torch.no_grad():
+            first = 0
+            for ro, rd in hrays.image_ray_chunks(cam, image, image, chunk):
+                out = rh.render(ro, rd, 0.4, 1.5, bt, T, None, None, None, 0)
+                img[first:first + len(ro)] = out["color_fine"]
+                first += len(ro)
+        return img
+    with torch.no_grad():
+        ro, rd = next(iter(hrays.image_ray_chunks(cam, image, image, chunk)))
+        rh.render(ro, rd, 0.4, 1.5, bt, T, None, None, None, 0)
+    ms, img = _timed_region(run, device, world)
+    n = image * image
+    return {"views": world, "image": [image, image], "rays": world * n, "ms": ms, "value": world * n / (ms * 1e-3), "unit": "rays/s",
+            "finite": bool(torch.isfinite(img).all()), "coverage": float((img.sum(-1) > 0).float().mean()),
+            "algorithmic_tflops": world * n * (112 * 2_468_352 + 128 * (2 * 2_468_352 + 1_249_280)) / (ms * 1e-3) / 1e12,
+            "sharding": "one %dx%d view per GPU" % (image, image)}
+
+
+def fitting_views_extra(H, device, rank, world, n_views=8, rays_per_view=196, iters=2):
+    """BASELINE configs[4]: one pose-fitting iteration of fitting_single.py:200-291 over the 8 views of a frame (fit_12_8views:
+    196 rays per view), views sharded over the ranks, pose gradients (bt_inv, Ro, To) SUMMED with one flat NCCL all-reduce
+    (honerf_b200.dist.allreduce_gradients(average=False)).  Rank 0 also renders all views alone and checks the summed
+    gradient against it."""
+    import ref_conf
+    import synth
+    from honerf_b200 import dist as hdist
+    hsp, hcp = synth.hand_states()
+    osp, ocp = synth.obj_states()
+    emb = H.Embedding()
+    hs = H.SDFNetwork(emb, 4, "real", use_batch=False, **ref_conf.HAND_SDF_CONF)
+    hc = H.RenderingNetwork(emb, "real", **ref_conf.HAND_COLOR_CONF)
+    os_ = H.SDFNetwork_OBJ(emb, 4, "real", **ref_conf.OBJ_SDF_CONF)
+    oc = H.RenderingNetwork_OBJ(emb, "real", **ref_conf.OBJ_COLOR_CONF)
+    hd, od = H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT), H.SingleVarianceNetwork(ref_conf.VARIANCE_INIT)
+    hs.load_state_dict(hsp); hc.load_state_dict(hcp); os_.load_state_dict(osp); oc.load_state_dict(ocp)
+    for m in (hs, hd, hc, os_, od, oc):
+        m.to(device)
+        for q in m.parameters():
+            q.requires_grad_(False)
+    r = H.renderer.NeuSRenderer_fitting(hs, hd, hc, os_, od, oc, **dict(ref_conf.RENDERER_CONF, perturb=0.0))
+    bt0, T, J = synth.hand_pose()
+    g = torch.Generator().manual_seed(106)
+    Ro0 = synth.random_rotation(g)
+    To0 = J.mean(0) + 0.02 * torch.randn(3, generator=g)
+    views = []
+    for v in range(n_views):
+        HR = synth.hand_rays(rays_per_view, J, seed=40 + v)
+        gv = torch.Generator().manual_seed(200 + v)
+        views.append((HR["rays_o"].to(device), HR["rays_d"].to(device), torch.rand(rays_per_view, 3, generator=gv).to(device),
+                      (torch.rand(rays_per_view, 1, generator=gv) > 0.3).float().to(device)))
+    T = T.to(device)
+    bt = bt0.to(device).requires_grad_(True)
+    Ro, To = Ro0.to(device).requires_grad_(True), To0.to(device).requires_grad_(True)
+    pose = [bt, Ro, To]
+
+    def iteration(lo, hi, reduce):
+        for q in pose:
+            q.grad = None
+        for v in range(lo, hi):
+            ro, rd, rgb, mask = views[v]
+            out = r.render(ro, rd, 0.4, 1.5, bt, T, None, Ro, To)
+            loss = H.losses.fitting_render_loss(out, rgb, mask) + H.losses.interaction_loss(out)
+            loss.backward()                              # gradients of the views of this rank accumulate
+        if reduce:
+            hdist.allreduce_gradients(pose, world, average=False)
+        return [q.grad.clone() for q in pose]
+    lo, hi = hdist.shard_views(n_views, rank, world)
+    iteration(lo, hi, world > 1)
+    ms, grads = _timed_region(lambda: [iteration(lo, hi, world > 1) for _ in range(iters)][-1], device, world)
+    ms /= iters
+    check = None
+    if world > 1:
+        ref = iteration(0, n_views, False) if rank == 0 else None
+        if rank == 0:
+            check = max(float((a - b).norm() / (b.norm() + 1e-30)) for a, b in zip(grads, ref))
+    n = n_views * rays_per_view
+    return {"views": n_views, "rays_per_view": rays_per_view, "samples_per_ray_and_field": 192, "ms_per_iteration": ms,
+            "value": n / (ms * 1e-3), "unit": "rays/s", "finite_pose_grads": bool(all(torch.isfinite(q).all() for q in grads)),
+            "pose_grad_allreduce_vs_single_rank_rel_err": check,
+            "algorithmic_tflops": n * 3_799_990_000 / (ms * 1e-3) / 1e12,
+            "sharding": "views x%d, one flat all-reduce (SUM) of the 336 + 9 + 3 pose-gradient floats" % world,
+            "loss": "fitting_single.py:253-283 (render + 30 contact + 20 penetration), fused loss kernels"}
 
 
 def _dbg(msg):
@@ -484,21 +712,41 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     _dbg("warm-up done, %d launches per step" % launches_per_step)
     graph, graph_b, loss_static = None, None, None
+    nccl_in_graph = False
     if not args.no_graph:
         try:
-            # N = 1: one graph for the whole step.  N > 1: graph A = render + loss + backward + gradient packing, then
-            # the NCCL all-reduce launched eagerly (never captured), then graph B = unpack + Adam.
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                loss_static = fwd_bwd(static) if world > 1 else train_step(static)
-            if world > 1:
-                graph_b = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph_b, pool=graph.pool()):
-                    apply_grads()
-            graph.replay()
-            if world > 1:
-                reduce_grads()
-                graph_b.replay()
+            # N = 1: one graph for the whole step.  N > 1: first try ONE graph as well, with the NCCL all-reduce captured as a
+            # node between the backward pass and Adam (no launch gap around the collective); if this NCCL / driver
+            # refuses, fall back to graph A = render + loss + backward + gradient packing, the all-reduce launched eagerly,
+            # graph B = Adam.  Every rank takes the same path (the outcome of the capture is all-reduced).
+            if world > 1 and not args.no_nccl_graph:
+                ok = 1
+                try:
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        loss_static = train_step(static)
+                    g1.replay()
+                    torch.cuda.synchronize()
+                except Exception as e:      # noqa: BLE001
+                    sys.stderr.write("bench.py: NCCL in a CUDA graph refused (%s); using the two-graph step\n" % str(e)[:200])
+                    ok = 0
+                import torch.distributed as dist
+                flag = torch.tensor([ok], device=device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag) == 1:
+                    graph, nccl_in_graph = g1, True
+            if graph is None:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    loss_static = fwd_bwd(static) if world > 1 else train_step(static)
+                if world > 1:
+                    graph_b = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph_b, pool=graph.pool()):
+                        apply_grads()
+                graph.replay()
+                if world > 1:
+                    reduce_grads()
+                    graph_b.replay()
             torch.cuda.synchronize()
             if not torch.isfinite(loss_static).all():
                 raise RuntimeError("non-finite loss from the captured step")
@@ -582,47 +830,67 @@ def run_gpu_arm(args):
         except Exception as e:      # noqa: BLE001
             large = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
+    # ---- strong scaling: the SAME 512 rays split over the ranks, eager launches ------------------------------
+    strong = None
+    if world > 1 and args.strong_rays > 0:
+        from honerf_b200 import dist as hdist
+        hb = synthetic_batch(args.strong_rays, seed=7)        # the same batch on every rank
+        lo, hi = hdist.shard_rays(args.strong_rays, rank, world)
+        sb = {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] == args.strong_rays else v) for k, v in hb.items()}
+        sb = {k: v.to(device) for k, v in sb.items() if torch.is_tensor(v)}
+        n_keep = n_rays
+        n_rays = hi - lo                                      # fwd_bwd's shard weights use the local ray count
+        renderer.ray_streams = 1
+        for _ in range(3):
+            train_step(sb)
+        ms_s = timed(lambda: train_step(sb), 5) / 5
+        renderer.ray_streams = args.ray_streams
+        n_rays = n_keep
+        strong = {"rays_total": args.strong_rays, "rays_per_gpu": hi - lo, "ms_per_step": ms_s,
+                  "value": args.strong_rays / (ms_s * 1e-3), "unit": "rays/s",
+                  "note": "strong scaling: one 512-ray batch split over the ranks (per-rank mean losses, gradients averaged), eager launches"}
+    # ---- the other BASELINE configs, sharded over the ranks (every rank takes part: they contain collectives) --------------
     grid = None
-    if rank == 0 and world == 1 and args.grid_res > 0:
-        # informational (BASELINE configs[1]): SDFNetwork_OBJ.sdf on the res^3 lattice of extract_geometry
+    if args.grid_res > 0:
         try:
-            bmin, bmax = torch.full((3,), -0.2), torch.full((3,), 0.2)
-            renderer.sdf_grid(bmin, bmax, 64)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            u = renderer.sdf_grid(bmin, bmax, args.grid_res)
-            e1.record()
-            torch.cuda.synchronize()
-            ms_g = e0.elapsed_time(e1)
-            npts = args.grid_res ** 3
-            grid = {"resolution": args.grid_res, "ms": ms_g, "points_per_s": npts / (ms_g * 1e-3),
-                    "algorithmic_tflops": npts * F_O / (ms_g * 1e-3) / 1e12, "finite": bool(torch.isfinite(u).all())}
-            del u
+            grid = lattice_extra(H, renderer, device, args.grid_res, rank, world)
         except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise
             grid = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
     fit = None
-    if rank == 0 and world == 1 and args.fit_rays > 0:
+    if args.fit_rays > 0:
         try:
-            fit = fitting_extra(H, device, args.fit_rays, args.precision)
+            fit = fitting_views_extra(H, device, rank, world)
+            if world == 1:
+                fit["one_512_ray_batch"] = fitting_extra(H, device, args.fit_rays, args.precision)
         except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise
             fit = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
     fwd_extra = None
-    if rank == 0 and world == 1 and args.fit_rays > 0:
+    if args.fit_rays > 0:
         try:
-            renderer.ray_streams = 1          # eager launches: extra streams only add CPU launch work here
-            fwd_extra = forward_extras(H, device, renderer, dev_batch, host, Ro, To, 4096)
-            renderer.ray_streams = args.ray_streams
+            fwd_extra = {}
+            if world == 1:
+                renderer.ray_streams = 1          # eager launches: extra streams only add CPU launch work here
+                fwd_extra = forward_extras(H, device, renderer, dev_batch, host, Ro, To, 4096)
+                renderer.ray_streams = args.ray_streams
+            fwd_extra["hand_views"] = hand_views_extra(H, device, rank, world, image=args.view_size)
         except Exception as e:      # noqa: BLE001
+            if world > 1:
+                raise
             fwd_extra = {"error": str(e)[:200]}
         torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, dt, cores = time_cpu(min(n_rays, 512), 3, 1)
-        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port",
-               "sample": "3 steps of one %d-ray batch (oracle/honerf_oracle.py, torch CPU)" % min(n_rays, 512)}
+        rps, dt, cores, kind, fwd_rps = time_cpu(min(n_rays, 512), 3, 1, forward_steps=2)
+        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": kind,
+               "sample": "3 steps of one %d-ray batch (%s, torch CPU)" % (
+                   min(n_rays, 512), "the reference's own classes" if kind == "reference" else "oracle/honerf_oracle.py"),
+               "forward_only_rays_per_s": fwd_rps}
     if rank == 0:
         line = {
             "metric": "rays/sec render fwd+bwd (64+64 samples), object-field train step",
@@ -636,6 +904,8 @@ def run_gpu_arm(args):
             "config": {"workload": WORKLOAD % n_rays,
                        "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
                        "cuda_graph": graph is not None,
+                       "allreduce": (None if world == 1 else "NCCL all-reduce of the flat gradient buffer captured in the step's CUDA graph"
+                                     if nccl_in_graph else "NCCL all-reduce launched eagerly between two CUDA graphs"),
                        "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
                        "loss": "hn_render_loss_fwd/_bwd (fused)" if args.loss == "fused" else "torch ops",
                        "ray_streams": args.ray_streams, "ray_shards": args.ray_shards or "equal",
@@ -644,7 +914,8 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e},
             "gpu_launches": int(launches),
-            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large, "sdf_grid": grid, "fitting_step": fit, "forward_only": fwd_extra,
+            "clocks": clocks, "roofline": roof, "compositor": comp, "cpu_baseline": cpu, "large_batch": large,
+            "strong_scaling": strong, "sdf_grid": grid, "fitting_step": fit, "forward_only": fwd_extra,
             "mlp_flops_per_ray": FLOPS_PER_RAY_TRAIN,
         }
         os.write(json_fd, (json.dumps(line) + "\n").encode())
@@ -692,10 +963,19 @@ def mlp_roofline(H, step_fn, n_rays):
         return None
     peak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     flops = _family_flops_per_step(n_rays)
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_chain_ncu_metrics.json")
+    # DRAM traffic per launch comes from an `ncu --set full` capture condensed by tools/ncu_metrics.py; it is only quoted
+    # when that capture was taken on THIS build (sha1 over csrc/), a stale file yields traffic = null
+    traffic, traffic_src = {}, None
+    tp = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
     if os.path.isfile(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch", {})
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from ncu_metrics import build_id
+        d = json.load(open(tp))
+        if d.get("build_id") == build_id():
+            traffic = d.get("dram_bytes_per_launch", {})
+            traffic_src = "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r02_ncu_metrics.json (build %s)" % d["build_id"]
+        else:
+            traffic_src = "profiles/r02_ncu_metrics.json was captured on build %s, this library is %s: not quoted" % (d.get("build_id"), build_id())
     fam = []
     for t in range(nt):
         if cnt[t] == 0:
@@ -711,8 +991,7 @@ def mlp_roofline(H, step_fn, n_rays):
     tot_fl = n_rays * FLOPS_PER_RAY_TRAIN
     return {"bound": "tensor", "kernel": dom["kernel"],
             "achieved": dom["achieved"], "peak": peak, "unit": "TFLOP/s", "frac": dom["frac"], "traffic": dom["traffic"],
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_chain_ncu_metrics.json"
-                              if dom["traffic"] else None,
+            "traffic_source": traffic_src,
             "algorithmic_flops_per_launch": dom["algorithmic_flops_per_step"] // max(dom["launches_per_step"], 1),
             "ms_per_launch": dom["ms_per_launch"], "share_of_mlp_time": dom["ms_per_step"] / tot_ms,
             "peak_source": src + ", sustained bf16 (dense, no split: the 3-MMA split caps algorithmic FLOPs at 1/3 of it)",
@@ -798,6 +1077,9 @@ def main():
     ap.add_argument("--large-rays", type=int, default=4096, help="extra informational measurement (0 disables)")
     ap.add_argument("--fit-rays", type=int, default=512, help="extra informational measurements: two-field fitting step, forward-only renders (0 disables)")
     ap.add_argument("--grid-res", type=int, default=512, help="extra informational SDF-lattice measurement (0 disables)")
+    ap.add_argument("--view-size", type=int, default=512, help="side of the synthetic hand views of the full-image extra")
+    ap.add_argument("--strong-rays", type=int, default=512, help="N > 1: strong-scaling extra on this many rays in total (0 disables)")
+    ap.add_argument("--no-nccl-graph", action="store_true", help="N > 1: keep the all-reduce outside the CUDA graphs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -40,12 +40,38 @@ class hn_mlp_grad_t(Structure):
                 ("db", c_void_p * HN_MAX_LAYERS)]
 
 
-if not os.path.isfile(LIB_PATH):
-    raise ImportError(
-        "honerf_b200: %s is missing. Build it with `python ho-nerf_b200/build.py` (nvcc, sm_100a); "
-        "there is no CPU or PyTorch fallback." % LIB_PATH)
+class _LazyLib:
+    """The shared library, loaded on first use: host-only modules (honerf_b200.dist, the PackedMLP layout helpers) import
+    on a machine that has not built it; the first C-ABI call on such a machine raises a clear ImportError, and a stale
+    library (a symbol of include/honerf_b200.h missing) says "rebuild" instead of an AttributeError deep inside ctypes.
+    There is still no CPU or PyTorch fallback."""
 
-lib = ctypes.CDLL(LIB_PATH)
+    def __init__(self):
+        object.__setattr__(self, "_cdll", None)
+
+    def _load(self):
+        if self._cdll is None:
+            if not os.path.isfile(LIB_PATH):
+                raise ImportError(
+                    "honerf_b200: %s is missing. Build it with `python ho-nerf_b200/build.py` (nvcc, sm_100a); "
+                    "there is no CPU or PyTorch fallback." % LIB_PATH)
+            cdll = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in PROTOTYPES.items():
+                try:
+                    fn = getattr(cdll, name)
+                except AttributeError:
+                    raise ImportError("honerf_b200: %s is stale (no symbol %s): rebuild it with "
+                                      "`python ho-nerf_b200/build.py --force`" % (LIB_PATH, name)) from None
+                fn.restype = res
+                fn.argtypes = args
+            object.__setattr__(self, "_cdll", cdll)
+        return self._cdll
+
+    def __getattr__(self, name):
+        return getattr(self._load(), name)
+
+
+lib = _LazyLib()
 
 P = c_void_p
 _mlp_p = POINTER(hn_mlp_t)
@@ -66,7 +92,7 @@ PROTOTYPES = {
     "hn_wn_bwd_batch": (c_int, [POINTER(hn_wn_job_t), c_int, P]),
     "hn_mlp_bx3_bytes": (c_int64, [_mlp_p]),
     "hn_mlp_bx3_pack": (c_int, [_mlp_p, P, c_int64, P]),
-    "hn_adam_flat": (c_int, [P, P, P, P, c_int64, P, c_float, c_float, c_float, c_float, c_float, c_float, P]),
+    "hn_adam_flat": (c_int, [P, P, P, P, c_int64, P, P, P, c_float, c_float, c_float, c_float, c_float, c_float, P]),
     "hn_wn_pack_gap": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int, P]),
     "hn_wn_bwd_gap": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, P]),
     "hn_sdf_hand_stash_floats": (c_int64, [c_int64]),
@@ -87,6 +113,7 @@ PROTOTYPES = {
     "hn_sdf_obj_chain_pack": (c_int, [_mlp_p, P, c_int64, P]),
     "hn_sdf_obj_stash_floats": (c_int64, [c_int64]),
     "hn_sdf_obj_ws_floats": (c_int64, [c_int64, c_int]),
+    "hn_sdf_obj_grid": (c_int, [_mlp_p, P, c_int, P, c_int, P, c_int, c_float, P, P]),
     "hn_sdf_obj_sdf": (c_int, [_mlp_p, P, c_int64, c_float, P, P, c_int64, c_int, P]),
     "hn_sdf_obj_fwd": (c_int, [_mlp_p, P, c_int64, c_float, P, P, c_int64, P, P, c_int64, P, c_int64,
                                c_int, P]),
@@ -103,9 +130,6 @@ PROTOTYPES = {
     "hn_dw16_test": (c_int, [P, c_int, P, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P, c_int64, P]),
     "hn_dw16_set_debug": (c_int, [c_int]),
     "hn_chain16_set_debug": (c_int, [P]),
-    "hn_tc_gemm_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
-    "hn_tc_gemm_ts_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
-    "hn_gemm_test": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
     "hn_ray_points": (c_int, [P, P, P, c_int64, c_int, P, P]),
     "hn_mid_points": (c_int, [P, P, P, c_int64, c_int, c_float, P, P, P, P]),
     "hn_mid_points_bwd": (c_int, [P, P, P, P, c_int64, c_int, P, P, P]),
@@ -132,10 +156,25 @@ PROTOTYPES = {
     "hn_interaction_loss_bwd": (c_int, [P, P, c_int64, P, c_int64, P, c_int64, c_float, c_float, c_float, P, P, P]),
 }
 
-for _name, (_res, _args) in PROTOTYPES.items():
-    _fn = getattr(lib, _name)          # AttributeError here == the .so is stale: rebuild
-    _fn.restype = _res
-    _fn.argtypes = _args
+# the tcgen05 bring-up self-test GEMMs: a separate library (csrc/selftest/), loaded by the tests only
+SELFTEST_LIB_PATH = os.path.join(HERE, "libhonerf_b200_selftest.so")
+SELFTEST_PROTOTYPES = {
+    "hn_tc_gemm_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "hn_tc_gemm_ts_test": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P]),
+    "hn_gemm_test": (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int64, P, c_int64, P, P, c_int64, P]),
+}
+
+
+def load_selftest():
+    if not os.path.isfile(SELFTEST_LIB_PATH):
+        raise ImportError("honerf_b200: %s is missing (python ho-nerf_b200/build.py)" % SELFTEST_LIB_PATH)
+    cdll = ctypes.CDLL(SELFTEST_LIB_PATH)
+    for name, (res, args) in SELFTEST_PROTOTYPES.items():
+        fn = getattr(cdll, name)
+        fn.restype = res
+        fn.argtypes = args
+    cdll.hn_last_error.restype = ctypes.c_char_p
+    return cdll
 
 
 class HonerfError(RuntimeError):

@@ -616,7 +616,8 @@ static int check_chain_mlp(const hn_mlp_t* m) {
 static long long* g_prof = nullptr;   // set by hn_chain_set_prof (diagnostics)
 static int g_stagger_fwd = 0, g_stagger_bwd = 0;   // cycles per stagger slot (hn_chain_set_stagger); measured: no effect
 
-int launch_sdf_only_ts(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s);   // chain_ts.cu
+int launch_sdf_only_ts(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s,
+                       const float* xs = nullptr, const float* ys = nullptr, const float* zs = nullptr, int ny = 0, int nz = 0);   // chain_ts.cu
 void set_prof_ts(long long* p);
 
 int launch_sdf_only(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s) {
@@ -878,6 +879,15 @@ int hn_chain_set_prof(void* buf) {
 }
 
 int64_t hn_sdf_obj_chain_bytes(void) { return (int64_t)chain::obj_layout().total; }
+
+int hn_sdf_obj_grid(const hn_mlp_t* mlp, const float* xs, int nx, const float* ys, int ny, const float* zs, int nz,
+                    float inv_scale, float* u, hn_stream_t stream) {
+    HN_REQUIRE(mlp && xs && ys && zs && u && nx >= 1 && ny >= 1 && nz >= 1, "hn_sdf_obj_grid: bad arguments");
+    HN_PROPAGATE(chain::check_chain_mlp(mlp));
+    const int64_t n = (int64_t)nx * ny * nz;
+    HN_REQUIRE(n < ((int64_t)1 << 31) * 64, "hn_sdf_obj_grid: lattice too large");
+    return chain::launch_sdf_only_ts(mlp, nullptr, n, inv_scale, u, (cudaStream_t)stream, xs, ys, zs, ny, nz);
+}
 
 int hn_sdf_obj_chain_pack(const hn_mlp_t* m, void* chain_buf, int64_t chain_bytes, hn_stream_t stream) {
     HN_REQUIRE(m && m->n_layers == 9, "hn_sdf_obj_chain_pack: object SDF mlp must have 9 layers");

@@ -32,7 +32,14 @@ struct BarriersTs {
 };
 
 struct SdfTsParams {
-    const float* pts;
+    const float* pts;         // [n,3] points, or NULL: lattice mode
+    // lattice mode (extract_geometry, utils/renderer.py:262-278): point i = (xs[i / (ny nz)], ys[(i / nz) % ny], zs[i % nz]),
+    // the ij-meshgrid order of the reference; the axes are the caller's torch.linspace values, so the coordinates are the
+    // reference's bits and no [n,3] point tensor is ever written or read
+    const float* xs;
+    const float* ys;
+    const float* zs;
+    int ny, nz;
     int64_t n;
     float inv_scale;
     float* sdf;
@@ -181,7 +188,17 @@ sdf_only_ts_kernel(const __grid_constant__ SdfTsParams p, const __grid_constant_
             // ---- encoding -> shared scratch (fp32, kept for the skip connection) -> packed first-layer operand --------
             {
                 float x[3] = {0.f, 0.f, 0.f};
-                if (gp < p.n) { x[0] = p.pts[gp * 3]; x[1] = p.pts[gp * 3 + 1]; x[2] = p.pts[gp * 3 + 2]; }
+                if (gp < p.n) {
+                    if (p.pts) {
+                        x[0] = p.pts[gp * 3]; x[1] = p.pts[gp * 3 + 1]; x[2] = p.pts[gp * 3 + 2];
+                    } else {
+                        const int64_t iyz = gp / p.nz;
+                        x[2] = __ldg(p.zs + (gp - iyz * p.nz));
+                        const int64_t ix = iyz / p.ny;
+                        x[1] = __ldg(p.ys + (iyz - ix * p.ny));
+                        x[0] = __ldg(p.xs + ix);
+                    }
+                }
                 float* e = s_enc + row * TS_ENC_LD;
                 if (cg == 0) {
                     e[0] = x[0]; e[1] = x[1]; e[2] = x[2]; e[63] = 0.0f;
@@ -269,10 +286,12 @@ sdf_only_ts_kernel(const __grid_constant__ SdfTsParams p, const __grid_constant_
 static long long* g_prof_ts = nullptr;
 void set_prof_ts(long long* p) { g_prof_ts = p; }
 
-int launch_sdf_only_ts(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s) {
+int launch_sdf_only_ts(const hn_mlp_t* m, const float* pts, int64_t n, float inv_scale, float* sdf, cudaStream_t s,
+                       const float* xs, const float* ys, const float* zs, int ny, int nz) {
     const ObjLayout L = obj_layout();
     SdfTsParams p;
     p.pts = pts; p.n = n; p.inv_scale = inv_scale; p.sdf = sdf;
+    p.xs = xs; p.ys = ys; p.zs = zs; p.ny = ny; p.nz = nz;
     p.chain = reinterpret_cast<const uint8_t*>(m->chain);
     for (int l = 0; l < 9; ++l) p.bias[l] = m->b[l];
     p.w_out0 = m->W[8];

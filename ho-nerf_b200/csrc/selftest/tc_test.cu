@@ -1,10 +1,11 @@
-// Bring-up / self-test kernel for the tcgen05 path: C[M,N] = A[M,K] * B[N,K]^T with fp16 operands,
+// SELF-TEST library (libhonerf_b200_selftest.so, NOT part of the product library): Bring-up / self-test kernel for the tcgen05 path: C[M,N] = A[M,K] * B[N,K]^T with fp16 operands,
 // fp32 accumulation in TMEM.  One CTA per 128-row tile, operands staged into shared memory with the
 // canonical SWIZZLE_128B K-major layout by ordinary stores.  Exercises exactly the descriptors, TMEM
 // allocation, MMA issue, commit/mbarrier and tcgen05.ld epilogue that the fused field kernels use,
 // against torch.matmul in tests/test_gpu_tc.py.
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "../common.cuh"
+#include "../../../include/honerf_b200_selftest.h"
+#include "../tc_common.cuh"
 
 namespace hn {
 
@@ -196,7 +197,7 @@ extern "C" int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K
     return HN_OK;
 }
 
-#include "gemm_dispatch.cuh"
+#include "../gemm_dispatch.cuh"
 
 extern "C" int hn_gemm_test(int layout, int passes, int M, int N, int K, const float* A, int64_t lda,
                             const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,

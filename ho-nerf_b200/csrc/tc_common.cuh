@@ -187,18 +187,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
-// ---- TMA (bulk tensor copy global -> shared), 2-D ---------------------------------------------
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_map, uint64_t* bar, int32_t c0,
-                                            int32_t c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
-}
-
+// ---- TMA: 1-D bulk copies (every operand the kernels stream -- packed weights, 16-bit stash tiles -- is stored in HBM in
+//      the exact shared-memory image its consumer wants, so no tensor map / 2-D box is needed: SASS UBLKCP) ---------------
 // 1-D bulk copy global -> shared (no tensor map): `bytes` % 16 == 0, both addresses 16 B aligned;
 // completion is signalled on `bar` as transaction bytes
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

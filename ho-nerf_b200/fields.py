@@ -247,6 +247,11 @@ class SDFNetwork_OBJ(nn.Module):
     def sdf_hidden_appearance(self, x):
         return self.forward(x)
 
+    def sdf_lattice(self, xs, ys, zs):
+        """sdf on the ij-meshgrid lattice of three axes (extract_geometry): [len(xs), len(ys), len(zs)], no gradients."""
+        with torch.no_grad():
+            return ops.sdf_obj_lattice(self.packed(), xs, ys, zs, 1.0 / float(self.scale))
+
     def gradient(self, x):
         return self.fused(x)[2].unsqueeze(1)
 

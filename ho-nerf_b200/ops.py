@@ -203,6 +203,15 @@ class PackedMLP:
         return [p for layer in self.layers for p in layer]
 
 
+def _check_same_weights(ctx, what):
+    """The backward reads the PackedMLP's shared W / WT / chain buffers and the raw parameter storage: if the parameters
+    were updated in place (or the net re-packed for a new parameter version) between this call's forward and its
+    backward, torch would raise a version-counter error for an ordinary op -- so do we."""
+    if ctx.packed._key != ctx.pkey or ctx.packed._version_key() != ctx.pkey:
+        raise _lib.HonerfError("%s: the network's parameters changed between forward and backward (in-place update or "
+                               "re-pack); the saved activations no longer match the packed weights" % what)
+
+
 class _ParamTokenFn(torch.autograd.Function):
     """One autograd edge for ALL parameters of a net: forward packs the weights (once per parameter version) and
     returns a token shaped like the flat packed gradient; every field call made with that token returns its flat
@@ -266,6 +275,19 @@ def sdf_obj_sdf_only(packed, pts, inv_scale=1.0, precision=None):
     return sdf
 
 
+def sdf_obj_lattice(packed, xs, ys, zs, inv_scale=1.0):
+    """u[ix, iy, iz] = SDFNetwork_OBJ.sdf((xs[ix], ys[iy], zs[iz])) of extract_geometry (utils/renderer.py:262-278), one
+    launch, lattice points generated in the kernel (hn_sdf_obj_grid)."""
+    xs, ys, zs = _f32c(xs.detach()), _f32c(ys.detach()), _f32c(zs.detach())
+    _require_cuda(xs, "sdf_obj_lattice")
+    pk = packed.get()
+    u = torch.empty(xs.numel(), ys.numel(), zs.numel(), device=xs.device, dtype=torch.float32)
+    if u.numel():
+        check(lib.hn_sdf_obj_grid(ctypes.byref(pk.struct), _ptr(xs), xs.numel(), _ptr(ys), ys.numel(), _ptr(zs), zs.numel(),
+                                  inv_scale, _ptr(u), _stream(xs)), "hn_sdf_obj_grid")
+    return u
+
+
 class _SdfObjFn(torch.autograd.Function):
     """(sdf, feature, normal) = f(pts, params) with a second-order-aware backward."""
 
@@ -286,6 +308,7 @@ class _SdfObjFn(torch.autograd.Function):
                                      256, _ptr(normal), _ptr(stash), stf, None, 0, precision, _stream(pts_c)),
                   "hn_sdf_obj_fwd")
         ctx.packed, ctx.stash, ctx.n = pk, stash, n
+        ctx.pkey = pk._key
         ctx.inv_scale, ctx.precision = inv_scale, precision
         ctx.struct = pk.struct
         ctx.pts_needs_grad = pts.requires_grad
@@ -299,6 +322,7 @@ class _SdfObjFn(torch.autograd.Function):
         n, pk = ctx.n, ctx.packed
         if ctx.stash is None:
             raise _lib.HonerfError("sdf_obj backward called twice (the stash is consumed)")
+        _check_same_weights(ctx, "sdf_obj backward")
         dev = ctx.stash.device
         d_sdf = _f32c(d_sdf) if d_sdf is not None else None
         d_feat = _f32c(d_feat) if d_feat is not None else None
@@ -351,6 +375,7 @@ class _ColorObjFn(torch.autograd.Function):
                                        feat_c.shape[1], _ptr(nrm_c), n, _ptr(rgb), _ptr(stash), stf, precision,
                                        _stream(pts_c)), "hn_color_obj_fwd")
         ctx.packed, ctx.stash, ctx.n, ctx.precision, ctx.struct = pk, stash, n, precision, pk.struct
+        ctx.pkey = pk._key
         ctx.rgb = rgb
         ctx.need = (pts.requires_grad, dirs.requires_grad, feat.requires_grad, normal.requires_grad)
         ctx.params_need_grad = any(p.requires_grad for p in params)
@@ -362,6 +387,7 @@ class _ColorObjFn(torch.autograd.Function):
     def backward(ctx, d_rgb):
         if ctx.stash is None:
             raise _lib.HonerfError("color_obj backward called twice (the stash is consumed)")
+        _check_same_weights(ctx, "color_obj backward")
         n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
         d_rgb = _f32c(d_rgb)
         d_pts = torch.empty(n, 3, device=dev) if ctx.need[0] else None
@@ -449,6 +475,7 @@ class _SdfHandFn(torch.autograd.Function):
                                       _ptr(feat), 256, _ptr(normal), _ptr(xyz), 1386, _ptr(stash), stf, precision,
                                       _stream(pts_c)), "hn_sdf_hand_fwd")
         ctx.packed, ctx.stash, ctx.n, ctx.ppf, ctx.precision, ctx.struct = pk, stash, n, ppf, precision, pk.struct
+        ctx.pkey = pk._key
         ctx.pts_c, ctx.bt_c, ctx.T_c = pts_c, bt_c, T_c
         ctx.need = (pts.requires_grad, bt_inv.requires_grad, T_pose.requires_grad)
         ctx.params_need_grad = any(p.requires_grad for p in params)
@@ -459,6 +486,7 @@ class _SdfHandFn(torch.autograd.Function):
     def backward(ctx, d_sdf, d_feat, d_normal, d_xyz):
         if ctx.stash is None:
             raise _lib.HonerfError("sdf_hand backward called twice (the stash is consumed)")
+        _check_same_weights(ctx, "sdf_hand backward")
         n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
         d_sdf = _f32c(d_sdf) if d_sdf is not None else None
         d_feat = _f32c(d_feat) if d_feat is not None else None
@@ -509,6 +537,7 @@ class _ColorHandFn(torch.autograd.Function):
                                         feat_c.shape[1], _ptr(nrm_c), n, _ptr(rgb), _ptr(stash), stf, precision,
                                         _stream(xyz_c)), "hn_color_hand_fwd")
         ctx.packed, ctx.stash, ctx.n, ctx.precision, ctx.struct, ctx.rgb = pk, stash, n, precision, pk.struct, rgb
+        ctx.pkey = pk._key
         ctx.need = (xyz.requires_grad, feat.requires_grad, normal.requires_grad)
         ctx.params_need_grad = any(p.requires_grad for p in params)
         return rgb
@@ -518,6 +547,7 @@ class _ColorHandFn(torch.autograd.Function):
     def backward(ctx, d_rgb):
         if ctx.stash is None:
             raise _lib.HonerfError("color_hand backward called twice (the stash is consumed)")
+        _check_same_weights(ctx, "color_hand backward")
         n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
         d_rgb = _f32c(d_rgb)
         d_xyz = torch.empty(n, 1386, device=dev) if ctx.need[0] else None

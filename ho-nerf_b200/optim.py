@@ -2,10 +2,17 @@
 
 The reference builds a single ``torch.optim.Adam`` over every network's parameters (exp_runner.py:83-90); with the
 weight-normalised MLPs that is ~90 small tensors per step.  ``FlatAdam`` re-homes the parameters as views of one
-contiguous buffer (their values, shapes and ``state_dict`` are unchanged), gathers the step's gradients into a
-second flat buffer and updates everything with one kernel.  Same update rule as ``torch.optim.Adam`` (bias
-correction, ``eps`` outside the square root, L2 ``weight_decay``); the step count lives on the device so the step
-can be captured in a CUDA graph.  ``flat_grad`` is also the payload of the multi-GPU gradient all-reduce.
+contiguous buffer (their values, shapes and the modules' ``state_dict`` are unchanged), gathers the step's gradients into a
+second flat buffer and updates everything with one kernel.  Same update rule as ``torch.optim.Adam`` (bias correction
+with a per-parameter step count, ``eps`` outside the square root, L2 ``weight_decay``).
+
+Drop-in surface the reference's training loop uses (exp_runner.py): ``param_groups`` (``update_learning_rate`` writes
+``param_groups[i]['lr']`` every iteration, the logger reads ``param_groups[0]['lr']``), ``zero_grad``, ``step``,
+``state_dict`` / ``load_state_dict`` in ``torch.optim.Adam``'s own format (checkpoints keep working in both directions).
+The step count and the learning rate live on the device, so the step can be captured in a CUDA graph and the schedule
+still applies on replay: ``step()`` pushes ``param_groups[0]['lr']`` to the device scalar whenever it is called outside a
+capture; a loop that only replays a graph calls ``sync_lr()`` before the replay.  ``flat_grad`` is also the payload of
+the multi-GPU gradient all-reduce.
 """
 import ctypes
 
@@ -19,13 +26,18 @@ class FlatAdam:
         self.params = [p for p in params]
         if not self.params:
             raise ValueError("FlatAdam: no parameters")
+        if isinstance(self.params[0], dict):
+            raise ValueError("FlatAdam: one parameter group only (the reference uses a single group)")
         dev = self.params[0].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdam: parameters must be CUDA tensors (there is no CPU path)")
         for p in self.params:
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("FlatAdam: parameters must be fp32 tensors on one device")
-        self.lr, self.betas, self.eps, self.weight_decay = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(weight_decay)
+        # torch.optim-style view of the hyper-parameters; 'lr' may be rewritten by the caller at any time
+        self.param_groups = [{"params": self.params, "lr": float(lr), "betas": (float(betas[0]), float(betas[1])),
+                              "eps": float(eps), "weight_decay": float(weight_decay), "amsgrad": False, "maximize": False,
+                              "foreach": None, "capturable": True, "differentiable": False, "fused": None}]
         # every parameter starts on a 128-byte boundary (the field kernels read weights and biases with vector loads);
         # the padding stays zero under Adam
         self.offsets, n = [], 0
@@ -44,6 +56,21 @@ class FlatAdam:
         self.flat_grad = torch.zeros_like(self.flat)
         self._grad_views = [self.flat_grad[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets)]
         self.step_t = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr_t = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self._lr_on_device = float(lr)
+        # steps a parameter sat out (no gradient), per 32-element block of the flat buffer; torch counts steps per parameter
+        self.skipped = torch.zeros(n // 32, device=dev, dtype=torch.float32)
+        self._block_slices = [slice(off // 32, (off + (p.numel() + 31) // 32 * 32) // 32) for p, off in zip(self.params, self.offsets)]
+        self._any_skipped = False
+
+    # -- torch.optim surface ---------------------------------------------------------------------------------------
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value):
+        self.param_groups[0]["lr"] = float(value)
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -52,6 +79,54 @@ class FlatAdam:
             elif p.grad is not None:
                 p.grad.zero_()
 
+    def sync_lr(self):
+        """Push param_groups[0]['lr'] to the device scalar the kernel reads (a host-to-device fill: call it OUTSIDE a CUDA
+        graph capture; step() does it itself whenever it runs eagerly)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_on_device:
+            self.lr_t.fill_(lr)
+            self._lr_on_device = lr
+
+    def state_dict(self):
+        """torch.optim.Adam's format: loadable by torch.optim.Adam(params).load_state_dict and by FlatAdam."""
+        step = float(self.step_t.item())
+        skipped = self.skipped.cpu()
+        state = {}
+        for i, (p, off, bs) in enumerate(zip(self.params, self.offsets, self._block_slices)):
+            t = step - float(skipped[bs.start])
+            if t <= 0:
+                continue                              # torch creates a parameter's state at its first step
+            state[i] = {"step": torch.tensor(t, dtype=torch.float32),
+                        "exp_avg": self.exp_avg[off:off + p.numel()].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off:off + p.numel()].view(p.shape).clone()}
+        group = {k: v for k, v in self.param_groups[0].items() if k != "params"}
+        group["params"] = list(range(len(self.params)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("FlatAdam.load_state_dict: expected one parameter group with %d parameters" % len(self.params))
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in groups[0]:
+                self.param_groups[0][k] = tuple(groups[0][k]) if k == "betas" else float(groups[0][k])
+        steps = [float(sd["state"][i]["step"]) if i in sd["state"] else 0.0 for i in range(len(self.params))]
+        top = max(steps) if steps else 0.0
+        self.step_t.fill_(top)
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_(); self.skipped.zero_()
+        self._any_skipped = False
+        for i, (p, off, bs) in enumerate(zip(self.params, self.offsets, self._block_slices)):
+            if steps[i] != top:
+                self.skipped[bs] = top - steps[i]
+                self._any_skipped = True
+            if i in sd["state"]:
+                st = sd["state"][i]
+                self.exp_avg[off:off + p.numel()].view(p.shape).copy_(st["exp_avg"])
+                self.exp_avg_sq[off:off + p.numel()].view(p.shape).copy_(st["exp_avg_sq"])
+        self._lr_on_device = None
+        self.sync_lr()
+
+    # -- the step ----------------------------------------------------------------------------------------------------
     def _runs(self):
         """maximal runs of consecutive parameters that have a gradient (torch's Adam skips the others entirely)"""
         runs, cur = [], None
@@ -79,13 +154,28 @@ class FlatAdam:
         ``flat_grad``); gathered here when omitted."""
         if runs is None:
             runs = self.gather_grads()
+        dev = self.flat.device
+        if not torch.cuda.is_current_stream_capturing():
+            self.sync_lr()
         self.step_t += 1.0
-        stream = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        # parameters outside every run sit this step out: their own step count stays behind (torch: per-parameter `step`)
+        covered = set()
+        for a, b in runs:
+            covered.update(range(a, b + 1))
+        missing = [i for i in range(len(self.params)) if i not in covered]
+        if missing:
+            for i in missing:
+                self.skipped[self._block_slices[i]] += 1.0
+            self._any_skipped = True
+        g = self.param_groups[0]
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         f = lambda t, off: ctypes.c_void_p(t.data_ptr() + 4 * off)
         for a, b in runs:
             lo, hi = self.offsets[a], self.offsets[b] + self.params[b].numel()
+            sk = f(self.skipped, lo // 32) if self._any_skipped else None
             check(lib.hn_adam_flat(f(self.flat, lo), f(self.flat_grad, lo), f(self.exp_avg, lo), f(self.exp_avg_sq, lo), hi - lo,
-                                   ctypes.c_void_p(self.step_t.data_ptr()), self.lr, self.betas[0], self.betas[1], self.eps,
-                                   self.weight_decay, float(grad_scale), stream), "hn_adam_flat")
+                                   ctypes.c_void_p(self.step_t.data_ptr()), ctypes.c_void_p(self.lr_t.data_ptr()), sk,
+                                   float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                   float(g["weight_decay"]), float(grad_scale), stream), "hn_adam_flat")
         # the kernel wrote through raw pointers: tell autograd (and the packed-weight caches keyed on _version)
         torch.autograd.graph.increment_version(self.params)

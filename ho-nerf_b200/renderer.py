@@ -215,20 +215,27 @@ class NeuSRenderer:
             'gradient_error': ret_fine['gradient_error'],
         }
 
-    def sdf_grid(self, bound_min, bound_max, resolution, bt_inv=None, T_pose_21=None, chunk_points=1 << 20):
+    def sdf_grid(self, bound_min, bound_max, resolution, bt_inv=None, T_pose_21=None, chunk_points=1 << 20, x_range=None):
         """The ``u`` lattice of extract_geometry (utils/renderer.py:262-278) as a device tensor
-        [res,res,res]; no per-chunk host round trip."""
+        [res,res,res]; no per-chunk host round trip.  ``x_range = (x0, x1)`` computes the slab u[x0:x1] only (the lattice
+        sharded over GPUs in x slabs: the axes are the full-resolution linspaces, so slabs are bit-identical to the rows
+        of the whole lattice).  Object field: the lattice points are generated inside the SDF kernel (hn_sdf_obj_grid), no
+        [res^3, 3] point tensor exists; hand field: chunked through the point kernel."""
         device = next(self.sdf_network.parameters()).device
         xs = torch.linspace(float(bound_min[0]), float(bound_max[0]), resolution).to(device)
         ys = torch.linspace(float(bound_min[1]), float(bound_max[1]), resolution).to(device)
         zs = torch.linspace(float(bound_min[2]), float(bound_max[2]), resolution).to(device)
-        u = torch.empty(resolution, resolution, resolution, device=device)
+        x0, x1 = (0, resolution) if x_range is None else (int(x_range[0]), int(x_range[1]))
+        if self.model_type == 'obj' and x1 > x0:
+            return self.sdf_network.sdf_lattice(xs[x0:x1].contiguous(), ys, zs)
+        u = torch.empty(x1 - x0, resolution, resolution, device=device)
         slab = max(1, chunk_points // (resolution * resolution))
         with torch.no_grad():
-            for x0 in range(0, resolution, slab):
-                xx, yy, zz = torch.meshgrid(xs[x0:x0 + slab], ys, zs, indexing='ij')
+            for a in range(x0, x1, slab):
+                b = min(a + slab, x1)
+                xx, yy, zz = torch.meshgrid(xs[a:b], ys, zs, indexing='ij')
                 pts = torch.stack([xx, yy, zz], dim=-1).reshape(-1, 3)
-                u[x0:x0 + slab] = self._sdf_only(pts, bt_inv, T_pose_21).reshape(xx.shape)
+                u[a - x0:b - x0] = self._sdf_only(pts, bt_inv, T_pose_21).reshape(xx.shape)
         return u
 
     def extract_geometry(self, bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, threshold=0.0):

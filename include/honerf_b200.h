@@ -138,12 +138,16 @@ HN_API int64_t hn_mlp_bx3_bytes(const hn_mlp_t* m);
 HN_API int hn_mlp_bx3_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_stream_t stream);
 
 /* Adam over one flat fp32 parameter buffer (torch.optim.Adam semantics; the reference builds one Adam over all
- * networks' parameters, exp_runner.py:83).  p, m, v [n] are updated in place from g [n] * grad_scale; `step` is a
- * DEVICE float holding the 1-based step count (the caller increments it before the call), so the launch is the
- * same every step and can be replayed from a CUDA graph. */
-HN_API int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* step, float lr,
-                        float beta1, float beta2, float eps, float weight_decay, float grad_scale,
-                        hn_stream_t stream);
+ * networks' parameters, exp_runner.py:83, and rewrites param_groups[i]['lr'] every iteration, exp_runner.py:258-268).
+ * p, m, v [n] are updated in place from g [n] * grad_scale; `step` is a DEVICE float holding the 1-based step count (the
+ * caller increments it before the call) and `lr_dev` (may be NULL: use `lr`) a DEVICE float holding the learning rate, so
+ * the launch is the same every step and can be replayed from a CUDA graph while the schedule still applies.  `skipped`
+ * (may be NULL) holds per 32-element block of the buffer how many steps that block's parameter received no gradient:
+ * its bias correction uses step - skipped, as torch's per-parameter step does.  p .. v and the blocks of `skipped`
+ * refer to the SAME element range (the caller offsets all of them for a sub-range that starts on a block boundary). */
+HN_API int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* step, const float* lr_dev,
+                        const float* skipped, float lr, float beta1, float beta2, float eps, float weight_decay,
+                        float grad_scale, hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Object SDF field: SDFNetwork_OBJ.forward / .sdf / .gradient (utils/fields.py:316-347) as ONE
@@ -170,6 +174,11 @@ HN_API int hn_chain_set_prof(void* buf);
 HN_API int hn_chain_set_stagger(int fwd_cycles, int bwd_cycles);
 
 /* sdf[n] = SDFNetwork_OBJ.sdf(pts) (utils/fields.py:330-331); no stash, no normal. */
+/* extract_geometry's lattice (utils/renderer.py:262-278) in ONE launch: u[ix, iy, iz] = sdf(xs[ix], ys[iy], zs[iz]) / scale with
+ * the lattice points generated inside the SDF kernel (ij-meshgrid order; the axes are the caller's linspace values): no
+ * [nx ny nz, 3] point tensor is written or read.  Tensor-core chain kernel (needs hn_sdf_obj_chain_pack). */
+HN_API int hn_sdf_obj_grid(const hn_mlp_t* mlp, const float* xs, int nx, const float* ys, int ny, const float* zs, int nz,
+                           float inv_scale, float* u, hn_stream_t stream);
 HN_API int hn_sdf_obj_sdf(const hn_mlp_t* mlp, const float* pts, int64_t n_pts, float inv_scale,
                           float* sdf, float* ws, int64_t ws_floats, int precision,
                           hn_stream_t stream);
@@ -418,15 +427,9 @@ HN_API int hn_nn_select(const float* pts, const uint8_t* in_mask, const uint8_t*
                         int n_pts, uint8_t* flag, int64_t* nearest, hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Diagnostics: C[M,N] (fp32) = A[M,K] * B[N,K]^T with fp16 (or bf16) operands on tcgen05 tensor cores
- * (fp32 accumulation in TMEM).  Self-test of the descriptors / TMEM / mbarrier plumbing shared by the
- * fused field kernels.  16 <= N <= 256, N % 16 == 0, K % 64 == 0.
+ * Diagnostics / test hooks of the product kernels (the tcgen05 bring-up self-test GEMMs live in a separate library:
+ * include/honerf_b200_selftest.h, libhonerf_b200_selftest.so)
  * ------------------------------------------------------------------------------------------- */
-HN_API int hn_tc_gemm_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
-                           hn_stream_t stream);
-/* Same product with the A operand staged in tensor memory (tcgen05.st + the `ts` MMA form); K <= 256. */
-HN_API int hn_tc_gemm_ts_test(const void* A, const void* B, int M, int N, int K, int is_bf16, float* C,
-                              hn_stream_t stream);
 /* The weight-gradient kernel of the HN_TC_BF16X3 path, for tests: C [out, ldc] += P^T Q (+ P2^T Q2) over n
  * points, P [n, out] and Q [n, in] fp32: row-major (x_tiled = 0, leading dimension ld), tiled (x_tiled = 1:
  * [tile][col/4][128][4], n padded to 128) or column-major tiles (x_tiled = 2: [tile][ld columns][128 rows]);
@@ -442,14 +445,6 @@ HN_API int hn_chain16_set_debug(void* host_mapped_words);
 HN_API int hn_dw_test(const float* P, int64_t ldp, int p_tiled, int out, const float* Q, int64_t ldq,
                       int q_tiled, int in, const float* P2, const float* Q2, int64_t n, float* C,
                       int64_t ldc, float* db, float* part, int64_t part_floats, hn_stream_t stream);
-/* One dense contraction through the production kernels, for tests: C [M, ldc] (fp32).
- *   layout 0: C = A[M,lda] @ B[N,ldb]^T (+ bias[N])      layout 1: C = A[M,lda] @ B[K,ldb]
- *   layout 2: C += A[K,lda]^T @ B[K,ldb]  (K split over CTAs, atomics; caller zeroes C)
- *   passes 0: fp32 SIMT, 1: tcgen05 TF32, 3: tcgen05 split TF32. */
-HN_API int hn_gemm_test(int layout, int passes, int M, int N, int K, const float* A, int64_t lda,
-                        const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
-                        hn_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

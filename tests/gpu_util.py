@@ -51,6 +51,29 @@ def oracle_core_fp64(case, z_vals):
     return core, loss, grads, names
 
 
+def reference_fp32_own_error(case, z_vals, ref_grads, names):
+    """rel-L2 error of the reference algorithm's OWN fp32 arithmetic (oracle port, torch CPU) against the fp64 gradients
+    `ref_grads` on the same z_vals: the conditioning yardstick for gradient bounds.  The colour net's weight gradients are
+    sums over 65 536 points of terms gated by ReLUs; a rounding-level perturbation of its inputs flips a fraction f of the
+    gates and moves such a sum by ~sqrt(f), so fp32 itself is 5-7e-3 away from fp64 on color.lin0 at 512 rays."""
+    import honerf_oracle as O
+    from golden_util import rel_l2
+    R = case["R"]
+    sp, cp = synth.obj_states()
+    spf = {k: v.clone().requires_grad_(k != "se3_refine") for k, v in sp.items()}
+    cpf = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
+    var = torch.tensor(0.3, requires_grad=True)
+    Ro, To = R["Ro"].clone().requires_grad_(True), R["To"].clone().requires_grad_(True)
+    lo, ld = O.rays_to_local(R["rays_o"], R["rays_d"], Ro, To)
+    core = O.render_core_obj(spf, cpf, var, lo, ld, z_vals.float(), 1.1 / 64)
+    out = {"color_fine": core["color"], "weight_sum": core["weights"].sum(-1, keepdim=True),
+           "gradient_error": core["gradient_error"]}
+    loss = O.training_loss(out, case["true_rgb"], case["true_mask"])
+    tens = [v for k, v in spf.items() if k != "se3_refine"] + list(cpf.values()) + [var, Ro, To]
+    g32 = dict(zip(names, torch.autograd.grad(loss, tens)))
+    return {k: rel_l2(g32[k], ref_grads[k]) for k in names}
+
+
 def hand_modules(device=DEV, requires_grad=True, use_batch=False):
     import honerf_b200 as H
     sp, cp = synth.hand_states()

@@ -21,7 +21,12 @@ def test_reference_arm_prints_one_json_line():
     assert BASE_KEYS <= set(d) and d["impl"] == "reference"
     assert d["unit"] == "rays/s" and d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
     assert d["vs_baseline"] is None and d["gpu_launches"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # "reference" where the reference tree is reachable (this build container: /root/reference through oracle/ref_loader.py),
+    # "port" on the GPU box; the arm honours the warm-up it is asked for
+    have_ref = os.path.isfile("/root/reference/utils/renderer.py") or os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "utils", "renderer.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"] and d["warmup"] == 1
+    assert d["forward_only"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

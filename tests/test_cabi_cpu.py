@@ -23,13 +23,22 @@ def test_library_exports_every_header_symbol():
         assert s in _lib.PROTOTYPES, "ctypes prototype missing for %s" % s
     assert set(_lib.PROTOTYPES) == set(syms)
     assert _lib.lib.hn_version() >= 100
+    # the bring-up self-test GEMMs are a separate library, not product symbols
+    txt = open(os.path.join(ROOT, "include", "honerf_b200_selftest.h")).read()
+    tsyms = set(re.findall(r"HN_API\s+[\w\s\*]+?\b(hn_\w+)\s*\(", txt))
+    assert tsyms == set(_lib.SELFTEST_PROTOTYPES) and not (tsyms & set(syms))
+    st = _lib.load_selftest()
+    for t in tsyms:
+        assert hasattr(st, t) and not hasattr(_lib.lib._load(), t)
 
 
 def test_size_queries_run_without_a_gpu():
     from honerf_b200 import _lib
-    # stashes are sized for whole 128-point tiles (the tiled layout of the HN_TC_BF16X3 chain kernels)
-    assert _lib.lib.hn_sdf_obj_stash_floats(1000) == 1024 * (64 + 16 * 256 + 64)
-    assert _lib.lib.hn_sdf_obj_stash_floats(1024) == 1024 * (64 + 16 * 256 + 64)
+    # stashes are sized for whole 128-point tiles and for the largest layout of any precision: HN_TC_BF16X3 keeps
+    # E | H[8] | D[8] | EB in fp32 (64 + 16 * 256 + 64 floats per point), HN_TC_MIXED16 keeps E | EB (fp32), E16 and the
+    # 16-bit tiles EM[8] | EML[8] | A16[8] | D16[8] (128 + 32 + 32 * 128 floats per point)
+    assert _lib.lib.hn_sdf_obj_stash_floats(1000) == 1024 * (128 + 32 + 32 * 128)
+    assert _lib.lib.hn_sdf_obj_stash_floats(1024) == 1024 * (128 + 32 + 32 * 128)
     assert _lib.lib.hn_sdf_obj_ws_floats(10, _lib.HN_WS_SDF_ONLY) > 0
     assert _lib.lib.hn_sdf_obj_ws_floats(1000, _lib.HN_WS_BWD) >= 1024 * (64 + 24 * 256 + 64)
     assert _lib.lib.hn_color_obj_stash_floats(10) == 128 * (128 + 5 * 256)

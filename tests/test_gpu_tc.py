@@ -9,15 +9,31 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+_ST = None
+
+
+def _selftest():
+    """libhonerf_b200_selftest.so (csrc/selftest/): the bring-up GEMMs are not part of the product library."""
+    global _ST
+    if _ST is None:
+        from honerf_b200 import _lib
+        _ST = _lib.load_selftest()
+    return _ST
+
+
+def _check(status, what):
+    if status != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, status, (_selftest().hn_last_error() or b"?").decode()))
+
+
 def _run(M, N, K, bf16, ts=False):
-    from honerf_b200 import _lib
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     dt = torch.bfloat16 if bf16 else torch.float16
     A = torch.randn(M, K, generator=g).to(dt).cuda()
     B = torch.randn(N, K, generator=g).to(dt).cuda()
     C = torch.full((M, N), float("nan"), device="cuda")
-    fn = _lib.lib.hn_tc_gemm_ts_test if ts else _lib.lib.hn_tc_gemm_test
-    _lib.check(fn(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), M, N, K, int(bf16),
+    fn = _selftest().hn_tc_gemm_ts_test if ts else _selftest().hn_tc_gemm_test
+    _check(fn(ctypes.c_void_p(A.data_ptr()), ctypes.c_void_p(B.data_ptr()), M, N, K, int(bf16),
                   ctypes.c_void_p(C.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "hn_tc_gemm_test")
     torch.cuda.synchronize()
     ref = A.float() @ B.float().T
@@ -63,7 +79,7 @@ def _gemm(layout, passes, M, N, K, lda_pad=0, with_bias=False, seed=0):
         ref = ref + bias.double()
     ldc = r4(N)
     C = torch.zeros(M, ldc, device="cuda")
-    _lib.check(_lib.lib.hn_gemm_test(layout, passes, M, N, K, P(A), lda, P(B), ldb, P(bias), P(C), ldc, st),
+    _check(_selftest().hn_gemm_test(layout, passes, M, N, K, P(A), lda, P(B), ldb, P(bias), P(C), ldc, st),
                "hn_gemm_test")
     torch.cuda.synchronize()
     err = (C[:, :N].double() - ref).abs().max().item()

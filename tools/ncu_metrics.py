@@ -18,7 +18,24 @@ KEEP = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio"]
 SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}
 FAMILY = {"sdf_only": "chain::sdf_only_kernel", "sdf_fwd": "chain::sdf_fwd_kernel", "sdf_bwd": "chain::sdf_bwd_kernel",
-          "dw_kernel": "chain::dw_kernel", "color_fwd": "chain::color_fwd_kernel", "color_bwd": "chain::color_bwd_kernel"}
+          "dw_kernel": "chain::dw_kernel", "color_fwd": "chain::color_fwd_kernel", "color_bwd": "chain::color_bwd_kernel",
+          # HN_TC_MIXED16: the forward is two launches (their traffic adds up), the backward one, the weight gradients one
+          "trunk16": "chain::sdf_fwd_kernel", "nsweep16": "chain::sdf_fwd_kernel", "bwd16": "chain::sdf_bwd_kernel",
+          "dw16": "chain::dw_kernel"}
+ADDITIVE = ("trunk16", "nsweep16")
+
+
+def build_id(root=None):
+    """sha1 over the CUDA sources: bench.py refuses a traffic figure whose build differs from the library it is timing."""
+    import hashlib
+    import os
+    root = root or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ho-nerf_b200", "csrc")
+    h = hashlib.sha1()
+    for f in sorted(os.listdir(root)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(root, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def main(src, dst, command):
@@ -35,10 +52,13 @@ def main(src, dst, command):
         kernels.append(k)
         for key, fam in FAMILY.items():
             if key in name:
-                per_family.setdefault(fam, []).append(k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0))
-    out = {"source": command,
-           # largest launch of each family (the step's dominant configuration), bytes per launch
-           "dram_bytes_per_launch": {fam: max(v) for fam, v in per_family.items()},
+                per_family.setdefault((fam, key), []).append(k.get("dram__bytes_read.sum", 0.0) + k.get("dram__bytes_write.sum", 0.0))
+    fam_bytes = {}
+    for (fam, key), v in per_family.items():
+        # largest launch of each kernel (the step's dominant configuration); a family made of two kernels adds them up
+        fam_bytes[fam] = fam_bytes.get(fam, 0.0) + max(v) if key in ADDITIVE else max(fam_bytes.get(fam, 0.0), max(v))
+    out = {"source": command, "build_id": build_id(),
+           "dram_bytes_per_launch": fam_bytes,
            "kernels": kernels}
     json.dump(out, open(dst, "w"), indent=1)
     print("wrote", dst, "with", len(kernels), "launches")
