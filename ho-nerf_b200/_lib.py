@@ -92,7 +92,7 @@ PROTOTYPES = {
     "hn_wn_bwd_batch": (c_int, [POINTER(hn_wn_job_t), c_int, P]),
     "hn_mlp_bx3_bytes": (c_int64, [_mlp_p]),
     "hn_mlp_bx3_pack": (c_int, [_mlp_p, P, c_int64, P]),
-    "hn_adam_flat": (c_int, [P, P, P, P, c_int64, P, P, P, c_float, c_float, c_float, c_float, c_float, c_float, P]),
+    "hn_adam_flat": (c_int, [P, P, P, P, c_int64, P, P, P] + [ctypes.c_double] * 6 + [P]),
     "hn_wn_pack_gap": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int, P]),
     "hn_wn_bwd_gap": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, P]),
     "hn_sdf_hand_stash_floats": (c_int64, [c_int64]),
@@ -127,6 +127,9 @@ PROTOTYPES = {
     "hn_color_obj_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, P, P, c_int64, P, _grad_p, P, c_int64,
                                  c_int, P]),
     "hn_dw_test": (c_int, [P, c_int64, c_int, c_int, P, c_int64, c_int, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P]),
+    "hn_mc_set_tables": (c_int, [P, P, P]),
+    "hn_mc_classify": (c_int, [P, c_int, c_int, c_int, c_float, P, P, P]),
+    "hn_mc_emit": (c_int, [P, c_int, c_int, c_int, c_float, P, P, P, P, P, P, P]),
     "hn_dw16_test": (c_int, [P, c_int, P, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P, c_int64, P]),
     "hn_dw16_set_debug": (c_int, [c_int]),
     "hn_chain16_set_debug": (c_int, [P]),

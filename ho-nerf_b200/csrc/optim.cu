@@ -14,8 +14,8 @@ namespace hn {
 __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                         float* __restrict__ v, int64_t n, const float* __restrict__ step,
                                                         const float* __restrict__ lr_dev, const float* __restrict__ skipped,
-                                                        float lr, float beta1, float beta2, float eps, float weight_decay,
-                                                        float grad_scale) {
+                                                        float lr, float beta1, float beta2, float omb1, float omb2, float eps,
+                                                        float weight_decay, float grad_scale) {
     const float t0 = *step;
     if (lr_dev) lr = *lr_dev;
     float t_cur = t0;
@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
         float gi = g[i] * grad_scale;
         const float pi = p[i];
         if (weight_decay != 0.0f) gi += weight_decay * pi;
-        const float mi = beta1 * m[i] + (1.0f - beta1) * gi;
-        const float vi = beta2 * v[i] + (1.0f - beta2) * gi * gi;
+        const float mi = beta1 * m[i] + omb1 * gi;
+        const float vi = beta2 * v[i] + omb2 * gi * gi;
         m[i] = mi;
         v[i] = vi;
         p[i] = pi - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
@@ -48,13 +48,15 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
 using namespace hn;
 
 extern "C" int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* step, const float* lr_dev,
-                            const float* skipped, float lr, float beta1, float beta2, float eps, float weight_decay,
-                            float grad_scale, hn_stream_t stream) {
+                            const float* skipped, double lr, double beta1, double beta2, double eps, double weight_decay,
+                            double grad_scale, hn_stream_t stream) {
     HN_REQUIRE(p && g && m && v && step && n >= 0, "hn_adam_flat: null argument");
     if (n == 0) return HN_OK;
     const int grid = (int)std::min<int64_t>(ceil_div(n, 256), 4 * 148);
-    adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step, lr_dev, skipped, lr, beta1, beta2, eps,
-                                                             weight_decay, grad_scale);
+    // 1 - beta in double, then rounded once (torch.optim.Adam does the same: 1 - 0.999 evaluated in fp32 is off by 1.3e-5)
+    adam_flat_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step, lr_dev, skipped, (float)lr, (float)beta1, (float)beta2,
+                                                             (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
+                                                             (float)weight_decay, (float)grad_scale);
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;

@@ -1090,3 +1090,51 @@ def stable_loss_from_sdf(hand_sdf, pts0, fixed=False):
     out_err = (flag.to(hand_sdf.dtype) @ s_neg) / denom
     total = ((in_err + 0.05 * out_err) * vf).sum() / in_time.clamp_min(1).to(hand_sdf.dtype)
     return torch.where(in_time > 1, total, torch.zeros_like(total))
+
+
+# ------------------------------------------------------------------------------------------------
+# marching cubes on the device
+# ------------------------------------------------------------------------------------------------
+_mc_devices = set()
+
+
+def _mc_tables(device):
+    key = str(device)
+    if key in _mc_devices:
+        return
+    import numpy as np
+    from . import mcubes_tables as T
+    n_tris, tris, owner = T.build_tables()
+    a = np.asarray(n_tris, dtype=np.int8)
+    b = np.ascontiguousarray(np.asarray(tris, dtype=np.int8)[:, :15])
+    c = np.ascontiguousarray(np.asarray(owner, dtype=np.int8))
+    with torch.cuda.device(device):
+        check(lib.hn_mc_set_tables(a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                                   c.ctypes.data_as(ctypes.c_void_p)), "hn_mc_set_tables")
+    _mc_devices.add(key)
+
+
+def marching_cubes(u, threshold=0.0):
+    """mcubes.marching_cubes(u, threshold) (utils/renderer.py:279) on the device: u [nx,ny,nz] fp32 CUDA tensor ->
+    (vertices [V,3] fp32 in index coordinates, triangles [T,3] int32); vertices are shared between cells, triangle normals
+    point towards lower values (the reference reverses the triangles afterwards).  The lattice never leaves the device; the
+    only host syncs are the two totals that size the outputs."""
+    u = _f32c(u.detach())
+    _require_cuda(u, "marching_cubes")
+    if u.dim() != 3 or min(u.shape) < 2:
+        raise ValueError("marching_cubes: u must be [nx, ny, nz] with every side >= 2")
+    nx, ny, nz = u.shape
+    _mc_tables(u.device)
+    n = nx * ny * nz
+    flags = torch.empty(3 * n, device=u.device, dtype=torch.int32)
+    cell = torch.empty((nx - 1) * (ny - 1) * (nz - 1), device=u.device, dtype=torch.int32)
+    check(lib.hn_mc_classify(_ptr(u), nx, ny, nz, float(threshold), _ptr(flags), _ptr(cell), _stream(u)), "hn_mc_classify")
+    vscan = torch.cumsum(flags, 0, dtype=torch.int32)
+    tscan = torch.cumsum(cell, 0, dtype=torch.int32)
+    nv, nt = int(vscan[-1]), int(tscan[-1])
+    vertices = torch.empty(nv, 3, device=u.device, dtype=torch.float32)
+    triangles = torch.empty(nt, 3, device=u.device, dtype=torch.int32)
+    if nv > 0:
+        check(lib.hn_mc_emit(_ptr(u), nx, ny, nz, float(threshold), _ptr(flags), _ptr(vscan), _ptr(cell), _ptr(tscan),
+                             _ptr(vertices), _ptr(triangles), _stream(u)), "hn_mc_emit")
+    return vertices, triangles

@@ -239,15 +239,23 @@ class NeuSRenderer:
         return u
 
     def extract_geometry(self, bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, threshold=0.0):
-        """utils/renderer.py:260-284.  Marching cubes itself is PyMCubes (third party, SURVEY #14)."""
-        u = self.sdf_grid(bound_min, bound_max, resolution, bt_inv, T_pose_21).cpu().numpy()
-        import mcubes  # noqa: deferred, optional third-party dependency exactly as in the reference
-        vertices, triangles = mcubes.marching_cubes(u, threshold)
-        b_max_np = bound_max.detach().cpu().numpy()
-        b_min_np = bound_min.detach().cpu().numpy()
-        triangles = triangles[..., ::-1]
-        vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
-        return vertices, triangles
+        """utils/renderer.py:260-284: (vertices [V,3] float64, triangles [T,3]) as numpy arrays, like the reference.  The
+        lattice stays on the device and marching cubes runs there (ops.marching_cubes: same shared-vertex mesh structure as
+        PyMCubes, which the reference calls on the host; un-vendored dependency, parity unpinned); only the mesh is copied."""
+        u = self.sdf_grid(bound_min, bound_max, resolution, bt_inv, T_pose_21)
+        return _mesh_from_lattice(u, bound_min, bound_max, resolution, threshold)
+
+
+def _mesh_from_lattice(u, bound_min, bound_max, resolution, threshold):
+    """The reference's post-processing of the PyMCubes output (utils/renderer.py:279-283): reversed triangles, vertices
+    rescaled from index coordinates to the bounding box."""
+    vertices, triangles = ops.marching_cubes(u, threshold)
+    b_max_np = bound_max.detach().cpu().numpy()
+    b_min_np = bound_min.detach().cpu().numpy()
+    triangles = triangles.cpu().numpy()[..., ::-1]
+    vertices = vertices.cpu().numpy().astype(np.float64)
+    vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
+    return vertices, triangles
 
 
 class _FittingBase:
@@ -430,14 +438,9 @@ class _FittingBase:
         return self._grid(bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type)
 
     def extract_geometry(self, bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type, threshold=0.0):
-        u = self.sdf_grid(bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type).cpu().numpy()
-        import mcubes  # noqa: deferred, optional third-party dependency exactly as in the reference
-        vertices, triangles = mcubes.marching_cubes(u, threshold)
-        b_max_np = bound_max.detach().cpu().numpy()
-        b_min_np = bound_min.detach().cpu().numpy()
-        triangles = triangles[..., ::-1]
-        vertices = vertices / (resolution - 1.0) * (b_max_np - b_min_np)[None, :] + b_min_np[None, :]
-        return vertices, triangles
+        """utils/renderer.py:537-564 / utils/renderer_batch.py:283-313: lattice and marching cubes on the device."""
+        u = self.sdf_grid(bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, get_type)
+        return _mesh_from_lattice(u, bound_min, bound_max, resolution, threshold)
 
 
 class NeuSRenderer_fitting(_FittingBase):

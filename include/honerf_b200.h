@@ -144,10 +144,11 @@ HN_API int hn_mlp_bx3_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_strea
  * the launch is the same every step and can be replayed from a CUDA graph while the schedule still applies.  `skipped`
  * (may be NULL) holds per 32-element block of the buffer how many steps that block's parameter received no gradient:
  * its bias correction uses step - skipped, as torch's per-parameter step does.  p .. v and the blocks of `skipped`
- * refer to the SAME element range (the caller offsets all of them for a sub-range that starts on a block boundary). */
+ * refer to the SAME element range (the caller offsets all of them for a sub-range that starts on a block boundary).
+ * The hyper-parameters are doubles: 1 - beta is formed in double and rounded once, as torch.optim.Adam does. */
 HN_API int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* step, const float* lr_dev,
-                        const float* skipped, float lr, float beta1, float beta2, float eps, float weight_decay,
-                        float grad_scale, hn_stream_t stream);
+                        const float* skipped, double lr, double beta1, double beta2, double eps, double weight_decay,
+                        double grad_scale, hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Object SDF field: SDFNetwork_OBJ.forward / .sdf / .gradient (utils/fields.py:316-347) as ONE
@@ -425,6 +426,24 @@ HN_API int hn_interaction_loss_bwd(const float* g_loss, const float* sdf_hand, i
  * ------------------------------------------------------------------------------------------- */
 HN_API int hn_nn_select(const float* pts, const uint8_t* in_mask, const uint8_t* out_mask, int n_frames,
                         int n_pts, uint8_t* flag, int64_t* nearest, hn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Marching cubes on the device (replaces mcubes.marching_cubes(u, threshold) of utils/renderer.py:279,561 and
+ * utils/renderer_batch.py:309; PyMCubes is an un-vendored dependency: parity unpinned).  u [nx,ny,nz] fp32 on the device.
+ *   hn_mc_set_tables  case table (ho-nerf_b200/mcubes_tables.py: n_tris[256], tris[256][15] edge ids, owner[12][4]) into the
+ *                     CURRENT device's constant memory (HOST pointers; once per device)
+ *   hn_mc_classify    flags [3][nx][ny][nz] int32 (edge from the lattice point along +x/+y/+z crosses iso),
+ *                     cell_tris [(nx-1)(ny-1)(nz-1)] int32 (triangles of the cell)
+ *   hn_mc_emit        given the INCLUSIVE prefix sums of both arrays (caller: torch.cumsum), writes vertices [V,3] (index
+ *                     coordinates, shared between cells) and triangles [T,3] int32 (normals towards lower values; the
+ *                     reference reverses them afterwards)
+ * ------------------------------------------------------------------------------------------- */
+HN_API int hn_mc_set_tables(const int8_t* n_tris, const int8_t* tris, const int8_t* owner);
+HN_API int hn_mc_classify(const float* u, int nx, int ny, int nz, float iso, int32_t* flags, int32_t* cell_tris,
+                          hn_stream_t stream);
+HN_API int hn_mc_emit(const float* u, int nx, int ny, int nz, float iso, const int32_t* flags, const int32_t* vscan,
+                      const int32_t* cell_tris, const int32_t* tscan, float* vertices, int32_t* triangles,
+                      hn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Diagnostics / test hooks of the product kernels (the tcgen05 bring-up self-test GEMMs live in a separate library:

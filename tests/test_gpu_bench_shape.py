@@ -185,6 +185,17 @@ def test_end_to_end_on_knot_margin_filtered_rays():
     got = _named_grads(sdf, col, var, Ro, To)
     worst = {k: rel_l2(got[k], ref_g[k]) for k in names}
     print("worst gradient rel-L2:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
+    # End to end the product renders on ITS samples and the oracle on its own: the kept rays' samples still differ by up to
+    # 1e-4.  How much that alone moves a gradient is a property of the reference, measured here by feeding the fp64 oracle
+    # the product's sample positions: `sens`.  Bound = max(1e-2, 2 x the reference's fp32-vs-fp64 error, 2 x sens); the
+    # comparison on IDENTICAL samples (test_bench_step_vs_fp64_oracle_on_the_products_z_vals) has no such term.
     own = reference_fp32_own_error(sub, zref[idx], ref_g, names)
-    bad = {k: (v, own[k]) for k, v in worst.items() if not v < max(1e-2, 2.0 * own[k])}
+    _, _, ref_g2, _ = oracle_core_fp64(sub, zg[idx])
+    sens = {k: rel_l2(ref_g2[k], ref_g[k]) for k in names}
+    print("reference fp64 on the product's samples vs on its own:", sorted(sens.items(), key=lambda kv: -kv[1])[:5])
+    bad = {k: (v, own[k], sens[k]) for k, v in worst.items() if not v < max(1e-2, 2.0 * own[k], 2.0 * sens[k])}
     assert not bad, bad
+    # against the oracle evaluated on the product's own samples the plain bound holds (colour net: 2 x the fp32 yardstick)
+    worst2 = {k: rel_l2(got[k], ref_g2[k]) for k in names}
+    print("vs the oracle on the product's samples:", sorted(worst2.items(), key=lambda kv: -kv[1])[:5])
+    assert not {k: v for k, v in worst2.items() if not v < max(1e-2, 2.0 * own[k])}, worst2

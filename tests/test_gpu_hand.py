@@ -138,10 +138,11 @@ def test_hand_render_core_given_same_z():
     _hand_same_z(None)
 
 
-def _hand_same_z(own_factor):
-    """own_factor: None -> every gradient within 1e-2; a number -> within max(1e-2, own_factor x the error of the
+def _hand_same_z(own_factor, floor=1e-2):
+    """own_factor: None -> every gradient within `floor`; a number -> within max(floor, own_factor x the error of the
     reference's OWN fp32 arithmetic against fp64 on this case) -- the synthetic hand weights make normals of magnitude
-    up to ~70 whose sin/cos(8 n) encodings amplify any rounding of n (the reference in fp32 is itself 0.7-1.4e-2 off)."""
+    up to ~70 whose sin/cos(8 n) encodings amplify any rounding of n (the reference in fp32 is itself 0.5-1.4e-2 off,
+    depending on the host's thread count)."""
     import honerf_b200 as H
     import ref_conf
     c = cases.hand_render_case()
@@ -183,7 +184,7 @@ def _hand_same_z(own_factor):
     got.update({"variance": dev.variance.grad, "bt_inv": bt.grad, "T": T.grad})
     worst = {k: rel_l2(got[k], ref_g[k]) for k in names}
     print("worst:", sorted(worst.items(), key=lambda kv: -kv[1])[:5])
-    bound = {k: 1e-2 for k in names}
+    bound = {k: floor for k in names}
     if own_factor is not None:
         sp32 = {k: v.clone().requires_grad_(k != "se3_refine") for k, v in sp.items()}
         cp32 = {k: v.clone().requires_grad_(True) for k, v in cp.items()}
@@ -196,6 +197,6 @@ def _hand_same_z(own_factor):
         own = dict(zip(names, torch.autograd.grad(cases.hand_render_loss(out32, c["true_rgb"]), t32)))
         own = {k: rel_l2(own[k], ref_g[k]) for k in names}
         print("reference fp32 vs fp64:", sorted(own.items(), key=lambda kv: -kv[1])[:5])
-        bound = {k: max(1e-2, own_factor * own[k]) for k in names}
+        bound = {k: max(floor, own_factor * own[k]) for k in names}
     bad = {k: (v, bound[k]) for k, v in worst.items() if not v < bound[k]}
     assert not bad, bad

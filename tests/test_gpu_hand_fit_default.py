@@ -39,11 +39,13 @@ def test_hand_render_vs_golden_default():
 
 def test_hand_render_core_given_same_z_default():
     """Same-z hand render_core under the tensor-core default: colour 3e-3 / weights 1e-4 as under SIMT; every gradient
-    (weights, variance, bt_inv, T_pose_21) within max(1e-2, 4 x the reference's own fp32-vs-fp64 error) -- measured on
-    the B200: 2.0-2.5e-2 where the reference's fp32 arithmetic is itself 0.7-1.4e-2 off (ill-conditioned synthetic case,
-    see _hand_same_z); the object field's same-z test holds the plain 1e-2."""
+    (weights, variance, bt_inv, T_pose_21) within 2.5e-2 -- measured on the B200: 2.0-2.2e-2 where the reference's own fp32
+    arithmetic is 0.5-1.4e-2 off fp64 (ill-conditioned synthetic case, see _hand_same_z: the per-layer bf16 hi+lo
+    contractions carry 16 mantissa bits, the normal of magnitude ~70 enters the colour net as sin / cos(8 n), and a flipped
+    ReLU gate moves the summed weight gradients); the fp32 SIMT path holds 1e-2 on the same case and the object field's
+    same-z test holds the plain 1e-2 under the default."""
     _assert_default()
-    TH._hand_same_z(4.0)
+    TH._hand_same_z(2.0, floor=2.5e-2)
 
 
 def test_fit_render_vs_golden_default():
@@ -59,9 +61,11 @@ def test_fit_render_given_same_z_default():
 
 
 def test_fit_render_batch_given_same_z_default():
-    """renderer_batch.NeuSRenderer_fitting (utils/renderer_batch.py:184-281), frame-batched."""
+    """renderer_batch.NeuSRenderer_fitting (utils/renderer_batch.py:184-281), frame-batched: pose gradients within
+    max(1.5e-2, 2 x the reference's own fp32-vs-fp64 error) under the tensor-core default (measured 0.5-1.0e-2 where the
+    reference's fp32 arithmetic is 0.4e-2 off; the SIMT path holds max(1e-2, 2 x own))."""
     _assert_default()
-    TF._same_z(True)
+    TF._same_z(True, floor=1.5e-2)
 
 
 def test_fit_render_batch_vs_golden_default():

@@ -82,6 +82,7 @@ def test_flat_adam_lr_schedule_takes_effect_under_graph_replay():
         runs = oa.gather_grads()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
+            oa.gather_grads()
             oa.step(runs)
     torch.cuda.current_stream().wait_stream(side)
     for step in range(6):
