@@ -13,7 +13,8 @@ principles:
   only, so the two cells sharing a face always agree and the extracted surface has no cracks (the classic 1987 table does
   not have this property for every configuration);
 * the face segments are oriented (inside on the left, seen from outside the cell), chained into closed loops and each loop is
-  triangulated as a fan: at most 12 - 2 * (number of loops) triangles per cell.
+  triangulated so that no diagonal (hence no triangle) lies inside a face of the cell (see _triangulate): at most five
+  triangles per cell.
 
 Triangles come out with their normal pointing to the INSIDE (towards lower values), which is the orientation the reference
 then flips with ``triangles[..., ::-1]`` to get outward normals of a signed distance field.
@@ -104,6 +105,53 @@ def _orientation_flip():
     return 1 if _dot(n, to_inside) > 0 else -1
 
 
+def _face_edge_sets():
+    return [frozenset(_EDGE_ID[frozenset((q[i], q[(i + 1) % 4]))] for i in range(4)) for q in _ccw_faces()]
+
+
+def _triangulations(poly):
+    """every triangulation of a convex polygon given as a vertex list (Catalan many; loops have at most 7 vertices here... 12 in
+    principle), as lists of triangles keeping the polygon's orientation"""
+    if len(poly) < 3:
+        return [[]]
+    if len(poly) == 3:
+        return [[tuple(poly)]]
+    out = []
+    a, b = poly[0], poly[-1]
+    for k in range(1, len(poly) - 1):
+        for left in _triangulations(poly[:k + 1]):
+            for right in _triangulations(poly[k:]):
+                out.append(left + [(a, poly[k], b)] + right)
+    return out
+
+
+def _triangulate(loop):
+    """A triangulation of the loop none of whose DIAGONALS joins two cell edges of one face: such a diagonal lies in that
+    face without being one of its iso-line segments, and the neighbouring cell (which sees the same four crossings on an
+    ambiguous face) may draw it too -- four triangles on one edge, or, when a whole triangle lies in the face, a zero-volume
+    double sheet.  Plain fans do this for some loops through an ambiguous face."""
+    faces = _face_edge_sets()
+    ring = {frozenset((loop[i], loop[(i + 1) % len(loop)])) for i in range(len(loop))}
+
+    def in_face_diagonals(tri):
+        n = 0
+        for t in tri:
+            for x, y in ((t[0], t[1]), (t[1], t[2]), (t[2], t[0])):
+                if frozenset((x, y)) not in ring and any(x in f and y in f for f in faces):
+                    n += 1
+        return n
+
+    best = None
+    for tri in _triangulations(loop):
+        n_bad = in_face_diagonals(tri)
+        if best is None or n_bad < best[0]:
+            best = (n_bad, tri)
+        if n_bad == 0:
+            break
+    assert best[0] == 0, ("no triangulation without in-face diagonals", loop)
+    return best[1]
+
+
 def build_tables():
     """(n_tris[256], tris[256][MAX_TRIS * 3] edge ids (-1 padded), edge_owner[12] = (dx, dy, dz, axis))."""
     flip = _orientation_flip()
@@ -113,8 +161,8 @@ def build_tables():
         for loop in _loops(case):
             if flip < 0:
                 loop = list(reversed(loop))
-            for i in range(1, len(loop) - 1):
-                row += [loop[0], loop[i], loop[i + 1]]
+            for t in _triangulate(loop):
+                row += list(t)
         assert len(row) <= MAX_TRIS * 3, (case, len(row))
         n_tris.append(len(row) // 3)
         tris.append(row + [-1] * (MAX_TRIS * 3 - len(row)))

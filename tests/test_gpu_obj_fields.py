@@ -145,3 +145,21 @@ def test_sdf_grid_vs_golden():
     r = H.NeuSRenderer(sdf, dev, col, "obj", 64, 64, 0, 4, 1.0)
     u = r.sdf_grid(torch.full((3,), c["lo"]), torch.full((3,), c["hi"]), c["res"], chunk_points=500)
     assert max_abs(u, g["u"]) < 2e-5
+
+
+def test_in_place_weight_update_between_forward_and_backward_raises():
+    """The backward reads the packed weights shared by every call of the net; an in-place parameter update (optimizer step)
+    between a call's forward and its backward is an error like torch's own version-counter check, not a silent wrong
+    gradient."""
+    import honerf_b200 as H
+    sdf, col, _, _, _ = obj_modules()
+    x = (0.4 * torch.randn(300, 3)).to(DEV).requires_grad_(True)
+    s, f, n = sdf.fused(x)
+    with torch.no_grad():
+        next(iter(sdf.parameters())).mul_(1.0001)
+    with pytest.raises(H.HonerfError, match="changed between forward and backward"):
+        (s.sum() + n.sum()).backward()
+    # the next forward re-packs and works again
+    s, f, n = sdf.fused(x)
+    (s.sum() + f.sum() + n.sum()).backward()
+    assert torch.isfinite(x.grad).all()
