@@ -97,61 +97,90 @@ __global__ void __launch_bounds__(HALO_WARPS * 32) halo_normal_kernel(
 //   dq_j = F'^T DF_j + H_j(FB_j) (R_j dn);   d_x = sum_j R_j^T dq_j
 //   dR_j += dq_j x^T + g_j(FB_j) dn^T ;  dt_j += dq_j ;  dT_j -= dq_j
 // d_bt [frames, 21, 16] (row-major 4x4, last row untouched) and d_T [frames, 21, 3] are ACCUMULATED.
+// Each warp walks a contiguous run of points and keeps the pose gradients of its joint (lane) in registers; they are
+// flushed with one atomicAdd per entry when the frame changes and at the end of the run (the per-point atomics of the
+// first version serialised on the 21 x 15 addresses of a frame).
 __global__ void __launch_bounds__(HALO_WARPS * 32) halo_bwd_kernel(
     const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp,
     const float* __restrict__ DF, int64_t ld_df, const float* __restrict__ FB, int64_t ld_fb,
-    const float* __restrict__ dn, int64_t n, int64_t ppf, float* __restrict__ d_pts, float* __restrict__ d_bt,
-    float* __restrict__ d_T) {
+    const float* __restrict__ dn, int64_t n, int64_t ppf, int64_t pts_per_warp, float* __restrict__ d_pts,
+    float* __restrict__ d_bt, float* __restrict__ d_T) {
     __shared__ float sdf_[HALO_WARPS][HALO_DIM + 2];
     __shared__ float sfb_[HALO_WARPS][HALO_DIM + 2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t p = (int64_t)blockIdx.x * HALO_WARPS + warp;
-    if (p >= n) return;
-    const int64_t f = p / ppf;
-    for (int i = lane; i < HALO_DIM; i += 32) {
-        sdf_[warp][i] = DF ? DF[p * ld_df + i] : 0.0f;
-        sfb_[warp][i] = (dn && FB) ? FB[p * ld_fb + i] : 0.0f;
-    }
-    __syncwarp();
-    float x[3], t[3] = {0.f, 0.f, 0.f}, dx[3] = {0.f, 0.f, 0.f};
-    load_x(pts, p, x);
-    if (dn) load_x(dn, p, t);
-    if (lane < HALO_J) {
-        const float* M = bt_inv + (f * HALO_J + lane) * 16;
-        HaloBase b = halo_base(M, Tp + (f * HALO_J + lane) * 3, x, lane);
-        if (!b.dead) {
-            float gq[3], g2[3] = {0.f, 0.f, 0.f}, hv[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f}, dummy[3];
-            halo_grad_hvp<false>(b, &sdf_[warp][lane * HALO_F], w, gq, dummy);
-            if (dn) {
+    const int64_t p_begin = ((int64_t)blockIdx.x * HALO_WARPS + warp) * pts_per_warp;
+    const int64_t p_end = min(n, p_begin + pts_per_warp);
+    float acc_bt[12], acc_T[3];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) w[a] = M[a * 4] * t[0] + M[a * 4 + 1] * t[1] + M[a * 4 + 2] * t[2];
-                halo_grad_hvp<true>(b, &sfb_[warp][lane * HALO_F], w, g2, hv);
+    for (int i = 0; i < 12; ++i) acc_bt[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) acc_T[i] = 0.0f;
+    int64_t f_acc = -1;
+    auto flush = [&]() {
+        if (f_acc < 0 || lane >= HALO_J) return;
+        if (d_bt) {
+            float* db = d_bt + (f_acc * HALO_J + lane) * 16;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                if (acc_bt[i] != 0.0f) atomicAdd(&db[i], acc_bt[i]);
+                acc_bt[i] = 0.0f;
             }
-            float dq[3];
+        }
+        if (d_T) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) dq[a] = gq[a] + hv[a];
+            for (int a = 0; a < 3; ++a) {
+                if (acc_T[a] != 0.0f) atomicAdd(&d_T[(f_acc * HALO_J + lane) * 3 + a], acc_T[a]);
+                acc_T[a] = 0.0f;
+            }
+        }
+    };
+    for (int64_t p = p_begin; p < p_end; ++p) {
+        const int64_t f = p / ppf;
+        if (f != f_acc) {
+            flush();
+            f_acc = f;
+        }
+        __syncwarp();
+        for (int i = lane; i < HALO_DIM; i += 32) {
+            sdf_[warp][i] = DF ? DF[p * ld_df + i] : 0.0f;
+            sfb_[warp][i] = (dn && FB) ? FB[p * ld_fb + i] : 0.0f;
+        }
+        __syncwarp();
+        float x[3], t[3] = {0.f, 0.f, 0.f}, dx[3] = {0.f, 0.f, 0.f};
+        load_x(pts, p, x);
+        if (dn) load_x(dn, p, t);
+        if (lane < HALO_J) {
+            const float* M = bt_inv + (f * HALO_J + lane) * 16;
+            HaloBase b = halo_base(M, Tp + (f * HALO_J + lane) * 3, x, lane);
+            if (!b.dead) {
+                float gq[3], g2[3] = {0.f, 0.f, 0.f}, hv[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f}, dummy[3];
+                halo_grad_hvp<false>(b, &sdf_[warp][lane * HALO_F], w, gq, dummy);
+                if (dn) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) dx[a] = M[0 * 4 + a] * dq[0] + M[1 * 4 + a] * dq[1] + M[2 * 4 + a] * dq[2];
-            if (d_bt) {
-                float* db = d_bt + (f * HALO_J + lane) * 16;
+                    for (int a = 0; a < 3; ++a) w[a] = M[a * 4] * t[0] + M[a * 4 + 1] * t[1] + M[a * 4 + 2] * t[2];
+                    halo_grad_hvp<true>(b, &sfb_[warp][lane * HALO_F], w, g2, hv);
+                }
+                float dq[3];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) dq[a] = gq[a] + hv[a];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) dx[a] = M[0 * 4 + a] * dq[0] + M[1 * 4 + a] * dq[1] + M[2 * 4 + a] * dq[2];
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) atomicAdd(&db[a * 4 + c], dq[a] * x[c] + g2[a] * t[c]);
-                    atomicAdd(&db[a * 4 + 3], dq[a]);
+                    for (int c = 0; c < 3; ++c) acc_bt[a * 4 + c] += dq[a] * x[c] + g2[a] * t[c];
+                    acc_bt[a * 4 + 3] += dq[a];
+                    acc_T[a] -= dq[a];
                 }
             }
-            if (d_T) {
+        }
+        if (d_pts) {
 #pragma unroll
-                for (int a = 0; a < 3; ++a) atomicAdd(&d_T[(f * HALO_J + lane) * 3 + a], -dq[a]);
-            }
+            for (int a = 0; a < 3; ++a) dx[a] = warp_sum(dx[a]);
+            if (lane < 3) d_pts[p * 3 + lane] = lane == 0 ? dx[0] : (lane == 1 ? dx[1] : dx[2]);
         }
     }
-    if (d_pts) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) dx[a] = warp_sum(dx[a]);
-        if (lane < 3) d_pts[p * 3 + lane] = lane == 0 ? dx[0] : (lane == 1 ? dx[1] : dx[2]);
-    }
+    flush();
 }
 
 // D7[p, c] = s'(H7[p, c]) * w_out0[c]
@@ -446,13 +475,8 @@ int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
     hand_assemble_dz8_kernel<<<nblocks(n * 260, 256), 256, 0, s>>>(d_sdf, d_feat, ld_dfeat, n, DZ8);
     count_launch();
     HN_CHECK_LAUNCH();
-    // DF starts as the cotangent that reaches the feature from outside (the colour net)
-    if (need_input_grad) {
-        copy_rows_kernel<<<nblocks(n * HFB_LD, 256), 256, 0, s>>>(d_xyz_feature, ld_dxyz, n,
-                                                                  d_xyz_feature ? HALO_DIM : HFB_LD, DF, HFB_LD);
-        count_launch();
-        HN_CHECK_LAUNCH();
-    }
+    // DF starts as the cotangent that reaches the feature from outside (the colour net): it enters as the aux operand of
+    // the first contraction that writes DF (the skip part of layer 4), no copy
     const float* dz = DZ8;
     int64_t ld_dz = 260;
     for (int l = 8; l >= 1; --l) {
@@ -474,8 +498,13 @@ int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
             f.A = dz; f.lda = ld_dz;
             set_w(f, mlp, 4, HFEAT_OFF);
             f.M = (int)n; f.N = HALO_DIM; f.K = 256;
-            f.C = DF; f.ldc = HFB_LD; f.aux1 = DF; f.ldaux1 = HFB_LD;
-            HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(f, s, precision)));
+            f.C = DF; f.ldc = HFB_LD;
+            if (d_xyz_feature) {
+                f.aux1 = d_xyz_feature; f.ldaux1 = ld_dxyz;
+                HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(f, s, precision)));
+            } else {
+                HN_PROPAGATE((gemm_nn<EPI_STORE>(f, s, precision)));
+            }
         }
         dz = out; ld_dz = 256;
     }
@@ -488,9 +517,10 @@ int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
         g.M = (int)n; g.N = HALO_DIM; g.K = 256;
         g.C = DF; g.ldc = HFB_LD; g.aux1 = DF; g.ldaux1 = HFB_LD;
         HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(g, s, precision)));
-        halo_bwd_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, DF, HFB_LD, st.FB, HFB_LD,
-                                                                           d_normal, n, pts_per_frame, d_pts, d_bt_inv,
-                                                                           d_T_pose);
+        // ~16 blocks per SM in flight; every warp owns a contiguous run of points
+        const int64_t per_warp = max((int64_t)1, ceil_div(n, (int64_t)sm_count() * 16 * HALO_WARPS));
+        halo_bwd_kernel<<<nblocks(ceil_div(n, per_warp), HALO_WARPS), HALO_WARPS * 32, 0, s>>>(
+            pts, bt_inv, T_pose, DF, HFB_LD, st.FB, HFB_LD, d_normal, n, pts_per_frame, per_warp, d_pts, d_bt_inv, d_T_pose);
         count_launch();
         HN_CHECK_LAUNCH();
     }

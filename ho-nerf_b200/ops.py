@@ -455,6 +455,20 @@ def sdf_hand_sdf_only(packed, pts, bt_inv, T_pose_21, precision=None):
     return sdf
 
 
+_HAND_ROW_LD = 1644      # csrc/fields_hand.cu HROW_LD
+
+
+def _rows_f32(t):
+    """(tensor, leading dimension) of a 2-D fp32 tensor whose rows are contiguous and 16-byte aligned (a column slice of a
+    wider buffer is passed as it is); anything else is made contiguous first."""
+    t = t.detach()
+    if (t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0 and t.stride(0) >= t.shape[1]
+            and t.data_ptr() % 16 == 0):
+        return t, t.stride(0)
+    t = _f32c(t)
+    return t, t.shape[1]
+
+
 class _SdfHandFn(torch.autograd.Function):
     """(sdf, feature, normal, xyz_feature) = f(pts, bt_inv, T_pose_21, params)."""
 
@@ -467,12 +481,14 @@ class _SdfHandFn(torch.autograd.Function):
         sdf = torch.empty(n, 1, device=dev)
         feat = torch.empty(n, 256, device=dev)
         normal = torch.empty(n, 3, device=dev)
-        xyz = torch.empty(n, 1386, device=dev)
         stf = lib.hn_sdf_hand_stash_floats(n)
         stash = torch.empty(max(stf, 4), device=dev, dtype=torch.float32)
+        # xyz_feature is a view of the stash's skip-input rows [h3 256 | feature 1386 | pad 2] (ld 1644): no copy; the
+        # backward only reads that part of the stash
+        xyz = stash[:n * _HAND_ROW_LD].view(n, _HAND_ROW_LD)[:, 256:256 + 1386]
         if n > 0:
             check(lib.hn_sdf_hand_fwd(ctypes.byref(pk.struct), _ptr(pts_c), _ptr(bt_c), _ptr(T_c), n, ppf, _ptr(sdf),
-                                      _ptr(feat), 256, _ptr(normal), _ptr(xyz), 1386, _ptr(stash), stf, precision,
+                                      _ptr(feat), 256, _ptr(normal), None, 0, _ptr(stash), stf, precision,
                                       _stream(pts_c)), "hn_sdf_hand_fwd")
         ctx.packed, ctx.stash, ctx.n, ctx.ppf, ctx.precision, ctx.struct = pk, stash, n, ppf, precision, pk.struct
         ctx.pkey = pk._key
@@ -490,7 +506,7 @@ class _SdfHandFn(torch.autograd.Function):
         n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
         d_sdf = _f32c(d_sdf) if d_sdf is not None else None
         d_feat = _f32c(d_feat) if d_feat is not None else None
-        d_xyz = _f32c(d_xyz) if d_xyz is not None else None
+        d_xyz, ld_dxyz = _rows_f32(d_xyz) if d_xyz is not None else (None, 1386)
         d_normal = _f32c(d_normal) if d_normal is not None else torch.zeros(n, 3, device=dev)
         d_pts = torch.empty(n, 3, device=dev) if ctx.need[0] else None
         d_bt = torch.zeros_like(ctx.bt_c) if ctx.need[1] else None
@@ -503,7 +519,7 @@ class _SdfHandFn(torch.autograd.Function):
             wsf = lib.hn_sdf_hand_ws_floats(n, HN_WS_BWD)
             ws = torch.empty(wsf, device=dev, dtype=torch.float32)
             check(lib.hn_sdf_hand_bwd(ctypes.byref(ctx.struct), _ptr(ctx.pts_c), _ptr(ctx.bt_c), _ptr(ctx.T_c), n, ctx.ppf,
-                                      _ptr(ctx.stash), _ptr(d_sdf), _ptr(d_feat), 256, _ptr(d_normal), _ptr(d_xyz), 1386,
+                                      _ptr(ctx.stash), _ptr(d_sdf), _ptr(d_feat), 256, _ptr(d_normal), _ptr(d_xyz), ld_dxyz,
                                       _ptr(d_pts), _ptr(d_bt), _ptr(d_T), ctypes.byref(gs) if gs is not None else None,
                                       _ptr(ws), wsf, ctx.precision, _stream(ctx.stash)), "hn_sdf_hand_bwd")
             if gs is not None:
@@ -525,7 +541,7 @@ def sdf_hand(packed, pts, bt_inv, T_pose_21, precision=None):
 class _ColorHandFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, feat, normal, packed, precision, *params):
-        xyz_c, feat_c, nrm_c = _f32c(xyz.detach()), _f32c(feat.detach()), _f32c(normal.detach())
+        (xyz_c, ld_xyz), feat_c, nrm_c = _rows_f32(xyz), _f32c(feat.detach()), _f32c(normal.detach())
         _require_cuda(xyz_c, "color_hand")
         pk = packed.get()
         n, dev = xyz_c.shape[0], xyz_c.device
@@ -533,7 +549,7 @@ class _ColorHandFn(torch.autograd.Function):
         stf = lib.hn_color_hand_stash_floats(n)
         stash = torch.empty(max(stf, 4), device=dev, dtype=torch.float32)
         if n > 0:
-            check(lib.hn_color_hand_fwd(ctypes.byref(pk.struct), _ptr(xyz_c), xyz_c.shape[1], _ptr(feat_c),
+            check(lib.hn_color_hand_fwd(ctypes.byref(pk.struct), _ptr(xyz_c), ld_xyz, _ptr(feat_c),
                                         feat_c.shape[1], _ptr(nrm_c), n, _ptr(rgb), _ptr(stash), stf, precision,
                                         _stream(xyz_c)), "hn_color_hand_fwd")
         ctx.packed, ctx.stash, ctx.n, ctx.precision, ctx.struct, ctx.rgb = pk, stash, n, precision, pk.struct, rgb
@@ -550,7 +566,8 @@ class _ColorHandFn(torch.autograd.Function):
         _check_same_weights(ctx, "color_hand backward")
         n, pk, dev = ctx.n, ctx.packed, ctx.stash.device
         d_rgb = _f32c(d_rgb)
-        d_xyz = torch.empty(n, 1386, device=dev) if ctx.need[0] else None
+        # rows padded to 1388 floats: the hand SDF backward takes this buffer as a 16-byte aligned aux operand
+        d_xyz = torch.empty(n, 1388, device=dev)[:, :1386] if ctx.need[0] else None
         d_feat = torch.empty(n, 256, device=dev) if ctx.need[1] else None
         d_nrm = torch.empty(n, 3, device=dev) if ctx.need[2] else None
         grads = [None] * (3 * len(pk.layers))
@@ -561,7 +578,7 @@ class _ColorHandFn(torch.autograd.Function):
             wsf = lib.hn_color_hand_ws_floats(n, HN_WS_BWD)
             ws = torch.empty(wsf, device=dev, dtype=torch.float32)
             check(lib.hn_color_hand_bwd(ctypes.byref(ctx.struct), n, _ptr(ctx.stash), _ptr(ctx.rgb), _ptr(d_rgb),
-                                        _ptr(d_xyz), 1386, _ptr(d_feat), 256, _ptr(d_nrm),
+                                        _ptr(d_xyz), 1388, _ptr(d_feat), 256, _ptr(d_nrm),
                                         ctypes.byref(gs) if gs is not None else None, _ptr(ws), wsf, ctx.precision,
                                         _stream(ctx.stash)), "hn_color_hand_bwd")
             if gs is not None:

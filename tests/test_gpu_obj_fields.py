@@ -156,7 +156,7 @@ def test_in_place_weight_update_between_forward_and_backward_raises():
     x = (0.4 * torch.randn(300, 3)).to(DEV).requires_grad_(True)
     s, f, n = sdf.fused(x)
     with torch.no_grad():
-        next(iter(sdf.parameters())).mul_(1.0001)
+        sdf.lin3.weight_v.mul_(1.0001)
     with pytest.raises(H.HonerfError, match="changed between forward and backward"):
         (s.sum() + n.sum()).backward()
     # the next forward re-packs and works again

@@ -26,13 +26,14 @@ ADDITIVE = ("trunk16", "nsweep16")
 
 
 def build_id(root=None):
-    """sha1 over the CUDA sources: bench.py refuses a traffic figure whose build differs from the library it is timing."""
+    """sha1 over the CUDA sources of the object-field chain kernels (the families the bench's roofline quotes traffic for) and
+    the headers they include: bench.py refuses a traffic figure whose build differs from the library it is timing."""
     import hashlib
     import os
     root = root or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ho-nerf_b200", "csrc")
     h = hashlib.sha1()
     for f in sorted(os.listdir(root)):
-        if f.endswith((".cu", ".cuh")):
+        if f.endswith((".cu", ".cuh")) and (f.startswith("chain") or f in ("tc_common.cuh", "common.cuh")):
             h.update(f.encode())
             h.update(open(os.path.join(root, f), "rb").read())
     return h.hexdigest()[:16]
