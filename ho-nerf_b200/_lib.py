@@ -92,6 +92,8 @@ PROTOTYPES = {
     "hn_wn_bwd_batch": (c_int, [POINTER(hn_wn_job_t), c_int, P]),
     "hn_mlp_bx3_bytes": (c_int64, [_mlp_p]),
     "hn_mlp_bx3_pack": (c_int, [_mlp_p, P, c_int64, P]),
+    "hn_sdf_hand_chain_bytes": (c_int64, [_mlp_p]),
+    "hn_sdf_hand_chain_pack": (c_int, [_mlp_p, P, c_int64, P]),
     "hn_adam_flat": (c_int, [P, P, P, P, c_int64, P, P, P] + [ctypes.c_double] * 6 + [P]),
     "hn_wn_pack_gap": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int, P]),
     "hn_wn_bwd_gap": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, P]),

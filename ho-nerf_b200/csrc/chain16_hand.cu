@@ -1,0 +1,697 @@
+// Hand SDF field (HALO pose-conditioned, utils/fields.py:56-177), HN_TC_MIXED16: the 256 x 256 layers of the value trunk,
+// the normal sweep, the tangent sweep and the reverse sweep as three persistent tile-chain kernels with the activations in
+// tensor memory (the machinery of chain16.cuh, built for the object field), three 16-bit MMAs per product.
+//
+// The two 1386-wide contractions on either side of the chain (HALO feature -> layer 0 / skip layer 4, and their transposes)
+// stay on the per-layer kernels (gemm_bx3.cuh); they meet the chain through fp32 row-major [points, 256] buffers:
+//   hand_trunk16_kernel   in : H0 = softplus(F W_0^T + b_0), ZF4 = F W_4[:, 256:]^T       out: sdf, feature, EM / EML tiles
+//   hand_nsweep16_kernel  in : EM / EML                                                    out: D16 tiles, D4, D0 rows
+//   hand_bwd16_kernel     in : Q0 = tF W_0^T, QF4 = tF W_4[:, 256:]^T, EM, D16, d_sdf / d_feat
+//                                                                                          out: DZ4, DZ0 rows (X16 scratch)
+// Used when no weight gradient is asked for (pose fitting, rendering): the weight-gradient contractions of the hand net
+// stay on the per-layer path (fields_hand.cu), which keeps an fp32 stash.
+#include <algorithm>
+
+#include "chain16.cuh"
+#include "chain_hand_layout.cuh"
+
+namespace hn {
+namespace chain {
+
+// ------------------------------------------------------------------------------------------------------------------
+// value trunk (layers 1..7 + feature head); TMEM columns [0,256) accumulator, [256,384) A_hi, [384,512) A_lo
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int HT_STAGE_BYTES = 128 * 128;
+constexpr int HT_STAGES = 12;
+constexpr int HT_HEAD_OFF = HT_STAGES * HT_STAGE_BYTES;
+constexpr int HT_SMEM_BYTES = HT_HEAD_OFF + EPI_CGROUPS * TILE_M * 4 + 1024;
+constexpr uint32_t HT_A_HI = 256, HT_A_LO = 384;
+
+struct HtBarriers {
+    uint64_t full[HT_STAGES];
+    uint64_t empty[HT_STAGES];
+    uint64_t a_ready;
+    uint64_t acc_full[2];    // one per N-half: each completes once per layer (see SwBarriers)
+    uint32_t tmem_base;
+};
+
+struct HandTrunkParams {
+    int64_t n;
+    const float* H0;         // [np, 256] fp32 rows
+    const float* ZF4;        // [np, 256] fp32 rows: the feature part of the skip layer's pre-activation
+    float* sdf;
+    float* feat;             // NULL: sdf only (no feature head, no stash)
+    int64_t ld_feat;
+    uint8_t* EM[8];          // fp16 T16 tiles: em = exp(-100 h) rounded to fp16 (NULL with feat == NULL)
+    uint8_t* EML[8];         // fp16 T16 tiles: fp16(em - fp16(em))
+    const uint8_t* chain;
+    const float* bias[9];
+    const float* w_out0;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_constant__ Program prog) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ HtBarriers bar;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float* s_head = reinterpret_cast<float*>(smem + HT_HEAD_OFF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tc::tmem_alloc(&bar.tmem_base, 512);
+    if (threadIdx.x == 32) {
+        for (int s = 0; s < HT_STAGES; ++s) {
+            tc::mbar_init(&bar.full[s], 1);
+            tc::mbar_init(&bar.empty[s], 1);
+        }
+        tc::mbar_init(&bar.a_ready, EPI_THREADS);
+        tc::mbar_init(&bar.acc_full[0], 1);
+        tc::mbar_init(&bar.acc_full[1], 1);
+        tc::mbar_fence_init();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = bar.tmem_base;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const bool stash = p.feat != nullptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int t = 0; t < n_my_tiles; ++t)
+                for (int s = 0; s < prog.n_steps; ++s) {
+                    const uint8_t* src = p.chain + prog.step[s].b_off;
+                    for (int c = 0; c < 2 * prog.step[s].kblocks; ++c) {
+                        tc::mbar_wait(&bar.empty[stage], phase ^ 1u);
+                        tc::mbar_arrive_expect_tx(&bar.full[stage], HT_STAGE_BYTES);
+                        tc::bulk_g2s(smem + stage * HT_STAGE_BYTES, src + (size_t)c * HT_STAGE_BYTES, HT_STAGE_BYTES, &bar.full[stage]);
+                        if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t ring = tc::smem_u32(smem);
+            const uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, 128);
+            uint32_t stage = 0, phase = 0, a_par = 0;
+            for (int t = 0; t < n_my_tiles; ++t)
+                for (int s = 0; s < prog.n_steps; ++s) {
+                    const Step st = prog.step[s];
+                    const uint32_t d = tmem + st.acc_col;
+                    if (!st.no_wait) {
+                        tc::mbar_wait(&bar.a_ready, a_par);
+                        a_par ^= 1u;
+                        tc::tc_fence_after_sync();
+                    }
+                    for (int kb = 0; kb < st.kblocks; ++kb) {
+                        const uint32_t ah = tmem + HT_A_HI + (uint32_t)kb * 32, al = tmem + HT_A_LO + (uint32_t)kb * 32;
+                        tc::mbar_wait(&bar.full[stage], phase);
+                        tc::tc_fence_after_sync();
+                        uint64_t dB = tc::make_smem_desc_sw128(ring + stage * HT_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            tc::umma_f16_ts(d, al + 8 * k, dB + 2 * k, idesc, (kb | k) != 0);
+                            tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc, 1);
+                        }
+                        tc::umma_commit(&bar.empty[stage]);
+                        if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                        tc::mbar_wait(&bar.full[stage], phase);
+                        tc::tc_fence_after_sync();
+                        dB = tc::make_smem_desc_sw128(ring + stage * HT_STAGE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc, 1);
+                        tc::umma_commit(&bar.empty[stage]);
+                        if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc::umma_commit(&bar.acc_full[st.acc_col ? 1 : 0]);
+                }
+        }
+    } else {
+        const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
+        uint32_t acc_par[2] = {0u, 0u};
+        auto publish = [&]() {
+            tc::tmem_st_wait();
+            tc::tc_fence_before_sync();
+            tc::mbar_arrive(&bar.a_ready);
+        };
+        auto wait_acc = [&](int hf) {
+            tc::mbar_wait(&bar.acc_full[hf], acc_par[hf]);
+            acc_par[hf] ^= 1u;
+            tc::tc_fence_after_sync();
+        };
+        auto store_a = [&](int col0, const uint32_t* hi, const uint32_t* lo) {
+            const uint32_t c = (uint32_t)(col0 >> 1);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + HT_A_HI + c, hi);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + HT_A_HI + c + 8, hi + 8);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + HT_A_LO + c, lo);
+            tc::tmem_st_32x32b_x8(tmem + lane_base + HT_A_LO + c + 8, lo + 8);
+        };
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            // 8 columns [c, c + 8) of layer l: EM / EML stash chunks + fp16 hi / lo words of the next A operand
+            auto emit8 = [&](int l, int c, const float* h, const float* em, uint32_t* hi4, uint32_t* lo4) {
+                if (stash) {
+                    const uint32_t off = t16_off(row, c >> 3);
+                    uint4 q, ql;
+                    split2_lo16(em[0], em[1], q.x, ql.x); split2_lo16(em[2], em[3], q.y, ql.y);
+                    split2_lo16(em[4], em[5], q.z, ql.z); split2_lo16(em[6], em[7], q.w, ql.w);
+                    stg16(p.EM[l] + (size_t)tile * T16_TILE_BYTES + off, q);
+                    stg16(p.EML[l] + (size_t)tile * T16_TILE_BYTES + off, ql);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) split2_lo16(h[2 * i], h[2 * i + 1], hi4[i], lo4[i]);
+            };
+            // softplus of accumulator columns [col0, +32) of layer l (+ the feature part of the skip layer's pre-activation)
+            auto act_half = [&](int l, int col0, uint32_t* hh, uint32_t* hl, float& head) {
+                const float* __restrict__ bias = p.bias[l];
+                float v[32];
+                acc_load32(tmem, row, col0, v);
+                if (l == 4 && live) {
+                    const float* __restrict__ z = p.ZF4 + gp * 256 + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 a = ld4(z + j);
+                        v[j] += a.x; v[j + 1] += a.y; v[j + 2] += a.z; v[j + 3] += a.w;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j + 4));
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    float h[8], em[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) h[i] = softplus100_em(v[j + i] + bb[i], em[i]);
+                    emit8(l, col0 + j, h, em, hh + (j >> 1), hl + (j >> 1));
+                    if (l == 7) {
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j));
+                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_out0 + col0 + j + 4));
+                        head += h[0] * w0.x + h[1] * w0.y + h[2] * w0.z + h[3] * w0.w + h[4] * w1.x + h[5] * w1.y + h[6] * w1.z + h[7] * w1.w;
+                    }
+                }
+            };
+            // ---- layer 0's activation rows (the feature contraction ran before this kernel) -> first A operand -----------
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                const int col0 = 128 * hf + cg * 32;
+                uint32_t hh[16], hl[16];
+                const float* __restrict__ hrow = p.H0 + gp * 256 + col0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float h[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, em[8];
+                    if (live) {
+                        const float4 a = ld4(hrow + j), b = ld4(hrow + j + 4);
+                        h[0] = a.x; h[1] = a.y; h[2] = a.z; h[3] = a.w; h[4] = b.x; h[5] = b.y; h[6] = b.z; h[7] = b.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) em[i] = ex2_approx(-h[i] * 144.26950408889634f);      // exp(-100 h)
+                    emit8(0, col0 + j, h, em, hh + (j >> 1), hl + (j >> 1));
+                }
+                store_a(col0, hh, hl);
+            }
+            publish();
+            float head = 0.0f;
+            for (int l = 1; l < 8; ++l) {
+                uint32_t hh[16], hl[16];
+                // first half (columns cg*32 ..) under the second half's MMAs
+                wait_acc(0);
+                act_half(l, cg * 32, hh, hl, head);
+                // second half: every MMA of the layer has read A, it may be overwritten
+                wait_acc(1);
+                const bool feeds = l < 7 || stash;      // sdf only: layer 7 feeds no further MMA step, nothing to publish
+                if (feeds) store_a(cg * 32, hh, hl);
+                act_half(l, 128 + cg * 32, hh, hl, head);
+                if (feeds) {
+                    store_a(128 + cg * 32, hh, hl);
+                    publish();
+                }
+            }
+            // sdf = h7 . W_out[0] + b_out[0]
+            s_head[cg * TILE_M + row] = head;
+            tc::named_bar_sync(1, EPI_THREADS);
+            if (cg == 0 && live) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int g = 0; g < EPI_CGROUPS; ++g) acc += s_head[g * TILE_M + row];
+                p.sdf[gp] = acc + __ldg(p.bias[8]);
+            }
+            if (stash) {
+                // feature head: rows 1..256 of the output layer, no activation
+                for (int hf = 0; hf < 2; ++hf) {
+                    wait_acc(hf);
+                    const int col0 = 128 * hf + cg * 32;
+                    float v[32];
+                    acc_load32(tmem, row, col0, v);
+                    if (live) {
+                        const float* __restrict__ bias = p.bias[8] + 1;
+                        float* __restrict__ fr = p.feat + gp * p.ld_feat + col0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            st4(fr + j, make_float4(v[j] + __ldg(bias + col0 + j), v[j + 1] + __ldg(bias + col0 + j + 1),
+                                                    v[j + 2] + __ldg(bias + col0 + j + 2), v[j + 3] + __ldg(bias + col0 + j + 3)));
+                    }
+                }
+            }
+            tc::tc_fence_before_sync();       // the accumulator reads above precede the next tile's MMAs (ordered by its a_ready)
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// normal sweep: D_7 = s'(h_7) W_out[0]; D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1
+// ------------------------------------------------------------------------------------------------------------------
+struct HandNsweepParams {
+    int64_t n;
+    uint8_t* D16[8];
+    float* D4;               // [np, 256] fp32 rows (operand of the feature-side contraction)
+    float* D0;
+    const uint8_t* chain;
+    const float* w_out0;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_constant__ SwProgram prog,
+                     const __grid_constant__ SwInputs inputs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ SwBarriers bar;
+    uint8_t* smem = sw_setup(smem_raw, &bar);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+    } else if (warp == 2 + EPI_WARPS) {
+        if (lane == 0) sw_in_producer(inputs, smem, &bar, n_my_tiles);
+    } else {
+        const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0, in_par[2] = {0u, 0u};
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            const size_t tb = (size_t)tile * T16_TILE_BYTES;
+            // 16 columns [c, c + 16) of D_lyr -> fp16 hi / lo halves of the next A operand, bf16 chunks of D16, fp32 rows
+            auto emit16 = [&](int lyr, int c, const float* d) {
+                if (lyr > 0) {
+                    uint32_t hi8[8], lo8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) split2_lo16(d[2 * i], d[2 * i + 1], hi8[i], lo8[i]);
+                    sw_st16(tmem, lane_base, SW_A0, c, hi8);
+                    sw_st16(tmem, lane_base, SW_A1, c, lo8);
+                }
+                uint4 q0, q1;
+                q0.x = pack_bf16x2(d[0], d[1]); q0.y = pack_bf16x2(d[2], d[3]); q0.z = pack_bf16x2(d[4], d[5]); q0.w = pack_bf16x2(d[6], d[7]);
+                q1.x = pack_bf16x2(d[8], d[9]); q1.y = pack_bf16x2(d[10], d[11]); q1.z = pack_bf16x2(d[12], d[13]); q1.w = pack_bf16x2(d[14], d[15]);
+                stg16(p.D16[lyr] + tb + t16_off(row, c >> 3), q0);
+                stg16(p.D16[lyr] + tb + t16_off(row, (c >> 3) + 1), q1);
+                if (lyr == 4 || lyr == 0) {
+                    float* __restrict__ o = (lyr == 4 ? p.D4 : p.D0) + gp * 256 + c;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) st4(o + j, make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]));
+                }
+            };
+            auto load_sp16 = [&](int hf, int c, float* sp) {       // s' = 1 - (em_hi + em_lo) of 16 columns, from the input slot
+                const uint4 a = sw_in_ld(smem, hf, 0, row, c), b = sw_in_ld(smem, hf, 0, row, c + 8);
+                const uint4 al = sw_in_ld(smem, hf, 1, row, c), bl = sw_in_ld(smem, hf, 1, row, c + 8);
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                const uint32_t wl[8] = {al.x, al.y, al.z, al.w, bl.x, bl.y, bl.z, bl.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 f = f16x2_unpack(w[i]), fl = f16x2_unpack(wl[i]);
+                    sp[2 * i] = 1.0f - (f.x + fl.x);
+                    sp[2 * i + 1] = 1.0f - (f.y + fl.y);
+                }
+            };
+            // ---- seed: D_7 = s'(h_7) * W_out[0] (the previous tile's MMAs are complete: A may be written) --------------------
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                sw_in_wait(&bar, hf, in_par);
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    const int c = 128 * hf + cg * 32 + 16 * sub;
+                    float sp[16], d[16];
+                    load_sp16(hf, c, sp);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + c + j));
+                        d[j] = sp[j] * w.x; d[j + 1] = sp[j + 1] * w.y; d[j + 2] = sp[j + 2] * w.z; d[j + 3] = sp[j + 3] * w.w;
+                    }
+                    if (!live) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) d[j] = 0.0f;
+                    }
+                    emit16(7, c, d);
+                }
+                sw_in_release(&bar, hf);
+            }
+            sw_publish(&bar);
+            for (int l = 7; l >= 1; --l) {
+                sw_wait_acc(&bar, acc_par);
+                // four 16-column sub-blocks; the accumulator load of the next one is in flight while this one is processed
+                float accv[2][16];
+                sw_ld16_nowait(tmem, lane_base, cg * 32, accv[0]);
+#pragma unroll
+                for (int sb = 0; sb < 4; ++sb) {
+                    const int hf = sb >> 1;
+                    const int c = 128 * hf + cg * 32 + 16 * (sb & 1);
+                    if ((sb & 1) == 0) sw_in_wait(&bar, hf, in_par);
+                    float sp[16];
+                    load_sp16(hf, c, sp);
+                    tc::tmem_ld_wait();
+                    if (sb < 3) sw_ld16_nowait(tmem, lane_base, 128 * ((sb + 1) >> 1) + cg * 32 + 16 * ((sb + 1) & 1), accv[(sb + 1) & 1]);
+                    float* g = accv[sb & 1];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) g[j] = live ? sp[j] * g[j] : 0.0f;
+                    emit16(l - 1, c, g);
+                    if (sb & 1) sw_in_release(&bar, hf);
+                }
+                if (l > 1) sw_publish(&bar);      // one arrival per MMA step: D_0 feeds none
+            }
+        }
+    }
+    sw_teardown(&bar);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// second-order backward: tangent sweep + reverse sweep over layers 0..8 (the 1386-wide ends outside)
+// ------------------------------------------------------------------------------------------------------------------
+struct HandBwdParams {
+    int64_t n;
+    const float* Q0;         // [np, 256] fp32 rows: tF W_0^T
+    const float* QF4;        // [np, 256] fp32 rows: tF W_4[:, 256:]^T
+    const float* d_sdf;      // may be NULL
+    const float* d_feat;     // may be NULL
+    int64_t ld_dfeat;
+    uint8_t* X16[8];
+    float* DZ4;              // [np, 256] fp32 rows (operands of the feature-side contraction)
+    float* DZ0;
+    const uint8_t* chain;
+    const float* w_out0;
+    int n_tiles;
+};
+
+__global__ void __launch_bounds__(SW_THREADS, 1)
+hand_bwd16_kernel(const __grid_constant__ HandBwdParams p, const __grid_constant__ SwProgram prog,
+                  const __grid_constant__ SwInputs inputs) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ SwBarriers bar;
+    uint8_t* smem = sw_setup(smem_raw, &bar);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    if (warp == 0) {
+        if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
+    } else if (warp == 1) {
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+    } else if (warp == 2 + EPI_WARPS) {
+        if (lane == 0) sw_in_producer(inputs, smem, &bar, n_my_tiles);
+    } else {
+        const int row = (warp & 3) * 32 + lane, cg = (warp - 2) >> 2;
+        const uint32_t lane_base = (uint32_t)(row & ~31) << 16;
+        const uint32_t tmem = bar.tmem_base;
+        uint32_t acc_par = 0, in_par[2] = {0u, 0u};
+        for (int t = 0; t < n_my_tiles; ++t) {
+            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t gp = tile * TILE_M + row;
+            const bool live = gp < p.n;
+            const size_t tb = (size_t)tile * T16_TILE_BYTES;
+            const float gs = (live && p.d_sdf) ? p.d_sdf[gp] : 0.0f;
+            auto pack16 = [&](const float* v, uint32_t* w) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            };
+            auto store16 = [&](uint8_t* arr, int c, const uint32_t* w) {
+                stg16(arr + tb + t16_off(row, c >> 3), make_uint4(w[0], w[1], w[2], w[3]));
+                stg16(arr + tb + t16_off(row, (c >> 3) + 1), make_uint4(w[4], w[5], w[6], w[7]));
+            };
+            // 16 values -> bf16 hi / lo halves of the next A operand (tensor memory)
+            auto emit_a16 = [&](int c, const float* v) {
+                uint32_t hi8[8], lo8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) split2(v[2 * i], v[2 * i + 1], hi8[i], lo8[i]);
+                sw_st16(tmem, lane_base, SW_A0, c, hi8);
+                sw_st16(tmem, lane_base, SW_A1, c, lo8);
+            };
+            auto unpack_bf16 = [&](const uint4& a, const uint4& b, float* v) {
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { v[2 * i] = bf16_lo(w[i]); v[2 * i + 1] = bf16_hi(w[i]); }
+            };
+            auto unpack_f16 = [&](const uint4& a, const uint4& b, float* v) {
+                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float2 f = f16x2_unpack(w[i]);
+                    v[2 * i] = f.x;
+                    v[2 * i + 1] = f.y;
+                }
+            };
+            auto add_row16 = [&](const float* __restrict__ src, int c, float* q) {
+                if (!live) return;
+                const float* __restrict__ r = src + gp * 256 + c;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 a = ld4(r + j);
+                    q[j] += a.x; q[j + 1] += a.y; q[j + 2] += a.z; q[j + 3] += a.w;
+                }
+            };
+            // ---- tangent sweep: q_l = W_l u_{l-1} (q_0, and the feature part of q_4, from the contractions that ran before this
+            //      kernel); u_l = s'(h_l) q_l; X_l = 100 (1 - s') D_l q_l -----------------------------------------------------
+            for (int l = 0; l < 8; ++l) {
+                if (l > 0) sw_wait_acc(&bar, acc_par);
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                    sw_in_wait(&bar, hf, in_par);
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int c = 128 * hf + cg * 32 + 16 * sub;
+                        float q[16], em[16], d[16];
+                        unpack_f16(sw_in_ld(smem, hf, 0, row, c), sw_in_ld(smem, hf, 0, row, c + 8), em);
+                        unpack_bf16(sw_in_ld(smem, hf, 1, row, c), sw_in_ld(smem, hf, 1, row, c + 8), d);
+                        if (l > 0) {
+                            sw_ld16(tmem, lane_base, c, q);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) q[j] = 0.0f;
+                            add_row16(p.Q0, c, q);
+                        }
+                        if (l == 4) add_row16(p.QF4, c, q);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float u = (1.0f - em[j]) * q[j];
+                            d[j] = 100.0f * em[j] * d[j] * q[j];
+                            q[j] = u;
+                        }
+                        if (l < 7) emit_a16(c, q);
+                        uint32_t w[8];
+                        pack16(d, w);
+                        store16(p.X16[l], c, w);
+                    }
+                    sw_in_release(&bar, hf);
+                }
+                if (l == 7) {
+                    // A operand of the output layer's reverse step: the point's row of d_feat
+#pragma unroll 1
+                    for (int sb = 0; sb < 4; ++sb) {
+                        const int c = 128 * (sb >> 1) + cg * 32 + 16 * (sb & 1);
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live && p.d_feat) a = ld4(p.d_feat + gp * p.ld_dfeat + c + j);
+                            v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
+                        }
+                        emit_a16(c, v);
+                    }
+                }
+                sw_publish(&bar);
+            }
+            // ---- reverse sweep: dz_{l-1} = s'(h_{l-1}) (dz_l W_l) + X_{l-1}, l = 8..1 -------------------------------------------
+            for (int l = 8; l >= 1; --l) {
+                // X_{l-1} was written by THIS thread during the tangent sweep: plain loads, issued before the wait for the MMAs
+                const uint8_t* xp = p.X16[l - 1] + tb;
+                uint4 xq[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xq[i] = ldg16(xp + t16_off(row, ((128 * (i >> 2) + cg * 32) >> 3) + (i & 3)));
+                sw_wait_acc(&bar, acc_par);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    sw_in_wait(&bar, hf, in_par);
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int c = 128 * hf + cg * 32 + 16 * sub;
+                        float da[16], em[16], x[16];
+                        unpack_f16(sw_in_ld(smem, hf, 0, row, c), sw_in_ld(smem, hf, 0, row, c + 8), em);
+                        unpack_bf16(xq[4 * hf + 2 * sub], xq[4 * hf + 2 * sub + 1], x);
+                        sw_ld16(tmem, lane_base, c, da);
+                        if (l == 8) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) {
+                                const float4 w = __ldg(reinterpret_cast<const float4*>(p.w_out0 + c + j));
+                                da[j] += gs * w.x; da[j + 1] += gs * w.y; da[j + 2] += gs * w.z; da[j + 3] += gs * w.w;
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) da[j] = live ? fmaf(1.0f - em[j], da[j], x[j]) : 0.0f;
+                        if (l > 1) emit_a16(c, da);
+                        if (l == 5 || l == 1) {
+                            float* __restrict__ o = (l == 5 ? p.DZ4 : p.DZ0) + gp * 256 + c;
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) st4(o + j, make_float4(da[j], da[j + 1], da[j + 2], da[j + 3]));
+                        }
+                    }
+                    sw_in_release(&bar, hf);
+                }
+                if (l > 1) sw_publish(&bar);      // one arrival per MMA step: dz_0 feeds none
+            }
+        }
+    }
+    sw_teardown(&bar);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+// stash (floats per padded point): HROW 1644 | FB 1388 | RA 256 | RB 256 | EM[8] | EML[8] | D16[8] (128 floats each)
+//   RA: H0 during the trunk, then D0; RB: ZF4 during the trunk, then D4
+int64_t hand16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 512 + 24 * 128); }
+// backward workspace: AU4 1644 | DF 1388 | Q0 | QF4 | DZ0 | DZ4 (256 each) | X16[8]
+int64_t hand16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 1024 + 8 * 128); }
+
+static void sw_layer(SwProgram& prog, int& k, uint32_t off, int n_mma, int kblocks, int f16) {
+    SwStep& st = prog.step[k++];
+    st.b_off = off;
+    st.n_mma = (uint16_t)n_mma;
+    st.kblocks = (uint8_t)kblocks;
+    st.f16 = (uint8_t)f16;
+    st.acc_in = 0;
+}
+
+int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const float* H0, const float* ZF4, float* sdf,
+                        float* feat, int64_t ld_feat, uint8_t* const* EM, uint8_t* const* EML, cudaStream_t s) {
+    const HandLayout L = hand_layout();
+    const int n_tiles = (int)ceil_div(n, TILE_M);
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hand_trunk16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
+        configured = true;
+    }
+    HandTrunkParams p;
+    p.n = n; p.H0 = H0; p.ZF4 = ZF4; p.sdf = sdf; p.feat = feat; p.ld_feat = ld_feat;
+    for (int l = 0; l < 8; ++l) { p.EM[l] = EM ? EM[l] : nullptr; p.EML[l] = EML ? EML[l] : nullptr; }
+    p.chain = ops;
+    for (int l = 0; l < 9; ++l) p.bias[l] = m->b[l];
+    p.w_out0 = m->W[8];
+    p.n_tiles = n_tiles;
+    Program prog = {};
+    int k = 0;
+    for (int l = 1; l <= (feat ? 8 : 7); ++l)
+        for (int h = 0; h < 2; ++h) {
+            Step& st = prog.step[k++];
+            st.b_off = L.nth_off[l][h];
+            st.n_mma = 128;
+            st.kblocks = 4;
+            st.f16 = 1;
+            st.no_wait = (uint8_t)h;
+            st.acc_col = (uint16_t)(128 * h);
+        }
+    prog.n_steps = k;
+    hand_trunk16_kernel<<<std::min(n_tiles, sm_count()), THREADS, HT_SMEM_BYTES, s>>>(p, prog);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* EML,
+                         uint8_t* const* D16, float* D4, float* D0, cudaStream_t s) {
+    const HandLayout L = hand_layout();
+    const int n_tiles = (int)ceil_div(n, TILE_M);
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hand_nsweep16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+        configured = true;
+    }
+    HandNsweepParams p;
+    p.n = n; p.D4 = D4; p.D0 = D0;
+    for (int l = 0; l < 8; ++l) p.D16[l] = D16[l];
+    p.chain = ops;
+    p.w_out0 = m->W[8];
+    p.n_tiles = n_tiles;
+    SwInputs in = {};
+    int ne = 0;
+    for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{EM[7], EML[7]};                  // seed
+    for (int l = 7; l >= 1; --l)
+        for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{EM[l - 1], EML[l - 1]};
+    in.n_events = ne;
+    SwProgram prog = {};
+    int k = 0;
+    for (int l = 7; l >= 1; --l) sw_layer(prog, k, L.nn16_off[l], 256, 4, 1);               // d @ W_l
+    prog.n_steps = k;
+    hand_nsweep16_kernel<<<std::min(n_tiles, sm_count()), SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* D16,
+                      uint8_t* const* X16, const float* Q0, const float* QF4, const float* d_sdf, const float* d_feat,
+                      int64_t ld_dfeat, float* DZ4, float* DZ0, cudaStream_t s) {
+    HN_REQUIRE(!d_feat || (ld_dfeat % 4 == 0 && aligned16(d_feat)), "d_feat must be 16-byte aligned with ld %% 4 == 0");
+    const HandLayout L = hand_layout();
+    const int n_tiles = (int)ceil_div(n, TILE_M);
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hand_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SW_SMEM_BYTES));
+        configured = true;
+    }
+    HandBwdParams p;
+    p.n = n; p.Q0 = Q0; p.QF4 = QF4; p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.DZ4 = DZ4; p.DZ0 = DZ0;
+    for (int l = 0; l < 8; ++l) p.X16[l] = X16[l];
+    p.chain = ops;
+    p.w_out0 = m->W[8];
+    p.n_tiles = n_tiles;
+    SwInputs in = {};
+    int ne = 0;
+    for (int l = 0; l < 8; ++l)
+        for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{EM[l], D16[l]};              // tangent sweep
+    for (int l = 8; l >= 1; --l)
+        for (int hf = 0; hf < 2; ++hf) in.ev[ne++] = SwInEvent{EM[l - 1], nullptr};         // reverse sweep
+    in.n_events = ne;
+    SwProgram prog = {};
+    int k = 0;
+    for (int l = 1; l <= 7; ++l) sw_layer(prog, k, L.nt_off[l], 256, 4, 0);                 // tangent: u @ W_l^T
+    for (int l = 8; l >= 1; --l) sw_layer(prog, k, L.nn_off[l], 256, 4, 0);                 // reverse: dz @ W_l
+    prog.n_steps = k;
+    hand_bwd16_kernel<<<std::min(n_tiles, sm_count()), SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+
+int hand16_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s) {
+    const HandLayout L = hand_layout();
+    pack_batch_begin();
+    for (int l = 1; l <= 8; ++l) {
+        const int row0 = l == 8 ? 1 : 0;
+        for (int h = 0; h < 2; ++h)
+            HN_PROPAGATE(launch_pack_b(m->W[l], m->ld[l], pack_map(row0 + 128 * h, 0), 128, 256, 128, 4, dst + L.nth_off[l][h], s, true));
+        if (l <= 7) {
+            HN_PROPAGATE(launch_pack_b(m->WT[l], m->ldT[l], pack_map(0, 0), 256, 256, 256, 4, dst + L.nn16_off[l], s, true));
+            HN_PROPAGATE(launch_pack_b(m->W[l], m->ld[l], pack_map(0, 0), 256, 256, 256, 4, dst + L.nt_off[l], s));
+        }
+        HN_PROPAGATE(launch_pack_b(m->WT[l], m->ldT[l], pack_map(0, row0), 256, 256, 256, 4, dst + L.nn_off[l], s));
+    }
+    return pack_batch_flush(s);
+}
+
+}  // namespace chain
+}  // namespace hn

@@ -3,12 +3,27 @@
 // and the hand colour field (utils/fields.py:179-240).  Same layer-by-layer structure as fields_obj.cu:
 // the 1386-wide HALO feature is produced once per point into the skip-input row [h3 (256) | feature
 // (1386) | pad 2] (ld 1644), which serves as the input of layer 0 and of the skip layer 4.
+#include <algorithm>
+
 #include "common.cuh"
 #include "fields_common.cuh"
 #include "gemm_dispatch.cuh"
 #include "halo.cuh"
+#include "chain_hand_layout.cuh"
+#include "gemm_bx3.cuh"
 
 namespace hn {
+
+namespace chain {      // chain16_hand.cu
+int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const float* H0, const float* ZF4, float* sdf,
+                        float* feat, int64_t ld_feat, uint8_t* const* EM, uint8_t* const* EML, cudaStream_t s);
+int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* EML,
+                         uint8_t* const* D16, float* D4, float* D0, cudaStream_t s);
+int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* D16,
+                      uint8_t* const* X16, const float* Q0, const float* QF4, const float* d_sdf, const float* d_feat,
+                      int64_t ld_dfeat, float* DZ4, float* DZ0, cudaStream_t s);
+int hand16_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s);
+}  // namespace chain
 
 constexpr int HROW_LD = 1644;        // [h3 256 | feature 1386 | pad 2]
 constexpr int HFEAT_OFF = 256;
@@ -300,20 +315,102 @@ static int hand_trunk_fwd(const hn_mlp_t* m, const float* pts, const float* bt_i
     return HN_OK;
 }
 
+// ---- HN_TC_MIXED16 (chain16_hand.cu): stash / workspace views and the operands appended to the bx3 pack -------------------
+struct Hand16Stash {
+    float *HROW, *FB, *RA, *RB;      // RA: H0, then D0;  RB: ZF4, then D4
+    uint8_t *EM[8], *EML[8], *D16[8];
+    Hand16Stash(float* base, int64_t n) {
+        const int64_t np = round_up(n, 128);
+        float* p = base;
+        HROW = p; p += np * HROW_LD;
+        FB = p; p += np * HFB_LD;
+        RA = p; p += np * 256;
+        RB = p; p += np * 256;
+        uint8_t* b = reinterpret_cast<uint8_t*>(p);
+        for (int l = 0; l < 8; ++l) { EM[l] = b; b += np * 512; }
+        for (int l = 0; l < 8; ++l) { EML[l] = b; b += np * 512; }
+        for (int l = 0; l < 8; ++l) { D16[l] = b; b += np * 512; }
+    }
+};
+static const uint8_t* hand16_ops(const hn_mlp_t* m) {
+    const int64_t off = round_up(bx3_layout(m).total, 1024);
+    if (!m->chain || m->chain_bytes < off + (int64_t)chain::hand_layout().total) return nullptr;
+    return reinterpret_cast<const uint8_t*>(m->chain) + off;
+}
+static bool use_hand16(const hn_mlp_t* m, int precision) { return precision == HN_TC_MIXED16 && hand16_ops(m) != nullptr; }
+
+// feature-side contractions into the chain: H0 = softplus(F W_0^T + b_0) and ZF4 = F W_4[:, 256:]^T (or, on the tangent
+// features, Q0 and QF4 without bias / activation)
+static int hand16_feature_in(const hn_mlp_t* m, const float* F, int64_t n, float* out0, float* out4, bool activate,
+                             cudaStream_t s) {
+    GemmArgs g;
+    g.A = F; g.lda = HROW_LD;
+    set_w(g, m, 0);
+    g.M = (int)n; g.N = 256; g.K = HALO_DIM;
+    g.C = out0; g.ldc = 256;
+    if (activate) {
+        g.bias = m->b[0];
+        HN_PROPAGATE((gemm_nt<EPI_BIAS_SOFTPLUS>(g, s, HN_TC_BF16X3, ROLE_VALUE)));
+    } else {
+        HN_PROPAGATE((gemm_nt<EPI_STORE>(g, s, HN_TC_BF16X3, ROLE_VALUE)));
+    }
+    GemmArgs f;
+    f.A = F; f.lda = HROW_LD;
+    set_w(f, m, 4, HFEAT_OFF);
+    f.M = (int)n; f.N = 256; f.K = HALO_DIM;
+    f.C = out4; f.ldc = 256;
+    return gemm_nt<EPI_STORE>(f, s, HN_TC_BF16X3, ROLE_VALUE);
+}
+// feature-side contraction out of the chain: OUT[n, 1386] = (aux ?) + R4 W_4[:, 256:] + R0 W_0
+static int hand16_feature_out(const hn_mlp_t* m, const float* R4, const float* R0, int64_t n, const float* aux, int64_t ld_aux,
+                              float* OUT, cudaStream_t s) {
+    GemmArgs f;
+    f.A = R4; f.lda = 256;
+    set_w(f, m, 4, HFEAT_OFF);
+    f.M = (int)n; f.N = HALO_DIM; f.K = 256;
+    f.C = OUT; f.ldc = HFB_LD;
+    if (aux) {
+        f.aux1 = aux; f.ldaux1 = ld_aux;
+        HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(f, s, HN_TC_BF16X3, ROLE_VALUE)));
+    } else {
+        HN_PROPAGATE((gemm_nn<EPI_STORE>(f, s, HN_TC_BF16X3, ROLE_VALUE)));
+    }
+    GemmArgs g;
+    g.A = R0; g.lda = 256;
+    set_w(g, m, 0);
+    g.M = (int)n; g.N = HALO_DIM; g.K = 256;
+    g.C = OUT; g.ldc = HFB_LD; g.aux1 = OUT; g.ldaux1 = HFB_LD;
+    return gemm_nn<EPI_ADD_AUX>(g, s, HN_TC_BF16X3, ROLE_VALUE);
+}
+
 }  // namespace hn
 
 using namespace hn;
 
 extern "C" {
 
-int64_t hn_sdf_hand_stash_floats(int64_t n) { return n * HandSdfStash::kFloatsPerPoint; }
+int64_t hn_sdf_hand_stash_floats(int64_t n) { return std::max(n * HandSdfStash::kFloatsPerPoint, chain::hand16_stash_floats(n)); }
+
+// The hand SDF net's packed operands: the per-layer bf16 hi/lo tiles of hn_mlp_bx3_pack, followed (1 KB aligned) by the
+// chain operands of its 256 x 256 layers (HN_TC_MIXED16, chain16_hand.cu)
+int64_t hn_sdf_hand_chain_bytes(const hn_mlp_t* m) {
+    if (!m || m->n_layers != 9) return 0;
+    return round_up(bx3_layout(m).total, 1024) + (int64_t)chain::hand_layout().total;
+}
+int hn_sdf_hand_chain_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_stream_t stream) {
+    HN_PROPAGATE(check_hand_sdf_mlp(m));
+    HN_REQUIRE(buf && bytes >= hn_sdf_hand_chain_bytes(m) && aligned16(buf), "hn_sdf_hand_chain_pack: buffer too small or misaligned");
+    HN_PROPAGATE(hn_mlp_bx3_pack(m, buf, bytes, stream));
+    for (int l = 1; l < 9; ++l) HN_REQUIRE(m->WT[l], "hn_sdf_hand_chain_pack: layer %d has no transposed copy", l);
+    return chain::hand16_pack(m, reinterpret_cast<uint8_t*>(buf) + round_up(bx3_layout(m).total, 1024), (cudaStream_t)stream);
+}
 
 int64_t hn_sdf_hand_ws_floats(int64_t n, int kind) {
     switch (kind) {
-        case HN_WS_SDF_ONLY: return n * (HROW_LD + 2 * 256);
+        case HN_WS_SDF_ONLY: return round_up(n, 128) * (HROW_LD + 2 * 256);
         case HN_WS_FWD: return 4;
         // AU4 [n,1644], U ping-pong 2x256, DZ8 260, DZ ping-pong 2x256, DF [n,1388]
-        case HN_WS_BWD: return n * (HROW_LD + 2 * 256 + 260 + 2 * 256 + HFB_LD);
+        case HN_WS_BWD: return std::max(n * (HROW_LD + 2 * 256 + 260 + 2 * 256 + HFB_LD), chain::hand16_bwd_ws_floats(n));
         default: return -1;
     }
 }
@@ -322,6 +419,7 @@ int hn_sdf_hand_sdf(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
                     int64_t pts_per_frame, float* sdf, float* ws, int64_t ws_floats, int precision,
                     hn_stream_t stream) {
     HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    const bool m16 = use_hand16(mlp, precision);
     precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_sdf: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
@@ -329,6 +427,18 @@ int hn_sdf_hand_sdf(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
     HN_REQUIRE(pts && bt_inv && T_pose && sdf && ws && ws_floats >= hn_sdf_hand_ws_floats(n, HN_WS_SDF_ONLY) &&
                    aligned16(ws), "hn_sdf_hand_sdf: null pointer or workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
+    if (m16) {
+        const int64_t np = round_up(n, 128);
+        float* HROW = ws;
+        float* H0 = HROW + np * HROW_LD;
+        float* ZF4 = H0 + np * 256;
+        halo_feature_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, n, pts_per_frame,
+                                                                               HROW + HFEAT_OFF, HROW_LD);
+        count_launch();
+        HN_CHECK_LAUNCH();
+        HN_PROPAGATE(hand16_feature_in(mlp, HROW + HFEAT_OFF, n, H0, ZF4, true, s));
+        return chain::launch_hand16_trunk(mlp, hand16_ops(mlp), n, H0, ZF4, sdf, nullptr, 0, nullptr, nullptr, s);
+    }
     float* HROW = ws;
     float* P0 = HROW + n * HROW_LD;
     float* P1 = P0 + n * 256;
@@ -345,6 +455,7 @@ int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
                     float* xyz_feature, int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
                     hn_stream_t stream) {
     HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    const bool m16 = use_hand16(mlp, precision);
     precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
@@ -353,6 +464,30 @@ int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
     HN_REQUIRE(stash_floats >= hn_sdf_hand_stash_floats(n) && aligned16(stash), "stash too small or misaligned");
     HN_REQUIRE(ld_feat >= 256 && ld_feat % 4 == 0 && aligned16(feat), "feat must be 16B aligned with ld%%4==0");
     cudaStream_t s = (cudaStream_t)stream;
+    if (m16) {
+        // HN_TC_MIXED16: the 256 x 256 layers as tile-chain kernels (chain16_hand.cu), the 1386-wide ends per layer
+        Hand16Stash h(stash, n);
+        const uint8_t* ops = hand16_ops(mlp);
+        halo_feature_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, n, pts_per_frame,
+                                                                               h.HROW + HFEAT_OFF, HROW_LD);
+        count_launch();
+        HN_CHECK_LAUNCH();
+        HN_PROPAGATE(hand16_feature_in(mlp, h.HROW + HFEAT_OFF, n, h.RA, h.RB, true, s));
+        HN_PROPAGATE(chain::launch_hand16_trunk(mlp, ops, n, h.RA, h.RB, sdf, feat, ld_feat, h.EM, h.EML, s));
+        if (xyz_feature) {
+            copy_rows_kernel<<<nblocks(n * HALO_DIM, 256), 256, 0, s>>>(h.HROW + HFEAT_OFF, HROW_LD, n, HALO_DIM, xyz_feature,
+                                                                        ld_xyz);
+            count_launch();
+            HN_CHECK_LAUNCH();
+        }
+        HN_PROPAGATE(chain::launch_hand16_nsweep(mlp, ops, n, h.EM, h.EML, h.D16, h.RB, h.RA, s));
+        HN_PROPAGATE(hand16_feature_out(mlp, h.RB, h.RA, n, nullptr, 0, h.FB, s));
+        halo_normal_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, h.FB, HFB_LD, n,
+                                                                              pts_per_frame, normal);
+        count_launch();
+        HN_CHECK_LAUNCH();
+        return HN_OK;
+    }
     HandSdfStash st(stash, n);
     HN_PROPAGATE(hand_trunk_fwd(mlp, pts, bt_inv, T_pose, n, pts_per_frame, st.HROW, st.H, s, precision));
     hand_sdf_head_kernel<<<nblocks(n * 32, 256), 256, 0, s>>>(st.H[7], mlp->W[8], mlp->b[8], n, sdf);
@@ -414,6 +549,7 @@ int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
                     float* d_T_pose, const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision,
                     hn_stream_t stream) {
     HN_PROPAGATE(check_hand_sdf_mlp(mlp));
+    const bool m16 = use_hand16(mlp, precision);
     precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_sdf_hand_bwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31) && pts_per_frame > 0, "bad sizes");
@@ -421,6 +557,37 @@ int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
     HN_REQUIRE(pts && bt_inv && T_pose && stash && d_normal && ws, "hn_sdf_hand_bwd: null pointer");
     HN_REQUIRE(ws_floats >= hn_sdf_hand_ws_floats(n, HN_WS_BWD) && aligned16(ws), "workspace too small or misaligned");
     cudaStream_t s = (cudaStream_t)stream;
+    if (m16) {
+        HN_REQUIRE(!grad, "hn_sdf_hand_bwd: HN_TC_MIXED16 computes no weight gradients for the hand net (the forward of a call "
+                          "that needs them must be made with HN_TC_BF16X3)");
+        Hand16Stash h(stash, n);
+        const uint8_t* ops = hand16_ops(mlp);
+        const int64_t np = round_up(n, 128);
+        float* AU4 = ws;                                   // [np, 1644]: tangent feature rows at + 256
+        float* DF = AU4 + np * HROW_LD;                    // [np, 1388]
+        float* Q0 = DF + np * HFB_LD;                      // [np, 256]: tF W_0^T
+        float* QF4 = Q0 + np * 256;                        // [np, 256]: tF W_4[:, 256:]^T
+        float* DZ0 = QF4 + np * 256;                       // [np, 256]
+        float* DZ4 = DZ0 + np * 256;
+        uint8_t* X16[8];
+        uint8_t* b = reinterpret_cast<uint8_t*>(DZ4 + np * 256);
+        for (int l = 0; l < 8; ++l) { X16[l] = b; b += np * 512; }
+        halo_tangent_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, d_normal, n, pts_per_frame,
+                                                                               AU4 + HFEAT_OFF, HROW_LD);
+        count_launch();
+        HN_CHECK_LAUNCH();
+        HN_PROPAGATE(hand16_feature_in(mlp, AU4 + HFEAT_OFF, n, Q0, QF4, false, s));
+        HN_PROPAGATE(chain::launch_hand16_bwd(mlp, ops, n, h.EM, h.D16, X16, Q0, QF4, d_sdf, d_feat, ld_dfeat, DZ4, DZ0, s));
+        if (d_pts || d_bt_inv || d_T_pose) {
+            HN_PROPAGATE(hand16_feature_out(mlp, DZ4, DZ0, n, d_xyz_feature, ld_dxyz, DF, s));
+            const int64_t per_warp = max((int64_t)1, ceil_div(n, (int64_t)sm_count() * 16 * HALO_WARPS));
+            halo_bwd_kernel<<<nblocks(ceil_div(n, per_warp), HALO_WARPS), HALO_WARPS * 32, 0, s>>>(
+                pts, bt_inv, T_pose, DF, HFB_LD, h.FB, HFB_LD, d_normal, n, pts_per_frame, per_warp, d_pts, d_bt_inv, d_T_pose);
+            count_launch();
+            HN_CHECK_LAUNCH();
+        }
+        return HN_OK;
+    }
     HandSdfStash st(stash, n);
     float* AU4 = ws;                                  // [n,1644] = [u3 | tangent feature | pad]
     float* U[2] = {AU4 + n * HROW_LD, AU4 + n * HROW_LD + n * 256};

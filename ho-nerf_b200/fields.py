@@ -89,6 +89,7 @@ class _PackedNet(nn.Module):
 
     _post_scales = None
     _gaps = None
+    _chain_kind = "bx3"
 
     def packed(self):
         if getattr(self, "_packed", None) is None:
@@ -96,7 +97,7 @@ class _PackedNet(nn.Module):
             layers = [(getattr(self, "lin%d" % l).weight_g, getattr(self, "lin%d" % l).weight_v,
                        getattr(self, "lin%d" % l).bias) for l in range(n)]
             scales = self._post_scales or [1.0] * n
-            self._packed = ops.PackedMLP(layers, scales, self._gaps, chain_kind="bx3")
+            self._packed = ops.PackedMLP(layers, scales, self._gaps, chain_kind=self._chain_kind)
         return self._packed
 
     def _apply(self, fn, *a, **k):      # .to()/.cuda()/.float() replace the parameter tensors
@@ -109,6 +110,7 @@ class SDFNetwork(_PackedNet):
     -> 256 x4 -> 257, softplus(beta=100), weight norm.  ``forward`` returns (out [N,257], xyz_feature
     [N,1386], None, None): the reference's extra ``r, h`` are not consumed by any caller
     (RenderingNetwork ignores ``h``, SURVEY D-5)."""
+    _chain_kind = "sdf_hand"
 
     def __init__(self, barf_encoding, traindata_num, data_type, d_in, d_out, d_hidden, n_layers, skip_in=(4,),
                  v_multires=10, r_multires=4, bias=0.5, scale=1, geometric_init=True, weight_norm=True,

@@ -125,13 +125,15 @@ class PackedMLP:
             st.b[l] = bd.data_ptr()
         # every layer's g * v / ||v|| (and its transposed copy) in one launch
         check(lib.hn_wn_pack_batch(jobs, len(self.layers), _stream(self.W)), "hn_wn_pack_batch")
-        if self.chain_kind == "bx3":
-            # no fused chain kernel for this net (hand field): pre-packed bf16 hi/lo operands of every layer for the
-            # per-layer HN_TC_BF16X3 contractions
-            nbytes = int(lib.hn_mlp_bx3_bytes(ctypes.byref(st)))
+        if self.chain_kind in ("bx3", "sdf_hand"):
+            # pre-packed bf16 hi/lo operands of every layer for the per-layer HN_TC_BF16X3 contractions (hand colour net), plus --
+            # for the hand SDF net -- the tile-chain operands of its 256 x 256 layers (HN_TC_MIXED16)
+            size_fn, pack_fn = ((lib.hn_mlp_bx3_bytes, lib.hn_mlp_bx3_pack) if self.chain_kind == "bx3" else
+                                (lib.hn_sdf_hand_chain_bytes, lib.hn_sdf_hand_chain_pack))
+            nbytes = int(size_fn(ctypes.byref(st)))
             if self.chain is None or self.chain.device != dev or self.chain.numel() < nbytes:
                 self.chain = torch.empty(nbytes, device=dev, dtype=torch.uint8)
-            check(lib.hn_mlp_bx3_pack(ctypes.byref(st), _ptr(self.chain), nbytes, _stream(self.W)), "hn_mlp_bx3_pack")
+            check(pack_fn(ctypes.byref(st), _ptr(self.chain), nbytes, _stream(self.W)), "hn_%s_pack" % self.chain_kind)
             st.chain = self.chain.data_ptr()
             st.chain_bytes = nbytes
         elif self.chain_kind is not None:
@@ -477,6 +479,12 @@ class _SdfHandFn(torch.autograd.Function):
         pts_c, bt_c, T_c = _f32c(pts.detach()), _f32c(bt_inv.detach()), _f32c(T_pose.detach())
         _require_cuda(pts_c, "sdf_hand")
         pk = packed.get()
+        ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero tensor
+        ctx.params_need_grad = any(p.requires_grad for p in params)
+        if precision == _lib.HN_TC_MIXED16 and ctx.params_need_grad:
+            # the tile-chain kernels of the hand net keep a 16-bit stash and compute no weight gradients (pose fitting,
+            # rendering); a call whose backward trains the net stays on the per-layer contractions with their fp32 stash
+            precision = _lib.HN_TC_BF16X3
         n, dev = pts_c.shape[0], pts_c.device
         sdf = torch.empty(n, 1, device=dev)
         feat = torch.empty(n, 256, device=dev)
@@ -494,7 +502,6 @@ class _SdfHandFn(torch.autograd.Function):
         ctx.pkey = pk._key
         ctx.pts_c, ctx.bt_c, ctx.T_c = pts_c, bt_c, T_c
         ctx.need = (pts.requires_grad, bt_inv.requires_grad, T_pose.requires_grad)
-        ctx.params_need_grad = any(p.requires_grad for p in params)
         return sdf, feat, normal, xyz
 
     @staticmethod

@@ -136,6 +136,13 @@ HN_API int hn_wn_bwd_batch(const hn_wn_job_t* jobs, int n, hn_stream_t stream);
  * of the split-TF32 kernel.  hn_mlp_bx3_bytes: size of that buffer. */
 HN_API int64_t hn_mlp_bx3_bytes(const hn_mlp_t* m);
 HN_API int hn_mlp_bx3_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_stream_t stream);
+/* Hand SDF net (SDFNetwork, utils/fields.py:56-177): the per-layer operands of hn_mlp_bx3_pack followed by the tile-chain
+ * operands of its 256 x 256 layers.  With this buffer in mlp->chain, HN_TC_MIXED16 runs those layers of hn_sdf_hand_sdf /
+ * _fwd / _bwd as persistent chain kernels with the activations in tensor memory (csrc/chain16_hand.cu); that path keeps a
+ * 16-bit stash and computes NO weight gradients (hn_sdf_hand_bwd rejects grad != NULL): pose fitting and rendering.  A
+ * forward whose backward needs weight gradients is made with HN_TC_BF16X3. */
+HN_API int64_t hn_sdf_hand_chain_bytes(const hn_mlp_t* m);
+HN_API int hn_sdf_hand_chain_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_stream_t stream);
 
 /* Adam over one flat fp32 parameter buffer (torch.optim.Adam semantics; the reference builds one Adam over all
  * networks' parameters, exp_runner.py:83, and rewrites param_groups[i]['lr'] every iteration, exp_runner.py:258-268).

@@ -15,6 +15,8 @@ from gpu_util import hand_modules  # noqa: E402
 
 grad_w = os.environ.get("PROF_HAND_WEIGHTS", "0") == "1"
 sdf, col, dev, _, _ = hand_modules(requires_grad=grad_w)
+for q in col.parameters():
+    q.requires_grad_(False)
 bt0, T, J = synth.hand_pose()
 n = int(os.environ.get("PROF_HAND_POINTS", 98304))
 g = torch.Generator().manual_seed(1)
