@@ -2,12 +2,15 @@
 // the normal sweep, the tangent sweep and the reverse sweep as three persistent tile-chain kernels with the activations in
 // tensor memory (the machinery of chain16.cuh, built for the object field), three 16-bit MMAs per product.
 //
-// The two 1386-wide contractions on either side of the chain (HALO feature -> layer 0 / skip layer 4, and their transposes)
-// stay on the per-layer kernels (gemm_bx3.cuh); they meet the chain through fp32 row-major [points, 256] buffers:
+// The 1386-wide contractions INTO the chain (HALO feature -> layer 0 / skip layer 4) stay on the per-layer kernels
+// (gemm_bx3.cuh) and meet it through fp32 row-major [points, 256] buffers; the ones OUT of it (cotangents of the feature)
+// are extra steps of the sweeps: while D_4 (resp. D_0) is the A operand in tensor memory, six 256-column chunks of
+// W_4[:, 256:] (resp. W_0) stream through the weight ring and the epilogue writes (resp. adds to) FB, kept as column-major
+// [1388][128 points] fp32 tiles (coalesced for the epilogue and for the thread-per-point HALO kernels that consume it).
 //   hand_trunk16_kernel   in : H0 = softplus(F W_0^T + b_0), ZF4 = F W_4[:, 256:]^T       out: sdf, feature, EM / EML tiles
-//   hand_nsweep16_kernel  in : EM / EML                                                    out: D16 tiles, D4, D0 rows
+//   hand_nsweep16_kernel  in : EM / EML                                                    out: D16 tiles, FB tiles
 //   hand_bwd16_kernel     in : Q0 = tF W_0^T, QF4 = tF W_4[:, 256:]^T, EM, D16, d_sdf / d_feat
-//                                                                                          out: DZ4, DZ0 rows (X16 scratch)
+//                                                                                          out: DF tiles (X16 scratch)
 // Used when no weight gradient is asked for (pose fitting, rendering): the weight-gradient contractions of the hand net
 // stay on the per-layer path (fields_hand.cu), which keeps an fp32 stash.
 #include <algorithm>
@@ -267,14 +270,41 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
 // normal sweep: D_7 = s'(h_7) W_out[0]; D_{l-1} = s'(h_{l-1}) * (D_l W_l), l = 7..1
 // ------------------------------------------------------------------------------------------------------------------
 struct HandNsweepParams {
+    uint32_t* dbg;
     int64_t n;
     uint8_t* D16[8];
-    float* D4;               // [np, 256] fp32 rows (operand of the feature-side contraction)
-    float* D0;
+    float* FB;               // column-major tiles [tile][1388][128] fp32: D_4 W_4[:, 256:] + D_0 W_0
     const uint8_t* chain;
     const float* w_out0;
     int n_tiles;
 };
+
+// One feature-side chunk step: accumulator columns [0, n) -> out[256 ch + c][row] of this tile's column-major
+// [1388 columns][128 points] fp32 block (a warp's 32 rows of one column are one 128-byte line; the thread-per-point HALO
+// kernels of fields_hand.cu read it the same way), or added to what the same thread stored there before
+template <bool ADD>
+__device__ __forceinline__ void hand_f_chunk(uint32_t tmem, uint32_t lane_base, int row, int cg, int ch, float* __restrict__ otile) {
+    const int n_mma = hand_f_chunk_n(ch);
+#pragma unroll
+    for (int sb = 0; sb < 4; ++sb) {
+        const int c = 128 * (sb >> 1) + cg * 32 + 16 * (sb & 1);
+        if (c >= n_mma) continue;
+        float* __restrict__ o = otile + (size_t)(256 * ch + c) * TILE_M + row;
+        const int valid = 1386 - (256 * ch + c);           // columns of this sub-block inside the 1386 features (>= 16: all)
+        float old[16];
+        if (ADD) {
+            // all sixteen loads in flight together, and before the accumulator load: written as `o[..] += g` the compiler
+            // chains load -> add -> store sixteen times (one L2 round trip each)
+#pragma unroll
+            for (int j = 0; j < 16; ++j) old[j] = j < valid ? __ldcg(o + j * TILE_M) : 0.0f;
+        }
+        float g[16];
+        sw_ld16(tmem, lane_base, c, g);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+            if (j < valid) __stcg(o + j * TILE_M, ADD ? old[j] + g[j] : g[j]);
+    }
+}
 
 __global__ void __launch_bounds__(SW_THREADS, 1)
 hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_constant__ SwProgram prog,
@@ -287,7 +317,7 @@ hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_co
     if (warp == 0) {
         if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
     } else if (warp == 1) {
-        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles, p.dbg);
     } else if (warp == 2 + EPI_WARPS) {
         if (lane == 0) sw_in_producer(inputs, smem, &bar, n_my_tiles);
     } else {
@@ -302,7 +332,7 @@ hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_co
             const size_t tb = (size_t)tile * T16_TILE_BYTES;
             // 16 columns [c, c + 16) of D_lyr -> fp16 hi / lo halves of the next A operand, bf16 chunks of D16, fp32 rows
             auto emit16 = [&](int lyr, int c, const float* d) {
-                if (lyr > 0) {
+                {
                     uint32_t hi8[8], lo8[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) split2_lo16(d[2 * i], d[2 * i + 1], hi8[i], lo8[i]);
@@ -314,12 +344,8 @@ hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_co
                 q1.x = pack_bf16x2(d[8], d[9]); q1.y = pack_bf16x2(d[10], d[11]); q1.z = pack_bf16x2(d[12], d[13]); q1.w = pack_bf16x2(d[14], d[15]);
                 stg16(p.D16[lyr] + tb + t16_off(row, c >> 3), q0);
                 stg16(p.D16[lyr] + tb + t16_off(row, (c >> 3) + 1), q1);
-                if (lyr == 4 || lyr == 0) {
-                    float* __restrict__ o = (lyr == 4 ? p.D4 : p.D0) + gp * 256 + c;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) st4(o + j, make_float4(d[j], d[j + 1], d[j + 2], d[j + 3]));
-                }
             };
+            float* __restrict__ fb_tile = p.FB + (size_t)tile * (1388 * TILE_M);
             auto load_sp16 = [&](int hf, int c, float* sp) {       // s' = 1 - (em_hi + em_lo) of 16 columns, from the input slot
                 const uint4 a = sw_in_ld(smem, hf, 0, row, c), b = sw_in_ld(smem, hf, 0, row, c + 8);
                 const uint4 al = sw_in_ld(smem, hf, 1, row, c), bl = sw_in_ld(smem, hf, 1, row, c + 8);
@@ -375,8 +401,26 @@ hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_co
                     emit16(l - 1, c, g);
                     if (sb & 1) sw_in_release(&bar, hf);
                 }
-                if (l > 1) sw_publish(&bar);      // one arrival per MMA step: D_0 feeds none
+                sw_publish(&bar);
+                if (l == 5) {
+                    // D_4 is the A operand: FB = D_4 W_4[:, 256:], six chunk steps, before the layer-4 step overwrites nothing
+                    // (A stays) -- every arrival below releases the accumulator for the next step
+#pragma unroll 1
+                    for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) {
+                        sw_wait_acc(&bar, acc_par);
+                        hand_f_chunk<false>(tmem, lane_base, row, cg, ch, fb_tile);
+                        sw_publish(&bar);
+                    }
+                }
             }
+            // D_0 is the A operand: FB += D_0 W_0 (the rows this thread wrote above)
+#pragma unroll 1
+            for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) {
+                sw_wait_acc(&bar, acc_par);
+                hand_f_chunk<true>(tmem, lane_base, row, cg, ch, fb_tile);
+                if (ch + 1 < HAND_F_CHUNKS) sw_publish(&bar);      // one arrival per MMA step: the last one feeds none
+            }
+            tc::tc_fence_before_sync();
         }
     }
     sw_teardown(&bar);
@@ -386,6 +430,7 @@ hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_co
 // second-order backward: tangent sweep + reverse sweep over layers 0..8 (the 1386-wide ends outside)
 // ------------------------------------------------------------------------------------------------------------------
 struct HandBwdParams {
+    uint32_t* dbg;
     int64_t n;
     const float* Q0;         // [np, 256] fp32 rows: tF W_0^T
     const float* QF4;        // [np, 256] fp32 rows: tF W_4[:, 256:]^T
@@ -393,8 +438,7 @@ struct HandBwdParams {
     const float* d_feat;     // may be NULL
     int64_t ld_dfeat;
     uint8_t* X16[8];
-    float* DZ4;              // [np, 256] fp32 rows (operands of the feature-side contraction)
-    float* DZ0;
+    float* DF;               // column-major tiles [tile][1388][128] fp32: dz_4 W_4[:, 256:] + dz_0 W_0
     const uint8_t* chain;
     const float* w_out0;
     int n_tiles;
@@ -411,7 +455,7 @@ hand_bwd16_kernel(const __grid_constant__ HandBwdParams p, const __grid_constant
     if (warp == 0) {
         if (lane == 0) sw_producer(prog, p.chain, smem, &bar, n_my_tiles);
     } else if (warp == 1) {
-        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles);
+        if (lane == 0) sw_mma(prog, smem, &bar, n_my_tiles, p.dbg);
     } else if (warp == 2 + EPI_WARPS) {
         if (lane == 0) sw_in_producer(inputs, smem, &bar, n_my_tiles);
     } else {
@@ -425,6 +469,7 @@ hand_bwd16_kernel(const __grid_constant__ HandBwdParams p, const __grid_constant
             const bool live = gp < p.n;
             const size_t tb = (size_t)tile * T16_TILE_BYTES;
             const float gs = (live && p.d_sdf) ? p.d_sdf[gp] : 0.0f;
+            float* __restrict__ df_tile = p.DF + (size_t)tile * (1388 * TILE_M);
             auto pack16 = [&](const float* v, uint32_t* w) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -542,17 +587,29 @@ hand_bwd16_kernel(const __grid_constant__ HandBwdParams p, const __grid_constant
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) da[j] = live ? fmaf(1.0f - em[j], da[j], x[j]) : 0.0f;
-                        if (l > 1) emit_a16(c, da);
-                        if (l == 5 || l == 1) {
-                            float* __restrict__ o = (l == 5 ? p.DZ4 : p.DZ0) + gp * 256 + c;
-#pragma unroll
-                            for (int j = 0; j < 16; j += 4) st4(o + j, make_float4(da[j], da[j + 1], da[j + 2], da[j + 3]));
-                        }
+                        emit_a16(c, da);
                     }
                     sw_in_release(&bar, hf);
                 }
-                if (l > 1) sw_publish(&bar);      // one arrival per MMA step: dz_0 feeds none
+                sw_publish(&bar);
+                if (l == 5) {
+                    // dz_4 is the A operand: DF = d_xyz_feature + dz_4 W_4[:, 256:] in six chunk steps
+#pragma unroll 1
+                    for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) {
+                        sw_wait_acc(&bar, acc_par);
+                        hand_f_chunk<false>(tmem, lane_base, row, cg, ch, df_tile);
+                        sw_publish(&bar);
+                    }
+                }
             }
+            // dz_0 is the A operand: DF += dz_0 W_0
+#pragma unroll 1
+            for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) {
+                sw_wait_acc(&bar, acc_par);
+                hand_f_chunk<true>(tmem, lane_base, row, cg, ch, df_tile);
+                if (ch + 1 < HAND_F_CHUNKS) sw_publish(&bar);      // one arrival per MMA step: the last one feeds none
+            }
+            tc::tc_fence_before_sync();
         }
     }
     sw_teardown(&bar);
@@ -562,10 +619,10 @@ hand_bwd16_kernel(const __grid_constant__ HandBwdParams p, const __grid_constant
 // host side
 // ------------------------------------------------------------------------------------------------------------------
 // stash (floats per padded point): HROW 1644 | FB 1388 | RA 256 | RB 256 | EM[8] | EML[8] | D16[8] (128 floats each)
-//   RA: H0 during the trunk, then D0; RB: ZF4 during the trunk, then D4
+//   RA: H0, RB: ZF4 (inputs of the trunk)
 int64_t hand16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 512 + 24 * 128); }
-// backward workspace: AU4 1644 | DF 1388 | Q0 | QF4 | DZ0 | DZ4 (256 each) | X16[8]
-int64_t hand16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 1024 + 8 * 128); }
+// backward workspace: AU4 1644 | DF 1388 | Q0 | QF4 (256 each) | X16[8]
+int64_t hand16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 512 + 8 * 128); }
 
 static void sw_layer(SwProgram& prog, int& k, uint32_t off, int n_mma, int kblocks, int f16) {
     SwStep& st = prog.step[k++];
@@ -612,7 +669,7 @@ int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const 
 }
 
 int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* EML,
-                         uint8_t* const* D16, float* D4, float* D0, cudaStream_t s) {
+                         uint8_t* const* D16, float* FB, cudaStream_t s) {
     const HandLayout L = hand_layout();
     const int n_tiles = (int)ceil_div(n, TILE_M);
     static bool configured = false;
@@ -621,7 +678,7 @@ int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8
         configured = true;
     }
     HandNsweepParams p;
-    p.n = n; p.D4 = D4; p.D0 = D0;
+    p.n = n; p.FB = FB; p.dbg = dbg_slot(1);
     for (int l = 0; l < 8; ++l) p.D16[l] = D16[l];
     p.chain = ops;
     p.w_out0 = m->W[8];
@@ -634,7 +691,12 @@ int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8
     in.n_events = ne;
     SwProgram prog = {};
     int k = 0;
-    for (int l = 7; l >= 1; --l) sw_layer(prog, k, L.nn16_off[l], 256, 4, 1);               // d @ W_l
+    for (int l = 7; l >= 1; --l) {
+        sw_layer(prog, k, L.nn16_off[l], 256, 4, 1);                                        // d @ W_l
+        if (l == 5)
+            for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) sw_layer(prog, k, L.nnf16_off[0][ch], hand_f_chunk_n(ch), 4, 1);   // D_4 @ W_4f
+    }
+    for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) sw_layer(prog, k, L.nnf16_off[1][ch], hand_f_chunk_n(ch), 4, 1);           // D_0 @ W_0
     prog.n_steps = k;
     hand_nsweep16_kernel<<<std::min(n_tiles, sm_count()), SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);
     count_launch();
@@ -644,7 +706,7 @@ int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8
 
 int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* D16,
                       uint8_t* const* X16, const float* Q0, const float* QF4, const float* d_sdf, const float* d_feat,
-                      int64_t ld_dfeat, float* DZ4, float* DZ0, cudaStream_t s) {
+                      int64_t ld_dfeat, float* DF, cudaStream_t s) {
     HN_REQUIRE(!d_feat || (ld_dfeat % 4 == 0 && aligned16(d_feat)), "d_feat must be 16-byte aligned with ld %% 4 == 0");
     const HandLayout L = hand_layout();
     const int n_tiles = (int)ceil_div(n, TILE_M);
@@ -654,7 +716,8 @@ int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t*
         configured = true;
     }
     HandBwdParams p;
-    p.n = n; p.Q0 = Q0; p.QF4 = QF4; p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat; p.DZ4 = DZ4; p.DZ0 = DZ0;
+    p.n = n; p.Q0 = Q0; p.QF4 = QF4; p.d_sdf = d_sdf; p.d_feat = d_feat; p.ld_dfeat = ld_dfeat;
+    p.DF = DF; p.dbg = dbg_slot(2);
     for (int l = 0; l < 8; ++l) p.X16[l] = X16[l];
     p.chain = ops;
     p.w_out0 = m->W[8];
@@ -669,7 +732,12 @@ int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t*
     SwProgram prog = {};
     int k = 0;
     for (int l = 1; l <= 7; ++l) sw_layer(prog, k, L.nt_off[l], 256, 4, 0);                 // tangent: u @ W_l^T
-    for (int l = 8; l >= 1; --l) sw_layer(prog, k, L.nn_off[l], 256, 4, 0);                 // reverse: dz @ W_l
+    for (int l = 8; l >= 1; --l) {
+        sw_layer(prog, k, L.nn_off[l], 256, 4, 0);                                          // reverse: dz @ W_l
+        if (l == 5)
+            for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) sw_layer(prog, k, L.nnf_off[0][ch], hand_f_chunk_n(ch), 4, 0);     // dz_4 @ W_4f
+    }
+    for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) sw_layer(prog, k, L.nnf_off[1][ch], hand_f_chunk_n(ch), 4, 0);             // dz_0 @ W_0
     prog.n_steps = k;
     hand_bwd16_kernel<<<std::min(n_tiles, sm_count()), SW_THREADS, SW_SMEM_BYTES, s>>>(p, prog, in);
     count_launch();
@@ -690,6 +758,15 @@ int hand16_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s) {
         }
         HN_PROPAGATE(launch_pack_b(m->WT[l], m->ldT[l], pack_map(0, row0), 256, 256, 256, 4, dst + L.nn_off[l], s));
     }
+    // feature-side chunks: rows = features of WT_4 (after the 256 h3 rows) / WT_0
+    for (int w = 0; w < 2; ++w)
+        for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) {
+            const int l = w == 0 ? 4 : 0, r0 = (w == 0 ? 256 : 0) + 256 * ch;
+            HN_PROPAGATE(launch_pack_b(m->WT[l], m->ldT[l], pack_map(r0, 0), hand_f_chunk_valid(ch), 256, hand_f_chunk_n(ch), 4,
+                                       dst + L.nnf16_off[w][ch], s, true));
+            HN_PROPAGATE(launch_pack_b(m->WT[l], m->ldT[l], pack_map(r0, 0), hand_f_chunk_valid(ch), 256, hand_f_chunk_n(ch), 4,
+                                       dst + L.nnf_off[w][ch], s));
+        }
     return pack_batch_flush(s);
 }
 

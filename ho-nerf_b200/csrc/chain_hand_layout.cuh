@@ -14,8 +14,15 @@ struct HandLayout {
     uint32_t nn16_off[8];       // d @ W_l, l = 1..7, fp16 pairs (normal sweep)
     uint32_t nt_off[8];         // u @ W_l^T, l = 1..7, bf16 pairs (tangent sweep)
     uint32_t nn_off[9];         // dz @ W_l, l = 1..8, bf16 pairs (reverse sweep)
+    // feature-side contractions out of the chain, in 256-column chunks of the 1386 HALO features (the last one 106 -> 112):
+    // [0]: d @ W_4[:, 256:], [1]: d @ W_0;  B(n = feature, k = output)
+    uint32_t nnf16_off[2][6];   // fp16 pairs (normal sweep -> FB)
+    uint32_t nnf_off[2][6];     // bf16 pairs (reverse sweep -> DF)
     uint32_t total;
 };
+constexpr int HAND_F_CHUNKS = 6;
+__host__ __device__ inline int hand_f_chunk_n(int ch) { return ch < 5 ? 256 : 112; }       // UMMA N of chunk ch
+__host__ __device__ inline int hand_f_chunk_valid(int ch) { return ch < 5 ? 256 : 106; }   // features in chunk ch
 inline HandLayout hand_layout() {
     HandLayout L = {};
     uint32_t off = 0;
@@ -24,6 +31,10 @@ inline HandLayout hand_layout() {
     for (int l = 1; l <= 7; ++l) { L.nn16_off[l] = off; off += b_operand_bytes(256, 4); }
     for (int l = 1; l <= 7; ++l) { L.nt_off[l] = off; off += b_operand_bytes(256, 4); }
     for (int l = 1; l <= 8; ++l) { L.nn_off[l] = off; off += b_operand_bytes(256, 4); }
+    for (int w = 0; w < 2; ++w)
+        for (int ch = 0; ch < 6; ++ch) { L.nnf16_off[w][ch] = off; off += b_operand_bytes(ch < 5 ? 256 : 112, 4); }
+    for (int w = 0; w < 2; ++w)
+        for (int ch = 0; ch < 6; ++ch) { L.nnf_off[w][ch] = off; off += b_operand_bytes(ch < 5 ? 256 : 112, 4); }
     L.total = off;
     return L;
 }

@@ -18,10 +18,10 @@ namespace chain {      // chain16_hand.cu
 int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const float* H0, const float* ZF4, float* sdf,
                         float* feat, int64_t ld_feat, uint8_t* const* EM, uint8_t* const* EML, cudaStream_t s);
 int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* EML,
-                         uint8_t* const* D16, float* D4, float* D0, cudaStream_t s);
+                         uint8_t* const* D16, float* FB, cudaStream_t s);
 int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* D16,
                       uint8_t* const* X16, const float* Q0, const float* QF4, const float* d_sdf, const float* d_feat,
-                      int64_t ld_dfeat, float* DZ4, float* DZ0, cudaStream_t s);
+                      int64_t ld_dfeat, float* DF, cudaStream_t s);
 int hand16_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s);
 }  // namespace chain
 
@@ -198,6 +198,145 @@ __global__ void __launch_bounds__(HALO_WARPS * 32) halo_bwd_kernel(
     flush();
 }
 
+// ---- thread-per-point variants over TILED cotangents (HN_TC_MIXED16, chain16_hand.cu) -------------------------------------
+// FB / DF arrive as column-major tiles [tile][1388 columns][128 points].  One block = one tile, one thread = one point; the 66
+// columns of a joint are staged into shared memory sc[66][129] (conflict-free both ways), joints that are dead (h == 0) for
+// every point of the tile are skipped without staging.
+constexpr int HALO_TP = 128, HALO_TLD = 129;
+constexpr int64_t HALO_TILE_FLOATS = (int64_t)HFB_LD * HALO_TP;
+
+__device__ __forceinline__ void halo_stage_joint(const float* __restrict__ tile, int j, float* __restrict__ sc) {
+    for (int idx = threadIdx.x; idx < HALO_F * HALO_TP; idx += HALO_TP) {
+        const int i = idx >> 7, r = idx & 127;
+        sc[i * HALO_TLD + r] = tile[(size_t)(j * HALO_F + i) * HALO_TP + r];
+    }
+}
+// sc[i][r] += rows[(p0 + r) * ld + j * 66 + i]   (row-major addend, e.g. the cotangent the colour net sends to the feature)
+__device__ __forceinline__ void halo_stage_add_rows(const float* __restrict__ rows, int64_t ld, int64_t p0, int64_t n, int j,
+                                                    float* __restrict__ sc) {
+    for (int idx = threadIdx.x; idx < HALO_F * HALO_TP; idx += HALO_TP) {
+        const int r = idx / HALO_F, i = idx - r * HALO_F;
+        if (p0 + r < n) sc[i * HALO_TLD + r] += rows[(p0 + r) * ld + j * HALO_F + i];
+    }
+}
+
+__global__ void __launch_bounds__(HALO_TP) halo_normal_tiled_kernel(
+    const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp,
+    const float* __restrict__ FBt, int64_t n, int64_t ppf, float* __restrict__ normal) {
+    __shared__ float sc[HALO_F * HALO_TLD];
+    const int r = threadIdx.x;
+    const int64_t p = (int64_t)blockIdx.x * HALO_TP + r;
+    const bool live = p < n;
+    const int64_t f = (live ? p : n - 1) / ppf;
+    float x[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
+    if (live) load_x(pts, p, x);
+    const float* tile = FBt + (size_t)blockIdx.x * HALO_TILE_FLOATS;
+    for (int j = 0; j < HALO_J; ++j) {
+        const float* M = bt_inv + (f * HALO_J + j) * 16;
+        HaloBase b = halo_base(M, Tp + (f * HALO_J + j) * 3, x, j);
+        const bool on = live && !b.dead;
+        if (!__syncthreads_or(on)) continue;          // also orders the previous joint's reads of sc before the restaging
+        halo_stage_joint(tile, j, sc);
+        __syncthreads();
+        if (on) {
+            float g[3], dummy[3], w[3] = {0.f, 0.f, 0.f};
+            halo_grad_hvp<false, HALO_TLD>(b, sc + r, w, g, dummy);
+#pragma unroll
+            for (int a = 0; a < 3; ++a) acc[a] += M[0 * 4 + a] * g[0] + M[1 * 4 + a] * g[1] + M[2 * 4 + a] * g[2];
+        }
+    }
+    if (live) {
+        normal[p * 3] = acc[0]; normal[p * 3 + 1] = acc[1]; normal[p * 3 + 2] = acc[2];
+    }
+}
+
+// halo_bwd_kernel over tiled DF / FB; d_xyz (row-major, may be NULL) is added to DF while staging.  uniform_frame: every
+// point of a tile belongs to one frame (pose gradients are reduced over the block before the atomics)
+__global__ void __launch_bounds__(HALO_TP) halo_bwd_tiled_kernel(
+    const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp,
+    const float* __restrict__ DFt, const float* __restrict__ d_xyz, int64_t ld_dxyz, const float* __restrict__ FBt,
+    const float* __restrict__ dn, int64_t n, int64_t ppf, int uniform_frame, float* __restrict__ d_pts,
+    float* __restrict__ d_bt, float* __restrict__ d_T) {
+    __shared__ float sc[HALO_F * HALO_TLD];
+    __shared__ float red[HALO_TP / 32][16];
+    const int r = threadIdx.x, warp = r >> 5, lane = r & 31;
+    const int64_t p0 = (int64_t)blockIdx.x * HALO_TP, p = p0 + r;
+    const bool live = p < n;
+    const int64_t f = (live ? p : n - 1) / ppf;
+    float x[3] = {0.f, 0.f, 0.f}, t[3] = {0.f, 0.f, 0.f}, dx[3] = {0.f, 0.f, 0.f};
+    if (live) {
+        load_x(pts, p, x);
+        load_x(dn, p, t);
+    }
+    const float* dtile = DFt + (size_t)blockIdx.x * HALO_TILE_FLOATS;
+    const float* ftile = FBt + (size_t)blockIdx.x * HALO_TILE_FLOATS;
+    for (int j = 0; j < HALO_J; ++j) {
+        const float* M = bt_inv + (f * HALO_J + j) * 16;
+        HaloBase b = halo_base(M, Tp + (f * HALO_J + j) * 3, x, j);
+        const bool on = live && !b.dead;
+        if (!__syncthreads_or(on)) continue;
+        halo_stage_joint(dtile, j, sc);
+        if (d_xyz) {
+            __syncthreads();
+            halo_stage_add_rows(d_xyz, ld_dxyz, p0, n, j, sc);
+        }
+        __syncthreads();
+        float gq[3] = {0.f, 0.f, 0.f}, g2[3] = {0.f, 0.f, 0.f}, hv[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f}, dummy[3];
+        if (on) halo_grad_hvp<false, HALO_TLD>(b, sc + r, w, gq, dummy);
+        __syncthreads();
+        halo_stage_joint(ftile, j, sc);
+        __syncthreads();
+        float v[15];
+#pragma unroll
+        for (int i = 0; i < 15; ++i) v[i] = 0.0f;
+        if (on) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) w[a] = M[a * 4] * t[0] + M[a * 4 + 1] * t[1] + M[a * 4 + 2] * t[2];
+            halo_grad_hvp<true, HALO_TLD>(b, sc + r, w, g2, hv);
+            float dq[3];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dq[a] = gq[a] + hv[a];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) dx[a] += M[0 * 4 + a] * dq[0] + M[1 * 4 + a] * dq[1] + M[2 * 4 + a] * dq[2];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[a * 4 + c] = dq[a] * x[c] + g2[a] * t[c];
+                v[a * 4 + 3] = dq[a];
+                v[12 + a] = -dq[a];
+            }
+        }
+        if (d_bt || d_T) {
+            if (uniform_frame) {
+#pragma unroll
+                for (int i = 0; i < 15; ++i) v[i] = warp_sum(v[i]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int i = 0; i < 15; ++i) red[warp][i] = v[i];
+                }
+                __syncthreads();
+                if (r < 15) {
+                    const float sum = red[0][r] + red[1][r] + red[2][r] + red[3][r];
+                    if (sum != 0.0f) {
+                        if (r < 12) { if (d_bt) atomicAdd(&d_bt[(f * HALO_J + j) * 16 + r], sum); }
+                        else if (d_T) atomicAdd(&d_T[(f * HALO_J + j) * 3 + (r - 12)], sum);
+                    }
+                }
+            } else if (on) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+                    if (d_bt) atomicAdd(&d_bt[(f * HALO_J + j) * 16 + i], v[i]);
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+                    if (d_T) atomicAdd(&d_T[(f * HALO_J + j) * 3 + a], v[12 + a]);
+            }
+        }
+    }
+    if (d_pts && live) {
+        d_pts[p * 3] = dx[0]; d_pts[p * 3 + 1] = dx[1]; d_pts[p * 3 + 2] = dx[2];
+    }
+}
+
 // D7[p, c] = s'(H7[p, c]) * w_out0[c]
 __global__ void hand_normal_seed_kernel(const float* __restrict__ H7, const float* __restrict__ w_out0, int64_t n,
                                         float* __restrict__ D7) {
@@ -361,28 +500,6 @@ static int hand16_feature_in(const hn_mlp_t* m, const float* F, int64_t n, float
     f.C = out4; f.ldc = 256;
     return gemm_nt<EPI_STORE>(f, s, HN_TC_BF16X3, ROLE_VALUE);
 }
-// feature-side contraction out of the chain: OUT[n, 1386] = (aux ?) + R4 W_4[:, 256:] + R0 W_0
-static int hand16_feature_out(const hn_mlp_t* m, const float* R4, const float* R0, int64_t n, const float* aux, int64_t ld_aux,
-                              float* OUT, cudaStream_t s) {
-    GemmArgs f;
-    f.A = R4; f.lda = 256;
-    set_w(f, m, 4, HFEAT_OFF);
-    f.M = (int)n; f.N = HALO_DIM; f.K = 256;
-    f.C = OUT; f.ldc = HFB_LD;
-    if (aux) {
-        f.aux1 = aux; f.ldaux1 = ld_aux;
-        HN_PROPAGATE((gemm_nn<EPI_ADD_AUX>(f, s, HN_TC_BF16X3, ROLE_VALUE)));
-    } else {
-        HN_PROPAGATE((gemm_nn<EPI_STORE>(f, s, HN_TC_BF16X3, ROLE_VALUE)));
-    }
-    GemmArgs g;
-    g.A = R0; g.lda = 256;
-    set_w(g, m, 0);
-    g.M = (int)n; g.N = HALO_DIM; g.K = 256;
-    g.C = OUT; g.ldc = HFB_LD; g.aux1 = OUT; g.ldaux1 = HFB_LD;
-    return gemm_nn<EPI_ADD_AUX>(g, s, HN_TC_BF16X3, ROLE_VALUE);
-}
-
 }  // namespace hn
 
 using namespace hn;
@@ -480,10 +597,8 @@ int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
             count_launch();
             HN_CHECK_LAUNCH();
         }
-        HN_PROPAGATE(chain::launch_hand16_nsweep(mlp, ops, n, h.EM, h.EML, h.D16, h.RB, h.RA, s));
-        HN_PROPAGATE(hand16_feature_out(mlp, h.RB, h.RA, n, nullptr, 0, h.FB, s));
-        halo_normal_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, h.FB, HFB_LD, n,
-                                                                              pts_per_frame, normal);
+        HN_PROPAGATE(chain::launch_hand16_nsweep(mlp, ops, n, h.EM, h.EML, h.D16, h.FB, s));
+        halo_normal_tiled_kernel<<<nblocks(n, HALO_TP), HALO_TP, 0, s>>>(pts, bt_inv, T_pose, h.FB, n, pts_per_frame, normal);
         count_launch();
         HN_CHECK_LAUNCH();
         return HN_OK;
@@ -567,22 +682,20 @@ int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
         float* DF = AU4 + np * HROW_LD;                    // [np, 1388]
         float* Q0 = DF + np * HFB_LD;                      // [np, 256]: tF W_0^T
         float* QF4 = Q0 + np * 256;                        // [np, 256]: tF W_4[:, 256:]^T
-        float* DZ0 = QF4 + np * 256;                       // [np, 256]
-        float* DZ4 = DZ0 + np * 256;
         uint8_t* X16[8];
-        uint8_t* b = reinterpret_cast<uint8_t*>(DZ4 + np * 256);
+        uint8_t* b = reinterpret_cast<uint8_t*>(QF4 + np * 256);
         for (int l = 0; l < 8; ++l) { X16[l] = b; b += np * 512; }
         halo_tangent_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, d_normal, n, pts_per_frame,
                                                                                AU4 + HFEAT_OFF, HROW_LD);
         count_launch();
         HN_CHECK_LAUNCH();
         HN_PROPAGATE(hand16_feature_in(mlp, AU4 + HFEAT_OFF, n, Q0, QF4, false, s));
-        HN_PROPAGATE(chain::launch_hand16_bwd(mlp, ops, n, h.EM, h.D16, X16, Q0, QF4, d_sdf, d_feat, ld_dfeat, DZ4, DZ0, s));
+        HN_PROPAGATE(chain::launch_hand16_bwd(mlp, ops, n, h.EM, h.D16, X16, Q0, QF4, d_sdf, d_feat, ld_dfeat, DF, s));
         if (d_pts || d_bt_inv || d_T_pose) {
-            HN_PROPAGATE(hand16_feature_out(mlp, DZ4, DZ0, n, d_xyz_feature, ld_dxyz, DF, s));
-            const int64_t per_warp = max((int64_t)1, ceil_div(n, (int64_t)sm_count() * 16 * HALO_WARPS));
-            halo_bwd_kernel<<<nblocks(ceil_div(n, per_warp), HALO_WARPS), HALO_WARPS * 32, 0, s>>>(
-                pts, bt_inv, T_pose, DF, HFB_LD, h.FB, HFB_LD, d_normal, n, pts_per_frame, per_warp, d_pts, d_bt_inv, d_T_pose);
+            const int uniform = (pts_per_frame % HALO_TP == 0 || n <= pts_per_frame) ? 1 : 0;
+            halo_bwd_tiled_kernel<<<nblocks(n, HALO_TP), HALO_TP, 0, s>>>(pts, bt_inv, T_pose, DF, d_xyz_feature, ld_dxyz, h.FB,
+                                                                          d_normal, n, pts_per_frame, uniform, d_pts, d_bt_inv,
+                                                                          d_T_pose);
             count_launch();
             HN_CHECK_LAUNCH();
         }

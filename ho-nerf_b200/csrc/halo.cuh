@@ -16,6 +16,16 @@ constexpr float HALO_TAU = 200.0f;
 __constant__ float c_halo_cutoff[HALO_J] = {0.08f, 0.03f, 0.03f, 0.02f, 0.02f, 0.03f, 0.02f, 0.02f, 0.02f, 0.03f, 0.02f,
                                             0.02f, 0.02f, 0.03f, 0.02f, 0.02f, 0.02f, 0.03f, 0.02f, 0.02f, 0.02f};
 
+// sin / cos of the encoding arguments (|x| < ~800) for the DERIVATIVE kernels: two-term Cody-Waite reduction to [-pi, pi],
+// then the SFU approximations (abs error ~4e-7; the feature itself keeps sincosf, its values enter the SDF directly)
+__device__ __forceinline__ void halo_sincos_fast(float x, float* s, float* c) {
+    const float n = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-n, 6.2831854820251465f, x);
+    r = fmaf(-n, -1.7484556000744883e-07f, r);
+    *s = __sinf(r);
+    *c = __cosf(r);
+}
+
 struct HaloBase {
     float q[3], r[3], v, h, h1, h2;
     bool dead;      // h == h' == h'' == 0 exactly (sigmoid saturated): every output is exactly zero
@@ -85,7 +95,7 @@ __device__ __forceinline__ void halo_jvp(const HaloBase& b, const float w[3], fl
     float f = 1.0f;
     for (int k = 0; k < HALO_LV; ++k) {
         float s, c;
-        sincosf(b.v * f, &s, &c);
+        halo_sincos_fast(b.v * f, &s, &c);
         out[1 + k] = (f * c * dv) * b.h + s * hd;
         out[1 + HALO_LV + k] = (-f * s * dv) * b.h + c * hd;
         f *= 2.0f;
@@ -96,7 +106,7 @@ __device__ __forceinline__ void halo_jvp(const HaloBase& b, const float w[3], fl
         f = 1.0f;
         for (int k = 0; k < HALO_LR; ++k) {
             float s, c;
-            sincosf(b.r[a] * f, &s, &c);
+            halo_sincos_fast(b.r[a] * f, &s, &c);
             out[24 + a * 14 + k] = (f * c * dr[a]) * b.h + s * hd;
             out[24 + a * 14 + HALO_LR + k] = (-f * s * dr[a]) * b.h + c * hd;
             f *= 2.0f;
@@ -104,8 +114,8 @@ __device__ __forceinline__ void halo_jvp(const HaloBase& b, const float w[3], fl
     }
 }
 
-// g = d<c,F>/dq ; when HVP: hv = d(g.w)/dq.  c points at 66 floats (shared memory).
-template <bool HVP>
+// g = d<c,F>/dq ; when HVP: hv = d(g.w)/dq.  c points at 66 floats (shared memory), CS floats apart.
+template <bool HVP, int CS = 1>
 __device__ __forceinline__ void halo_grad_hvp(const HaloBase& b, const float* __restrict__ c, const float w[3],
                                               float g[3], float hv[3]) {
     if (b.dead) {
@@ -117,8 +127,8 @@ __device__ __forceinline__ void halo_grad_hvp(const HaloBase& b, const float* __
     float f = 1.0f;
     for (int k = 0; k < HALO_LV; ++k) {
         float s, co;
-        sincosf(b.v * f, &s, &co);
-        const float cs = c[1 + k], cc = c[1 + HALO_LV + k];
+        halo_sincos_fast(b.v * f, &s, &co);
+        const float cs = c[(1 + k) * CS], cc = c[(1 + HALO_LV + k) * CS];
         A += cs * s + cc * co;
         A1 += f * (cs * co - cc * s);
         A2 -= f * f * (cs * s + cc * co);
@@ -127,14 +137,14 @@ __device__ __forceinline__ void halo_grad_hvp(const HaloBase& b, const float* __
     float B = 0.0f, b1[3], b2[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        B += c[21 + a] * b.r[a];
-        b1[a] = c[21 + a];
+        B += c[(21 + a) * CS] * b.r[a];
+        b1[a] = c[(21 + a) * CS];
         b2[a] = 0.0f;
         f = 1.0f;
         for (int k = 0; k < HALO_LR; ++k) {
             float s, co;
-            sincosf(b.r[a] * f, &s, &co);
-            const float cs = c[24 + a * 14 + k], cc = c[24 + a * 14 + HALO_LR + k];
+            halo_sincos_fast(b.r[a] * f, &s, &co);
+            const float cs = c[(24 + a * 14 + k) * CS], cc = c[(24 + a * 14 + HALO_LR + k) * CS];
             B += cs * s + cc * co;
             b1[a] += f * (cs * co - cc * s);
             b2[a] -= f * f * (cs * s + cc * co);
