@@ -481,10 +481,6 @@ class _SdfHandFn(torch.autograd.Function):
         pk = packed.get()
         ctx.set_materialize_grads(False)      # an output nobody differentiates arrives as None, not as a zero tensor
         ctx.params_need_grad = any(p.requires_grad for p in params)
-        if precision == _lib.HN_TC_MIXED16 and ctx.params_need_grad:
-            # the tile-chain kernels of the hand net keep a 16-bit stash and compute no weight gradients (pose fitting,
-            # rendering); a call whose backward trains the net stays on the per-layer contractions with their fp32 stash
-            precision = _lib.HN_TC_BF16X3
         n, dev = pts_c.shape[0], pts_c.device
         sdf = torch.empty(n, 1, device=dev)
         feat = torch.empty(n, 256, device=dev)
@@ -541,8 +537,13 @@ def sdf_hand(packed, pts, bt_inv, T_pose_21, precision=None):
     """Fused anerf_emb_point(_batch) + SDFNetwork.forward + .gradient (utils/fields.py:22-52, 132-177).
     Returns sdf [N,1], feature [N,256], normal [N,3], xyz_feature [N,1386]."""
     precision = _default_precision if precision is None else precision
+    params = packed.flat_params()
+    if precision == _lib.HN_TC_MIXED16 and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        # the tile-chain kernels of the hand net keep a 16-bit stash and compute no weight gradients (pose fitting, rendering);
+        # a call whose backward trains the net stays on the per-layer contractions with their fp32 stash
+        precision = _lib.HN_TC_BF16X3
     pts2, bt, T, ppf = _hand_pose_args(pts, bt_inv, T_pose_21)
-    return _SdfHandFn.apply(pts2, bt, T, ppf, packed, precision, *packed.flat_params())
+    return _SdfHandFn.apply(pts2, bt, T, ppf, packed, precision, *params)
 
 
 class _ColorHandFn(torch.autograd.Function):

@@ -86,8 +86,8 @@ def test_pose_and_point_gradients_vs_fp64_oracle(n_rep):
 
 
 def test_trainable_weights_stay_on_the_per_layer_path():
-    """With trainable weights the default precision falls back to the per-layer contractions (fp32 stash, weight gradients);
-    asking the C entry point for weight gradients under HN_TC_MIXED16 is an error, not a silent zero."""
+    """With trainable weights (and grad mode on) the default precision falls back to the per-layer contractions (fp32 stash,
+    weight gradients): hn_sdf_hand_bwd rejects grad != NULL under HN_TC_MIXED16 rather than returning zeros."""
     import honerf_b200 as H
     pts, bt0, T0 = _case()
     sdf_t, _, _, _, _ = hand_modules(requires_grad=True)
@@ -98,6 +98,11 @@ def test_trainable_weights_stay_on_the_per_layer_path():
     assert torch.equal(s_t, s3) and torch.equal(f_t, f3) and torch.equal(n_t, n3)
     (s_t.sum() + n_t.sum()).backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for k, p in sdf_t.named_parameters() if k != "se3_refine")
+    # under no_grad the same net renders through the chain kernels (bit-identical to the frozen net's default path)
+    with torch.no_grad():
+        s_n, f_n, n_n, _ = sdf_t.fused(x, bt0.to(DEV), T0.to(DEV))
+    s_f, f_f, n_f, _ = sdf_f.fused(x, bt0.to(DEV), T0.to(DEV))
+    assert torch.equal(s_n, s_f) and torch.equal(f_n, f_f) and torch.equal(n_n, n_f) and not torch.equal(s_n, s3)
 
 
 def test_sdf_only_sizes():

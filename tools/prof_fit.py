@@ -1,4 +1,4 @@
-"""Short workload for an ncu launch list: a few two-field fitting steps (bench.fitting_extra)."""
+"""Launch-list workload: the two-field pose-fitting step of bench.py (512 rays x 192 samples x 2 fields, frozen nets)."""
 import os
 import sys
 
@@ -10,4 +10,4 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 import honerf_b200 as H  # noqa: E402
 
-print(bench.fitting_extra(H, torch.device("cuda", 0), int(sys.argv[1]) if len(sys.argv) > 1 else 512, "tc_bf16x3"))
+print(bench.fitting_extra(H, torch.device("cuda:0"), int(os.environ.get("PROF_FIT_RAYS", 512)), "tc_mixed16"))
