@@ -33,7 +33,7 @@ def build_id(root=None):
     root = root or os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ho-nerf_b200", "csrc")
     h = hashlib.sha1()
     for f in sorted(os.listdir(root)):
-        if f.endswith((".cu", ".cuh")) and (f.startswith("chain") or f in ("tc_common.cuh", "common.cuh")):
+        if f.endswith((".cu", ".cuh")) and ((f.startswith("chain") and "hand" not in f) or f in ("tc_common.cuh", "common.cuh")):
             h.update(f.encode())
             h.update(open(os.path.join(root, f), "rb").read())
     return h.hexdigest()[:16]
