@@ -300,9 +300,10 @@ int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
 
 // weight-gradient kernel over 16-bit dW-ready tiles
 struct Dw16Job {
-    const uint8_t* P[2];     // [tiles] T16 tiles (256 features): M operand (output features)
-    const uint8_t* Q[2];     // [tiles] T16 tiles of q_chunks * 8 features: N operand (input features)
-    int n_pairs;
+    const uint8_t* P[3];     // [tiles] T16 tiles (256 features): M operand (output features)
+    const uint8_t* Q[3];     // [tiles] T16 tiles of q_chunks * 8 features: N operand (input features)
+    int n_pairs;             // dW = sum over pairs of P[i]^T Q[i]  (three pairs = hi/lo operand split: Ph Qh + Pl Qh + Ph Ql)
+    int db_mask;             // pairs whose P enters the bias gradient (0 = pair 0 only)
     int q_chunks;            // 32 (T16) or 8 (T16N)
     int n_mma;               // UMMA N: multiple of 16, <= 8 * q_chunks
     float* db;               // += column sums of P[0] (may be NULL)

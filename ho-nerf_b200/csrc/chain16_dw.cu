@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(D16_THREADS, 1) dw16_kernel(const __grid_const
         {
             uint32_t stage = 0, phase = 0;
             for (int it = 0; it < n_iters; ++it) {
-                const bool first_pair = job.n_pairs == 1 || (it & 1) == 0;
+                const bool first_pair = (((job.db_mask ? job.db_mask : 1) >> (it % job.n_pairs)) & 1) != 0;
                 tc::mbar_wait(&full[stage], phase);         // never run ahead of the stage (the empty count includes us)
                 if (job.db && first_pair) {
                     const uint8_t* P = smem + stage * D16_STAGE_BYTES;
@@ -309,7 +309,7 @@ int hn_dw16_test(const float* P, int out, const float* Q, int in, const float* P
         chain::to_t16_kernel<<<(unsigned)ceil_div(np * nch, 256), 256, 0, s>>>(qs[a], in, n, in, nch, tq[a]);
     }
     HN_CHECK_LAUNCH();
-    chain::Dw16Params p;
+    chain::Dw16Params p = {};
     p.n_tiles = (int)(np / chain::TILE_M); p.n_jobs = 1; p.part = part;
     chain::Dw16Job& j = p.job[0];
     j.P[0] = tp[0]; j.Q[0] = tq[0]; j.P[1] = tp[pairs - 1]; j.Q[1] = tq[pairs - 1];

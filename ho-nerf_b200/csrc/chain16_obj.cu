@@ -854,7 +854,7 @@ int launch_m16_bwd(const hn_mlp_t* m, int64_t n, float inv_scale, const float* s
     HN_CHECK_LAUNCH();
     if (!grad) return HN_OK;
     // ---- all weight / bias gradients from the tiles the two sweep kernels left in HBM ------------------------------------
-    Dw16Params dp;
+    Dw16Params dp = {};
     DwReduceParams rp;
     dp.n_tiles = n_tiles; dp.part = part; rp.part = part;
     int k = 0;

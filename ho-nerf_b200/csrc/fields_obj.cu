@@ -17,10 +17,10 @@ int launch_sdf_fwd(const hn_mlp_t* m, const float* pts, int64_t n, float inv_sca
 int64_t color_stash_floats(int64_t n);
 int64_t color_bwd_ws_floats(int64_t n);
 int launch_color_fwd(const hn_mlp_t* m, const float* pts, const float* dirs, const float* feat, int64_t ld_feat,
-                     const float* normal, int64_t n, float* rgb, float* stash, cudaStream_t s);
+                     const float* normal, int64_t n, float* rgb, float* stash, cudaStream_t s, bool s16);
 int launch_color_bwd(const hn_mlp_t* m, int64_t n, const float* stash, const float* rgb, const float* d_rgb, float* d_pts,
                      float* d_dirs, float* d_feat, int64_t ld_dfeat, float* d_normal, const hn_mlp_grad_t* grad, float* ws,
-                     cudaStream_t s);
+                     cudaStream_t s, bool s16);
 int64_t bwd_ws_floats(int64_t n);
 int64_t stash_floats(int64_t n);
 int launch_sdf_bwd_weights(const hn_mlp_t* m, int64_t n, float inv_scale, const float* stash, const float* d_sdf,
@@ -527,6 +527,7 @@ int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs, c
                      int64_t ld_feat, const float* normal, int64_t n, float* rgb, float* stash,
                      int64_t stash_floats, int precision, hn_stream_t stream) {
     HN_PROPAGATE(check_color_obj_mlp(mlp));
+    const bool s16 = precision == HN_TC_MIXED16;      // same chain arithmetic, 16-bit dW-ready stash (chain_color.cu)
     precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_color_obj_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
@@ -534,7 +535,7 @@ int hn_color_obj_fwd(const hn_mlp_t* mlp, const float* pts, const float* dirs, c
     HN_REQUIRE(pts && dirs && feat && normal && rgb && stash, "hn_color_obj_fwd: null pointer");
     HN_REQUIRE(stash_floats >= hn_color_obj_stash_floats(n) && aligned16(stash), "stash too small or misaligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (precision == HN_TC_BF16X3) return chain::launch_color_fwd(mlp, pts, dirs, feat, ld_feat, normal, n, rgb, stash, s);
+    if (precision == HN_TC_BF16X3) return chain::launch_color_fwd(mlp, pts, dirs, feat, ld_feat, normal, n, rgb, stash, s, s16);
     float* CIN = stash;
     float* R[4];
     for (int l = 0; l < 4; ++l) R[l] = stash + n * CIN_LD + (int64_t)l * n * 256;
@@ -561,6 +562,7 @@ int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* 
                      const hn_mlp_grad_t* grad, float* ws, int64_t ws_floats, int precision,
                      hn_stream_t stream) {
     HN_PROPAGATE(check_color_obj_mlp(mlp));
+    const bool s16 = precision == HN_TC_MIXED16;
     precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_color_obj_bwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
@@ -569,7 +571,7 @@ int hn_color_obj_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float* 
     HN_REQUIRE(ws_floats >= hn_color_obj_ws_floats(n, HN_WS_BWD) && aligned16(ws), "workspace too small or misaligned");
     cudaStream_t s = (cudaStream_t)stream;
     if (precision == HN_TC_BF16X3)
-        return chain::launch_color_bwd(mlp, n, stash, rgb, d_rgb, d_pts, d_dirs, d_feat, ld_dfeat, d_normal, grad, ws, s);
+        return chain::launch_color_bwd(mlp, n, stash, rgb, d_rgb, d_pts, d_dirs, d_feat, ld_dfeat, d_normal, grad, ws, s, s16);
     float* CIN = stash;
     float* R[4];
     for (int l = 0; l < 4; ++l) R[l] = stash + n * CIN_LD + (int64_t)l * n * 256;

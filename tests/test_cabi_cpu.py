@@ -41,7 +41,8 @@ def test_size_queries_run_without_a_gpu():
     assert _lib.lib.hn_sdf_obj_stash_floats(1024) == 1024 * (128 + 32 + 32 * 128)
     assert _lib.lib.hn_sdf_obj_ws_floats(10, _lib.HN_WS_SDF_ONLY) > 0
     assert _lib.lib.hn_sdf_obj_ws_floats(1000, _lib.HN_WS_BWD) >= 1024 * (64 + 24 * 256 + 64)
-    assert _lib.lib.hn_color_obj_stash_floats(10) == 128 * (128 + 5 * 256)
+    # colour stash: fp32 layout ENC | FEAT | R[4] (128 + 5 * 256) or, HN_TC_MIXED16, ENC + hi / lo T16 tiles of six arrays (128 + 12 * 128)
+    assert _lib.lib.hn_color_obj_stash_floats(10) == 128 * (128 + 12 * 128)
     assert _lib.lib.hn_sdf_obj_chain_bytes() > 4 * 1024 * 1024 and _lib.lib.hn_color_obj_chain_bytes() > 2 * 1024 * 1024
 
 

@@ -96,3 +96,31 @@ def test_mixed16_matches_bf16x3_path_loosely_and_no_weight_grads():
     ga, = torch.autograd.grad((a[2] * w).sum() + a[0].sum(), x)
     gb, = torch.autograd.grad((b[2] * w).sum() + b[0].sum(), x)
     assert rel_l2(ga, gb) < 1e-2
+
+
+def test_colour_net_16bit_stash_matches_the_fp32_stash_path():
+    """HN_TC_MIXED16 keeps the colour chain's arithmetic and only changes what is stashed (hi / lo bf16 T16 tile pairs) and
+    which kernel forms the weight gradients (dw16_kernel, three MMAs per product on the pairs): forward and input gradients
+    bit-identical to HN_TC_BF16X3, weight / bias gradients within 2e-5 relative (fp32 summation order only)."""
+    import honerf_b200 as H
+    n = 40000
+    _, col, _, _, _ = obj_modules()
+    g = torch.Generator().manual_seed(0)
+    x = (0.45 * torch.randn(n, 3, generator=g)).to(DEV)
+    d = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+    feat = (0.3 * torch.randn(n, 256, generator=g)).to(DEV)
+    nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+    go = (1e-3 * torch.randn(n, 3, generator=g)).to(DEV)
+    res = {}
+    for name in ("tc_bf16x3", "tc_mixed16"):
+        for q in col.parameters():
+            q.grad = None
+        xs = [t.clone().requires_grad_(True) for t in (x, d, feat, nrm)]
+        rgb = H.ops.color_obj(col.packed(), xs[0], xs[1], xs[2], xs[3], precision=H.ops._PRECISIONS[name])
+        (rgb * go).sum().backward()
+        res[name] = ({k: q.grad.clone() for k, q in col.named_parameters()}, [t.grad for t in xs], rgb.detach())
+    a, b = res["tc_mixed16"], res["tc_bf16x3"]
+    assert torch.equal(a[2], b[2]) and all(torch.equal(u, v) for u, v in zip(a[1], b[1]))
+    worst = {k: rel_l2(a[0][k], b[0][k]) for k in a[0]}
+    print("colour weight gradients, 16-bit pair stash vs fp32 stash:", sorted(worst.items(), key=lambda kv: -kv[1])[:3])
+    assert all(v < 2e-5 for v in worst.values()), worst
