@@ -1104,7 +1104,7 @@ def main():
     ap.add_argument("--precision", default="tc_mixed16", choices=["simt_fp32", "tc_tf32", "tc_tf32x3", "tc_bf16x3", "tc_mixed16"])
     ap.add_argument("--optimizer", default="flat", choices=["flat", "torch"],
                     help="flat: honerf_b200.optim.FlatAdam (one launch); torch: torch.optim.Adam(fused, capturable)")
-    ap.add_argument("--ray-streams", type=int, default=3,
+    ap.add_argument("--ray-streams", type=int, default=2,
                     help="render each GPU's rays as this many shards on concurrent CUDA streams (NeuSRenderer.ray_streams)")
     ap.add_argument("--ray-shards", default="", help="explicit shard sizes, e.g. 148,148,216 (overrides --ray-streams)")
     ap.add_argument("--shard-loss", type=int, default=1,
