@@ -132,6 +132,9 @@ PROTOTYPES = {
     "hn_mc_set_tables": (c_int, [P, P, P]),
     "hn_mc_classify": (c_int, [P, c_int, c_int, c_int, c_float, P, P, P]),
     "hn_mc_emit": (c_int, [P, c_int, c_int, c_int, c_float, P, P, P, P, P, P, P]),
+    "hn_outside_points": (c_int, [P, P, P, c_float, c_int64, c_int, P, P, P, P]),
+    "hn_outside_composite_fwd": (c_int, [P, P, P, P, c_int64, c_int, P, P, P, P, P]),
+    "hn_outside_composite_bwd": (c_int, [P, P, P, P, P, P, c_int64, c_int, P, P, P, P, P, P, P]),
     "hn_dw16_test": (c_int, [P, c_int, P, c_int, P, P, c_int64, P, c_int64, P, P, c_int64, P, c_int64, P]),
     "hn_dw16_set_debug": (c_int, [c_int]),
     "hn_chain16_set_debug": (c_int, [P]),

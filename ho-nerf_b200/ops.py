@@ -1139,6 +1139,60 @@ def _mc_tables(device):
     _mc_devices.add(key)
 
 
+def outside_points(rays_o, rays_d, z_vals, sample_dist):
+    """Inverted-sphere query points of render_core_outside: -> (pts4 [B*n,4] = (p/r, 1/r), dirs [B*n,3], dists [B,n]).
+    Rays are data here (no gradient), like everywhere in the sampling stage."""
+    o, d, z = _f32c(rays_o.detach()), _f32c(rays_d.detach()), _f32c(z_vals.detach())
+    _require_cuda(z, "outside_points")
+    B, n = z.shape
+    pts4 = torch.empty(B * n, 4, device=z.device)
+    dirs = torch.empty(B * n, 3, device=z.device)
+    dists = torch.empty(B, n, device=z.device)
+    check(lib.hn_outside_points(_ptr(o), _ptr(d), _ptr(z), float(sample_dist), B, n, _ptr(pts4), _ptr(dirs), _ptr(dists),
+                                _stream(z)), "hn_outside_points")
+    return pts4, dirs, dists
+
+
+class _OutsideCompositeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, density, raw_rgb, dists, background):
+        dn, rw, ds = _f32c(density.detach()), _f32c(raw_rgb.detach()), _f32c(dists.detach())
+        _require_cuda(dn, "outside_composite")
+        B, n = ds.shape
+        bg = _f32c(background.detach().reshape(3)) if background is not None else None
+        sampled = torch.empty(B, n, 3, device=dn.device)
+        alpha = torch.empty(B, n, device=dn.device)
+        weights = torch.empty(B, n, device=dn.device)
+        color = torch.empty(B, 3, device=dn.device)
+        check(lib.hn_outside_composite_fwd(_ptr(dn), _ptr(rw), _ptr(ds), _ptr(bg), B, n, _ptr(sampled), _ptr(alpha), _ptr(weights),
+                                           _ptr(color), _stream(dn)), "hn_outside_composite_fwd")
+        ctx.set_materialize_grads(False)
+        ctx.saved = (dn, ds, bg, sampled, alpha, weights)
+        ctx.shapes = (density.shape, raw_rgb.shape)
+        return color, sampled, alpha, weights
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_color, g_sampled, g_alpha, g_weights):
+        dn, ds, bg, sampled, alpha, weights = ctx.saved
+        B, n = ds.shape
+        d_density = torch.empty(B, n, device=dn.device)
+        d_raw = torch.empty(B, n, 3, device=dn.device)
+        f = lambda t: _f32c(t) if t is not None else None
+        g_color, g_sampled, g_alpha, g_weights = f(g_color), f(g_sampled), f(g_alpha), f(g_weights)
+        check(lib.hn_outside_composite_bwd(_ptr(dn), _ptr(ds), _ptr(bg), _ptr(sampled), _ptr(alpha), _ptr(weights), B, n,
+                                           _ptr(g_color), _ptr(g_sampled), _ptr(g_alpha), _ptr(g_weights), _ptr(d_density),
+                                           _ptr(d_raw), _stream(dn)), "hn_outside_composite_bwd")
+        return d_density.reshape(ctx.shapes[0]), d_raw.reshape(ctx.shapes[1]), None, None
+
+
+def outside_composite(density, raw_rgb, dists, background=None):
+    """alpha / transmittance / colour compositing of a density field along rays (render_core_outside): density [B*n,1] or
+    [B,n], raw_rgb [B*n,3] or [B,n,3] (the NeRF's raw outputs), dists [B,n] -> (color [B,3], sampled_color [B,n,3],
+    alpha [B,n], weights [B,n]); differentiable in density and raw_rgb through all four outputs."""
+    return _OutsideCompositeFn.apply(density, raw_rgb, dists, background)
+
+
 def marching_cubes(u, threshold=0.0):
     """mcubes.marching_cubes(u, threshold) (utils/renderer.py:279) on the device: u [nx,ny,nz] fp32 CUDA tensor ->
     (vertices [V,3] fp32 in index coordinates, triangles [T,3] int32); vertices are shared between cells, triangle normals

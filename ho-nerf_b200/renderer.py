@@ -238,6 +238,20 @@ class NeuSRenderer:
                 u[a - x0:b - x0] = self._sdf_only(pts, bt_inv, T_pose_21).reshape(xx.shape)
         return u
 
+    def render_core_outside(self, rays_o, rays_d, z_vals, sample_dist, nerf, background_rgb=None):
+        """The background branch the north star names.  The HO-NeRF reference stores ``n_outside`` (utils/renderer.py:47,56) but
+        never defines this method and every config sets 0, so the semantics are those of the NeuS renderer it derives from
+        (PARITY UNPINNED): the samples are mapped to inverted-sphere coordinates (p / r, 1 / r), ``nerf(pts4, dirs)`` -- the
+        caller's module, any callable returning (density [N,1], raw rgb [N,3]) -- is evaluated there, and density is
+        composited along the ray.  Point mapping and compositing (forward + backward) are device kernels
+        (``hn_outside_points``, ``hn_outside_composite_*``).  Returns the upstream dict: color, sampled_color, alpha, weights."""
+        pts4, dirs, dists = ops.outside_points(rays_o, rays_d, z_vals, sample_dist)
+        if self.n_outside <= 0:
+            pts4 = pts4[:, :3]          # upstream: pts.reshape(-1, 3 + int(n_outside > 0))
+        density, raw = nerf(pts4, dirs)
+        color, sampled, alpha, weights = ops.outside_composite(density, raw, dists, background_rgb)
+        return {"color": color, "sampled_color": sampled, "alpha": alpha, "weights": weights}
+
     def extract_geometry(self, bound_min, bound_max, resolution, bt_inv, T_pose_21, Ro, To, threshold=0.0):
         """utils/renderer.py:260-284: (vertices [V,3] float64, triangles [T,3]) as numpy arrays, like the reference.  The
         lattice stays on the device and marching cubes runs there (ops.marching_cubes: same shared-vertex mesh structure as

@@ -471,6 +471,26 @@ HN_API int hn_chain16_set_debug(void* host_mapped_words);
 HN_API int hn_dw_test(const float* P, int64_t ldp, int p_tiled, int out, const float* Q, int64_t ldq,
                       int q_tiled, int in, const float* P2, const float* Q2, int64_t n, float* C,
                       int64_t ldc, float* db, float* part, int64_t part_floats, hn_stream_t stream);
+/* ---- render_core_outside (background branch of a NeuS renderer) ---------------------------------------------------------
+ * Named by the north star; the HO-NeRF reference only stores n_outside (utils/renderer.py:47,56; every config sets 0) and has
+ * no such method: these follow the semantics of the NeuS renderer it was derived from (PARITY UNPINNED; oracle:
+ * oracle/honerf_oracle.render_core_outside).
+ * hn_outside_points: z_vals [n_rays, n] -> inverted-sphere query points pts4 [n_rays*n, 4] = (p / r, 1 / r), r = clip(|p|, 1,
+ *   1e10), p = o + d (z + dists / 2); dirs [n_rays*n, 3]; dists [n_rays, n] (= diff(z), sample_dist appended).
+ * hn_outside_composite_fwd: density [n_rays, n], raw_rgb [n_rays, n, 3] (the NeRF's outputs) -> sampled_color = sigmoid(raw),
+ *   alpha = 1 - exp(-softplus(density) dists), weights = alpha * exclusive cumprod(1 - alpha + 1e-7), color [n_rays, 3] =
+ *   sum w c (+ background[3] (1 - sum w) when background != NULL).
+ * hn_outside_composite_bwd: cotangents of any of the four outputs (NULL = none) -> d_density, d_raw_rgb.  n <= 512. */
+HN_API int hn_outside_points(const float* rays_o, const float* rays_d, const float* z_vals, float sample_dist, int64_t n_rays,
+                             int n, float* pts4, float* dirs, float* dists, hn_stream_t stream);
+HN_API int hn_outside_composite_fwd(const float* density, const float* raw_rgb, const float* dists, const float* background,
+                                    int64_t n_rays, int n, float* sampled_color, float* alpha, float* weights, float* color,
+                                    hn_stream_t stream);
+HN_API int hn_outside_composite_bwd(const float* density, const float* dists, const float* background,
+                                    const float* sampled_color, const float* alpha, const float* weights, int64_t n_rays, int n,
+                                    const float* g_color, const float* g_sampled_color, const float* g_alpha,
+                                    const float* g_weights, float* d_density, float* d_raw_rgb, hn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

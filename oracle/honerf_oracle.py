@@ -653,3 +653,32 @@ def stable_loss_from_sdf(hand_sdf, pts0):
             stable_loss = stable_loss + in_err + 0.05 * out_err
         stable_loss /= in_time
     return stable_loss
+
+
+# ------------------------------------------------------------------------------------------------
+# render_core_outside (background NeRF branch).  NOT in the HO-NeRF reference: utils/renderer.py:47,56 only store
+# n_outside and every config sets 0.  The north star names it, so it is restated from the semantics of the NeuS renderer
+# the reference derives from -- PARITY UNPINNED: no reference code, golden vector or test exists to pin this function to.
+# ------------------------------------------------------------------------------------------------
+def render_core_outside(rays_o, rays_d, z_vals, sample_dist, nerf, n_outside=1, background_rgb=None):
+    """z_vals [B,n] -> dict(color [B,3], sampled_color [B,n,3], alpha [B,n], weights [B,n]).  `nerf(pts, dirs)` returns
+    (density [B*n,1], raw rgb [B*n,3]); pts are the inverted-sphere coordinates (p / r, 1 / r), r = clip(|p|, 1, 1e10)."""
+    B, n = z_vals.shape
+    dists = z_vals[..., 1:] - z_vals[..., :-1]
+    dists = torch.cat([dists, torch.full_like(dists[..., :1], float(sample_dist))], -1)
+    mid_z_vals = z_vals + dists * 0.5
+    pts = rays_o[:, None, :] + rays_d[:, None, :] * mid_z_vals[..., :, None]
+    dis_to_center = torch.linalg.norm(pts, ord=2, dim=-1, keepdim=True).clip(1.0, 1e10)
+    pts = torch.cat([pts / dis_to_center, 1.0 / dis_to_center], dim=-1)
+    dirs = rays_d[:, None, :].expand(B, n, 3)
+    pts = pts.reshape(-1, 4)[:, : 3 + int(n_outside > 0)]
+    dirs = dirs.reshape(-1, 3)
+    density, sampled_color = nerf(pts, dirs)
+    sampled_color = torch.sigmoid(sampled_color)
+    alpha = 1.0 - torch.exp(-F.softplus(density.reshape(B, n)) * dists)
+    weights = alpha * torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    sampled_color = sampled_color.reshape(B, n, 3)
+    color = (weights[:, :, None] * sampled_color).sum(dim=1)
+    if background_rgb is not None:
+        color = color + background_rgb * (1.0 - weights.sum(dim=-1, keepdim=True))
+    return {"color": color, "sampled_color": sampled_color, "alpha": alpha, "weights": weights}

@@ -121,3 +121,34 @@ def test_nn_bruteforce_model_equals_ckdtree():
         want = torch.zeros(700, dtype=torch.bool)
         want[torch.from_numpy(np.unique(out_ids[near]))] = True
         assert torch.equal(flag[t], want)
+
+
+def test_render_core_outside_oracle_properties():
+    """oracle/honerf_oracle.render_core_outside is PARITY UNPINNED (the reference has no such method: utils/renderer.py:47,56
+    store n_outside and nothing reads it).  What can be checked without a reference: the inverted-sphere points lie in the
+    unit ball with 1/r in (0, 1], weights form a sub-probability, colour is a convex combination of the sampled colours and
+    the background, and a constant-density medium gives the closed-form transmittance."""
+    import honerf_oracle as O
+    import torch
+    g = torch.Generator().manual_seed(0)
+    B, n = 7, 40
+    o = torch.randn(B, 3, generator=g) * 0.3
+    d = torch.nn.functional.normalize(torch.randn(B, 3, generator=g), dim=-1)
+    z = torch.sort(1.0 + 5.0 * torch.rand(B, n, generator=g), dim=-1).values
+    seen = {}
+
+    def nerf(pts, dirs):
+        seen["pts"] = pts
+        return torch.full((pts.shape[0], 1), 2.0), torch.zeros(pts.shape[0], 3)
+    out = O.render_core_outside(o.double(), d.double(), z.double(), 0.1, nerf, 1, torch.tensor([1.0, 0.0, 0.0]).double())
+    p = seen["pts"]
+    assert p.shape == (B * n, 4) and float(p[:, :3].norm(dim=-1).max()) <= 1.0 + 1e-12 and float(p[:, 3].min()) > 0 and float(p[:, 3].max()) <= 1.0
+    w = out["weights"]
+    assert float(w.min()) >= 0 and float(w.sum(-1).max()) <= 1.0 + 1e-6
+    # constant sigma = softplus(2): transmittance after the ray = exp(-sigma * total length)
+    sigma = torch.nn.functional.softplus(torch.tensor(2.0)).double()
+    length = (z[:, -1] - z[:, 0]).double() + 0.1
+    assert torch.allclose(1.0 - w.sum(-1), torch.exp(-sigma * length), atol=1e-5)
+    # colour = 0.5 * sum w + background * (1 - sum w)
+    ws = w.sum(-1, keepdim=True)
+    assert torch.allclose(out["color"], 0.5 * ws + torch.tensor([1.0, 0.0, 0.0]).double() * (1 - ws), atol=1e-12)
