@@ -404,7 +404,7 @@ def forward_extras(H, device, renderer, batch, host, Ro, To, hand_rays_n):
         ro, rd = HR["rays_o"].to(device), HR["rays_d"].to(device)
         ms = _time_calls(lambda: rh.render(ro, rd, HR["near"], HR["far"], bt, T, None, None, None, 0))
         res["hand_render_fwd"] = {"rays": hand_rays_n, "ms": ms, "value": hand_rays_n / (ms * 1e-3), "unit": "rays/s",
-                                  "note": "hand field on the per-layer kernels (chain kernels: object field only)"}
+                                  "note": "hand SDF net through its chain kernels (csrc/chain16_hand.cu), hand colour net per layer"}
     return res
 
 

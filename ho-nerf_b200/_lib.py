@@ -102,6 +102,8 @@ PROTOTYPES = {
     "hn_sdf_hand_sdf": (c_int, [_mlp_p, P, P, P, c_int64, c_int64, P, P, c_int64, c_int, P]),
     "hn_sdf_hand_fwd": (c_int, [_mlp_p, P, P, P, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P, c_int64,
                                 c_int, P]),
+    "hn_sdf_hand_fwd_render": (c_int, [_mlp_p, P, P, P, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P, c_int64,
+                                c_int, P]),
     "hn_sdf_hand_bwd": (c_int, [_mlp_p, P, P, P, c_int64, c_int64, P, P, P, c_int64, P, P, c_int64, P, P, P,
                                 _grad_p, P, c_int64, c_int, P]),
     "hn_color_hand_stash_floats": (c_int64, [c_int64]),

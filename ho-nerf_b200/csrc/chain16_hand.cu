@@ -272,7 +272,7 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
 struct HandNsweepParams {
     uint32_t* dbg;
     int64_t n;
-    uint8_t* D16[8];
+    uint8_t* D16[8];         // NULL entries: nothing will be differentiated (rendering), the tiles are not written
     float* FB;               // column-major tiles [tile][1388][128] fp32: D_4 W_4[:, 256:] + D_0 W_0
     const uint8_t* chain;
     const float* w_out0;
@@ -339,11 +339,13 @@ hand_nsweep16_kernel(const __grid_constant__ HandNsweepParams p, const __grid_co
                     sw_st16(tmem, lane_base, SW_A0, c, hi8);
                     sw_st16(tmem, lane_base, SW_A1, c, lo8);
                 }
-                uint4 q0, q1;
-                q0.x = pack_bf16x2(d[0], d[1]); q0.y = pack_bf16x2(d[2], d[3]); q0.z = pack_bf16x2(d[4], d[5]); q0.w = pack_bf16x2(d[6], d[7]);
-                q1.x = pack_bf16x2(d[8], d[9]); q1.y = pack_bf16x2(d[10], d[11]); q1.z = pack_bf16x2(d[12], d[13]); q1.w = pack_bf16x2(d[14], d[15]);
-                stg16(p.D16[lyr] + tb + t16_off(row, c >> 3), q0);
-                stg16(p.D16[lyr] + tb + t16_off(row, (c >> 3) + 1), q1);
+                if (p.D16[lyr]) {
+                    uint4 q0, q1;
+                    q0.x = pack_bf16x2(d[0], d[1]); q0.y = pack_bf16x2(d[2], d[3]); q0.z = pack_bf16x2(d[4], d[5]); q0.w = pack_bf16x2(d[6], d[7]);
+                    q1.x = pack_bf16x2(d[8], d[9]); q1.y = pack_bf16x2(d[10], d[11]); q1.z = pack_bf16x2(d[12], d[13]); q1.w = pack_bf16x2(d[14], d[15]);
+                    stg16(p.D16[lyr] + tb + t16_off(row, c >> 3), q0);
+                    stg16(p.D16[lyr] + tb + t16_off(row, (c >> 3) + 1), q1);
+                }
             };
             float* __restrict__ fb_tile = p.FB + (size_t)tile * (1388 * TILE_M);
             auto load_sp16 = [&](int hf, int c, float* sp) {       // s' = 1 - (em_hi + em_lo) of 16 columns, from the input slot
@@ -679,7 +681,7 @@ int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8
     }
     HandNsweepParams p;
     p.n = n; p.FB = FB; p.dbg = dbg_slot(1);
-    for (int l = 0; l < 8; ++l) p.D16[l] = D16[l];
+    for (int l = 0; l < 8; ++l) p.D16[l] = D16 ? D16[l] : nullptr;
     p.chain = ops;
     p.w_out0 = m->W[8];
     p.n_tiles = n_tiles;

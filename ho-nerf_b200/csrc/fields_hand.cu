@@ -567,6 +567,19 @@ int hn_sdf_hand_sdf(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
     return HN_OK;
 }
 
+static thread_local bool t_hand_render_only = false;
+
+int hn_sdf_hand_fwd_render(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, const float* T_pose, int64_t n,
+                           int64_t pts_per_frame, float* sdf, float* feat, int64_t ld_feat, float* normal,
+                           float* xyz_feature, int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
+                           hn_stream_t stream) {
+    t_hand_render_only = true;
+    const int r = hn_sdf_hand_fwd(mlp, pts, bt_inv, T_pose, n, pts_per_frame, sdf, feat, ld_feat, normal, xyz_feature, ld_xyz, stash,
+                                  stash_floats, precision, stream);
+    t_hand_render_only = false;
+    return r;
+}
+
 int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, const float* T_pose, int64_t n,
                     int64_t pts_per_frame, float* sdf, float* feat, int64_t ld_feat, float* normal,
                     float* xyz_feature, int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
@@ -597,7 +610,7 @@ int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
             count_launch();
             HN_CHECK_LAUNCH();
         }
-        HN_PROPAGATE(chain::launch_hand16_nsweep(mlp, ops, n, h.EM, h.EML, h.D16, h.FB, s));
+        HN_PROPAGATE(chain::launch_hand16_nsweep(mlp, ops, n, h.EM, h.EML, t_hand_render_only ? nullptr : h.D16, h.FB, s));
         halo_normal_tiled_kernel<<<nblocks(n, HALO_TP), HALO_TP, 0, s>>>(pts, bt_inv, T_pose, h.FB, n, pts_per_frame, normal);
         count_launch();
         HN_CHECK_LAUNCH();
@@ -817,38 +830,69 @@ namespace hn {
 
 constexpr int HCIN_LD = 1672, HCIN_OFF_FEAT = 1388, HCIN_OFF_NRM = 1644, HCIN_DIM = 1671;
 
-__global__ void color_hand_input_kernel(const float* __restrict__ xyz, int64_t ld_xyz, const float* __restrict__ feat,
+// one thread per float4 of a [n, 1672] input row; the feature and encoding blocks start at multiples of 4 (1388, 1644) and the
+// xyz rows are 16-byte aligned whenever vec_xyz (a view of the SDF stash, ld 1644)
+__global__ void color_hand_input_kernel(const float* __restrict__ xyz, int64_t ld_xyz, int vec_xyz, const float* __restrict__ feat,
                                         int64_t ld_feat, const float* __restrict__ normal, int64_t n,
                                         float* __restrict__ CIN) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * HCIN_LD) return;
-    int64_t p = i / HCIN_LD;
-    int j = (int)(i - p * HCIN_LD);
-    float v = 0.0f;
-    if (j < HALO_DIM) v = xyz[p * ld_xyz + j];
-    else if (j >= HCIN_OFF_FEAT && j < HCIN_OFF_NRM) v = feat[p * ld_feat + (j - HCIN_OFF_FEAT)];
-    else if (j >= HCIN_OFF_NRM && j < HCIN_DIM) {
+    constexpr int Q = HCIN_LD / 4;      // 418 float4 per row
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * Q) return;
+    const int64_t p = i / Q;
+    const int q = (int)(i - p * Q), j = q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j + 3 < HALO_DIM) {
+        const float* s = xyz + p * ld_xyz + j;
+        v = vec_xyz ? *reinterpret_cast<const float4*>(s) : make_float4(s[0], s[1], s[2], s[3]);
+    } else if (j < HALO_DIM) {          // 1384..1387: two feature values, then the 2-column gap
+        v.x = xyz[p * ld_xyz + j];
+        v.y = xyz[p * ld_xyz + j + 1];
+    } else if (j >= HCIN_OFF_FEAT && j < HCIN_OFF_NRM) {
+        v = *reinterpret_cast<const float4*>(feat + p * ld_feat + (j - HCIN_OFF_FEAT));
+    } else if (j >= HCIN_OFF_NRM) {
         const float x[3] = {normal[p * 3], normal[p * 3 + 1], normal[p * 3 + 2]};
-        v = enc3_col(x, 4, j - HCIN_OFF_NRM);
+        const int c = j - HCIN_OFF_NRM;
+        v.x = enc3_col(x, 4, c);
+        v.y = enc3_col(x, 4, c + 1);
+        v.z = enc3_col(x, 4, c + 2);
+        v.w = c + 3 < HCIN_DIM - HCIN_OFF_NRM ? enc3_col(x, 4, c + 3) : 0.0f;
     }
-    CIN[i] = v;
+    *reinterpret_cast<float4*>(CIN + p * HCIN_LD + j) = v;
 }
 
+// scatter of the first layer's input cotangent DCIN [n, 1672]: one thread per float4 of the xyz / feature blocks (vec: both
+// destinations 16-byte aligned with ld % 4 == 0), three more threads per point for the normal through J_enc^T
 __global__ void color_hand_input_bwd_kernel(const float* __restrict__ CIN, const float* __restrict__ DCIN, int64_t n,
                                             float* __restrict__ d_xyz, int64_t ld_dxyz, float* __restrict__ d_feat,
-                                            int64_t ld_dfeat, float* __restrict__ d_normal) {
-    const int per = HALO_DIM + 256 + 3;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                            int64_t ld_dfeat, float* __restrict__ d_normal, int vec) {
+    constexpr int QX = (HALO_DIM + 3) / 4, QF = 64, per = QX + QF + 3;      // 347 + 64 + 3
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n * per) return;
-    int64_t p = i / per;
-    int j = (int)(i - p * per);
+    const int64_t p = i / per;
+    const int q = (int)(i - p * per);
     const float* g = DCIN + p * HCIN_LD;
-    if (j < HALO_DIM) {
-        if (d_xyz) d_xyz[p * ld_dxyz + j] = g[j];
-    } else if (j < HALO_DIM + 256) {
-        if (d_feat) d_feat[p * ld_dfeat + (j - HALO_DIM)] = g[HCIN_OFF_FEAT + (j - HALO_DIM)];
+    if (q < QX) {
+        if (!d_xyz) return;
+        const int j = q * 4;
+        const float4 v = *reinterpret_cast<const float4*>(g + j);
+        float* o = d_xyz + p * ld_dxyz + j;
+        if (vec && j + 3 < HALO_DIM) {
+            *reinterpret_cast<float4*>(o) = v;
+        } else {
+            const float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (j + k < HALO_DIM) o[k] = t[k];
+        }
+    } else if (q < QX + QF) {
+        if (!d_feat) return;
+        const int j = (q - QX) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(g + HCIN_OFF_FEAT + j);
+        float* o = d_feat + p * ld_dfeat + j;
+        if (vec) *reinterpret_cast<float4*>(o) = v;
+        else { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
     } else if (d_normal) {
-        int c = j - HALO_DIM - 256;
+        const int c = q - QX - QF;
         d_normal[p * 3 + c] = enc3_jt_from_enc(CIN + p * HCIN_LD + HCIN_OFF_NRM, g + HCIN_OFF_NRM, 4, c);
     }
 }
@@ -904,7 +948,9 @@ int hn_color_hand_fwd(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_
     float* CIN = stash;
     float* R[4];
     for (int l = 0; l < 4; ++l) R[l] = stash + n * HCIN_LD + (int64_t)l * n * 256;
-    color_hand_input_kernel<<<nblocks(n * HCIN_LD, 256), 256, 0, s>>>(xyz_feature, ld_xyz, feat, ld_feat, normal, n, CIN);
+    HN_REQUIRE(ld_feat % 4 == 0 && aligned16(feat), "hn_color_hand_fwd: feat must be 16-byte aligned with ld %% 4 == 0");
+    const int vec_xyz = (aligned16(xyz_feature) && ld_xyz % 4 == 0) ? 1 : 0;
+    color_hand_input_kernel<<<nblocks(n * (HCIN_LD / 4), 256), 256, 0, s>>>(xyz_feature, ld_xyz, vec_xyz, feat, ld_feat, normal, n, CIN);
     count_launch();
     HN_CHECK_LAUNCH();
     for (int l = 0; l < 4; ++l) {
@@ -972,8 +1018,10 @@ int hn_color_hand_bwd(const hn_mlp_t* mlp, int64_t n, float* stash, const float*
         g.A = dz; g.lda = 256; set_w(g, mlp, 0);
         g.M = (int)n; g.N = HCIN_DIM; g.K = 256; g.C = DCIN; g.ldc = HCIN_LD;
         HN_PROPAGATE((gemm_nn<EPI_STORE>(g, s, precision)));
-        color_hand_input_bwd_kernel<<<nblocks(n * (HALO_DIM + 256 + 3), 256), 256, 0, s>>>(CIN, DCIN, n, d_xyz_feature, ld_dxyz,
-                                                                                          d_feat, ld_dfeat, d_normal);
+        const int vec = ((!d_xyz_feature || (aligned16(d_xyz_feature) && ld_dxyz % 4 == 0)) &&
+                         (!d_feat || (aligned16(d_feat) && ld_dfeat % 4 == 0))) ? 1 : 0;
+        color_hand_input_bwd_kernel<<<nblocks(n * ((HALO_DIM + 3) / 4 + 64 + 3), 256), 256, 0, s>>>(
+            CIN, DCIN, n, d_xyz_feature, ld_dxyz, d_feat, ld_dfeat, d_normal, vec);
         count_launch();
         HN_CHECK_LAUNCH();
     }

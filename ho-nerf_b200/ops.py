@@ -475,7 +475,7 @@ class _SdfHandFn(torch.autograd.Function):
     """(sdf, feature, normal, xyz_feature) = f(pts, bt_inv, T_pose_21, params)."""
 
     @staticmethod
-    def forward(ctx, pts, bt_inv, T_pose, ppf, packed, precision, *params):
+    def forward(ctx, pts, bt_inv, T_pose, ppf, packed, precision, differentiable, *params):
         pts_c, bt_c, T_c = _f32c(pts.detach()), _f32c(bt_inv.detach()), _f32c(T_pose.detach())
         _require_cuda(pts_c, "sdf_hand")
         pk = packed.get()
@@ -491,9 +491,9 @@ class _SdfHandFn(torch.autograd.Function):
         # backward only reads that part of the stash
         xyz = stash[:n * _HAND_ROW_LD].view(n, _HAND_ROW_LD)[:, 256:256 + 1386]
         if n > 0:
-            check(lib.hn_sdf_hand_fwd(ctypes.byref(pk.struct), _ptr(pts_c), _ptr(bt_c), _ptr(T_c), n, ppf, _ptr(sdf),
-                                      _ptr(feat), 256, _ptr(normal), None, 0, _ptr(stash), stf, precision,
-                                      _stream(pts_c)), "hn_sdf_hand_fwd")
+            fwd = lib.hn_sdf_hand_fwd if differentiable else lib.hn_sdf_hand_fwd_render
+            check(fwd(ctypes.byref(pk.struct), _ptr(pts_c), _ptr(bt_c), _ptr(T_c), n, ppf, _ptr(sdf), _ptr(feat), 256, _ptr(normal),
+                      None, 0, _ptr(stash), stf, precision, _stream(pts_c)), "hn_sdf_hand_fwd")
         ctx.packed, ctx.stash, ctx.n, ctx.ppf, ctx.precision, ctx.struct = pk, stash, n, ppf, precision, pk.struct
         ctx.pkey = pk._key
         ctx.pts_c, ctx.bt_c, ctx.T_c = pts_c, bt_c, T_c
@@ -530,7 +530,7 @@ class _SdfHandFn(torch.autograd.Function):
         elif d_pts is not None:
             d_pts.zero_()
         ctx.stash = None
-        return (d_pts, d_bt, d_T, None, None, None) + tuple(grads)
+        return (d_pts, d_bt, d_T, None, None, None, None) + tuple(grads)
 
 
 def sdf_hand(packed, pts, bt_inv, T_pose_21, precision=None):
@@ -543,7 +543,10 @@ def sdf_hand(packed, pts, bt_inv, T_pose_21, precision=None):
         # a call whose backward trains the net stays on the per-layer contractions with their fp32 stash
         precision = _lib.HN_TC_BF16X3
     pts2, bt, T, ppf = _hand_pose_args(pts, bt_inv, T_pose_21)
-    return _SdfHandFn.apply(pts2, bt, T, ppf, packed, precision, *params)
+    # nothing to differentiate (rendering): the operator skips what only its backward would read
+    differentiable = torch.is_grad_enabled() and (pts2.requires_grad or bt.requires_grad or T.requires_grad or
+                                                  any(p.requires_grad for p in params))
+    return _SdfHandFn.apply(pts2, bt, T, ppf, packed, precision, differentiable, *params)
 
 
 class _ColorHandFn(torch.autograd.Function):

@@ -248,6 +248,13 @@ HN_API int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* b
                            float* feat, int64_t ld_feat, float* normal, float* xyz_feature,
                            int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
                            hn_stream_t stream);
+/* Same call for a forward that will never be differentiated (rendering under no_grad): the stash is still the scratch of the
+ * call (same size), but what only hn_sdf_hand_bwd would read is not written (HN_TC_MIXED16: the D16 tiles of the normal sweep). */
+HN_API int hn_sdf_hand_fwd_render(const hn_mlp_t* mlp, const float* pts, const float* bt_inv,
+                           const float* T_pose, int64_t n_pts, int64_t pts_per_frame, float* sdf,
+                           float* feat, int64_t ld_feat, float* normal, float* xyz_feature,
+                           int64_t ld_xyz, float* stash, int64_t stash_floats, int precision,
+                           hn_stream_t stream);
 HN_API int hn_sdf_hand_bwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv,
                            const float* T_pose, int64_t n_pts, int64_t pts_per_frame, float* stash,
                            const float* d_sdf, const float* d_feat, int64_t ld_dfeat,
