@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(128) out_row0_grad16_kernel(const uint8_t* __r
 
 int launch_out_row0_grad16(const uint8_t* H7, const uint8_t* U7, const float* d_sdf, int64_t n, int n_tiles, float inv_scale,
                            float* dW_row0, float* db0, cudaStream_t s) {
-    const int splits = std::max(1, std::min(n_tiles, 8));
+    const int splits = std::max(1, std::min(n_tiles, 64));
     out_row0_grad16_kernel<<<dim3(32, splits), 128, 0, s>>>(H7, U7, d_sdf, n, n_tiles, inv_scale, dW_row0, db0);
     count_launch();
     HN_CHECK_LAUNCH();

@@ -575,7 +575,7 @@ int launch_color_bwd(const hn_mlp_t* m, int64_t n, const float* stash, const flo
         dp.n_jobs = k;
         HN_PROPAGATE(launch_dw16(dp, rp, s));
         if (grad->dW[4] || grad->db[4]) {
-            const int splits = std::max(1, std::min(p.n_tiles, 8));
+            const int splits = std::max(1, std::min(p.n_tiles, 64));
             color_out_grad16_kernel<<<dim3(32, splits), 128, 0, s>>>(S.R16[3], color_dw_x3() ? S.R16[3] + S.lo_off : nullptr, p.DZ4, n, p.n_tiles,
                                                                      grad->dW[4], m->ld[4], grad->db[4]);
             count_launch();
