@@ -24,8 +24,8 @@ namespace chain {
 // ------------------------------------------------------------------------------------------------------------------
 // value trunk (layers 1..7 + feature head); TMEM columns [0,256) accumulator, [256,384) A_hi, [384,512) A_lo
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int HT_STAGE_BYTES = 128 * 128;
-constexpr int HT_STAGES = 12;
+constexpr int HT_STAGE_BYTES = 256 * 128;        // 32 KB: one k-block of a feature tile (hi + lo) or 256 weight rows; half steps use 16 KB
+constexpr int HT_STAGES = 6;
 constexpr int HT_HEAD_OFF = HT_STAGES * HT_STAGE_BYTES;
 constexpr int HT_SMEM_BYTES = HT_HEAD_OFF + EPI_CGROUPS * TILE_M * 4 + 1024;
 constexpr uint32_t HT_A_HI = 256, HT_A_LO = 384;
@@ -38,8 +38,26 @@ struct HtBarriers {
     uint32_t tmem_base;
 };
 
+// One MMA step of the trunk.  Half steps (ts form): acc[:, 128 h .. +128] = A (tensor memory, hi + lo fp16) @ B^T, B = 128 weight
+// rows x 64 k per stage (hi stage, lo stage).  Feature steps (ss form): acc[:, 0 .. 256] (+)= F @ B^T over 22 k-blocks, A = the
+// fp16 pair tiles of the HALO feature bulk-copied from HBM (one 32 KB stage per k-block), B = 256 weight rows (hi stage, lo stage).
+struct HtStep {
+    uint32_t b_off;
+    uint16_t acc_col;
+    uint8_t kblocks;
+    uint8_t feature : 1;     // ss form over the feature tiles
+    uint8_t no_wait : 1;     // do not wait for a_ready (second half of a layer / the feature part of the skip layer)
+    uint8_t acc_in : 1;      // accumulate onto what the accumulator holds
+    uint8_t commit : 2;      // 0: none (more MMAs of this layer follow), 1: this half's acc_full, 2: both
+};
+struct HtProgram {
+    int n_steps;
+    HtStep step[20];
+};
+
 struct HandTrunkParams {
     int64_t n;
+    const uint8_t* F16;      // fp16 pair tiles of the HALO feature (halo_feature16_kernel); NULL: legacy inputs H0 / ZF4
     const float* H0;         // [np, 256] fp32 rows
     const float* ZF4;        // [np, 256] fp32 rows: the feature part of the skip layer's pre-activation
     float* sdf;
@@ -54,7 +72,7 @@ struct HandTrunkParams {
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_constant__ Program prog) {
+hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_constant__ HtProgram prog) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ HtBarriers bar;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -81,52 +99,101 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int t = 0; t < n_my_tiles; ++t)
+            auto put = [&](const uint8_t* src, uint32_t bytes) {
+                tc::mbar_wait(&bar.empty[stage], phase ^ 1u);
+                tc::mbar_arrive_expect_tx(&bar.full[stage], bytes);
+                tc::bulk_g2s(smem + stage * HT_STAGE_BYTES, src, bytes, &bar.full[stage]);
+                if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+            };
+            for (int t = 0; t < n_my_tiles; ++t) {
+                const uint8_t* ftile = p.F16 + ((size_t)blockIdx.x + (size_t)t * gridDim.x) * HAND_F16_TILE_BYTES;
                 for (int s = 0; s < prog.n_steps; ++s) {
-                    const uint8_t* src = p.chain + prog.step[s].b_off;
-                    for (int c = 0; c < 2 * prog.step[s].kblocks; ++c) {
-                        tc::mbar_wait(&bar.empty[stage], phase ^ 1u);
-                        tc::mbar_arrive_expect_tx(&bar.full[stage], HT_STAGE_BYTES);
-                        tc::bulk_g2s(smem + stage * HT_STAGE_BYTES, src + (size_t)c * HT_STAGE_BYTES, HT_STAGE_BYTES, &bar.full[stage]);
-                        if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                    const HtStep st = prog.step[s];
+                    const uint8_t* src = p.chain + st.b_off;
+                    if (st.feature) {
+                        for (int kb = 0; kb < st.kblocks; ++kb) {
+                            put(ftile + (size_t)kb * HAND_F16_KB_BYTES, HAND_F16_KB_BYTES);      // A: hi tile + lo tile
+                            put(src + (size_t)kb * 65536, 32768);                                // B hi: 256 rows
+                            put(src + (size_t)kb * 65536 + 32768, 32768);                        // B lo
+                        }
+                    } else {
+                        for (int c = 0; c < 2 * st.kblocks; ++c) put(src + (size_t)c * 16384, 16384);
                     }
                 }
+            }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t ring = tc::smem_u32(smem);
-            const uint32_t idesc = tc::make_idesc(tc::FMT_F16, 128, 128);
+            const uint32_t idesc_half = tc::make_idesc(tc::FMT_F16, 128, 128), idesc_full = tc::make_idesc(tc::FMT_F16, 128, 256);
             uint32_t stage = 0, phase = 0, a_par = 0;
+            auto next = [&]() {
+                const uint32_t addr = ring + stage * HT_STAGE_BYTES;
+                tc::mbar_wait(&bar.full[stage], phase);
+                return addr;
+            };
+            auto release = [&]() {
+                tc::umma_commit(&bar.empty[stage]);
+                if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+            };
             for (int t = 0; t < n_my_tiles; ++t)
                 for (int s = 0; s < prog.n_steps; ++s) {
-                    const Step st = prog.step[s];
+                    const HtStep st = prog.step[s];
                     const uint32_t d = tmem + st.acc_col;
                     if (!st.no_wait) {
                         tc::mbar_wait(&bar.a_ready, a_par);
                         a_par ^= 1u;
                         tc::tc_fence_after_sync();
                     }
-                    for (int kb = 0; kb < st.kblocks; ++kb) {
-                        const uint32_t ah = tmem + HT_A_HI + (uint32_t)kb * 32, al = tmem + HT_A_LO + (uint32_t)kb * 32;
-                        tc::mbar_wait(&bar.full[stage], phase);
-                        tc::tc_fence_after_sync();
-                        uint64_t dB = tc::make_smem_desc_sw128(ring + stage * HT_STAGE_BYTES);
+                    if (st.feature) {
+                        for (int kb = 0; kb < st.kblocks; ++kb) {
+                            // three stages per k-block, all released by commits behind the k-block's last MMA
+                            const uint32_t a_addr = next();
+                            const uint32_t st_a = stage;
+                            if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                            const uint32_t bh_addr = next();
+                            const uint32_t st_bh = stage;
+                            if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                            const uint32_t bl_addr = next();
+                            const uint32_t st_bl = stage;
+                            if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                            tc::tc_fence_after_sync();
+                            const uint64_t dAh = tc::make_smem_desc_sw128(a_addr), dAl = tc::make_smem_desc_sw128(a_addr + 16384);
+                            const uint64_t dBh = tc::make_smem_desc_sw128(bh_addr), dBl = tc::make_smem_desc_sw128(bl_addr);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            tc::umma_f16_ts(d, al + 8 * k, dB + 2 * k, idesc, (kb | k) != 0);
-                            tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc, 1);
+                            for (int k = 0; k < 4; ++k) {
+                                tc::umma_f16(d, dAl + 2 * k, dBh + 2 * k, idesc_full, (kb | k | st.acc_in) != 0);
+                                tc::umma_f16(d, dAh + 2 * k, dBh + 2 * k, idesc_full, 1);
+                                tc::umma_f16(d, dAh + 2 * k, dBl + 2 * k, idesc_full, 1);
+                            }
+                            tc::umma_commit(&bar.empty[st_a]);
+                            tc::umma_commit(&bar.empty[st_bh]);
+                            tc::umma_commit(&bar.empty[st_bl]);
                         }
-                        tc::umma_commit(&bar.empty[stage]);
-                        if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
-                        tc::mbar_wait(&bar.full[stage], phase);
-                        tc::tc_fence_after_sync();
-                        dB = tc::make_smem_desc_sw128(ring + stage * HT_STAGE_BYTES);
+                    } else {
+                        for (int kb = 0; kb < st.kblocks; ++kb) {
+                            const uint32_t ah = tmem + HT_A_HI + (uint32_t)kb * 32, al = tmem + HT_A_LO + (uint32_t)kb * 32;
+                            uint64_t dB = tc::make_smem_desc_sw128(next());
+                            tc::tc_fence_after_sync();
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc, 1);
-                        tc::umma_commit(&bar.empty[stage]);
-                        if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+                            for (int k = 0; k < 4; ++k) {
+                                tc::umma_f16_ts(d, al + 8 * k, dB + 2 * k, idesc_half, (kb | k | st.acc_in) != 0);
+                                tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc_half, 1);
+                            }
+                            release();
+                            dB = tc::make_smem_desc_sw128(next());
+                            tc::tc_fence_after_sync();
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) tc::umma_f16_ts(d, ah + 8 * k, dB + 2 * k, idesc_half, 1);
+                            release();
+                        }
                     }
-                    tc::umma_commit(&bar.acc_full[st.acc_col ? 1 : 0]);
+                    if (st.commit == 2) {
+                        tc::umma_commit(&bar.acc_full[0]);
+                        tc::umma_commit(&bar.acc_full[1]);
+                    } else if (st.commit == 1) {
+                        tc::umma_commit(&bar.acc_full[st.acc_col ? 1 : 0]);
+                    }
                 }
         }
     } else {
@@ -172,7 +239,7 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
                 const float* __restrict__ bias = p.bias[l];
                 float v[32];
                 acc_load32(tmem, row, col0, v);
-                if (l == 4 && live) {
+                if (l == 4 && live && !p.F16) {
                     const float* __restrict__ z = p.ZF4 + gp * 256 + col0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -196,9 +263,11 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
                     }
                 }
             };
-            // ---- layer 0's activation rows (the feature contraction ran before this kernel) -> first A operand -----------
+            // ---- layer 0: with the feature tiles it is an MMA step like the others (this arrival only tells the issuer that the
+            //      previous tile's accumulator has been read); legacy inputs: its activation rows were computed before this
+            //      kernel and become the first A operand here
 #pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = 0; hf < (p.F16 ? 0 : 2); ++hf) {
                 const int col0 = 128 * hf + cg * 32;
                 uint32_t hh[16], hl[16];
                 const float* __restrict__ hrow = p.H0 + gp * 256 + col0;
@@ -217,7 +286,7 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
             }
             publish();
             float head = 0.0f;
-            for (int l = 1; l < 8; ++l) {
+            for (int l = p.F16 ? 0 : 1; l < 8; ++l) {
                 uint32_t hh[16], hl[16];
                 // first half (columns cg*32 ..) under the second half's MMAs
                 wait_acc(0);
@@ -620,9 +689,9 @@ hand_bwd16_kernel(const __grid_constant__ HandBwdParams p, const __grid_constant
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-// stash (floats per padded point): HROW 1644 | FB 1388 | RA 256 | RB 256 | EM[8] | EML[8] | D16[8] (128 floats each)
-//   RA: H0, RB: ZF4 (inputs of the trunk)
-int64_t hand16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 512 + 24 * 128); }
+// stash (floats per padded point): HROW 1644 | FB 1388 | RA 256 | RB 256 | EM[8] | EML[8] | D16[8] (128 floats each) | F16 1408
+//   RA: H0, RB: ZF4 (legacy inputs of the trunk); F16: the fp16 pair tiles of the HALO feature (22 k-blocks x 64 x 2 x 2 bytes)
+int64_t hand16_stash_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 512 + 24 * 128 + 1408); }
 // backward workspace: AU4 1644 | DF 1388 | Q0 | QF4 (256 each) | X16[8]
 int64_t hand16_bwd_ws_floats(int64_t n) { return round_up(n, TILE_M) * (1644 + 1388 + 512 + 8 * 128); }
 
@@ -635,8 +704,8 @@ static void sw_layer(SwProgram& prog, int& k, uint32_t off, int n_mma, int kbloc
     st.acc_in = 0;
 }
 
-int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const float* H0, const float* ZF4, float* sdf,
-                        float* feat, int64_t ld_feat, uint8_t* const* EM, uint8_t* const* EML, cudaStream_t s) {
+int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const uint8_t* F16, const float* H0, const float* ZF4,
+                        float* sdf, float* feat, int64_t ld_feat, uint8_t* const* EM, uint8_t* const* EML, cudaStream_t s) {
     const HandLayout L = hand_layout();
     const int n_tiles = (int)ceil_div(n, TILE_M);
     static bool configured = false;
@@ -645,24 +714,29 @@ int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const 
         configured = true;
     }
     HandTrunkParams p;
-    p.n = n; p.H0 = H0; p.ZF4 = ZF4; p.sdf = sdf; p.feat = feat; p.ld_feat = ld_feat;
+    p.n = n; p.F16 = F16; p.H0 = H0; p.ZF4 = ZF4; p.sdf = sdf; p.feat = feat; p.ld_feat = ld_feat;
     for (int l = 0; l < 8; ++l) { p.EM[l] = EM ? EM[l] : nullptr; p.EML[l] = EML ? EML[l] : nullptr; }
     p.chain = ops;
     for (int l = 0; l < 9; ++l) p.bias[l] = m->b[l];
     p.w_out0 = m->W[8];
     p.n_tiles = n_tiles;
-    Program prog = {};
+    HtProgram prog = {};
     int k = 0;
-    for (int l = 1; l <= (feat ? 8 : 7); ++l)
+    auto feature_step = [&](int which, bool first) {
+        HtStep& st = prog.step[k++];
+        st.b_off = L.ntf16_off[which]; st.acc_col = 0; st.kblocks = HAND_F_KBLOCKS;
+        st.feature = 1; st.no_wait = first ? 0 : 1; st.acc_in = first ? 0 : 1; st.commit = 2;
+    };
+    if (F16) feature_step(0, true);                                   // layer 0: F @ W_0^T
+    for (int l = 1; l <= (feat ? 8 : 7); ++l) {
         for (int h = 0; h < 2; ++h) {
-            Step& st = prog.step[k++];
-            st.b_off = L.nth_off[l][h];
-            st.n_mma = 128;
-            st.kblocks = 4;
-            st.f16 = 1;
-            st.no_wait = (uint8_t)h;
-            st.acc_col = (uint16_t)(128 * h);
+            HtStep& st = prog.step[k++];
+            st.b_off = L.nth_off[l][h]; st.acc_col = (uint16_t)(128 * h); st.kblocks = 4;
+            st.feature = 0; st.no_wait = (uint8_t)h; st.acc_in = 0;
+            st.commit = (F16 && l == 4) ? 0 : 1;                      // the skip layer's accumulator is complete after its feature part
         }
+        if (F16 && l == 4) feature_step(1, false);                    // + F @ W_4[:, 256:]^T onto both halves
+    }
     prog.n_steps = k;
     hand_trunk16_kernel<<<std::min(n_tiles, sm_count()), THREADS, HT_SMEM_BYTES, s>>>(p, prog);
     count_launch();
@@ -760,6 +834,9 @@ int hand16_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s) {
         }
         HN_PROPAGATE(launch_pack_b(m->WT[l], m->ldT[l], pack_map(0, row0), 256, 256, 256, 4, dst + L.nn_off[l], s));
     }
+    // feature-side INPUT contractions of the value trunk: B(n = output, k = feature) from W_0 and W_4[:, 256:], fp16 pairs
+    HN_PROPAGATE(launch_pack_b(m->W[0], m->ld[0], pack_map(0, 0), 256, 1386, 256, HAND_F_KBLOCKS, dst + L.ntf16_off[0], s, true));
+    HN_PROPAGATE(launch_pack_b(m->W[4], m->ld[4], pack_map(0, 256), 256, 1386, 256, HAND_F_KBLOCKS, dst + L.ntf16_off[1], s, true));
     // feature-side chunks: rows = features of WT_4 (after the 256 h3 rows) / WT_0
     for (int w = 0; w < 2; ++w)
         for (int ch = 0; ch < HAND_F_CHUNKS; ++ch) {

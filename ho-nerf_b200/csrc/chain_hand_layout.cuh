@@ -18,8 +18,14 @@ struct HandLayout {
     // [0]: d @ W_4[:, 256:], [1]: d @ W_0;  B(n = feature, k = output)
     uint32_t nnf16_off[2][6];   // fp16 pairs (normal sweep -> FB)
     uint32_t nnf_off[2][6];     // bf16 pairs (reverse sweep -> DF)
+    // feature-side contractions INTO the chain (value trunk): F @ W_0^T ([0]) and F @ W_4[:, 256:]^T ([1]) as fp16 pairs,
+    // B(n = output 256, k = feature, 22 k-blocks of 64 = 1408 >= 1386); A = the fp16 pair tiles halo_feature16 writes
+    uint32_t ntf16_off[2];
     uint32_t total;
 };
+constexpr int HAND_F_KBLOCKS = 22;
+constexpr int HAND_F16_KB_BYTES = 2 * 128 * 128;                           // one k-block of a 128-point feature tile: hi + lo, 32 KB
+constexpr int HAND_F16_TILE_BYTES = HAND_F_KBLOCKS * HAND_F16_KB_BYTES;    // 704 KB per 128 points
 constexpr int HAND_F_CHUNKS = 6;
 __host__ __device__ inline int hand_f_chunk_n(int ch) { return ch < 5 ? 256 : 112; }       // UMMA N of chunk ch
 __host__ __device__ inline int hand_f_chunk_valid(int ch) { return ch < 5 ? 256 : 106; }   // features in chunk ch
@@ -35,6 +41,7 @@ inline HandLayout hand_layout() {
         for (int ch = 0; ch < 6; ++ch) { L.nnf16_off[w][ch] = off; off += b_operand_bytes(ch < 5 ? 256 : 112, 4); }
     for (int w = 0; w < 2; ++w)
         for (int ch = 0; ch < 6; ++ch) { L.nnf_off[w][ch] = off; off += b_operand_bytes(ch < 5 ? 256 : 112, 4); }
+    for (int w = 0; w < 2; ++w) { L.ntf16_off[w] = off; off += b_operand_bytes(256, 22); }
     L.total = off;
     return L;
 }

@@ -15,8 +15,8 @@
 namespace hn {
 
 namespace chain {      // chain16_hand.cu
-int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const float* H0, const float* ZF4, float* sdf,
-                        float* feat, int64_t ld_feat, uint8_t* const* EM, uint8_t* const* EML, cudaStream_t s);
+int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const uint8_t* F16, const float* H0, const float* ZF4,
+                        float* sdf, float* feat, int64_t ld_feat, uint8_t* const* EM, uint8_t* const* EML, cudaStream_t s);
 int launch_hand16_nsweep(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* EML,
                          uint8_t* const* D16, float* FB, cudaStream_t s);
 int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t* const* EM, uint8_t* const* D16,
@@ -53,6 +53,50 @@ __global__ void __launch_bounds__(HALO_WARPS * 32) halo_feature_kernel(
     float* o = out + p * ld;
     for (int i = lane; i < HALO_DIM; i += 32) o[i] = sm[warp][i];
     if (lane < 2) o[HALO_DIM + lane] = 0.0f;
+}
+
+// Same features, additionally (or only: out == NULL) as the fp16 hi / lo pair tiles the value trunk consumes straight from
+// shared memory (chain16_hand.cu): per 128-point tile 22 k-blocks of 64 features, each {hi tile, lo tile} of [128 rows x 128 B]
+// in the K-major SWIZZLE_128B UMMA layout; features 1386 .. 1407 and the rows past n are zero.  Launched over whole tiles.
+__global__ void __launch_bounds__(HALO_WARPS * 32) halo_feature16_kernel(
+    const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp, int64_t n,
+    int64_t ppf, float* __restrict__ out, int64_t ld, uint8_t* __restrict__ F16) {
+    constexpr int KPAD = chain::HAND_F_KBLOCKS * 64;      // 1408
+    __shared__ __align__(16) float sm[HALO_WARPS][KPAD];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t p = (int64_t)blockIdx.x * HALO_WARPS + warp;
+    const bool live = p < n;
+    for (int i = HALO_DIM + lane; i < KPAD; i += 32) sm[warp][i] = 0.0f;
+    if (live) {
+        const int64_t f = p / ppf;
+        float x[3];
+        load_x(pts, p, x);
+        if (lane < HALO_J) {
+            HaloBase b = halo_base(bt_inv + (f * HALO_J + lane) * 16, Tp + (f * HALO_J + lane) * 3, x, lane);
+            halo_feature(b, &sm[warp][lane * HALO_F]);
+        }
+    } else {
+        for (int i = lane; i < HALO_DIM; i += 32) sm[warp][i] = 0.0f;
+    }
+    __syncwarp();
+    if (out && live) {
+        float* o = out + p * ld;
+        for (int i = lane; i < HALO_DIM; i += 32) o[i] = sm[warp][i];
+        if (lane < 2) o[HALO_DIM + lane] = 0.0f;
+    }
+    uint8_t* tile = F16 + (size_t)(p >> 7) * chain::HAND_F16_TILE_BYTES;
+    const uint32_t r = (uint32_t)(p & 127);
+    for (int c = lane; c < KPAD / 8; c += 32) {          // 176 chunks of 8 features
+        const float4 a = *reinterpret_cast<const float4*>(&sm[warp][c * 8]), bq = *reinterpret_cast<const float4*>(&sm[warp][c * 8 + 4]);
+        uint4 hi, lo;
+        chain::split2_lo16(a.x, a.y, hi.x, lo.x);
+        chain::split2_lo16(a.z, a.w, hi.y, lo.y);
+        chain::split2_lo16(bq.x, bq.y, hi.z, lo.z);
+        chain::split2_lo16(bq.z, bq.w, hi.w, lo.w);
+        uint8_t* dst = tile + (size_t)(c >> 3) * chain::HAND_F16_KB_BYTES + tc::sw128_offset(r, (uint32_t)(c & 7));
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + 16384) = lo;
+    }
 }
 
 // tangent rows: out[p, 0:1386] = F'(x_p) (R dn_p)
@@ -458,6 +502,7 @@ static int hand_trunk_fwd(const hn_mlp_t* m, const float* pts, const float* bt_i
 struct Hand16Stash {
     float *HROW, *FB, *RA, *RB;      // RA: H0, then D0;  RB: ZF4, then D4
     uint8_t *EM[8], *EML[8], *D16[8];
+    uint8_t* F16;                    // fp16 pair tiles of the HALO feature (input of the value trunk)
     Hand16Stash(float* base, int64_t n) {
         const int64_t np = round_up(n, 128);
         float* p = base;
@@ -469,6 +514,7 @@ struct Hand16Stash {
         for (int l = 0; l < 8; ++l) { EM[l] = b; b += np * 512; }
         for (int l = 0; l < 8; ++l) { EML[l] = b; b += np * 512; }
         for (int l = 0; l < 8; ++l) { D16[l] = b; b += np * 512; }
+        F16 = b;
     }
 };
 static const uint8_t* hand16_ops(const hn_mlp_t* m) {
@@ -545,16 +591,13 @@ int hn_sdf_hand_sdf(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
                    aligned16(ws), "hn_sdf_hand_sdf: null pointer or workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     if (m16) {
+        // the feature goes straight into the trunk's fp16 pair tiles (no fp32 rows, no per-layer contraction)
         const int64_t np = round_up(n, 128);
-        float* HROW = ws;
-        float* H0 = HROW + np * HROW_LD;
-        float* ZF4 = H0 + np * 256;
-        halo_feature_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, n, pts_per_frame,
-                                                                               HROW + HFEAT_OFF, HROW_LD);
+        uint8_t* F16 = reinterpret_cast<uint8_t*>(ws);
+        halo_feature16_kernel<<<nblocks(np, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, n, pts_per_frame, nullptr, 0, F16);
         count_launch();
         HN_CHECK_LAUNCH();
-        HN_PROPAGATE(hand16_feature_in(mlp, HROW + HFEAT_OFF, n, H0, ZF4, true, s));
-        return chain::launch_hand16_trunk(mlp, hand16_ops(mlp), n, H0, ZF4, sdf, nullptr, 0, nullptr, nullptr, s);
+        return chain::launch_hand16_trunk(mlp, hand16_ops(mlp), n, F16, nullptr, nullptr, sdf, nullptr, 0, nullptr, nullptr, s);
     }
     float* HROW = ws;
     float* P0 = HROW + n * HROW_LD;
@@ -598,12 +641,12 @@ int hn_sdf_hand_fwd(const hn_mlp_t* mlp, const float* pts, const float* bt_inv, 
         // HN_TC_MIXED16: the 256 x 256 layers as tile-chain kernels (chain16_hand.cu), the 1386-wide ends per layer
         Hand16Stash h(stash, n);
         const uint8_t* ops = hand16_ops(mlp);
-        halo_feature_kernel<<<nblocks(n, HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, n, pts_per_frame,
-                                                                               h.HROW + HFEAT_OFF, HROW_LD);
+        // HALO feature once: fp32 rows (the colour net's xyz_feature, a view of the stash) + the trunk's fp16 pair tiles
+        halo_feature16_kernel<<<nblocks(round_up(n, 128), HALO_WARPS), HALO_WARPS * 32, 0, s>>>(pts, bt_inv, T_pose, n, pts_per_frame,
+                                                                                                h.HROW + HFEAT_OFF, HROW_LD, h.F16);
         count_launch();
         HN_CHECK_LAUNCH();
-        HN_PROPAGATE(hand16_feature_in(mlp, h.HROW + HFEAT_OFF, n, h.RA, h.RB, true, s));
-        HN_PROPAGATE(chain::launch_hand16_trunk(mlp, ops, n, h.RA, h.RB, sdf, feat, ld_feat, h.EM, h.EML, s));
+        HN_PROPAGATE(chain::launch_hand16_trunk(mlp, ops, n, h.F16, nullptr, nullptr, sdf, feat, ld_feat, h.EM, h.EML, s));
         if (xyz_feature) {
             copy_rows_kernel<<<nblocks(n * HALO_DIM, 256), 256, 0, s>>>(h.HROW + HFEAT_OFF, HROW_LD, n, HALO_DIM, xyz_feature,
                                                                         ld_xyz);
