@@ -267,31 +267,25 @@ __device__ __forceinline__ void halo_stage_add_rows(const float* __restrict__ ro
 __global__ void __launch_bounds__(HALO_TP) halo_normal_tiled_kernel(
     const float* __restrict__ pts, const float* __restrict__ bt_inv, const float* __restrict__ Tp,
     const float* __restrict__ FBt, int64_t n, int64_t ppf, float* __restrict__ normal) {
-    __shared__ float sc[HALO_F * HALO_TLD];
+    // The column-major tile IS the thread-per-point layout (a warp's 32 rows of a column are one 128-byte line, every value is
+    // read once): no staging through shared memory, no block-wide barrier.
     const int r = threadIdx.x;
     const int64_t p = (int64_t)blockIdx.x * HALO_TP + r;
-    const bool live = p < n;
-    const int64_t f = (live ? p : n - 1) / ppf;
-    float x[3] = {0.f, 0.f, 0.f}, acc[3] = {0.f, 0.f, 0.f};
-    if (live) load_x(pts, p, x);
-    const float* tile = FBt + (size_t)blockIdx.x * HALO_TILE_FLOATS;
+    if (p >= n) return;
+    const int64_t f = p / ppf;
+    float x[3], acc[3] = {0.f, 0.f, 0.f};
+    load_x(pts, p, x);
+    const float* tile = FBt + (size_t)blockIdx.x * HALO_TILE_FLOATS + r;
     for (int j = 0; j < HALO_J; ++j) {
         const float* M = bt_inv + (f * HALO_J + j) * 16;
         HaloBase b = halo_base(M, Tp + (f * HALO_J + j) * 3, x, j);
-        const bool on = live && !b.dead;
-        if (!__syncthreads_or(on)) continue;          // also orders the previous joint's reads of sc before the restaging
-        halo_stage_joint(tile, j, sc);
-        __syncthreads();
-        if (on) {
-            float g[3], dummy[3], w[3] = {0.f, 0.f, 0.f};
-            halo_grad_hvp<false, HALO_TLD>(b, sc + r, w, g, dummy);
+        if (b.dead) continue;
+        float g[3], dummy[3], w[3] = {0.f, 0.f, 0.f};
+        halo_grad_hvp<false, HALO_TP>(b, tile + (size_t)j * HALO_F * HALO_TP, w, g, dummy);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) acc[a] += M[0 * 4 + a] * g[0] + M[1 * 4 + a] * g[1] + M[2 * 4 + a] * g[2];
-        }
+        for (int a = 0; a < 3; ++a) acc[a] += M[0 * 4 + a] * g[0] + M[1 * 4 + a] * g[1] + M[2 * 4 + a] * g[2];
     }
-    if (live) {
-        normal[p * 3] = acc[0]; normal[p * 3 + 1] = acc[1]; normal[p * 3 + 2] = acc[2];
-    }
+    normal[p * 3] = acc[0]; normal[p * 3 + 1] = acc[1]; normal[p * 3 + 2] = acc[2];
 }
 
 // halo_bwd_kernel over tiled DF / FB; d_xyz (row-major, may be NULL) is added to DF while staging.  uniform_frame: every
@@ -319,24 +313,25 @@ __global__ void __launch_bounds__(HALO_TP) halo_bwd_tiled_kernel(
         HaloBase b = halo_base(M, Tp + (f * HALO_J + j) * 3, x, j);
         const bool on = live && !b.dead;
         if (!__syncthreads_or(on)) continue;
-        halo_stage_joint(dtile, j, sc);
+        // DF: straight from its column-major tile (= the thread-per-point layout) unless the colour net's row-major cotangent
+        // has to be added, which goes through shared memory; FB: always straight from its tile
+        float gq[3] = {0.f, 0.f, 0.f}, g2[3] = {0.f, 0.f, 0.f}, hv[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f}, dummy[3];
         if (d_xyz) {
+            halo_stage_joint(dtile, j, sc);
             __syncthreads();
             halo_stage_add_rows(d_xyz, ld_dxyz, p0, n, j, sc);
+            __syncthreads();
+            if (on) halo_grad_hvp<false, HALO_TLD>(b, sc + r, w, gq, dummy);
+        } else if (on) {
+            halo_grad_hvp<false, HALO_TP>(b, dtile + (size_t)j * HALO_F * HALO_TP + r, w, gq, dummy);
         }
-        __syncthreads();
-        float gq[3] = {0.f, 0.f, 0.f}, g2[3] = {0.f, 0.f, 0.f}, hv[3] = {0.f, 0.f, 0.f}, w[3] = {0.f, 0.f, 0.f}, dummy[3];
-        if (on) halo_grad_hvp<false, HALO_TLD>(b, sc + r, w, gq, dummy);
-        __syncthreads();
-        halo_stage_joint(ftile, j, sc);
-        __syncthreads();
         float v[15];
 #pragma unroll
         for (int i = 0; i < 15; ++i) v[i] = 0.0f;
         if (on) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) w[a] = M[a * 4] * t[0] + M[a * 4 + 1] * t[1] + M[a * 4 + 2] * t[2];
-            halo_grad_hvp<true, HALO_TLD>(b, sc + r, w, g2, hv);
+            halo_grad_hvp<true, HALO_TP>(b, ftile + (size_t)j * HALO_F * HALO_TP + r, w, g2, hv);
             float dq[3];
 #pragma unroll
             for (int a = 0; a < 3; ++a) dq[a] = gq[a] + hv[a];
