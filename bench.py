@@ -442,7 +442,13 @@ def lattice_extra(H, renderer, device, res, rank, world):
     bmin, bmax = torch.full((3,), -0.2), torch.full((3,), 0.2)
     sizes = [hdist.shard_rays(res, r, world) for r in range(world)]
     lo, hi = sizes[rank]
-    renderer.sdf_grid(bmin, bmax, 64)
+    # warm-up at 64^3 INCLUDING the all-gather: the first collective of a kind pays NCCL's lazy channel set-up (it put 150 ms
+    # into one 8-GPU run of this line)
+    wsz = [hdist.shard_rays(64, r, world) for r in range(world)]
+    w = renderer.sdf_grid(bmin, bmax, 64, x_range=wsz[rank])
+    if world > 1:
+        hdist.gather_slabs(w, [b - a for a, b in wsz], dim=0)
+    del w
 
     def run():
         u = renderer.sdf_grid(bmin, bmax, res, x_range=(lo, hi))
