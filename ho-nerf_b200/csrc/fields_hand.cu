@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(HALO_WARPS * 32) halo_feature16_kernel(
         load_x(pts, p, x);
         if (lane < HALO_J) {
             HaloBase b = halo_base(bt_inv + (f * HALO_J + lane) * 16, Tp + (f * HALO_J + lane) * 3, x, lane);
-            halo_feature(b, &sm[warp][lane * HALO_F]);
+            halo_feature<true>(b, &sm[warp][lane * HALO_F]);
         }
     } else {
         for (int i = lane; i < HALO_DIM; i += 32) sm[warp][i] = 0.0f;

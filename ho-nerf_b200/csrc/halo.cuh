@@ -49,7 +49,9 @@ __device__ __forceinline__ HaloBase halo_base(const float* __restrict__ M, const
     return b;
 }
 
-// out[66] = F(q)
+// out[66] = F(q).  FAST: SFU sin / cos after the Cody-Waite reduction (abs error ~6e-7 on values that already carry ~1e-5 from the
+// fp32 cancellation in q = R x + t - T; used by the HN_TC_MIXED16 path, whose tiles round the feature to 22 bits anyway)
+template <bool FAST = false>
 __device__ __forceinline__ void halo_feature(const HaloBase& b, float* out) {
     if (b.dead) {
 #pragma unroll 6
@@ -60,7 +62,7 @@ __device__ __forceinline__ void halo_feature(const HaloBase& b, float* out) {
     float f = 1.0f;
     for (int k = 0; k < HALO_LV; ++k) {
         float s, c;
-        sincosf(b.v * f, &s, &c);
+        if (FAST) halo_sincos_fast(b.v * f, &s, &c); else sincosf(b.v * f, &s, &c);
         out[1 + k] = s * b.h;
         out[1 + HALO_LV + k] = c * b.h;
         f *= 2.0f;
@@ -71,7 +73,7 @@ __device__ __forceinline__ void halo_feature(const HaloBase& b, float* out) {
         f = 1.0f;
         for (int k = 0; k < HALO_LR; ++k) {
             float s, c;
-            sincosf(b.r[a] * f, &s, &c);
+            if (FAST) halo_sincos_fast(b.r[a] * f, &s, &c); else sincosf(b.r[a] * f, &s, &c);
             out[24 + a * 14 + k] = s * b.h;
             out[24 + a * 14 + HALO_LR + k] = c * b.h;
             f *= 2.0f;
