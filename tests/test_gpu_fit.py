@@ -15,11 +15,13 @@ KEYS = {"color_fine", "weight_sum", "sdf_hand", "sdf_obj", "gradient_error_hand"
         "gradient_hand", "gradient_obj"}
 
 
-def _renderer(batched):
+def _renderer(batched, freeze=False):
     import honerf_b200 as H
     import ref_conf
-    hs, hc, hd, hsp, hcp = hand_modules(use_batch=batched)
-    os_, oc, od, osp, ocp = obj_modules()
+    # freeze: nets without trainable weights, as fitting_single.py / fitting_video.py run them -- under the default precision
+    # this is what routes the hand SDF net through its chain kernels (csrc/chain16_hand.cu)
+    hs, hc, hd, hsp, hcp = hand_modules(use_batch=batched, requires_grad=not freeze)
+    os_, oc, od, osp, ocp = obj_modules(requires_grad=not freeze)
     cls = H.renderer_batch.NeuSRenderer_fitting if batched else H.renderer.NeuSRenderer_fitting
     return cls(hs, hd, hc, os_, od, oc, **ref_conf.RENDERER_CONF), (hsp, hcp), (osp, ocp)
 
@@ -92,9 +94,9 @@ def test_fit_render_vs_golden():
     assert torch.isfinite(bt.grad).all() and torch.isfinite(Ro.grad).all() and torch.isfinite(To.grad).all()
 
 
-def _same_z(batched, floor=1e-2):
+def _same_z(batched, floor=1e-2, freeze=False):
     c = cases.fit_render_batch_case() if batched else cases.fit_render_case()
-    r, (hsp, hcp), (osp, ocp) = _renderer(batched)
+    r, (hsp, hcp), (osp, ocp) = _renderer(batched, freeze)
     if batched:
         ro, rd, tr, near, far = c["rays_o"], c["rays_d"], c["t_rand"], c["near"], c["far"]
     else:

@@ -140,3 +140,29 @@ def test_many_tiles_per_cta_match_the_per_layer_path():
     errs = [max_abs(a[0], b[0]), max_abs(a[1], b[1]), rel_l2(a[2], b[2]), rel_l2(a[3], b[3]), rel_l2(a[4], b[4])]
     print("m16 vs per-layer at n=%d: sdf %.2e feat %.2e normal %.2e d_pts %.2e d_bt %.2e" % tuple([n] + errs))
     assert errs[0] < 5e-5 and errs[1] < 2e-4 and errs[2] < 1e-3 and errs[3] < 5e-3 and errs[4] < 5e-3
+
+
+def test_batched_frames_match_the_per_layer_path():
+    """use_batch=True: bt_inv [F,21,4,4], points [F,P,3] with P = 300 (frame boundaries inside tiles): chain kernels against
+    the per-layer path, forward and the gradients to every frame's bone transforms."""
+    import honerf_b200 as H
+    sdf, _, _, _, _ = hand_modules(requires_grad=False, use_batch=True)
+    Fn, P = 3, 300
+    btF, TF_, JF = synth.hand_pose(n_frames=Fn)
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.stack([JF[f][torch.randint(0, 21, (P,), generator=g)] + 0.03 * torch.randn(P, 3, generator=g) for f in range(Fn)]).to(DEV)
+    d_sdf = torch.randn(Fn * P, 1, generator=g).to(DEV)
+    d_n = (1e-2 * torch.randn(Fn * P, 3, generator=g)).to(DEV)
+    res = {}
+    for name in ("tc_mixed16", "tc_bf16x3"):
+        x = x0.clone().requires_grad_(True)
+        bt = btF.to(DEV).requires_grad_(True)
+        s, f, nn, xyz = H.ops.sdf_hand(sdf.packed(), x, bt, TF_.to(DEV), precision=H.ops._PRECISIONS[name])
+        ((s * d_sdf).sum() + (nn * d_n).sum() + 0.01 * f.sum()).backward()
+        res[name] = (s.detach(), f.detach(), nn.detach(), x.grad, bt.grad)
+    a, b = res["tc_mixed16"], res["tc_bf16x3"]
+    errs = [max_abs(a[0], b[0]), max_abs(a[1], b[1]), rel_l2(a[2], b[2]), rel_l2(a[3], b[3])] + \
+           [rel_l2(a[4][f], b[4][f]) for f in range(Fn)]
+    print("batched frames, m16 vs per-layer: sdf %.2e feat %.2e normal %.2e d_pts %.2e d_bt per frame %s" % (
+        errs[0], errs[1], errs[2], errs[3], ["%.2e" % e for e in errs[4:]]))
+    assert errs[0] < 5e-5 and errs[1] < 2e-4 and errs[2] < 1e-3 and all(e < 5e-3 for e in errs[3:])

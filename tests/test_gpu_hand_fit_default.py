@@ -71,3 +71,17 @@ def test_fit_render_batch_given_same_z_default():
 def test_fit_render_batch_vs_golden_default():
     _assert_default()
     TF.test_fit_render_batch_vs_golden_including_frame0_gather_quirk()
+
+
+def test_fit_render_given_same_z_frozen_nets_take_the_hand_chain():
+    """The same comparison with the nets FROZEN (how fitting_single.py runs them): under the default precision the hand SDF net
+    then goes through its tile-chain kernels (csrc/chain16_hand.cu) -- values and pose gradients vs fp64 with the same bounds."""
+    _assert_default()
+    TF._same_z(False, freeze=True)
+
+
+def test_fit_render_batch_given_same_z_frozen_nets_take_the_hand_chain():
+    """Frame-batched renderer, frozen nets: 2 frames x 960 points (a frame boundary inside a 128-point tile: the per-thread
+    frame index and the non-uniform pose-gradient accumulation of halo_bwd_tiled_kernel)."""
+    _assert_default()
+    TF._same_z(True, floor=1.5e-2, freeze=True)
