@@ -30,6 +30,29 @@ constexpr int HT_HEAD_OFF = HT_STAGES * HT_STAGE_BYTES;
 constexpr int HT_SMEM_BYTES = HT_HEAD_OFF + EPI_CGROUPS * TILE_M * 4 + 1024;
 constexpr uint32_t HT_A_HI = 256, HT_A_LO = 384;
 
+// ---- 2-CTA cluster helpers (MC: the two CTAs of a pair run the same weight stream; each fetches HALF of every weight stage and
+// multicasts it into both CTAs' rings, which halves the L2 -> SM weight traffic the 1386-wide layers are co-limited by) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// tcgen05.commit whose arrival lands on the mbarrier at the same CTA-relative address in every CTA of `mask` (SASS: UTCBAR.MULTICAST)
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(tc::smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// bulk copy global -> the same CTA-relative shared address in every CTA of `mask`, completing on each one's mbarrier
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(tc::smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
 struct HtBarriers {
     uint64_t full[HT_STAGES];
     uint64_t empty[HT_STAGES];
@@ -71,6 +94,7 @@ struct HandTrunkParams {
     int n_tiles;
 };
 
+template <bool MC>
 __global__ void __launch_bounds__(THREADS, 1)
 hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_constant__ HtProgram prog) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -82,7 +106,9 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
     if (threadIdx.x == 32) {
         for (int s = 0; s < HT_STAGES; ++s) {
             tc::mbar_init(&bar.full[s], 1);
-            tc::mbar_init(&bar.empty[s], 1);
+            // MC: a stage is free when BOTH CTAs' MMAs have released it (the peer's weight copy lands in this ring too): every
+            // release is a multicast commit, so each `empty` barrier collects two arrivals per lap, in hardware
+            tc::mbar_init(&bar.empty[s], MC ? 2 : 1);
         }
         tc::mbar_init(&bar.a_ready, EPI_THREADS);
         tc::mbar_init(&bar.acc_full[0], 1);
@@ -92,32 +118,56 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
+    if (MC) cluster_sync_all();          // the peer's barriers are initialised before anything is sent to them
     const uint32_t tmem = bar.tmem_base;
-    const int n_my_tiles = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    // tile walk.  MC: clusters walk over PAIRS of tiles, rank r takes tile 2 q + r, both CTAs of a cluster run the same number of
+    // iterations (a tile index past the end is a dummy: its feature rows come from the last tile, nothing is stored)
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    const int walkers = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int me = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = MC ? (p.n_tiles + 1) / 2 : p.n_tiles;
+    const int n_my_tiles = n_units > me ? (n_units - me + walkers - 1) / walkers : 0;
+    auto tile_of = [&](int t) -> int64_t {
+        const int64_t u = (int64_t)me + (int64_t)t * walkers;
+        return MC ? 2 * u + rank : u;
+    };
     const bool stash = p.feat != nullptr;
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            // a stage of this CTA's own data (feature tiles)
             auto put = [&](const uint8_t* src, uint32_t bytes) {
                 tc::mbar_wait(&bar.empty[stage], phase ^ 1u);
                 tc::mbar_arrive_expect_tx(&bar.full[stage], bytes);
                 tc::bulk_g2s(smem + stage * HT_STAGE_BYTES, src, bytes, &bar.full[stage]);
                 if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
             };
+            // a stage of WEIGHTS: identical in both CTAs of the pair.  MC: once both CTAs released the stage, fetch half of it and
+            // multicast it into both rings (each CTA's `full` barrier expects the whole stage: half from its own copy, half from
+            // the peer's)
+            auto put_w = [&](const uint8_t* src, uint32_t bytes) {
+                if (!MC) { put(src, bytes); return; }
+                tc::mbar_wait(&bar.empty[stage], phase ^ 1u);
+                tc::mbar_arrive_expect_tx(&bar.full[stage], bytes);
+                const uint32_t half = bytes >> 1;
+                bulk_g2s_multicast(smem + stage * HT_STAGE_BYTES + rank * half, src + rank * half, half, &bar.full[stage], (uint16_t)3);
+                if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
+            };
             for (int t = 0; t < n_my_tiles; ++t) {
-                const uint8_t* ftile = p.F16 + ((size_t)blockIdx.x + (size_t)t * gridDim.x) * HAND_F16_TILE_BYTES;
+                const int64_t tile = tile_of(t) < p.n_tiles ? tile_of(t) : (int64_t)p.n_tiles - 1;
+                const uint8_t* ftile = p.F16 + (size_t)tile * HAND_F16_TILE_BYTES;
                 for (int s = 0; s < prog.n_steps; ++s) {
                     const HtStep st = prog.step[s];
                     const uint8_t* src = p.chain + st.b_off;
                     if (st.feature) {
                         for (int kb = 0; kb < st.kblocks; ++kb) {
                             put(ftile + (size_t)kb * HAND_F16_KB_BYTES, HAND_F16_KB_BYTES);      // A: hi tile + lo tile
-                            put(src + (size_t)kb * 65536, 32768);                                // B hi: 256 rows
-                            put(src + (size_t)kb * 65536 + 32768, 32768);                        // B lo
+                            put_w(src + (size_t)kb * 65536, 32768);                              // B hi: 256 rows
+                            put_w(src + (size_t)kb * 65536 + 32768, 32768);                      // B lo
                         }
                     } else {
-                        for (int c = 0; c < 2 * st.kblocks; ++c) put(src + (size_t)c * 16384, 16384);
+                        for (int c = 0; c < 2 * st.kblocks; ++c) put_w(src + (size_t)c * 16384, 16384);
                     }
                 }
             }
@@ -132,8 +182,11 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
                 tc::mbar_wait(&bar.full[stage], phase);
                 return addr;
             };
+            auto commit_empty = [&](uint32_t st_idx) {
+                if (MC) umma_commit_multicast(&bar.empty[st_idx], (uint16_t)3); else tc::umma_commit(&bar.empty[st_idx]);
+            };
             auto release = [&]() {
-                tc::umma_commit(&bar.empty[stage]);
+                commit_empty(stage);
                 if (++stage == HT_STAGES) { stage = 0; phase ^= 1u; }
             };
             for (int t = 0; t < n_my_tiles; ++t)
@@ -166,9 +219,9 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
                                 tc::umma_f16(d, dAh + 2 * k, dBh + 2 * k, idesc_full, 1);
                                 tc::umma_f16(d, dAh + 2 * k, dBl + 2 * k, idesc_full, 1);
                             }
-                            tc::umma_commit(&bar.empty[st_a]);
-                            tc::umma_commit(&bar.empty[st_bh]);
-                            tc::umma_commit(&bar.empty[st_bl]);
+                            commit_empty(st_a);
+                            commit_empty(st_bh);
+                            commit_empty(st_bl);
                         }
                     } else {
                         for (int kb = 0; kb < st.kblocks; ++kb) {
@@ -218,12 +271,13 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
             tc::tmem_st_32x32b_x8(tmem + lane_base + HT_A_LO + c + 8, lo + 8);
         };
         for (int t = 0; t < n_my_tiles; ++t) {
-            const int64_t tile = (int64_t)blockIdx.x + (int64_t)t * gridDim.x;
+            const int64_t tile = tile_of(t);
+            const bool real = tile < p.n_tiles;              // MC: the odd tile's partner walks a dummy
             const int64_t gp = tile * TILE_M + row;
-            const bool live = gp < p.n;
+            const bool live = real && gp < p.n;
             // 8 columns [c, c + 8) of layer l: EM / EML stash chunks + fp16 hi / lo words of the next A operand
             auto emit8 = [&](int l, int c, const float* h, const float* em, uint32_t* hi4, uint32_t* lo4) {
-                if (stash) {
+                if (stash && real) {
                     const uint32_t off = t16_off(row, c >> 3);
                     uint4 q, ql;
                     split2_lo16(em[0], em[1], q.x, ql.x); split2_lo16(em[2], em[3], q.y, ql.y);
@@ -332,6 +386,7 @@ hand_trunk16_kernel(const __grid_constant__ HandTrunkParams p, const __grid_cons
     }
     tc::tc_fence_before_sync();
     __syncthreads();
+    if (MC) cluster_sync_all();          // no CTA leaves while its peer may still address its shared memory
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -709,8 +764,22 @@ int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const 
     const HandLayout L = hand_layout();
     const int n_tiles = (int)ceil_div(n, TILE_M);
     static bool configured = false;
+    static int mc_clusters = 0;      // > 0: pairs of CTAs with multicast weight stages (HONERF_HAND_MC=0 turns it off)
     if (!configured) {
-        HN_CHECK_CUDA(cudaFuncSetAttribute(hand_trunk16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hand_trunk16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
+        HN_CHECK_CUDA(cudaFuncSetAttribute(hand_trunk16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
+        const bool want = getenv("HONERF_HAND_MC") ? atoi(getenv("HONERF_HAND_MC")) != 0 : true;
+        if (want) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(sm_count() & ~1)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = HT_SMEM_BYTES;
+            cudaLaunchAttribute at;
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, hand_trunk16_kernel<true>, &cfg) == cudaSuccess && nc > 0) mc_clusters = nc;
+            else (void)cudaGetLastError();
+        }
         configured = true;
     }
     HandTrunkParams p;
@@ -738,7 +807,18 @@ int launch_hand16_trunk(const hn_mlp_t* m, const uint8_t* ops, int64_t n, const 
         if (F16 && l == 4) feature_step(1, false);                    // + F @ W_4[:, 256:]^T onto both halves
     }
     prog.n_steps = k;
-    hand_trunk16_kernel<<<std::min(n_tiles, sm_count()), THREADS, HT_SMEM_BYTES, s>>>(p, prog);
+    if (F16 && mc_clusters > 0 && n_tiles >= 2) {
+        const int clusters = std::min((n_tiles + 1) / 2, mc_clusters);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * clusters)); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = HT_SMEM_BYTES; cfg.stream = s;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at; cfg.numAttrs = 1;
+        HN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, hand_trunk16_kernel<true>, p, prog));
+    } else {
+        hand_trunk16_kernel<false><<<std::min(n_tiles, sm_count()), THREADS, HT_SMEM_BYTES, s>>>(p, prog);
+    }
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;
