@@ -109,6 +109,9 @@ PROTOTYPES = {
     "hn_color_hand_stash_floats": (c_int64, [c_int64]),
     "hn_color_hand_ws_floats": (c_int64, [c_int64, c_int]),
     "hn_color_hand_fwd": (c_int, [_mlp_p, P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P]),
+    "hn_color_hand_fwd_render": (c_int, [_mlp_p, P, c_int64, P, c_int64, P, c_int64, P, P, c_int64, c_int, P]),
+    "hn_color_hand_chain_bytes": (c_int64, [_mlp_p]),
+    "hn_color_hand_chain_pack": (c_int, [_mlp_p, P, c_int64, P]),
     "hn_color_hand_bwd": (c_int, [_mlp_p, c_int64, P, P, P, P, c_int64, P, c_int64, P, _grad_p, P, c_int64,
                                   c_int, P]),
     "hn_chain_set_prof": (c_int, [P]),

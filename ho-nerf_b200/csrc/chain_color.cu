@@ -76,6 +76,7 @@ struct ColorFwdParams {
     const float* dirs;
     const float* feat;
     int64_t ld_feat;
+    const float* feat2;     // TAIL: second addend of the first layer's pre-activation rows (may be NULL), same ld
     const float* normal;
     int64_t n;
     float* rgb;
@@ -93,7 +94,9 @@ struct ColorFwdParams {
     int n_tiles;
 };
 
-template <bool S16>
+// TAIL (hand colour net, forward-only rendering): the first layer's ReLU output arrives as fp32 rows in p.feat (its 1669-wide
+// contraction stays a per-layer kernel); the chain runs layers 1..3 and the sigmoid output layer, nothing is stashed.
+template <bool S16, bool TAIL = false>
 __global__ void __launch_bounds__(THREADS, 1)
 color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant__ Program prog) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -128,12 +131,21 @@ color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant
                     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (g < p.n) {
                         a = ld4(p.feat + g * p.ld_feat + c);
-                        if (!S16) st4(ft + toff(r, c), a);
+                        if (!S16 && !TAIL) st4(ft + toff(r, c), a);
+                        if (TAIL) {      // rows are PRE-activations of the first layer (two partial contractions): + bias, ReLU
+                            if (p.feat2) {
+                                const float4 b2 = ld4(p.feat2 + g * p.ld_feat + c);
+                                a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+                            }
+                            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias[0] + c));
+                            a.x = fmaxf(a.x + b0.x, 0.0f); a.y = fmaxf(a.y + b0.y, 0.0f);
+                            a.z = fmaxf(a.z + b0.z, 0.0f); a.w = fmaxf(a.w + b0.w, 0.0f);
+                        }
                     }
                     uint2 hi, lo;
                     split2(a.x, a.y, hi.x, lo.x);
                     split2(a.z, a.w, hi.y, lo.y);
-                    if (S16) {    // rows past n are stored too (zeros): the weight-gradient MMAs read whole tiles
+                    if (S16 && !TAIL) {    // rows past n are stored too (zeros): the weight-gradient MMAs read whole tiles
                         uint8_t* f16 = p.FEAT16 + (size_t)tile * T16_TILE_BYTES + t16_off(r, c >> 3) + (uint32_t)(c & 4) * 2u;
                         *reinterpret_cast<uint2*>(f16) = hi;
                         if (p.store_lo) *reinterpret_cast<uint2*>(f16 + p.lo_off) = lo;
@@ -146,6 +158,7 @@ color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant
             }
             epi_publish_a(&bar);
             // ---- A <- encodings of pts, dirs, normal (columns 0..127), accumulated onto the feature part ------
+            if (!TAIL) {
             epi_wait_acc(&bar, acc_par);
             {
                 float x[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f}, nr[3] = {0.f, 0.f, 0.f};
@@ -178,8 +191,9 @@ color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant
                 }
             }
             epi_publish_a(&bar);
+            }
             // ---- hidden layers: ReLU ----------------------------------------------------------------------------
-            for (int l = 0; l < 4; ++l) {
+            for (int l = TAIL ? 1 : 0; l < 4; ++l) {
                 epi_wait_acc(&bar, acc_par);
                 const float* __restrict__ bias = p.bias[l];
                 float* __restrict__ rt = p.R[l] + tile * TILE_FLOATS;
@@ -195,12 +209,12 @@ color_fwd_kernel(const __grid_constant__ ColorFwdParams p, const __grid_constant
                         v[j + 1] = fmaxf(v[j + 1] + b.y, 0.0f);
                         v[j + 2] = fmaxf(v[j + 2] + b.z, 0.0f);
                         v[j + 3] = fmaxf(v[j + 3] + b.w, 0.0f);
-                        if (!S16 && live) st4(rt + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        if (!S16 && !TAIL && live) st4(rt + toff(row, col0 + j), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
                     }
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         a_store8(smem, row, col0 + j, v + j);
-                        if (S16) {
+                        if (S16 && !TAIL) {
                             uint4 qh, ql;
                             split2(v[j], v[j + 1], qh.x, ql.x); split2(v[j + 2], v[j + 3], qh.y, ql.y);
                             split2(v[j + 4], v[j + 5], qh.z, ql.z); split2(v[j + 6], v[j + 7], qh.w, ql.w);
@@ -500,6 +514,41 @@ int launch_color_fwd(const hn_mlp_t* m, const float* pts, const float* dirs, con
     count_launch();
     HN_CHECK_LAUNCH();
     return HN_OK;
+}
+
+// Hand colour net, forward-only: layers 1..3 + output of a 5-layer colour mlp (same shapes as the object colour net's) on the
+// chain kernel; `ops` = operands packed by color_tail_pack at the ColorLayout offsets; Z0a (+ Z0b) = the first layer's
+// pre-activation rows WITHOUT bias (one or two partial contractions), bias and ReLU are applied while they are loaded
+int launch_color_tail_fwd(const hn_mlp_t* m, const uint8_t* ops, const float* Z0a, const float* Z0b, int64_t ld_z, int64_t n,
+                          float* rgb, cudaStream_t s) {
+    HN_REQUIRE(ld_z % 4 == 0 && aligned16(Z0a) && aligned16(Z0b), "colour tail: first-layer rows must be 16-byte aligned with ld %% 4 == 0");
+    const ColorLayout L = color_layout();
+    ColorFwdParams p = {};
+    p.feat = Z0a; p.feat2 = Z0b; p.ld_feat = ld_z; p.n = n; p.rgb = rgb;
+    p.chain = ops;
+    for (int l = 0; l < 5; ++l) p.bias[l] = m->b[l];
+    p.n_tiles = (int)ceil_div(n, TILE_M);
+    Program prog = {};
+    for (int l = 1; l <= 3; ++l) set_step(prog.step[l - 1], L.nt[l], 256, 4);
+    set_step(prog.step[3], L.nt[4], 16, 4);
+    prog.n_steps = 4;
+    static bool configured = false;
+    if (!configured) {
+        HN_CHECK_CUDA(cudaFuncSetAttribute(color_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+    }
+    color_fwd_kernel<false, true><<<std::min(p.n_tiles, sm_count()), THREADS, SMEM_BYTES, s>>>(p, prog);
+    count_launch();
+    HN_CHECK_LAUNCH();
+    return HN_OK;
+}
+int64_t color_tail_bytes() { return (int64_t)color_layout().total; }
+int color_tail_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s) {
+    const ColorLayout L = color_layout();
+    pack_batch_begin();
+    for (int l = 1; l <= 3; ++l) HN_PROPAGATE(launch_pack_b(m->W[l], m->ld[l], 0, 0, 256, 256, 256, 4, dst + L.nt[l], s));
+    HN_PROPAGATE(launch_pack_b(m->W[4], m->ld[4], 0, 0, 3, 256, 16, 4, dst + L.nt[4], s));
+    return pack_batch_flush(s);
 }
 
 int launch_color_bwd(const hn_mlp_t* m, int64_t n, const float* stash, const float* rgb, const float* d_rgb, float* d_pts,

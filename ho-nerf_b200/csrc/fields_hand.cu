@@ -23,6 +23,11 @@ int launch_hand16_bwd(const hn_mlp_t* m, const uint8_t* ops, int64_t n, uint8_t*
                       uint8_t* const* X16, const float* Q0, const float* QF4, const float* d_sdf, const float* d_feat,
                       int64_t ld_dfeat, float* DF, cudaStream_t s);
 int hand16_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s);
+// chain_color.cu: layers 1..3 + output of the hand colour net on the colour chain kernel (forward-only rendering)
+int launch_color_tail_fwd(const hn_mlp_t* m, const uint8_t* ops, const float* Z0a, const float* Z0b, int64_t ld_z, int64_t n,
+                          float* rgb, cudaStream_t s);
+int64_t color_tail_bytes();
+int color_tail_pack(const hn_mlp_t* m, uint8_t* dst, cudaStream_t s);
 }  // namespace chain
 
 constexpr int HROW_LD = 1644;        // [h3 256 | feature 1386 | pad 2]
@@ -898,6 +903,31 @@ __global__ void color_hand_input_kernel(const float* __restrict__ xyz, int64_t l
     *reinterpret_cast<float4*>(CIN + p * HCIN_LD + j) = v;
 }
 
+// Render path: the first layer as TWO contractions -- over the xyz_feature rows where they lie (no copy into an input row) and
+// over this small second operand A2 [n, 328] = [44 zeros | feature 256 | enc4(normal) 27 | 0], whose column c is input column
+// 1344 + c of the packed first-layer weights (k-block 21 onwards; the 44 leading columns belong to the xyz part)
+constexpr int HCIN2_LD = 328, HCIN2_KB0 = 21, HCIN2_OFF = HCIN2_KB0 * 64;     // 1344
+__global__ void color_hand_input2_kernel(const float* __restrict__ feat, int64_t ld_feat, const float* __restrict__ normal, int64_t n,
+                                         float* __restrict__ A2) {
+    constexpr int Q = HCIN2_LD / 4;     // 82 float4 per row
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * Q) return;
+    const int64_t p = i / Q;
+    const int j = (int)(i - p * Q) * 4 + HCIN2_OFF;      // column of the full 1672-wide row
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j >= HCIN_OFF_FEAT && j < HCIN_OFF_NRM) {
+        v = *reinterpret_cast<const float4*>(feat + p * ld_feat + (j - HCIN_OFF_FEAT));
+    } else if (j >= HCIN_OFF_NRM) {
+        const float x[3] = {normal[p * 3], normal[p * 3 + 1], normal[p * 3 + 2]};
+        const int c = j - HCIN_OFF_NRM;
+        v.x = enc3_col(x, 4, c);
+        v.y = enc3_col(x, 4, c + 1);
+        v.z = enc3_col(x, 4, c + 2);
+        v.w = c + 3 < HCIN_DIM - HCIN_OFF_NRM ? enc3_col(x, 4, c + 3) : 0.0f;
+    }
+    *reinterpret_cast<float4*>(A2 + p * HCIN2_LD + (j - HCIN2_OFF)) = v;
+}
+
 // scatter of the first layer's input cotangent DCIN [n, 1672]: one thread per float4 of the xyz / feature blocks (vec: both
 // destinations 16-byte aligned with ld % 4 == 0), three more threads per point for the normal through J_enc^T
 __global__ void color_hand_input_bwd_kernel(const float* __restrict__ CIN, const float* __restrict__ DCIN, int64_t n,
@@ -972,10 +1002,40 @@ int64_t hn_color_hand_ws_floats(int64_t n, int kind) {
     return 4;
 }
 
+static thread_local bool t_color_hand_render_only = false;
+static const uint8_t* color_hand_tail_ops(const hn_mlp_t* m) {
+    const int64_t off = round_up(bx3_layout(m).total, 1024);
+    if (!m->chain || m->chain_bytes < off + chain::color_tail_bytes()) return nullptr;
+    return reinterpret_cast<const uint8_t*>(m->chain) + off;
+}
+
+// The hand colour net's packed operands: the per-layer tiles of hn_mlp_bx3_pack followed (1 KB aligned) by the chain operands of
+// its layers 1..4 (forward-only rendering under HN_TC_MIXED16: hn_color_hand_fwd_render)
+int64_t hn_color_hand_chain_bytes(const hn_mlp_t* m) {
+    if (!m || m->n_layers != 5) return 0;
+    return round_up(bx3_layout(m).total, 1024) + chain::color_tail_bytes();
+}
+int hn_color_hand_chain_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_stream_t stream) {
+    HN_PROPAGATE(check_color_hand_mlp(m));
+    HN_REQUIRE(buf && bytes >= hn_color_hand_chain_bytes(m) && aligned16(buf), "hn_color_hand_chain_pack: buffer too small or misaligned");
+    HN_PROPAGATE(hn_mlp_bx3_pack(m, buf, bytes, stream));
+    return chain::color_tail_pack(m, reinterpret_cast<uint8_t*>(buf) + round_up(bx3_layout(m).total, 1024), (cudaStream_t)stream);
+}
+
+int hn_color_hand_fwd_render(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_xyz, const float* feat,
+                             int64_t ld_feat, const float* normal, int64_t n, float* rgb, float* stash,
+                             int64_t stash_floats, int precision, hn_stream_t stream) {
+    t_color_hand_render_only = true;
+    const int r = hn_color_hand_fwd(mlp, xyz_feature, ld_xyz, feat, ld_feat, normal, n, rgb, stash, stash_floats, precision, stream);
+    t_color_hand_render_only = false;
+    return r;
+}
+
 int hn_color_hand_fwd(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_xyz, const float* feat,
                       int64_t ld_feat, const float* normal, int64_t n, float* rgb, float* stash,
                       int64_t stash_floats, int precision, hn_stream_t stream) {
     HN_PROPAGATE(check_color_hand_mlp(mlp));
+    const bool tail = precision == HN_TC_MIXED16 && t_color_hand_render_only && color_hand_tail_ops(mlp) != nullptr;
     precision = base_precision(precision);
     HN_REQUIRE(precision_supported(precision), "hn_color_hand_fwd: precision %d not supported", precision);
     HN_REQUIRE(n >= 0 && n < (1ll << 31), "n_pts out of range");
@@ -988,6 +1048,29 @@ int hn_color_hand_fwd(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_
     for (int l = 0; l < 4; ++l) R[l] = stash + n * HCIN_LD + (int64_t)l * n * 256;
     HN_REQUIRE(ld_feat % 4 == 0 && aligned16(feat), "hn_color_hand_fwd: feat must be 16-byte aligned with ld %% 4 == 0");
     const int vec_xyz = (aligned16(xyz_feature) && ld_xyz % 4 == 0) ? 1 : 0;
+    if (tail && vec_xyz && mlp->chain) {
+        // forward-only rendering: no 1672-wide input row is assembled.  First layer = (xyz_feature rows in place) x (packed
+        // k-blocks 0..21, columns past 1386 masked) + (A2) x (packed k-blocks 21..26); layers 1..3 + the sigmoid output on the
+        // colour chain kernel, which adds the two partial results, the bias and the ReLU while it loads them
+        float* A2 = CIN;
+        float* Z1 = R[0];
+        float* Z2 = R[1];
+        color_hand_input2_kernel<<<nblocks(n * (HCIN2_LD / 4), 256), 256, 0, s>>>(feat, ld_feat, normal, n, A2);
+        count_launch();
+        HN_CHECK_LAUNCH();
+        GemmArgs g1;
+        g1.A = xyz_feature; g1.lda = ld_xyz;
+        set_w(g1, mlp, 0);
+        g1.M = (int)n; g1.N = 256; g1.K = HALO_DIM; g1.C = Z1; g1.ldc = 256;
+        HN_PROPAGATE((gemm_nt<EPI_STORE>(g1, s, precision)));
+        GemmArgs g2;
+        g2.A = A2; g2.lda = HCIN2_LD;
+        set_w(g2, mlp, 0);
+        g2.B = mlp->W[0] + HCIN2_OFF; g2.bp_kb0 = HCIN2_KB0;
+        g2.M = (int)n; g2.N = 256; g2.K = HCIN_DIM - HCIN2_OFF; g2.C = Z2; g2.ldc = 256;
+        HN_PROPAGATE((gemm_nt<EPI_STORE>(g2, s, precision)));
+        return chain::launch_color_tail_fwd(mlp, color_hand_tail_ops(mlp), Z1, Z2, 256, n, rgb, s);
+    }
     color_hand_input_kernel<<<nblocks(n * (HCIN_LD / 4), 256), 256, 0, s>>>(xyz_feature, ld_xyz, vec_xyz, feat, ld_feat, normal, n, CIN);
     count_launch();
     HN_CHECK_LAUNCH();

@@ -163,6 +163,7 @@ class SDFNetwork(_PackedNet):
 class RenderingNetwork(_PackedNet):
     """Hand colour network (utils/fields.py:179-240): [xyz_feature 1386, feature 256, normal+enc4 27] = 1669
     -> 256 x4 -> 3, ReLU, sigmoid."""
+    _chain_kind = "color_hand"
 
     def __init__(self, barf_encoding, data_type, d_feature, d_in, d_out, d_hidden, n_layers, weight_norm=True,
                  v_multires=10, r_multires=4, grad_multires=4, squeeze_out=True, use_gradients=False):

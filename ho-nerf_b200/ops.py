@@ -125,11 +125,12 @@ class PackedMLP:
             st.b[l] = bd.data_ptr()
         # every layer's g * v / ||v|| (and its transposed copy) in one launch
         check(lib.hn_wn_pack_batch(jobs, len(self.layers), _stream(self.W)), "hn_wn_pack_batch")
-        if self.chain_kind in ("bx3", "sdf_hand"):
+        if self.chain_kind in ("bx3", "sdf_hand", "color_hand"):
             # pre-packed bf16 hi/lo operands of every layer for the per-layer HN_TC_BF16X3 contractions (hand colour net), plus --
             # for the hand SDF net -- the tile-chain operands of its 256 x 256 layers (HN_TC_MIXED16)
-            size_fn, pack_fn = ((lib.hn_mlp_bx3_bytes, lib.hn_mlp_bx3_pack) if self.chain_kind == "bx3" else
-                                (lib.hn_sdf_hand_chain_bytes, lib.hn_sdf_hand_chain_pack))
+            size_fn, pack_fn = {"bx3": (lib.hn_mlp_bx3_bytes, lib.hn_mlp_bx3_pack),
+                                "sdf_hand": (lib.hn_sdf_hand_chain_bytes, lib.hn_sdf_hand_chain_pack),
+                                "color_hand": (lib.hn_color_hand_chain_bytes, lib.hn_color_hand_chain_pack)}[self.chain_kind]
             nbytes = int(size_fn(ctypes.byref(st)))
             if self.chain is None or self.chain.device != dev or self.chain.numel() < nbytes:
                 self.chain = torch.empty(nbytes, device=dev, dtype=torch.uint8)
@@ -551,7 +552,7 @@ def sdf_hand(packed, pts, bt_inv, T_pose_21, precision=None):
 
 class _ColorHandFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xyz, feat, normal, packed, precision, *params):
+    def forward(ctx, xyz, feat, normal, packed, precision, differentiable, *params):
         (xyz_c, ld_xyz), feat_c, nrm_c = _rows_f32(xyz), _f32c(feat.detach()), _f32c(normal.detach())
         _require_cuda(xyz_c, "color_hand")
         pk = packed.get()
@@ -560,9 +561,9 @@ class _ColorHandFn(torch.autograd.Function):
         stf = lib.hn_color_hand_stash_floats(n)
         stash = torch.empty(max(stf, 4), device=dev, dtype=torch.float32)
         if n > 0:
-            check(lib.hn_color_hand_fwd(ctypes.byref(pk.struct), _ptr(xyz_c), ld_xyz, _ptr(feat_c),
-                                        feat_c.shape[1], _ptr(nrm_c), n, _ptr(rgb), _ptr(stash), stf, precision,
-                                        _stream(xyz_c)), "hn_color_hand_fwd")
+            fwd = lib.hn_color_hand_fwd if differentiable else lib.hn_color_hand_fwd_render
+            check(fwd(ctypes.byref(pk.struct), _ptr(xyz_c), ld_xyz, _ptr(feat_c), feat_c.shape[1], _ptr(nrm_c), n, _ptr(rgb),
+                      _ptr(stash), stf, precision, _stream(xyz_c)), "hn_color_hand_fwd")
         ctx.packed, ctx.stash, ctx.n, ctx.precision, ctx.struct, ctx.rgb = pk, stash, n, precision, pk.struct, rgb
         ctx.pkey = pk._key
         ctx.need = (xyz.requires_grad, feat.requires_grad, normal.requires_grad)
@@ -595,13 +596,16 @@ class _ColorHandFn(torch.autograd.Function):
             if gs is not None:
                 grads = pk.unpack_grads(dW, db)
         ctx.stash = None
-        return (d_xyz, d_feat, d_nrm, None, None) + tuple(grads)
+        return (d_xyz, d_feat, d_nrm, None, None, None) + tuple(grads)
 
 
 def color_hand(packed, xyz_feature, feat, normal, precision=None):
     """RenderingNetwork.forward (utils/fields.py:222-240): -> rgb [N,3]."""
     precision = _default_precision if precision is None else precision
-    return _ColorHandFn.apply(xyz_feature, feat, normal, packed, precision, *packed.flat_params())
+    params = packed.flat_params()
+    differentiable = torch.is_grad_enabled() and (xyz_feature.requires_grad or feat.requires_grad or normal.requires_grad or
+                                                  any(p.requires_grad for p in params))
+    return _ColorHandFn.apply(xyz_feature, feat, normal, packed, precision, differentiable, *params)
 
 
 # ------------------------------------------------------------------------------------------------

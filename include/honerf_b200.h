@@ -271,6 +271,16 @@ HN_API int hn_color_hand_fwd(const hn_mlp_t* mlp, const float* xyz_feature, int6
                              const float* feat, int64_t ld_feat, const float* normal, int64_t n_pts,
                              float* rgb, float* stash, int64_t stash_floats, int precision,
                              hn_stream_t stream);
+/* Forward that will never be differentiated (rendering): with the operands of hn_color_hand_chain_pack in mlp->chain and
+ * HN_TC_MIXED16, layers 1..3 and the output layer run on the colour chain kernel (csrc/chain_color.cu) and nothing is stashed for
+ * a backward; the stash is still the scratch of the call (same size). */
+HN_API int hn_color_hand_fwd_render(const hn_mlp_t* mlp, const float* xyz_feature, int64_t ld_xyz,
+                             const float* feat, int64_t ld_feat, const float* normal, int64_t n_pts,
+                             float* rgb, float* stash, int64_t stash_floats, int precision,
+                             hn_stream_t stream);
+/* per-layer operands of hn_mlp_bx3_pack followed by the chain operands of layers 1..4 */
+HN_API int64_t hn_color_hand_chain_bytes(const hn_mlp_t* m);
+HN_API int hn_color_hand_chain_pack(const hn_mlp_t* m, void* buf, int64_t bytes, hn_stream_t stream);
 HN_API int hn_color_hand_bwd(const hn_mlp_t* mlp, int64_t n_pts, float* stash, const float* rgb,
                              const float* d_rgb, float* d_xyz_feature, int64_t ld_dxyz, float* d_feat,
                              int64_t ld_dfeat, float* d_normal, const hn_mlp_grad_t* grad, float* ws,

@@ -166,3 +166,25 @@ def test_batched_frames_match_the_per_layer_path():
     print("batched frames, m16 vs per-layer: sdf %.2e feat %.2e normal %.2e d_pts %.2e d_bt per frame %s" % (
         errs[0], errs[1], errs[2], errs[3], ["%.2e" % e for e in errs[4:]]))
     assert errs[0] < 5e-5 and errs[1] < 2e-4 and errs[2] < 1e-3 and all(e < 5e-3 for e in errs[3:])
+
+
+def test_hand_colour_render_path_matches_the_differentiable_path():
+    """Forward-only rendering runs layers 1..3 + output of the hand colour net on the colour chain kernel
+    (hn_color_hand_fwd_render); same colours as the differentiable per-layer call: 2e-5 abs."""
+    import honerf_b200 as H
+    _, col, _, _, _ = hand_modules(requires_grad=False)
+    for n in (1, 130, 20000):
+        g = torch.Generator().manual_seed(n)
+        xyz = (0.3 * torch.randn(n, 1386, generator=g)).to(DEV)
+        feat = (0.3 * torch.randn(n, 256, generator=g)).to(DEV)
+        nrm = torch.nn.functional.normalize(torch.randn(n, 3, generator=g), dim=-1).to(DEV)
+        b = H.ops.color_hand(col.packed(), xyz.clone().requires_grad_(True), feat, nrm).detach()
+        with torch.no_grad():
+            a = H.ops.color_hand(col.packed(), xyz, feat, nrm)          # contiguous rows (ld 1386): input row assembled
+            # the way the renderer passes it: a 16-byte aligned view of the SDF operator's stash rows (ld 1644), which the
+            # first layer then reads in place (two partial contractions, no 1672-wide input row)
+            wide = torch.zeros(n, 1644, device=DEV)
+            wide[:, 256:256 + 1386] = xyz
+            a2 = H.ops.color_hand(col.packed(), wide[:, 256:256 + 1386], feat, nrm)
+        assert a.shape == (n, 3) and max_abs(a, b) < 2e-5, (n, max_abs(a, b))
+        assert max_abs(a2, b) < 2e-5, (n, max_abs(a2, b))
