@@ -679,14 +679,43 @@ def run_gpu_arm(args):
             flat_holder["flat"] = hdist.flatten_gradients(params)
         return loss
 
+    # ---- the step's ONE exchange: the flat gradient buffer ------------------------------------------------------------
+    # default: summed over the ranks INSIDE the Adam kernel, over NVLink peer memory (hn_peer_adam_flat, csrc/peer.cu);
+    # --exchange nccl (or a failed set-up / check, decided collectively): ncclAllReduce followed by hn_adam_flat
+    peer = {"on": False, "check": None, "why": None}
+    if world > 1 and flat_opt and args.exchange == "peer":
+        import torch.distributed as dist
+        if opt.enable_peer_exchange():
+            gen = torch.Generator(device=device)
+            gen.manual_seed(1234 + rank)
+            opt.flat_grad.copy_(torch.randn(opt.n, device=device, generator=gen))
+            want = opt.flat_grad.clone()
+            dist.all_reduce(want, op=dist.ReduceOp.SUM)
+            got = opt.peer_allreduce()
+            torch.cuda.synchronize()
+            rel = float((got - want).abs().max() / want.abs().max())
+            good = torch.tensor([1 if (opt.peer_error() == 0 and rel < 1e-5) else 0], device=device)
+            dist.all_reduce(good, op=dist.ReduceOp.MIN)
+            opt.flat_grad.zero_()
+            peer["check"] = rel
+            if int(good) == 1:
+                peer["on"] = True
+            else:
+                peer["why"] = "check against ncclAllReduce failed (rel %.3g, err %d)" % (rel, opt.peer_error())
+        else:
+            peer["why"] = "peer-memory set-up failed (cudaIpc handles)"
+        if not peer["on"]:
+            sys.stderr.write("bench.py: peer-memory exchange off (%s); using ncclAllReduce\n" % peer["why"])
+
     def reduce_grads():
-        """the ONE collective of the step: all-reduce of the flat gradient buffer (NCCL over NVLink)"""
-        if world > 1:
+        """the NCCL form of the exchange: all-reduce of the flat gradient buffer"""
+        if world > 1 and not peer["on"]:
             hdist.allreduce_flat(opt.flat_grad if flat_opt else flat_holder["flat"])
 
-    def apply_grads():
+    def apply_grads(local=False):
         if flat_opt:
-            opt.step(flat_holder["runs"], grad_scale=1.0 / world)     # averaging folded into the Adam kernel
+            # averaging folded into the Adam kernel; `local`: rank 0's solo kernel-timing pass (no collective)
+            opt.step(flat_holder["runs"], grad_scale=1.0 / world, peer_exchange=peer["on"] and not local)
             return
         if world > 1:
             hdist.unflatten_gradients(params, flat_holder["flat"], world)
@@ -851,7 +880,7 @@ def run_gpu_arm(args):
         # per-kernel durations are taken with the shards serialised (one stream): events around a launch that shares
         # the SMs with the other shard's kernels would time the sharing, not the kernel
         renderer.ray_streams = 1
-        roof = mlp_roofline(H, lambda: (fwd_bwd(dev_batch), apply_grads()), n_rays)
+        roof = mlp_roofline(H, lambda: (fwd_bwd(dev_batch), apply_grads(local=True)), n_rays)
         renderer.ray_streams = args.ray_streams
         if roof is not None:
             roof["measured_with"] = "ray_streams=1 (kernels serialised, one launch per family and step)"
@@ -873,6 +902,11 @@ def run_gpu_arm(args):
         torch.cuda.empty_cache()
     # ---- strong scaling: the SAME 512 rays split over the ranks, eager launches ------------------------------
     strong = None
+    if peer["on"]:
+        e = opt.peer_error()
+        if e:
+            raise RuntimeError("bench.py: hn_peer_adam_flat gave up waiting for rank %d inside the timed region" % (e - 1))
+        barrier()           # rank 0 ran its solo pass: line the ranks up before the next peer-memory step
     if world > 1 and args.strong_rays > 0:
         from honerf_b200 import dist as hdist
         hb = synthetic_batch(args.strong_rays, seed=7)        # the same batch on every rank
@@ -945,9 +979,15 @@ def run_gpu_arm(args):
             "config": {"workload": WORKLOAD % n_rays,
                        "rays_per_gpu": n_rays, "precision": args.precision, "parallelism": "rays sharded x%d" % world,
                        "cuda_graph": graph is not None,
-                       "allreduce": (None if world == 1 else "NCCL all-reduce of the flat gradient buffer captured in the step's CUDA graph"
+                       "allreduce": (None if world == 1 else
+                                     "two-shot sum over NVLink peer memory fused with Adam (hn_peer_adam_flat, one kernel, captured "
+                                     "in the step's CUDA graph); checked against ncclAllReduce before timing: max rel diff %.2g"
+                                     % peer["check"] if peer["on"] else
+                                     "NCCL all-reduce of the flat gradient buffer captured in the step's CUDA graph"
                                      if nccl_in_graph else "NCCL all-reduce launched eagerly between two CUDA graphs"),
-                       "optimizer": "FlatAdam (hn_adam_flat, one launch)" if flat_opt else "torch.optim.Adam(fused, capturable)",
+                       "exchange_fallback": peer["why"],
+                       "optimizer": ("FlatAdam (hn_peer_adam_flat, one launch)" if peer["on"] else "FlatAdam (hn_adam_flat, one launch)")
+                       if flat_opt else "torch.optim.Adam(fused, capturable)",
                        "loss": "hn_render_loss_fwd/_bwd (fused)" if args.loss == "fused" else "torch ops",
                        "ray_streams": args.ray_streams, "ray_shards": args.ray_shards or "equal",
                        "shard_loss": bool(args.shard_loss) and args.loss == "fused",
@@ -1128,6 +1168,9 @@ def main():
     ap.add_argument("--view-size", type=int, default=512, help="side of the synthetic hand views of the full-image extra")
     ap.add_argument("--strong-rays", type=int, default=512, help="N > 1: strong-scaling extra on this many rays in total (0 disables)")
     ap.add_argument("--no-nccl-graph", action="store_true", help="N > 1: keep the all-reduce outside the CUDA graphs")
+    ap.add_argument("--exchange", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: how the flat gradient is summed over the ranks -- peer: inside the Adam kernel over NVLink peer "
+                         "memory (hn_peer_adam_flat; falls back to nccl if the set-up or its check fails); nccl: ncclAllReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

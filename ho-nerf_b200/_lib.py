@@ -95,6 +95,12 @@ PROTOTYPES = {
     "hn_sdf_hand_chain_bytes": (c_int64, [_mlp_p]),
     "hn_sdf_hand_chain_pack": (c_int, [_mlp_p, P, c_int64, P]),
     "hn_adam_flat": (c_int, [P, P, P, P, c_int64, P, P, P] + [ctypes.c_double] * 6 + [P]),
+    "hn_peer_block_bytes": (c_int64, [c_int64, c_int]),
+    "hn_peer_alloc": (c_int, [c_int64, P, P]),
+    "hn_peer_open": (c_int, [P, P]),
+    "hn_peer_close": (c_int, [P]),
+    "hn_peer_free": (c_int, [P]),
+    "hn_peer_adam_flat": (c_int, [P, P, P, c_int64, P, c_int, c_int, P, P, c_int] + [P, P] + [ctypes.c_double] * 6 + [P]),
     "hn_wn_pack_gap": (c_int, [P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, c_int, P]),
     "hn_wn_bwd_gap": (c_int, [P, P, P, c_int, c_int, c_int, c_float, c_int, c_int, P, P, P]),
     "hn_sdf_hand_stash_floats": (c_int64, [c_int64]),

@@ -21,6 +21,13 @@ import torch
 from ._lib import check, lib
 
 
+class _DeviceArray:
+    """n fp32 elements at a raw device address, as the __cuda_array_interface__ torch.as_tensor maps without a copy"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 2}
+
+
 class FlatAdam:
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.params = [p for p in params]
@@ -62,6 +69,7 @@ class FlatAdam:
         self.skipped = torch.zeros(n // 32, device=dev, dtype=torch.float32)
         self._block_slices = [slice(off // 32, (off + (p.numel() + 31) // 32 * 32) // 32) for p, off in zip(self.params, self.offsets)]
         self._any_skipped = False
+        self._peer = None                   # set by enable_peer_exchange()
 
     # -- torch.optim surface ---------------------------------------------------------------------------------------
     @property
@@ -149,14 +157,111 @@ class FlatAdam:
             torch._foreach_copy_([self._grad_views[i] for i in have], [self.params[i].grad for i in have])
         return self._runs()
 
-    def step(self, runs=None, grad_scale=1.0):
+    # -- multi-GPU: gradient exchange fused with the update (csrc/peer.cu) -----------------------------------------------
+    def enable_peer_exchange(self):
+        """COLLECTIVE (every rank of the default process group calls it, after construction and before the first step):
+        moves ``flat_grad`` into a peer-mapped block (hn_peer_alloc), exchanges the IPC handles and opens the other ranks'
+        blocks.  Afterwards ``step(..., peer_exchange=True)`` sums the ranks' gradients over NVLink peer memory and applies
+        Adam in ONE launch (hn_peer_adam_flat) instead of ncclAllReduce(flat_grad) + hn_adam_flat.  Returns True when every
+        rank succeeded; on False nothing changed and the caller keeps the NCCL path (dist.allreduce_flat + step)."""
+        import torch.distributed as dist
+        if self._peer is not None:
+            return True
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return False
+        world, rank, dev = dist.get_world_size(), dist.get_rank(), self.flat.device
+        nbytes = lib.hn_peer_block_bytes(self.n, world)
+        ptr, handle = ctypes.c_void_p(), (ctypes.c_uint8 * 64)()
+        ok = nbytes > 0 and lib.hn_peer_alloc(nbytes, ctypes.byref(ptr), handle) == 0
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle) if ok else None)
+        ok = ok and all(h is not None for h in handles)
+        blocks = [None] * world
+        if ok:
+            blocks[rank] = ptr.value
+            for r in range(world):
+                if r == rank:
+                    continue
+                q = ctypes.c_void_p()
+                hb = (ctypes.c_uint8 * 64).from_buffer_copy(handles[r])
+                if lib.hn_peer_open(hb, ctypes.byref(q)) != 0:
+                    ok = False
+                    break
+                blocks[r] = q.value
+        grad = None
+        if ok:
+            try:                                    # the block's first n floats as a tensor: p.grad is gathered straight into it
+                grad = torch.as_tensor(_DeviceArray(ptr.value, self.n), device=dev)
+                ok = grad.data_ptr() == ptr.value and grad.numel() == self.n and grad.dtype == torch.float32
+            except Exception:                       # noqa: BLE001
+                ok = False
+        flag = torch.tensor([1 if ok else 0], device=dev if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag) != 1:
+            for r, b in enumerate(blocks):
+                if b is not None and r != rank:
+                    lib.hn_peer_close(ctypes.c_void_p(b))
+            if ptr.value:
+                lib.hn_peer_free(ptr)
+            return False
+        grad.copy_(self.flat_grad)
+        self.flat_grad = grad
+        self._grad_views = [grad[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets)]
+        self._peer = {"blocks": (ctypes.c_void_p * world)(*blocks), "rank": rank, "world": world, "own": ptr,
+                      "epoch": torch.zeros(148, device=dev, dtype=torch.int32),
+                      "err": torch.zeros(1, device=dev, dtype=torch.int32)}
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        return True
+
+    def peer_error(self):
+        """0, or 1 + the rank a barrier of hn_peer_adam_flat gave up waiting for (device -> host read: not inside a capture)"""
+        return 0 if self._peer is None else int(self._peer["err"].item())
+
+    def _peer_launch(self, mode, out, grad_scale):
+        g, pe = self.param_groups[0], self._peer
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.flat.device).cuda_stream)
+        v = lambda t: ctypes.c_void_p(t.data_ptr())
+        check(lib.hn_peer_adam_flat(v(out), v(self.exp_avg), v(self.exp_avg_sq), self.n, pe["blocks"], pe["rank"], pe["world"],
+                                    v(pe["epoch"]), v(pe["err"]), mode, v(self.step_t), v(self.lr_t), float(g["lr"]),
+                                    float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                                    float(grad_scale), stream), "hn_peer_adam_flat")
+
+    def peer_allreduce(self, out=None, grad_scale=1.0):
+        """COLLECTIVE: out [n] = grad_scale * (sum over ranks of flat_grad), by the same exchange the fused step uses (mode 1
+        of hn_peer_adam_flat); flat_grad itself is left untouched.  Used to check the exchange against ncclAllReduce."""
+        if self._peer is None:
+            raise RuntimeError("FlatAdam.peer_allreduce: call enable_peer_exchange() first")
+        out = torch.empty_like(self.flat) if out is None else out
+        self._peer_launch(1, out, grad_scale)
+        return out
+
+    def step(self, runs=None, grad_scale=1.0, peer_exchange=False):
         """One Adam update.  ``runs``: the result of an earlier ``gather_grads`` (e.g. before an all-reduce of
-        ``flat_grad``); gathered here when omitted."""
+        ``flat_grad``); gathered here when omitted.  ``peer_exchange=True`` (after enable_peer_exchange(); COLLECTIVE): the
+        gradients are summed over the ranks inside the update kernel -- the caller does NOT all-reduce flat_grad."""
         if runs is None:
             runs = self.gather_grads()
         dev = self.flat.device
         if not torch.cuda.is_current_stream_capturing():
             self.sync_lr()
+        if peer_exchange:
+            # every rank launches the same kernel over the whole buffer: a parameter without a gradient on this rank may
+            # have one elsewhere, so its slot of flat_grad is sent as zeros
+            covered = set()
+            for a, b in runs:
+                covered.update(range(a, b + 1))
+            missing = [self._grad_views[i] for i in range(len(self.params)) if i not in covered]
+            if missing:
+                torch._foreach_zero_(missing)
+            if self._peer is None:
+                raise RuntimeError("FlatAdam.step(peer_exchange=True): call enable_peer_exchange() first")
+            if self._any_skipped:
+                raise RuntimeError("FlatAdam.step(peer_exchange=True): per-parameter step counts are not supported on this path")
+            self.step_t += 1.0
+            self._peer_launch(0, self.flat, grad_scale)
+            torch.autograd.graph.increment_version(self.params)
+            return
         self.step_t += 1.0
         # parameters outside every run sit this step out: their own step count stays behind (torch: per-parameter `step`)
         covered = set()

@@ -157,6 +157,34 @@ HN_API int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
                         const float* skipped, double lr, double beta1, double beta2, double eps, double weight_decay,
                         double grad_scale, hn_stream_t stream);
 
+/* Multi-GPU training step (one process per GPU, rays sharded): the step's ONE exchange -- the all-reduce of
+ * the flat gradient buffer -- fused with hn_adam_flat into one kernel over NVLink / NVSwitch peer memory (csrc/peer.cu)
+ * instead of ncclAllReduce followed by the Adam launch.  The reference trains on one GPU (exp_runner.py:83-90, :206-230:
+ * loss.backward(); optimizer.step()), so there is no upstream interface to mirror: these are the calls a data-parallel
+ * exp_runner would bind.
+ *   hn_peer_block_bytes  size of one rank's peer block for n parameters: [g : n floats | reduced g | barrier flags]
+ *   hn_peer_alloc        cudaMalloc + zero + cudaIpcGetMemHandle: *ptr = the block (its first n floats are the rank's
+ *                        flat gradient buffer), handle64 = the 64-byte handle the other ranks open
+ *   hn_peer_open/_close  map / unmap another rank's block (cudaIpcOpenMemHandle, peer access enabled lazily)
+ *   hn_peer_free         release an hn_peer_alloc block
+ *   hn_peer_adam_flat    blocks[world] (HOST array of the ranks' block addresses in this process, own block at [rank]):
+ *                        p, m, v [n] <- Adam(sum over ranks of g * grad_scale); two-shot (each rank sums 1/world of the
+ *                        buffer in rank order, every rank reads the sums), so all ranks hold bit-identical parameters.
+ *                        mode 1: p [n] = grad_scale * sum (plain all-reduce into a local buffer, m / v / step unused).
+ *                        `epoch` [148] device words (zero at start, owned by the kernel) carry the barrier generation so
+ *                        the launch replays from a CUDA graph; *err (device word, zero at start) becomes non-zero if a
+ *                        peer did not arrive within 20 s -- the kernel never hangs the GPU, the caller must check it.
+ *                        Every rank must make the same sequence of calls (same n, world, mode).  n % 4 == 0. */
+HN_API int64_t hn_peer_block_bytes(int64_t n, int world);
+HN_API int hn_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle64);
+HN_API int hn_peer_open(const uint8_t* handle64, void** ptr);
+HN_API int hn_peer_close(void* ptr);
+HN_API int hn_peer_free(void* ptr);
+HN_API int hn_peer_adam_flat(float* p, float* m, float* v, int64_t n, const void* const* blocks, int rank, int world,
+                             uint32_t* epoch, uint32_t* err, int mode, const float* step, const float* lr_dev, double lr,
+                             double beta1, double beta2, double eps, double weight_decay, double grad_scale,
+                             hn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Object SDF field: SDFNetwork_OBJ.forward / .sdf / .gradient (utils/fields.py:316-347) as ONE
  * operator (value + feature + analytic normal) with a hand-written second-order backward.
