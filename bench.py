@@ -967,6 +967,21 @@ def run_gpu_arm(args):
                    min(n_rays, 512), "the reference's own classes" if kind == "reference" else "oracle/honerf_oracle.py"),
                "forward_only_rays_per_s": fwd_rps}
     if rank == 0:
+        # every extra that states its algorithmic TFLOP/s also states the fraction of the measured dense bf16 peak (same
+        # denominator as `roofline`: sustained figure, these are long runs), per GPU
+        peaks, peak_src = measured_peaks()
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+
+        def add_frac(d):
+            if isinstance(d, dict):
+                if isinstance(d.get("algorithmic_tflops"), (int, float)):
+                    per_gpu = d["algorithmic_tflops"] / max(int(d.get("n_gpus", world if "sharding" in d else 1)), 1)
+                    d["roofline"] = {"bound": "tensor", "achieved": per_gpu, "peak": peak_tf, "unit": "TFLOP/s per GPU",
+                                     "frac": per_gpu / peak_tf, "peak_source": peak_src}
+                for v in list(d.values()):
+                    add_frac(v)
+        for extra in (grid, fit, fwd_extra):
+            add_frac(extra)
         line = {
             "metric": "rays/sec render fwd+bwd (64+64 samples), object-field train step",
             "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
