@@ -16,6 +16,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    sys.stdout.flush()
+    json_fd = os.dup(1)             # stdout carries the JSON line only (NCCL prints its banner there)
+    os.dup2(2, 1)
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", device_id=dev)
@@ -122,7 +125,7 @@ def main():
     host_loop("eager:60_small_kernels+adam_only_us", lambda: opt.step(runs, grad_scale=1.0 / world), eager_kernels=60)
     res["peer_error"] = opt.peer_error()
     if rank == 0:
-        print(json.dumps({"world": world, "n_floats": n, **res}))
+        os.write(json_fd, (json.dumps({"world": world, "n_floats": n, **res}) + "\n").encode())
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0)
