@@ -24,8 +24,16 @@ A("| step (512 rays x (64+64), fwd + 2nd-order bwd + Adam, CUDA graph) | 3.04 ms
 A("| end to end (host inputs, H2D + D2H inside the timed region) | 166.4k rays/s | **%.1fk rays/s** |" % (b["e2e"]["value"] / 1e3))
 A("| reference arm (oracle port on the box's 16 host cores) | 420 rays/s | %.0f rays/s |" % ref["value"])
 for k, m in multi.items():
-    A("| %d GPUs (weak scaling, NCCL all-reduce captured in the step's graph) | %s | **%.1fk rays/s (%.1f %% of %d x the 1-GPU line), %.3f ms/step** |" % (
-        k, {2: "326.9k (98 %)", 4: "634.0k (98 %)"}.get(k, "-"), m["value"] / 1e3, 100 * m["value"] / (k * b["value"]), k, m["ms_per_step"]))
+    A("| %d GPUs (weak scaling, NCCL all-reduce captured in the step's graph; earlier build, 1-GPU line of that box 2.283 ms) | %s | %.1fk rays/s, %.3f ms/step |" % (
+        k, {2: "326.9k (98 %)", 4: "634.0k (98 %)"}.get(k, "-"), m["value"] / 1e3, m["ms_per_step"]))
+ab_path = P("r02_peer_exchange_ab.json")
+if os.path.isfile(ab_path):
+    ab = json.load(open(ab_path))["ms_per_step"]
+    mean = lambda v: sum(v) / len(v)
+    A("| gradient exchange fused with Adam over NVLink peer memory (`hn_peer_adam_flat`), ms/step peer vs NCCL, same box | - | "
+      "2 GPUs **%.3f** vs %.3f; 4 GPUs **%.3f** vs %.3f; 8 GPUs **%.3f** (%.0fk rays/s; NCCL on an earlier box: %.3f) |" % (
+          mean(ab["2"]["peer"]), mean(ab["2"]["nccl"]), ab["4"]["peer"][0], ab["4"]["nccl"][0], ab["8"]["peer"][0],
+          8 * 512 / ab["8"]["peer"][0], ab["8"]["nccl_earlier_box"][0]))
 fam = {f["kernel"]: f for f in r["families"]}
 dram = sum((f["traffic"] or 0) * f["launches_per_step"] for f in r["families"] if f["kernel"] not in ("chain::sdf_fwd_kernel", "chain::dw_kernel"))
 dram += (fam["chain::sdf_fwd_kernel"]["traffic"] or 0)       # trunk + normal sweep already added up per step
@@ -82,6 +90,24 @@ A("weights 16 %, issuing 36 %), tangent + reverse sweep 2 157 kcycles (53 / 13 /
 A("(`tools/prof_hand_render.py`, 23.4 ms before the last changes): trunk x5 4.4 ms, normal sweep 4.4, the 1386-wide input")
 A("contractions 5.9, hand colour net 6.0 (2.8 of it assembling its 1672-wide input row: vectorised since, 21.5 ms), HALO")
 A("feature / normal kernels 2.5.\n")
+px = P("r02_peer_exchange.json")
+if os.path.isfile(px):
+    pe = json.load(open(px))
+    c, f0 = pe["final_kernel"], pe["first_version_one_remote_load_per_loop_trip"]
+    A("## The step's exchange: gradient sum over the ranks + Adam (2x B200, 824 064 floats, `tools/prof_peer.py`, graphs of 50 launches)\n")
+    A("| variant | us / launch |\n|---|---:|")
+    A("| `ncclAllReduce` + `hn_adam_flat` | %.1f |" % c["nccl_allreduce+hn_adam_flat_us"])
+    A("| `hn_adam_flat` alone | %.1f |" % c["hn_adam_flat_alone_us"])
+    A("| `hn_peer_adam_flat`, first version (one remote load per thread and loop trip), 148 / 64 / 16 / 8 CTAs | %.1f / %.1f / %.1f / %.1f |" % (
+        f0["hn_peer_adam_flat_148_ctas_us"], f0["hn_peer_adam_flat_64_ctas_us"], f0["hn_peer_adam_flat_16_ctas_us"], f0["hn_peer_adam_flat_8_ctas_us"]))
+    A("| `hn_peer_adam_flat`, remote loads batched, 1 024 threads, 148 / 64 / 16 CTAs | **%.1f** / %.1f / %.1f |" % (
+        c["hn_peer_adam_flat_148_ctas_us"], c["hn_peer_adam_flat_64_ctas_us"], c["hn_peer_adam_flat_16_ctas_us"]))
+    A("| one rank 204 us late: NCCL form / peer kernel | %.1f / %.1f |" % (c["late_rank:nccl_allreduce+hn_adam_flat_us"], c["late_rank:hn_peer_adam_flat_us"]))
+    A("| host in the loop (50 us kernel + exchange + blocking D2H per step): NCCL / peer / Adam only | %.1f / %.1f / %.1f |" % (
+        c["host_in_loop:sleep50us+nccl+adam+d2h_us"], c["host_in_loop:sleep50us+peer+d2h_us"], c["host_in_loop:sleep50us+adam_only+d2h_us"]))
+    A("")
+    A("The kernel is latency-bound (time ~ 10 us + 3 us per sequential NVLink round trip: the CTA sweep of the first version), not")
+    A("bandwidth-bound: 2 x 1.65 MB cross NVLink per GPU and launch.  What the exchange costs on the step at 2 GPUs: 19 us of 2 327.\n")
 A("## Step-time history of the round (512 rays, 1x B200)\n")
 A("3.04 ms (r01) -> dW-ready 16-bit operands + `dw16_kernel` 2.83 -> sweeps with a single 16-bit operand in tensor memory 2.37 (rejected")
 A("on parity) -> x3 sweeps with hi / lo pairs in tensor memory 2.46 -> colour net on hi / lo T16 tile pairs + `dw16_kernel` 2.41 (one MMA")
