@@ -214,6 +214,25 @@ class FlatAdam:
         dist.barrier()
         return True
 
+    def close_peer_exchange(self):
+        """COLLECTIVE: back to a private flat_grad (same values), unmap the other ranks' blocks, and -- after a barrier, so
+        that no rank can still be reading it -- free the own one.  A captured graph that contains the peer step must not be
+        replayed afterwards."""
+        import torch.distributed as dist
+        if self._peer is None:
+            return
+        pe, dev = self._peer, self.flat.device
+        torch.cuda.synchronize(dev)
+        grad = self.flat_grad.clone()
+        self.flat_grad = grad
+        self._grad_views = [grad[off:off + p.numel()].view(p.shape) for p, off in zip(self.params, self.offsets)]
+        self._peer = None
+        for r in range(pe["world"]):
+            if r != pe["rank"] and pe["blocks"][r]:
+                lib.hn_peer_close(ctypes.c_void_p(pe["blocks"][r]))
+        dist.barrier()
+        lib.hn_peer_free(pe["own"])
+
     def peer_error(self):
         """0, or 1 + the rank a barrier of hn_peer_adam_flat gave up waiting for (device -> host read: not inside a capture)"""
         return 0 if self._peer is None else int(self._peer["err"].item())

@@ -129,7 +129,17 @@ def _worker(rank, world, port, backend, one_gpu, out):
                                       for i in range(len(shapes))]) for r in range(world))
         got = torch.cat([reduced[off:off + p.numel()] for p, off in zip(pa, oa.offsets)])
         errs = [float((a - b).abs().max() / b.abs().max()) for a, b in zip(pa, pb)]
-        out[rank] = ("ok", oa.peer_error(), errs, oa.flat.detach().cpu(), float((got - want_reduced).abs().max()))
+        flat_after = oa.flat.detach().cpu().clone()          # the parameters after the exchanged steps (compared across ranks)
+        err = oa.peer_error()
+        # leaving the exchange: flat_grad keeps its values in private memory and the NCCL-form step works on it
+        before = oa.flat_grad.clone()
+        oa.close_peer_exchange()
+        closed_ok = oa._peer is None and torch.equal(oa.flat_grad, before) and oa.flat_grad.data_ptr() != before.data_ptr()
+        for i, p in enumerate(pa):
+            p.grad = static[i]
+        oa.step(grad_scale=1.0)
+        torch.cuda.synchronize()
+        out[rank] = ("ok" if closed_ok else "close-failed", err, errs, flat_after, float((got - want_reduced).abs().max()))
         dist.barrier()
     finally:
         torch.cuda.synchronize()
