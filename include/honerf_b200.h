@@ -10,7 +10,9 @@
  *     fp32 (indices int64), 16-byte aligned, leading dimensions multiples of 4 floats;
  *   - functions never allocate, never synchronise and enqueue all work on `stream`
  *     (a cudaStream_t); outputs, stashes and workspaces are caller-allocated -- the *_floats()
- *     queries give their sizes;
+ *     queries give their sizes.  The one exception is the multi-GPU set-up (hn_peer_alloc / _open /
+ *     _close / _free): peer-mapped memory cannot be caller-allocated torch memory, these four run
+ *     once, outside the step;
  *   - return value: HN_OK (0) or a negative hn_status; hn_last_error() gives the message of the
  *     calling thread's last failure;
  *   - there is NO CPU fallback: with no CUDA device every compute entry point fails.
