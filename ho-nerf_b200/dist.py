@@ -13,6 +13,10 @@ The recipe that reproduces the single-process gradient exactly (tests/test_dist_
     loss.backward()
     allreduce_gradients(params, average=False)                 # SUM: the shard losses add up to the batch loss
 
+With ``optim.FlatAdam`` the last two lines (all-reduce, then the optimiser step) can be ONE kernel over NVLink peer memory:
+``opt.enable_peer_exchange()`` once, then ``opt.step(peer_exchange=True)`` instead of ``allreduce_flat(opt.flat_grad);
+opt.step()`` (csrc/peer.cu: two-shot rank-ordered sum + Adam, bit-identical parameters on every rank).
+
 The reference's colour loss is normalised by the BATCH's mask_sum (exp_runner.py:207,221) and its BCE / eikonal terms
 are means over the BATCH: a rank-local normaliser followed by an average over ranks is only right for equal shards
 with equal mask counts.  Passing the global divisor and weighting the mean terms by the shard's share of the rays makes
