@@ -14,7 +14,7 @@
 // launch's barrier 1, which every rank reaches after its previous launch completed: no trailing barrier is needed.
 // A barrier is a flag per (CTA, source rank) holding a monotonically increasing epoch: st.release.sys into every peer's
 // flag array, ld.acquire.sys spins on the own one.  The epoch lives in device memory (per CTA), so a captured CUDA graph
-// replays correctly.  A spin that outlasts PEER_TIMEOUT_NS (20 s) sets *err and lets the CTA run on (garbage, but no hung GPU):
+// replays correctly.  A spin that outlasts PEER_TIMEOUT_NS (60 s) sets *err and lets the CTA run on (garbage, but no hung GPU):
 // the host checks the word (hn_peer_adam_flat's caller: optim.FlatAdam.peer_error()).
 #include <algorithm>
 #include <stdlib.h>
@@ -27,7 +27,7 @@ namespace hn {
 constexpr int PEER_MAX_WORLD = 16;
 constexpr int PEER_MAX_CTAS = 148;
 constexpr int PEER_THREADS = 1024;
-constexpr unsigned long long PEER_TIMEOUT_NS = 20000000000ull;
+constexpr unsigned long long PEER_TIMEOUT_NS = 60000000000ull;
 
 struct PeerPtrs {
     const float* g[PEER_MAX_WORLD];

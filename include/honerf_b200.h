@@ -175,7 +175,7 @@ HN_API int hn_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
  *                        mode 1: p [n] = grad_scale * sum (plain all-reduce into a local buffer, m / v / step unused).
  *                        `epoch` [148] device words (zero at start, owned by the kernel) carry the barrier generation so
  *                        the launch replays from a CUDA graph; *err (device word, zero at start) becomes non-zero if a
- *                        peer did not arrive within 20 s -- the kernel never hangs the GPU, the caller must check it.
+ *                        peer did not arrive within 60 s -- the kernel never hangs the GPU, the caller must check it.
  *                        Every rank must make the same sequence of calls (same n, world, mode).  n % 4 == 0. */
 HN_API int64_t hn_peer_block_bytes(int64_t n, int world);
 HN_API int hn_peer_alloc(int64_t bytes, void** ptr, uint8_t* handle64);
