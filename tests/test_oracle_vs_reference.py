@@ -125,3 +125,74 @@ def test_hand_fields_fresh_pose():
     n = O.sdf_gradient(lambda q: O.sdf_hand_forward(sp, q, bt, T)[0][:, :1], pts.clone())
     assert rel_err(n, want_n) < 1e-4
     assert max_abs(O.color_hand_forward(cp, feat, out[:, 1:], n), want_rgb) < 1e-4
+
+
+def _hand_nets(ref, seed, use_batch=False):
+    sp, cp = synth.hand_states(seed=seed)
+    emb = ref.fields.Embedding()
+    hsdf = ref.fields.SDFNetwork(emb, 4, "real", use_batch=use_batch, **ref_loader.HAND_SDF_CONF)
+    hcol = ref.fields.RenderingNetwork(emb, "real", **ref_loader.HAND_COLOR_CONF)
+    hdev = ref.fields.SingleVarianceNetwork(ref_loader.VARIANCE_INIT)
+    hsdf.load_state_dict(sp)
+    hcol.load_state_dict(cp)
+    return sp, cp, hsdf, hcol, hdev
+
+
+def test_hand_render_and_pose_gradients_fresh_seed():
+    """NeuSRenderer.render, hand branch (utils/renderer.py:190-258), 6 rays, gradients to the bone transforms and the
+    T-pose joints (what pose fitting differentiates)"""
+    import cases
+    ref = ref_loader.load_reference()
+    sp, cp, hsdf, hcol, hdev = _hand_nets(ref, 43)
+    bt, T, J = synth.hand_pose(seed=11)
+    B = 6
+    HR = synth.hand_rays(B, J, seed=12)
+    true_rgb = torch.rand(B, 3, generator=torch.Generator().manual_seed(13))
+    hr = ref.renderer.NeuSRenderer(hsdf, hdev, hcol, "hand", **ref_loader.RENDERER_CONF)
+    btg, Tg = bt.clone().requires_grad_(True), T.clone().requires_grad_(True)
+    with _fixed_rand(HR["t_rand"]):
+        want = hr.render(HR["rays_o"], HR["rays_d"], HR["near"], HR["far"], btg, Tg, None, None, None, 0)
+    want_loss = cases.hand_render_loss(want, true_rgb)
+    want_g = torch.autograd.grad(want_loss, [btg, Tg])
+    bt2, T2 = bt.clone().requires_grad_(True), T.clone().requires_grad_(True)
+    var = torch.tensor(ref_loader.VARIANCE_INIT)
+    out = O.render_hand(sp, cp, var, HR["rays_o"], HR["rays_d"], HR["near"], HR["far"], bt2, T2, HR["t_rand"])
+    for k in ("color_fine", "cdf_fine", "weight_sum", "weight_max"):
+        assert max_abs(out[k], want[k]) < 2e-4, k
+    loss = cases.hand_render_loss(out, true_rgb)
+    assert rel_err(loss, want_loss) < 1e-4
+    got = torch.autograd.grad(loss, [bt2, T2])
+    for a, b, name in zip(got, want_g, ("bt_inv", "T_pose_21")):
+        assert rel_err(a, b) < 2e-2, name                     # the golden test's bound (steep field, fp32 on both sides)
+
+
+def test_fitting_render_fresh_seed():
+    """NeuSRenderer_fitting.render (utils/renderer.py:434-535): two fields, shared samples, gradients to bt_inv, Ro, To"""
+    import cases
+    ref = ref_loader.load_reference()
+    hs, hc, hsdf, hcol, hdev = _hand_nets(ref, 44)
+    os_, oc, sdf, col, dev = _obj_nets(ref, 34)
+    bt, T, J = synth.hand_pose(seed=14)
+    B = 6
+    HR = synth.hand_rays(B, J, seed=15)
+    gq = torch.Generator().manual_seed(16)
+    Ro0 = synth.random_rotation(gq)
+    To0 = J.mean(0) + 0.02 * torch.randn(3, generator=gq)
+    true_rgb = torch.rand(B, 3, generator=gq)
+    fr = ref.renderer.NeuSRenderer_fitting(hsdf, hdev, hcol, sdf, dev, col, **ref_loader.RENDERER_CONF)
+    btg, Ro, To = bt.clone().requires_grad_(True), Ro0.clone().requires_grad_(True), To0.clone().requires_grad_(True)
+    with _fixed_rand(HR["t_rand"]):
+        want = fr.render(HR["rays_o"], HR["rays_d"], HR["near"], HR["far"], btg, T, None, Ro, To)
+    want_loss = cases.fit_loss(want, true_rgb)
+    want_g = torch.autograd.grad(want_loss, [btg, Ro, To])
+    var = torch.tensor(ref_loader.VARIANCE_INIT)
+    bt2, Ro2, To2 = bt.clone().requires_grad_(True), Ro0.clone().requires_grad_(True), To0.clone().requires_grad_(True)
+    out = O.fit_render((hs, hc, var), (os_, oc, var), HR["rays_o"], HR["rays_d"], HR["near"], HR["far"], bt2, T, Ro2, To2,
+                       HR["t_rand"])
+    # an importance sample may cross a cdf knot on a 1-ulp difference of the ray transform: north-star tolerance
+    for k in ("color_fine", "weight_sum", "sdf_hand", "sdf_obj"):
+        assert max_abs(out[k], want[k]) < 1e-3, k
+    loss = cases.fit_loss(out, true_rgb)
+    got = torch.autograd.grad(loss, [bt2, Ro2, To2])
+    for a, b, name in zip(got, want_g, ("bt_inv", "Ro", "To")):
+        assert rel_err(a, b) < 2e-2, name
